@@ -263,8 +263,9 @@ def gr_to_regions(sites: Sites):
         raise ValueError("sites must have REF and ALT columns")
     if any(s != e for s, e in zip(sites.start, sites.end)):
         raise ValueError("each site must be a single position (start = end)")
-    if any(s not in "+-" for s in sites.strand):
-        raise ValueError("strand only + or - strand is supported")
+    if any(s == "*" for s in sites.strand):
+        warnings.warn("missing strand not found in input, coercing strand to '+'")
+        sites = Sites(sites.seqnames, sites.start, sites.end, ["+"] * n, sites.ref, sites.alt)
     if any(len(r) != 1 for r in sites.ref) or any(len(a) != 1 for a in sites.alt):
         raise ValueError("REF and ALT must be single bases")
     strand = [1 if s == "+" else 2 for s in sites.strand]
