@@ -1,0 +1,253 @@
+/*
+ * raer_b200.h -- C ABI of the B200-native pileup engines (libraer_b200.so).
+ *
+ * Two layers, both plain C (pointers and sizes only, no torch / R types):
+ *
+ *  1. The ".Call" layer: raer_pileup() / raer_scpileup() take exactly the arguments the reference
+ *     passes through .Call(".pileup", 13 args) and .Call(".scpileup", 14 args)
+ *     (reference: src/init.c:12-18, src/plp.c:1143-1145, src/sc-plp.c:945-948) and return what
+ *     those calls return (column vectors per BAM file + rpbz/vdb/sor; three text files).
+ *     raer_get_region() / raer_fisher_exact() cover the two remaining registered routines
+ *     (src/plp_utils.c:14-46, src/utils.c:14-44) so that one shared object can replace raer.so.
+ *     The R shim that binds these to SEXPs is raer_b200/csrc/r_shim.c.
+ *
+ *  2. The batch layer: host code (BGZF inflate + record parsing, src/plp.c:32-78 semantics)
+ *     packs alignment records into a read batch (raer_read_batch) which raer_batch_*() hands to
+ *     the CUDA kernels. This is the boundary between the C host side and the device code; bench.py
+ *     drives it directly for the device-resident and host-buffer (e2e) measurements.
+ *
+ * There is no CPU fallback: every compute entry point returns RAER_ERR_NO_DEVICE when no CUDA
+ * device is usable.
+ */
+#ifndef RAER_B200_H
+#define RAER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAER_OK 0
+#define RAER_ERR -1            /* generic failure ("[raer internal] error detected during pileup") */
+#define RAER_ERR_ARG -2        /* argument validation failed (Rf_error before any allocation) */
+#define RAER_ERR_IO -3         /* cannot open / parse BAM, BAI or FASTA */
+#define RAER_ERR_NO_DEVICE -4  /* no usable CUDA device: the product has no CPU path */
+#define RAER_ERR_CUDA -5       /* CUDA runtime error, see raer_last_error() */
+#define RAER_ERR_MD -6         /* MD tag inconsistent with CIGAR while max_mismatch_type is active */
+#define RAER_ERR_LIMIT -7      /* input exceeds a documented limit (files per call, read length) */
+
+#define RAER_MAX_FILES 32      /* BAM files per raer_pileup call (shared-memory counter budget) */
+
+const char* raer_last_error(void);
+const char* raer_version(void);
+int raer_device_count(void);
+
+/* ------------------------------------------------------------------ layer 1: .Call equivalents */
+
+/* .Call(".pileup", bampaths, indexes, n, fapath, region, lst, int_args, dbl_args, lgl_args,
+ *       libtype, only_keep_variants, min_mapQ, umi)       -- reference src/plp.c:1143-1198 */
+typedef struct raer_pileup_args {
+    int32_t nbam;
+    const char* const* bampaths;
+    const char* const* indexes;      /* nbam entries; an entry may be NULL => "<bam>.bai" */
+    const char* fapath;
+    const char* region;              /* NULL == character(0) */
+    int32_t n_regions;               /* 0 == lst NULL (or empty) */
+    const char* const* reg_seqnames; /* lst[[1]] */
+    const int32_t* reg_start;        /* lst[[2]], 1-based */
+    const int32_t* reg_end;          /* lst[[3]], 1-based inclusive */
+    int32_t int_args[14];            /* max_depth, min_depth, min_base_quality, trim_5p, trim_3p, indel_dist,
+                                        splice_dist, min_splice_overhang, homopolymer_len, min_variant_reads,
+                                        max_mismatch_type[2], bam_flags[2]  (R/pileup.R:434-477) */
+    double dbl_args[5];              /* ftrim_5p, ftrim_3p, min_allelic_freq, read_bqual[2] */
+    int32_t lgl_args[2];             /* report_multiallelic, remove_overlaps */
+    const int32_t* libtype;          /* nbam: 0 unstranded, 1 fr-first-strand, 2 fr-second-strand */
+    const int32_t* only_keep_variants; /* nbam */
+    const int32_t* min_mapq;         /* nbam */
+    const char* umi_tag;             /* NULL == character(0) */
+    /* extensions (zero-initialise for reference behaviour) */
+    int32_t overlap_mode;            /* 0/1: htslib >= 1.13 mate-overlap rule (default); 2: htslib <= 1.12 */
+    int32_t device;                  /* CUDA device ordinal */
+    int32_t host_threads;            /* BGZF inflate threads; 0 = hardware concurrency */
+    int32_t shard_index;             /* multi-GPU: this process handles contig-tiles i where       */
+    int32_t shard_count;             /*   i % shard_count == shard_index; 0/1 = everything         */
+} raer_pileup_args;
+
+/* Column layout of the .Call(".pileup") result (src/plp_data.c:285-289, 321-361). Every file has
+ * the same rows (src/plp.c:445-459); row order = contig order of the first BAM header, ascending
+ * position, '+' before '-'. */
+typedef struct raer_pileup_result {
+    int64_t nrows;
+    int32_t nbam;
+    int32_t n_targets;
+    char** target_names;
+    int32_t* tid;
+    int32_t* pos;     /* 1-based */
+    char* strand;     /* '+' | '-' */
+    char* ref;        /* REF on that strand */
+    double* rpbz;
+    double* vdb;
+    double* sor;
+    char* alt;        /* [nbam][nrows][12], NUL terminated: "-" or comma-joined bases */
+    int32_t* counts;  /* [nbam][nrows][8]: nRef nAlt nA nT nC nG nN nX */
+    /* timing breakdown of this call, seconds (BASELINE.json: "host decode and H2D broken out") */
+    double t_decode, t_pack, t_h2d, t_kernel, t_d2h, t_total;
+    int64_t n_records, n_aligned_bases, gpu_launches;
+} raer_pileup_result;
+
+int raer_pileup(const raer_pileup_args* args, raer_pileup_result* out);
+void raer_pileup_result_free(raer_pileup_result* r);
+
+/* .Call(".scpileup", bampaths, indexes, query_region, lst, barcodes, cbtag, int_args, dbl_args,
+ *       libtype, outfns, umi, remove_overlaps, min_mapq, min_counts) -- src/sc-plp.c:945-1031 */
+typedef struct raer_scpileup_args {
+    int32_t nbam;                    /* > 1 => Smart-seq2 mode: barcode i names BAM i (src/sc-plp.c:760) */
+    const char* const* bampaths;
+    const char* const* indexes;
+    const char* region;
+    int32_t n_sites;
+    const char* const* site_seqnames;
+    const int32_t* site_pos;         /* 1-based */
+    const int32_t* site_strand;      /* 1 '+', 2 '-' */
+    const char* const* site_ref;
+    const char* const* site_alt;
+    const int32_t* site_idx;         /* 1-based row index written to the matrix file */
+    int32_t n_barcodes;
+    const char* const* barcodes;
+    const char* cb_tag;              /* NULL == character(0) */
+    int32_t int_args[14];
+    double dbl_args[5];
+    int32_t libtype;
+    const char* outfns[3];           /* matrix, sites, barcodes */
+    const char* umi_tag;             /* NULL == character(0) */
+    int32_t remove_overlaps;
+    int32_t min_mapq;
+    int32_t min_counts;
+    int32_t overlap_mode;
+    int32_t device;
+    int32_t host_threads;
+} raer_scpileup_args;
+
+/* returns the status the reference returns through ScalarInteger (>= 0 ok, < 0 failure) */
+int raer_scpileup(const raer_scpileup_args* args);
+
+/* .Call(".get_region", region): hts_parse_reg semantics; *beg 0-based, *end exclusive */
+int raer_get_region(const char* region, char* chrom, int32_t chrom_cap, int32_t* beg, int32_t* end);
+/* .Call(".fisher_exact", mat): mat is 4 x ncol column-major (a_ref, a_alt, b_ref, b_alt) */
+int raer_fisher_exact(const int32_t* mat, int32_t ncol, double* pvalue);
+
+/* ------------------------------------------------------------------ layer 2: read batches */
+
+/* One alignment record, 32 bytes, one 32-byte sector per warp-wide broadcast load. */
+typedef struct raer_read_hdr {
+    int32_t pos;        /* 0-based leftmost reference position */
+    int32_t end;        /* pos + reference length of the CIGAR (exclusive) */
+    uint16_t flag;      /* BAM flag */
+    uint8_t mapq;
+    uint8_t bits;       /* RAER_RB_* */
+    uint16_t l_qseq;
+    uint16_t n_cigar;
+    uint32_t cigar_off; /* first CIGAR word in raer_read_batch.cigar */
+    uint32_t sq_off;    /* byte offset of the packed sequence; qualities start at 2*sq_off */
+    int32_t mate;       /* batch index of the earlier mate this read resolves its overlap with, or -1 */
+    uint32_t aux;       /* bulk: unused (0); single cell: index into cb/umi arrays == read index */
+} raer_read_hdr;
+
+#define RAER_RB_INVERT 0x01  /* library type + flag put this read on the minus strand (plp_utils.c:331-371) */
+#define RAER_RB_MMFAIL 0x02  /* parse_mismatches() > 0 for the configured max_mismatch_type */
+#define RAER_RB_MMERR 0x04   /* MD tag inconsistent: hard error if the mismatch filter consults this read */
+#define RAER_RB_KEEP_A 0x08  /* mate overlap: the earlier mate keeps its qualities (qname hash, htslib >= 1.13) */
+#define RAER_RB_OHANG_N 0x10 /* the word after the CIGAR reads as a ref-skip (plp_utils.c:245-251 over-read) */
+
+/* Struct-of-arrays read batch: all reads of all files that overlap the genomic window
+ * [beg, end) of contig tid, file-major, coordinate sorted inside a file. Host or device pointers. */
+typedef struct raer_read_batch {
+    int32_t n_files;
+    int32_t tid;
+    int32_t beg, end;          /* positions this batch finalises */
+    int64_t n_reads;
+    const int64_t* file_off;   /* n_files + 1 (host memory, always) */
+    const raer_read_hdr* hdr;  /* n_reads */
+    const int32_t* maxend;     /* n_reads: running maximum of hdr.end inside each file range */
+    const uint32_t* cigar;     /* n_cigar_words */
+    const uint8_t* seq;        /* n_sq_bytes: 4-bit packed, every read starts on a byte */
+    const uint8_t* qual;       /* 2 * n_sq_bytes */
+    int64_t n_cigar_words;
+    int64_t n_sq_bytes;
+    const int32_t* pair_b;     /* n_pairs: indices of reads whose hdr.mate >= 0 */
+    int64_t n_pairs;
+    const int32_t* cb;         /* single cell: whitelist column (1-based) per read, 0 = none; else NULL */
+    const uint32_t* umi;       /* single cell: UMI dictionary id per read, 0 = no tag; else NULL */
+    int64_t n_aligned_bases;   /* M/=/X bases of the batch (metric unit), informational */
+} raer_read_batch;
+
+/* Per-call configuration of the bulk kernels (the unpacked FilterParam, src/plp.c:1094-1138). */
+typedef struct raer_bulk_conf {
+    int32_t n_files;
+    int32_t min_depth, min_bq;
+    int32_t trim_5p, trim_3p, indel_dist, splice_dist, min_overhang, nmer, min_var_reads;
+    int32_t n_mm_type, n_mm;
+    int32_t report_multiallelic;
+    int32_t remove_overlaps;   /* 0 none, 1 htslib >= 1.13, 2 htslib <= 1.12 */
+    int32_t want_stats;        /* 1: rpbz/vdb/sor + ALT order (reference behaviour); 0 skips the second pass */
+    int32_t pad0;
+    double ftrim_5p, ftrim_3p, min_af;
+    int32_t min_mapq[RAER_MAX_FILES];
+    int32_t only_keep_variants[RAER_MAX_FILES];
+    /* positions eligible for output: [reg_beg, reg_end) and, if site_mask != NULL, bit (p - mask_beg) set */
+    int32_t reg_beg, reg_end;
+    const uint32_t* site_mask; /* same memory space as the batch */
+    int32_t mask_beg, mask_bits;
+} raer_bulk_conf;
+
+/* Rows produced by one batch, in host memory, ordered by (pos, strand). altcode encodes the ALT
+ * string (see raer_altcode_to_string). */
+typedef struct raer_rows {
+    int64_t n_rows;
+    int32_t n_files;
+    int32_t* pos;        /* 0-based */
+    uint32_t* meta;      /* bit0: 1 = '-' strand; bits 8-15: REF character */
+    double* stats;       /* [n_rows][3]: rpbz, vdb, sor */
+    int32_t* counts;     /* [n_rows][n_files][8] */
+    uint32_t* altcode;   /* [n_rows][n_files] */
+} raer_rows;
+void raer_rows_free(raer_rows* r);
+
+typedef struct raer_ctx raer_ctx; /* one per device: stream, scratch buffers, reference cache */
+raer_ctx* raer_ctx_create(int32_t device);
+void raer_ctx_destroy(raer_ctx* ctx);
+/* stream used by the context (cudaStream_t) so that callers can time with events on it */
+void* raer_ctx_stream(raer_ctx* ctx);
+/* install the reference bases of one contig (raw FASTA bytes, case preserved) for later batches */
+int raer_ctx_set_reference(raer_ctx* ctx, int32_t tid, const char* seq, int64_t len);
+/* same, from a device pointer that stays valid (bench: synthetic reference generated in HBM) */
+int raer_ctx_set_reference_device(raer_ctx* ctx, int32_t tid, const void* dseq, int64_t len);
+
+/* e2e path: host batch -> H2D -> kernels -> D2H rows. */
+int raer_batch_pileup_host(raer_ctx* ctx, const raer_bulk_conf* conf, const raer_read_batch* host_batch,
+                           raer_rows* out);
+/* device-resident path (bench "value"): every pointer of dev_batch (except file_off) is device memory.
+ * Runs the kernels on the context stream; rows stay on the device. *n_rows is read back at the end
+ * unless NULL. Counts launched kernels into *launches when not NULL. */
+int raer_batch_pileup_device(raer_ctx* ctx, const raer_bulk_conf* conf, const raer_read_batch* dev_batch,
+                             int64_t* n_rows, int64_t* launches);
+/* algorithmic bytes of a batch + its output rows (SURVEY.md section 8d constants) */
+int64_t raer_batch_algorithmic_bytes(const raer_read_batch* b, int64_t n_rows, int64_t ref_bases);
+
+/* decode an ALT code to "-" / "A,G" ... given and updating the khash size state of that
+ * (file, strand) variant table (4 or 8 buckets, src/plp.c:193-215). out needs 12 bytes. */
+void raer_altcode_to_string(uint32_t altcode, int ref_char, int32_t* khash_buckets, char* out);
+
+/* Host-only probe of the ingest used by raer_pileup() (no device needed): streams the BAMs, applies
+ * the read-level prefilter, packs batches of about target_reads reads and reports
+ * out[0..7] = reads handed to the device (halo reads once per batch), mate pairs, CIGAR words,
+ * packed sequence bytes, batches, aligned bases of all mapped records, records read, distinct reads. */
+int raer_ingest_summary(const raer_pileup_args* args, int64_t target_reads, int64_t* out);
+/* seconds spent in H2D copies, kernels and D2H copies by the last raer_batch_pileup_host() call */
+void raer_ctx_last_timing(raer_ctx* ctx, double* h2d_s, double* kernel_s, double* d2h_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAER_B200_H */

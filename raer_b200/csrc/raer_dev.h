@@ -1,0 +1,63 @@
+// raer_dev.h -- internal structs shared by the host runtime and the CUDA kernels.
+#ifndef RAER_DEV_H
+#define RAER_DEV_H
+
+#include <stdint.h>
+
+#include "raer_b200.h"
+
+#define RAER_NCLS 6           // shared-memory counter classes per (file, strand): A C G T other X
+#define RAER_CLS_OTHER 4
+#define RAER_CLS_X 5
+#define RAER_BLOCK 512        // threads per CTA of the tile kernel
+#define RAER_NHIST 100        // read-position bins (src/plp.c:17 NBASE_POS)
+
+// ALT code layout (uint32 per row per file), decoded by raer_altcode_to_string()
+#define RAER_ALT_MASK 0x0fu        // bit c: variant base c in {A,C,G,T} survives min_allelic_freq pruning
+#define RAER_ALT_OTHER 0x10u       // a non-ACGT read base was counted as variant
+#define RAER_ALT_ORDER_SHIFT 8     // 4 x 2 bits: variant bases in first-seen (BAM) order
+#define RAER_ALT_NINS_SHIFT 16     // 3 bits: number of distinct variant bases inserted
+#define RAER_ALT_GROW 0x80000u     // the puts at this site grew the khash from 4 to 8 buckets
+
+struct PlpParams {
+    // read batch (device pointers)
+    const raer_read_hdr* hdr;
+    const int32_t* maxend;
+    const uint32_t* cigar;
+    const uint8_t* seq;
+    uint8_t* qual;
+    long long file_off[RAER_MAX_FILES + 1];
+    int n_files;
+    // tiling
+    int t_beg, t_end, W, n_tiles;
+    int2* tile_ranges;               // [n_tiles][n_files] {lo, hi}
+    unsigned int* tile_counter;      // dynamic tile scheduler
+    // reference of the contig
+    const char* ref;
+    int ref_len;
+    // configuration
+    int min_depth, min_bq, trim_5p, trim_3p, indel_dist, splice_dist, min_overhang, nmer, min_var_reads;
+    int n_mm_type, n_mm, report_multiallelic, want_stats, any_okv;
+    double ftrim_5p, ftrim_3p, min_af;
+    int min_mapq[RAER_MAX_FILES];
+    int okv[RAER_MAX_FILES];
+    int reg_beg, reg_end;
+    const uint32_t* site_mask;
+    int mask_beg, mask_bits;
+    // outputs
+    int* row_pos;
+    unsigned int* row_meta;
+    double* row_stats;
+    int* row_counts;
+    unsigned int* row_alt;
+    long long row_cap;
+    unsigned long long* row_counter;
+    int2* tile_rows;                 // per tile {first row, n rows}
+    int* err_flag;
+    // shared memory plan
+    int S;                           // second-pass site slots per round
+    int cnt_words;                   // words of the counter region (>= S * slot_words)
+    int slot_words;
+};
+
+#endif

@@ -1,0 +1,190 @@
+// raer_host.h -- host-side ingest: BGZF/BAM streaming, read-level prefilter, batch packing.
+//
+// Replaces what the reference gets from htslib + readaln()/screadaln() (src/plp.c:32-78,
+// src/sc-plp.c:449-511) and the buffer-state dependent parts of bam_plp_push / overlap_push
+// (mate pairing, max_depth) that must be decided in stream order. Everything positional is left
+// to the device.
+#ifndef RAER_HOST_H
+#define RAER_HOST_H
+
+#include <stdint.h>
+#include <stdio.h>
+
+#include <queue>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "raer_b200.h"
+
+namespace raer {
+
+void set_error(const char* fmt, ...);
+
+struct BamRecView {  // points into the stream's inflate buffer; valid until the next call
+    int32_t tid, pos, mtid, mpos, isize;
+    uint16_t flag;
+    uint8_t mapq;
+    int l_qname, n_cigar, l_qseq, l_aux;
+    const char* qname;
+    const uint8_t* cigar_bytes;  // unaligned little-endian words
+    const uint8_t* seq;
+    const uint8_t* qual;
+    const uint8_t* aux;
+};
+
+class BamStream {
+public:
+    ~BamStream();
+    bool open(const char* path, int threads);
+    // restrict to [beg, end) of tid using the BAI linear index; returns false on a missing/bad index
+    bool set_region(const char* bai_path, int tid, int beg, int end);
+    // 0 ok, -1 EOF (or past the region), -2 error
+    int next(BamRecView& r);
+    int n_targets() const { return (int)names_.size(); }
+    const std::vector<std::string>& names() const { return names_; }
+    const std::vector<int32_t>& lengths() const { return lens_; }
+    int name2tid(const std::string& n) const;
+    double decode_seconds() const { return t_decode_; }
+    int64_t records_read() const { return n_records_; }
+
+private:
+    bool fill();  // inflate the next group of BGZF blocks into ubuf_
+    bool read_header();
+    bool need(size_t n);
+    FILE* fp_ = nullptr;
+    int threads_ = 1;
+    std::vector<uint8_t> cbuf_;  // compressed bytes not yet inflated
+    size_t c_off_ = 0;
+    bool file_eof_ = false;
+    std::vector<uint8_t> ubuf_;  // inflated bytes
+    size_t u_off_ = 0;
+    std::vector<std::string> names_;
+    std::vector<int32_t> lens_;
+    bool has_region_ = false, region_done_ = false;
+    int r_tid_ = -1, r_beg_ = 0, r_end_ = 0;
+    double t_decode_ = 0;
+    int64_t n_records_ = 0;
+};
+
+// sorted, merged-on-query interval index (htslib regidx semantics: 0-based inclusive)
+struct RegionIndex {
+    struct Chr {
+        std::vector<int32_t> beg, end, maxend, payload;
+    };
+    std::unordered_map<std::string, Chr> chr;
+    void build(int n, const char* const* names, const int32_t* beg0, const int32_t* end0);
+    const Chr* find(const std::string& name) const;
+    static bool overlap(const Chr* c, int from, int to);
+};
+
+struct IngestConf {
+    int n_files = 0;
+    uint32_t keep_flag[2] = {0, 0};
+    int min_global_mq = 0;
+    int rq_minq = 0;
+    double rq_pct = 0;
+    int max_depth = 10000;
+    int remove_overlaps = 1;  // 0 none, 1 htslib >= 1.13, 2 <= 1.12
+    int n_mm_type = 0, n_mm = 0;
+    int min_overhang = 0;
+    std::vector<int> libtype;
+    const RegionIndex* regidx = nullptr;
+    // single cell
+    bool sc = false;
+    const std::unordered_map<std::string, int>* cb_index = nullptr;  // barcode -> 1-based column
+    std::string cb_tag, umi_tag;                                     // empty = not configured
+    int64_t target_reads = 1 << 21;                                  // reads per batch over all files
+};
+
+struct HostRead {
+    raer_read_hdr h;   // cigar_off / sq_off relative to the owning file pool
+    int64_t ordinal;   // arrival index among kept reads of the file
+    int64_t mate_ord;  // ordinal of the earlier mate or -1
+    int32_t cb;
+    uint32_t umi;
+};
+
+struct FilePending {
+    BamStream bs;
+    std::vector<HostRead> reads;
+    size_t front = 0;
+    std::vector<uint32_t> cigar;
+    std::vector<uint8_t> seq, qual;
+    size_t cig_base = 0, sq_base = 0;  // pool offsets already compacted away
+    bool eof = false;
+    bool have_look = false;  // a parsed record waiting in `look`
+    HostRead look;
+    std::vector<uint32_t> look_cigar;
+    std::vector<uint8_t> look_seq, look_qual;
+    int look_tid = -1;
+    // stream-order state (bam_plp_push emulation)
+    int64_t next_ordinal = 0;
+    int prev_tid = 0, prev_pos = 0;
+    struct OlEnt { int64_t ordinal; int tid; int end; bool keep_a; };
+    std::unordered_map<std::string, OlEnt> olap;
+    std::priority_queue<int, std::vector<int>, std::greater<int>> live_ends;
+    int live_tid = -1;
+    int64_t n_aligned_bases = 0;
+};
+
+// Owned, host-resident batch (pinned when a device is present)
+struct PackedBatch {
+    raer_read_batch b{};
+    std::vector<int64_t> file_off;
+    raer_read_hdr* hdr = nullptr;
+    int32_t* maxend = nullptr;
+    uint32_t* cigar = nullptr;
+    uint8_t* seq = nullptr;
+    uint8_t* qual = nullptr;
+    int32_t* pair_b = nullptr;
+    int32_t* cb = nullptr;
+    uint32_t* umi = nullptr;
+    size_t cap_reads = 0, cap_cigar = 0, cap_sq = 0, cap_pairs = 0;
+    bool pinned = false;
+    void reserve(size_t reads, size_t cig, size_t sq, bool sc);
+    void release();
+    ~PackedBatch() { release(); }
+};
+
+class Ingest {
+public:
+    Ingest(const IngestConf& c) : conf_(c) {}
+    bool open(const char* const* paths, const char* const* indexes, int threads, const char* region);
+    // next contig with reads in any file (ascending tid of file 0's header); -1 when done
+    int next_contig();
+    // pack the next batch of the current contig; false when the contig is exhausted
+    bool next_batch(PackedBatch& out);
+    const std::vector<std::string>& names() const { return files_[0]->bs.names(); }
+    const std::vector<int32_t>& lengths() const { return files_[0]->bs.lengths(); }
+    int reg_tid() const { return reg_tid_; }
+    int reg_beg() const { return reg_beg_; }
+    int reg_end() const { return reg_end_; }
+    double decode_seconds() const;
+    double pack_seconds() const { return t_pack_; }
+    int64_t records() const;
+    int64_t aligned_bases() const;
+    std::unordered_map<std::string, uint32_t>& umi_dict() { return umi_dict_; }
+    ~Ingest();
+
+private:
+    // parse records of file f until it holds `want` pending reads of contig cur_tid_ past the window start
+    bool parse_ahead(int f, size_t want);
+    bool parse_one(int f);  // parse + prefilter one record into look / pending
+    IngestConf conf_;
+    std::vector<FilePending*> files_;
+    int cur_tid_ = -1;
+    int win_beg_ = 0;
+    int reg_tid_ = -1, reg_beg_ = 0, reg_end_ = INT32_MAX;
+    bool has_region_ = false;
+    double t_pack_ = 0;
+    std::unordered_map<std::string, uint32_t> umi_dict_;
+};
+
+// FASTA via .fai, whole contig, case preserved (faidx_fetch_seq64 semantics)
+bool fasta_fetch(const char* fa, const std::string& name, std::string& out);
+int parse_region(const char* s, int* beg, int* end);  // hts_parse_reg; returns length of the name part or -1
+double now_seconds();
+
+}  // namespace raer
+#endif

@@ -1,0 +1,868 @@
+// raer_ingest.cpp -- BGZF/BAM streaming (multi-threaded inflate), read prefilter, batch packing.
+// See raer_host.h. Reference semantics: readaln src/plp.c:32-78, screadaln src/sc-plp.c:449-511,
+// invert_read_orientation src/plp_utils.c:331-371, read_base_quality :310-328,
+// parse_mismatches src/ext/htsbox/htsbox-ext.c:17-97; htslib bam_plp_push / overlap_push for the
+// stream-order decisions.
+#include <ctype.h>
+#include <limits.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <chrono>
+#include <thread>
+
+#include "raer_host.h"
+
+extern "C" void* raer_pinned_alloc(size_t n, int* pinned);
+extern "C" void raer_pinned_free(void* p, int pinned);
+
+namespace raer {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+double now_seconds() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static inline uint16_t le16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+static inline uint32_t le32(const uint8_t* p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+static inline uint64_t le64(const uint8_t* p) { return (uint64_t)le32(p) | ((uint64_t)le32(p + 4) << 32); }
+
+// ------------------------------------------------------------------------------------- BamStream
+BamStream::~BamStream() {
+    if (fp_) fclose(fp_);
+}
+
+struct BlockJob {
+    size_t c_off;   // start of deflate payload in cbuf_
+    uint32_t c_len; // payload bytes
+    size_t u_off;   // destination in ubuf_
+    uint32_t u_len;
+};
+
+bool BamStream::fill() {
+    double t0 = now_seconds();
+    const size_t kChunk = 32u << 20, kMaxOut = 96u << 20;
+    // refill the compressed buffer
+    if (!file_eof_ && cbuf_.size() - c_off_ < (1u << 20)) {
+        if (c_off_ > 0) {
+            cbuf_.erase(cbuf_.begin(), cbuf_.begin() + c_off_);
+            c_off_ = 0;
+        }
+        size_t old = cbuf_.size();
+        cbuf_.resize(old + kChunk);
+        size_t got = fread(cbuf_.data() + old, 1, kChunk, fp_);
+        cbuf_.resize(old + got);
+        if (got < kChunk) file_eof_ = true;
+    }
+    std::vector<BlockJob> jobs;
+    size_t leftover = ubuf_.size() - u_off_;
+    size_t out_off = leftover, o = c_off_;
+    while (o + 18 <= cbuf_.size() && out_off < kMaxOut) {
+        const uint8_t* h = cbuf_.data() + o;
+        if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { set_error("corrupt BGZF block"); return false; }
+        int xlen = le16(h + 10);
+        if (o + 12 + xlen > cbuf_.size()) break;
+        int bsize = -1;
+        for (int e = 0; e + 4 <= xlen;) {
+            int slen = le16(h + 12 + e + 2);
+            if (h[12 + e] == 'B' && h[13 + e] == 'C' && slen == 2) bsize = le16(h + 12 + e + 4);
+            e += 4 + slen;
+        }
+        if (bsize < 0) { set_error("BGZF block without BC field"); return false; }
+        if (o + bsize + 1 > cbuf_.size()) break;
+        uint32_t isize = le32(h + bsize + 1 - 4);
+        BlockJob j;
+        j.c_off = o + 12 + xlen;
+        j.c_len = (uint32_t)(bsize + 1 - 12 - xlen - 8);
+        j.u_off = out_off;
+        j.u_len = isize;
+        if (isize) jobs.push_back(j);
+        out_off += isize;
+        o += bsize + 1;
+    }
+    if (o == c_off_) {
+        if (file_eof_ && cbuf_.size() - c_off_ > 0 && cbuf_.size() - c_off_ < 18) return false;
+        if (file_eof_) return false;
+        // a block larger than what is buffered cannot happen (blocks are <= 64 KiB); force another read
+        if (cbuf_.size() - c_off_ >= (1u << 20)) { set_error("BGZF framing error"); return false; }
+    }
+    c_off_ = o;
+    // compact the inflated buffer and make room
+    if (u_off_ > 0) {
+        memmove(ubuf_.data(), ubuf_.data() + u_off_, leftover);
+        u_off_ = 0;
+    }
+    ubuf_.resize(out_off);
+    if (!jobs.empty()) {
+        int nt = std::max(1, std::min<int>(threads_, (int)jobs.size() / 4 + 1));
+        std::vector<int> status(nt, 0);
+        auto work = [&](int t) {
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            if (inflateInit2(&zs, -15) != Z_OK) { status[t] = -1; return; }
+            for (size_t i = t; i < jobs.size(); i += nt) {
+                const BlockJob& j = jobs[i];
+                inflateReset(&zs);
+                zs.next_in = cbuf_.data() + j.c_off;
+                zs.avail_in = j.c_len;
+                zs.next_out = ubuf_.data() + j.u_off;
+                zs.avail_out = j.u_len;
+                int zr = inflate(&zs, Z_FINISH);
+                if (zr != Z_STREAM_END || zs.avail_out != 0) { status[t] = -1; break; }
+            }
+            inflateEnd(&zs);
+        };
+        if (nt == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+            for (auto& x : th) x.join();
+        }
+        for (int s : status)
+            if (s) { set_error("inflate failed"); return false; }
+    }
+    t_decode_ += now_seconds() - t0;
+    return out_off > leftover || !file_eof_;
+}
+
+bool BamStream::need(size_t n) {
+    while (ubuf_.size() - u_off_ < n) {
+        size_t before = ubuf_.size() - u_off_;
+        if (!fill()) return false;
+        if (ubuf_.size() - u_off_ == before && file_eof_ && c_off_ >= cbuf_.size()) return false;
+    }
+    return true;
+}
+
+bool BamStream::read_header() {
+    if (!need(12)) return false;
+    const uint8_t* p = ubuf_.data() + u_off_;
+    if (memcmp(p, "BAM\1", 4)) { set_error("not a BAM file"); return false; }
+    uint32_t l_text = le32(p + 4);
+    if (!need(12 + (size_t)l_text)) return false;
+    p = ubuf_.data() + u_off_;
+    int n_ref = (int)le32(p + 8 + l_text);
+    u_off_ += 12 + l_text;
+    for (int i = 0; i < n_ref; ++i) {
+        if (!need(4)) return false;
+        uint32_t ln = le32(ubuf_.data() + u_off_);
+        if (!need(8 + (size_t)ln)) return false;
+        p = ubuf_.data() + u_off_;
+        names_.emplace_back((const char*)p + 4, strnlen((const char*)p + 4, ln));
+        lens_.push_back((int32_t)le32(p + 4 + ln));
+        u_off_ += 8 + ln;
+    }
+    return true;
+}
+
+bool BamStream::open(const char* path, int threads) {
+    fp_ = fopen(path, "rb");
+    if (!fp_) { set_error("failed to open %s", path); return false; }
+    threads_ = threads > 0 ? threads : 1;
+    return read_header();
+}
+
+int BamStream::name2tid(const std::string& n) const {
+    for (size_t i = 0; i < names_.size(); ++i)
+        if (names_[i] == n) return (int)i;
+    return -1;
+}
+
+bool BamStream::set_region(const char* bai_path, int tid, int beg, int end) {
+    has_region_ = true;
+    r_tid_ = tid; r_beg_ = beg; r_end_ = end;
+    FILE* fp = fopen(bai_path, "rb");
+    if (!fp) { set_error("fail to load bamfile index %s", bai_path); return false; }
+    fseek(fp, 0, SEEK_END);
+    long sz = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    std::vector<uint8_t> d(sz);
+    if (fread(d.data(), 1, sz, fp) != (size_t)sz) { fclose(fp); return false; }
+    fclose(fp);
+    if (sz < 8 || memcmp(d.data(), "BAI\1", 4)) { set_error("bad BAI magic"); return false; }
+    int n_ref = (int)le32(d.data() + 4);
+    long o = 8;
+    uint64_t voff = 0;
+    bool found = false;
+    for (int t = 0; t < n_ref && o + 4 <= sz; ++t) {
+        int n_bin = (int)le32(d.data() + o);
+        o += 4;
+        uint64_t min_chunk = UINT64_MAX;
+        for (int b = 0; b < n_bin; ++b) {
+            uint32_t bin = le32(d.data() + o);
+            int n_chunk = (int)le32(d.data() + o + 4);
+            o += 8;
+            for (int c = 0; c < n_chunk; ++c) {
+                uint64_t cb = le64(d.data() + o);
+                if (bin != 37450 && cb < min_chunk) min_chunk = cb;
+                o += 16;
+            }
+        }
+        int n_intv = (int)le32(d.data() + o);
+        o += 4;
+        if (t == tid) {
+            int w = beg >> 14;
+            uint64_t v = 0;
+            if (n_intv > 0) {
+                if (w >= n_intv) w = n_intv - 1;
+                v = le64(d.data() + o + 8L * w);
+                while (v == 0 && w > 0) { --w; v = le64(d.data() + o + 8L * w); }
+            }
+            if (v == 0 && min_chunk != UINT64_MAX) v = min_chunk;
+            voff = v;
+            found = v != 0;
+            break;
+        }
+        o += 8L * n_intv;
+    }
+    if (!found) { region_done_ = true; return true; }  // no alignments on that contig
+    if (fseek(fp_, (long)(voff >> 16), SEEK_SET) != 0) return false;
+    cbuf_.clear(); c_off_ = 0; file_eof_ = false;
+    ubuf_.clear(); u_off_ = 0;
+    if (!fill()) { region_done_ = true; return true; }
+    u_off_ = (size_t)(voff & 0xffff);
+    return true;
+}
+
+int BamStream::next(BamRecView& r) {
+    while (true) {
+        if (region_done_) return -1;
+        if (!need(4)) return -1;
+        uint32_t bs = le32(ubuf_.data() + u_off_);
+        if (bs < 32) { set_error("corrupt BAM record"); return -2; }
+        if (!need(4 + (size_t)bs)) { set_error("truncated BAM record"); return -2; }
+        const uint8_t* p = ubuf_.data() + u_off_ + 4;
+        u_off_ += 4 + bs;
+        ++n_records_;
+        r.tid = (int32_t)le32(p);
+        r.pos = (int32_t)le32(p + 4);
+        r.l_qname = p[8];
+        r.mapq = p[9];
+        r.n_cigar = le16(p + 12);
+        r.flag = le16(p + 14);
+        r.l_qseq = (int)le32(p + 16);
+        r.mtid = (int32_t)le32(p + 20);
+        r.mpos = (int32_t)le32(p + 24);
+        r.isize = (int32_t)le32(p + 28);
+        size_t fixed = (size_t)r.l_qname + 4u * r.n_cigar + (size_t)(r.l_qseq + 1) / 2 + r.l_qseq;
+        if (32 + fixed > bs) { set_error("corrupt BAM record layout"); return -2; }
+        r.qname = (const char*)p + 32;
+        r.cigar_bytes = p + 32 + r.l_qname;
+        r.seq = r.cigar_bytes + 4u * r.n_cigar;
+        r.qual = r.seq + (r.l_qseq + 1) / 2;
+        r.aux = r.qual + r.l_qseq;
+        r.l_aux = (int)(bs - 32 - fixed);
+        if (has_region_) {
+            if (r.tid != r_tid_ || r.pos >= r_end_) {
+                if (r.tid < 0 || r.tid > r_tid_ || (r.tid == r_tid_ && r.pos >= r_end_)) { region_done_ = true; return -1; }
+                continue;
+            }
+            int rlen = 0;
+            for (int k = 0; k < r.n_cigar; ++k) {
+                uint32_t w = le32(r.cigar_bytes + 4 * k);
+                if ((0x3C1A7 >> ((w & 0xf) << 1)) & 2) rlen += (int)(w >> 4);
+            }
+            if ((r.flag & 4) || r.n_cigar == 0 || rlen == 0) rlen = 1;
+            if (r.pos + rlen <= r_beg_) continue;
+        }
+        return 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------- regions
+void RegionIndex::build(int n, const char* const* names, const int32_t* beg0, const int32_t* end0) {
+    struct Iv { int b, e, p; };
+    std::unordered_map<std::string, std::vector<Iv>> tmp;
+    for (int i = 0; i < n; ++i) tmp[names[i]].push_back({beg0[i], end0[i], i});
+    for (auto& kv : tmp) {
+        std::stable_sort(kv.second.begin(), kv.second.end(), [](const Iv& a, const Iv& b) {
+            return a.b != b.b ? a.b < b.b : a.e < b.e;
+        });
+        Chr& c = chr[kv.first];
+        int me = -1;
+        for (auto& iv : kv.second) {
+            c.beg.push_back(iv.b);
+            c.end.push_back(iv.e);
+            c.payload.push_back(iv.p);
+            me = std::max(me, iv.e);
+            c.maxend.push_back(me);
+        }
+    }
+}
+const RegionIndex::Chr* RegionIndex::find(const std::string& name) const {
+    auto it = chr.find(name);
+    return it == chr.end() ? nullptr : &it->second;
+}
+bool RegionIndex::overlap(const Chr* c, int from, int to) {
+    if (!c || c->beg.empty()) return false;
+    size_t k = std::upper_bound(c->beg.begin(), c->beg.end(), to) - c->beg.begin();
+    if (k == 0) return false;
+    return c->maxend[k - 1] >= from;
+}
+
+// ------------------------------------------------------------------------------------- helpers
+static const uint8_t* aux_get(const BamRecView& r, const char tag[2]) {
+    const uint8_t* p = r.aux;
+    const uint8_t* end = r.aux + r.l_aux;
+    auto tsz = [](int t) {
+        switch (t) {
+        case 'A': case 'c': case 'C': return 1;
+        case 's': case 'S': return 2;
+        case 'i': case 'I': case 'f': return 4;
+        case 'd': return 8;
+        default: return 0;
+        }
+    };
+    while (p + 3 <= end) {
+        bool hit = p[0] == (uint8_t)tag[0] && p[1] == (uint8_t)tag[1];
+        int t = p[2];
+        const uint8_t* v = p + 2;
+        p += 3;
+        if (t == 'Z' || t == 'H') {
+            while (p < end && *p) ++p;
+            ++p;
+        } else if (t == 'B') {
+            if (p + 5 > end) return nullptr;
+            int sz = tsz(p[0]);
+            uint32_t cnt = le32(p + 1);
+            p += 5 + (size_t)sz * cnt;
+        } else {
+            int sz = tsz(t);
+            if (!sz) return nullptr;
+            p += sz;
+        }
+        if (p > end) return nullptr;
+        if (hit) return v;
+    }
+    return nullptr;
+}
+static const char* aux_z(const BamRecView& r, const std::string& tag) {
+    if (tag.size() != 2) return nullptr;
+    const uint8_t* v = aux_get(r, tag.c_str());
+    if (!v || (*v != 'Z' && *v != 'H')) return nullptr;
+    return (const char*)v + 1;
+}
+static inline int seqi(const uint8_t* s, int i) { return (s[i >> 1] >> ((~i & 1) << 2)) & 0xf; }
+
+// htsbox-ext.c:17-97 -> 0 pass, >0 fail, -1 inconsistent MD
+static int md_verdict(const BamRecView& r, const uint32_t* cigar, int n_types, int n_mis) {
+    if (n_types < 1 && n_mis < 1) return 0;
+    const uint8_t* md = aux_get(r, "MD");
+    if (!md || (*md != 'Z' && *md != 'H')) return 0;
+    int x = 0;
+    for (int k = 0; k < r.n_cigar; ++k) {
+        int op = cigar[k] & 0xf;
+        if (op == 0 || op == 7 || op == 8) x += (int)(cigar[k] >> 4);
+    }
+    const char* p = (const char*)md + 1;
+    int y = 0, nm = 0, ntypes = 0;
+    unsigned seen = 0;
+    while (isdigit((unsigned char)*p)) {
+        char* q;
+        y += (int)strtol(p, &q, 10);
+        p = q;
+        if (*p == 0) break;
+        if (*p == '^') {
+            ++p;
+            while (isalpha((unsigned char)*p)) ++p;
+        } else {
+            while (isalpha((unsigned char)*p)) {
+                if (y >= x) { y = -1; break; }
+                int code = y < r.l_qseq ? seqi(r.seq, y) : 15;
+                ++nm;
+                if (!(seen & (1u << code))) { seen |= 1u << code; ++ntypes; }
+                ++y;
+                ++p;
+            }
+            if (y == -1) break;
+        }
+    }
+    if (x != y) return -1;
+    return (ntypes >= n_types && nm >= n_mis) ? (ntypes > 0 ? ntypes : 0) : 0;
+}
+
+static unsigned x31(const char* s) {
+    unsigned h = (unsigned)(int)*s;
+    if (h)
+        for (++s; *s; ++s) h = (h << 5) - h + (unsigned)(int)*s;
+    return h;
+}
+static unsigned wang(unsigned key) {
+    key += ~(key << 15); key ^= (key >> 10); key += (key << 3);
+    key ^= (key >> 6); key += ~(key << 11); key ^= (key >> 16);
+    return key;
+}
+
+bool fasta_fetch(const char* fa, const std::string& name, std::string& out) {
+    std::string fai = std::string(fa) + ".fai";
+    FILE* fp = fopen(fai.c_str(), "r");
+    if (!fp) return false;
+    char line[4096];
+    long long slen = -1, off = 0, lb = 0, lw = 0;
+    while (fgets(line, sizeof(line), fp)) {
+        char* tab = strchr(line, '\t');
+        if (!tab) continue;
+        *tab = 0;
+        if (name != line) continue;
+        if (sscanf(tab + 1, "%lld\t%lld\t%lld\t%lld", &slen, &off, &lb, &lw) != 4) slen = -1;
+        break;
+    }
+    fclose(fp);
+    if (slen < 0) return false;
+    fp = fopen(fa, "rb");
+    if (!fp) return false;
+    fseek(fp, (long)off, SEEK_SET);
+    out.clear();
+    out.reserve(slen);
+    // whole lines at once: linebases graph characters then the line terminator
+    size_t raw = (size_t)(lb > 0 ? (slen / lb + 1) * lw : slen) + 16;
+    std::vector<char> buf(raw);
+    size_t got = fread(buf.data(), 1, raw, fp);
+    fclose(fp);
+    for (size_t i = 0; i < got && (long long)out.size() < slen; ++i)
+        if (isgraph((unsigned char)buf[i])) out.push_back(buf[i]);
+    return true;
+}
+
+int parse_region(const char* s, int* beg, int* end) {
+    const char* colon = strrchr(s, ':');
+    *beg = 0;
+    *end = INT_MAX;
+    if (!colon) return (int)strlen(s);
+    char tmp[128];
+    int k = 0;
+    for (const char* p = colon + 1; *p && k < 127; ++p)
+        if (*p != ',') tmp[k++] = *p;
+    tmp[k] = 0;
+    char* q;
+    long b = strtol(tmp, &q, 10);
+    if (q == tmp) return -1;
+    *beg = (int)(b - 1);
+    if (*beg < 0) *beg = 0;
+    if (*q == '-') {
+        char* q2;
+        long e = strtol(q + 1, &q2, 10);
+        *end = q2 == q + 1 ? INT_MAX : (int)e;
+    } else if (*q) {
+        return -1;
+    }
+    if (*beg > *end) return -1;
+    return (int)(colon - s);
+}
+
+// ------------------------------------------------------------------------------------- batches
+void PackedBatch::release() {
+    raer_pinned_free(hdr, pinned); raer_pinned_free(maxend, pinned); raer_pinned_free(cigar, pinned);
+    raer_pinned_free(seq, pinned); raer_pinned_free(qual, pinned); raer_pinned_free(pair_b, pinned);
+    raer_pinned_free(cb, pinned); raer_pinned_free(umi, pinned);
+    hdr = nullptr; maxend = nullptr; cigar = nullptr; seq = nullptr; qual = nullptr; pair_b = nullptr;
+    cb = nullptr; umi = nullptr;
+    cap_reads = cap_cigar = cap_sq = cap_pairs = 0;
+}
+
+void PackedBatch::reserve(size_t reads, size_t cig, size_t sq, bool sc) {
+    int pin = 0;
+    auto grow = [&](void** p, size_t bytes) {
+        raer_pinned_free(*p, pinned);
+        *p = raer_pinned_alloc(bytes ? bytes : 16, &pin);
+    };
+    if (reads > cap_reads || !hdr) {
+        size_t n = reads + reads / 4 + 1024;
+        grow((void**)&hdr, n * sizeof(raer_read_hdr));
+        grow((void**)&maxend, n * 4);
+        grow((void**)&pair_b, n * 4);
+        if (sc) { grow((void**)&cb, n * 4); grow((void**)&umi, n * 4); }
+        cap_reads = n;
+        pinned = pin;
+    }
+    if (cig > cap_cigar || !cigar) {
+        size_t n = cig + cig / 4 + 1024;
+        grow((void**)&cigar, n * 4);
+        cap_cigar = n;
+    }
+    if (sq > cap_sq || !seq) {
+        size_t n = sq + sq / 4 + 4096;
+        grow((void**)&seq, n);
+        grow((void**)&qual, 2 * n);
+        cap_sq = n;
+    }
+}
+
+Ingest::~Ingest() {
+    for (auto* f : files_) delete f;
+}
+
+bool Ingest::open(const char* const* paths, const char* const* indexes, int threads, const char* region) {
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = 4;
+    for (int i = 0; i < conf_.n_files; ++i) {
+        FilePending* f = new FilePending();
+        files_.push_back(f);
+        if (!f->bs.open(paths[i], threads)) return false;
+    }
+    if (region) {
+        int rb, re;
+        int nl = parse_region(region, &rb, &re);
+        if (nl < 0) { set_error("fail to parse region '%s'", region); return false; }
+        int tid = files_[0]->bs.name2tid(region);
+        if (tid >= 0) { rb = 0; re = INT_MAX; }
+        else tid = files_[0]->bs.name2tid(std::string(region, nl));
+        if (tid < 0) { set_error("fail to parse region '%s'", region); return false; }
+        has_region_ = true;
+        reg_tid_ = tid; reg_beg_ = rb; reg_end_ = re;
+        for (int i = 0; i < conf_.n_files; ++i) {
+            std::string bai = (indexes && indexes[i]) ? indexes[i] : std::string(paths[i]) + ".bai";
+            // each file resolves the name in its own header, like sam_itr_querys
+            int ftid = files_[i]->bs.name2tid(tid < (int)names().size() ? names()[tid] : "");
+            if (ftid < 0) { set_error("fail to parse region '%s' with %s", region, paths[i]); return false; }
+            if (!files_[i]->bs.set_region(bai.c_str(), ftid, rb, re)) return false;
+        }
+    }
+    return true;
+}
+
+double Ingest::decode_seconds() const {
+    double t = 0;
+    for (auto* f : files_) t += f->bs.decode_seconds();
+    return t;
+}
+int64_t Ingest::records() const {
+    int64_t n = 0;
+    for (auto* f : files_) n += f->bs.records_read();
+    return n;
+}
+int64_t Ingest::aligned_bases() const {
+    int64_t n = 0;
+    for (auto* f : files_) n += f->n_aligned_bases;
+    return n;
+}
+
+// Reads the next record that survives the prefilter into fp.look. Returns false at EOF / error.
+bool Ingest::parse_one(int fi) {
+    FilePending& F = *files_[fi];
+    BamRecView r;
+    std::vector<uint32_t>& cig = F.look_cigar;
+    while (true) {
+        int rc = F.bs.next(r);
+        if (rc < 0) { F.eof = true; F.have_look = false; return false; }
+        if (r.tid < 0 || (r.flag & 4)) continue;
+        int rlen = 0;
+        int64_t nal = 0;
+        cig.resize(r.n_cigar);
+        for (int k = 0; k < r.n_cigar; ++k) {
+            uint32_t w = le32(r.cigar_bytes + 4 * k);
+            cig[k] = w;
+            int op = w & 0xf;
+            if ((0x3C1A7 >> (op << 1)) & 2) rlen += (int)(w >> 4);
+            if (op == 0 || op == 7 || op == 8) nal += (w >> 4);
+        }
+        F.n_aligned_bases += nal;  // unit of the bench metric: every mapped input record, before filters
+        int cbcol = 0;
+        if (conf_.sc && conf_.cb_index && !conf_.cb_tag.empty()) {  // src/sc-plp.c:464-477
+            const char* cb = aux_z(r, conf_.cb_tag);
+            if (!cb) continue;
+            auto it = conf_.cb_index->find(cb);
+            if (it == conf_.cb_index->end()) continue;
+            cbcol = it->second;
+        }
+        uint32_t test = (conf_.keep_flag[0] & ~(uint32_t)r.flag) | (conf_.keep_flag[1] & (uint32_t)r.flag);
+        if (~test & 2047u) continue;
+        int endpos = r.pos + ((r.n_cigar == 0 || rlen == 0) ? 1 : rlen);
+        if (conf_.regidx) {
+            const std::string& nm = names()[r.tid < (int)names().size() ? r.tid : 0];
+            if (!RegionIndex::overlap(conf_.regidx->find(nm), r.pos, endpos)) continue;  // inclusive end, src/plp.c:56-60
+        }
+        if (r.mapq < conf_.min_global_mq) continue;
+        if ((r.flag & 1) && !(r.flag & 2)) continue;
+        if (conf_.rq_pct && conf_.rq_minq) {  // read_base_quality, float threshold
+            if (!r.l_qseq) continue;
+            int lq = 0;
+            for (int i = 0; i < r.l_qseq; ++i) lq += r.qual[i] < conf_.rq_minq;
+            double frac = (double)lq / r.l_qseq;
+            if (!(frac <= (float)conf_.rq_pct)) continue;
+        }
+        if (r.l_qseq > 65535 || r.n_cigar > 65535) { set_error("read longer than 65535 bases is not supported"); F.eof = true; F.have_look = false; return false; }
+
+        // ---- stream-order decisions of bam_plp_push
+        if (F.live_tid != r.tid) {
+            while (!F.live_ends.empty()) F.live_ends.pop();
+            F.live_tid = r.tid;
+        } else {
+            while (!F.live_ends.empty() && F.live_ends.top() < F.prev_pos) F.live_ends.pop();
+        }
+        int cnt = (int)F.live_ends.size() + 1;
+        if (F.prev_tid == r.tid && F.prev_pos == r.pos && cnt > conf_.max_depth) {
+            if (conf_.remove_overlaps) F.olap.erase(std::string(r.qname));
+            continue;  // dropped by maxcnt
+        }
+        HostRead& H = F.look;
+        memset(&H, 0, sizeof(H));
+        H.h.pos = r.pos;
+        H.h.end = r.pos + rlen;
+        H.h.flag = r.flag;
+        H.h.mapq = r.mapq;
+        H.h.l_qseq = (uint16_t)r.l_qseq;
+        H.h.n_cigar = (uint16_t)r.n_cigar;
+        H.h.mate = -1;
+        H.mate_ord = -1;
+        H.ordinal = F.next_ordinal++;
+        H.cb = cbcol;
+        uint8_t bits = 0;
+        {  // invert_read_orientation
+            int lt = conf_.libtype[fi], rev = (r.flag & 16) != 0, inv = 0;
+            if (lt == 1 || lt == 2) {
+                int r1 = -1;
+                if (!(r.flag & 1)) r1 = 1;
+                else if (r.flag & 64) r1 = 1;
+                else if (r.flag & 128) r1 = 0;
+                if (r1 >= 0) {
+                    int when_rev = (lt == 2);
+                    inv = r1 ? (rev == when_rev) : (rev != when_rev);
+                }
+            }
+            if (inv) bits |= RAER_RB_INVERT;
+        }
+        if (conf_.n_mm_type > 0 || conf_.n_mm > 0) {
+            int m = md_verdict(r, cig.data(), conf_.n_mm_type, conf_.n_mm);
+            if (m > 0) bits |= RAER_RB_MMFAIL;
+            else if (m < 0) bits |= RAER_RB_MMERR;
+        }
+        if (conf_.min_overhang && r.l_qseq >= 2 && (r.seq[0] & 0xf) == 3) bits |= RAER_RB_OHANG_N;
+        // bam_plp_push keeps a read only if it can still produce a column (end > iterator position)
+        bool kept = (r.tid != F.prev_tid) || (H.h.end > F.prev_pos);
+        if (!kept) {
+            F.prev_tid = r.tid;
+            F.prev_pos = r.pos;
+            continue;
+        }
+        if (conf_.remove_overlaps) {
+            // overlap_push
+            bool eligible = !(r.flag & 8) && (r.flag & 2);
+            long long isz = r.isize < 0 ? -(long long)r.isize : r.isize;
+            if ((r.mtid >= 0 && r.tid != r.mtid) || (isz >= 2LL * r.l_qseq && r.mpos >= H.h.end)) eligible = false;
+            if (eligible) {
+                std::string q(r.qname);
+                auto it = F.olap.find(q);
+                // an entry is gone once its read left the pileup buffer (end < position of the last pushed read)
+                if (it != F.olap.end() && (it->second.tid != r.tid || it->second.end < F.prev_pos)) {
+                    F.olap.erase(it);
+                    it = F.olap.end();
+                }
+                if (it == F.olap.end()) {
+                    if (r.mpos >= r.pos || ((r.flag & 1) && r.mpos == -1)) {
+                        bool keep_a = (wang(x31(r.qname)) & 1) != 0;
+                        F.olap[q] = {H.ordinal, r.tid, H.h.end, keep_a};
+                    }
+                } else {
+                    H.mate_ord = it->second.ordinal;
+                    if (it->second.keep_a) bits |= RAER_RB_KEEP_A;
+                    F.olap.erase(it);
+                }
+            }
+            if (F.olap.size() > 4000000) {  // purge entries whose reads have left the buffer
+                for (auto it = F.olap.begin(); it != F.olap.end();)
+                    it = (it->second.tid != r.tid || it->second.end < F.prev_pos) ? F.olap.erase(it) : std::next(it);
+            }
+        }
+        H.h.bits = bits;
+        F.prev_tid = r.tid;
+        F.prev_pos = r.pos;
+        F.live_ends.push(H.h.end);
+        if (conf_.sc) {
+            if (!conf_.umi_tag.empty()) {
+                const char* u = aux_z(r, conf_.umi_tag);
+                if (u) {
+                    auto ins = umi_dict_.emplace(u, (uint32_t)umi_dict_.size() + 1);
+                    H.umi = ins.first->second;
+                }
+            }
+        }
+        F.look_seq.assign(r.seq, r.seq + (r.l_qseq + 1) / 2);
+        F.look_qual.assign(r.qual, r.qual + r.l_qseq);
+        F.look_tid = r.tid;
+        F.have_look = true;
+        return true;
+    }
+}
+
+bool Ingest::parse_ahead(int fi, size_t want) {
+    FilePending& F = *files_[fi];
+    while (true) {
+        if (!F.have_look) {
+            if (F.eof) return false;
+            if (!parse_one(fi)) return false;
+        }
+        if (F.look_tid != cur_tid_) return false;  // next contig: stays in look
+        if (F.reads.size() - F.front >= want) return true;  // enough pending; look holds the next read
+        HostRead H = F.look;
+        H.h.cigar_off = (uint32_t)(F.cigar.size());
+        H.h.sq_off = (uint32_t)(F.seq.size());
+        F.cigar.insert(F.cigar.end(), F.look_cigar.begin(), F.look_cigar.end());
+        F.seq.insert(F.seq.end(), F.look_seq.begin(), F.look_seq.end());
+        // qualities live at 2 * sq_off: pad odd lengths
+        F.qual.insert(F.qual.end(), F.look_qual.begin(), F.look_qual.end());
+        if (F.look_qual.size() & 1) F.qual.push_back(0);
+        F.reads.push_back(H);
+        F.have_look = false;
+    }
+}
+
+int Ingest::next_contig() {
+    int best = -1;
+    for (int i = 0; i < conf_.n_files; ++i) {
+        FilePending& F = *files_[i];
+        // drop whatever is left of the previous contig
+        F.reads.clear(); F.front = 0; F.cigar.clear(); F.seq.clear(); F.qual.clear();
+        if (!F.have_look && !F.eof) parse_one(i);
+        if (F.have_look && (best < 0 || F.look_tid < best)) best = F.look_tid;
+    }
+    cur_tid_ = best;
+    win_beg_ = 0;
+    if (has_region_ && best >= 0) win_beg_ = reg_beg_;
+    return best;
+}
+
+bool Ingest::next_batch(PackedBatch& out) {
+    if (cur_tid_ < 0) return false;
+    const int nf = conf_.n_files;
+    size_t want = (size_t)std::max<int64_t>(1024, conf_.target_reads / nf);
+    int boundary;
+    while (true) {
+        boundary = INT_MAX;
+        bool all_done = true;
+        for (int i = 0; i < nf; ++i) {
+            parse_ahead(i, want);
+            FilePending& F = *files_[i];
+            bool done = !F.have_look || F.look_tid != cur_tid_;
+            if (!done) {
+                all_done = false;
+                boundary = std::min(boundary, (int)F.look.h.pos);
+            }
+        }
+        if (all_done || boundary > win_beg_) break;
+        want *= 2;  // every pending read starts at the window start: look further
+    }
+    double t0 = now_seconds();
+    // reads of each file starting before the boundary
+    std::vector<size_t> upto(nf);
+    size_t n_reads = 0, n_cig = 0, n_sq = 0;
+    int min_pos = INT_MAX, max_end = INT_MIN;
+    for (int i = 0; i < nf; ++i) {
+        FilePending& F = *files_[i];
+        size_t lo = F.front, hi = F.reads.size();
+        while (lo < hi) {
+            size_t mid = (lo + hi) >> 1;
+            if (F.reads[mid].h.pos >= boundary) hi = mid; else lo = mid + 1;
+        }
+        upto[i] = lo;
+        if (lo > F.front) {
+            n_reads += lo - F.front;
+            size_t c0 = F.reads[F.front].h.cigar_off, s0 = F.reads[F.front].h.sq_off;
+            size_t c1 = lo < F.reads.size() ? F.reads[lo].h.cigar_off : F.cigar.size();
+            size_t s1 = lo < F.reads.size() ? F.reads[lo].h.sq_off : F.seq.size();
+            n_cig += c1 - c0;
+            n_sq += s1 - s0;
+            min_pos = std::min(min_pos, (int)F.reads[F.front].h.pos);
+        }
+    }
+    if (n_reads == 0) {
+        bool any_left = false;
+        for (int i = 0; i < nf; ++i) any_left |= files_[i]->have_look && files_[i]->look_tid == cur_tid_;
+        if (!any_left) return false;
+    }
+    out.reserve(n_reads, n_cig, n_sq, conf_.sc);
+    out.file_off.assign(nf + 1, 0);
+    size_t ro = 0, co = 0, so = 0, np = 0;
+    int64_t nal = 0;
+    for (int i = 0; i < nf; ++i) {
+        FilePending& F = *files_[i];
+        out.file_off[i] = (int64_t)ro;
+        if (upto[i] > F.front) {
+            size_t c0 = F.reads[F.front].h.cigar_off, s0 = F.reads[F.front].h.sq_off;
+            size_t c1 = upto[i] < F.reads.size() ? F.reads[upto[i]].h.cigar_off : F.cigar.size();
+            size_t s1 = upto[i] < F.reads.size() ? F.reads[upto[i]].h.sq_off : F.seq.size();
+            memcpy(out.cigar + co, F.cigar.data() + c0, (c1 - c0) * 4);
+            memcpy(out.seq + so, F.seq.data() + s0, s1 - s0);
+            memcpy(out.qual + 2 * so, F.qual.data() + 2 * s0, 2 * (s1 - s0));
+            int64_t front_ord = F.reads[F.front].ordinal;
+            int me = INT_MIN;
+            for (size_t k = F.front; k < upto[i]; ++k) {
+                const HostRead& H = F.reads[k];
+                raer_read_hdr h = H.h;
+                h.cigar_off = (uint32_t)(co + (H.h.cigar_off - c0));
+                h.sq_off = (uint32_t)(so + (H.h.sq_off - s0));
+                h.mate = (H.mate_ord >= front_ord) ? (int32_t)(ro + (size_t)(H.mate_ord - front_ord)) : -1;
+                h.aux = (uint32_t)(ro + (k - F.front));
+                size_t bi = ro + (k - F.front);
+                out.hdr[bi] = h;
+                me = std::max(me, (int)h.end);
+                out.maxend[bi] = me;
+                if (h.mate >= 0) out.pair_b[np++] = (int32_t)bi;
+                if (conf_.sc) { out.cb[bi] = H.cb; out.umi[bi] = H.umi; }
+                if (h.end > win_beg_) max_end = std::max(max_end, (int)h.end);
+            }
+            ro += upto[i] - F.front;
+            co += c1 - c0;
+            so += s1 - s0;
+        }
+    }
+    out.file_off[nf] = (int64_t)ro;
+    raer_read_batch& b = out.b;
+    memset(&b, 0, sizeof(b));
+    b.n_files = nf;
+    b.tid = cur_tid_;
+    b.beg = std::max(win_beg_, min_pos == INT_MAX ? win_beg_ : std::min(min_pos, boundary));
+    b.beg = std::max(b.beg, win_beg_);
+    b.end = std::min(boundary, max_end == INT_MIN ? win_beg_ : max_end);
+    if (has_region_) { b.beg = std::max(b.beg, reg_beg_); b.end = std::min(b.end, reg_end_); }
+    if (b.end < b.beg) b.end = b.beg;
+    b.n_reads = (int64_t)ro;
+    b.file_off = out.file_off.data();
+    b.hdr = out.hdr; b.maxend = out.maxend; b.cigar = out.cigar; b.seq = out.seq; b.qual = out.qual;
+    b.n_cigar_words = (int64_t)co;
+    b.n_sq_bytes = (int64_t)so;
+    b.pair_b = out.pair_b;
+    b.n_pairs = (int64_t)np;
+    b.cb = conf_.sc ? out.cb : nullptr;
+    b.umi = conf_.sc ? out.umi : nullptr;
+    b.n_aligned_bases = nal;
+    // retire reads that end before the boundary (front only, so ordinals stay contiguous) and compact pools
+    win_beg_ = boundary;
+    for (int i = 0; i < nf; ++i) {
+        FilePending& F = *files_[i];
+        while (F.front < upto[i] && F.reads[F.front].h.end <= boundary) ++F.front;
+        if (F.front == F.reads.size()) {
+            F.reads.clear(); F.front = 0; F.cigar.clear(); F.seq.clear(); F.qual.clear();
+        } else if (F.front > (1u << 16) && F.front * 2 > F.reads.size()) {
+            uint32_t c0 = F.reads[F.front].h.cigar_off, s0 = F.reads[F.front].h.sq_off;
+            F.cigar.erase(F.cigar.begin(), F.cigar.begin() + c0);
+            F.seq.erase(F.seq.begin(), F.seq.begin() + s0);
+            F.qual.erase(F.qual.begin(), F.qual.begin() + 2 * (size_t)s0);
+            F.reads.erase(F.reads.begin(), F.reads.begin() + F.front);
+            F.front = 0;
+            for (auto& H : F.reads) { H.h.cigar_off -= c0; H.h.sq_off -= s0; }
+        }
+    }
+    t_pack_ += now_seconds() - t0;
+    if (boundary == INT_MAX) {
+        // the contig is finished after this batch
+        for (int i = 0; i < nf; ++i) { files_[i]->reads.clear(); files_[i]->front = 0; files_[i]->cigar.clear(); files_[i]->seq.clear(); files_[i]->qual.clear(); }
+    }
+    return true;
+}
+
+}  // namespace raer

@@ -1,0 +1,840 @@
+// raer_kernels.cu -- hand-written sm_100a kernels of the bulk pileup path.
+//
+//   k_mate_overlap   htslib bam_mplp overlap logic (overlap_push + tweak_overlap_quality), one
+//                    thread per overlapping pair, qualities rewritten in place before counting.
+//   k_tile_ranges    per (tile, file): first/last read that can overlap the tile (binary search).
+//   k_pileup_tiles   persistent CTAs pull genomic tiles from an atomic queue; per tile:
+//        phase 1  warp-per-read CIGAR expansion, read/base filters (src/plp.c:568-615,
+//                 src/plp_utils.c), shared-memory counters [file][strand][class][pos] updated with
+//                 conflict-free atomics (a warp's lanes sit on consecutive positions of one read)
+//        phase 2  per-position site decision (src/plp.c:671-704 + store_counts :358-461),
+//                 block scan, coalesced row stores
+//        phase 3  second, sparse pass over the tile's reads for the rows that carry a variant:
+//                 100-bin read-position histograms, strand tallies, first-seen order of variant bases
+//        phase 4  rpbz / vdb / sor (src/ext/bcftools/bcftools-ext.c, src/plp_utils.c:375-387) and ALT codes
+//
+// Nothing here is a dense contraction: no tensor cores. The bound is HBM traffic of the read batch
+// (about 1.9 B per aligned base) and shared-memory atomic throughput; see DESIGN.md.
+// Compiled with -fmad=false so that the fp32/fp64 statistics round exactly like the reference's C.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "raer_dev.h"
+
+#define FULL 0xffffffffu
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cg_op(uint32_t c) { return (int)(c & 0xf); }
+__device__ __forceinline__ int cg_len(uint32_t c) { return (int)(c >> 4); }
+// bit0 consumes query, bit1 consumes reference (M I D N S H P = X B)
+__device__ __forceinline__ int cg_type(int op) { return (0x3C1A7 >> (op << 1)) & 3; }
+enum { OP_M = 0, OP_I, OP_D, OP_N, OP_S, OP_H, OP_P, OP_EQ, OP_X };
+
+// 4-bit base code -> counter class: A0 C1 G2 T3, 4 = other IUPAC, -1 = N (code 15)
+__device__ __forceinline__ int cls_of_code(int code) {
+    const unsigned long long lut = 0x0555555455535215ull;  // (class + 1) per nibble, code 0 first
+    return (int)((lut >> (code << 2)) & 0xf) - 1;
+}
+__device__ __forceinline__ int d_upper(int c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
+__device__ __forceinline__ int cls_of_ref(int up) {
+    return up == 'A' ? 0 : up == 'C' ? 1 : up == 'G' ? 2 : up == 'T' ? 3 : 4;
+}
+__device__ __forceinline__ int d_comp_char(int c) {  // src/plp_utils.c:438-455 (upper case part)
+    switch (c) {
+    case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C';
+    case 'B': return 'V'; case 'V': return 'B'; case 'D': return 'H'; case 'H': return 'D';
+    case 'K': return 'M'; case 'M': return 'K'; case 'R': return 'Y'; case 'Y': return 'R';
+    case 'U': return 'A';
+    default: return c;
+    }
+}
+__device__ __forceinline__ int seq_code(const uint8_t* seq, int q) { return (seq[q >> 1] >> ((~q & 1) << 2)) & 0xf; }
+
+struct ReadCtx {
+    const uint32_t* cig;
+    const uint8_t* seq;
+    const uint8_t* qual;
+    int pos, end, flag, mapq, bits, l_qseq, n_cigar;
+    int qs, qe, rev, invert, d5f, d3f, ftrim_all;
+};
+
+__device__ __forceinline__ void load_read(const PlpParams& P, long long r, ReadCtx& c) {
+    const int4* h = reinterpret_cast<const int4*>(P.hdr + r);
+    int4 a = __ldg(h), b = __ldg(h + 1);
+    c.pos = a.x;
+    c.end = a.y;
+    c.flag = a.z & 0xffff;
+    c.mapq = (a.z >> 16) & 0xff;
+    c.bits = (a.z >> 24) & 0xff;
+    c.l_qseq = a.w & 0xffff;
+    c.n_cigar = (a.w >> 16) & 0xffff;
+    c.cig = P.cigar + (unsigned)b.x;
+    c.seq = P.seq + (unsigned)b.y;
+    c.qual = P.qual + 2ull * (unsigned)b.y;
+    c.rev = (c.flag >> 4) & 1;
+    c.invert = c.bits & RAER_RB_INVERT;
+    // query_start / query_end (src/plp_utils.c:52-104): soft clips at either end, hard clips skipped
+    int qs = 0, k;
+    for (k = 0; k < c.n_cigar; ++k) {
+        uint32_t w = __ldg(c.cig + k);
+        int op = cg_op(w);
+        if (op == OP_H) continue;
+        if (op == OP_S) qs += cg_len(w);
+        else break;
+    }
+    int qe = c.l_qseq;
+    for (k = c.n_cigar - 1; k >= 0; --k) {
+        uint32_t w = __ldg(c.cig + k);
+        int op = cg_op(w);
+        if (op == OP_H) continue;
+        if (op == OP_S) qe -= cg_len(w);
+        else break;
+    }
+    c.qs = qs;
+    c.qe = qe;
+    c.d5f = c.d3f = 0;
+    c.ftrim_all = 0;
+    if (P.ftrim_5p > 0 || P.ftrim_3p > 0) {  // check_variant_fpos, src/plp_utils.c:163-193
+        int ql = qe - qs;
+        if (ql <= 0) c.ftrim_all = 1;
+        c.d5f = (int)floor(P.ftrim_5p * ql);
+        c.d3f = (int)ceil(P.ftrim_3p * ql);
+    }
+}
+
+// src/plp_utils.c:196-221
+__device__ int d_dist_to_splice(const ReadCtx& c, int q, int dist) {
+    int ip = 0;
+    for (int i = 0; i < c.n_cigar; ++i) {
+        uint32_t w = __ldg(c.cig + i);
+        int op = cg_op(w);
+        if (cg_type(op) & 1) { ip += cg_len(w); continue; }
+        if (op == OP_N && ip >= q - dist && ip <= q + dist) return abs(ip - q);
+    }
+    return -1;
+}
+// src/plp_utils.c:228-266 (inclusive upper bound, BAM_CMATCH only, one-past-the-end read modelled by RAER_RB_OHANG_N)
+__device__ int d_check_splice_overhang(const ReadCtx& c, int q, int dist) {
+    int ip = 0, p_op = -1;
+    for (int i = 0; i < c.n_cigar; ++i) {
+        uint32_t w = __ldg(c.cig + i);
+        int op = cg_op(w), cl = cg_len(w);
+        if (op == OP_M && q >= ip && q <= cl + ip) {
+            if (i > 0 && p_op == OP_N) return cl >= dist ? -1 : cl;
+            int nop = (i + 1 < c.n_cigar) ? cg_op(__ldg(c.cig + i + 1)) : ((c.bits & RAER_RB_OHANG_N) ? OP_N : -1);
+            if (nop == OP_N) return cl >= dist ? -1 : cl;
+            return 0;
+        }
+        p_op = op;
+        if (cg_type(op) & 1) ip += cl;
+    }
+    return -2;
+}
+// src/plp_utils.c:269-306
+__device__ int d_dist_to_indel(const ReadCtx& c, int q, int dist) {
+    int rp = 0, sp = q - dist, ep = q + dist;
+    for (int i = 0; i < c.n_cigar; ++i) {
+        uint32_t w = __ldg(c.cig + i);
+        int op = cg_op(w), cl = cg_len(w);
+        if (cg_type(op) & 1) {
+            if (op == OP_I) {
+                int is = rp, ie = rp + cl;
+                if (sp <= ie && is <= ep) {
+                    int l = q - ie, r = is - q;
+                    return l > r ? l : r;
+                }
+            }
+            rp += cl;
+        }
+        if (op == OP_D && rp >= sp && rp <= ep) return abs(rp - q);
+    }
+    return -1;
+}
+
+// check_read_filters for an aligned base (src/plp.c:568-615): 0 count, 1 count as nX, 2 drop silently
+__device__ __forceinline__ int base_verdict(const PlpParams& P, const ReadCtx& c, int mapq_fail, int q, int bq) {
+    if (mapq_fail) return 1;
+    if (bq < P.min_bq) return bq == 0 ? 2 : 1;
+    if (P.ftrim_5p > 0 || P.ftrim_3p > 0) {
+        if (c.ftrim_all) return 1;
+        if (!c.rev) { if (q < c.d5f + c.qs || c.qe - q <= c.d3f) return 1; }
+        else { if (c.qe - q <= c.d5f || q < c.d3f + c.qs) return 1; }
+    }
+    if (P.trim_5p > 0 || P.trim_3p > 0) {  // check_variant_pos, src/plp_utils.c:137-159
+        if (!c.rev) { if (q < P.trim_5p + c.qs || c.qe - q <= P.trim_3p) return 1; }
+        else { if (c.qe - q <= P.trim_5p || q < P.trim_3p + c.qs) return 1; }
+    }
+    if (P.splice_dist && d_dist_to_splice(c, q, P.splice_dist) >= 0) return 1;
+    if (P.min_overhang) {
+        int r = d_check_splice_overhang(c, q, P.min_overhang);
+        if (r > 0) return 1;  // r == -2 propagates as -1 upstream, which the caller treats as pass (src/plp.c:735)
+    }
+    if (P.indel_dist && d_dist_to_indel(c, q, P.indel_dist) >= 0) return 1;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mate overlap: htslib tweak_overlap_quality (>= 1.13 when mode == 1, <= 1.12 when mode == 2)
+// ---------------------------------------------------------------------------------------------
+struct CigCur {
+    const uint32_t* cig;
+    int k, n;      // current op, number of ops
+    int icig, iseq, iref;
+};
+__device__ int cur_set(CigCur& c, int iref_in) {
+    int pos = iref_in;
+    if (pos < 0) return -1;
+    c.icig = c.iseq = c.iref = 0;
+    while (c.k < c.n) {
+        uint32_t w = c.cig[c.k];
+        int op = cg_op(w), n = cg_len(w);
+        if (op == OP_S) { c.k++; c.iseq += n; c.icig = 0; continue; }
+        if (op == OP_H || op == OP_P) { c.k++; c.icig = 0; continue; }
+        if (op == OP_M || op == OP_EQ || op == OP_X) {
+            pos -= n;
+            if (pos < 0) { c.icig = n + pos; c.iseq += c.icig; c.iref += c.icig; return OP_M; }
+            c.k++; c.iseq += n; c.icig = 0; c.iref += n;
+            continue;
+        }
+        if (op == OP_I) { c.k++; c.iseq += n; c.icig = 0; continue; }
+        if (op == OP_D || op == OP_N) {
+            pos -= n;
+            if (pos < 0) pos = 0;
+            c.k++; c.icig = 0; c.iref += n;
+            continue;
+        }
+        return -2;
+    }
+    c.iseq = -1;
+    return -1;
+}
+__device__ int cur_next(CigCur& c) {
+    while (c.k < c.n) {
+        uint32_t w = c.cig[c.k];
+        int op = cg_op(w), n = cg_len(w);
+        if (op == OP_M || op == OP_EQ || op == OP_X) {
+            if (c.icig >= n - 1) { c.icig = -1; c.k++; continue; }
+            c.iseq++; c.icig++; c.iref++;
+            return OP_M;
+        }
+        if (op == OP_D || op == OP_N) { c.k++; c.iref += n; c.icig = -1; continue; }
+        if (op == OP_I || op == OP_S) { c.k++; c.iseq += n; c.icig = -1; continue; }
+        if (op == OP_H || op == OP_P) { c.k++; c.icig = -1; continue; }
+        return -2;
+    }
+    c.iseq = -1;
+    c.iref = -1;
+    return -1;
+}
+
+__global__ void k_mate_overlap(const raer_read_hdr* __restrict__ hdr, const uint32_t* __restrict__ cigar,
+                               const uint8_t* __restrict__ seq, uint8_t* qual, const int32_t* __restrict__ pair_b,
+                               long long n_pairs, int mode) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n_pairs) return;
+    const raer_read_hdr hb = hdr[pair_b[t]];
+    const raer_read_hdr ha = hdr[hb.mate];
+    CigCur A, B;
+    A.cig = cigar + ha.cigar_off; A.k = 0; A.n = ha.n_cigar;
+    B.cig = cigar + hb.cigar_off; B.k = 0; B.n = hb.n_cigar;
+    const uint8_t* a_seq = seq + ha.sq_off;
+    const uint8_t* b_seq = seq + hb.sq_off;
+    uint8_t* a_q = qual + 2ull * ha.sq_off;
+    uint8_t* b_q = qual + 2ull * hb.sq_off;
+    const int apos = ha.pos, bpos = hb.pos;
+    int iref = bpos;
+    int a_ret = cur_set(A, iref - apos);
+    if (a_ret < 0) return;
+    int b_ret = cur_set(B, iref - bpos);
+    if (b_ret < 0) return;
+    int amul, bmul;
+    if (mode == 2 || (hb.bits & RAER_RB_KEEP_A)) { amul = 1; bmul = 0; }
+    else { amul = 0; bmul = 1; }
+    while (true) {
+        while (a_ret >= 0 && A.iref >= 0 && A.iref < iref - apos) a_ret = cur_next(A);
+        if (a_ret < 0) break;
+        if (iref < A.iref + apos) iref = A.iref + apos;
+        while (b_ret >= 0 && B.iref >= 0 && B.iref < iref - bpos) b_ret = cur_next(B);
+        if (b_ret < 0) break;
+        if (iref < B.iref + bpos) iref = B.iref + bpos;
+        iref++;
+        if (A.iref + apos != B.iref + bpos) {
+            if (mode == 2) continue;
+            if (A.iref + apos < B.iref + bpos && B.k > 0 && cg_op(B.cig[B.k - 1]) == OP_D) {
+                bool done = false;
+                do {
+                    a_q[A.iseq] = amul ? (uint8_t)(a_q[A.iseq] * 0.8) : 0;
+                    a_ret = cur_next(A);
+                    if (a_ret < 0) { done = true; break; }
+                } while (A.iref + apos < B.iref + bpos);
+                if (done) return;
+            } else if (A.k > 0 && cg_op(A.cig[A.k - 1]) == OP_D) {
+                bool done = false;
+                do {
+                    b_q[B.iseq] = bmul ? (uint8_t)(b_q[B.iseq] * 0.8) : 0;
+                    b_ret = cur_next(B);
+                    if (b_ret < 0) { done = true; break; }
+                } while (B.iref + bpos < A.iref + apos);
+                if (done) return;
+            } else {
+                continue;
+            }
+        }
+        if (A.iseq > ha.l_qseq || B.iseq > hb.l_qseq) return;
+        int qa = a_q[A.iseq], qb = b_q[B.iseq];
+        if (seq_code(a_seq, A.iseq) == seq_code(b_seq, B.iseq)) {
+            int q = qa + qb;
+            if (q > 200) q = 200;
+            if (mode == 2) { a_q[A.iseq] = (uint8_t)q; b_q[B.iseq] = 0; }
+            else { a_q[A.iseq] = (uint8_t)(amul * q); b_q[B.iseq] = (uint8_t)(bmul * q); }
+        } else if (mode == 2) {
+            if (qa >= qb) { a_q[A.iseq] = (uint8_t)(0.8 * qa); b_q[B.iseq] = 0; }
+            else { b_q[B.iseq] = (uint8_t)(0.8 * qb); a_q[A.iseq] = 0; }
+        } else {
+            if (qa > qb) { a_q[A.iseq] = (uint8_t)(0.8 * qa); b_q[B.iseq] = 0; }
+            else if (qa < qb) { b_q[B.iseq] = (uint8_t)(0.8 * qb); a_q[A.iseq] = 0; }
+            else { a_q[A.iseq] = (uint8_t)(amul * 0.8 * qa); b_q[B.iseq] = (uint8_t)(bmul * 0.8 * qb); }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile read ranges
+// ---------------------------------------------------------------------------------------------
+__global__ void k_tile_ranges(PlpParams P) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.n_tiles * P.n_files) return;
+    int tile = t / P.n_files, f = t % P.n_files;
+    int t0 = P.t_beg + tile * P.W;
+    int t1 = min(t0 + P.W, P.t_end);
+    long long fo = P.file_off[f], fe = P.file_off[f + 1];
+    long long lo = fo, hi = fe;
+    while (lo < hi) {  // first read whose running max end exceeds t0
+        long long mid = (lo + hi) >> 1;
+        if (P.maxend[mid] > t0) hi = mid; else lo = mid + 1;
+    }
+    long long first = lo;
+    lo = first; hi = fe;
+    while (lo < hi) {  // first read starting at or after t1
+        long long mid = (lo + hi) >> 1;
+        if (P.hdr[mid].pos >= t1) hi = mid; else lo = mid + 1;
+    }
+    P.tile_ranges[t] = make_int2((int)first, (int)lo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// statistics (device restatements; exactness notes in DESIGN.md)
+// ---------------------------------------------------------------------------------------------
+__device__ double d_kf_erfc(double x) {  // htslib kfunc.c kf_erfc (AS66)
+    const double p0 = 220.2068679123761, p1 = 221.2135961699311, p2 = 112.0792914978709, p3 = 33.912866078383,
+                 p4 = 6.37396220353165, p5 = .7003830644436881, p6 = .03526249659989109;
+    const double q0 = 440.4137358247522, q1 = 793.8265125199484, q2 = 637.3336333788311, q3 = 296.5642487796737,
+                 q4 = 86.78073220294608, q5 = 16.06417757920695, q6 = 1.755667163182642, q7 = .08838834764831844;
+    double z = fabs(x) * 1.41421356237309504880;
+    if (z > 37.) return x > 0. ? 0. : 2.;
+    double e = exp(z * z * -.5), r;
+    if (z < 10. / 1.41421356237309504880)
+        r = e * ((((((p6 * z + p5) * z + p4) * z + p3) * z + p2) * z + p1) * z + p0) /
+            (((((((q7 * z + q6) * z + q5) * z + q4) * z + q3) * z + q2) * z + q1) * z + q0);
+    else
+        r = e / 2.506628274631001 / (z + 1. / (z + 2. / (z + 3. / (z + 4. / (z + .65)))));
+    return x > 0. ? 2. * r : 2. * (1. - r);
+}
+
+__device__ double d_calc_vdb(const uint32_t* pos) {  // src/ext/bcftools/bcftools-ext.c:51-111
+    const float prm[15][3] = {{3, 0.079f, 18},    {4, 0.09f, 19.8f},  {5, 0.1f, 20.5f},   {6, 0.11f, 21.5f},
+                              {7, 0.125f, 21.6f}, {8, 0.135f, 22},    {9, 0.14f, 22.2f},  {10, 0.153f, 22.3f},
+                              {15, 0.19f, 22.8f}, {20, 0.22f, 23.2f}, {30, 0.26f, 23.4f}, {40, 0.29f, 23.5f},
+                              {50, 0.35f, 23.65f}, {100, 0.5f, 23.7f}, {200, 0.7f, 23.7f}};
+    int i, dp = 0;
+    float mean_pos = 0, mean_diff = 0;
+    for (i = 0; i < RAER_NHIST; ++i) {
+        int v = (int)pos[i];
+        if (!v) continue;
+        dp += v;
+        mean_pos += (float)(v * i);
+    }
+    if (dp < 2) return CUDART_INF;
+    mean_pos /= (float)dp;
+    for (i = 0; i < RAER_NHIST; ++i) {
+        int v = (int)pos[i];
+        if (!v) continue;
+        // float += int * fabs(float): evaluated in double, rounded back to float
+        mean_diff = (float)((double)mean_diff + (double)v * fabs((double)((float)i - mean_pos)));
+    }
+    mean_diff /= (float)dp;
+    int ipos = (int)mean_diff;
+    if (dp == 2) return (double)((2 * 100 - 2 * (ipos + 1) - 1) * (ipos + 1) / 99) / (100 * 0.5);
+    if (dp >= 200) i = 15;
+    else
+        for (i = 0; i < 15; ++i)
+            if (prm[i][0] >= (float)dp) break;
+    float pshift, pscale;
+    if (i == 15) { pscale = prm[14][1]; pshift = prm[14][2]; }
+    else if (i > 0 && prm[i][0] != (float)dp) {
+        pscale = (float)((double)(prm[i - 1][1] + prm[i][1]) * 0.5);
+        pshift = (float)((double)(prm[i - 1][2] + prm[i][2]) * 0.5);
+    } else { pscale = prm[i][1]; pshift = prm[i][2]; }
+    return 0.5 * d_kf_erfc((double)(-(mean_diff - pshift) * pscale));
+}
+
+__device__ double d_calc_mwu_z(const uint32_t* a, const uint32_t* b) {  // bcftools-ext.c:144-212, do_Z = 1
+    int i;
+    long long t = 0;
+    for (i = 0; i < RAER_NHIST; ++i)
+        if (b[i]) break;
+    int b_empty = (i == RAER_NHIST);
+    int e = 0, l = 0, na = 0, nb = 0;
+    if (b_empty) {
+        for (i = RAER_NHIST - 1; i >= 0; --i) {
+            int ai = (int)a[i];
+            na += ai;
+            t += (ai * ai - 1) * ai;
+        }
+    } else {
+        for (i = RAER_NHIST - 1; i >= 0; --i) {
+            int ai = (int)a[i], bi = (int)b[i];
+            e += ai * bi;
+            l += ai * nb;
+            na += ai;
+            nb += bi;
+            int p = ai + bi;
+            t += (p * p - 1) * p;
+        }
+    }
+    if (!na || !nb) return CUDART_INF;
+    double U = l + e * 0.5;
+    double m = na * nb / 2.0;
+    double var2 = (na * nb) / 12.0 * ((na + nb + 1) - t / (double)((na + nb) * (na + nb - 1)));
+    if (var2 <= 0) return 0;
+    return (U - m) / sqrt(var2);
+}
+
+__device__ double d_calc_sor(int fwd_ref, int rev_ref, int fwd_alt, int rev_alt) {  // src/plp_utils.c:375-387
+    double t00 = (double)fwd_ref + 1, t01 = (double)rev_ref + 1, t11 = (double)fwd_alt + 1, t10 = (double)rev_alt + 1;
+    double ratio = (t00 / t01) * (t11 / t10) + (t01 / t00) * (t10 / t11);
+    double rr = fmin(t00, t01) / fmax(t00, t01);
+    double ar = fmin(t10, t11) / fmax(t10, t11);
+    return log(ratio) + log(rr) - log(ar);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the tile kernel
+// ---------------------------------------------------------------------------------------------
+struct TileSmem {
+    uint32_t* cnt;        // counters, later second-pass slots
+    uint32_t* covered;    // W/32 words
+    int* flag_rowp;       // W
+    int* flag_rowm;       // W
+    uint16_t* flag_pidx;  // W
+    uint16_t* slot_of;    // W
+    uint8_t* dec;         // W
+};
+
+__device__ __forceinline__ bool pos_eligible(const PlpParams& P, int p) {
+    if (p < P.reg_beg || p >= P.reg_end) return false;
+    if (P.site_mask) {
+        int b = p - P.mask_beg;
+        if (b < 0 || b >= P.mask_bits) return false;
+        return (__ldg(P.site_mask + (b >> 5)) >> (b & 31)) & 1u;
+    }
+    return true;
+}
+
+// src/plp_utils.c:106-133 on the raw FASTA bytes
+__device__ bool d_simple_repeat(const char* ref, int ref_len, int pos, int nmer) {
+    int n_pos = nmer * 2 - 1;
+    if (n_pos < 1 || nmer < 1 || ref_len < nmer || pos < 0) return false;
+    int start = pos - nmer + 1;
+    if (start < 0) { n_pos += start; start = 0; }
+    if (n_pos + start > ref_len) n_pos = ref_len - start;
+    int run = 0;
+    char prev = 0;
+    for (int i = 0; i < n_pos; ++i) {
+        char c = ref[start + i];
+        run = (i > 0 && c == prev) ? run + 1 : 1;
+        prev = c;
+        if (run >= nmer) return true;
+    }
+    return false;
+}
+
+struct SiteCounts {  // per (file, strand)
+    int c[RAER_NCLS];
+};
+
+// Site decision for one position; mirrors process_one_site + store_counts. Returns bit0 write '+',
+// bit1 write '-', bit2 '+' has a variant in some file, bit3 '-' has a variant.
+__device__ int decide_site(const PlpParams& P, const uint32_t* cnt, const uint32_t* covered, int pidx, int p) {
+    if (!pos_eligible(P, p)) return 0;
+    int r = (P.ref && p < P.ref_len) ? (unsigned char)P.ref[p] : 'N';
+    int pref = d_upper(r);
+    if (pref == 'N') return 0;
+    if (P.nmer > 0 && d_simple_repeat(P.ref, P.ref_len, p, P.nmer)) return 0;
+    if (P.min_depth <= 0 && !((covered[pidx >> 5] >> (pidx & 31)) & 1u)) return 0;  // no pileup column here
+    const int W = P.W;
+    int pc = cls_of_ref(pref);
+    int write_s[2] = {0, 0}, has_v[2] = {0, 0}, is_ma[2] = {0, 0}, any_var[2] = {0, 0};
+    for (int f = 0; f < P.n_files; ++f) {
+        for (int s = 0; s < 2; ++s) {
+            const uint32_t* base = cnt + (size_t)((f * 2 + s) * RAER_NCLS) * W + pidx;
+            int c0 = base[0], c1 = base[W], c2 = base[2 * W], c3 = base[3 * W], co = base[4 * W];
+            int total = c0 + c1 + c2 + c3 + co;
+            int rc = s == 0 ? pc : (pc < 4 ? 3 - pc : 4);
+            int cc[4] = {c0, c1, c2, c3};
+            int nr = rc < 4 ? cc[rc] : 0;
+            int nv = total - nr;
+            if (total >= P.min_depth && nv >= P.min_var_reads) write_s[s] = 1;
+            if (nv > 0) any_var[s] = 1;
+            int vs = 0;
+            for (int b = 0; b < 4; ++b) {
+                if (b == rc || cc[b] == 0) continue;
+                if (P.min_af > 0 && (double)cc[b] / (double)total < P.min_af) continue;
+                ++vs;
+            }
+            if (co > 0 && !(P.min_af > 0 && (double)co / (double)total < P.min_af)) ++vs;
+            if (vs > 0) {
+                if (P.okv[f]) has_v[s] = 1;
+                if (vs > 1) is_ma[s] = 1;
+            }
+        }
+    }
+    int out = 0;
+    for (int s = 0; s < 2; ++s) {
+        int w = write_s[s];
+        if (P.any_okv) w = w && has_v[s];
+        if (!P.report_multiallelic) w = w && !is_ma[s];
+        if (w) out |= 1 << s;
+        if (any_var[s]) out |= 4 << s;
+    }
+    return out;
+}
+
+__device__ void write_row(const PlpParams& P, const uint32_t* cnt, int pidx, int p, int s, long long row) {
+    const int W = P.W;
+    int pref = d_upper((unsigned char)P.ref[p]);
+    int pc = cls_of_ref(pref);
+    int rc = s == 0 ? pc : (pc < 4 ? 3 - pc : 4);
+    int refc = s == 0 ? pref : d_comp_char(pref);
+    P.row_pos[row] = p;
+    P.row_meta[row] = (unsigned)s | ((unsigned)refc << 8);
+    P.row_stats[row * 3 + 0] = 0.0;
+    P.row_stats[row * 3 + 1] = 0.0;
+    P.row_stats[row * 3 + 2] = 0.0;
+    for (int f = 0; f < P.n_files; ++f) {
+        const uint32_t* base = cnt + (size_t)((f * 2 + s) * RAER_NCLS) * W + pidx;
+        int cc[4] = {(int)base[0], (int)base[W], (int)base[2 * W], (int)base[3 * W]};
+        int co = base[4 * W], cx = base[5 * W];
+        int total = cc[0] + cc[1] + cc[2] + cc[3] + co;
+        int nr = rc < 4 ? cc[rc] : 0;
+        unsigned alt = 0;
+        for (int b = 0; b < 4; ++b) {
+            if (b == rc || cc[b] == 0) continue;
+            if (P.min_af > 0 && (double)cc[b] / (double)total < P.min_af) continue;
+            alt |= 1u << b;
+        }
+        if (co > 0 && !(P.min_af > 0 && (double)co / (double)total < P.min_af)) alt |= RAER_ALT_OTHER;
+        int4* o = reinterpret_cast<int4*>(P.row_counts + (row * P.n_files + f) * 8);
+        o[0] = make_int4(nr, total - nr, cc[0], cc[3]);  // nRef nAlt nA nT
+        o[1] = make_int4(cc[1], cc[2], co, cx);          // nC nG nN nX
+        P.row_alt[row * P.n_files + f] = alt;
+    }
+}
+
+// One warp expands one read. PASS2 == false: phase 1 (counters). PASS2 == true: phase 3 (histograms).
+template <bool PASS2>
+__device__ void walk_read(const PlpParams& P, const TileSmem& S, int f, long long r, int t0, int t1, int lane) {
+    ReadCtx c;
+    load_read(P, r, c);
+    if (c.end <= t0 || c.pos >= t1) return;
+    const int W = P.W;
+    const int mapq_fail = c.mapq < P.min_mapq[f];
+    const int s = c.invert ? 1 : 0;
+    const bool mm_on = (P.n_mm_type > 0 || P.n_mm > 0) && (c.bits & (RAER_RB_MMFAIL | RAER_RB_MMERR));
+    const bool need_cov = !PASS2 && P.min_depth <= 0;
+    const int ordinal = (int)(r - P.file_off[f]);
+    int x = c.pos, y = 0;
+    for (int k = 0; k < c.n_cigar; ++k) {
+        uint32_t w = __ldg(c.cig + k);
+        int op = cg_op(w), len = cg_len(w);
+        if (op == OP_M || op == OP_EQ || op == OP_X) {
+            int lo = max(x, t0), hi = min(x + len, t1);
+            for (int p = lo + lane; p < hi; p += 32) {
+                int pidx = p - t0;
+                if (need_cov) atomicOr(&S.covered[pidx >> 5], 1u << (pidx & 31));
+                if (PASS2) {
+                    if (S.slot_of[pidx] == 0xffff) continue;
+                }
+                int q = y + (p - x);
+                if (q >= c.l_qseq) continue;
+                int code = seq_code(c.seq, q);
+                if (code == 15) continue;  // read base N: not counted anywhere (src/plp.c:718)
+                int bq = c.qual[q];
+                int v = base_verdict(P, c, mapq_fail, q, bq);
+                if (v == 2) continue;
+                int cls = cls_of_code(code);
+                int pref = 0;
+                if (PASS2 || (mm_on && v == 0)) pref = (p < P.ref_len) ? d_upper((unsigned char)P.ref[p]) : 'N';
+                if (v == 0 && mm_on) {
+                    // src/plp.c:750: inverted reads always consult the MD verdict, others only on a mismatch
+                    int letter = "=ACMGRSVTWYHKDBN"[code];
+                    if (c.invert || letter != pref) {
+                        if (c.bits & RAER_RB_MMERR) { atomicExch(P.err_flag, RAER_ERR_MD); continue; }
+                        if (c.bits & RAER_RB_MMFAIL) continue;
+                    }
+                }
+                if (!PASS2) {
+                    int k2 = v == 1 ? RAER_CLS_X : ((c.invert && cls < 4) ? 3 - cls : cls);
+                    atomicAdd(&S.cnt[(size_t)((f * 2 + s) * RAER_NCLS + k2) * W + pidx], 1u);
+                } else {
+                    if (v != 0) continue;
+                    uint32_t* slot = S.cnt + (size_t)S.slot_of[pidx] * P.slot_words;
+                    int letter = "=ACMGRSVTWYHKDBN"[code];
+                    int isref = letter == pref;
+                    // strand-bias tally on the uncomplemented base (src/plp.c:762-774)
+                    atomicAdd(&slot[400 + (isref ? 0 : 2) + c.rev], 1u);  // ref_fwd ref_rev alt_fwd alt_rev
+                    // get_relative_position (src/plp_utils.c:401-412)
+                    int tail = c.l_qseq - c.qe;
+                    int alen = c.l_qseq - c.qs - tail;
+                    int rpos = (int)((double)(q + 1 - c.qs) / (double)(alen + 1) * 99.0);
+                    if (rpos < 0 || rpos >= RAER_NHIST) { atomicExch(P.err_flag, RAER_ERR); continue; }
+                    atomicAdd(&slot[(s * 2 + (isref ? 0 : 1)) * RAER_NHIST + rpos], 1u);
+                    if (!isref) {
+                        int cb = (c.invert && cls < 4) ? 3 - cls : cls;
+                        uint32_t* fs = slot + 404 + (f * 2 + s) * 5;
+                        if (cb < 4) atomicMin(&fs[cb], (unsigned)ordinal);
+                        atomicMax(&fs[4], (unsigned)ordinal + 1u);  // last variant read (ordinal + 1; 0 = none)
+                    }
+                }
+            }
+            x += len;
+            y += len;
+        } else if (op == OP_D || op == OP_N) {
+            if (need_cov) {
+                int lo = max(x, t0), hi = min(x + len, t1);
+                for (int p = lo + lane; p < hi; p += 32) atomicOr(&S.covered[(p - t0) >> 5], 1u << ((p - t0) & 31));
+            }
+            x += len;
+        } else if (op == OP_I || op == OP_S) {
+            y += len;
+        }
+    }
+}
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* scratch) {
+    // RAER_BLOCK threads, warp shuffle scan + smem across warps
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(FULL, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) scratch[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int nw = blockDim.x >> 5;
+        int wv = lane < nw ? scratch[lane] : 0;
+        int z = wv;
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(FULL, z, o);
+            if (lane >= o) z += y;
+        }
+        if (lane < nw) scratch[lane] = z - wv;
+        if (lane == nw - 1) scratch[32] = z;
+    }
+    __syncthreads();
+    int res = x - v + scratch[wid];
+    *total = scratch[32];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ int s_scan[40];
+    __shared__ int s_tile, s_nflag, s_rowbase;
+    const int W = P.W;
+    TileSmem S;
+    S.cnt = smem;
+    S.covered = S.cnt + P.cnt_words;
+    S.flag_rowp = (int*)(S.covered + (W >> 5));
+    S.flag_rowm = S.flag_rowp + W;
+    S.flag_pidx = (uint16_t*)(S.flag_rowm + W);
+    S.slot_of = S.flag_pidx + W;
+    S.dec = (uint8_t*)(S.slot_of + W);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int cnt_used = P.n_files * 2 * RAER_NCLS * W;
+
+    while (true) {
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(P.tile_counter, 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= P.n_tiles) break;
+        const int t0 = P.t_beg + tile * W;
+        const int t1 = min(t0 + W, P.t_end);
+        for (int i = threadIdx.x; i < cnt_used; i += blockDim.x) S.cnt[i] = 0;
+        for (int i = threadIdx.x; i < (W >> 5); i += blockDim.x) S.covered[i] = 0;
+        if (threadIdx.x == 0) s_nflag = 0;
+        __syncthreads();
+
+        // ---- phase 1: count
+        for (int f = 0; f < P.n_files; ++f) {
+            int2 rg = P.tile_ranges[tile * P.n_files + f];
+            for (long long r = rg.x + wid; r < rg.y; r += nwarp) walk_read<false>(P, S, f, r, t0, t1, lane);
+        }
+        __syncthreads();
+
+        // ---- phase 2: decide, reserve rows, write them in (pos, strand) order
+        int my_rows = 0;
+        for (int pidx = threadIdx.x; pidx < W; pidx += blockDim.x) {
+            int d = 0;
+            if (t0 + pidx < t1) d = decide_site(P, S.cnt, S.covered, pidx, t0 + pidx);
+            S.dec[pidx] = (uint8_t)d;
+            my_rows += (d & 1) + ((d >> 1) & 1);
+        }
+        int tile_rows_total;
+        block_exclusive_scan(my_rows, &tile_rows_total, s_scan);
+        if (threadIdx.x == 0) {
+            long long base = (long long)atomicAdd(P.row_counter, (unsigned long long)tile_rows_total);
+            if (base + tile_rows_total > P.row_cap) { atomicExch(P.err_flag, RAER_ERR_LIMIT); base = -1; }
+            s_rowbase = (int)base;
+            P.tile_rows[tile] = make_int2((int)base, base < 0 ? 0 : tile_rows_total);
+        }
+        __syncthreads();
+        const long long rowbase = s_rowbase;
+        if (rowbase >= 0 && tile_rows_total > 0) {
+            int carried = 0;
+            for (int chunk = 0; chunk < W; chunk += blockDim.x) {
+                int pidx = chunk + threadIdx.x;
+                int d = pidx < W ? S.dec[pidx] : 0;
+                int n = (d & 1) + ((d >> 1) & 1);
+                int tot;
+                int off = block_exclusive_scan(n, &tot, s_scan) + carried;
+                carried += tot;
+                if (n) {
+                    long long row = rowbase + off;
+                    int rp = -1, rm = -1;
+                    if (d & 1) { write_row(P, S.cnt, pidx, t0 + pidx, 0, row); rp = (int)row; ++row; }
+                    if (d & 2) { write_row(P, S.cnt, pidx, t0 + pidx, 1, row); rm = (int)row; }
+                    bool fl = P.want_stats && (((d & 1) && (d & 4)) || ((d & 2) && (d & 8)));
+                    if (fl) {
+                        int slot = atomicAdd(&s_nflag, 1);
+                        S.flag_pidx[slot] = (uint16_t)pidx;
+                        S.flag_rowp[slot] = ((d & 1) && (d & 4)) ? rp : -1;
+                        S.flag_rowm[slot] = ((d & 2) && (d & 8)) ? rm : -1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phases 3+4: second pass for the variant rows, S sites per round
+        const int nflag = s_nflag;
+        for (int round0 = 0; round0 < nflag; round0 += P.S) {
+            const int ns = min(P.S, nflag - round0);
+            for (int i = threadIdx.x; i < W; i += blockDim.x) S.slot_of[i] = 0xffff;
+            for (int i = threadIdx.x; i < ns * P.slot_words; i += blockDim.x) {
+                int wsl = i % P.slot_words;
+                // first-seen ordinals start at +inf, everything else at 0
+                bool is_fs = wsl >= 404 && ((wsl - 404) % 5) < 4;
+                S.cnt[i] = is_fs ? 0xffffffffu : 0u;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < ns; i += blockDim.x) S.slot_of[S.flag_pidx[round0 + i]] = (uint16_t)i;
+            __syncthreads();
+            for (int f = 0; f < P.n_files; ++f) {
+                int2 rg = P.tile_ranges[tile * P.n_files + f];
+                for (long long r = rg.x + wid; r < rg.y; r += nwarp) walk_read<true>(P, S, f, r, t0, t1, lane);
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+                const uint32_t* slot = S.cnt + (size_t)i * P.slot_words;
+                int rowp = S.flag_rowp[round0 + i], rowm = S.flag_rowm[round0 + i];
+                double sor = d_calc_sor((int)slot[400], (int)slot[401], (int)slot[402], (int)slot[403]);
+                for (int s = 0; s < 2; ++s) {
+                    long long row = s == 0 ? rowp : rowm;
+                    if (row < 0) continue;
+                    const uint32_t* hr = slot + (s * 2) * RAER_NHIST;
+                    const uint32_t* ha = slot + (s * 2 + 1) * RAER_NHIST;
+                    P.row_stats[row * 3 + 0] = d_calc_mwu_z(hr, ha);
+                    P.row_stats[row * 3 + 1] = d_calc_vdb(ha);
+                    P.row_stats[row * 3 + 2] = sor;
+                    for (int f = 0; f < P.n_files; ++f) {
+                        const uint32_t* fs = slot + 404 + (f * 2 + s) * 5;
+                        // order the (at most 4) variant bases by first-seen ordinal
+                        unsigned ord[4] = {fs[0], fs[1], fs[2], fs[3]};
+                        unsigned code = 0;
+                        int nins = 0;
+                        unsigned third = 0;
+                        for (int k = 0; k < 4; ++k) {
+                            int best = -1;
+                            for (int b = 0; b < 4; ++b)
+                                if (ord[b] != 0xffffffffu && (best < 0 || ord[b] < ord[best])) best = b;
+                            if (best < 0) break;
+                            code |= (unsigned)best << (2 * nins);
+                            if (nins == 2) third = ord[best];
+                            ord[best] = 0xffffffffu;
+                            ++nins;
+                        }
+                        unsigned alt = P.row_alt[row * P.n_files + f] & (RAER_ALT_MASK | RAER_ALT_OTHER);
+                        alt |= code << RAER_ALT_ORDER_SHIFT;
+                        alt |= (unsigned)nins << RAER_ALT_NINS_SHIFT;
+                        // kh_put resizes 4 -> 8 buckets when a put arrives with 3 keys occupied (khash.h)
+                        if (nins >= 3 && fs[4] > third + 1u) alt |= RAER_ALT_GROW;
+                        P.row_alt[row * P.n_files + f] = alt;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers (called from raer_runtime.cpp)
+// ---------------------------------------------------------------------------------------------
+extern "C" int raer_launch_overlap(const raer_read_hdr* hdr, const uint32_t* cigar, const uint8_t* seq, uint8_t* qual,
+                                   const int32_t* pair_b, long long n_pairs, int mode, cudaStream_t st) {
+    if (n_pairs <= 0) return 0;
+    int block = 128;
+    long long grid = (n_pairs + block - 1) / block;
+    k_mate_overlap<<<(unsigned)grid, block, 0, st>>>(hdr, cigar, seq, qual, pair_b, n_pairs, mode);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+extern "C" size_t raer_tile_smem_bytes(int n_files, int W, int S, int* cnt_words, int* slot_words) {
+    int sw = 404 + 10 * n_files;
+    int cw = n_files * 2 * RAER_NCLS * W;
+    if (S * sw > cw) cw = S * sw;
+    *cnt_words = cw;
+    *slot_words = sw;
+    return (size_t)cw * 4 + (W >> 5) * 4 + (size_t)W * (4 + 4 + 2 + 2 + 1) + 64;
+}
+
+extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* launches) {
+    int nl = 0;
+    if (P->n_tiles <= 0) { *launches = 0; return 0; }
+    {
+        int n = P->n_tiles * P->n_files;
+        k_tile_ranges<<<(n + 255) / 256, 256, 0, st>>>(*P);
+        ++nl;
+    }
+    size_t smem = raer_tile_smem_bytes(P->n_files, P->W, P->S, &P->cnt_words, &P->slot_words);
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(k_pileup_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return -1;
+        configured = smem;
+    }
+    int per_sm = smem > 110 * 1024 ? 1 : 2;
+    int grid = n_sm * per_sm;
+    if (grid > P->n_tiles) grid = P->n_tiles;
+    k_pileup_tiles<<<grid, RAER_BLOCK, smem, st>>>(*P);
+    ++nl;
+    *launches = nl;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}

@@ -1,0 +1,670 @@
+// raer_runtime.cu -- device context, batch transfer, kernel orchestration and the C ABI of the
+// bulk path (include/raer_b200.h). Host logic above it: raer_ingest.cpp. Kernels: raer_kernels.cu.
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "raer_dev.h"
+#include "raer_host.h"
+
+namespace raer {
+const char* last_error();
+}
+using raer::set_error;
+
+extern "C" int raer_launch_overlap(const raer_read_hdr* hdr, const uint32_t* cigar, const uint8_t* seq, uint8_t* qual,
+                                   const int32_t* pair_b, long long n_pairs, int mode, cudaStream_t st);
+extern "C" size_t raer_tile_smem_bytes(int n_files, int W, int S, int* cnt_words, int* slot_words);
+extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* launches);
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            set_error("CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__);  \
+            return RAER_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+extern "C" const char* raer_last_error(void) { return raer::last_error(); }
+extern "C" const char* raer_version(void) { return "raer_b200 0.1 (sm_100a)"; }
+extern "C" int raer_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" void* raer_pinned_alloc(size_t n, int* pinned) {
+    void* p = nullptr;
+    static int have_dev = -1;
+    if (have_dev < 0) have_dev = raer_device_count() > 0;
+    if (have_dev && cudaHostAlloc(&p, n, cudaHostAllocDefault) == cudaSuccess) { *pinned = 1; return p; }
+    if (have_dev) cudaGetLastError();
+    *pinned = 0;
+    return malloc(n);
+}
+extern "C" void raer_pinned_free(void* p, int pinned) {
+    if (!p) return;
+    if (pinned) cudaFreeHost(p);
+    else free(p);
+}
+
+// ------------------------------------------------------------------------------------- context
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        size_t want = n + n / 4 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; cap = 0; set_error("cudaMalloc(%zu) failed", want); return RAER_ERR_CUDA; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct raer_ctx {
+    int device = 0, n_sm = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6];
+    DevBuf hdr, maxend, cigar, seq, qual, pair_b, mask;
+    DevBuf tile_ranges, tile_rows, small;  // small: tile_counter(4) | pad | row_counter(8) | err(4)
+    DevBuf row_pos, row_meta, row_stats, row_counts, row_alt;
+    DevBuf ref;
+    const char* ref_ptr = nullptr;
+    int64_t ref_len = 0;
+    int ref_tid = -1;
+    // last-run info
+    int n_tiles = 0, W = 0;
+    long long row_cap = 0;
+    float ms_h2d = 0, ms_kernel = 0, ms_d2h = 0;
+    int64_t last_launches = 0;
+};
+
+extern "C" raer_ctx* raer_ctx_create(int32_t device) {
+    int n = raer_device_count();
+    if (n <= 0 || device >= n) { set_error("no usable CUDA device (the product has no CPU path)"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
+    raer_ctx* c = new raer_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->n_sm = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; set_error("stream"); return nullptr; }
+    for (auto& e : c->ev) cudaEventCreate(&e);
+    return c;
+}
+extern "C" void raer_ctx_destroy(raer_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuf* b : {&c->hdr, &c->maxend, &c->cigar, &c->seq, &c->qual, &c->pair_b, &c->mask, &c->tile_ranges, &c->tile_rows,
+                      &c->small, &c->row_pos, &c->row_meta, &c->row_stats, &c->row_counts, &c->row_alt, &c->ref})
+        b->release();
+    for (auto& e : c->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+extern "C" void* raer_ctx_stream(raer_ctx* c) { return (void*)c->stream; }
+
+extern "C" int raer_ctx_set_reference(raer_ctx* c, int32_t tid, const char* seq, int64_t len) {
+    cudaSetDevice(c->device);
+    if (len > 0) {
+        int rc = c->ref.ensure((size_t)len);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(c->ref.p, seq, (size_t)len, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    c->ref_ptr = len > 0 ? (const char*)c->ref.p : nullptr;
+    c->ref_len = len;
+    c->ref_tid = tid;
+    return RAER_OK;
+}
+extern "C" int raer_ctx_set_reference_device(raer_ctx* c, int32_t tid, const void* dseq, int64_t len) {
+    c->ref_ptr = (const char*)dseq;
+    c->ref_len = len;
+    c->ref_tid = tid;
+    return RAER_OK;
+}
+
+// choose the tile width: counters [file][strand][6][W] x 4 B must fit, leave room for 2 CTAs/SM when cheap
+static int choose_tile_width(int n_files) {
+    int budget = 200 * 1024;
+    int w = budget / (48 * n_files + 16);
+    w = std::min(w, 2048);
+    w &= ~31;
+    if (n_files <= 2) w = std::min(w, 1024);  // 2 CTAs per SM
+    return std::max(w, 32);
+}
+
+static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_batch* b, const uint32_t* d_mask,
+                      int64_t* launches) {
+    const int nf = b->n_files;
+    PlpParams P;
+    memset(&P, 0, sizeof(P));
+    P.hdr = b->hdr; P.maxend = b->maxend; P.cigar = b->cigar; P.seq = b->seq; P.qual = (uint8_t*)b->qual;
+    for (int i = 0; i <= nf; ++i) P.file_off[i] = b->file_off[i];
+    P.n_files = nf;
+    P.t_beg = b->beg; P.t_end = b->end;
+    P.W = choose_tile_width(nf);
+    long long span = (long long)b->end - b->beg;
+    P.n_tiles = span > 0 ? (int)((span + P.W - 1) / P.W) : 0;
+    P.ref = c->ref_ptr; P.ref_len = (int)std::min<int64_t>(c->ref_len, INT_MAX);
+    P.min_depth = conf->min_depth; P.min_bq = conf->min_bq; P.trim_5p = conf->trim_5p; P.trim_3p = conf->trim_3p;
+    P.indel_dist = conf->indel_dist; P.splice_dist = conf->splice_dist; P.min_overhang = conf->min_overhang;
+    P.nmer = conf->nmer; P.min_var_reads = conf->min_var_reads; P.n_mm_type = conf->n_mm_type; P.n_mm = conf->n_mm;
+    P.report_multiallelic = conf->report_multiallelic; P.want_stats = conf->want_stats;
+    P.ftrim_5p = conf->ftrim_5p; P.ftrim_3p = conf->ftrim_3p; P.min_af = conf->min_af;
+    P.any_okv = 0;
+    for (int i = 0; i < nf; ++i) {
+        P.min_mapq[i] = conf->min_mapq[i];
+        P.okv[i] = conf->only_keep_variants[i];
+        P.any_okv |= P.okv[i] != 0;
+    }
+    P.reg_beg = conf->reg_beg; P.reg_end = conf->reg_end;
+    P.site_mask = d_mask; P.mask_beg = conf->mask_beg; P.mask_bits = conf->mask_bits;
+    c->n_tiles = P.n_tiles; c->W = P.W;
+    int nl = 0;
+    int rc;
+    if ((rc = c->small.ensure(64))) return rc;
+    CK(cudaMemsetAsync(c->small.p, 0, 64, c->stream));
+    P.tile_counter = (unsigned int*)c->small.p;
+    P.row_counter = (unsigned long long*)((char*)c->small.p + 8);
+    P.err_flag = (int*)((char*)c->small.p + 16);
+    if (P.n_tiles > 0) {
+        if ((rc = c->tile_ranges.ensure((size_t)P.n_tiles * nf * sizeof(int2)))) return rc;
+        if ((rc = c->tile_rows.ensure((size_t)P.n_tiles * sizeof(int2)))) return rc;
+        long long cap = 2 * span + 64;
+        if ((rc = c->row_pos.ensure((size_t)cap * 4))) return rc;
+        if ((rc = c->row_meta.ensure((size_t)cap * 4))) return rc;
+        if ((rc = c->row_stats.ensure((size_t)cap * 24))) return rc;
+        if ((rc = c->row_counts.ensure((size_t)cap * nf * 32))) return rc;
+        if ((rc = c->row_alt.ensure((size_t)cap * nf * 4))) return rc;
+        c->row_cap = cap;
+        P.row_cap = cap;
+        P.tile_ranges = (int2*)c->tile_ranges.p; P.tile_rows = (int2*)c->tile_rows.p;
+        P.row_pos = (int*)c->row_pos.p; P.row_meta = (unsigned*)c->row_meta.p; P.row_stats = (double*)c->row_stats.p;
+        P.row_counts = (int*)c->row_counts.p; P.row_alt = (unsigned*)c->row_alt.p;
+        // second-pass slots: reuse the counter region, at least 32 sites per round
+        int cw, sw;
+        P.S = 0;
+        raer_tile_smem_bytes(nf, P.W, 0, &cw, &sw);
+        P.S = std::max(32, cw / sw);
+        if (P.S > 4096) P.S = 4096;
+        if (conf->remove_overlaps && b->n_pairs > 0) {
+            int r = raer_launch_overlap(b->hdr, b->cigar, b->seq, (uint8_t*)b->qual, b->pair_b, b->n_pairs,
+                                        conf->remove_overlaps, c->stream);
+            if (r < 0) { set_error("overlap kernel launch failed"); return RAER_ERR_CUDA; }
+            nl += r;
+        }
+        int tl = 0;
+        if (raer_launch_tiles(&P, c->n_sm, c->stream, &tl) < 0) {
+            set_error("tile kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return RAER_ERR_CUDA;
+        }
+        nl += tl;
+    }
+    if (launches) *launches += nl;
+    return RAER_OK;
+}
+
+extern "C" int raer_batch_pileup_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_batch* b,
+                                        int64_t* n_rows, int64_t* launches) {
+    cudaSetDevice(c->device);
+    if (conf->n_files != b->n_files || b->n_files > RAER_MAX_FILES) { set_error("bad file count"); return RAER_ERR_ARG; }
+    int rc = run_device(c, conf, b, conf->site_mask, launches);
+    if (rc) return rc;
+    if (n_rows) {
+        struct { unsigned tc, pad; unsigned long long rows; int err; } s;
+        CK(cudaMemcpyAsync(&s, c->small.p, sizeof(s), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (s.err) { set_error("device reported error %d", s.err); return s.err; }
+        *n_rows = (int64_t)s.rows;
+    }
+    return RAER_OK;
+}
+
+extern "C" void raer_rows_free(raer_rows* r) {
+    if (!r) return;
+    free(r->pos); free(r->meta); free(r->stats); free(r->counts); free(r->altcode);
+    memset(r, 0, sizeof(*r));
+}
+
+// download the rows of the last run in tile order (host-side ordered concatenation)
+static int fetch_rows(raer_ctx* c, int nf, raer_rows* out) {
+    struct { unsigned tc, pad; unsigned long long rows; int err; } s;
+    CK(cudaMemcpyAsync(&s, c->small.p, sizeof(s), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (s.err) {
+        set_error(s.err == RAER_ERR_MD ? "inconsistent MD tag with max_mismatch_type" : "device reported error %d", s.err);
+        return s.err;
+    }
+    memset(out, 0, sizeof(*out));
+    out->n_files = nf;
+    size_t n = (size_t)s.rows;
+    out->n_rows = (int64_t)n;
+    if (n == 0 || c->n_tiles == 0) return RAER_OK;
+    std::vector<int2> tr(c->n_tiles);
+    std::vector<int> pos(n);
+    std::vector<unsigned> meta(n), alt(n * nf);
+    std::vector<double> st(n * 3);
+    std::vector<int> cnt(n * nf * 8);
+    CK(cudaMemcpyAsync(tr.data(), c->tile_rows.p, sizeof(int2) * c->n_tiles, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(pos.data(), c->row_pos.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(meta.data(), c->row_meta.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(st.data(), c->row_stats.p, n * 24, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(cnt.data(), c->row_counts.p, n * nf * 32, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(alt.data(), c->row_alt.p, n * nf * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    out->pos = (int32_t*)malloc(n * 4);
+    out->meta = (uint32_t*)malloc(n * 4);
+    out->stats = (double*)malloc(n * 24);
+    out->counts = (int32_t*)malloc(n * nf * 32);
+    out->altcode = (uint32_t*)malloc(n * nf * 4);
+    size_t o = 0;
+    for (int t = 0; t < c->n_tiles; ++t) {
+        int base = tr[t].x, k = tr[t].y;
+        if (k <= 0) continue;
+        memcpy(out->pos + o, pos.data() + base, (size_t)k * 4);
+        memcpy(out->meta + o, meta.data() + base, (size_t)k * 4);
+        memcpy(out->stats + o * 3, st.data() + (size_t)base * 3, (size_t)k * 24);
+        memcpy(out->counts + o * nf * 8, cnt.data() + (size_t)base * nf * 8, (size_t)k * nf * 32);
+        memcpy(out->altcode + o * nf, alt.data() + (size_t)base * nf, (size_t)k * nf * 4);
+        o += k;
+    }
+    if (o != n) { set_error("row bookkeeping mismatch (%zu vs %zu)", o, n); return RAER_ERR; }
+    return RAER_OK;
+}
+
+extern "C" int raer_batch_pileup_host(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_batch* hb, raer_rows* out) {
+    cudaSetDevice(c->device);
+    const int nf = hb->n_files;
+    if (conf->n_files != nf || nf > RAER_MAX_FILES || nf < 1) { set_error("bad file count"); return RAER_ERR_ARG; }
+    memset(out, 0, sizeof(*out));
+    out->n_files = nf;
+    if (hb->n_reads == 0 || hb->end <= hb->beg) return RAER_OK;
+    int rc;
+    size_t nr = (size_t)hb->n_reads;
+    if ((rc = c->hdr.ensure(nr * sizeof(raer_read_hdr)))) return rc;
+    if ((rc = c->maxend.ensure(nr * 4))) return rc;
+    if ((rc = c->cigar.ensure((size_t)hb->n_cigar_words * 4 + 16))) return rc;
+    if ((rc = c->seq.ensure((size_t)hb->n_sq_bytes + 16))) return rc;
+    if ((rc = c->qual.ensure((size_t)hb->n_sq_bytes * 2 + 16))) return rc;
+    if ((rc = c->pair_b.ensure((size_t)hb->n_pairs * 4 + 16))) return rc;
+    cudaEventRecord(c->ev[0], c->stream);
+    CK(cudaMemcpyAsync(c->hdr.p, hb->hdr, nr * sizeof(raer_read_hdr), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->maxend.p, hb->maxend, nr * 4, cudaMemcpyHostToDevice, c->stream));
+    if (hb->n_cigar_words) CK(cudaMemcpyAsync(c->cigar.p, hb->cigar, (size_t)hb->n_cigar_words * 4, cudaMemcpyHostToDevice, c->stream));
+    if (hb->n_sq_bytes) {
+        CK(cudaMemcpyAsync(c->seq.p, hb->seq, (size_t)hb->n_sq_bytes, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->qual.p, hb->qual, (size_t)hb->n_sq_bytes * 2, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (hb->n_pairs) CK(cudaMemcpyAsync(c->pair_b.p, hb->pair_b, (size_t)hb->n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+    const uint32_t* d_mask = nullptr;
+    if (conf->site_mask) {
+        size_t words = ((size_t)conf->mask_bits + 31) / 32;
+        if ((rc = c->mask.ensure(words * 4 + 16))) return rc;
+        CK(cudaMemcpyAsync(c->mask.p, conf->site_mask, words * 4, cudaMemcpyHostToDevice, c->stream));
+        d_mask = (const uint32_t*)c->mask.p;
+    }
+    cudaEventRecord(c->ev[1], c->stream);
+    raer_read_batch db = *hb;
+    db.hdr = (const raer_read_hdr*)c->hdr.p; db.maxend = (const int32_t*)c->maxend.p;
+    db.cigar = (const uint32_t*)c->cigar.p; db.seq = (const uint8_t*)c->seq.p; db.qual = (const uint8_t*)c->qual.p;
+    db.pair_b = (const int32_t*)c->pair_b.p;
+    int64_t nl = 0;
+    rc = run_device(c, conf, &db, d_mask, &nl);
+    if (rc) return rc;
+    c->last_launches = nl;
+    cudaEventRecord(c->ev[2], c->stream);
+    rc = fetch_rows(c, nf, out);
+    cudaEventRecord(c->ev[3], c->stream);
+    cudaEventSynchronize(c->ev[3]);
+    cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->ms_kernel, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]);
+    return rc;
+}
+
+extern "C" void raer_ctx_last_timing(raer_ctx* c, double* h2d_s, double* kernel_s, double* d2h_s) {
+    *h2d_s = c->ms_h2d * 1e-3; *kernel_s = c->ms_kernel * 1e-3; *d2h_s = c->ms_d2h * 1e-3;
+}
+
+extern "C" int64_t raer_batch_algorithmic_bytes(const raer_read_batch* b, int64_t n_rows, int64_t ref_bases) {
+    // 32 B/record + 4 B/CIGAR op + 0.5 B/base (seq) + 1 B/base (qual)
+    // + 1 B/reference base + (40 B x files + 24 B) per output row
+    int64_t bases = b->n_sq_bytes * 2;
+    return 32 * b->n_reads + 4 * b->n_cigar_words + bases / 2 + bases + ref_bases + n_rows * (40LL * b->n_files + 24);
+}
+
+// ------------------------------------------------------------------------------------- ALT strings
+// Simulates the 4/8 bucket khash of single-character keys the reference walks to print ALT
+// (src/plp.c:193-215; htslib khash.h: home = key & mask, probe i += ++step). State per (file, strand).
+extern "C" void raer_altcode_to_string(uint32_t code, int ref_char, int32_t* buckets, char* out) {
+    (void)ref_char;
+    static const char L[4] = {'A', 'C', 'G', 'T'};
+    unsigned mask = code & RAER_ALT_MASK;
+    int nins = (code >> RAER_ALT_NINS_SHIFT) & 7;
+    if (*buckets != 8) *buckets = 4;
+    if (code & RAER_ALT_GROW) *buckets = 8;
+    int nb = *buckets;
+    char slot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (nins == 0) {
+        // rows without a second pass (want_stats == 0) or a single surviving base: derive order from the mask
+        for (int b = 0; b < 4; ++b)
+            if (mask & (1u << b)) { ++nins; }
+        int k = 0;
+        unsigned order = 0;
+        for (int b = 0; b < 4; ++b)
+            if (mask & (1u << b)) order |= (unsigned)b << (2 * k++);
+        code = (code & ~(0xffu << RAER_ALT_ORDER_SHIFT)) | (order << RAER_ALT_ORDER_SHIFT);
+    }
+    for (int k = 0; k < nins; ++k) {
+        int b = (code >> (RAER_ALT_ORDER_SHIFT + 2 * k)) & 3;
+        unsigned i = (unsigned)L[b] & (nb - 1), step = 0;
+        while (slot[i]) i = (i + (++step)) & (nb - 1);
+        slot[i] = L[b];
+    }
+    int z = 0;
+    for (int i = 0; i < nb; ++i) {
+        if (!slot[i]) continue;
+        int b = slot[i] == 'A' ? 0 : slot[i] == 'C' ? 1 : slot[i] == 'G' ? 2 : 3;
+        if (!(mask & (1u << b))) continue;  // pruned by min_allelic_freq after insertion
+        if (z) out[z++] = ',';
+        out[z++] = slot[i];
+    }
+    if (z == 0) { out[0] = '-'; z = 1; }
+    out[z] = 0;
+}
+
+// ------------------------------------------------------------------------------------- .Call(".pileup")
+struct ResultSink {
+    raer_pileup_result* r;
+    int64_t cap = 0;
+    std::vector<char> alt;       // [file][cap][12]
+    std::vector<int32_t> counts; // [file][cap][8]
+};
+
+static void sink_reserve(ResultSink& s, int64_t need) {
+    raer_pileup_result* r = s.r;
+    if (need <= s.cap) return;
+    int64_t ncap = std::max<int64_t>(need + need / 2, 1 << 16);
+    r->tid = (int32_t*)realloc(r->tid, ncap * 4);
+    r->pos = (int32_t*)realloc(r->pos, ncap * 4);
+    r->strand = (char*)realloc(r->strand, ncap);
+    r->ref = (char*)realloc(r->ref, ncap);
+    r->rpbz = (double*)realloc(r->rpbz, ncap * 8);
+    r->vdb = (double*)realloc(r->vdb, ncap * 8);
+    r->sor = (double*)realloc(r->sor, ncap * 8);
+    char* nalt = (char*)calloc((size_t)r->nbam * ncap, 12);
+    int32_t* ncnt = (int32_t*)calloc((size_t)r->nbam * ncap * 8, 4);
+    for (int f = 0; f < r->nbam && r->nrows; ++f) {
+        memcpy(nalt + (size_t)f * ncap * 12, r->alt + (size_t)f * s.cap * 12, (size_t)r->nrows * 12);
+        memcpy(ncnt + (size_t)f * ncap * 8, r->counts + (size_t)f * s.cap * 8, (size_t)r->nrows * 32);
+    }
+    free(r->alt); free(r->counts);
+    r->alt = nalt; r->counts = ncnt;
+    s.cap = ncap;
+}
+
+extern "C" void raer_pileup_result_free(raer_pileup_result* r) {
+    if (!r) return;
+    free(r->tid); free(r->pos); free(r->strand); free(r->ref); free(r->rpbz); free(r->vdb); free(r->sor);
+    free(r->alt); free(r->counts);
+    if (r->target_names) {
+        for (int i = 0; i < r->n_targets; ++i) free(r->target_names[i]);
+        free(r->target_names);
+    }
+    memset(r, 0, sizeof(*r));
+}
+
+extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
+    double t_start = raer::now_seconds();
+    memset(out, 0, sizeof(*out));
+    // check_plp_args (src/plp.c:998-1055)
+    if (!a || a->nbam < 1 || !a->bampaths || !a->fapath || !a->libtype || !a->only_keep_variants || !a->min_mapq) {
+        set_error("invalid arguments"); return RAER_ERR_ARG;
+    }
+    if (a->nbam > RAER_MAX_FILES) { set_error("at most %d BAM files per call", RAER_MAX_FILES); return RAER_ERR_LIMIT; }
+    if (a->umi_tag) { set_error("umi_tag in pileup_sites is not implemented on the device path yet"); return RAER_ERR_LIMIT; }
+    if (raer_device_count() <= 0) { set_error("no usable CUDA device (the product has no CPU path)"); return RAER_ERR_NO_DEVICE; }
+    const int nf = a->nbam;
+    out->nbam = nf;
+
+    raer::RegionIndex ridx;
+    bool has_ridx = a->n_regions > 0;
+    if (has_ridx) {
+        std::vector<int32_t> b0(a->n_regions), e0(a->n_regions);
+        for (int i = 0; i < a->n_regions; ++i) { b0[i] = a->reg_start[i] - 1; e0[i] = a->reg_end[i] - 1; }
+        ridx.build(a->n_regions, a->reg_seqnames, b0.data(), e0.data());
+    }
+    raer::IngestConf ic;
+    ic.n_files = nf;
+    ic.keep_flag[0] = (uint32_t)a->int_args[12];
+    ic.keep_flag[1] = (uint32_t)a->int_args[13];
+    ic.max_depth = a->int_args[0];
+    ic.min_global_mq = 0;
+    if (a->min_mapq[0] > 0) {  // src/plp.c:1124-1133
+        int mq = a->min_mapq[0];
+        for (int i = 0; i < nf; ++i) mq = std::min(mq, (int)a->min_mapq[i]);
+        ic.min_global_mq = mq;
+    }
+    ic.rq_pct = a->dbl_args[3];
+    ic.rq_minq = (int)a->dbl_args[4];
+    ic.remove_overlaps = a->lgl_args[1] ? (a->overlap_mode == 2 ? 2 : 1) : 0;
+    ic.n_mm_type = a->int_args[10];
+    ic.n_mm = a->int_args[11];
+    ic.min_overhang = a->int_args[7];
+    ic.libtype.assign(a->libtype, a->libtype + nf);
+    for (int lt : ic.libtype)
+        if (lt < 0 || lt > 2) { set_error("invert read orientation failure"); return RAER_ERR; }
+    ic.regidx = has_ridx ? &ridx : nullptr;
+
+    raer::Ingest ing(ic);
+    if (!ing.open(a->bampaths, a->indexes, a->host_threads, a->region)) return RAER_ERR_IO;
+
+    raer_ctx* ctx = raer_ctx_create(a->device);
+    if (!ctx) return RAER_ERR_NO_DEVICE;
+
+    raer_bulk_conf bc;
+    memset(&bc, 0, sizeof(bc));
+    bc.n_files = nf;
+    bc.min_depth = a->int_args[1]; bc.min_bq = a->int_args[2]; bc.trim_5p = a->int_args[3]; bc.trim_3p = a->int_args[4];
+    bc.indel_dist = a->int_args[5]; bc.splice_dist = a->int_args[6]; bc.min_overhang = a->int_args[7];
+    bc.nmer = a->int_args[8]; bc.min_var_reads = a->int_args[9]; bc.n_mm_type = a->int_args[10]; bc.n_mm = a->int_args[11];
+    bc.ftrim_5p = a->dbl_args[0]; bc.ftrim_3p = a->dbl_args[1]; bc.min_af = a->dbl_args[2];
+    bc.report_multiallelic = a->lgl_args[0];
+    bc.remove_overlaps = ic.remove_overlaps;
+    bc.want_stats = 1;
+    for (int i = 0; i < nf; ++i) { bc.min_mapq[i] = a->min_mapq[i]; bc.only_keep_variants[i] = a->only_keep_variants[i]; }
+
+    const std::vector<std::string>& names = ing.names();
+    out->n_targets = (int)names.size();
+    out->target_names = (char**)calloc(names.size() ? names.size() : 1, sizeof(char*));
+    for (size_t i = 0; i < names.size(); ++i) out->target_names[i] = strdup(names[i].c_str());
+
+    ResultSink sink;
+    sink.r = out;
+    std::vector<int32_t> kh(nf * 2, 4);  // khash bucket count of every (file, strand) variant table
+    raer::PackedBatch pb;
+    std::vector<uint32_t> mask;
+    int rc = RAER_OK;
+    int tid;
+    int contig_no = 0;
+    while (rc == RAER_OK && (tid = ing.next_contig()) >= 0) {
+        bool mine = a->shard_count <= 1 || (contig_no % a->shard_count) == a->shard_index;
+        ++contig_no;
+        std::string seq;
+        bool have_ref = raer::fasta_fetch(a->fapath, names[tid], seq);
+        if (!have_ref) seq.clear();  // reference: every site reads as 'N' and is skipped
+        if (mine) {
+            rc = raer_ctx_set_reference(ctx, tid, seq.data(), (int64_t)seq.size());
+            if (rc) break;
+        }
+        const raer::RegionIndex::Chr* rchr = has_ridx ? ridx.find(names[tid]) : nullptr;
+        while (rc == RAER_OK && ing.next_batch(pb)) {
+            if (!mine || pb.b.n_reads == 0 || pb.b.end <= pb.b.beg) continue;
+            if (has_ridx && !rchr) continue;
+            bc.reg_beg = ing.reg_tid() >= 0 ? ing.reg_beg() : 0;
+            bc.reg_end = ing.reg_tid() >= 0 ? ing.reg_end() : INT_MAX;
+            bc.site_mask = nullptr;
+            if (has_ridx) {  // bitmap of eligible positions inside the batch window
+                int wb = pb.b.beg, we = pb.b.end;
+                size_t words = ((size_t)(we - wb) + 31) / 32;
+                mask.assign(words, 0);
+                size_t k = std::lower_bound(rchr->maxend.begin(), rchr->maxend.end(), wb) - rchr->maxend.begin();
+                for (; k < rchr->beg.size() && rchr->beg[k] < we; ++k) {
+                    int lo = std::max(rchr->beg[k], wb), hi = std::min(rchr->end[k] + 1, we);
+                    for (int p = lo; p < hi; ++p) mask[(p - wb) >> 5] |= 1u << ((p - wb) & 31);
+                }
+                bc.site_mask = mask.data();
+                bc.mask_beg = wb;
+                bc.mask_bits = we - wb;
+            }
+            raer_rows rows;
+            rc = raer_batch_pileup_host(ctx, &bc, &pb.b, &rows);
+            if (rc) break;
+            out->gpu_launches += ctx->last_launches;
+            out->t_h2d += ctx->ms_h2d * 1e-3; out->t_kernel += ctx->ms_kernel * 1e-3; out->t_d2h += ctx->ms_d2h * 1e-3;
+            sink_reserve(sink, out->nrows + rows.n_rows);
+            for (int64_t i = 0; i < rows.n_rows; ++i) {
+                int64_t o = out->nrows + i;
+                int s = rows.meta[i] & 1;
+                out->tid[o] = tid;
+                out->pos[o] = rows.pos[i] + 1;
+                out->strand[o] = s ? '-' : '+';
+                out->ref[o] = (char)((rows.meta[i] >> 8) & 0xff);
+                out->rpbz[o] = rows.stats[i * 3];
+                out->vdb[o] = rows.stats[i * 3 + 1];
+                out->sor[o] = rows.stats[i * 3 + 2];
+                for (int f = 0; f < nf; ++f) {
+                    memcpy(out->counts + ((size_t)f * sink.cap + o) * 8, rows.counts + ((size_t)i * nf + f) * 8, 32);
+                    raer_altcode_to_string(rows.altcode[i * nf + f], out->ref[o], &kh[f * 2 + s],
+                                           out->alt + ((size_t)f * sink.cap + o) * 12);
+                }
+            }
+            out->nrows += rows.n_rows;
+            raer_rows_free(&rows);
+        }
+    }
+    // compact the [file][row] stride to nrows
+    if (sink.cap != out->nrows && out->nrows > 0) {
+        for (int f = 1; f < nf; ++f) {
+            memmove(out->alt + (size_t)f * out->nrows * 12, out->alt + (size_t)f * sink.cap * 12, (size_t)out->nrows * 12);
+            memmove(out->counts + (size_t)f * out->nrows * 8, out->counts + (size_t)f * sink.cap * 8, (size_t)out->nrows * 32);
+        }
+    }
+    out->t_decode = ing.decode_seconds();
+    out->t_pack = ing.pack_seconds();
+    out->n_records = ing.records();
+    out->n_aligned_bases = ing.aligned_bases();
+    raer_ctx_destroy(ctx);
+    out->t_total = raer::now_seconds() - t_start;
+    if (rc != RAER_OK) {
+        raer_pileup_result_free(out);
+        return rc;
+    }
+    if (raer::last_error()[0] && ing.records() == 0 && false) return RAER_ERR_IO;
+    return RAER_OK;
+}
+
+// Host-only probe of the ingest (no device needed): streams the BAMs exactly like raer_pileup() and
+// reports what would be handed to the kernels. out[0..7] = kept reads (summed over batches, halo
+// reads counted once per batch), mate pairs, CIGAR words, packed sequence bytes, batches, aligned
+// bases of all mapped records, records read, distinct kept reads.
+extern "C" int raer_ingest_summary(const raer_pileup_args* a, int64_t target_reads, int64_t* out) {
+    memset(out, 0, 8 * sizeof(int64_t));
+    if (!a || a->nbam < 1 || a->nbam > RAER_MAX_FILES) return RAER_ERR_ARG;
+    const int nf = a->nbam;
+    raer::RegionIndex ridx;
+    bool has_ridx = a->n_regions > 0;
+    if (has_ridx) {
+        std::vector<int32_t> b0(a->n_regions), e0(a->n_regions);
+        for (int i = 0; i < a->n_regions; ++i) { b0[i] = a->reg_start[i] - 1; e0[i] = a->reg_end[i] - 1; }
+        ridx.build(a->n_regions, a->reg_seqnames, b0.data(), e0.data());
+    }
+    raer::IngestConf ic;
+    ic.n_files = nf;
+    ic.keep_flag[0] = (uint32_t)a->int_args[12];
+    ic.keep_flag[1] = (uint32_t)a->int_args[13];
+    ic.max_depth = a->int_args[0];
+    if (a->min_mapq[0] > 0) {
+        int mq = a->min_mapq[0];
+        for (int i = 0; i < nf; ++i) mq = std::min(mq, (int)a->min_mapq[i]);
+        ic.min_global_mq = mq;
+    }
+    ic.rq_pct = a->dbl_args[3];
+    ic.rq_minq = (int)a->dbl_args[4];
+    ic.remove_overlaps = a->lgl_args[1] ? (a->overlap_mode == 2 ? 2 : 1) : 0;
+    ic.n_mm_type = a->int_args[10];
+    ic.n_mm = a->int_args[11];
+    ic.min_overhang = a->int_args[7];
+    ic.libtype.assign(a->libtype, a->libtype + nf);
+    ic.regidx = has_ridx ? &ridx : nullptr;
+    if (target_reads > 0) ic.target_reads = target_reads;
+    raer::Ingest ing(ic);
+    if (!ing.open(a->bampaths, a->indexes, a->host_threads, a->region)) return RAER_ERR_IO;
+    raer::PackedBatch pb;
+    int prev_boundary = 0;
+    while (ing.next_contig() >= 0) {
+        prev_boundary = INT_MIN;
+        while (ing.next_batch(pb)) {
+            out[0] += pb.b.n_reads;
+            out[1] += pb.b.n_pairs;
+            out[2] += pb.b.n_cigar_words;
+            out[3] += pb.b.n_sq_bytes;
+            out[4] += 1;
+            for (int64_t i = 0; i < pb.b.n_reads; ++i)
+                if (pb.hdr[i].pos >= prev_boundary) out[7] += 1;  // first appearance of the read
+            if (pb.b.n_reads) {
+                int mx = INT_MIN;
+                for (int64_t i = 0; i < pb.b.n_reads; ++i) mx = std::max(mx, (int)pb.hdr[i].pos);
+                prev_boundary = mx + 1 > prev_boundary ? mx + 1 : prev_boundary;
+            }
+        }
+    }
+    out[5] = ing.aligned_bases();
+    out[6] = ing.records();
+    return RAER_OK;
+}
+
+// ------------------------------------------------------------------------------------- misc .Call entries
+extern "C" int raer_get_region(const char* region, char* chrom, int32_t chrom_cap, int32_t* beg, int32_t* end) {
+    if (!region || !chrom || chrom_cap < 1) return RAER_ERR_ARG;
+    int b, e;
+    int nl = raer::parse_region(region, &b, &e);
+    if (nl < 0) { set_error("could not parse region:%s", region); return RAER_ERR_ARG; }
+    if (nl >= chrom_cap) nl = chrom_cap - 1;
+    memcpy(chrom, region, nl);
+    chrom[nl] = 0;
+    *beg = b;
+    *end = e;
+    return RAER_OK;
+}
+
+// Fisher exact test, two-sided p-value as htslib kt_fisher_exact reports it (sum of the
+// probabilities of all tables no more likely than the observed one; hypergeometric via lgamma).
+static double lbinom(int n, int k) { return lgamma(n + 1.0) - lgamma(k + 1.0) - lgamma(n - k + 1.0); }
+static double hyper(int n11, int n1_, int n_1, int n) { return exp(lbinom(n1_, n11) + lbinom(n - n1_, n_1 - n11) - lbinom(n, n_1)); }
+extern "C" int raer_fisher_exact(const int32_t* mat, int32_t ncol, double* pvalue) {
+    for (int j = 0; j < ncol; ++j) {
+        int n11 = mat[4 * j], n12 = mat[4 * j + 1], n21 = mat[4 * j + 2], n22 = mat[4 * j + 3];
+        int n1_ = n11 + n12, n_1 = n11 + n21, n = n11 + n12 + n21 + n22;
+        int lo = std::max(0, n1_ + n_1 - n), hi = std::min(n1_, n_1);
+        if (lo == hi) { pvalue[j] = 1.0; continue; }
+        double q = hyper(n11, n1_, n_1, n), two = 0;
+        for (int i = lo; i <= hi; ++i) {
+            double p = hyper(i, n1_, n_1, n);
+            if (p < q * (1 + 1e-7)) two += p;  // htslib uses a relative slack when comparing table probabilities
+        }
+        pvalue[j] = two > 1 ? 1.0 : two;
+    }
+    return RAER_OK;
+}
