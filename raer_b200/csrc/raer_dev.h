@@ -14,10 +14,13 @@
 
 // ALT code layout (uint32 per row per file), decoded by raer_altcode_to_string()
 #define RAER_ALT_MASK 0x0fu        // bit c: variant base c in {A,C,G,T} survives min_allelic_freq pruning
-#define RAER_ALT_OTHER 0x10u       // a non-ACGT read base was counted as variant
-#define RAER_ALT_ORDER_SHIFT 8     // 4 x 2 bits: variant bases in first-seen (BAM) order
-#define RAER_ALT_NINS_SHIFT 16     // 3 bits: number of distinct variant bases inserted
-#define RAER_ALT_GROW 0x80000u     // the puts at this site grew the khash from 4 to 8 buckets
+#define RAER_ALT_OTHER 0x10u       // a non-ACGT (IUPAC) read base was counted as variant and survives pruning
+#define RAER_ALT_NINS_SHIFT 5      // 3 bits: number of distinct variant keys inserted (ACGT + one IUPAC key)
+#define RAER_ALT_ORDER_SHIFT 8     // 5 x 3 bits: keys (0..3 = ACGT, 4 = the IUPAC key) in first-seen (BAM) order
+#define RAER_ALT_GROW 0x800000u    // the puts at this site grew the khash from 4 to 8 buckets
+#define RAER_ALT_OCODE_SHIFT 24    // 4 bits: nt16 code of the IUPAC key (complemented on the minus strand)
+#define RAER_ALT_OAMBIG 0x10000000u // more than one distinct IUPAC key at the site: ALT shows the smallest code only
+#define RAER_SLOT_FS 8             // words per (file, strand) in a second-pass slot
 
 struct PlpParams {
     // read batch (device pointers)

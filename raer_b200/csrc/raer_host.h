@@ -101,6 +101,7 @@ struct HostRead {
     raer_read_hdr h;   // cigar_off / sq_off relative to the owning file pool
     int64_t ordinal;   // arrival index among kept reads of the file
     int64_t mate_ord;  // ordinal of the earlier mate or -1
+    int32_t keep_end;  // the read stays in the pending window until this position (its own end or its mate's)
     int32_t cb;
     uint32_t umi;
 };

@@ -619,7 +619,7 @@ bool Ingest::parse_one(int fi) {
         H.h.n_cigar = (uint16_t)r.n_cigar;
         H.h.mate = -1;
         H.mate_ord = -1;
-        H.ordinal = F.next_ordinal++;
+        H.keep_end = H.h.end;
         H.cb = cbcol;
         uint8_t bits = 0;
         {  // invert_read_orientation
@@ -649,6 +649,7 @@ bool Ingest::parse_one(int fi) {
             F.prev_pos = r.pos;
             continue;
         }
+        H.ordinal = F.next_ordinal++;
         if (conf_.remove_overlaps) {
             // overlap_push
             bool eligible = !(r.flag & 8) && (r.flag & 2);
@@ -716,6 +717,13 @@ bool Ingest::parse_ahead(int fi, size_t want) {
         // qualities live at 2 * sq_off: pad odd lengths
         F.qual.insert(F.qual.end(), F.look_qual.begin(), F.look_qual.end());
         if (F.look_qual.size() & 1) F.qual.push_back(0);
+        if (H.mate_ord >= 0 && F.front < F.reads.size()) {
+            // htslib's overlap pass can rewrite qualities of the later mate far beyond the earlier mate's
+            // end (deletion catch-up across a ref-skip), so the earlier mate must stay packed with it
+            int64_t k = (int64_t)F.front + (H.mate_ord - F.reads[F.front].ordinal);
+            if (k >= (int64_t)F.front && k < (int64_t)F.reads.size())
+                F.reads[k].keep_end = std::max(F.reads[k].keep_end, (int32_t)H.h.end);
+        }
         F.reads.push_back(H);
         F.have_look = false;
     }
@@ -739,7 +747,7 @@ int Ingest::next_contig() {
 bool Ingest::next_batch(PackedBatch& out) {
     if (cur_tid_ < 0) return false;
     const int nf = conf_.n_files;
-    size_t want = (size_t)std::max<int64_t>(1024, conf_.target_reads / nf);
+    size_t want = (size_t)std::max<int64_t>(16, conf_.target_reads / nf);
     int boundary;
     while (true) {
         boundary = INT_MAX;
@@ -844,7 +852,7 @@ bool Ingest::next_batch(PackedBatch& out) {
     win_beg_ = boundary;
     for (int i = 0; i < nf; ++i) {
         FilePending& F = *files_[i];
-        while (F.front < upto[i] && F.reads[F.front].h.end <= boundary) ++F.front;
+        while (F.front < upto[i] && F.reads[F.front].keep_end <= boundary) ++F.front;
         if (F.front == F.reads.size()) {
             F.reads.clear(); F.front = 0; F.cigar.clear(); F.seq.clear(); F.qual.clear();
         } else if (F.front > (1u << 16) && F.front * 2 > F.reads.size()) {

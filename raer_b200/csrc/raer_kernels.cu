@@ -604,8 +604,16 @@ __device__ void walk_read(const PlpParams& P, const TileSmem& S, int f, long lon
                     atomicAdd(&slot[(s * 2 + (isref ? 0 : 1)) * RAER_NHIST + rpos], 1u);
                     if (!isref) {
                         int cb = (c.invert && cls < 4) ? 3 - cls : cls;
-                        uint32_t* fs = slot + 404 + (f * 2 + s) * 5;
-                        if (cb < 4) atomicMin(&fs[cb], (unsigned)ordinal);
+                        uint32_t* fs = slot + 404 + (f * 2 + s) * RAER_SLOT_FS;
+                        if (cb < 4) {
+                            atomicMin(&fs[cb], (unsigned)ordinal);
+                        } else {
+                            // IUPAC key: complement of an nt16 code is its 4-bit reversal
+                            unsigned oc = c.invert ? (__brev((unsigned)code) >> 28) : (unsigned)code;
+                            atomicMin(&fs[5], (unsigned)ordinal);
+                            atomicMin(&fs[6], oc);
+                            atomicMax(&fs[7], oc);
+                        }
                         atomicMax(&fs[4], (unsigned)ordinal + 1u);  // last variant read (ordinal + 1; 0 = none)
                     }
                 }
@@ -738,8 +746,9 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
             for (int i = threadIdx.x; i < W; i += blockDim.x) S.slot_of[i] = 0xffff;
             for (int i = threadIdx.x; i < ns * P.slot_words; i += blockDim.x) {
                 int wsl = i % P.slot_words;
-                // first-seen ordinals start at +inf, everything else at 0
-                bool is_fs = wsl >= 404 && ((wsl - 404) % 5) < 4;
+                // first-seen ordinals (and the minimum IUPAC code) start at +inf, everything else at 0
+                int fw = (wsl - 404) % RAER_SLOT_FS;
+                bool is_fs = wsl >= 404 && (fw < 4 || fw == 5 || fw == 6);
                 S.cnt[i] = is_fs ? 0xffffffffu : 0u;
             }
             __syncthreads();
@@ -763,18 +772,18 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
                     P.row_stats[row * 3 + 1] = d_calc_vdb(ha);
                     P.row_stats[row * 3 + 2] = sor;
                     for (int f = 0; f < P.n_files; ++f) {
-                        const uint32_t* fs = slot + 404 + (f * 2 + s) * 5;
-                        // order the (at most 4) variant bases by first-seen ordinal
-                        unsigned ord[4] = {fs[0], fs[1], fs[2], fs[3]};
+                        const uint32_t* fs = slot + 404 + (f * 2 + s) * RAER_SLOT_FS;
+                        // order the (at most 5) variant keys by first-seen ordinal: 0..3 = ACGT, 4 = IUPAC key
+                        unsigned ord[5] = {fs[0], fs[1], fs[2], fs[3], fs[5]};
                         unsigned code = 0;
                         int nins = 0;
                         unsigned third = 0;
-                        for (int k = 0; k < 4; ++k) {
+                        for (int k = 0; k < 5; ++k) {
                             int best = -1;
-                            for (int b = 0; b < 4; ++b)
+                            for (int b = 0; b < 5; ++b)
                                 if (ord[b] != 0xffffffffu && (best < 0 || ord[b] < ord[best])) best = b;
                             if (best < 0) break;
-                            code |= (unsigned)best << (2 * nins);
+                            code |= (unsigned)best << (3 * nins);
                             if (nins == 2) third = ord[best];
                             ord[best] = 0xffffffffu;
                             ++nins;
@@ -784,6 +793,10 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
                         alt |= (unsigned)nins << RAER_ALT_NINS_SHIFT;
                         // kh_put resizes 4 -> 8 buckets when a put arrives with 3 keys occupied (khash.h)
                         if (nins >= 3 && fs[4] > third + 1u) alt |= RAER_ALT_GROW;
+                        if (fs[5] != 0xffffffffu) {
+                            alt |= (fs[6] & 0xfu) << RAER_ALT_OCODE_SHIFT;
+                            if (fs[6] != fs[7]) alt |= RAER_ALT_OAMBIG;
+                        }
                         P.row_alt[row * P.n_files + f] = alt;
                     }
                 }
@@ -807,7 +820,7 @@ extern "C" int raer_launch_overlap(const raer_read_hdr* hdr, const uint32_t* cig
 }
 
 extern "C" size_t raer_tile_smem_bytes(int n_files, int W, int S, int* cnt_words, int* slot_words) {
-    int sw = 404 + 10 * n_files;
+    int sw = 404 + 2 * RAER_SLOT_FS * n_files;
     int cw = n_files * 2 * RAER_NCLS * W;
     if (S * sw > cw) cw = S * sw;
     *cnt_words = cw;

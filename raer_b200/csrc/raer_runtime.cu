@@ -350,35 +350,63 @@ extern "C" int64_t raer_batch_algorithmic_bytes(const raer_read_batch* b, int64_
 extern "C" void raer_altcode_to_string(uint32_t code, int ref_char, int32_t* buckets, char* out) {
     (void)ref_char;
     static const char L[4] = {'A', 'C', 'G', 'T'};
+    static const char NT16[17] = "=ACMGRSVTWYHKDBN";
     unsigned mask = code & RAER_ALT_MASK;
     int nins = (code >> RAER_ALT_NINS_SHIFT) & 7;
-    if (*buckets != 8) *buckets = 4;
-    if (code & RAER_ALT_GROW) *buckets = 8;
-    int nb = *buckets;
-    char slot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    char okey = NT16[(code >> RAER_ALT_OCODE_SHIFT) & 0xf];
+    char keys[5];
+    bool live[5];
+    int nk = 0;
     if (nins == 0) {
-        // rows without a second pass (want_stats == 0) or a single surviving base: derive order from the mask
+        // rows without a second pass (want_stats == 0): no order information, use base order
         for (int b = 0; b < 4; ++b)
-            if (mask & (1u << b)) { ++nins; }
-        int k = 0;
-        unsigned order = 0;
-        for (int b = 0; b < 4; ++b)
-            if (mask & (1u << b)) order |= (unsigned)b << (2 * k++);
-        code = (code & ~(0xffu << RAER_ALT_ORDER_SHIFT)) | (order << RAER_ALT_ORDER_SHIFT);
+            if (mask & (1u << b)) { keys[nk] = L[b]; live[nk++] = true; }
+    } else {
+        for (int k = 0; k < nins && k < 5; ++k) {
+            int id = (code >> (RAER_ALT_ORDER_SHIFT + 3 * k)) & 7;
+            if (id < 4) { keys[nk] = L[id]; live[nk++] = (mask >> id) & 1u; }
+            else { keys[nk] = okey; live[nk++] = (code & RAER_ALT_OTHER) != 0; }
+        }
     }
-    for (int k = 0; k < nins; ++k) {
-        int b = (code >> (RAER_ALT_ORDER_SHIFT + 2 * k)) & 3;
-        unsigned i = (unsigned)L[b] & (nb - 1), step = 0;
+    // khash emulation: home = key & (nb-1), probe i += ++step; a put finding n_occupied >= 0.77*nb resizes
+    // (4 -> 8) and re-inserts the live keys in bucket order before going on. The table never shrinks.
+    if (*buckets != 8 && *buckets != 16) *buckets = 4;
+    int nb = *buckets;
+    char slot[16];
+    memset(slot, 0, sizeof(slot));
+    int occ = 0;
+    auto put = [&](char key) {
+        unsigned i = (unsigned)(unsigned char)key & (nb - 1), step = 0;
         while (slot[i]) i = (i + (++step)) & (nb - 1);
-        slot[i] = L[b];
+        slot[i] = key;
+        ++occ;
+    };
+    auto grow = [&]() {
+        char old[16];
+        int onb = nb;
+        memcpy(old, slot, sizeof(old));
+        nb *= 2;
+        memset(slot, 0, sizeof(slot));
+        occ = 0;
+        for (int i = 0; i < onb; ++i)
+            if (old[i]) put(old[i]);
+    };
+    for (int k = 0; k < nk; ++k) {
+        if (occ >= (int)(nb * 0.77 + 0.5) && nb < 16) grow();
+        put(keys[k]);
     }
+    // a further put of an already present key with 3 keys occupied also resizes (flag from the device)
+    if ((code & RAER_ALT_GROW) && nb == 4) grow();
+    *buckets = nb;
     int z = 0;
     for (int i = 0; i < nb; ++i) {
         if (!slot[i]) continue;
-        int b = slot[i] == 'A' ? 0 : slot[i] == 'C' ? 1 : slot[i] == 'G' ? 2 : 3;
-        if (!(mask & (1u << b))) continue;  // pruned by min_allelic_freq after insertion
-        if (z) out[z++] = ',';
-        out[z++] = slot[i];
+        bool alive = false;
+        for (int k = 0; k < nk; ++k)
+            if (keys[k] == slot[i]) alive = live[k];
+        if (!alive) continue;  // pruned by min_allelic_freq after insertion (kh_del keeps the layout)
+        if (z && z < 10) out[z++] = ',';
+        if (z < 11) out[z++] = slot[i];
     }
     if (z == 0) { out[0] = '-'; z = 1; }
     out[z] = 0;
@@ -466,6 +494,10 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
     for (int lt : ic.libtype)
         if (lt < 0 || lt > 2) { set_error("invert read orientation failure"); return RAER_ERR; }
     ic.regidx = has_ridx ? &ridx : nullptr;
+    if (const char* e = getenv("RAER_BATCH_READS")) {  // reads per batch (tests exercise batch seams with small values)
+        long v = atol(e);
+        if (v > 0) ic.target_reads = v;
+    }
 
     raer::Ingest ing(ic);
     if (!ing.open(a->bampaths, a->indexes, a->host_threads, a->region)) return RAER_ERR_IO;

@@ -1,0 +1,389 @@
+"""Seeded synthetic RNA-seq-like alignments of the shapes BASELINE.json names.
+
+One generator, written with torch ops so that it runs
+  * on the CPU -> numpy arrays -> BAM/BAI/FASTA files (tests, e2e through the .Call layer, CPU baseline), and
+  * on the GPU -> HBM-resident read batches in the raer_read_batch layout (bench "value").
+Not part of the pileup path. torch is plumbing here (random numbers, sort, gather).
+
+Shape (bulk, config C2): 2x100 bp proper pairs, fragment length N(180, 40) clipped to [100, 400],
+strand by 50 kb "gene" blocks consistent with fr-first-strand, CIGAR mix 80% 100M / 12% aMbNcM /
+4% soft clip / 2% insertion / 2% deletion, base quality 90% Q37 / 8% Q11-25 / 2% Q2, substitution
+errors at 10^(-Q/10), A->G edits at 1e-3 of A positions with level U[0.05, 0.5], MAPQ 255/3/0.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+READ_LEN = 100
+_NT16 = {"A": 1, "C": 2, "G": 4, "T": 8, "N": 15}
+_CODE_OF_IDX = torch.tensor([1, 2, 4, 8], dtype=torch.uint8)  # A C G T
+
+
+def make_reference(contig_lens: List[int], seed: int, device="cpu") -> List[torch.Tensor]:
+    """Uniform ACGT reference, one uint8 tensor (values 0..3) per contig."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    return [torch.randint(0, 4, (L,), generator=g, device=device, dtype=torch.uint8) for L in contig_lens]
+
+
+def reference_ascii(ref_idx: torch.Tensor) -> torch.Tensor:
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=ref_idx.device)
+    return lut[ref_idx.long()]
+
+
+def write_fasta(path: str, names: List[str], refs: List[torch.Tensor], width: int = 60) -> None:
+    with open(path, "w") as fa, open(path + ".fai", "w") as fai:
+        off = 0
+        for nm, r in zip(names, refs):
+            hdr = f">{nm}\n"
+            fa.write(hdr)
+            off += len(hdr)
+            s = reference_ascii(r).cpu().numpy().tobytes().decode()
+            L = len(s)
+            fai.write(f"{nm}\t{L}\t{off}\t{width}\t{width + 1}\n")
+            for i in range(0, L, width):
+                fa.write(s[i:i + width] + "\n")
+            off += L + (L + width - 1) // width
+
+
+@dataclass
+class Reads:
+    """Coordinate-sorted records of one contig of one BAM (device tensors)."""
+
+    pos: torch.Tensor        # int32
+    end: torch.Tensor        # int32
+    flag: torch.Tensor       # int32
+    mapq: torch.Tensor       # uint8
+    cigar: torch.Tensor      # [n, 3] uint32-in-int64 (len<<4|op), 0 = unused slot
+    n_cigar: torch.Tensor    # int32
+    seq: torch.Tensor        # [n, READ_LEN] uint8 4-bit codes
+    qual: torch.Tensor       # [n, READ_LEN] uint8
+    pair_id: torch.Tensor    # int64
+    mate_pos: torch.Tensor   # int32
+    isize: torch.Tensor      # int32
+    mate_idx: torch.Tensor   # int64 index of the mate inside this contig's sorted order
+
+
+def gen_contig(ref: torch.Tensor, n_pairs: int, seed: int, *, edit_frac=1e-3, gene_block=50_000,
+               p_splice=0.12, p_clip=0.04, p_ins=0.02, p_del=0.02, intron=(100, 5000), device="cpu",
+               qual_mix=(0.90, 0.08, 0.02), mapq_mix=(0.95, 0.03, 0.02), single_end=False) -> Reads:
+    """2x100 bp pairs on one contig (or single-end 91 bp style reads when single_end)."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    L = ref.numel()
+    n = n_pairs
+    U = lambda *s: torch.rand(*s, generator=g, device=dev)  # noqa: E731
+    frag = (180 + 40 * torch.randn(n, generator=g, device=dev)).round().clamp(100, 400).long()
+    if single_end:
+        frag = torch.full((n,), READ_LEN, device=dev, dtype=torch.long)
+    max_span = READ_LEN + intron[1] + 8
+    start = (U(n) * max(L - 400 - max_span, 1)).long()
+    # left mate starts at the fragment start, right mate ends at the fragment end
+    lpos = start
+    rpos = start + frag - READ_LEN
+    gene_minus = ((start // gene_block) % 2 == 1)
+    n_reads = n if single_end else 2 * n
+    pos0 = lpos if single_end else torch.cat([lpos, rpos])
+    is_right = torch.zeros(n_reads, dtype=torch.bool, device=dev)
+    if not single_end:
+        is_right[n:] = True
+    pid = torch.arange(n, device=dev).repeat(1 if single_end else 2)
+    gm = gene_minus.repeat(1 if single_end else 2)
+    # fr-first-strand: read1 is antisense. plus gene: left=R2 fwd (163), right=R1 rev (83); minus gene: left=R1 fwd (99), right=R2 rev (147)
+    if single_end:
+        flag = torch.where(gm, torch.tensor(16, device=dev), torch.tensor(0, device=dev))
+    else:
+        flag = torch.where(is_right, torch.where(gm, torch.tensor(147, device=dev), torch.tensor(83, device=dev)),
+                           torch.where(gm, torch.tensor(99, device=dev), torch.tensor(163, device=dev)))
+    # CIGAR type per read
+    u = U(n_reads)
+    c1, c2, c3, c4 = p_splice, p_splice + p_clip, p_splice + p_clip + p_ins, p_splice + p_clip + p_ins + p_del
+    ctype = torch.zeros(n_reads, dtype=torch.long, device=dev)
+    ctype[u < c4] = 4
+    ctype[u < c3] = 3
+    ctype[u < c2] = 2
+    ctype[u < c1] = 1
+    a = (10 + U(n_reads) * 80).long()                       # split point
+    k = (1 + U(n_reads) * 3).long().clamp(1, 3)             # indel / clip length base
+    nlen = (intron[0] + U(n_reads) * (intron[1] - intron[0])).long()
+    clip_left = U(n_reads) < 0.5
+    k_clip = (1 + U(n_reads) * 20).long()
+    j = torch.arange(READ_LEN, device=dev).unsqueeze(0)     # [1, RL]
+    A = a.unsqueeze(1)
+    K = k.unsqueeze(1)
+    KC = k_clip.unsqueeze(1)
+    NL = nlen.unsqueeze(1)
+    P0 = pos0.unsqueeze(1)
+    T = ctype.unsqueeze(1)
+    CL = clip_left.unsqueeze(1)
+    # reference offset of query base j (or -1 when the base is clipped / inserted)
+    off = j.expand(n_reads, READ_LEN).clone()
+    off = torch.where(T == 1, j + (j >= A) * NL, off)
+    off = torch.where((T == 2) & CL, torch.where(j < KC, torch.full_like(off, -1), j - KC), off)
+    off = torch.where((T == 2) & ~CL, torch.where(j >= READ_LEN - KC, torch.full_like(off, -1), off), off)
+    off = torch.where(T == 3, torch.where(j < A, j, torch.where(j < A + K, torch.full_like(off, -1), j - K)), off)
+    off = torch.where(T == 4, j + (j >= A) * K, off)
+    refpos = torch.where(off >= 0, P0 + off, torch.full_like(off, -1))
+    refpos = refpos.clamp(max=L - 1)
+    span = torch.full((n_reads,), READ_LEN, device=dev, dtype=torch.long)
+    span = torch.where(ctype == 1, READ_LEN + nlen, span)
+    span = torch.where(ctype == 2, READ_LEN - k_clip, span)
+    span = torch.where(ctype == 3, READ_LEN - k, span)
+    span = torch.where(ctype == 4, READ_LEN + k, span)
+    # CIGAR words (len << 4 | op): M0 I1 D2 N3 S4
+    w = lambda ln, op: (ln << 4) | op  # noqa: E731
+    z = torch.zeros(n_reads, dtype=torch.long, device=dev)
+    cig = torch.stack([w(torch.full_like(z, READ_LEN), 0), z, z], dim=1)
+    m = ctype == 1
+    cig[m] = torch.stack([w(a, 0), w(nlen, 3), w(READ_LEN - a, 0)], dim=1)[m]
+    m = (ctype == 2) & clip_left
+    cig[m] = torch.stack([w(k_clip, 4), w(READ_LEN - k_clip, 0), z], dim=1)[m]
+    m = (ctype == 2) & ~clip_left
+    cig[m] = torch.stack([w(READ_LEN - k_clip, 0), w(k_clip, 4), z], dim=1)[m]
+    m = ctype == 3
+    cig[m] = torch.stack([w(a, 0), w(k, 1), w(READ_LEN - a - k, 0)], dim=1)[m]
+    m = ctype == 4
+    cig[m] = torch.stack([w(a, 0), w(k, 2), w(READ_LEN - a, 0)], dim=1)[m]
+    n_cig = torch.where(ctype == 0, 1, torch.where(ctype == 2, 2, 3)).int()
+    # bases: reference, then A->G editing (T->C for minus genes), then sequencing errors
+    base = ref[refpos.clamp(min=0)].long()
+    rnd_base = (U(n_reads, READ_LEN) * 4).long().clamp(0, 3)
+    base = torch.where(refpos >= 0, base, rnd_base)
+    g2 = torch.Generator(device=dev)
+    g2.manual_seed(seed * 7919 + 13)
+    site_u = torch.rand(L, generator=g2, device=dev)
+    level = 0.05 + 0.45 * torch.rand(L, generator=g2, device=dev)
+    editable = site_u < edit_frac
+    rp = refpos.clamp(min=0)
+    ed_hit = editable[rp] & (refpos >= 0) & (U(n_reads, READ_LEN) < level[rp])
+    GM = gm.unsqueeze(1)
+    base = torch.where(ed_hit & ~GM & (base == 0), torch.full_like(base, 2), base)   # A->G on plus genes
+    base = torch.where(ed_hit & GM & (base == 3), torch.full_like(base, 1), base)    # T->C on minus genes
+    uq = U(n_reads, READ_LEN)
+    qual = torch.full((n_reads, READ_LEN), 37, dtype=torch.long, device=dev)
+    qual = torch.where(uq < qual_mix[1] + qual_mix[2], (11 + U(n_reads, READ_LEN) * 15).long(), qual)
+    qual = torch.where(uq < qual_mix[2], torch.full_like(qual, 2), qual)
+    perr = torch.pow(10.0, -qual.float() / 10.0)
+    err = U(n_reads, READ_LEN) < perr
+    base = torch.where(err, (base + 1 + (U(n_reads, READ_LEN) * 3).long().clamp(0, 2)) % 4, base)
+    codes = _CODE_OF_IDX.to(dev)[base]
+    um = U(n)
+    mq = torch.full((n,), 255, dtype=torch.long, device=dev)
+    mq = torch.where(um < mapq_mix[1] + mapq_mix[2], torch.full_like(mq, 3), mq)
+    mq = torch.where(um < mapq_mix[2], torch.zeros_like(mq), mq)
+    mapq = mq.repeat(1 if single_end else 2)
+    end = pos0 + span
+    # mates
+    if single_end:
+        mate_pos = torch.full((n_reads,), -1, device=dev, dtype=torch.long)
+        isize = torch.zeros(n_reads, device=dev, dtype=torch.long)
+    else:
+        mate_pos = torch.cat([rpos, lpos])
+        tl = (end[n:] - lpos)
+        isize = torch.cat([tl, -tl])
+    order = torch.argsort(pos0 * 2 + is_right.long(), stable=True)
+    inv = torch.empty_like(order)
+    inv[order] = torch.arange(n_reads, device=dev)
+    if single_end:
+        mate_idx = torch.full((n_reads,), -1, device=dev, dtype=torch.long)
+    else:
+        partner = torch.cat([torch.arange(n, 2 * n, device=dev), torch.arange(0, n, device=dev)])
+        mate_idx = inv[partner][order]
+    return Reads(
+        pos=pos0[order].int(), end=end[order].int(), flag=flag[order].int(), mapq=mapq[order].to(torch.uint8),
+        cigar=cig[order], n_cigar=n_cig[order], seq=codes[order], qual=qual[order].to(torch.uint8),
+        pair_id=pid[order], mate_pos=mate_pos[order].int(), isize=isize[order].int(), mate_idx=mate_idx,
+    )
+
+
+# --------------------------------------------------------------------------------------- BAM files
+_SYNTH = None
+
+
+def _synth_lib():
+    global _SYNTH
+    if _SYNTH is None:
+        so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libraer_synth.so")
+        L = C.CDLL(so)
+        L.synth_write_bam.restype = C.c_int
+        _SYNTH = L
+    return _SYNTH
+
+
+def write_bam(path: str, names: List[str], lens: List[int], per_contig: List[Optional[Reads]], *, qname_prefix="r",
+              tags: Optional[Dict[str, np.ndarray]] = None, level: int = 1) -> int:
+    """Write one BAM (+.bai) from per-contig Reads. Returns the number of records."""
+    tid, pos, flag, mapq, mpos, isize, ncig, cig, seq, qual, pid = [], [], [], [], [], [], [], [], [], [], []
+    for t, r in enumerate(per_contig):
+        if r is None or r.pos.numel() == 0:
+            continue
+        k = r.pos.numel()
+        tid.append(np.full(k, t, dtype=np.int32))
+        pos.append(r.pos.cpu().numpy()); flag.append(r.flag.cpu().numpy().astype(np.uint16))
+        mapq.append(r.mapq.cpu().numpy()); mpos.append(r.mate_pos.cpu().numpy()); isize.append(r.isize.cpu().numpy())
+        ncig.append(r.n_cigar.cpu().numpy()); cig.append(r.cigar.cpu().numpy()); seq.append(r.seq.cpu().numpy())
+        qual.append(r.qual.cpu().numpy()); pid.append(r.pair_id.cpu().numpy() + (t << 40))
+    if not tid:
+        tid = [np.zeros(0, np.int32)]
+    cat = np.concatenate
+    tid, pos, flag, mapq, mpos, isize, ncig = map(cat, (tid, pos, flag, mapq, mpos, isize, ncig))
+    cig, seq, qual, pid = cat(cig), cat(seq), cat(qual), cat(pid)
+    n = len(tid)
+    cig_flat = cig[np.arange(3)[None, :] < ncig[:, None]].astype(np.uint32)
+    cig_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(ncig, out=cig_off[1:])
+    rl = seq.shape[1] if n else READ_LEN
+    sq_off = np.arange(n + 1, dtype=np.int64) * rl
+    qn = [f"{qname_prefix}{int(p)}".encode() for p in pid]
+    qn_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(q) for q in qn], out=qn_off[1:])
+    qn_blob = b"".join(qn)
+    if tags:
+        blobs = []
+        for i in range(n):
+            b = b""
+            for tg, vals in tags.items():
+                v = vals[i]
+                if v is not None and v != "":
+                    b += tg.encode() + b"Z" + str(v).encode() + b"\0"
+            blobs.append(b)
+        aux_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum([len(b) for b in blobs], out=aux_off[1:])
+        aux_blob = b"".join(blobs)
+    else:
+        aux_off, aux_blob = None, b""
+    mtid = np.where(mpos >= 0, tid, -1).astype(np.int32)
+    hdr = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{nm}\tLN:{ln}\n" for nm, ln in zip(names, lens))
+    names_c = (C.c_char_p * len(names))(*[x.encode() for x in names])
+    lens_c = (C.c_int32 * len(lens))(*lens)
+    P = lambda a, t: np.ascontiguousarray(a).ctypes.data_as(C.POINTER(t))  # noqa: E731
+    seq_c = np.ascontiguousarray(seq.reshape(-1))
+    qual_c = np.ascontiguousarray(qual.reshape(-1))
+    rc = _synth_lib().synth_write_bam(
+        path.encode(), hdr.encode(), len(names), names_c, lens_c, C.c_int64(n), P(tid, C.c_int32), P(pos, C.c_int32),
+        P(flag, C.c_uint16), P(mapq, C.c_uint8), P(mtid, C.c_int32), P(mpos.astype(np.int32), C.c_int32),
+        P(isize.astype(np.int32), C.c_int32), P(cig_off, C.c_int64), P(cig_flat, C.c_uint32), P(sq_off, C.c_int64),
+        P(seq_c, C.c_uint8), P(qual_c, C.c_uint8), P(qn_off, C.c_int64), C.c_char_p(qn_blob),
+        P(aux_off, C.c_int64) if aux_off is not None else None, C.c_char_p(aux_blob) if aux_off is not None else None,
+        C.c_int(level))
+    if rc != 0:
+        raise RuntimeError("synth_write_bam failed")
+    return n
+
+
+def make_bulk_dataset(outdir: str, *, n_bams=2, n_contigs=2, contig_len=200_000, pairs_per_contig=20_000, seed=1001,
+                      **gen_kw) -> dict:
+    """Reference + n_bams BAMs of the C2 shape at a chosen size. Returns paths and counts."""
+    os.makedirs(outdir, exist_ok=True)
+    names = [f"chr{i + 1}" for i in range(n_contigs)]
+    lens = [contig_len] * n_contigs
+    refs = make_reference(lens, seed)
+    fa = os.path.join(outdir, "ref.fa")
+    write_fasta(fa, names, refs)
+    bams, n_bases = [], 0
+    for b in range(n_bams):
+        per = [gen_contig(refs[t], pairs_per_contig, seed + 1000 * (b + 1) + t, **gen_kw) for t in range(n_contigs)]
+        p = os.path.join(outdir, f"s{b + 1}.bam")
+        write_bam(p, names, lens, per, qname_prefix=f"b{b}_")
+        for r in per:
+            c = r.cigar
+            op, ln = c & 0xF, c >> 4
+            n_bases += int((ln * (op == 0)).sum())
+        bams.append(p)
+    return {"fasta": fa, "bams": bams, "names": names, "lens": lens, "aligned_bases": n_bases}
+
+
+# --------------------------------------------------------------------------------------- device batches
+def pack_device_batch(per_file: List[Reads], tid: int, beg: int, end: int, remove_overlaps: bool = True):
+    """Lay out the reads of one contig (all files) as a raer_read_batch in the memory of their
+    device (HBM when generated on cuda). Returns (dict of tensors kept alive, fields for ReadBatch)."""
+    from . import _cabi
+
+    dev = per_file[0].pos.device
+    hdrs, cigs, seqs, quals, maxends, pairs = [], [], [], [], [], []
+    file_off = [0]
+    ro = co = so = 0
+    for r in per_file:
+        n = r.pos.numel()
+        rl = r.seq.shape[1]
+        rl_pad = rl + (rl & 1)
+        h = torch.zeros((n, 8), dtype=torch.int32, device=dev)
+        h[:, 0] = r.pos
+        h[:, 1] = r.end
+        bits = torch.zeros(n, dtype=torch.int32, device=dev)
+        # fr-first-strand inversion (src/plp_utils.c:339-352): read1 forward or read2 reverse (unpaired: forward)
+        fl = r.flag
+        rev = (fl & 16) != 0
+        paired = (fl & 1) != 0
+        r1 = (~paired) | ((fl & 64) != 0)
+        inv = torch.where(r1, ~rev, rev)
+        bits |= inv.int() * 1
+        h[:, 2] = (fl & 0xFFFF) | (r.mapq.int() << 16) | (bits << 24)
+        h[:, 3] = rl | (r.n_cigar << 16)
+        ncum = torch.cumsum(r.n_cigar.long(), 0)
+        h[:, 4] = (co + ncum - r.n_cigar.long()).int()
+        h[:, 5] = (so + torch.arange(n, device=dev) * (rl_pad // 2)).int()
+        mate = torch.full((n,), -1, dtype=torch.int64, device=dev)
+        if remove_overlaps and (r.mate_idx >= 0).any():
+            idx = torch.arange(n, device=dev)
+            m = r.mate_idx
+            later = (m >= 0) & (m < idx)                     # the mate arrived first
+            mpos = r.pos[m.clamp(min=0)]
+            mend = r.end[m.clamp(min=0)]
+            # overlap_push: skip pairs that cannot overlap (|isize| >= 2*l_qseq and mate start beyond own end)
+            ok = later & ~((r.isize.abs() >= 2 * rl) & (r.mate_pos >= r.end))
+            ok &= mend >= r.pos                              # entry still alive in the pileup buffer
+            mate = torch.where(ok, m + ro, mate)
+            keep_a = _keep_a_bits(r.pair_id[m.clamp(min=0)])
+            h[:, 2] |= (ok & keep_a).int() << (24 + 3)
+            pairs.append((idx[ok] + ro).int())
+            del mpos
+        h[:, 6] = mate.int()
+        h[:, 7] = (torch.arange(n, device=dev) + ro).int()
+        hdrs.append(h)
+        valid = torch.arange(3, device=dev).unsqueeze(0) < r.n_cigar.unsqueeze(1)
+        cigs.append(r.cigar[valid].int())
+        sq = r.seq
+        if rl & 1:
+            sq = torch.cat([sq, torch.zeros((n, 1), dtype=torch.uint8, device=dev)], 1)
+            ql = torch.cat([r.qual, torch.zeros((n, 1), dtype=torch.uint8, device=dev)], 1)
+        else:
+            ql = r.qual
+        seqs.append(((sq[:, 0::2] << 4) | sq[:, 1::2]).reshape(-1))
+        quals.append(ql.reshape(-1))
+        maxends.append(torch.cummax(r.end, 0)[0].int())
+        ro += n
+        co += int(ncum[-1]) if n else 0
+        so += n * (rl_pad // 2)
+        file_off.append(ro)
+    T = {
+        "hdr": torch.cat(hdrs).contiguous(), "cigar": torch.cat(cigs).contiguous(), "seq": torch.cat(seqs).contiguous(),
+        "qual": torch.cat(quals).contiguous(), "maxend": torch.cat(maxends).contiguous(),
+        "pair_b": (torch.cat(pairs) if pairs else torch.zeros(0, dtype=torch.int32, device=dev)).contiguous(),
+        "file_off": np.asarray(file_off, dtype=np.int64),
+    }
+    b = _cabi.ReadBatch()
+    b.n_files = len(per_file)
+    b.tid, b.beg, b.end = tid, beg, end
+    b.n_reads = ro
+    b.file_off = T["file_off"].ctypes.data
+    b.hdr, b.maxend, b.cigar = T["hdr"].data_ptr(), T["maxend"].data_ptr(), T["cigar"].data_ptr()
+    b.seq, b.qual = T["seq"].data_ptr(), T["qual"].data_ptr()
+    b.n_cigar_words, b.n_sq_bytes = co, so
+    b.pair_b, b.n_pairs = T["pair_b"].data_ptr(), T["pair_b"].numel()
+    return T, b
+
+
+def _keep_a_bits(pair_id: torch.Tensor) -> torch.Tensor:
+    """Stand-in for htslib's qname-hash coin (Wang(X31(qname)) & 1) on device-generated batches that
+    have no qname strings: a fixed integer hash of the pair id. Only used by bench data."""
+    x = (pair_id * 2654435761) & 0xFFFFFFFF
+    x = x ^ (x >> 15)
+    return (x & 1) == 1
