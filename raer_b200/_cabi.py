@@ -192,6 +192,10 @@ def lib() -> C.CDLL:
         L.raer_rows_free.argtypes = [C.POINTER(Rows)]
         L.raer_batch_algorithmic_bytes.argtypes = [C.POINTER(ReadBatch), C.c_int64, C.c_int64]
         L.raer_batch_algorithmic_bytes.restype = C.c_int64
+        L.raer_ctx_profile.argtypes = [C.c_void_p, C.c_int]
+        L.raer_ctx_profile.restype = None
+        L.raer_ctx_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        L.raer_ctx_profile_read.restype = C.c_int
         L.raer_altcode_to_string.argtypes = [C.c_uint32, C.c_int, C.POINTER(C.c_int32), C.c_char_p]
         L.raer_ctx_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                            C.POINTER(C.c_double)]

@@ -828,7 +828,7 @@ extern "C" size_t raer_tile_smem_bytes(int n_files, int W, int S, int* cnt_words
     return (size_t)cw * 4 + (W >> 5) * 4 + (size_t)W * (4 + 4 + 2 + 2 + 1) + 64;
 }
 
-extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* launches) {
+extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* launches, cudaEvent_t e0, cudaEvent_t e1) {
     int nl = 0;
     if (P->n_tiles <= 0) { *launches = 0; return 0; }
     {
@@ -846,7 +846,9 @@ extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* l
     int per_sm = smem > 110 * 1024 ? 1 : 2;
     int grid = n_sm * per_sm;
     if (grid > P->n_tiles) grid = P->n_tiles;
+    if (e0) cudaEventRecord(e0, st);
     k_pileup_tiles<<<grid, RAER_BLOCK, smem, st>>>(*P);
+    if (e1) cudaEventRecord(e1, st);
     ++nl;
     *launches = nl;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;

@@ -22,7 +22,7 @@ using raer::set_error;
 extern "C" int raer_launch_overlap(const raer_read_hdr* hdr, const uint32_t* cigar, const uint8_t* seq, uint8_t* qual,
                                    const int32_t* pair_b, long long n_pairs, int mode, cudaStream_t st);
 extern "C" size_t raer_tile_smem_bytes(int n_files, int W, int S, int* cnt_words, int* slot_words);
-extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* launches);
+extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* launches, cudaEvent_t e0, cudaEvent_t e1);
 
 #define CK(call)                                                                              \
     do {                                                                                      \
@@ -87,6 +87,10 @@ struct raer_ctx {
     long long row_cap = 0;
     float ms_h2d = 0, ms_kernel = 0, ms_d2h = 0;
     int64_t last_launches = 0;
+    // optional per-launch timing of the dominant kernel (bench roofline)
+    bool prof = false;
+    std::vector<cudaEvent_t> pev;
+    size_t pev_used = 0;
 };
 
 extern "C" raer_ctx* raer_ctx_create(int32_t device) {
@@ -113,6 +117,20 @@ extern "C" void raer_ctx_destroy(raer_ctx* c) {
     delete c;
 }
 extern "C" void* raer_ctx_stream(raer_ctx* c) { return (void*)c->stream; }
+// switch per-launch CUDA-event timing of k_pileup_tiles on/off (resets the accumulated launches)
+extern "C" void raer_ctx_profile(raer_ctx* c, int on) { c->prof = on != 0; c->pev_used = 0; }
+// after a stream synchronize: total milliseconds and number of k_pileup_tiles launches since raer_ctx_profile(1)
+extern "C" int raer_ctx_profile_read(raer_ctx* c, double* ms_sum, int64_t* n_launches) {
+    double tot = 0;
+    for (size_t i = 0; i + 1 < c->pev_used; i += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->pev[i], c->pev[i + 1]) != cudaSuccess) { cudaGetLastError(); return RAER_ERR_CUDA; }
+        tot += ms;
+    }
+    *ms_sum = tot;
+    *n_launches = (int64_t)(c->pev_used / 2);
+    return RAER_OK;
+}
 
 extern "C" int raer_ctx_set_reference(raer_ctx* c, int32_t tid, const char* seq, int64_t len) {
     cudaSetDevice(c->device);
@@ -205,7 +223,13 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
             nl += r;
         }
         int tl = 0;
-        if (raer_launch_tiles(&P, c->n_sm, c->stream, &tl) < 0) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (c->prof) {
+            while (c->pev.size() < c->pev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); c->pev.push_back(e); }
+            e0 = c->pev[c->pev_used++];
+            e1 = c->pev[c->pev_used++];
+        }
+        if (raer_launch_tiles(&P, c->n_sm, c->stream, &tl, e0, e1) < 0) {
             set_error("tile kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             return RAER_ERR_CUDA;
         }
