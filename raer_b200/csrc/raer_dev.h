@@ -41,6 +41,7 @@ struct PlpParams {
     // configuration
     int min_depth, min_bq, trim_5p, trim_3p, indel_dist, splice_dist, min_overhang, nmer, min_var_reads;
     int n_mm_type, n_mm, report_multiallelic, want_stats, any_okv;
+    int fast;                        // only mapq / base-quality filters configured: branch-free item path
     double ftrim_5p, ftrim_3p, min_af;
     int min_mapq[RAER_MAX_FILES];
     int okv[RAER_MAX_FILES];

@@ -714,9 +714,11 @@ bool Ingest::parse_ahead(int fi, size_t want) {
         H.h.sq_off = (uint32_t)(F.seq.size());
         F.cigar.insert(F.cigar.end(), F.look_cigar.begin(), F.look_cigar.end());
         F.seq.insert(F.seq.end(), F.look_seq.begin(), F.look_seq.end());
-        // qualities live at 2 * sq_off: pad odd lengths
+        // every read starts on a 4-byte (sequence) / 8-byte (quality) boundary: the kernels fetch 8 bases
+        // per load; qualities live at 2 * sq_off
+        while (F.seq.size() & 3) F.seq.push_back(0xff);
         F.qual.insert(F.qual.end(), F.look_qual.begin(), F.look_qual.end());
-        if (F.look_qual.size() & 1) F.qual.push_back(0);
+        F.qual.resize(2 * F.seq.size(), 0);
         if (H.mate_ord >= 0 && F.front < F.reads.size()) {
             // htslib's overlap pass can rewrite qualities of the later mate far beyond the earlier mate's
             // end (deletion catch-up across a ref-skip), so the earlier mate must stay packed with it

@@ -23,6 +23,9 @@
 #include "raer_dev.h"
 
 #define FULL 0xffffffffu
+// counter slot of tile position pidx: positions 8 apart are adjacent words, so the 8-base items of one
+// read (lanes 8 positions apart) hit distinct banks
+#define CIDX(pidx, W) ((((pidx) & 7) * ((W) >> 3)) + ((pidx) >> 3))
 
 // ---------------------------------------------------------------------------------------------
 // small device helpers
@@ -61,25 +64,13 @@ struct ReadCtx {
     int qs, qe, rev, invert, d5f, d3f, ftrim_all;
 };
 
-__device__ __forceinline__ void load_read(const PlpParams& P, long long r, ReadCtx& c) {
-    const int4* h = reinterpret_cast<const int4*>(P.hdr + r);
-    int4 a = __ldg(h), b = __ldg(h + 1);
-    c.pos = a.x;
-    c.end = a.y;
-    c.flag = a.z & 0xffff;
-    c.mapq = (a.z >> 16) & 0xff;
-    c.bits = (a.z >> 24) & 0xff;
-    c.l_qseq = a.w & 0xffff;
-    c.n_cigar = (a.w >> 16) & 0xffff;
-    c.cig = P.cigar + (unsigned)b.x;
-    c.seq = P.seq + (unsigned)b.y;
-    c.qual = P.qual + 2ull * (unsigned)b.y;
+__device__ __forceinline__ void finish_ctx(const PlpParams& P, ReadCtx& c) {
     c.rev = (c.flag >> 4) & 1;
     c.invert = c.bits & RAER_RB_INVERT;
     // query_start / query_end (src/plp_utils.c:52-104): soft clips at either end, hard clips skipped
     int qs = 0, k;
     for (k = 0; k < c.n_cigar; ++k) {
-        uint32_t w = __ldg(c.cig + k);
+        uint32_t w = c.cig[k];
         int op = cg_op(w);
         if (op == OP_H) continue;
         if (op == OP_S) qs += cg_len(w);
@@ -87,7 +78,7 @@ __device__ __forceinline__ void load_read(const PlpParams& P, long long r, ReadC
     }
     int qe = c.l_qseq;
     for (k = c.n_cigar - 1; k >= 0; --k) {
-        uint32_t w = __ldg(c.cig + k);
+        uint32_t w = c.cig[k];
         int op = cg_op(w);
         if (op == OP_H) continue;
         if (op == OP_S) qe -= cg_len(w);
@@ -109,7 +100,7 @@ __device__ __forceinline__ void load_read(const PlpParams& P, long long r, ReadC
 __device__ int d_dist_to_splice(const ReadCtx& c, int q, int dist) {
     int ip = 0;
     for (int i = 0; i < c.n_cigar; ++i) {
-        uint32_t w = __ldg(c.cig + i);
+        uint32_t w = c.cig[i];
         int op = cg_op(w);
         if (cg_type(op) & 1) { ip += cg_len(w); continue; }
         if (op == OP_N && ip >= q - dist && ip <= q + dist) return abs(ip - q);
@@ -120,11 +111,11 @@ __device__ int d_dist_to_splice(const ReadCtx& c, int q, int dist) {
 __device__ int d_check_splice_overhang(const ReadCtx& c, int q, int dist) {
     int ip = 0, p_op = -1;
     for (int i = 0; i < c.n_cigar; ++i) {
-        uint32_t w = __ldg(c.cig + i);
+        uint32_t w = c.cig[i];
         int op = cg_op(w), cl = cg_len(w);
         if (op == OP_M && q >= ip && q <= cl + ip) {
             if (i > 0 && p_op == OP_N) return cl >= dist ? -1 : cl;
-            int nop = (i + 1 < c.n_cigar) ? cg_op(__ldg(c.cig + i + 1)) : ((c.bits & RAER_RB_OHANG_N) ? OP_N : -1);
+            int nop = (i + 1 < c.n_cigar) ? cg_op(c.cig[i + 1]) : ((c.bits & RAER_RB_OHANG_N) ? OP_N : -1);
             if (nop == OP_N) return cl >= dist ? -1 : cl;
             return 0;
         }
@@ -137,7 +128,7 @@ __device__ int d_check_splice_overhang(const ReadCtx& c, int q, int dist) {
 __device__ int d_dist_to_indel(const ReadCtx& c, int q, int dist) {
     int rp = 0, sp = q - dist, ep = q + dist;
     for (int i = 0; i < c.n_cigar; ++i) {
-        uint32_t w = __ldg(c.cig + i);
+        uint32_t w = c.cig[i];
         int op = cg_op(w), cl = cg_len(w);
         if (cg_type(op) & 1) {
             if (op == OP_I) {
@@ -432,6 +423,7 @@ struct TileSmem {
     uint16_t* flag_pidx;  // W
     uint16_t* slot_of;    // W
     uint8_t* dec;         // W
+    uint32_t* cigs;       // per warp: 32 staged read records (ST_WORDS each) + 32 item prefix sums
 };
 
 __device__ __forceinline__ bool pos_eligible(const PlpParams& P, int p) {
@@ -480,7 +472,7 @@ __device__ int decide_site(const PlpParams& P, const uint32_t* cnt, const uint32
     int write_s[2] = {0, 0}, has_v[2] = {0, 0}, is_ma[2] = {0, 0}, any_var[2] = {0, 0};
     for (int f = 0; f < P.n_files; ++f) {
         for (int s = 0; s < 2; ++s) {
-            const uint32_t* base = cnt + (size_t)((f * 2 + s) * RAER_NCLS) * W + pidx;
+            const uint32_t* base = cnt + (size_t)((f * 2 + s) * RAER_NCLS) * W + CIDX(pidx, W);
             int c0 = base[0], c1 = base[W], c2 = base[2 * W], c3 = base[3 * W], co = base[4 * W];
             int total = c0 + c1 + c2 + c3 + co;
             int rc = s == 0 ? pc : (pc < 4 ? 3 - pc : 4);
@@ -525,7 +517,7 @@ __device__ void write_row(const PlpParams& P, const uint32_t* cnt, int pidx, int
     P.row_stats[row * 3 + 1] = 0.0;
     P.row_stats[row * 3 + 2] = 0.0;
     for (int f = 0; f < P.n_files; ++f) {
-        const uint32_t* base = cnt + (size_t)((f * 2 + s) * RAER_NCLS) * W + pidx;
+        const uint32_t* base = cnt + (size_t)((f * 2 + s) * RAER_NCLS) * W + CIDX(pidx, W);
         int cc[4] = {(int)base[0], (int)base[W], (int)base[2 * W], (int)base[3 * W]};
         int co = base[4 * W], cx = base[5 * W];
         int total = cc[0] + cc[1] + cc[2] + cc[3] + co;
@@ -544,93 +536,303 @@ __device__ void write_row(const PlpParams& P, const uint32_t* cnt, int pidx, int
     }
 }
 
-// One warp expands one read. PASS2 == false: phase 1 (counters). PASS2 == true: phase 3 (histograms).
+// Second-pass accumulation of one counted base at a flagged site: read-position histogram, strand
+// tallies, first-seen order of the variant keys.
+__device__ __forceinline__ void pass2_accumulate(const PlpParams& P, const TileSmem& S, const ReadCtx& c, int f, int s,
+                                                 int ordinal, int p, int pidx, int q, int code) {
+    uint32_t* slot = S.cnt + (size_t)S.slot_of[pidx] * P.slot_words;
+    int pref = (p < P.ref_len) ? d_upper((unsigned char)P.ref[p]) : 'N';
+    int letter = "=ACMGRSVTWYHKDBN"[code];
+    int isref = letter == pref;
+    int cls = cls_of_code(code);
+    // strand-bias tally on the uncomplemented base (src/plp.c:762-774)
+    atomicAdd(&slot[400 + (isref ? 0 : 2) + c.rev], 1u);  // ref_fwd ref_rev alt_fwd alt_rev
+    // get_relative_position (src/plp_utils.c:401-412)
+    int tail = c.l_qseq - c.qe;
+    int alen = c.l_qseq - c.qs - tail;
+    int rpos = (int)((double)(q + 1 - c.qs) / (double)(alen + 1) * 99.0);
+    if (rpos < 0 || rpos >= RAER_NHIST) { atomicExch(P.err_flag, RAER_ERR); return; }
+    atomicAdd(&slot[(s * 2 + (isref ? 0 : 1)) * RAER_NHIST + rpos], 1u);
+    if (!isref) {
+        int cb = (c.invert && cls < 4) ? 3 - cls : cls;
+        uint32_t* fs = slot + 404 + (f * 2 + s) * RAER_SLOT_FS;
+        if (cb < 4) {
+            atomicMin(&fs[cb], (unsigned)ordinal);
+        } else {
+            // IUPAC key: complement of an nt16 code is its 4-bit reversal
+            unsigned oc = c.invert ? (__brev((unsigned)code) >> 28) : (unsigned)code;
+            atomicMin(&fs[5], (unsigned)ordinal);
+            atomicMin(&fs[6], oc);
+            atomicMax(&fs[7], oc);
+        }
+        atomicMax(&fs[4], (unsigned)ordinal + 1u);  // last variant read (ordinal + 1; 0 = none)
+    }
+}
+
+// Per-base work. PASS2 == false: phase 1 (counters). PASS2 == true: phase 3 (histograms of flagged sites).
 template <bool PASS2>
-__device__ void walk_read(const PlpParams& P, const TileSmem& S, int f, long long r, int t0, int t1, int lane) {
-    ReadCtx c;
-    load_read(P, r, c);
-    if (c.end <= t0 || c.pos >= t1) return;
-    const int W = P.W;
-    const int mapq_fail = c.mapq < P.min_mapq[f];
-    const int s = c.invert ? 1 : 0;
-    const bool mm_on = (P.n_mm_type > 0 || P.n_mm > 0) && (c.bits & (RAER_RB_MMFAIL | RAER_RB_MMERR));
-    const bool need_cov = !PASS2 && P.min_depth <= 0;
-    const int ordinal = (int)(r - P.file_off[f]);
-    int x = c.pos, y = 0;
-    for (int k = 0; k < c.n_cigar; ++k) {
-        uint32_t w = __ldg(c.cig + k);
-        int op = cg_op(w), len = cg_len(w);
-        if (op == OP_M || op == OP_EQ || op == OP_X) {
-            int lo = max(x, t0), hi = min(x + len, t1);
-            for (int p = lo + lane; p < hi; p += 32) {
-                int pidx = p - t0;
-                if (need_cov) atomicOr(&S.covered[pidx >> 5], 1u << (pidx & 31));
-                if (PASS2) {
-                    if (S.slot_of[pidx] == 0xffff) continue;
-                }
-                int q = y + (p - x);
-                if (q >= c.l_qseq) continue;
-                int code = seq_code(c.seq, q);
-                if (code == 15) continue;  // read base N: not counted anywhere (src/plp.c:718)
-                int bq = c.qual[q];
-                int v = base_verdict(P, c, mapq_fail, q, bq);
-                if (v == 2) continue;
-                int cls = cls_of_code(code);
-                int pref = 0;
-                if (PASS2 || (mm_on && v == 0)) pref = (p < P.ref_len) ? d_upper((unsigned char)P.ref[p]) : 'N';
-                if (v == 0 && mm_on) {
-                    // src/plp.c:750: inverted reads always consult the MD verdict, others only on a mismatch
-                    int letter = "=ACMGRSVTWYHKDBN"[code];
-                    if (c.invert || letter != pref) {
-                        if (c.bits & RAER_RB_MMERR) { atomicExch(P.err_flag, RAER_ERR_MD); continue; }
-                        if (c.bits & RAER_RB_MMFAIL) continue;
-                    }
-                }
-                if (!PASS2) {
-                    int k2 = v == 1 ? RAER_CLS_X : ((c.invert && cls < 4) ? 3 - cls : cls);
-                    atomicAdd(&S.cnt[(size_t)((f * 2 + s) * RAER_NCLS + k2) * W + pidx], 1u);
-                } else {
-                    if (v != 0) continue;
-                    uint32_t* slot = S.cnt + (size_t)S.slot_of[pidx] * P.slot_words;
-                    int letter = "=ACMGRSVTWYHKDBN"[code];
-                    int isref = letter == pref;
-                    // strand-bias tally on the uncomplemented base (src/plp.c:762-774)
-                    atomicAdd(&slot[400 + (isref ? 0 : 2) + c.rev], 1u);  // ref_fwd ref_rev alt_fwd alt_rev
-                    // get_relative_position (src/plp_utils.c:401-412)
-                    int tail = c.l_qseq - c.qe;
-                    int alen = c.l_qseq - c.qs - tail;
-                    int rpos = (int)((double)(q + 1 - c.qs) / (double)(alen + 1) * 99.0);
-                    if (rpos < 0 || rpos >= RAER_NHIST) { atomicExch(P.err_flag, RAER_ERR); continue; }
-                    atomicAdd(&slot[(s * 2 + (isref ? 0 : 1)) * RAER_NHIST + rpos], 1u);
-                    if (!isref) {
-                        int cb = (c.invert && cls < 4) ? 3 - cls : cls;
-                        uint32_t* fs = slot + 404 + (f * 2 + s) * RAER_SLOT_FS;
-                        if (cb < 4) {
-                            atomicMin(&fs[cb], (unsigned)ordinal);
-                        } else {
-                            // IUPAC key: complement of an nt16 code is its 4-bit reversal
-                            unsigned oc = c.invert ? (__brev((unsigned)code) >> 28) : (unsigned)code;
-                            atomicMin(&fs[5], (unsigned)ordinal);
-                            atomicMin(&fs[6], oc);
-                            atomicMax(&fs[7], oc);
-                        }
-                        atomicMax(&fs[4], (unsigned)ordinal + 1u);  // last variant read (ordinal + 1; 0 = none)
-                    }
-                }
+__device__ __forceinline__ void process_base(const PlpParams& P, const TileSmem& S, const ReadCtx& c, int f, int s,
+                                             int mapq_fail, bool mm_on, int ordinal, int p, int pidx, int q, int code,
+                                             int bq) {
+    int v = base_verdict(P, c, mapq_fail, q, bq);
+    if (v == 2) return;
+    int cls = cls_of_code(code);
+    int pref = 0;
+    if (PASS2 || (mm_on && v == 0)) pref = (p < P.ref_len) ? d_upper((unsigned char)P.ref[p]) : 'N';
+    if (v == 0 && mm_on) {
+        // src/plp.c:750: inverted reads always consult the MD verdict, others only on a mismatch
+        int letter = "=ACMGRSVTWYHKDBN"[code];
+        if (c.invert || letter != pref) {
+            if (c.bits & RAER_RB_MMERR) { atomicExch(P.err_flag, RAER_ERR_MD); return; }
+            if (c.bits & RAER_RB_MMFAIL) return;
+        }
+    }
+    if (!PASS2) {
+        int k2 = v == 1 ? RAER_CLS_X : ((c.invert && cls < 4) ? 3 - cls : cls);
+        atomicAdd(&S.cnt[(size_t)((f * 2 + s) * RAER_NCLS + k2) * P.W + CIDX(pidx, P.W)], 1u);
+    } else {
+        if (v != 0) return;
+        uint32_t* slot = S.cnt + (size_t)S.slot_of[pidx] * P.slot_words;
+        int letter = "=ACMGRSVTWYHKDBN"[code];
+        int isref = letter == pref;
+        // strand-bias tally on the uncomplemented base (src/plp.c:762-774)
+        atomicAdd(&slot[400 + (isref ? 0 : 2) + c.rev], 1u);  // ref_fwd ref_rev alt_fwd alt_rev
+        // get_relative_position (src/plp_utils.c:401-412)
+        int tail = c.l_qseq - c.qe;
+        int alen = c.l_qseq - c.qs - tail;
+        int rpos = (int)((double)(q + 1 - c.qs) / (double)(alen + 1) * 99.0);
+        if (rpos < 0 || rpos >= RAER_NHIST) { atomicExch(P.err_flag, RAER_ERR); return; }
+        atomicAdd(&slot[(s * 2 + (isref ? 0 : 1)) * RAER_NHIST + rpos], 1u);
+        if (!isref) {
+            int cb = (c.invert && cls < 4) ? 3 - cls : cls;
+            uint32_t* fs = slot + 404 + (f * 2 + s) * RAER_SLOT_FS;
+            if (cb < 4) {
+                atomicMin(&fs[cb], (unsigned)ordinal);
+            } else {
+                // IUPAC key: complement of an nt16 code is its 4-bit reversal
+                unsigned oc = c.invert ? (__brev((unsigned)code) >> 28) : (unsigned)code;
+                atomicMin(&fs[5], (unsigned)ordinal);
+                atomicMin(&fs[6], oc);
+                atomicMax(&fs[7], oc);
             }
-            x += len;
-            y += len;
-        } else if (op == OP_D || op == OP_N) {
-            if (need_cov) {
-                int lo = max(x, t0), hi = min(x + len, t1);
-                for (int p = lo + lane; p < hi; p += 32) atomicOr(&S.covered[(p - t0) >> 5], 1u << ((p - t0) & 31));
-            }
-            x += len;
-        } else if (op == OP_I || op == OP_S) {
-            y += len;
+            atomicMax(&fs[4], (unsigned)ordinal + 1u);  // last variant read (ordinal + 1; 0 = none)
         }
     }
 }
+
+// ---- item-parallel walker ----------------------------------------------------------------------
+// A warp fetches 32 consecutive read headers (one per lane, coalesced), the owning lane derives every
+// per-read quantity (clips, fractional trim, filter bits) and stages a 48-byte record in the warp's
+// shared-memory scratch. The reads are then cut into items of 8 consecutive QUERY bases; lanes take
+// items from the warp-wide item list, so there is no warp-uniform per-read work and short reads do not
+// leave lanes idle. An item costs one 32-bit sequence load and one 64-bit quality load.
+#define ST_WORDS 12
+enum { ST_POS = 0, ST_LEN, ST_SQ, ST_FLAGS, ST_QSQE, ST_FTRIM, ST_CIGOFF, ST_ORD, ST_CIG0 };
+#define STF_MAPQ_FAIL 0x100u
+#define STF_FTRIM_ALL 0x200u
+
+__device__ __forceinline__ void stage_ctx(const PlpParams& P, const uint32_t* rec, ReadCtx& c) {
+    c.pos = (int)rec[ST_POS];
+    c.l_qseq = (int)(rec[ST_LEN] & 0xffff);
+    c.n_cigar = (int)(rec[ST_LEN] >> 16);
+    unsigned fl = rec[ST_FLAGS];
+    c.bits = (int)(fl & 0xff);
+    c.invert = c.bits & RAER_RB_INVERT;
+    c.rev = (fl >> 16) & 1;
+    c.ftrim_all = (fl & STF_FTRIM_ALL) != 0;
+    c.qs = (int)(rec[ST_QSQE] & 0xffff);
+    c.qe = (int)(rec[ST_QSQE] >> 16);
+    c.d5f = (int)(rec[ST_FTRIM] & 0xffff);
+    c.d3f = (int)(rec[ST_FTRIM] >> 16);
+    c.cig = c.n_cigar <= 4 ? rec + ST_CIG0 : P.cigar + rec[ST_CIGOFF];
+    c.seq = P.seq + rec[ST_SQ];
+    c.qual = P.qual + 2ull * rec[ST_SQ];
+    c.end = 0; c.flag = 0; c.mapq = 0;
+}
+
+#include "raer_walk.cuh"  // scan_reads<PASS2, FAST>: the item-parallel walker
+
+#if 0  // superseded first version of the item walker (kept out of the build)
+template <bool PASS2, bool FAST>
+__device__ void scan_reads(const PlpParams& P, const TileSmem& S, int f, int2 rg, int t0, int t1, int span_lo,
+                           int span_hi, int lane, int wid, int nwarp) {
+    uint32_t* st = S.cigs + wid * (32 * ST_WORDS + 32);
+    uint32_t* pref = st + 32 * ST_WORDS;
+    const bool need_cov = !PASS2 && P.min_depth <= 0;
+    const bool mm_cfg = (P.n_mm_type > 0 || P.n_mm > 0);
+    for (long long base = rg.x + (long long)wid * 32; base < rg.y; base += (long long)nwarp * 32) {
+        long long r = base + lane;
+        int nq = 0;
+        if (r < rg.y) {
+            const int4* h = reinterpret_cast<const int4*>(P.hdr + r);
+            int4 a = __ldg(h);
+            if (a.y > span_lo && a.x < span_hi) {
+                int4 b = __ldg(h + 1);
+                int flag = a.z & 0xffff, mapq = (a.z >> 16) & 0xff, bits = (a.z >> 24) & 0xff;
+                int lq = a.w & 0xffff, n = (a.w >> 16) & 0xffff;
+                const uint32_t* cg = P.cigar + (unsigned)b.x;
+                uint32_t* rec = st + lane * ST_WORDS;
+                // query_start / query_end (src/plp_utils.c:52-104): soft clips at either end, hard clips skipped
+                int qs = 0, qe = lq, k;
+                for (k = 0; k < n; ++k) {
+                    uint32_t w = __ldg(cg + k);
+                    if (k < 4) rec[ST_CIG0 + k] = w;
+                    int op = cg_op(w);
+                    if (op == OP_H) continue;
+                    if (op == OP_S) qs += cg_len(w);
+                    else break;
+                }
+                for (++k; k < n && k < 4; ++k) rec[ST_CIG0 + k] = __ldg(cg + k);
+                for (k = n - 1; k >= 0; --k) {
+                    uint32_t w = __ldg(cg + k);
+                    int op = cg_op(w);
+                    if (op == OP_H) continue;
+                    if (op == OP_S) qe -= cg_len(w);
+                    else break;
+                }
+                unsigned fl = (unsigned)bits | ((unsigned)((flag >> 4) & 1) << 16);
+                if (mapq < P.min_mapq[f]) fl |= STF_MAPQ_FAIL;
+                int d5f = 0, d3f = 0;
+                if (P.ftrim_5p > 0 || P.ftrim_3p > 0) {  // check_variant_fpos, src/plp_utils.c:163-193
+                    int ql = qe - qs;
+                    if (ql <= 0) fl |= STF_FTRIM_ALL;
+                    d5f = (int)floor(P.ftrim_5p * ql);
+                    d3f = (int)ceil(P.ftrim_3p * ql);
+                }
+                rec[ST_POS] = (uint32_t)a.x;
+                rec[ST_LEN] = (uint32_t)lq | ((uint32_t)n << 16);
+                rec[ST_SQ] = (uint32_t)b.y;
+                rec[ST_FLAGS] = fl;
+                rec[ST_QSQE] = (uint32_t)qs | ((uint32_t)qe << 16);
+                rec[ST_FTRIM] = (uint32_t)(d5f & 0xffff) | ((uint32_t)d3f << 16);
+                rec[ST_CIGOFF] = (uint32_t)b.x;
+                rec[ST_ORD] = (uint32_t)(r - P.file_off[f]);
+                nq = (lq + 7) >> 3;
+            }
+        }
+        int inc = nq;
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += v;
+        }
+        pref[lane] = (uint32_t)inc;
+        const int total = __shfl_sync(FULL, inc, 31);
+        __syncwarp();
+        if (need_cov) {
+            // a pileup column exists wherever a read spans the position, deletions and ref-skips included
+            unsigned m = __ballot_sync(FULL, nq > 0);
+            while (m) {
+                int i = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t* rec = st + i * ST_WORDS;
+                int n = (int)(rec[ST_LEN] >> 16);
+                const uint32_t* cg = n <= 4 ? rec + ST_CIG0 : P.cigar + rec[ST_CIGOFF];
+                int x = (int)rec[ST_POS];
+                for (int k = 0; k < n; ++k) {
+                    uint32_t w = cg[k];
+                    if (cg_type(cg_op(w)) & 2) {
+                        int lo = max(x, t0), hi = min(x + cg_len(w), t1);
+                        for (int p = lo + lane; p < hi; p += 32) atomicOr(&S.covered[(p - t0) >> 5], 1u << ((p - t0) & 31));
+                        x += cg_len(w);
+                    }
+                }
+            }
+        }
+        for (int it = lane; it < total; it += 32) {
+            // owning read: smallest i with pref[i] > it
+            int lo = 0, hi = 31;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if ((int)pref[mid] > it) hi = mid; else lo = mid + 1;
+            }
+            const uint32_t* rec = st + lo * ST_WORDS;
+            const int q0 = (it - (lo ? (int)pref[lo - 1] : 0)) << 3;
+            ReadCtx c;
+            stage_ctx(P, rec, c);
+            const int mapq_fail = (rec[ST_FLAGS] & STF_MAPQ_FAIL) != 0;
+            const int s = c.invert ? 1 : 0;
+            const bool mm_on = mm_cfg && (c.bits & (RAER_RB_MMFAIL | RAER_RB_MMERR));
+            const int ordinal = (int)rec[ST_ORD];
+            const uint32_t sw = __ldg(reinterpret_cast<const uint32_t*>(c.seq + (q0 >> 1)));
+            const uint2 qw = __ldg(reinterpret_cast<const uint2*>(c.qual + q0));
+            const int q1 = min(q0 + 8, c.l_qseq);
+            if (FAST) {
+                // Common case, branch-free: the 8 query bases lie inside one aligned block and only the
+                // mapq / base-quality filters are configured. Everything else takes the generic walk below.
+                int x = c.pos, y = 0, p0 = 0;
+                bool simple = false;
+                for (int k = 0; k < c.n_cigar; ++k) {
+                    uint32_t w = c.cig[k];
+                    int op = cg_op(w), len = cg_len(w);
+                    if (op == OP_M || op == OP_EQ || op == OP_X) {
+                        if (q0 < y + len) {
+                            simple = q0 >= y && q0 + 8 <= y + len;
+                            p0 = x + (q0 - y);
+                            break;
+                        }
+                        x += len;
+                        y += len;
+                    } else if (op == OP_D || op == OP_N) {
+                        x += len;
+                    } else if (op == OP_I || op == OP_S) {
+                        y += len;
+                        if (y > q0) break;
+                    }
+                }
+                if (simple) {
+                    const int rel = p0 - t0, tw = t1 - t0, minbq = P.min_bq, W = P.W;
+                    uint32_t* cbase = S.cnt + (size_t)((f * 2 + s) * RAER_NCLS) * W;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int pidx = rel + j;
+                        const int code = (sw >> (((j >> 1) << 3) + ((~j & 1) << 2))) & 0xf;
+                        const int bq = (int)(((j < 4 ? qw.x : qw.y) >> ((j & 3) << 3)) & 0xff);
+                        const bool lowq = bq < minbq;
+                        // src/plp.c:718 (N), :574 (mapq first), :580-586 (quality 0 is dropped silently)
+                        bool go = (unsigned)pidx < (unsigned)tw && code != 15 && (mapq_fail || !(lowq && bq == 0));
+                        if (PASS2) {
+                            go = go && !mapq_fail && !lowq && S.slot_of[go ? pidx : 0] != 0xffff;
+                            if (go) pass2_accumulate(P, S, c, f, s, ordinal, p0 + j, pidx, q0 + j, code);
+                        } else if (go) {
+                            int cls = cls_of_code(code);
+                            int k2 = (mapq_fail || lowq) ? RAER_CLS_X : ((c.invert && cls < 4) ? 3 - cls : cls);
+                            atomicAdd(cbase + k2 * W + CIDX(pidx, W), 1u);
+                        }
+                    }
+                    continue;
+                }
+            }
+            int x = c.pos, y = 0;
+            for (int k = 0; k < c.n_cigar && y < q1; ++k) {
+                uint32_t w = c.cig[k];
+                int op = cg_op(w), len = cg_len(w);
+                if (op == OP_M || op == OP_EQ || op == OP_X) {
+                    int qa = max(q0, y), qb = min(q1, y + len);
+                    for (int q = qa; q < qb; ++q) {
+                        int p = x + (q - y);
+                        if (p < t0 || p >= t1) continue;
+                        int pidx = p - t0;
+                        if (PASS2 && S.slot_of[pidx] == 0xffff) continue;
+                        int j = q - q0;
+                        int code = (sw >> (((j >> 1) << 3) + ((~j & 1) << 2))) & 0xf;
+                        if (code == 15) continue;  // read base N is not counted anywhere (src/plp.c:718)
+                        int bq = (int)(((j < 4 ? qw.x : qw.y) >> ((j & 3) << 3)) & 0xff);
+                        process_base<PASS2>(P, S, c, f, s, mapq_fail, mm_on, ordinal, p, pidx, q, code, bq);
+                    }
+                    x += len;
+                    y += len;
+                } else if (op == OP_D || op == OP_N) {
+                    x += len;
+                } else if (op == OP_I || op == OP_S) {
+                    y += len;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+#endif
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* scratch) {
     // RAER_BLOCK threads, warp shuffle scan + smem across warps
@@ -673,6 +875,7 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
     S.flag_pidx = (uint16_t*)(S.flag_rowm + W);
     S.slot_of = S.flag_pidx + W;
     S.dec = (uint8_t*)(S.slot_of + W);
+    S.cigs = (uint32_t*)(S.dec + W);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int cnt_used = P.n_files * 2 * RAER_NCLS * W;
 
@@ -691,7 +894,8 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
         // ---- phase 1: count
         for (int f = 0; f < P.n_files; ++f) {
             int2 rg = P.tile_ranges[tile * P.n_files + f];
-            for (long long r = rg.x + wid; r < rg.y; r += nwarp) walk_read<false>(P, S, f, r, t0, t1, lane);
+            if (P.fast) scan_reads<false, true>(P, S, f, rg, t0, t1, t0, t1, lane, wid, nwarp);
+            else scan_reads<false, false>(P, S, f, rg, t0, t1, t0, t1, lane, wid, nwarp);
         }
         __syncthreads();
 
@@ -714,28 +918,30 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
         __syncthreads();
         const long long rowbase = s_rowbase;
         if (rowbase >= 0 && tile_rows_total > 0) {
-            int carried = 0;
+            int carried = 0, fcarried = 0;
             for (int chunk = 0; chunk < W; chunk += blockDim.x) {
                 int pidx = chunk + threadIdx.x;
                 int d = pidx < W ? S.dec[pidx] : 0;
                 int n = (d & 1) + ((d >> 1) & 1);
-                int tot;
+                bool fl = P.want_stats && (((d & 1) && (d & 4)) || ((d & 2) && (d & 8)));
+                int tot, ftot;
                 int off = block_exclusive_scan(n, &tot, s_scan) + carried;
+                int slot = block_exclusive_scan(fl ? 1 : 0, &ftot, s_scan) + fcarried;  // position-sorted flag list
                 carried += tot;
+                fcarried += ftot;
                 if (n) {
                     long long row = rowbase + off;
                     int rp = -1, rm = -1;
                     if (d & 1) { write_row(P, S.cnt, pidx, t0 + pidx, 0, row); rp = (int)row; ++row; }
                     if (d & 2) { write_row(P, S.cnt, pidx, t0 + pidx, 1, row); rm = (int)row; }
-                    bool fl = P.want_stats && (((d & 1) && (d & 4)) || ((d & 2) && (d & 8)));
                     if (fl) {
-                        int slot = atomicAdd(&s_nflag, 1);
                         S.flag_pidx[slot] = (uint16_t)pidx;
                         S.flag_rowp[slot] = ((d & 1) && (d & 4)) ? rp : -1;
                         S.flag_rowm[slot] = ((d & 2) && (d & 8)) ? rm : -1;
                     }
                 }
             }
+            if (threadIdx.x == 0) s_nflag = fcarried;
         }
         __syncthreads();
 
@@ -754,9 +960,13 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
             __syncthreads();
             for (int i = threadIdx.x; i < ns; i += blockDim.x) S.slot_of[S.flag_pidx[round0 + i]] = (uint16_t)i;
             __syncthreads();
+            // the flag list is position sorted: only reads overlapping this round's span need a second look
+            const int span_lo = t0 + S.flag_pidx[round0];
+            const int span_hi = t0 + S.flag_pidx[round0 + ns - 1] + 1;
             for (int f = 0; f < P.n_files; ++f) {
                 int2 rg = P.tile_ranges[tile * P.n_files + f];
-                for (long long r = rg.x + wid; r < rg.y; r += nwarp) walk_read<true>(P, S, f, r, t0, t1, lane);
+                if (P.fast) scan_reads<true, true>(P, S, f, rg, t0, t1, span_lo, span_hi, lane, wid, nwarp);
+                else scan_reads<true, false>(P, S, f, rg, t0, t1, span_lo, span_hi, lane, wid, nwarp);
             }
             __syncthreads();
             for (int i = threadIdx.x; i < ns; i += blockDim.x) {
@@ -825,7 +1035,7 @@ extern "C" size_t raer_tile_smem_bytes(int n_files, int W, int S, int* cnt_words
     if (S * sw > cw) cw = S * sw;
     *cnt_words = cw;
     *slot_words = sw;
-    return (size_t)cw * 4 + (W >> 5) * 4 + (size_t)W * (4 + 4 + 2 + 2 + 1) + 64;
+    return (size_t)cw * 4 + (W >> 5) * 4 + (size_t)W * (4 + 4 + 2 + 2 + 1) + (RAER_BLOCK / 32) * (ST_CAP * ST_WORDS + ST_CAP) * 4 + 64;
 }
 
 extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* launches, cudaEvent_t e0, cudaEvent_t e1) {

@@ -154,11 +154,13 @@ extern "C" int raer_ctx_set_reference_device(raer_ctx* c, int32_t tid, const voi
 
 // choose the tile width: counters [file][strand][6][W] x 4 B must fit, leave room for 2 CTAs/SM when cheap
 static int choose_tile_width(int n_files) {
-    int budget = 200 * 1024;
-    int w = budget / (48 * n_files + 16);
-    w = std::min(w, 2048);
+    // 227 KB per CTA minus the per-warp read stages (raer_tile_smem_bytes) and slack
+    int cw, sw;
+    int fixed = (int)raer_tile_smem_bytes(n_files, 0, 0, &cw, &sw);
+    int budget = 227 * 1024 - fixed - 512;
+    int w = budget / (48 * n_files + 14);
+    w = std::min(w, n_files <= 2 ? 1024 : 2048);
     w &= ~31;
-    if (n_files <= 2) w = std::min(w, 1024);  // 2 CTAs per SM
     return std::max(w, 32);
 }
 
@@ -181,6 +183,8 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
     P.report_multiallelic = conf->report_multiallelic; P.want_stats = conf->want_stats;
     P.ftrim_5p = conf->ftrim_5p; P.ftrim_3p = conf->ftrim_3p; P.min_af = conf->min_af;
     P.any_okv = 0;
+    P.fast = !(conf->trim_5p > 0 || conf->trim_3p > 0 || conf->ftrim_5p > 0 || conf->ftrim_3p > 0 || conf->splice_dist ||
+               conf->min_overhang || conf->indel_dist || conf->n_mm_type > 0 || conf->n_mm > 0);
     for (int i = 0; i < nf; ++i) {
         P.min_mapq[i] = conf->min_mapq[i];
         P.okv[i] = conf->only_keep_variants[i];

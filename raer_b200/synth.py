@@ -313,7 +313,7 @@ def pack_device_batch(per_file: List[Reads], tid: int, beg: int, end: int, remov
     for r in per_file:
         n = r.pos.numel()
         rl = r.seq.shape[1]
-        rl_pad = rl + (rl & 1)
+        rl_pad = (rl + 7) & ~7  # reads start on 4-byte sequence / 8-byte quality boundaries (raer_read_hdr.sq_off)
         h = torch.zeros((n, 8), dtype=torch.int32, device=dev)
         h[:, 0] = r.pos
         h[:, 1] = r.end
@@ -351,9 +351,9 @@ def pack_device_batch(per_file: List[Reads], tid: int, beg: int, end: int, remov
         valid = torch.arange(3, device=dev).unsqueeze(0) < r.n_cigar.unsqueeze(1)
         cigs.append(r.cigar[valid].int())
         sq = r.seq
-        if rl & 1:
-            sq = torch.cat([sq, torch.zeros((n, 1), dtype=torch.uint8, device=dev)], 1)
-            ql = torch.cat([r.qual, torch.zeros((n, 1), dtype=torch.uint8, device=dev)], 1)
+        if rl_pad != rl:
+            sq = torch.cat([sq, torch.full((n, rl_pad - rl), 15, dtype=torch.uint8, device=dev)], 1)
+            ql = torch.cat([r.qual, torch.zeros((n, rl_pad - rl), dtype=torch.uint8, device=dev)], 1)
         else:
             ql = r.qual
         seqs.append(((sq[:, 0::2] << 4) | sq[:, 1::2]).reshape(-1))
