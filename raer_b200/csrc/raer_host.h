@@ -94,6 +94,7 @@ struct IngestConf {
     bool sc = false;
     const std::unordered_map<std::string, int>* cb_index = nullptr;  // barcode -> 1-based column
     std::string cb_tag, umi_tag;                                     // empty = not configured
+    int fixed_cb = 0;  // Smart-seq2 mode: every read of this BAM belongs to this whitelist column (src/sc-plp.c:245-246)
     int64_t target_reads = 1 << 21;                                  // reads per batch over all files
 };
 

@@ -579,6 +579,7 @@ bool Ingest::parse_one(int fi) {
             if (it == conf_.cb_index->end()) continue;
             cbcol = it->second;
         }
+        if (conf_.sc && conf_.fixed_cb) cbcol = conf_.fixed_cb;
         uint32_t test = (conf_.keep_flag[0] & ~(uint32_t)r.flag) | (conf_.keep_flag[1] & (uint32_t)r.flag);
         if (~test & 2047u) continue;
         int endpos = r.pos + ((r.n_cigar == 0 || rlen == 0) ? 1 : rlen);

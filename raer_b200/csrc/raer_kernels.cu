@@ -97,7 +97,7 @@ __device__ __forceinline__ void finish_ctx(const PlpParams& P, ReadCtx& c) {
 }
 
 // src/plp_utils.c:196-221
-__device__ int d_dist_to_splice(const ReadCtx& c, int q, int dist) {
+static __device__ int d_dist_to_splice(const ReadCtx& c, int q, int dist) {
     int ip = 0;
     for (int i = 0; i < c.n_cigar; ++i) {
         uint32_t w = c.cig[i];
@@ -108,7 +108,7 @@ __device__ int d_dist_to_splice(const ReadCtx& c, int q, int dist) {
     return -1;
 }
 // src/plp_utils.c:228-266 (inclusive upper bound, BAM_CMATCH only, one-past-the-end read modelled by RAER_RB_OHANG_N)
-__device__ int d_check_splice_overhang(const ReadCtx& c, int q, int dist) {
+static __device__ int d_check_splice_overhang(const ReadCtx& c, int q, int dist) {
     int ip = 0, p_op = -1;
     for (int i = 0; i < c.n_cigar; ++i) {
         uint32_t w = c.cig[i];
@@ -125,7 +125,7 @@ __device__ int d_check_splice_overhang(const ReadCtx& c, int q, int dist) {
     return -2;
 }
 // src/plp_utils.c:269-306
-__device__ int d_dist_to_indel(const ReadCtx& c, int q, int dist) {
+static __device__ int d_dist_to_indel(const ReadCtx& c, int q, int dist) {
     int rp = 0, sp = q - dist, ep = q + dist;
     for (int i = 0; i < c.n_cigar; ++i) {
         uint32_t w = c.cig[i];
@@ -166,6 +166,9 @@ __device__ __forceinline__ int base_verdict(const PlpParams& P, const ReadCtx& c
     if (P.indel_dist && d_dist_to_indel(c, q, P.indel_dist) >= 0) return 1;
     return 0;
 }
+
+// raer_sc.cu includes this file with RAER_HELPERS_ONLY to share the read/filter helpers above.
+#ifndef RAER_HELPERS_ONLY
 
 // ---------------------------------------------------------------------------------------------
 // mate overlap: htslib tweak_overlap_quality (>= 1.13 when mode == 1, <= 1.12 when mode == 2)
@@ -1063,3 +1066,5 @@ extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* l
     *launches = nl;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
+
+#endif  // RAER_HELPERS_ONLY
