@@ -9,7 +9,7 @@
 #define RAER_NCLS 6           // shared-memory counter classes per (file, strand): A C G T other X
 #define RAER_CLS_OTHER 4
 #define RAER_CLS_X 5
-#define RAER_BLOCK 512        // threads per CTA of the tile kernel
+#define RAER_BLOCK 1024       // threads per CTA of the tile kernel (one CTA per SM, 32 warps)
 #define RAER_NHIST 100        // read-position bins (src/plp.c:17 NBASE_POS)
 
 // ALT code layout (uint32 per row per file), decoded by raer_altcode_to_string()

@@ -23,9 +23,11 @@
 #include "raer_dev.h"
 
 #define FULL 0xffffffffu
-// counter slot of tile position pidx: positions 8 apart are adjacent words, so the 8-base items of one
-// read (lanes 8 positions apart) hit distinct banks
-#define CIDX(pidx, W) ((((pidx) & 7) * ((W) >> 3)) + ((pidx) >> 3))
+// counter slot of tile position pidx: one pad word every 32 positions skews the banks, so the 8-base
+// items of one read (lanes 8 positions apart: 8l + (8l >> 5) covers all 32 banks) do not conflict, and
+// the 8 positions of an item stay consecutive words.
+#define CIDX(pidx, W) ((pidx) + ((pidx) >> 5))
+#define WPAD(W) ((W) + ((W) >> 5))  // words per counter class
 
 // ---------------------------------------------------------------------------------------------
 // small device helpers
@@ -421,6 +423,7 @@ __device__ double d_calc_sor(int fwd_ref, int rev_ref, int fwd_alt, int rev_alt)
 struct TileSmem {
     uint32_t* cnt;        // counters, later second-pass slots
     uint32_t* covered;    // W/32 words
+    uint32_t* fbits;      // W/32 + 4 words: flagged positions of the current second-pass round, one pad word in front
     int* flag_rowp;       // W
     int* flag_rowm;       // W
     uint16_t* flag_pidx;  // W
@@ -475,8 +478,9 @@ __device__ int decide_site(const PlpParams& P, const uint32_t* cnt, const uint32
     int write_s[2] = {0, 0}, has_v[2] = {0, 0}, is_ma[2] = {0, 0}, any_var[2] = {0, 0};
     for (int f = 0; f < P.n_files; ++f) {
         for (int s = 0; s < 2; ++s) {
-            const uint32_t* base = cnt + (size_t)((f * 2 + s) * RAER_NCLS) * W + CIDX(pidx, W);
-            int c0 = base[0], c1 = base[W], c2 = base[2 * W], c3 = base[3 * W], co = base[4 * W];
+            const int WP = WPAD(W);
+            const uint32_t* base = cnt + (size_t)((f * 2 + s) * RAER_NCLS) * WP + CIDX(pidx, W);
+            int c0 = base[0], c1 = base[WP], c2 = base[2 * WP], c3 = base[3 * WP], co = base[4 * WP];
             int total = c0 + c1 + c2 + c3 + co;
             int rc = s == 0 ? pc : (pc < 4 ? 3 - pc : 4);
             int cc[4] = {c0, c1, c2, c3};
@@ -520,9 +524,10 @@ __device__ void write_row(const PlpParams& P, const uint32_t* cnt, int pidx, int
     P.row_stats[row * 3 + 1] = 0.0;
     P.row_stats[row * 3 + 2] = 0.0;
     for (int f = 0; f < P.n_files; ++f) {
-        const uint32_t* base = cnt + (size_t)((f * 2 + s) * RAER_NCLS) * W + CIDX(pidx, W);
-        int cc[4] = {(int)base[0], (int)base[W], (int)base[2 * W], (int)base[3 * W]};
-        int co = base[4 * W], cx = base[5 * W];
+        const int WP = WPAD(W);
+        const uint32_t* base = cnt + (size_t)((f * 2 + s) * RAER_NCLS) * WP + CIDX(pidx, W);
+        int cc[4] = {(int)base[0], (int)base[WP], (int)base[2 * WP], (int)base[3 * WP]};
+        int co = base[4 * WP], cx = base[5 * WP];
         int total = cc[0] + cc[1] + cc[2] + cc[3] + co;
         int nr = rc < 4 ? cc[rc] : 0;
         unsigned alt = 0;
@@ -541,9 +546,9 @@ __device__ void write_row(const PlpParams& P, const uint32_t* cnt, int pidx, int
 
 // Second-pass accumulation of one counted base at a flagged site: read-position histogram, strand
 // tallies, first-seen order of the variant keys.
-__device__ __forceinline__ void pass2_accumulate(const PlpParams& P, const TileSmem& S, const ReadCtx& c, int f, int s,
-                                                 int ordinal, int p, int pidx, int q, int code) {
-    uint32_t* slot = S.cnt + (size_t)S.slot_of[pidx] * P.slot_words;
+__device__ __forceinline__ void pass2_accumulate_slot(const PlpParams& P, const TileSmem& S, const ReadCtx& c, int f, int s,
+                                                      int ordinal, int p, int slot_index, int q, int code) {
+    uint32_t* slot = S.cnt + (size_t)slot_index * P.slot_words;
     int pref = (p < P.ref_len) ? d_upper((unsigned char)P.ref[p]) : 'N';
     int letter = "=ACMGRSVTWYHKDBN"[code];
     int isref = letter == pref;
@@ -572,6 +577,11 @@ __device__ __forceinline__ void pass2_accumulate(const PlpParams& P, const TileS
     }
 }
 
+__device__ __forceinline__ void pass2_accumulate(const PlpParams& P, const TileSmem& S, const ReadCtx& c, int f, int s,
+                                                 int ordinal, int p, int pidx, int q, int code) {
+    pass2_accumulate_slot(P, S, c, f, s, ordinal, p, (int)S.slot_of[pidx], q, code);
+}
+
 // Per-base work. PASS2 == false: phase 1 (counters). PASS2 == true: phase 3 (histograms of flagged sites).
 template <bool PASS2>
 __device__ __forceinline__ void process_base(const PlpParams& P, const TileSmem& S, const ReadCtx& c, int f, int s,
@@ -592,7 +602,7 @@ __device__ __forceinline__ void process_base(const PlpParams& P, const TileSmem&
     }
     if (!PASS2) {
         int k2 = v == 1 ? RAER_CLS_X : ((c.invert && cls < 4) ? 3 - cls : cls);
-        atomicAdd(&S.cnt[(size_t)((f * 2 + s) * RAER_NCLS + k2) * P.W + CIDX(pidx, P.W)], 1u);
+        atomicAdd(&S.cnt[(size_t)((f * 2 + s) * RAER_NCLS + k2) * WPAD(P.W) + CIDX(pidx, P.W)], 1u);
     } else {
         if (v != 0) return;
         uint32_t* slot = S.cnt + (size_t)S.slot_of[pidx] * P.slot_words;
@@ -873,14 +883,15 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
     TileSmem S;
     S.cnt = smem;
     S.covered = S.cnt + P.cnt_words;
-    S.flag_rowp = (int*)(S.covered + (W >> 5));
+    S.fbits = S.covered + (W >> 5);
+    S.flag_rowp = (int*)(S.fbits + (W >> 5) + 4);
     S.flag_rowm = S.flag_rowp + W;
     S.flag_pidx = (uint16_t*)(S.flag_rowm + W);
     S.slot_of = S.flag_pidx + W;
     S.dec = (uint8_t*)(S.slot_of + W);
     S.cigs = (uint32_t*)(S.dec + W);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int cnt_used = P.n_files * 2 * RAER_NCLS * W;
+    const int cnt_used = P.n_files * 2 * RAER_NCLS * WPAD(W);
 
     while (true) {
         if (threadIdx.x == 0) s_tile = (int)atomicAdd(P.tile_counter, 1u);
@@ -961,15 +972,21 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
                 S.cnt[i] = is_fs ? 0xffffffffu : 0u;
             }
             __syncthreads();
-            for (int i = threadIdx.x; i < ns; i += blockDim.x) S.slot_of[S.flag_pidx[round0 + i]] = (uint16_t)i;
+            for (int i = threadIdx.x; i < (W >> 5) + 4; i += blockDim.x) S.fbits[i] = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+                int fp = S.flag_pidx[round0 + i];
+                S.slot_of[fp] = (uint16_t)i;
+                atomicOr(&S.fbits[1 + (fp >> 5)], 1u << (fp & 31));
+            }
             __syncthreads();
             // the flag list is position sorted: only reads overlapping this round's span need a second look
             const int span_lo = t0 + S.flag_pidx[round0];
             const int span_hi = t0 + S.flag_pidx[round0 + ns - 1] + 1;
             for (int f = 0; f < P.n_files; ++f) {
                 int2 rg = P.tile_ranges[tile * P.n_files + f];
-                if (P.fast) scan_reads<true, true>(P, S, f, rg, t0, t1, span_lo, span_hi, lane, wid, nwarp);
-                else scan_reads<true, false>(P, S, f, rg, t0, t1, span_lo, span_hi, lane, wid, nwarp);
+                if (P.fast) scan_reads<true, true>(P, S, f, rg, t0, t1, span_lo, span_hi, lane, wid, nwarp, S.flag_pidx + round0, ns);
+                else scan_reads<true, false>(P, S, f, rg, t0, t1, span_lo, span_hi, lane, wid, nwarp, S.flag_pidx + round0, ns);
             }
             __syncthreads();
             for (int i = threadIdx.x; i < ns; i += blockDim.x) {
@@ -1034,11 +1051,11 @@ extern "C" int raer_launch_overlap(const raer_read_hdr* hdr, const uint32_t* cig
 
 extern "C" size_t raer_tile_smem_bytes(int n_files, int W, int S, int* cnt_words, int* slot_words) {
     int sw = 404 + 2 * RAER_SLOT_FS * n_files;
-    int cw = n_files * 2 * RAER_NCLS * W;
+    int cw = n_files * 2 * RAER_NCLS * WPAD(W);
     if (S * sw > cw) cw = S * sw;
     *cnt_words = cw;
     *slot_words = sw;
-    return (size_t)cw * 4 + (W >> 5) * 4 + (size_t)W * (4 + 4 + 2 + 2 + 1) + (RAER_BLOCK / 32) * (ST_CAP * ST_WORDS + ST_CAP) * 4 + 64;
+    return (size_t)cw * 4 + ((W >> 5) * 2 + 4) * 4 + (size_t)W * (4 + 4 + 2 + 2 + 1) + (RAER_BLOCK / 32) * (ST_CAP * ST_WORDS + ST_CAP) * 4 + 64;
 }
 
 extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* launches, cudaEvent_t e0, cudaEvent_t e1) {

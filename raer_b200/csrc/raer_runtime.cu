@@ -158,7 +158,7 @@ static int choose_tile_width(int n_files) {
     int cw, sw;
     int fixed = (int)raer_tile_smem_bytes(n_files, 0, 0, &cw, &sw);
     int budget = 227 * 1024 - fixed - 512;
-    int w = budget / (48 * n_files + 14);
+    int w = budget / (50 * n_files + 14);  // 48 B of counters per position and file, + 1/32 bank-skew padding
     w = std::min(w, n_files <= 2 ? 1024 : 2048);
     w &= ~31;
     return std::max(w, 32);

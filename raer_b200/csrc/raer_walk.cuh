@@ -26,15 +26,22 @@ __device__ __forceinline__ void walk_item(const PlpParams& P, const TileSmem& S,
     const int lq = (int)(rec[ST_LEN] & 0xffff), n = (int)(rec[ST_LEN] >> 16);
     const unsigned fl = rec[ST_FLAGS];
     const uint32_t sq = rec[ST_SQ];
-    const uint32_t sw = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (q0 >> 1)));
-    const uint2 qw = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + q0));
+    // the second pass only fetches bases of items that touch a flagged position
+    uint32_t sw = 0;
+    uint2 qw = make_uint2(0, 0);
+    bool loaded = !PASS2;
+    if (!PASS2) {
+        sw = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (q0 >> 1)));
+        qw = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + q0));
+    }
     const int q1 = min(q0 + 8, lq);
     const bool mapq_fail = (fl & STF_MAPQ_FAIL) != 0;
     const int invert = fl & RAER_RB_INVERT;
     const int s = invert ? 1 : 0;
     const uint32_t* cig = n <= 4 ? rec + ST_CIG0 : P.cigar + rec[ST_CIGOFF];
-    const int W = P.W, minbq = P.min_bq;
-    uint32_t* cbase = S.cnt + (size_t)((f * 2 + s) * RAER_NCLS) * W;
+    const int W = P.W, WP = WPAD(P.W), minbq = P.min_bq;
+    const int cxor = invert ? 3 : 0;
+    const unsigned cbase_s = (unsigned)__cvta_generic_to_shared(S.cnt + (size_t)((f * 2 + s) * RAER_NCLS) * WP);
     ReadCtx c;  // only the fields a path really reads survive dead-code elimination
     if (!FAST || PASS2) stage_ctx(P, rec, c);
     const bool mm_on = !FAST && mm_cfg && (fl & (RAER_RB_MMFAIL | RAER_RB_MMERR));
@@ -47,13 +54,32 @@ __device__ __forceinline__ void walk_item(const PlpParams& P, const TileSmem& S,
             if (y + len > q0) {
                 const int rel = x + (q0 - y) - t0;  // tile index query base q0 would have under this block
                 const int jlo = y - q0, jhi = min(y + len, q1) - q0;
+                unsigned fb = 0xffu;
+                if (PASS2) {
+                    // 8 flag bits of positions rel .. rel+7 (bitmap padded by one word in front)
+                    fb = 0;
+                    if (rel > -32 && rel < tw) {
+                        const int bp = rel + 32;
+                        fb = __funnelshift_r(S.fbits[bp >> 5], S.fbits[(bp >> 5) + 1], bp & 31) & 0xffu;
+                    }
+                    if (fb == 0) {
+                        x += len;
+                        y += len;
+                        continue;
+                    }
+                    if (!loaded) {
+                        sw = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (q0 >> 1)));
+                        qw = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + q0));
+                        loaded = true;
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int pidx = rel + j;
                     const int code = (sw >> (((j >> 1) << 3) + ((~j & 1) << 2))) & 0xf;
                     const int bq = (int)(((j < 4 ? qw.x : qw.y) >> ((j & 3) << 3)) & 0xff);
                     // inside this aligned block, inside the tile, and not a read base N (src/plp.c:718)
-                    bool go = (j >= jlo) & (j < jhi) & ((unsigned)pidx < (unsigned)tw) & (code != 15);
+                    bool go = (j >= jlo) & (j < jhi) & ((unsigned)pidx < (unsigned)tw) & (code != 15) & ((fb >> j) & 1u);
                     if (FAST) {
                         const bool lowq = bq < minbq;
                         // src/plp.c:574 (mapq first), :580-586 (quality 0 below the threshold is dropped silently)
@@ -63,9 +89,12 @@ __device__ __forceinline__ void walk_item(const PlpParams& P, const TileSmem& S,
                             if (go && S.slot_of[pidx] != 0xffff)
                                 pass2_accumulate(P, S, c, f, s, ordinal, t0 + pidx, pidx, q0 + j, code);
                         } else if (go) {
-                            const int cls = cls_of_code_fast(code);
-                            const int k2 = (mapq_fail | lowq) ? RAER_CLS_X : ((invert && cls < 4) ? 3 - cls : cls);
-                            atomicAdd(cbase + k2 * W + CIDX(pidx, W), 1u);
+                            // A=1 C=2 G=4 T=8 -> 0..3 via (code>>1)-(code>>3); complement = xor 3; other codes -> 4
+                            int cls = ((code >> 1) - (code >> 3)) ^ cxor;
+                            if (__popc(code) != 1) cls = RAER_CLS_OTHER;
+                            const int k2 = (mapq_fail | lowq) ? RAER_CLS_X : cls;
+                            // no return value needed: RED on the shared window
+                            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cbase_s + (unsigned)((k2 * WP + CIDX(pidx, W)) << 2)) : "memory");
                         }
                     } else if (go) {
                         if (!PASS2 || S.slot_of[pidx] != 0xffff)
@@ -83,9 +112,75 @@ __device__ __forceinline__ void walk_item(const PlpParams& P, const TileSmem& S,
     }
 }
 
+// Second pass, position driven: one lane owns one staged read and visits only the flagged positions
+// (sorted tile indices flist[0..nfl), slot j <-> flist[j]) that fall inside its aligned blocks. Work is
+// proportional to (flagged sites x depth) instead of the number of bases in the tile.
+template <bool FAST>
+__device__ __forceinline__ void walk_read_flags(const PlpParams& P, const TileSmem& S, const uint32_t* rec, int f,
+                                                int t0, const uint16_t* flist, int nfl, bool mm_cfg) {
+    ReadCtx c;
+    stage_ctx(P, rec, c);
+    const unsigned fl = rec[ST_FLAGS];
+    const bool mapq_fail = (fl & STF_MAPQ_FAIL) != 0;
+    if (mapq_fail) return;  // every base of the read is nX: nothing to accumulate (src/plp.c:574)
+    const int s = c.invert ? 1 : 0;
+    const bool mm_on = !FAST && mm_cfg && (fl & (RAER_RB_MMFAIL | RAER_RB_MMERR));
+    const int ordinal = (int)rec[ST_ORD];
+    // first flagged position at or after the read start
+    int lo = 0, hi = nfl;
+    const int rel0 = c.pos - t0;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if ((int)flist[mid] < rel0) lo = mid + 1; else hi = mid;
+    }
+    int x = c.pos, y = 0, k = 0;
+    for (int j = lo; j < nfl; ++j) {
+        const int pidx = (int)flist[j];
+        const int p = t0 + pidx;
+        // advance the CIGAR cursor to the operation that covers p
+        int op = -1, len = 0;
+        while (k < c.n_cigar) {
+            const uint32_t w = c.cig[k];
+            op = cg_op(w);
+            len = cg_len(w);
+            if (op == OP_M || op == OP_EQ || op == OP_X || op == OP_D || op == OP_N) {
+                if (p < x + len) break;
+                x += len;
+                if (op == OP_M || op == OP_EQ || op == OP_X) y += len;
+            } else if (op == OP_I || op == OP_S) {
+                y += len;
+            }
+            ++k;
+        }
+        if (k >= c.n_cigar) break;  // past the end of the read
+        if (op == OP_D || op == OP_N) continue;  // deletion / ref-skip at p: filtered silently (src/plp.c:571)
+        const int q = y + (p - x);
+        if (q >= c.l_qseq) continue;
+        const int code = seq_code(c.seq, q);
+        if (code == 15) continue;
+        const int bq = c.qual[q];
+        if (FAST) {
+            if (bq < P.min_bq) continue;
+            pass2_accumulate_slot(P, S, c, f, s, ordinal, p, j, q, code);
+        } else {
+            int v = base_verdict(P, c, 0, q, bq);
+            if (v != 0) continue;
+            if (mm_on) {
+                int pref = (p < P.ref_len) ? d_upper((unsigned char)P.ref[p]) : 'N';
+                int letter = "=ACMGRSVTWYHKDBN"[code];
+                if (c.invert || letter != pref) {
+                    if (c.bits & RAER_RB_MMERR) { atomicExch(P.err_flag, RAER_ERR_MD); continue; }
+                    if (c.bits & RAER_RB_MMFAIL) continue;
+                }
+            }
+            pass2_accumulate_slot(P, S, c, f, s, ordinal, p, j, q, code);
+        }
+    }
+}
+
 template <bool PASS2, bool FAST>
 __device__ void scan_reads(const PlpParams& P, const TileSmem& S, int f, int2 rg, int t0, int t1, int span_lo,
-                           int span_hi, int lane, int wid, int nwarp) {
+                           int span_hi, int lane, int wid, int nwarp, const uint16_t* flist = nullptr, int nfl = 0) {
     uint32_t* st = S.cigs + wid * (ST_CAP * ST_WORDS + ST_CAP);
     uint32_t* pref = st + ST_CAP * ST_WORDS;
     const bool need_cov = !PASS2 && P.min_depth <= 0;
@@ -183,8 +278,11 @@ __device__ void scan_reads(const PlpParams& P, const TileSmem& S, int f, int2 rg
                     }
                 }
             }
+            if (PASS2) {
+                for (int i = lane; i < nst; i += 32) walk_read_flags<FAST>(P, S, st + i * ST_WORDS, f, t0, flist, nfl, mm_cfg);
+            }
             const float inv_nq = uni && nq0 > 0 ? 1.0f / (float)nq0 : 0.f;
-            for (int it = lane; it < tot_items; it += 32) {
+            for (int it = lane; !PASS2 && it < tot_items; it += 32) {
                 int i, first;
                 if (uni) {
                     i = __float2int_rz(((float)it + 0.5f) * inv_nq);
