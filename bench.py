@@ -214,6 +214,8 @@ def run_ours(args):
     conf.report_multiallelic, conf.remove_overlaps, conf.want_stats = 1, 1, 1
     if os.environ.get("RAER_BENCH_NO_STATS"):  # development probe: skip the second pass (not the reference behaviour)
         conf.want_stats = 0
+    if os.environ.get("RAER_BENCH_NO_OVERLAP"):  # development probe: skip the mate-overlap kernel
+        conf.remove_overlaps = 0
     for f in range(n_bams):
         conf.min_mapq[f] = 0
         conf.only_keep_variants[f] = 1

@@ -639,7 +639,7 @@ __device__ __forceinline__ void process_base(const PlpParams& P, const TileSmem&
 // shared-memory scratch. The reads are then cut into items of 8 consecutive QUERY bases; lanes take
 // items from the warp-wide item list, so there is no warp-uniform per-read work and short reads do not
 // leave lanes idle. An item costs one 32-bit sequence load and one 64-bit quality load.
-#define ST_WORDS 12
+#define ST_WORDS 13  // 12 used + 1: an odd stride keeps lanes reading the same field of different records off one bank
 enum { ST_POS = 0, ST_LEN, ST_SQ, ST_FLAGS, ST_QSQE, ST_FTRIM, ST_CIGOFF, ST_ORD, ST_CIG0 };
 #define STF_MAPQ_FAIL 0x100u
 #define STF_FTRIM_ALL 0x200u
@@ -1055,7 +1055,7 @@ extern "C" size_t raer_tile_smem_bytes(int n_files, int W, int S, int* cnt_words
     if (S * sw > cw) cw = S * sw;
     *cnt_words = cw;
     *slot_words = sw;
-    return (size_t)cw * 4 + ((W >> 5) * 2 + 4) * 4 + (size_t)W * (4 + 4 + 2 + 2 + 1) + (RAER_BLOCK / 32) * (ST_CAP * ST_WORDS + ST_CAP) * 4 + 64;
+    return (size_t)cw * 4 + ((W >> 5) * 2 + 4) * 4 + (size_t)W * (4 + 4 + 2 + 2 + 1) + (RAER_BLOCK / 32) * ST_STRIDE * 4 + 64;
 }
 
 extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* launches, cudaEvent_t e0, cudaEvent_t e1) {

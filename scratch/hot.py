@@ -26,6 +26,6 @@ for i,n in enumerate(h):
     if n in('gpu__time_duration.sum','smsp__inst_executed.sum','smsp__thread_inst_executed_per_inst_executed.ratio','smsp__issue_active.avg.pct_of_peak_sustained_active','l1tex__data_pipe_lsu_wavefronts_mem_shared.sum','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum','smsp__inst_executed_op_shared_atom.sum','launch__registers_per_thread','dram__bytes_read.sum','dram__bytes_write.sum','sm__warps_active.avg.pct_of_peak_sustained_active'): print(n,u[i],v[i])
 print("total warp inst %.3e thread inst %.3e samples %d"%(ti,tt,ts))
 N=int(sys.argv[3]) if len(sys.argv)>3 else 30
-for ln,a in sorted(agg.items(), key=lambda kv:-kv[1][0])[:N]:
+for ln,a in sorted(agg.items(), key=lambda kv:-kv[1][int(os.environ.get("SORTCOL","0"))])[:N]:
     txt = src[ln[1]-1].strip()[:95] if ln and ln[0]=='raer_kernels.cu' else str(ln)
     print("%-5s inst %5.1f%% thr/inst %4.1f samp %5.1f%%  %s"%(ln[1] if ln else '?',100*a[0]/ti,a[2]/max(a[0],1),100*a[1]/ts,txt))
