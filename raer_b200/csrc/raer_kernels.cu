@@ -340,7 +340,17 @@ __device__ double d_kf_erfc(double x) {  // htslib kfunc.c kf_erfc (AS66)
     return x > 0. ? 2. * r : 2. * (1. - r);
 }
 
-__device__ double d_calc_vdb(const uint32_t* pos) {  // src/ext/bcftools/bcftools-ext.c:51-111
+// 100-bin read-position histogram inside a second-pass slot: 32-bit bins, or two 16-bit bins per word
+struct HistView {
+    const uint32_t* w;
+    int base, narrow;
+    __device__ __forceinline__ int operator[](int i) const {
+        int b = base + i;
+        return narrow ? (int)((w[b >> 1] >> ((b & 1) << 4)) & 0xffffu) : (int)w[b];
+    }
+};
+
+__device__ double d_calc_vdb(const HistView pos) {  // src/ext/bcftools/bcftools-ext.c:51-111
     const float prm[15][3] = {{3, 0.079f, 18},    {4, 0.09f, 19.8f},  {5, 0.1f, 20.5f},   {6, 0.11f, 21.5f},
                               {7, 0.125f, 21.6f}, {8, 0.135f, 22},    {9, 0.14f, 22.2f},  {10, 0.153f, 22.3f},
                               {15, 0.19f, 22.8f}, {20, 0.22f, 23.2f}, {30, 0.26f, 23.4f}, {40, 0.29f, 23.5f},
@@ -377,7 +387,7 @@ __device__ double d_calc_vdb(const uint32_t* pos) {  // src/ext/bcftools/bcftool
     return 0.5 * d_kf_erfc((double)(-(mean_diff - pshift) * pscale));
 }
 
-__device__ double d_calc_mwu_z(const uint32_t* a, const uint32_t* b) {  // bcftools-ext.c:144-212, do_Z = 1
+__device__ double d_calc_mwu_z(const HistView a, const HistView b) {  // bcftools-ext.c:144-212, do_Z = 1
     int i;
     long long t = 0;
     for (i = 0; i < RAER_NHIST; ++i)
@@ -429,7 +439,9 @@ struct TileSmem {
     uint16_t* flag_pidx;  // W
     uint16_t* slot_of;    // W
     uint8_t* dec;         // W
-    uint32_t* cigs;       // per warp: 32 staged read records (ST_WORDS each) + 32 item prefix sums
+    uint32_t* cigs;       // per warp: staged read records + work prefix sums (raer_walk.cuh, ST_STRIDE words)
+    int hist_words;       // second pass: 400 (32-bit bins) or 200 (packed 16-bit bins), chosen per tile
+    int slot_words;       // hist_words + 4 tallies + RAER_SLOT_FS words per (file, strand)
 };
 
 __device__ __forceinline__ bool pos_eligible(const PlpParams& P, int p) {
@@ -548,22 +560,25 @@ __device__ void write_row(const PlpParams& P, const uint32_t* cnt, int pidx, int
 // tallies, first-seen order of the variant keys.
 __device__ __forceinline__ void pass2_accumulate_slot(const PlpParams& P, const TileSmem& S, const ReadCtx& c, int f, int s,
                                                       int ordinal, int p, int slot_index, int q, int code) {
-    uint32_t* slot = S.cnt + (size_t)slot_index * P.slot_words;
+    const int HW = S.hist_words;  // 400: 32-bit bins; 200: two 16-bit bins per word (tile depth <= 65535)
+    uint32_t* slot = S.cnt + (size_t)slot_index * S.slot_words;
     int pref = (p < P.ref_len) ? d_upper((unsigned char)P.ref[p]) : 'N';
     int letter = "=ACMGRSVTWYHKDBN"[code];
     int isref = letter == pref;
     int cls = cls_of_code(code);
     // strand-bias tally on the uncomplemented base (src/plp.c:762-774)
-    atomicAdd(&slot[400 + (isref ? 0 : 2) + c.rev], 1u);  // ref_fwd ref_rev alt_fwd alt_rev
+    atomicAdd(&slot[HW + (isref ? 0 : 2) + c.rev], 1u);  // ref_fwd ref_rev alt_fwd alt_rev
     // get_relative_position (src/plp_utils.c:401-412)
     int tail = c.l_qseq - c.qe;
     int alen = c.l_qseq - c.qs - tail;
     int rpos = (int)((double)(q + 1 - c.qs) / (double)(alen + 1) * 99.0);
     if (rpos < 0 || rpos >= RAER_NHIST) { atomicExch(P.err_flag, RAER_ERR); return; }
-    atomicAdd(&slot[(s * 2 + (isref ? 0 : 1)) * RAER_NHIST + rpos], 1u);
+    const int bin = (s * 2 + (isref ? 0 : 1)) * RAER_NHIST + rpos;
+    if (HW == 400) atomicAdd(&slot[bin], 1u);
+    else atomicAdd(&slot[bin >> 1], 1u << ((bin & 1) << 4));
     if (!isref) {
         int cb = (c.invert && cls < 4) ? 3 - cls : cls;
-        uint32_t* fs = slot + 404 + (f * 2 + s) * RAER_SLOT_FS;
+        uint32_t* fs = slot + HW + 4 + (f * 2 + s) * RAER_SLOT_FS;
         if (cb < 4) {
             atomicMin(&fs[cb], (unsigned)ordinal);
         } else {
@@ -605,31 +620,7 @@ __device__ __forceinline__ void process_base(const PlpParams& P, const TileSmem&
         atomicAdd(&S.cnt[(size_t)((f * 2 + s) * RAER_NCLS + k2) * WPAD(P.W) + CIDX(pidx, P.W)], 1u);
     } else {
         if (v != 0) return;
-        uint32_t* slot = S.cnt + (size_t)S.slot_of[pidx] * P.slot_words;
-        int letter = "=ACMGRSVTWYHKDBN"[code];
-        int isref = letter == pref;
-        // strand-bias tally on the uncomplemented base (src/plp.c:762-774)
-        atomicAdd(&slot[400 + (isref ? 0 : 2) + c.rev], 1u);  // ref_fwd ref_rev alt_fwd alt_rev
-        // get_relative_position (src/plp_utils.c:401-412)
-        int tail = c.l_qseq - c.qe;
-        int alen = c.l_qseq - c.qs - tail;
-        int rpos = (int)((double)(q + 1 - c.qs) / (double)(alen + 1) * 99.0);
-        if (rpos < 0 || rpos >= RAER_NHIST) { atomicExch(P.err_flag, RAER_ERR); return; }
-        atomicAdd(&slot[(s * 2 + (isref ? 0 : 1)) * RAER_NHIST + rpos], 1u);
-        if (!isref) {
-            int cb = (c.invert && cls < 4) ? 3 - cls : cls;
-            uint32_t* fs = slot + 404 + (f * 2 + s) * RAER_SLOT_FS;
-            if (cb < 4) {
-                atomicMin(&fs[cb], (unsigned)ordinal);
-            } else {
-                // IUPAC key: complement of an nt16 code is its 4-bit reversal
-                unsigned oc = c.invert ? (__brev((unsigned)code) >> 28) : (unsigned)code;
-                atomicMin(&fs[5], (unsigned)ordinal);
-                atomicMin(&fs[6], oc);
-                atomicMax(&fs[7], oc);
-            }
-            atomicMax(&fs[4], (unsigned)ordinal + 1u);  // last variant read (ordinal + 1; 0 = none)
-        }
+        pass2_accumulate(P, S, c, f, s, ordinal, p, pidx, q, code);
     }
 }
 
@@ -878,7 +869,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* scra
 __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ int s_scan[40];
-    __shared__ int s_tile, s_nflag, s_rowbase;
+    __shared__ int s_tile, s_nflag, s_rowbase, s_deep;
     const int W = P.W;
     TileSmem S;
     S.cnt = smem;
@@ -902,7 +893,7 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
         const int t1 = min(t0 + W, P.t_end);
         for (int i = threadIdx.x; i < cnt_used; i += blockDim.x) S.cnt[i] = 0;
         for (int i = threadIdx.x; i < (W >> 5); i += blockDim.x) S.covered[i] = 0;
-        if (threadIdx.x == 0) s_nflag = 0;
+        if (threadIdx.x == 0) { s_nflag = 0; s_deep = 0; }
         __syncthreads();
 
         // ---- phase 1: count
@@ -952,6 +943,10 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
                         S.flag_pidx[slot] = (uint16_t)pidx;
                         S.flag_rowp[slot] = ((d & 1) && (d & 4)) ? rp : -1;
                         S.flag_rowm[slot] = ((d & 2) && (d & 8)) ? rm : -1;
+                        // 16-bit histogram bins are safe while no flagged site is deeper than 65535 counted bases
+                        unsigned depth = 0;
+                        for (int k = 0; k < P.n_files * 2 * RAER_NCLS; ++k) depth += S.cnt[(size_t)k * WPAD(W) + CIDX(pidx, W)];
+                        if (depth > 65535u) s_deep = 1;
                     }
                 }
             }
@@ -959,16 +954,20 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
         }
         __syncthreads();
 
-        // ---- phases 3+4: second pass for the variant rows, S sites per round
+        // ---- phases 3+4: second pass for the variant rows, `spr` sites per round
         const int nflag = s_nflag;
-        for (int round0 = 0; round0 < nflag; round0 += P.S) {
-            const int ns = min(P.S, nflag - round0);
+        S.hist_words = s_deep ? 4 * RAER_NHIST : 2 * RAER_NHIST;
+        S.slot_words = S.hist_words + 4 + 2 * RAER_SLOT_FS * P.n_files;
+        const int HW = S.hist_words, SW = S.slot_words;
+        const int spr = min(P.cnt_words / SW, 4096);
+        for (int round0 = 0; round0 < nflag; round0 += spr) {
+            const int ns = min(spr, nflag - round0);
             for (int i = threadIdx.x; i < W; i += blockDim.x) S.slot_of[i] = 0xffff;
-            for (int i = threadIdx.x; i < ns * P.slot_words; i += blockDim.x) {
-                int wsl = i % P.slot_words;
+            for (int i = threadIdx.x; i < ns * SW; i += blockDim.x) {
+                int wsl = i % SW;
                 // first-seen ordinals (and the minimum IUPAC code) start at +inf, everything else at 0
-                int fw = (wsl - 404) % RAER_SLOT_FS;
-                bool is_fs = wsl >= 404 && (fw < 4 || fw == 5 || fw == 6);
+                int fw = (wsl - (HW + 4)) % RAER_SLOT_FS;
+                bool is_fs = wsl >= HW + 4 && (fw < 4 || fw == 5 || fw == 6);
                 S.cnt[i] = is_fs ? 0xffffffffu : 0u;
             }
             __syncthreads();
@@ -990,19 +989,19 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
             }
             __syncthreads();
             for (int i = threadIdx.x; i < ns; i += blockDim.x) {
-                const uint32_t* slot = S.cnt + (size_t)i * P.slot_words;
+                const uint32_t* slot = S.cnt + (size_t)i * SW;
                 int rowp = S.flag_rowp[round0 + i], rowm = S.flag_rowm[round0 + i];
-                double sor = d_calc_sor((int)slot[400], (int)slot[401], (int)slot[402], (int)slot[403]);
+                double sor = d_calc_sor((int)slot[HW], (int)slot[HW + 1], (int)slot[HW + 2], (int)slot[HW + 3]);
                 for (int s = 0; s < 2; ++s) {
                     long long row = s == 0 ? rowp : rowm;
                     if (row < 0) continue;
-                    const uint32_t* hr = slot + (s * 2) * RAER_NHIST;
-                    const uint32_t* ha = slot + (s * 2 + 1) * RAER_NHIST;
+                    const HistView hr = {slot, (s * 2) * RAER_NHIST, HW != 4 * RAER_NHIST};
+                    const HistView ha = {slot, (s * 2 + 1) * RAER_NHIST, HW != 4 * RAER_NHIST};
                     P.row_stats[row * 3 + 0] = d_calc_mwu_z(hr, ha);
                     P.row_stats[row * 3 + 1] = d_calc_vdb(ha);
                     P.row_stats[row * 3 + 2] = sor;
                     for (int f = 0; f < P.n_files; ++f) {
-                        const uint32_t* fs = slot + 404 + (f * 2 + s) * RAER_SLOT_FS;
+                        const uint32_t* fs = slot + HW + 4 + (f * 2 + s) * RAER_SLOT_FS;
                         // order the (at most 5) variant keys by first-seen ordinal: 0..3 = ACGT, 4 = IUPAC key
                         unsigned ord[5] = {fs[0], fs[1], fs[2], fs[3], fs[5]};
                         unsigned code = 0;
