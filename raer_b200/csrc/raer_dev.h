@@ -34,6 +34,8 @@ struct PlpParams {
     // tiling
     int t_beg, t_end, W, n_tiles;
     int2* tile_ranges;               // [n_tiles][n_files] {lo, hi}
+    const int* tile_off;             // k_pileup_fast: [n_tiles * n_files + 1] offsets into tile_list
+    const int* tile_list;            //   indices of the reads overlapping each (tile, file)
     unsigned int* tile_counter;      // dynamic tile scheduler
     // reference of the contig
     const char* ref;
@@ -42,6 +44,7 @@ struct PlpParams {
     int min_depth, min_bq, trim_5p, trim_3p, indel_dist, splice_dist, min_overhang, nmer, min_var_reads;
     int n_mm_type, n_mm, report_multiallelic, want_stats, any_okv;
     int fast;                        // only mapq / base-quality filters configured: branch-free item path
+    int use_fast;                    // launch k_pileup_fast (raer_fast.cuh) instead of k_pileup_tiles
     double ftrim_5p, ftrim_3p, min_af;
     int min_mapq[RAER_MAX_FILES];
     int okv[RAER_MAX_FILES];

@@ -1,0 +1,705 @@
+// raer_fast.cuh -- k_pileup_fast: the tile kernel for the common configuration (only the mapq and
+// base-quality filters of check_read_filters are active, src/plp.c:568-586). Included from
+// raer_kernels.cu; every other configuration runs k_pileup_tiles.
+//
+// The reference touches a counter for every aligned base. Here a base that equals the reference and
+// passes the quality filter touches nothing:
+//   * coverage per (file, strand) comes from +1/-1 events at the ends of each aligned block, written once
+//     per read while its record is staged, and one prefix sum per tile;
+//   * the 8 query bases of an item (one 32-bit sequence word, one 64-bit quality word) are compared with
+//     8 packed reference bases by XOR, and with the quality threshold by byte-parallel arithmetic;
+//   * only exceptional bases -- mismatch, quality below the threshold, N -- run scalar code and issue a
+//     shared-memory RED; runs of quality 0 (what htslib's mate-overlap rule leaves behind) are taken out
+//     of the coverage with one -1/+1 event pair per run;
+//   * nRef of a site = coverage - everything explicit (CntPacked::get).
+// Counters are 16-bit pairs in 32-bit words (A|C, G|T, other|X): a tile whose coverage exceeds 65535 is
+// reported through err_flag (RAER_ERR_LIMIT).
+//
+// Reads reach a tile through per-tile index lists built by k_tile_count / k_tile_scan / k_tile_fill (every
+// read that overlaps the tile, nothing else), so the CTA stages dense batches of FCAP read records in
+// shared memory and all 512 threads take items from one batch-wide list: no idle lanes for reads that only
+// pass by, no per-warp tails. The second pass (read-position histograms, strand tallies and first-seen
+// order at the sites that carry a variant) is the same walk with a packed "flagged position" mask in place
+// of the reference compare; sequence and qualities are only fetched for items that touch a flagged site.
+// Two CTAs of 512 threads per SM.
+#ifndef RAER_FAST_CUH
+#define RAER_FAST_CUH
+
+#define FB_THREADS 512
+#define FCAP 768  // read records staged per batch
+#define FREC 11   // words per record (odd: lanes reading one field of different records spread over banks)
+enum { FR_POS = 0, FR_LEN, FR_SQ, FR_FLAGS, FR_QSQE, FR_ORD, FR_CIG0 };  // FR_CIG0..+3: CIGAR words, or [0] = offset if n > 4
+#define FRF_FILE_SHIFT 24
+#define FWS(W) ((W) + 8)  // words per counter array: W positions + the -1 event one past the end
+
+struct FastSmem {
+    uint32_t* cnt;      // [file][strand]{coverage events, A|C<<16, G|T<<16, other|X<<16}[WS]; second-pass slots later
+    uint32_t* refn;     // packed reference: nibble i of word k = nt16 code of position t0 - 8 + 8k + i
+    uint32_t* fnib;     // second pass: same geometry, nibble = 1 where the position is flagged in this round
+    uint32_t* covered;  // min_depth <= 0 only: a pileup column exists here
+    int* flag_row;      // per flagged site: its first output row
+    uint32_t* stage;    // FCAP records
+    uint16_t* slot_of;  // per position: rank among the tile's flagged sites, 0xffff = none
+    uint8_t* flag_d;    // per flagged site: decision bits
+    uint8_t* dec;       // per position: decision bits
+    int WS;
+};
+
+__device__ __forceinline__ void red_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+// BAM packs base 2b in the high nibble of byte b; after the swap base j sits in nibble j of the word
+__device__ __forceinline__ uint32_t nib_swap(uint32_t w) { return ((w & 0x0f0f0f0fu) << 4) | ((w >> 4) & 0x0f0f0f0fu); }
+__device__ __forceinline__ uint32_t nib_nonzero(uint32_t x) {  // bit 4j set iff nibble j != 0
+    uint32_t t = x | (x >> 2);
+    t |= t >> 1;
+    return t & 0x11111111u;
+}
+// per byte: bit 7 set iff byte < m (m4 = m in every byte, m <= 128: no borrow crosses a byte)
+__device__ __forceinline__ uint32_t byte_lt(uint32_t v, uint32_t m4) { return ~(((v | 0x80808080u) - m4) | v) & 0x80808080u; }
+__device__ __forceinline__ uint32_t byte_zero(uint32_t v) { return ~(((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u; }
+// low nibble of byte j of lo -> nibble j, of hi -> nibble 4 + j
+__device__ __forceinline__ uint32_t bytes_to_nibbles(uint32_t lo, uint32_t hi) {
+    lo = (lo | (lo >> 4)) & 0x00ff00ffu;
+    lo = (lo | (lo >> 8)) & 0xffffu;
+    hi = (hi | (hi >> 4)) & 0x00ff00ffu;
+    hi = ((hi << 16) | (hi << 8)) & 0xffff0000u;
+    return lo | hi;
+}
+// nt16 code of the upper-cased reference letter; letters outside the nt16 alphabet -> 0 (never equal to a
+// read base except the never-produced '=' code), beyond the contig -> N
+__device__ __forceinline__ int ref_nibble(const PlpParams& P, int p) {
+    if (!P.ref || p < 0 || p >= P.ref_len) return 15;
+    const int u = d_upper((unsigned char)__ldg(P.ref + p));
+    if (u < 'A' || u > 'Y') return 0;
+    //                                   A  B  C  D  E F G  H  I J K   L M N   O P Q R S T U V W X Y
+    const unsigned char lut[25] = {1, 14, 2, 13, 0, 0, 4, 11, 0, 0, 12, 0, 3, 15, 0, 0, 0, 5, 6, 8, 0, 7, 9, 0, 10};
+    return lut[u - 'A'];
+}
+__device__ __forceinline__ void cover_range(uint32_t* cov, int lo, int hi) {  // tile-relative [lo, hi), lo < hi
+    const int w0 = lo >> 5, w1 = (hi - 1) >> 5;
+    for (int w = w0; w <= w1; ++w) {
+        uint32_t m = 0xffffffffu;
+        if (w == w0) m &= 0xffffffffu << (lo & 31);
+        if (w == w1) m &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+        atomicOr(&cov[w], m);
+    }
+}
+
+struct FastCtx {  // per-kernel constants of the item walk
+    int t0, tw, minbq;
+    uint32_t mb4, zall;
+    int round0, ns, HW, SW;  // second pass: flagged ranks [round0, round0 + ns) own slots of SW words
+};
+
+// ---- phase 1: one aligned block's share of an item. Bases j in [jlo, jhi) sit on tile positions rel + j.
+__device__ __forceinline__ void fast_block_count(const FastSmem& S, const FastCtx& X, uint32_t* cb, uint32_t rw, uint2 qw,
+                                                 uint32_t LT, uint32_t Z, bool mapq_fail, int cxor, int rel, int jlo, int jhi) {
+    const int lo = max(max(jlo, -rel), 0), hi = min(min(jhi, X.tw - rel), 8);
+    if (lo >= hi) return;
+    const uint32_t V = (0x11111111u >> ((8 - (hi - lo)) << 2)) << (lo << 2);
+    const int a = rel + 8;  // >= 1 here: index of the item's first base in the packed reference
+    const uint32_t refw = __funnelshift_r(S.refn[a >> 3], S.refn[(a >> 3) + 1], (a & 7) << 2);
+    uint32_t E, ZZ;
+    if (mapq_fail) {  // every base of the read is nX (src/plp.c:574), read base N still counted nowhere (:718)
+        E = V;
+        ZZ = 0;
+    } else {
+        ZZ = Z & V;  // quality 0 below the threshold: dropped silently (src/plp.c:580-586)
+        E = (nib_nonzero(rw ^ refw) | LT) & V & ~ZZ;
+    }
+    // runs of dropped bases leave the coverage: -1 where a run starts, +1 after its end
+    uint32_t rs = ZZ & ~(ZZ << 4), re = ZZ & ~(ZZ >> 4);
+    while (rs) {
+        const int b1 = __ffs(rs) - 1, b2 = __ffs(re) - 1;
+        rs &= rs - 1;
+        re &= re - 1;
+        red_add(cb + rel + (b1 >> 2), 0xffffffffu);
+        red_add(cb + rel + (b2 >> 2) + 1, 1u);
+    }
+    while (E) {
+        const int b = __ffs(E) - 1;
+        E &= E - 1;
+        const int j = b >> 2, p = rel + j;
+        const int code = (rw >> b) & 15;
+        if (code == 15) {  // read base N
+            red_add(cb + p, 0xffffffffu);
+            red_add(cb + p + 1, 1u);
+            continue;
+        }
+        const int bq = __byte_perm(qw.x, qw.y, j) & 0xff;
+        uint32_t* dst;
+        uint32_t val;
+        if (mapq_fail | (bq < X.minbq)) {  // nX
+            dst = cb + 3 * S.WS + p;
+            val = 0x10000u;
+        } else {
+            // A=1 C=2 G=4 T=8 -> 0..3; complement on the minus strand = xor 3; any other code -> other
+            int cls = ((code >> 1) - (code >> 3)) ^ cxor;
+            if (__popc(code) != 1) cls = RAER_CLS_OTHER;
+            dst = cb + (1 + (cls >> 1)) * S.WS + p;
+            val = 1u << ((cls & 1) << 4);
+        }
+        red_add(dst, val);
+    }
+}
+
+// ---- second pass: the bases of one aligned block that sit on flagged positions
+__device__ __forceinline__ void fast_block_stats(const PlpParams& P, const FastSmem& S, const FastCtx& X, const TileSmem& T2,
+                                                 const uint32_t* rec, int q0, int rel, int jlo, int jhi) {
+    const int lo = max(max(jlo, -rel), 0), hi = min(min(jhi, X.tw - rel), 8);
+    if (lo >= hi) return;
+    const uint32_t V = (0x11111111u >> ((8 - (hi - lo)) << 2)) << (lo << 2);
+    const int a = rel + 8;
+    const int sh = (a & 7) << 2;
+    uint32_t E = __funnelshift_r(S.fnib[a >> 3], S.fnib[(a >> 3) + 1], sh) & V;
+    if (!E) return;
+    const uint32_t refw = __funnelshift_r(S.refn[a >> 3], S.refn[(a >> 3) + 1], sh);
+    const uint32_t sq = rec[FR_SQ];
+    const uint32_t rw = nib_swap(__ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (q0 >> 1))));
+    const uint2 qw = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + q0));
+    const unsigned fl = rec[FR_FLAGS];
+    ReadCtx c;
+    c.l_qseq = (int)(rec[FR_LEN] & 0xffff);
+    c.qs = (int)(rec[FR_QSQE] & 0xffff);
+    c.qe = (int)(rec[FR_QSQE] >> 16);
+    c.rev = (fl >> 16) & 1;
+    c.invert = fl & RAER_RB_INVERT;
+    const int f = (int)(fl >> FRF_FILE_SHIFT);
+    while (E) {
+        const int b = __ffs(E) - 1;
+        E &= E - 1;
+        const int j = b >> 2;
+        const int code = (rw >> b) & 15;
+        if (code == 15) continue;                                       // src/plp.c:718
+        if ((int)(__byte_perm(qw.x, qw.y, j) & 0xff) < X.minbq) continue;  // nX or dropped: not counted
+        const int rcode = (refw >> b) & 15;
+        const int isref = (code == rcode) & (code != 0);
+        pass2_accumulate_core(P, T2, c, f, c.invert ? 1 : 0, (int)rec[FR_ORD], (int)S.slot_of[rel + j] - X.round0, q0 + j, code,
+                              isref);
+    }
+}
+
+template <int PASS>
+__device__ __forceinline__ void fast_item(const PlpParams& P, const FastSmem& S, const FastCtx& X, const TileSmem& T2,
+                                          const uint32_t* rec, int q0, uint32_t sw, uint2 qw) {
+    const int pos = (int)rec[FR_POS];
+    const int lq = (int)(rec[FR_LEN] & 0xffff), n = (int)(rec[FR_LEN] >> 16);
+    const unsigned fl = rec[FR_FLAGS];
+    const int q1 = min(q0 + 8, lq);
+    const bool mapq_fail = (fl & STF_MAPQ_FAIL) != 0;
+    const int s = fl & RAER_RB_INVERT;
+    uint32_t* cb = nullptr;
+    uint32_t rw = 0, LT = 0, Z = 0;
+    if (PASS == 0) {
+        cb = S.cnt + (size_t)(((fl >> FRF_FILE_SHIFT) * 2 + s) * 4) * S.WS;
+        rw = nib_swap(sw);
+        // nibble j: bit 0 = quality below the threshold, bit 1 = quality 0
+        const uint32_t Q = bytes_to_nibbles((byte_lt(qw.x, X.mb4) >> 7) | (byte_zero(qw.x) >> 6),
+                                            (byte_lt(qw.y, X.mb4) >> 7) | (byte_zero(qw.y) >> 6));
+        LT = Q & 0x11111111u;
+        Z = (Q >> 1) & 0x11111111u & X.zall;
+    }
+    const uint32_t* cig = n <= 4 ? rec + FR_CIG0 : P.cigar + rec[FR_CIG0];
+    int x = pos, y = 0;
+    for (int k = 0; k < n && y < q1; ++k) {
+        const uint32_t w = cig[k];
+        const int op = cg_op(w), len = cg_len(w);
+        if ((0x181 >> op) & 1) {  // M = X
+            if (y + len > q0) {
+                const int rel = x + (q0 - y) - X.t0, jlo = y - q0, jhi = min(y + len, q1) - q0;
+                if (PASS == 0) fast_block_count(S, X, cb, rw, qw, LT, Z, mapq_fail, s ? 3 : 0, rel, jlo, jhi);
+                else fast_block_stats(P, S, X, T2, rec, q0, rel, jlo, jhi);
+            }
+            x += len;
+            y += len;
+        } else if ((0xC >> op) & 1) {  // D N
+            x += len;
+        } else if ((0x12 >> op) & 1) {  // I S
+            y += len;
+        }
+    }
+}
+
+// Stage one read record (thread per read). PASS 0 also writes the read's coverage events.
+template <int PASS, bool NEEDCOV>
+__device__ __forceinline__ int fast_stage(const PlpParams& P, const FastSmem& S, const FastCtx& X, int r, int f, int t1,
+                                          int span_lo, int span_hi, uint32_t* rec) {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(P.hdr + r));
+    const int4 b = __ldg(reinterpret_cast<const int4*>(P.hdr + r) + 1);
+    const int flag = a.z & 0xffff, mapq = (a.z >> 16) & 0xff, bits = (a.z >> 24) & 0xff;
+    const int lq = a.w & 0xffff, n = (a.w >> 16) & 0xffff;
+    const bool mapq_fail = mapq < P.min_mapq[f];
+    if (PASS == 1 && (mapq_fail || a.y <= span_lo || a.x >= span_hi)) {
+        rec[FR_LEN] = 0;  // a read below the mapq threshold only produces nX: nothing to accumulate (src/plp.c:574)
+        return 0;
+    }
+    const int s = bits & RAER_RB_INVERT;
+    unsigned fl = (unsigned)bits | ((unsigned)((flag >> 4) & 1) << 16) | ((unsigned)f << FRF_FILE_SHIFT);
+    if (mapq_fail) fl |= STF_MAPQ_FAIL;
+    const uint32_t* cg = P.cigar + (unsigned)b.x;
+    if (PASS == 0) {
+        uint32_t* dl = S.cnt + (size_t)((f * 2 + s) * 4) * S.WS;
+        int x = a.x, y = 0;
+        for (int k = 0; k < n; ++k) {
+            const uint32_t w = __ldg(cg + k);
+            if (k < 4) rec[FR_CIG0 + k] = w;
+            const int op = cg_op(w), len = cg_len(w);
+            if (NEEDCOV && (cg_type(op) & 2)) {
+                const int lo = max(x, X.t0), h2 = min(x + len, t1);
+                if (lo < h2) cover_range(S.covered, lo - X.t0, h2 - X.t0);
+            }
+            if ((0x181 >> op) & 1) {
+                // coverage events of the aligned block, clipped to the tile (and to the bases the read really has)
+                const int lo = max(x, X.t0), h2 = min(x + min(len, lq - y), t1);
+                if (lo < h2) {
+                    red_add(dl + (lo - X.t0), 1u);
+                    red_add(dl + (h2 - X.t0), 0xffffffffu);
+                }
+                x += len;
+                y += len;
+            } else if ((0xC >> op) & 1) {
+                x += len;
+            } else if ((0x12 >> op) & 1) {
+                y += len;
+            }
+        }
+    } else {
+        // query_start / query_end (src/plp_utils.c:52-104): soft clips at either end, hard clips skipped
+        int qs = 0, qe = lq, k;
+        for (k = 0; k < n; ++k) {
+            const uint32_t w = __ldg(cg + k);
+            if (k < 4) rec[FR_CIG0 + k] = w;
+            const int op = cg_op(w);
+            if (op == OP_H) continue;
+            if (op == OP_S) qs += cg_len(w);
+            else break;
+        }
+        for (++k; k < n && k < 4; ++k) rec[FR_CIG0 + k] = __ldg(cg + k);
+        for (k = n - 1; k >= 0; --k) {
+            const uint32_t w = __ldg(cg + k);
+            const int op = cg_op(w);
+            if (op == OP_H) continue;
+            if (op == OP_S) qe -= cg_len(w);
+            else break;
+        }
+        rec[FR_QSQE] = (uint32_t)qs | ((uint32_t)qe << 16);
+        rec[FR_ORD] = (uint32_t)(r - (int)P.file_off[f]);
+    }
+    if (n > 4) rec[FR_CIG0] = (uint32_t)b.x;
+    rec[FR_POS] = (uint32_t)a.x;
+    rec[FR_LEN] = (uint32_t)lq | ((uint32_t)n << 16);
+    rec[FR_SQ] = (uint32_t)b.y;
+    rec[FR_FLAGS] = fl;
+    return (lq + 7) >> 3;
+}
+
+// Walk every read of the tile: stage dense batches of FCAP records, then take items from the batch-wide list.
+template <int PASS>
+__device__ void fast_walk(const PlpParams& P, const FastSmem& S, const FastCtx& X, const TileSmem& T2, int tile, int t1,
+                          int span_lo, int span_hi, int* s_ni) {
+    const int F = P.n_files;
+    const int l0 = P.tile_off[tile * F], l1 = P.tile_off[tile * F + F];
+    const bool need_cov = P.min_depth <= 0;
+    int parity = 0;
+    for (int base = l0; base < l1; base += FCAP, parity ^= 1) {
+        const int nb = min(FCAP, l1 - base);
+        int ni = 0;
+        for (int k = threadIdx.x; k < nb; k += FB_THREADS) {
+            const int li = base + k;
+            int f = 0;
+            while (f + 1 < F && li >= P.tile_off[tile * F + f + 1]) ++f;
+            const int r = __ldg(P.tile_list + li);
+            uint32_t* rec = S.stage + k * FREC;
+            int nq;
+            if (PASS == 0 && need_cov) nq = fast_stage<PASS, true>(P, S, X, r, f, t1, span_lo, span_hi, rec);
+            else nq = fast_stage<PASS, false>(P, S, X, r, f, t1, span_lo, span_hi, rec);
+            ni = max(ni, nq);
+        }
+        ni = __reduce_max_sync(FULL, ni);
+        if ((threadIdx.x & 31) == 0 && ni > 0) atomicMax(&s_ni[parity], ni);
+        __syncthreads();
+        const int NI = s_ni[parity];  // item slots per record of this batch
+        if (threadIdx.x == 0) s_ni[parity ^ 1] = 0;
+        if (NI > 0) {
+            const int tot = nb * NI;
+            const uint32_t M32 = (uint32_t)((0x100000000ull + NI - 1) / NI);  // it / NI == umulhi(it, M32) while it * NI < 2^32
+            const bool mul_ok = NI > 1 && (unsigned long long)tot * NI < 0x100000000ull;
+            for (int itb = 0; itb < tot; itb += 2 * FB_THREADS) {
+                // The trip count is CTA-uniform, so the warp can be re-joined here: without it the lanes that took
+                // different paths through the previous items keep running as separate sub-warps.
+                __syncwarp();
+                const int it0 = itb + threadIdx.x;
+                // two items in flight per thread
+                const uint32_t* recA = S.stage;
+                const uint32_t* recB = S.stage;
+                int qA = 0, qB = 0;
+                bool okA, okB;
+                uint32_t swA = 0, swB = 0;
+                uint2 qwA = make_uint2(0, 0), qwB = make_uint2(0, 0);
+                {
+                    const int it = it0;
+                    okA = it < tot;
+                    if (okA) {
+                        const int i = mul_ok ? (int)__umulhi((uint32_t)it, M32) : it / NI;
+                        recA = S.stage + i * FREC;
+                        qA = (it - i * NI) << 3;
+                        okA = qA < (int)(recA[FR_LEN] & 0xffff);
+                    }
+                    if (PASS == 0 && okA) {
+                        const uint32_t sq = recA[FR_SQ];
+                        swA = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qA >> 1)));
+                        qwA = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qA));
+                    }
+                }
+                {
+                    const int it = it0 + FB_THREADS;
+                    okB = it < tot;
+                    if (okB) {
+                        const int i = mul_ok ? (int)__umulhi((uint32_t)it, M32) : it / NI;
+                        recB = S.stage + i * FREC;
+                        qB = (it - i * NI) << 3;
+                        okB = qB < (int)(recB[FR_LEN] & 0xffff);
+                        if (PASS == 0 && okB) {
+                            const uint32_t sq = recB[FR_SQ];
+                            swB = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qB >> 1)));
+                            qwB = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qB));
+                        }
+                    }
+                }
+                if (okA) fast_item<PASS>(P, S, X, T2, recA, qA, swA, qwA);
+                if (okB) fast_item<PASS>(P, S, X, T2, recB, qB, swB, qwB);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// rpbz / vdb / sor and the ALT order codes of one second-pass slot (shared by both tile kernels)
+__device__ void slot_stats(const PlpParams& P, const uint32_t* slot, int HW, int rowp, int rowm) {
+    const double sor = d_calc_sor((int)slot[HW], (int)slot[HW + 1], (int)slot[HW + 2], (int)slot[HW + 3]);
+    for (int s = 0; s < 2; ++s) {
+        const long long row = s == 0 ? rowp : rowm;
+        if (row < 0) continue;
+        const HistView hr = {slot, (s * 2) * RAER_NHIST, HW != 4 * RAER_NHIST};
+        const HistView ha = {slot, (s * 2 + 1) * RAER_NHIST, HW != 4 * RAER_NHIST};
+        P.row_stats[row * 3 + 0] = d_calc_mwu_z(hr, ha);
+        P.row_stats[row * 3 + 1] = d_calc_vdb(ha);
+        P.row_stats[row * 3 + 2] = sor;
+        for (int f = 0; f < P.n_files; ++f) {
+            const uint32_t* fs = slot + HW + 4 + (f * 2 + s) * RAER_SLOT_FS;
+            // order the (at most 5) variant keys by first-seen ordinal: 0..3 = ACGT, 4 = IUPAC key
+            unsigned ord[5] = {fs[0], fs[1], fs[2], fs[3], fs[5]};
+            unsigned code = 0;
+            int nins = 0;
+            unsigned third = 0;
+            for (int k = 0; k < 5; ++k) {
+                int best = -1;
+                for (int b = 0; b < 5; ++b)
+                    if (ord[b] != 0xffffffffu && (best < 0 || ord[b] < ord[best])) best = b;
+                if (best < 0) break;
+                code |= (unsigned)best << (3 * nins);
+                if (nins == 2) third = ord[best];
+                ord[best] = 0xffffffffu;
+                ++nins;
+            }
+            unsigned alt = P.row_alt[row * P.n_files + f] & (RAER_ALT_MASK | RAER_ALT_OTHER);
+            alt |= code << RAER_ALT_ORDER_SHIFT;
+            alt |= (unsigned)nins << RAER_ALT_NINS_SHIFT;
+            // kh_put resizes 4 -> 8 buckets when a put arrives with 3 keys occupied (khash.h)
+            if (nins >= 3 && fs[4] > third + 1u) alt |= RAER_ALT_GROW;
+            if (fs[5] != 0xffffffffu) {
+                alt |= (fs[6] & 0xfu) << RAER_ALT_OCODE_SHIFT;
+                if (fs[6] != fs[7]) alt |= RAER_ALT_OAMBIG;
+            }
+            P.row_alt[row * P.n_files + f] = alt;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ int s_scan[40];
+    __shared__ int s_tile, s_nflag, s_rowbase, s_deep;
+    __shared__ int s_ni[2];
+    const int W = P.W, F = P.n_files;
+    FastSmem S;
+    S.WS = FWS(W);
+    const int cnt_words = F * 8 * S.WS;
+    S.cnt = smem;
+    S.refn = S.cnt + cnt_words;
+    S.fnib = S.refn + (W >> 3) + 4;
+    S.covered = S.fnib + (W >> 3) + 4;
+    S.flag_row = (int*)(S.covered + (W >> 5) + 1);
+    S.stage = (uint32_t*)(S.flag_row + W);
+    S.slot_of = (uint16_t*)(S.stage + FCAP * FREC);
+    S.flag_d = (uint8_t*)(S.slot_of + W);
+    S.dec = S.flag_d + W;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const CntPacked CN = {S.cnt, S.WS};
+    TileSmem T2;
+    T2.cnt = S.cnt;
+    T2.hist_words = 2 * RAER_NHIST;  // coverage <= 65535 in this kernel: two 16-bit bins per word
+    T2.slot_words = T2.hist_words + 4 + 2 * RAER_SLOT_FS * F;
+    FastCtx X;
+    X.minbq = P.min_bq;
+    X.mb4 = (uint32_t)max(P.min_bq, 0) * 0x01010101u;
+    X.zall = P.min_bq > 0 ? 0xffffffffu : 0u;
+    X.HW = T2.hist_words;
+    X.SW = T2.slot_words;
+    X.round0 = 0;
+    X.ns = 0;
+
+    while (true) {
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(P.tile_counter, 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= P.n_tiles) break;
+        const int t0 = P.t_beg + tile * W;
+        const int t1 = min(t0 + W, P.t_end);
+        X.t0 = t0;
+        X.tw = t1 - t0;
+        {
+            uint4* z = reinterpret_cast<uint4*>(S.cnt);
+            for (int i = threadIdx.x; i < (cnt_words >> 2); i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        }
+        for (int i = threadIdx.x; i < (W >> 5) + 1; i += blockDim.x) S.covered[i] = 0;
+        for (int i = threadIdx.x; i < (W >> 3) + 3; i += blockDim.x) {
+            uint32_t w = 0;
+            const int p0 = t0 - 8 + 8 * i;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) w |= (uint32_t)ref_nibble(P, p0 + m) << (4 * m);
+            S.refn[i] = w;
+        }
+        if (threadIdx.x == 0) { s_nflag = 0; s_deep = 0; s_ni[0] = 0; s_ni[1] = 0; }
+        __syncthreads();
+
+        // ---- phase 1: coverage events + exceptional bases
+        fast_walk<0>(P, S, X, T2, tile, t1, t0, t1, s_ni);
+
+        // ---- coverage: prefix sum of the events, one warp per (file, strand)
+        for (int a = wid; a < 2 * F; a += FB_THREADS / 32) {
+            uint32_t* dl = S.cnt + (size_t)(a * 4) * S.WS;
+            uint32_t carry = 0;
+            for (int e0 = 0; e0 < W; e0 += 128) {
+                const int e = e0 + lane * 4;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (e < W) v = *reinterpret_cast<uint4*>(dl + e);
+                v.y += v.x; v.z += v.y; v.w += v.z;
+                uint32_t inc = v.w;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += u;
+                }
+                const uint32_t ex = inc - v.w + carry;
+                v.x += ex; v.y += ex; v.z += ex; v.w += ex;
+                if (e < W) {
+                    *reinterpret_cast<uint4*>(dl + e) = v;
+                    if (max(max(v.x, v.y), max(v.z, v.w)) > 65535u) s_deep = 1;
+                }
+                carry += __shfl_sync(FULL, inc, 31);
+            }
+        }
+        __syncthreads();
+        if (s_deep) atomicExch(P.err_flag, RAER_ERR_LIMIT);  // 16-bit class counters cannot hold this tile
+
+        // ---- phase 2: decide, reserve rows, write them in (pos, strand) order
+        int my_rows = 0;
+        for (int pidx = threadIdx.x; pidx < W; pidx += blockDim.x) {
+            int d = 0;
+            if (t0 + pidx < t1) d = decide_site(P, CN, S.covered, pidx, t0 + pidx);
+            S.dec[pidx] = (uint8_t)d;
+            S.slot_of[pidx] = 0xffff;
+            my_rows += (d & 1) + ((d >> 1) & 1);
+        }
+        int tile_rows_total;
+        block_exclusive_scan(my_rows, &tile_rows_total, s_scan);
+        if (threadIdx.x == 0) {
+            long long base = (long long)atomicAdd(P.row_counter, (unsigned long long)tile_rows_total);
+            if (base + tile_rows_total > P.row_cap) { atomicExch(P.err_flag, RAER_ERR_LIMIT); base = -1; }
+            s_rowbase = (int)base;
+            P.tile_rows[tile] = make_int2((int)base, base < 0 ? 0 : tile_rows_total);
+        }
+        __syncthreads();
+        const long long rowbase = s_rowbase;
+        if (rowbase >= 0 && tile_rows_total > 0) {
+            int carried = 0, fcarried = 0;
+            for (int chunk = 0; chunk < W; chunk += blockDim.x) {
+                const int pidx = chunk + threadIdx.x;
+                const int d = pidx < W ? S.dec[pidx] : 0;
+                const int n = (d & 1) + ((d >> 1) & 1);
+                const bool fl = P.want_stats && (((d & 1) && (d & 4)) || ((d & 2) && (d & 8)));
+                int tot, ftot;
+                const int off = block_exclusive_scan(n, &tot, s_scan) + carried;
+                const int rank = block_exclusive_scan(fl ? 1 : 0, &ftot, s_scan) + fcarried;  // position-sorted
+                carried += tot;
+                fcarried += ftot;
+                if (n) {
+                    const long long row = rowbase + off;
+                    if (d & 1) write_row(P, CN, pidx, t0 + pidx, 0, row);
+                    if (d & 2) write_row(P, CN, pidx, t0 + pidx, 1, row + (d & 1));
+                    if (fl) {
+                        S.slot_of[pidx] = (uint16_t)rank;
+                        S.flag_row[rank] = (int)row;
+                        S.flag_d[rank] = (uint8_t)d;
+                    }
+                }
+            }
+            if (threadIdx.x == 0) s_nflag = fcarried;
+        }
+        __syncthreads();
+
+        // ---- phases 3+4: second pass over the sites that carry a variant, `spr` sites per round
+        const int nflag = s_nflag;
+        const int HW = X.HW, SW = X.SW;
+        const int spr = min(cnt_words / SW, 4096);
+        for (int round0 = 0; round0 < nflag; round0 += spr) {
+            const int ns = min(spr, nflag - round0);
+            X.round0 = round0;
+            X.ns = ns;
+            for (int i = threadIdx.x; i < ns * SW; i += blockDim.x) {
+                const int wsl = i % SW;
+                // first-seen ordinals (and the minimum IUPAC code) start at +inf, everything else at 0
+                const int fw = (wsl - (HW + 4)) % RAER_SLOT_FS;
+                const bool is_fs = wsl >= HW + 4 && (fw < 4 || fw == 5 || fw == 6);
+                S.cnt[i] = is_fs ? 0xffffffffu : 0u;
+            }
+            for (int i = threadIdx.x; i < (W >> 3) + 3; i += blockDim.x) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const int pidx = 8 * i + m - 8;
+                    if (pidx >= 0 && pidx < W) {
+                        const int rk = (int)S.slot_of[pidx] - round0;
+                        if (S.slot_of[pidx] != 0xffff && rk >= 0 && rk < ns) w |= 1u << (4 * m);
+                    }
+                }
+                S.fnib[i] = w;
+            }
+            if (threadIdx.x == 0) { s_ni[0] = 0; s_ni[1] = 0; }
+            __syncthreads();
+            const int span_lo = t0, span_hi = t1;
+            fast_walk<1>(P, S, X, T2, tile, t1, span_lo, span_hi, s_ni);
+            for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+                const int d = S.flag_d[round0 + i], row = S.flag_row[round0 + i];
+                slot_stats(P, S.cnt + (size_t)i * SW, HW, ((d & 1) && (d & 4)) ? row : -1,
+                           ((d & 2) && (d & 8)) ? row + (d & 1) : -1);
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+}
+
+// ---- per-tile read lists: every read that overlaps the tile [t_beg + t*W, +W), per (tile, file)
+__device__ __forceinline__ bool tile_span(const PlpParams& P, long long r, int& f, int& tf, int& tl) {
+    f = 0;
+    while (f + 1 < P.n_files && r >= P.file_off[f + 1]) ++f;
+    const int2 pe = __ldg(reinterpret_cast<const int2*>(P.hdr + r));
+    if (pe.y <= P.t_beg || pe.x >= P.t_end || pe.y <= pe.x) return false;
+    tf = (max(pe.x, P.t_beg) - P.t_beg) / P.W;
+    tl = (min(pe.y, P.t_end) - 1 - P.t_beg) / P.W;
+    return true;
+}
+__global__ void k_tile_count(PlpParams P, long long n_reads, int* cnt) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int f = 0, tf = 0, tl = -1;
+    const bool ok = r < n_reads && tile_span(P, r, f, tf, tl);
+    const int key = ok ? tf * P.n_files + f : -1;
+    const unsigned peers = __match_any_sync(FULL, key);  // sorted reads: a warp mostly shares one (tile, file)
+    if (ok && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&cnt[key], __popc(peers));
+    for (int t = tf + 1; t <= tl; ++t) atomicAdd(&cnt[t * P.n_files + f], 1);
+}
+// exclusive scan of n counts into off[0..n] (one CTA), cursors cleared
+__global__ void k_tile_scan(const int* cnt, int* off, int* cur, int n, int* total) {
+    __shared__ int s_w[33];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? cnt[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_w[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int z = lane < (int)(blockDim.x >> 5) ? s_w[lane] : 0;
+            const int own = z;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(FULL, z, o);
+                if (lane >= o) z += y;
+            }
+            s_w[lane] = z - own;
+            if (lane == 31) s_w[32] = z;
+        }
+        __syncthreads();
+        if (i < n) {
+            off[i] = s_carry + s_w[wid] + x - v;
+            cur[i] = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += s_w[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { off[n] = s_carry; *total = s_carry; }
+}
+__global__ void k_tile_fill(PlpParams P, long long n_reads, const int* off, int* cur, int* list, int cap) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int f = 0, tf = 0, tl = -1;
+    const bool ok = r < n_reads && tile_span(P, r, f, tf, tl);
+    const int key = ok ? tf * P.n_files + f : -1;
+    const unsigned peers = __match_any_sync(FULL, key);
+    const int leader = __ffs(peers) - 1;
+    int first = 0;
+    if (ok && leader == lane) first = atomicAdd(&cur[key], __popc(peers));
+    first = __shfl_sync(FULL, first, leader);
+    if (ok) {
+        const int slot = off[key] + first + __popc(peers & ((1u << lane) - 1u));
+        if (slot < cap) list[slot] = (int)r;
+    }
+    for (int t = tf + 1; t <= tl; ++t) {
+        const int k2 = t * P.n_files + f;
+        const int slot = off[k2] + atomicAdd(&cur[k2], 1);
+        if (slot < cap) list[slot] = (int)r;
+    }
+}
+
+extern "C" size_t raer_fast_smem_bytes(int n_files, int W) {
+    const size_t words = (size_t)n_files * 8 * FWS(W) + 2 * ((W >> 3) + 4) + (W >> 5) + 1 + (size_t)W + (size_t)FCAP * FREC;
+    return words * 4 + (size_t)W * 4 + 16;
+}
+
+// widest tile (multiple of 128 positions, at most 1024) that lets two CTAs share one SM; 0 = does not fit
+extern "C" int raer_fast_width(int n_files) {
+    const size_t budget = (227 * 1024 - 2 * 1024) / 2 - 768;  // per CTA, minus the static part
+    int best = 0;
+    for (int w = 128; w <= 1024; w += 128)
+        if (raer_fast_smem_bytes(n_files, w) <= budget) best = w;
+    if (best == 0)
+        for (int w = 32; w < 128; w += 32)
+            if (raer_fast_smem_bytes(n_files, w) <= budget) best = w;
+    return best;
+}
+
+// count + scan of the tile lists; the caller reads *total back, sizes the list and calls raer_fast_fill
+extern "C" int raer_fast_index_count(PlpParams* P, long long n_reads, int* cnt, int* off, int* cur, int* total,
+                                     cudaStream_t st) {
+    const int n = P->n_tiles * P->n_files;
+    cudaMemsetAsync(cnt, 0, (size_t)n * sizeof(int), st);
+    if (n_reads > 0) k_tile_count<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(*P, n_reads, cnt);
+    k_tile_scan<<<1, 1024, 0, st>>>(cnt, off, cur, n, total);
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}
+extern "C" int raer_fast_index_fill(PlpParams* P, long long n_reads, const int* off, int* cur, int* list, int cap,
+                                    cudaStream_t st) {
+    if (n_reads > 0) k_tile_fill<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(*P, n_reads, off, cur, list, cap);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+#endif

@@ -478,24 +478,52 @@ struct SiteCounts {  // per (file, strand)
 
 // Site decision for one position; mirrors process_one_site + store_counts. Returns bit0 write '+',
 // bit1 write '-', bit2 '+' has a variant in some file, bit3 '-' has a variant.
-__device__ int decide_site(const PlpParams& P, const uint32_t* cnt, const uint32_t* covered, int pidx, int p) {
+// Counter layouts behind one accessor: get() returns the six class counts A C G T other X of (file, strand)
+// at tile position pidx; pc is the class of the reference base on the plus strand.
+struct CntPlain {  // k_pileup_tiles: 32-bit words [file][strand][class][W], bank-skewed
+    const uint32_t* cnt;
+    int W;
+    __device__ __forceinline__ void get(int f, int s, int pidx, int pc, int c[RAER_NCLS]) const {
+        const int WP = WPAD(W);
+        const uint32_t* base = cnt + (size_t)((f * 2 + s) * RAER_NCLS) * WP + CIDX(pidx, W);
+#pragma unroll
+        for (int k = 0; k < RAER_NCLS; ++k) c[k] = (int)base[k * WP];
+    }
+};
+struct CntPacked {  // k_pileup_fast: [file][strand]{coverage, A|C<<16, G|T<<16, other|X<<16}[WS]; matches are implicit
+    const uint32_t* cnt;
+    int WS;
+    __device__ __forceinline__ void get(int f, int s, int pidx, int pc, int c[RAER_NCLS]) const {
+        const uint32_t* base = cnt + (size_t)((f * 2 + s) * 4) * WS + pidx;
+        const uint32_t cov = base[0], ac = base[WS], gt = base[2 * WS], ox = base[3 * WS];
+        c[0] = (int)(ac & 0xffffu); c[1] = (int)(ac >> 16);
+        c[2] = (int)(gt & 0xffffu); c[3] = (int)(gt >> 16);
+        c[4] = (int)(ox & 0xffffu); c[5] = (int)(ox >> 16);
+        // bases that equal the reference never touched a class counter: coverage minus everything explicit
+        const int match = (int)cov - (c[0] + c[1] + c[2] + c[3] + c[4] + c[5]);
+        const int rc = pc < 4 ? (s == 0 ? pc : 3 - pc) : 4;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) c[k] += (k == rc) ? match : 0;
+    }
+};
+
+template <class CNT>
+__device__ int decide_site(const PlpParams& P, const CNT cnt, const uint32_t* covered, int pidx, int p) {
     if (!pos_eligible(P, p)) return 0;
     int r = (P.ref && p < P.ref_len) ? (unsigned char)P.ref[p] : 'N';
     int pref = d_upper(r);
     if (pref == 'N') return 0;
     if (P.nmer > 0 && d_simple_repeat(P.ref, P.ref_len, p, P.nmer)) return 0;
     if (P.min_depth <= 0 && !((covered[pidx >> 5] >> (pidx & 31)) & 1u)) return 0;  // no pileup column here
-    const int W = P.W;
     int pc = cls_of_ref(pref);
     int write_s[2] = {0, 0}, has_v[2] = {0, 0}, is_ma[2] = {0, 0}, any_var[2] = {0, 0};
     for (int f = 0; f < P.n_files; ++f) {
         for (int s = 0; s < 2; ++s) {
-            const int WP = WPAD(W);
-            const uint32_t* base = cnt + (size_t)((f * 2 + s) * RAER_NCLS) * WP + CIDX(pidx, W);
-            int c0 = base[0], c1 = base[WP], c2 = base[2 * WP], c3 = base[3 * WP], co = base[4 * WP];
-            int total = c0 + c1 + c2 + c3 + co;
+            int cc[RAER_NCLS];
+            cnt.get(f, s, pidx, pc, cc);
+            const int co = cc[4];
+            int total = cc[0] + cc[1] + cc[2] + cc[3] + co;
             int rc = s == 0 ? pc : (pc < 4 ? 3 - pc : 4);
-            int cc[4] = {c0, c1, c2, c3};
             int nr = rc < 4 ? cc[rc] : 0;
             int nv = total - nr;
             if (total >= P.min_depth && nv >= P.min_var_reads) write_s[s] = 1;
@@ -524,8 +552,8 @@ __device__ int decide_site(const PlpParams& P, const uint32_t* cnt, const uint32
     return out;
 }
 
-__device__ void write_row(const PlpParams& P, const uint32_t* cnt, int pidx, int p, int s, long long row) {
-    const int W = P.W;
+template <class CNT>
+__device__ void write_row(const PlpParams& P, const CNT cnt, int pidx, int p, int s, long long row) {
     int pref = d_upper((unsigned char)P.ref[p]);
     int pc = cls_of_ref(pref);
     int rc = s == 0 ? pc : (pc < 4 ? 3 - pc : 4);
@@ -536,10 +564,9 @@ __device__ void write_row(const PlpParams& P, const uint32_t* cnt, int pidx, int
     P.row_stats[row * 3 + 1] = 0.0;
     P.row_stats[row * 3 + 2] = 0.0;
     for (int f = 0; f < P.n_files; ++f) {
-        const int WP = WPAD(W);
-        const uint32_t* base = cnt + (size_t)((f * 2 + s) * RAER_NCLS) * WP + CIDX(pidx, W);
-        int cc[4] = {(int)base[0], (int)base[WP], (int)base[2 * WP], (int)base[3 * WP]};
-        int co = base[4 * WP], cx = base[5 * WP];
+        int cc[RAER_NCLS];
+        cnt.get(f, s, pidx, pc, cc);
+        const int co = cc[4], cx = cc[5];
         int total = cc[0] + cc[1] + cc[2] + cc[3] + co;
         int nr = rc < 4 ? cc[rc] : 0;
         unsigned alt = 0;
@@ -558,20 +585,26 @@ __device__ void write_row(const PlpParams& P, const uint32_t* cnt, int pidx, int
 
 // Second-pass accumulation of one counted base at a flagged site: read-position histogram, strand
 // tallies, first-seen order of the variant keys.
-__device__ __forceinline__ void pass2_accumulate_slot(const PlpParams& P, const TileSmem& S, const ReadCtx& c, int f, int s,
-                                                      int ordinal, int p, int slot_index, int q, int code) {
+__device__ __forceinline__ void pass2_accumulate_core(const PlpParams& P, const TileSmem& S, const ReadCtx& c, int f, int s,
+                                                      int ordinal, int slot_index, int q, int code, int isref) {
     const int HW = S.hist_words;  // 400: 32-bit bins; 200: two 16-bit bins per word (tile depth <= 65535)
     uint32_t* slot = S.cnt + (size_t)slot_index * S.slot_words;
-    int pref = (p < P.ref_len) ? d_upper((unsigned char)P.ref[p]) : 'N';
-    int letter = "=ACMGRSVTWYHKDBN"[code];
-    int isref = letter == pref;
     int cls = cls_of_code(code);
     // strand-bias tally on the uncomplemented base (src/plp.c:762-774)
     atomicAdd(&slot[HW + (isref ? 0 : 2) + c.rev], 1u);  // ref_fwd ref_rev alt_fwd alt_rev
     // get_relative_position (src/plp_utils.c:401-412)
     int tail = c.l_qseq - c.qe;
     int alen = c.l_qseq - c.qs - tail;
-    int rpos = (int)((double)(q + 1 - c.qs) / (double)(alen + 1) * 99.0);
+    // (int)((double)a / b * 99): the two roundings are ~1e-14 away from 99a/b, which is at least 1/b away from
+    // an integer unless it is one, so the integer quotient is exact except when b divides 99a (fp64 then).
+    const int ra = q + 1 - c.qs, rb = alen + 1;
+    int rpos;
+    if (ra > 0 && rb > 0 && ra < (1 << 24)) {
+        rpos = (99 * ra) / rb;
+        if (rpos * rb == 99 * ra) rpos = (int)((double)ra / (double)rb * 99.0);
+    } else {
+        rpos = (int)((double)ra / (double)rb * 99.0);
+    }
     if (rpos < 0 || rpos >= RAER_NHIST) { atomicExch(P.err_flag, RAER_ERR); return; }
     const int bin = (s * 2 + (isref ? 0 : 1)) * RAER_NHIST + rpos;
     if (HW == 400) atomicAdd(&slot[bin], 1u);
@@ -590,6 +623,13 @@ __device__ __forceinline__ void pass2_accumulate_slot(const PlpParams& P, const 
         }
         atomicMax(&fs[4], (unsigned)ordinal + 1u);  // last variant read (ordinal + 1; 0 = none)
     }
+}
+
+__device__ __forceinline__ void pass2_accumulate_slot(const PlpParams& P, const TileSmem& S, const ReadCtx& c, int f, int s,
+                                                      int ordinal, int p, int slot_index, int q, int code) {
+    int pref = (p < P.ref_len) ? d_upper((unsigned char)P.ref[p]) : 'N';
+    int letter = "=ACMGRSVTWYHKDBN"[code];
+    pass2_accumulate_core(P, S, c, f, s, ordinal, slot_index, q, code, letter == pref);
 }
 
 __device__ __forceinline__ void pass2_accumulate(const PlpParams& P, const TileSmem& S, const ReadCtx& c, int f, int s,
@@ -866,6 +906,8 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* scra
     return res;
 }
 
+#include "raer_fast.cuh"  // k_pileup_fast: the mapq / base-quality-only configuration
+
 __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ int s_scan[40];
@@ -908,7 +950,7 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
         int my_rows = 0;
         for (int pidx = threadIdx.x; pidx < W; pidx += blockDim.x) {
             int d = 0;
-            if (t0 + pidx < t1) d = decide_site(P, S.cnt, S.covered, pidx, t0 + pidx);
+            if (t0 + pidx < t1) d = decide_site(P, CntPlain{S.cnt, W}, S.covered, pidx, t0 + pidx);
             S.dec[pidx] = (uint8_t)d;
             my_rows += (d & 1) + ((d >> 1) & 1);
         }
@@ -937,8 +979,8 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
                 if (n) {
                     long long row = rowbase + off;
                     int rp = -1, rm = -1;
-                    if (d & 1) { write_row(P, S.cnt, pidx, t0 + pidx, 0, row); rp = (int)row; ++row; }
-                    if (d & 2) { write_row(P, S.cnt, pidx, t0 + pidx, 1, row); rm = (int)row; }
+                    if (d & 1) { write_row(P, CntPlain{S.cnt, W}, pidx, t0 + pidx, 0, row); rp = (int)row; ++row; }
+                    if (d & 2) { write_row(P, CntPlain{S.cnt, W}, pidx, t0 + pidx, 1, row); rm = (int)row; }
                     if (fl) {
                         S.flag_pidx[slot] = (uint16_t)pidx;
                         S.flag_rowp[slot] = ((d & 1) && (d & 4)) ? rp : -1;
@@ -988,48 +1030,8 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
                 else scan_reads<true, false>(P, S, f, rg, t0, t1, span_lo, span_hi, lane, wid, nwarp, S.flag_pidx + round0, ns);
             }
             __syncthreads();
-            for (int i = threadIdx.x; i < ns; i += blockDim.x) {
-                const uint32_t* slot = S.cnt + (size_t)i * SW;
-                int rowp = S.flag_rowp[round0 + i], rowm = S.flag_rowm[round0 + i];
-                double sor = d_calc_sor((int)slot[HW], (int)slot[HW + 1], (int)slot[HW + 2], (int)slot[HW + 3]);
-                for (int s = 0; s < 2; ++s) {
-                    long long row = s == 0 ? rowp : rowm;
-                    if (row < 0) continue;
-                    const HistView hr = {slot, (s * 2) * RAER_NHIST, HW != 4 * RAER_NHIST};
-                    const HistView ha = {slot, (s * 2 + 1) * RAER_NHIST, HW != 4 * RAER_NHIST};
-                    P.row_stats[row * 3 + 0] = d_calc_mwu_z(hr, ha);
-                    P.row_stats[row * 3 + 1] = d_calc_vdb(ha);
-                    P.row_stats[row * 3 + 2] = sor;
-                    for (int f = 0; f < P.n_files; ++f) {
-                        const uint32_t* fs = slot + HW + 4 + (f * 2 + s) * RAER_SLOT_FS;
-                        // order the (at most 5) variant keys by first-seen ordinal: 0..3 = ACGT, 4 = IUPAC key
-                        unsigned ord[5] = {fs[0], fs[1], fs[2], fs[3], fs[5]};
-                        unsigned code = 0;
-                        int nins = 0;
-                        unsigned third = 0;
-                        for (int k = 0; k < 5; ++k) {
-                            int best = -1;
-                            for (int b = 0; b < 5; ++b)
-                                if (ord[b] != 0xffffffffu && (best < 0 || ord[b] < ord[best])) best = b;
-                            if (best < 0) break;
-                            code |= (unsigned)best << (3 * nins);
-                            if (nins == 2) third = ord[best];
-                            ord[best] = 0xffffffffu;
-                            ++nins;
-                        }
-                        unsigned alt = P.row_alt[row * P.n_files + f] & (RAER_ALT_MASK | RAER_ALT_OTHER);
-                        alt |= code << RAER_ALT_ORDER_SHIFT;
-                        alt |= (unsigned)nins << RAER_ALT_NINS_SHIFT;
-                        // kh_put resizes 4 -> 8 buckets when a put arrives with 3 keys occupied (khash.h)
-                        if (nins >= 3 && fs[4] > third + 1u) alt |= RAER_ALT_GROW;
-                        if (fs[5] != 0xffffffffu) {
-                            alt |= (fs[6] & 0xfu) << RAER_ALT_OCODE_SHIFT;
-                            if (fs[6] != fs[7]) alt |= RAER_ALT_OAMBIG;
-                        }
-                        P.row_alt[row * P.n_files + f] = alt;
-                    }
-                }
-            }
+            for (int i = threadIdx.x; i < ns; i += blockDim.x)
+                slot_stats(P, S.cnt + (size_t)i * SW, HW, S.flag_rowp[round0 + i], S.flag_rowm[round0 + i]);
             __syncthreads();
         }
         __syncthreads();
@@ -1060,10 +1062,27 @@ extern "C" size_t raer_tile_smem_bytes(int n_files, int W, int S, int* cnt_words
 extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* launches, cudaEvent_t e0, cudaEvent_t e1) {
     int nl = 0;
     if (P->n_tiles <= 0) { *launches = 0; return 0; }
-    {
+    if (!P->use_fast) {
         int n = P->n_tiles * P->n_files;
         k_tile_ranges<<<(n + 255) / 256, 256, 0, st>>>(*P);
         ++nl;
+    }
+    if (P->use_fast) {
+        const size_t fsmem = raer_fast_smem_bytes(P->n_files, P->W);
+        static size_t fconfigured = 0;
+        if (fsmem > fconfigured) {
+            if (cudaFuncSetAttribute(k_pileup_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem) != cudaSuccess)
+                return -1;
+            fconfigured = fsmem;
+        }
+        int grid = n_sm * 2;
+        if (grid > P->n_tiles) grid = P->n_tiles;
+        if (e0) cudaEventRecord(e0, st);
+        k_pileup_fast<<<grid, FB_THREADS, fsmem, st>>>(*P);
+        if (e1) cudaEventRecord(e1, st);
+        ++nl;
+        *launches = nl;
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;
     }
     size_t smem = raer_tile_smem_bytes(P->n_files, P->W, P->S, &P->cnt_words, &P->slot_words);
     static size_t configured = 0;

@@ -22,6 +22,9 @@ using raer::set_error;
 extern "C" int raer_launch_overlap(const raer_read_hdr* hdr, const uint32_t* cigar, const uint8_t* seq, uint8_t* qual,
                                    const int32_t* pair_b, long long n_pairs, int mode, cudaStream_t st);
 extern "C" size_t raer_tile_smem_bytes(int n_files, int W, int S, int* cnt_words, int* slot_words);
+extern "C" int raer_fast_width(int n_files);
+extern "C" int raer_fast_index_count(PlpParams* P, long long n_reads, int* cnt, int* off, int* cur, int* total, cudaStream_t st);
+extern "C" int raer_fast_index_fill(PlpParams* P, long long n_reads, const int* off, int* cur, int* list, int cap, cudaStream_t st);
 extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* launches, cudaEvent_t e0, cudaEvent_t e1);
 
 #define CK(call)                                                                              \
@@ -76,6 +79,7 @@ struct raer_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6];
     DevBuf hdr, maxend, cigar, seq, qual, pair_b, mask;
+    DevBuf tile_idx, tile_list;            // k_pileup_fast: counts | offsets | cursors, and the per-tile read lists
     DevBuf tile_ranges, tile_rows, small;  // small: tile_counter(4) | pad | row_counter(8) | err(4)
     DevBuf row_pos, row_meta, row_stats, row_counts, row_alt;
     DevBuf ref;
@@ -109,7 +113,7 @@ extern "C" void raer_ctx_destroy(raer_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->hdr, &c->maxend, &c->cigar, &c->seq, &c->qual, &c->pair_b, &c->mask, &c->tile_ranges, &c->tile_rows,
+    for (DevBuf* b : {&c->hdr, &c->maxend, &c->cigar, &c->seq, &c->qual, &c->pair_b, &c->mask, &c->tile_ranges, &c->tile_rows, &c->tile_idx, &c->tile_list,
                       &c->small, &c->row_pos, &c->row_meta, &c->row_stats, &c->row_counts, &c->row_alt, &c->ref})
         b->release();
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -173,7 +177,15 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
     for (int i = 0; i <= nf; ++i) P.file_off[i] = b->file_off[i];
     P.n_files = nf;
     P.t_beg = b->beg; P.t_end = b->end;
-    P.W = choose_tile_width(nf);
+    // k_pileup_fast: mapq / base-quality filters only, threshold within the byte-parallel compare's range.
+    // RAER_KERNEL=generic forces k_pileup_tiles (tests run both kernels on the same inputs).
+    const bool only_bq = !(conf->trim_5p > 0 || conf->trim_3p > 0 || conf->ftrim_5p > 0 || conf->ftrim_3p > 0 ||
+                           conf->splice_dist || conf->min_overhang || conf->indel_dist || conf->n_mm_type > 0 || conf->n_mm > 0);
+    const char* kforce = getenv("RAER_KERNEL");
+    const int fw = raer_fast_width(nf);
+    P.use_fast = only_bq && conf->min_bq <= 128 && fw > 0 && !(kforce && !strcmp(kforce, "generic"));
+    P.W = P.use_fast ? fw : choose_tile_width(nf);
+    if (P.use_fast && getenv("RAER_FAST_W")) P.W = std::max(32, std::min(fw, atoi(getenv("RAER_FAST_W")) & ~31));
     long long span = (long long)b->end - b->beg;
     P.n_tiles = span > 0 ? (int)((span + P.W - 1) / P.W) : 0;
     P.ref = c->ref_ptr; P.ref_len = (int)std::min<int64_t>(c->ref_len, INT_MAX);
@@ -225,6 +237,28 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
                                         conf->remove_overlaps, c->stream);
             if (r < 0) { set_error("overlap kernel launch failed"); return RAER_ERR_CUDA; }
             nl += r;
+        }
+        if (P.use_fast) {
+            // per-tile read lists: count, scan, read the total back (sizes the list), fill
+            const size_t ne = (size_t)P.n_tiles * nf + 1;
+            if ((rc = c->tile_idx.ensure(ne * 3 * sizeof(int) + 16))) return rc;
+            int* cnt = (int*)c->tile_idx.p;
+            int* off = cnt + ne;
+            int* cur = off + ne;
+            int* d_total = (int*)((char*)c->small.p + 32);
+            const long long n_reads = b->file_off[nf];
+            int r = raer_fast_index_count(&P, n_reads, cnt, off, cur, d_total, c->stream);
+            if (r < 0) { set_error("tile index kernels failed"); return RAER_ERR_CUDA; }
+            nl += r;
+            int total = 0;
+            CK(cudaMemcpyAsync(&total, d_total, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            if ((rc = c->tile_list.ensure((size_t)std::max(total, 1) * sizeof(int)))) return rc;
+            r = raer_fast_index_fill(&P, n_reads, off, cur, (int*)c->tile_list.p, total, c->stream);
+            if (r < 0) { set_error("tile index kernels failed"); return RAER_ERR_CUDA; }
+            nl += r;
+            P.tile_off = off;
+            P.tile_list = (const int*)c->tile_list.p;
         }
         int tl = 0;
         cudaEvent_t e0 = nullptr, e1 = nullptr;

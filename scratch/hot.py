@@ -20,12 +20,12 @@ for r in data:
     ln=off2line.get(int(r[0],16)-base)
     inst=float(r[ix['Instructions Executed']] or 0); samp=float(r[ix['# Samples']] or 0); th=float(r[ix['Thread Instructions Executed']] or 0)
     a=agg[ln]; a[0]+=inst; a[1]+=samp; a[2]+=th; ti+=inst; ts+=samp; tt+=th
-src=open('/root/repo/raer_b200/csrc/raer_kernels.cu').read().split('\n')
+src=open('/root/repo/raer_b200/csrc/'+os.environ.get('SRCF','raer_fast.cuh')).read().split('\n')
 r=list(csv.reader(open('/tmp/raw_m.csv'))); h,u,v=r[0],r[1],r[2]
 for i,n in enumerate(h):
     if n in('gpu__time_duration.sum','smsp__inst_executed.sum','smsp__thread_inst_executed_per_inst_executed.ratio','smsp__issue_active.avg.pct_of_peak_sustained_active','l1tex__data_pipe_lsu_wavefronts_mem_shared.sum','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum','smsp__inst_executed_op_shared_atom.sum','launch__registers_per_thread','dram__bytes_read.sum','dram__bytes_write.sum','sm__warps_active.avg.pct_of_peak_sustained_active'): print(n,u[i],v[i])
 print("total warp inst %.3e thread inst %.3e samples %d"%(ti,tt,ts))
 N=int(sys.argv[3]) if len(sys.argv)>3 else 30
 for ln,a in sorted(agg.items(), key=lambda kv:-kv[1][int(os.environ.get("SORTCOL","0"))])[:N]:
-    txt = src[ln[1]-1].strip()[:95] if ln and ln[0]=='raer_kernels.cu' else str(ln)
+    txt = src[ln[1]-1].strip()[:95] if ln and ln[0]==os.environ.get('SRCF','raer_fast.cuh') else str(ln)
     print("%-5s inst %5.1f%% thr/inst %4.1f samp %5.1f%%  %s"%(ln[1] if ln else '?',100*a[0]/ti,a[2]/max(a[0],1),100*a[1]/ts,txt))

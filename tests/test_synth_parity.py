@@ -68,6 +68,28 @@ def test_two_bam_parity(syn, kw):
     _assert_same(got, want)
 
 
+# The configurations with only mapq / base-quality filters run k_pileup_fast by default; RAER_KERNEL=generic
+# sends the same call through k_pileup_tiles, so both kernels are held to the oracle.
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [CONFIGS[i] for i in (0, 1, 2, 3, 4, 9, 12)], ids=[str(i) for i in (0, 1, 2, 3, 4, 9, 12)])
+def test_two_bam_parity_generic_kernel(syn, kw, monkeypatch):
+    monkeypatch.setenv("RAER_KERNEL", "generic")
+    fp = FilterParam(**kw)
+    want = oracle_backend.pileup_sites(syn["bams"], syn["fasta"], param=fp)
+    got = _cuda()(syn["bams"], syn["fasta"], param=fp)
+    _assert_same(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fast_w", [32, 160, 512])
+def test_fast_kernel_tile_width_does_not_change_results(syn, fast_w, monkeypatch):
+    fp = FilterParam(library_type="fr-first-strand", min_depth=0)
+    want = oracle_backend.pileup_sites(syn["bams"], syn["fasta"], param=fp)
+    monkeypatch.setenv("RAER_FAST_W", str(fast_w))
+    got = _cuda()(syn["bams"], syn["fasta"], param=fp)
+    _assert_same(got, want)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("batch_reads", [40, 333, 5000])
 def test_batch_seams_do_not_change_results(syn, batch_reads, monkeypatch):
