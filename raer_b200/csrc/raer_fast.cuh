@@ -19,8 +19,9 @@
 // read that overlaps the tile, nothing else), so the CTA stages dense batches of FCAP read records in
 // shared memory and all 512 threads take items from one batch-wide list: no idle lanes for reads that only
 // pass by, no per-warp tails. The second pass (read-position histograms, strand tallies and first-seen
-// order at the sites that carry a variant) is the same walk with a packed "flagged position" mask in place
-// of the reference compare; sequence and qualities are only fetched for items that touch a flagged site.
+// order at the sites that carry a variant) is pair parallel: a prefix count of flagged positions gives every
+// read its number of (read, flagged position) pairs in O(1), warps pull chunks of 32 listed reads and their
+// lanes take one pair each.
 // Two CTAs of 512 threads per SM.
 #ifndef RAER_FAST_CUH
 #define RAER_FAST_CUH
@@ -28,18 +29,18 @@
 #define FB_THREADS 512
 #define FCAP 768  // read records staged per batch
 #define FREC 11   // words per record (odd: lanes reading one field of different records spread over banks)
-enum { FR_POS = 0, FR_LEN, FR_SQ, FR_FLAGS, FR_QSQE, FR_ORD, FR_CIG0 };  // FR_CIG0..+3: CIGAR words, or [0] = offset if n > 4
+enum { FR_POS = 0, FR_LEN, FR_SQ, FR_FLAGS, FR_QSQE, FR_FIRST, FR_CIG0 };  // FR_CIG0..+3: CIGAR words, or [0] = offset if n > 4
 #define FRF_FILE_SHIFT 24
 #define FWS(W) ((W) + 8)  // words per counter array: W positions + the -1 event one past the end
 
 struct FastSmem {
     uint32_t* cnt;      // [file][strand]{coverage events, A|C<<16, G|T<<16, other|X<<16}[WS]; second-pass slots later
     uint32_t* refn;     // packed reference: nibble i of word k = nt16 code of position t0 - 8 + 8k + i
-    uint32_t* fnib;     // second pass: same geometry, nibble = 1 where the position is flagged in this round
     uint32_t* covered;  // min_depth <= 0 only: a pileup column exists here
     int* flag_row;      // per flagged site: its first output row
     uint32_t* stage;    // FCAP records
-    uint16_t* slot_of;  // per position: rank among the tile's flagged sites, 0xffff = none
+    uint16_t* fpre;     // per position (W + 1): number of flagged sites before it (their ranks are position sorted)
+    uint16_t* flag_pidx;  // per flagged site: its tile position
     uint8_t* flag_d;    // per flagged site: decision bits
     uint8_t* dec;       // per position: decision bits
     int WS;
@@ -47,6 +48,9 @@ struct FastSmem {
 
 __device__ __forceinline__ void red_add(uint32_t* p, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_s(unsigned saddr, uint32_t v) {  // saddr: shared-window byte address
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
 // BAM packs base 2b in the high nibble of byte b; after the swap base j sits in nibble j of the word
 __device__ __forceinline__ uint32_t nib_swap(uint32_t w) { return ((w & 0x0f0f0f0fu) << 4) | ((w >> 4) & 0x0f0f0f0fu); }
@@ -93,124 +97,75 @@ struct FastCtx {  // per-kernel constants of the item walk
 };
 
 // ---- phase 1: one aligned block's share of an item. Bases j in [jlo, jhi) sit on tile positions rel + j.
-__device__ __forceinline__ void fast_block_count(const FastSmem& S, const FastCtx& X, uint32_t* cb, uint32_t rw, uint2 qw,
+// NM/LT/Z: nibble-bit masks (bit 4j) of read base N, quality below the threshold, quality 0.
+__device__ __forceinline__ void fast_block_count(const FastSmem& S, const FastCtx& X, unsigned cbs, uint32_t rw, uint32_t NM,
                                                  uint32_t LT, uint32_t Z, bool mapq_fail, int cxor, int rel, int jlo, int jhi) {
     const int lo = max(max(jlo, -rel), 0), hi = min(min(jhi, X.tw - rel), 8);
     if (lo >= hi) return;
     const uint32_t V = (0x11111111u >> ((8 - (hi - lo)) << 2)) << (lo << 2);
     const int a = rel + 8;  // >= 1 here: index of the item's first base in the packed reference
     const uint32_t refw = __funnelshift_r(S.refn[a >> 3], S.refn[(a >> 3) + 1], (a & 7) << 2);
-    uint32_t E, ZZ;
-    if (mapq_fail) {  // every base of the read is nX (src/plp.c:574), read base N still counted nowhere (:718)
-        E = V;
-        ZZ = 0;
+    uint32_t D, XM, MM;
+    if (mapq_fail) {  // every base of the read is nX (src/plp.c:574); read base N is counted nowhere (:718)
+        D = NM & V;
+        XM = V & ~NM;
+        MM = 0;
     } else {
-        ZZ = Z & V;  // quality 0 below the threshold: dropped silently (src/plp.c:580-586)
-        E = (nib_nonzero(rw ^ refw) | LT) & V & ~ZZ;
+        D = (Z | NM) & V;   // quality 0 below the threshold is dropped silently (src/plp.c:580-586), so is N
+        XM = LT & V & ~D;   // nX
+        MM = nib_nonzero(rw ^ refw) & V & ~(LT | D);
     }
+    const unsigned base = cbs + ((unsigned)rel << 2);  // shared address of this item's first coverage word
     // runs of dropped bases leave the coverage: -1 where a run starts, +1 after its end
-    uint32_t rs = ZZ & ~(ZZ << 4), re = ZZ & ~(ZZ >> 4);
+    uint32_t rs = D & ~(D << 4), re = D & ~(D >> 4);
     while (rs) {
         const int b1 = __ffs(rs) - 1, b2 = __ffs(re) - 1;
         rs &= rs - 1;
         re &= re - 1;
-        red_add(cb + rel + (b1 >> 2), 0xffffffffu);
-        red_add(cb + rel + (b2 >> 2) + 1, 1u);
+        red_add_s(base + b1, 0xffffffffu);  // b = 4j: byte offset of word j
+        red_add_s(base + b2 + 4, 1u);
     }
-    while (E) {
-        const int b = __ffs(E) - 1;
-        E &= E - 1;
-        const int j = b >> 2, p = rel + j;
+    const unsigned xb = base + (unsigned)(3 * S.WS) * 4;
+    while (XM) {
+        const int b = __ffs(XM) - 1;
+        XM &= XM - 1;
+        red_add_s(xb + b, 0x10000u);
+    }
+    while (MM) {
+        const int b = __ffs(MM) - 1;
+        MM &= MM - 1;
         const int code = (rw >> b) & 15;
-        if (code == 15) {  // read base N
-            red_add(cb + p, 0xffffffffu);
-            red_add(cb + p + 1, 1u);
-            continue;
-        }
-        const int bq = __byte_perm(qw.x, qw.y, j) & 0xff;
-        uint32_t* dst;
-        uint32_t val;
-        if (mapq_fail | (bq < X.minbq)) {  // nX
-            dst = cb + 3 * S.WS + p;
-            val = 0x10000u;
-        } else {
-            // A=1 C=2 G=4 T=8 -> 0..3; complement on the minus strand = xor 3; any other code -> other
-            int cls = ((code >> 1) - (code >> 3)) ^ cxor;
-            if (__popc(code) != 1) cls = RAER_CLS_OTHER;
-            dst = cb + (1 + (cls >> 1)) * S.WS + p;
-            val = 1u << ((cls & 1) << 4);
-        }
-        red_add(dst, val);
+        // A=1 C=2 G=4 T=8 -> 0..3; complement on the minus strand = xor 3; any other code -> other
+        int cls = ((code >> 1) - (code >> 3)) ^ cxor;
+        if (__popc(code) != 1) cls = RAER_CLS_OTHER;
+        red_add_s(base + (unsigned)((1 + (cls >> 1)) * S.WS) * 4 + b, 1u << ((cls & 1) << 4));
     }
 }
 
-// ---- second pass: the bases of one aligned block that sit on flagged positions
-__device__ __forceinline__ void fast_block_stats(const PlpParams& P, const FastSmem& S, const FastCtx& X, const TileSmem& T2,
-                                                 const uint32_t* rec, int q0, int rel, int jlo, int jhi) {
-    const int lo = max(max(jlo, -rel), 0), hi = min(min(jhi, X.tw - rel), 8);
-    if (lo >= hi) return;
-    const uint32_t V = (0x11111111u >> ((8 - (hi - lo)) << 2)) << (lo << 2);
-    const int a = rel + 8;
-    const int sh = (a & 7) << 2;
-    uint32_t E = __funnelshift_r(S.fnib[a >> 3], S.fnib[(a >> 3) + 1], sh) & V;
-    if (!E) return;
-    const uint32_t refw = __funnelshift_r(S.refn[a >> 3], S.refn[(a >> 3) + 1], sh);
-    const uint32_t sq = rec[FR_SQ];
-    const uint32_t rw = nib_swap(__ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (q0 >> 1))));
-    const uint2 qw = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + q0));
-    const unsigned fl = rec[FR_FLAGS];
-    ReadCtx c;
-    c.l_qseq = (int)(rec[FR_LEN] & 0xffff);
-    c.qs = (int)(rec[FR_QSQE] & 0xffff);
-    c.qe = (int)(rec[FR_QSQE] >> 16);
-    c.rev = (fl >> 16) & 1;
-    c.invert = fl & RAER_RB_INVERT;
-    const int f = (int)(fl >> FRF_FILE_SHIFT);
-    while (E) {
-        const int b = __ffs(E) - 1;
-        E &= E - 1;
-        const int j = b >> 2;
-        const int code = (rw >> b) & 15;
-        if (code == 15) continue;                                       // src/plp.c:718
-        if ((int)(__byte_perm(qw.x, qw.y, j) & 0xff) < X.minbq) continue;  // nX or dropped: not counted
-        const int rcode = (refw >> b) & 15;
-        const int isref = (code == rcode) & (code != 0);
-        pass2_accumulate_core(P, T2, c, f, c.invert ? 1 : 0, (int)rec[FR_ORD], (int)S.slot_of[rel + j] - X.round0, q0 + j, code,
-                              isref);
-    }
-}
-
-template <int PASS>
-__device__ __forceinline__ void fast_item(const PlpParams& P, const FastSmem& S, const FastCtx& X, const TileSmem& T2,
-                                          const uint32_t* rec, int q0, uint32_t sw, uint2 qw) {
+__device__ __forceinline__ void fast_item(const PlpParams& P, const FastSmem& S, const FastCtx& X, const uint32_t* rec, int q0,
+                                          uint32_t sw, uint2 qw) {
     const int pos = (int)rec[FR_POS];
     const int lq = (int)(rec[FR_LEN] & 0xffff), n = (int)(rec[FR_LEN] >> 16);
     const unsigned fl = rec[FR_FLAGS];
     const int q1 = min(q0 + 8, lq);
     const bool mapq_fail = (fl & STF_MAPQ_FAIL) != 0;
     const int s = fl & RAER_RB_INVERT;
-    uint32_t* cb = nullptr;
-    uint32_t rw = 0, LT = 0, Z = 0;
-    if (PASS == 0) {
-        cb = S.cnt + (size_t)(((fl >> FRF_FILE_SHIFT) * 2 + s) * 4) * S.WS;
-        rw = nib_swap(sw);
-        // nibble j: bit 0 = quality below the threshold, bit 1 = quality 0
-        const uint32_t Q = bytes_to_nibbles((byte_lt(qw.x, X.mb4) >> 7) | (byte_zero(qw.x) >> 6),
-                                            (byte_lt(qw.y, X.mb4) >> 7) | (byte_zero(qw.y) >> 6));
-        LT = Q & 0x11111111u;
-        Z = (Q >> 1) & 0x11111111u & X.zall;
-    }
+    const unsigned cbs = (unsigned)__cvta_generic_to_shared(S.cnt + (size_t)(((fl >> FRF_FILE_SHIFT) * 2 + s) * 4) * S.WS);
+    const uint32_t rw = nib_swap(sw);
+    const uint32_t NM = rw & (rw >> 1) & (rw >> 2) & (rw >> 3) & 0x11111111u;
+    // nibble j: bit 0 = quality below the threshold, bit 1 = quality 0
+    const uint32_t Q = bytes_to_nibbles((byte_lt(qw.x, X.mb4) >> 7) | (byte_zero(qw.x) >> 6),
+                                        (byte_lt(qw.y, X.mb4) >> 7) | (byte_zero(qw.y) >> 6));
+    const uint32_t LT = Q & 0x11111111u, Z = (Q >> 1) & 0x11111111u & X.zall;
     const uint32_t* cig = n <= 4 ? rec + FR_CIG0 : P.cigar + rec[FR_CIG0];
     int x = pos, y = 0;
     for (int k = 0; k < n && y < q1; ++k) {
         const uint32_t w = cig[k];
         const int op = cg_op(w), len = cg_len(w);
         if ((0x181 >> op) & 1) {  // M = X
-            if (y + len > q0) {
-                const int rel = x + (q0 - y) - X.t0, jlo = y - q0, jhi = min(y + len, q1) - q0;
-                if (PASS == 0) fast_block_count(S, X, cb, rw, qw, LT, Z, mapq_fail, s ? 3 : 0, rel, jlo, jhi);
-                else fast_block_stats(P, S, X, T2, rec, q0, rel, jlo, jhi);
-            }
+            if (y + len > q0)
+                fast_block_count(S, X, cbs, rw, NM, LT, Z, mapq_fail, s ? 3 : 0, x + (q0 - y) - X.t0, y - q0,
+                                 min(y + len, q1) - q0);
             x += len;
             y += len;
         } else if ((0xC >> op) & 1) {  // D N
@@ -221,70 +176,42 @@ __device__ __forceinline__ void fast_item(const PlpParams& P, const FastSmem& S,
     }
 }
 
-// Stage one read record (thread per read). PASS 0 also writes the read's coverage events.
-template <int PASS, bool NEEDCOV>
+// Phase 1: stage one read record (thread per read) and write the read's coverage events.
+template <bool NEEDCOV>
 __device__ __forceinline__ int fast_stage(const PlpParams& P, const FastSmem& S, const FastCtx& X, int r, int f, int t1,
-                                          int span_lo, int span_hi, uint32_t* rec) {
+                                          uint32_t* rec) {
     const int4 a = __ldg(reinterpret_cast<const int4*>(P.hdr + r));
     const int4 b = __ldg(reinterpret_cast<const int4*>(P.hdr + r) + 1);
     const int flag = a.z & 0xffff, mapq = (a.z >> 16) & 0xff, bits = (a.z >> 24) & 0xff;
     const int lq = a.w & 0xffff, n = (a.w >> 16) & 0xffff;
-    const bool mapq_fail = mapq < P.min_mapq[f];
-    if (PASS == 1 && (mapq_fail || a.y <= span_lo || a.x >= span_hi)) {
-        rec[FR_LEN] = 0;  // a read below the mapq threshold only produces nX: nothing to accumulate (src/plp.c:574)
-        return 0;
-    }
     const int s = bits & RAER_RB_INVERT;
     unsigned fl = (unsigned)bits | ((unsigned)((flag >> 4) & 1) << 16) | ((unsigned)f << FRF_FILE_SHIFT);
-    if (mapq_fail) fl |= STF_MAPQ_FAIL;
+    if (mapq < P.min_mapq[f]) fl |= STF_MAPQ_FAIL;
     const uint32_t* cg = P.cigar + (unsigned)b.x;
-    if (PASS == 0) {
-        uint32_t* dl = S.cnt + (size_t)((f * 2 + s) * 4) * S.WS;
-        int x = a.x, y = 0;
-        for (int k = 0; k < n; ++k) {
-            const uint32_t w = __ldg(cg + k);
-            if (k < 4) rec[FR_CIG0 + k] = w;
-            const int op = cg_op(w), len = cg_len(w);
-            if (NEEDCOV && (cg_type(op) & 2)) {
-                const int lo = max(x, X.t0), h2 = min(x + len, t1);
-                if (lo < h2) cover_range(S.covered, lo - X.t0, h2 - X.t0);
+    uint32_t* dl = S.cnt + (size_t)((f * 2 + s) * 4) * S.WS;
+    int x = a.x, y = 0;
+    for (int k = 0; k < n; ++k) {
+        const uint32_t w = __ldg(cg + k);
+        if (k < 4) rec[FR_CIG0 + k] = w;
+        const int op = cg_op(w), len = cg_len(w);
+        if (NEEDCOV && (cg_type(op) & 2)) {
+            const int lo = max(x, X.t0), h2 = min(x + len, t1);
+            if (lo < h2) cover_range(S.covered, lo - X.t0, h2 - X.t0);
+        }
+        if ((0x181 >> op) & 1) {
+            // coverage events of the aligned block, clipped to the tile (and to the bases the read really has)
+            const int lo = max(x, X.t0), h2 = min(x + min(len, lq - y), t1);
+            if (lo < h2) {
+                red_add(dl + (lo - X.t0), 1u);
+                red_add(dl + (h2 - X.t0), 0xffffffffu);
             }
-            if ((0x181 >> op) & 1) {
-                // coverage events of the aligned block, clipped to the tile (and to the bases the read really has)
-                const int lo = max(x, X.t0), h2 = min(x + min(len, lq - y), t1);
-                if (lo < h2) {
-                    red_add(dl + (lo - X.t0), 1u);
-                    red_add(dl + (h2 - X.t0), 0xffffffffu);
-                }
-                x += len;
-                y += len;
-            } else if ((0xC >> op) & 1) {
-                x += len;
-            } else if ((0x12 >> op) & 1) {
-                y += len;
-            }
+            x += len;
+            y += len;
+        } else if ((0xC >> op) & 1) {
+            x += len;
+        } else if ((0x12 >> op) & 1) {
+            y += len;
         }
-    } else {
-        // query_start / query_end (src/plp_utils.c:52-104): soft clips at either end, hard clips skipped
-        int qs = 0, qe = lq, k;
-        for (k = 0; k < n; ++k) {
-            const uint32_t w = __ldg(cg + k);
-            if (k < 4) rec[FR_CIG0 + k] = w;
-            const int op = cg_op(w);
-            if (op == OP_H) continue;
-            if (op == OP_S) qs += cg_len(w);
-            else break;
-        }
-        for (++k; k < n && k < 4; ++k) rec[FR_CIG0 + k] = __ldg(cg + k);
-        for (k = n - 1; k >= 0; --k) {
-            const uint32_t w = __ldg(cg + k);
-            const int op = cg_op(w);
-            if (op == OP_H) continue;
-            if (op == OP_S) qe -= cg_len(w);
-            else break;
-        }
-        rec[FR_QSQE] = (uint32_t)qs | ((uint32_t)qe << 16);
-        rec[FR_ORD] = (uint32_t)(r - (int)P.file_off[f]);
     }
     if (n > 4) rec[FR_CIG0] = (uint32_t)b.x;
     rec[FR_POS] = (uint32_t)a.x;
@@ -294,10 +221,8 @@ __device__ __forceinline__ int fast_stage(const PlpParams& P, const FastSmem& S,
     return (lq + 7) >> 3;
 }
 
-// Walk every read of the tile: stage dense batches of FCAP records, then take items from the batch-wide list.
-template <int PASS>
-__device__ void fast_walk(const PlpParams& P, const FastSmem& S, const FastCtx& X, const TileSmem& T2, int tile, int t1,
-                          int span_lo, int span_hi, int* s_ni) {
+// Phase 1 over every read of the tile: stage dense batches of FCAP records, then take items from the batch-wide list.
+__device__ void fast_walk(const PlpParams& P, const FastSmem& S, const FastCtx& X, int tile, int t1, int* s_ni) {
     const int F = P.n_files;
     const int l0 = P.tile_off[tile * F], l1 = P.tile_off[tile * F + F];
     const bool need_cov = P.min_depth <= 0;
@@ -311,10 +236,7 @@ __device__ void fast_walk(const PlpParams& P, const FastSmem& S, const FastCtx& 
             while (f + 1 < F && li >= P.tile_off[tile * F + f + 1]) ++f;
             const int r = __ldg(P.tile_list + li);
             uint32_t* rec = S.stage + k * FREC;
-            int nq;
-            if (PASS == 0 && need_cov) nq = fast_stage<PASS, true>(P, S, X, r, f, t1, span_lo, span_hi, rec);
-            else nq = fast_stage<PASS, false>(P, S, X, r, f, t1, span_lo, span_hi, rec);
-            ni = max(ni, nq);
+            ni = max(ni, need_cov ? fast_stage<true>(P, S, X, r, f, t1, rec) : fast_stage<false>(P, S, X, r, f, t1, rec));
         }
         ni = __reduce_max_sync(FULL, ni);
         if ((threadIdx.x & 31) == 0 && ni > 0) atomicMax(&s_ni[parity], ni);
@@ -329,50 +251,166 @@ __device__ void fast_walk(const PlpParams& P, const FastSmem& S, const FastCtx& 
                 // The trip count is CTA-uniform, so the warp can be re-joined here: without it the lanes that took
                 // different paths through the previous items keep running as separate sub-warps.
                 __syncwarp();
-                const int it0 = itb + threadIdx.x;
                 // two items in flight per thread
                 const uint32_t* recA = S.stage;
                 const uint32_t* recB = S.stage;
                 int qA = 0, qB = 0;
-                bool okA, okB;
                 uint32_t swA = 0, swB = 0;
                 uint2 qwA = make_uint2(0, 0), qwB = make_uint2(0, 0);
-                {
-                    const int it = it0;
-                    okA = it < tot;
-                    if (okA) {
-                        const int i = mul_ok ? (int)__umulhi((uint32_t)it, M32) : it / NI;
-                        recA = S.stage + i * FREC;
-                        qA = (it - i * NI) << 3;
-                        okA = qA < (int)(recA[FR_LEN] & 0xffff);
-                    }
-                    if (PASS == 0 && okA) {
-                        const uint32_t sq = recA[FR_SQ];
-                        swA = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qA >> 1)));
-                        qwA = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qA));
-                    }
+                const int itA = itb + threadIdx.x, itB = itA + FB_THREADS;
+                bool okA = itA < tot, okB = itB < tot;
+                if (okA) {
+                    const int i = mul_ok ? (int)__umulhi((uint32_t)itA, M32) : itA / NI;
+                    recA = S.stage + i * FREC;
+                    qA = (itA - i * NI) << 3;
+                    okA = qA < (int)(recA[FR_LEN] & 0xffff);
                 }
-                {
-                    const int it = it0 + FB_THREADS;
-                    okB = it < tot;
-                    if (okB) {
-                        const int i = mul_ok ? (int)__umulhi((uint32_t)it, M32) : it / NI;
-                        recB = S.stage + i * FREC;
-                        qB = (it - i * NI) << 3;
-                        okB = qB < (int)(recB[FR_LEN] & 0xffff);
-                        if (PASS == 0 && okB) {
-                            const uint32_t sq = recB[FR_SQ];
-                            swB = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qB >> 1)));
-                            qwB = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qB));
-                        }
-                    }
+                if (okA) {
+                    const uint32_t sq = recA[FR_SQ];
+                    swA = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qA >> 1)));
+                    qwA = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qA));
                 }
-                if (okA) fast_item<PASS>(P, S, X, T2, recA, qA, swA, qwA);
-                if (okB) fast_item<PASS>(P, S, X, T2, recB, qB, swB, qwB);
+                if (okB) {
+                    const int i = mul_ok ? (int)__umulhi((uint32_t)itB, M32) : itB / NI;
+                    recB = S.stage + i * FREC;
+                    qB = (itB - i * NI) << 3;
+                    okB = qB < (int)(recB[FR_LEN] & 0xffff);
+                }
+                if (okB) {
+                    const uint32_t sq = recB[FR_SQ];
+                    swB = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qB >> 1)));
+                    qwB = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qB));
+                }
+                if (okA) fast_item(P, S, X, recA, qA, swA, qwA);
+                __syncwarp();
+                if (okB) fast_item(P, S, X, recB, qB, swB, qwB);
             }
         }
         __syncthreads();
     }
+}
+
+// ---- second pass: one (read, flagged position) pair per lane
+__device__ __forceinline__ void fast_pair(const PlpParams& P, const FastSmem& S, const FastCtx& X, const TileSmem& T2,
+                                          const uint32_t* rec, int rank, int ordinal) {
+    const int pos = (int)rec[FR_POS];
+    const int lq = (int)(rec[FR_LEN] & 0xffff), n = (int)(rec[FR_LEN] >> 16);
+    const unsigned fl = rec[FR_FLAGS];
+    const uint32_t sq = rec[FR_SQ];
+    const uint32_t* cig = n <= 4 ? rec + FR_CIG0 : P.cigar + rec[FR_CIG0];
+    const int pidx = (int)S.flag_pidx[rank];
+    const int p = X.t0 + pidx;
+    int x = pos, y = 0, k = 0, op = -1, len = 0;
+    for (; k < n; ++k) {
+        const uint32_t w = cig[k];
+        op = cg_op(w);
+        len = cg_len(w);
+        if ((0x18D >> op) & 1) {  // M D N = X
+            if (p < x + len) break;
+            x += len;
+            if ((0x181 >> op) & 1) y += len;
+        } else if ((0x12 >> op) & 1) {
+            y += len;
+        }
+    }
+    if (k >= n) return;            // past the end of the read
+    if ((0xC >> op) & 1) return;   // deletion / ref-skip at p: filtered silently (src/plp.c:571)
+    const int q = y + (p - x);
+    if (q >= lq) return;
+    const int code = seq_code(P.seq + sq, q);
+    if (code == 15) return;        // src/plp.c:718
+    const int bq = P.qual[2ull * sq + q];
+    if (bq < X.minbq) return;      // nX or dropped: not part of the statistics
+    const int a = pidx + 8;
+    const int rcode = (S.refn[a >> 3] >> ((a & 7) << 2)) & 15;
+    ReadCtx c;
+    c.l_qseq = lq;
+    c.qs = (int)(rec[FR_QSQE] & 0xffff);
+    c.qe = (int)(rec[FR_QSQE] >> 16);
+    c.rev = (fl >> 16) & 1;
+    c.invert = fl & RAER_RB_INVERT;
+    pass2_accumulate_core(P, T2, c, (int)(fl >> FRF_FILE_SHIFT), c.invert ? 1 : 0, ordinal, rank - X.round0, q, code,
+                          (code == rcode) & (code != 0));
+}
+
+// One chunk of 32 listed reads, handled by one warp: stage the reads that cover a flagged site of this round,
+// prefix-sum their pair counts, lanes take pairs.
+__device__ __forceinline__ void fast_pair_chunk(const PlpParams& P, const FastSmem& S, const FastCtx& X, const TileSmem& T2,
+                                                int tile, int li0, int l1, int lane, uint32_t* st) {
+    uint32_t* pref = st + 32 * FREC;  // inclusive prefix of pairs per read
+    const int F = P.n_files;
+    const int li = li0 + lane;
+    uint32_t* rec = st + lane * FREC;
+    int np = 0, r = 0, f = 0;
+    if (li < l1) {
+        while (f + 1 < F && li >= P.tile_off[tile * F + f + 1]) ++f;
+        r = __ldg(P.tile_list + li);
+        const int4 a = __ldg(reinterpret_cast<const int4*>(P.hdr + r));
+        // a read below the mapq threshold only produces nX: nothing to accumulate (src/plp.c:574)
+        if (((a.z >> 16) & 0xff) >= P.min_mapq[f]) {
+            const int lo = min(max(a.x - X.t0, 0), X.tw), hi = min(max(a.y - X.t0, 0), X.tw);
+            const int first = max((int)S.fpre[lo], X.round0), last = min((int)S.fpre[hi], X.round0 + X.ns);
+            np = max(last - first, 0);
+            if (np > 0) {
+                const int4 b = __ldg(reinterpret_cast<const int4*>(P.hdr + r) + 1);
+                const int flag = a.z & 0xffff, bits = (a.z >> 24) & 0xff;
+                const int lq = a.w & 0xffff, n = (a.w >> 16) & 0xffff;
+                const uint32_t* cg = P.cigar + (unsigned)b.x;
+                // query_start / query_end (src/plp_utils.c:52-104): soft clips at either end, hard clips skipped
+                int qs = 0, qe = lq, k;
+                for (k = 0; k < n; ++k) {
+                    const uint32_t w = __ldg(cg + k);
+                    if (k < 4) rec[FR_CIG0 + k] = w;
+                    const int op = cg_op(w);
+                    if (op == OP_H) continue;
+                    if (op == OP_S) qs += cg_len(w);
+                    else break;
+                }
+                for (++k; k < n && k < 4; ++k) rec[FR_CIG0 + k] = __ldg(cg + k);
+                for (k = n - 1; k >= 0; --k) {
+                    const uint32_t w = __ldg(cg + k);
+                    const int op = cg_op(w);
+                    if (op == OP_H) continue;
+                    if (op == OP_S) qe -= cg_len(w);
+                    else break;
+                }
+                if (n > 4) rec[FR_CIG0] = (uint32_t)b.x;
+                rec[FR_POS] = (uint32_t)a.x;
+                rec[FR_LEN] = (uint32_t)lq | ((uint32_t)n << 16);
+                rec[FR_SQ] = (uint32_t)b.y;
+                rec[FR_FLAGS] = (unsigned)bits | ((unsigned)((flag >> 4) & 1) << 16) | ((unsigned)f << FRF_FILE_SHIFT);
+                rec[FR_QSQE] = (uint32_t)qs | ((uint32_t)qe << 16);
+                rec[FR_FIRST] = (uint32_t)first;
+            }
+        }
+    }
+    int inc = np;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += v;
+    }
+    pref[lane] = (uint32_t)inc;
+    // ordinal of the read inside its file: what "first seen" means in BAM order
+    pref[32 + lane] = (uint32_t)(r - (int)P.file_off[f]);
+    const int tot = __shfl_sync(FULL, inc, 31);
+    __syncwarp();
+    for (int itb = 0; itb < tot; itb += 32) {
+        __syncwarp();
+        const int it = itb + lane;
+        if (it < tot) {
+            int lo = 0, hh = 31;  // smallest i with pref[i] > it
+#pragma unroll
+            for (int step = 0; step < 5; ++step) {
+                const int mid = (lo + hh) >> 1;
+                if ((int)pref[mid] > it) hh = mid; else lo = mid + 1;
+            }
+            const int i = lo;
+            const int firstp = i ? (int)pref[i - 1] : 0;
+            const uint32_t* ri = st + i * FREC;
+            fast_pair(P, S, X, T2, ri, (int)ri[FR_FIRST] + (it - firstp), (int)pref[32 + i]);
+        }
+    }
+    __syncwarp();
 }
 
 // rpbz / vdb / sor and the ALT order codes of one second-pass slot (shared by both tile kernels)
@@ -420,7 +458,7 @@ __device__ void slot_stats(const PlpParams& P, const uint32_t* slot, int HW, int
 __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ int s_scan[40];
-    __shared__ int s_tile, s_nflag, s_rowbase, s_deep;
+    __shared__ int s_tile, s_nflag, s_rowbase, s_deep, s_chunk;
     __shared__ int s_ni[2];
     const int W = P.W, F = P.n_files;
     FastSmem S;
@@ -428,12 +466,12 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
     const int cnt_words = F * 8 * S.WS;
     S.cnt = smem;
     S.refn = S.cnt + cnt_words;
-    S.fnib = S.refn + (W >> 3) + 4;
-    S.covered = S.fnib + (W >> 3) + 4;
+    S.covered = S.refn + (W >> 3) + 4;
     S.flag_row = (int*)(S.covered + (W >> 5) + 1);
     S.stage = (uint32_t*)(S.flag_row + W);
-    S.slot_of = (uint16_t*)(S.stage + FCAP * FREC);
-    S.flag_d = (uint8_t*)(S.slot_of + W);
+    S.fpre = (uint16_t*)(S.stage + FCAP * FREC);
+    S.flag_pidx = S.fpre + W + 2;
+    S.flag_d = (uint8_t*)(S.flag_pidx + W);
     S.dec = S.flag_d + W;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const CntPacked CN = {S.cnt, S.WS};
@@ -475,7 +513,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
         __syncthreads();
 
         // ---- phase 1: coverage events + exceptional bases
-        fast_walk<0>(P, S, X, T2, tile, t1, t0, t1, s_ni);
+        fast_walk(P, S, X, tile, t1, s_ni);
 
         // ---- coverage: prefix sum of the events, one warp per (file, strand)
         for (int a = wid; a < 2 * F; a += FB_THREADS / 32) {
@@ -509,7 +547,6 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
             int d = 0;
             if (t0 + pidx < t1) d = decide_site(P, CN, S.covered, pidx, t0 + pidx);
             S.dec[pidx] = (uint8_t)d;
-            S.slot_of[pidx] = 0xffff;
             my_rows += (d & 1) + ((d >> 1) & 1);
         }
         int tile_rows_total;
@@ -534,18 +571,19 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
                 const int rank = block_exclusive_scan(fl ? 1 : 0, &ftot, s_scan) + fcarried;  // position-sorted
                 carried += tot;
                 fcarried += ftot;
+                if (pidx < W) S.fpre[pidx] = (uint16_t)rank;
                 if (n) {
                     const long long row = rowbase + off;
                     if (d & 1) write_row(P, CN, pidx, t0 + pidx, 0, row);
                     if (d & 2) write_row(P, CN, pidx, t0 + pidx, 1, row + (d & 1));
                     if (fl) {
-                        S.slot_of[pidx] = (uint16_t)rank;
+                        S.flag_pidx[rank] = (uint16_t)pidx;
                         S.flag_row[rank] = (int)row;
                         S.flag_d[rank] = (uint8_t)d;
                     }
                 }
             }
-            if (threadIdx.x == 0) s_nflag = fcarried;
+            if (threadIdx.x == 0) { s_nflag = fcarried; S.fpre[W] = (uint16_t)fcarried; }
         }
         __syncthreads();
 
@@ -564,22 +602,21 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
                 const bool is_fs = wsl >= HW + 4 && (fw < 4 || fw == 5 || fw == 6);
                 S.cnt[i] = is_fs ? 0xffffffffu : 0u;
             }
-            for (int i = threadIdx.x; i < (W >> 3) + 3; i += blockDim.x) {
-                uint32_t w = 0;
-#pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    const int pidx = 8 * i + m - 8;
-                    if (pidx >= 0 && pidx < W) {
-                        const int rk = (int)S.slot_of[pidx] - round0;
-                        if (S.slot_of[pidx] != 0xffff && rk >= 0 && rk < ns) w |= 1u << (4 * m);
-                    }
-                }
-                S.fnib[i] = w;
-            }
-            if (threadIdx.x == 0) { s_ni[0] = 0; s_ni[1] = 0; }
+            if (threadIdx.x == 0) s_chunk = 0;
             __syncthreads();
-            const int span_lo = t0, span_hi = t1;
-            fast_walk<1>(P, S, X, T2, tile, t1, span_lo, span_hi, s_ni);
+            {
+                const int l0 = P.tile_off[tile * F], l1 = P.tile_off[tile * F + F];
+                const int nchunks = (l1 - l0 + 31) >> 5;
+                uint32_t* st = S.stage + wid * (32 * FREC + 64);
+                while (true) {  // warps pull chunks of 32 listed reads
+                    int c = 0;
+                    if (lane == 0) c = atomicAdd(&s_chunk, 1);
+                    c = __shfl_sync(FULL, c, 0);
+                    if (c >= nchunks) break;
+                    fast_pair_chunk(P, S, X, T2, tile, l0 + (c << 5), l1, lane, st);
+                }
+            }
+            __syncthreads();
             for (int i = threadIdx.x; i < ns; i += blockDim.x) {
                 const int d = S.flag_d[round0 + i], row = S.flag_row[round0 + i];
                 slot_stats(P, S.cnt + (size_t)i * SW, HW, ((d & 1) && (d & 4)) ? row : -1,
@@ -671,8 +708,8 @@ __global__ void k_tile_fill(PlpParams P, long long n_reads, const int* off, int*
 }
 
 extern "C" size_t raer_fast_smem_bytes(int n_files, int W) {
-    const size_t words = (size_t)n_files * 8 * FWS(W) + 2 * ((W >> 3) + 4) + (W >> 5) + 1 + (size_t)W + (size_t)FCAP * FREC;
-    return words * 4 + (size_t)W * 4 + 16;
+    const size_t words = (size_t)n_files * 8 * FWS(W) + (W >> 3) + 4 + (W >> 5) + 1 + (size_t)W + (size_t)FCAP * FREC;
+    return words * 4 + (size_t)(2 * W + 2) * 2 + (size_t)W * 2 + 16;
 }
 
 // widest tile (multiple of 128 positions, at most 1024) that lets two CTAs share one SM; 0 = does not fit

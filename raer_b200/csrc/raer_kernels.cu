@@ -280,20 +280,36 @@ __global__ void k_mate_overlap(const raer_read_hdr* __restrict__ hdr, const uint
             }
         }
         if (A.iseq > ha.l_qseq || B.iseq > hb.l_qseq) return;
-        int qa = a_q[A.iseq], qb = b_q[B.iseq];
-        if (seq_code(a_seq, A.iseq) == seq_code(b_seq, B.iseq)) {
-            int q = qa + qb;
-            if (q > 200) q = 200;
-            if (mode == 2) { a_q[A.iseq] = (uint8_t)q; b_q[B.iseq] = 0; }
-            else { a_q[A.iseq] = (uint8_t)(amul * q); b_q[B.iseq] = (uint8_t)(bmul * q); }
-        } else if (mode == 2) {
-            if (qa >= qb) { a_q[A.iseq] = (uint8_t)(0.8 * qa); b_q[B.iseq] = 0; }
-            else { b_q[B.iseq] = (uint8_t)(0.8 * qb); a_q[A.iseq] = 0; }
-        } else {
-            if (qa > qb) { a_q[A.iseq] = (uint8_t)(0.8 * qa); b_q[B.iseq] = 0; }
-            else if (qa < qb) { b_q[B.iseq] = (uint8_t)(0.8 * qb); a_q[A.iseq] = 0; }
-            else { a_q[A.iseq] = (uint8_t)(amul * 0.8 * qa); b_q[B.iseq] = (uint8_t)(bmul * 0.8 * qb); }
+        // Both cursors sit on the same reference position inside an aligned block. The literal loop would now
+        // step both by one base per iteration until one of the blocks ends; do those `run` extra positions here
+        // without the cursor machinery (same positions, same order, same arithmetic).
+        int run = min(cg_len(A.cig[A.k]) - 1 - A.icig, cg_len(B.cig[B.k]) - 1 - B.icig);
+        run = min(run, min((int)ha.l_qseq - 1 - A.iseq, (int)hb.l_qseq - 1 - B.iseq));
+        // (after a deletion catch-up the two cursors may sit on different positions: no run then)
+        if (run < 0 || A.iref + apos != B.iref + bpos) run = 0;
+        for (int i = 0; i <= run; ++i) {
+            const int ia = A.iseq + i, ib = B.iseq + i;
+            const int qa = a_q[ia], qb = b_q[ib];
+            int na, nb;
+            if (seq_code(a_seq, ia) == seq_code(b_seq, ib)) {
+                int q = qa + qb;
+                if (q > 200) q = 200;
+                if (mode == 2) { na = q; nb = 0; }
+                else { na = amul * q; nb = bmul * q; }
+            } else if (mode == 2) {
+                if (qa >= qb) { na = (uint8_t)(0.8 * qa); nb = 0; }
+                else { nb = (uint8_t)(0.8 * qb); na = 0; }
+            } else {
+                if (qa > qb) { na = (uint8_t)(0.8 * qa); nb = 0; }
+                else if (qa < qb) { nb = (uint8_t)(0.8 * qb); na = 0; }
+                else { na = (uint8_t)(amul * 0.8 * qa); nb = (uint8_t)(bmul * 0.8 * qb); }
+            }
+            a_q[ia] = (uint8_t)na;
+            b_q[ib] = (uint8_t)nb;
         }
+        A.iseq += run; A.icig += run; A.iref += run;
+        B.iseq += run; B.icig += run; B.iref += run;
+        iref += run;
     }
 }
 
