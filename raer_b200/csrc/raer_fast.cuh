@@ -16,9 +16,9 @@
 // reported through err_flag (RAER_ERR_LIMIT).
 //
 // Reads reach a tile through per-tile index lists built by k_tile_count / k_tile_scan / k_tile_fill (every
-// read that overlaps the tile, nothing else), so the CTA stages dense batches of FCAP read records in
-// shared memory and all 512 threads take items from one batch-wide list: no idle lanes for reads that only
-// pass by, no per-warp tails. The second pass (read-position histograms, strand tallies and first-seen
+// read that overlaps the tile, nothing else). Warps work on their own: each pulls chunks of 32 listed reads
+// from a per-tile queue, stages their records in its slice of shared memory and spreads the chunk's items over
+// its lanes, so there is no CTA barrier inside a phase and no idle lanes for reads that only pass by. The second pass (read-position histograms, strand tallies and first-seen
 // order at the sites that carry a variant) is pair parallel: a prefix count of flagged positions gives every
 // read its number of (read, flagged position) pairs in O(1), warps pull chunks of 32 listed reads and their
 // lanes take one pair each.
@@ -27,9 +27,11 @@
 #define RAER_FAST_CUH
 
 #define FB_THREADS 512
-#define FCAP 768  // read records staged per batch
+#define FSTAGE_WORDS (32 * FREC + 64)  // per warp: 32 read records, pair prefix sums, read ordinals
 #define FREC 11   // words per record (odd: lanes reading one field of different records spread over banks)
-enum { FR_POS = 0, FR_LEN, FR_SQ, FR_FLAGS, FR_QSQE, FR_FIRST, FR_CIG0 };  // FR_CIG0..+3: CIGAR words, or [0] = offset if n > 4
+enum { FR_POS = 0, FR_LEN, FR_SQ, FR_FLAGS, FR_QSQE, FR_FIRST, FR_RCP, FR_CIG0 };  // FR_CIG0..+3: CIGAR words, or [0] = offset if n > 4
+#define STF_SIMPLE 0x400u  // one aligned block, nothing but clips around it: query q sits on pos + q - qs
+#define FWMAX 1024         // widest tile; the fixed part of the shared-memory layout is sized for it
 #define FRF_FILE_SHIFT 24
 #define FWS(W) ((W) + 8)  // words per counter array: W positions + the -1 event one past the end
 
@@ -38,7 +40,7 @@ struct FastSmem {
     uint32_t* refn;     // packed reference: nibble i of word k = nt16 code of position t0 - 8 + 8k + i
     uint32_t* covered;  // min_depth <= 0 only: a pileup column exists here
     int* flag_row;      // per flagged site: its first output row
-    uint32_t* stage;    // FCAP records
+    uint32_t* stage;    // FSTAGE_WORDS per warp
     uint16_t* fpre;     // per position (W + 1): number of flagged sites before it (their ranks are position sorted)
     uint16_t* flag_pidx;  // per flagged site: its tile position
     uint8_t* flag_d;    // per flagged site: decision bits
@@ -157,6 +159,12 @@ __device__ __forceinline__ void fast_item(const PlpParams& P, const FastSmem& S,
     const uint32_t Q = bytes_to_nibbles((byte_lt(qw.x, X.mb4) >> 7) | (byte_zero(qw.x) >> 6),
                                         (byte_lt(qw.y, X.mb4) >> 7) | (byte_zero(qw.y) >> 6));
     const uint32_t LT = Q & 0x11111111u, Z = (Q >> 1) & 0x11111111u & X.zall;
+    if (fl & STF_SIMPLE) {  // the aligned block is query [qs, qe)
+        const int qs = (int)(rec[FR_QSQE] & 0xffff), qe = (int)(rec[FR_QSQE] >> 16);
+        if (qe > q0 && qs < q1)
+            fast_block_count(S, X, cbs, rw, NM, LT, Z, mapq_fail, s ? 3 : 0, pos + (q0 - qs) - X.t0, qs - q0, min(qe, q1) - q0);
+        return;
+    }
     const uint32_t* cig = n <= 4 ? rec + FR_CIG0 : P.cigar + rec[FR_CIG0];
     int x = pos, y = 0;
     for (int k = 0; k < n && y < q1; ++k) {
@@ -190,10 +198,15 @@ __device__ __forceinline__ int fast_stage(const PlpParams& P, const FastSmem& S,
     const uint32_t* cg = P.cigar + (unsigned)b.x;
     uint32_t* dl = S.cnt + (size_t)((f * 2 + s) * 4) * S.WS;
     int x = a.x, y = 0;
+    int qs = 0, tail = 0, nblk = 0, other = 0;
+    bool lead = true;
     for (int k = 0; k < n; ++k) {
         const uint32_t w = __ldg(cg + k);
         if (k < 4) rec[FR_CIG0 + k] = w;
         const int op = cg_op(w), len = cg_len(w);
+        // query_start / query_end (src/plp_utils.c:52-104): soft clips at either end, hard clips skipped
+        if (op == OP_S) { if (lead) qs += len; tail += len; }
+        else if (op != OP_H) { lead = false; tail = 0; if ((0x181 >> op) & 1) ++nblk; else other = 1; }
         if (NEEDCOV && (cg_type(op) & 2)) {
             const int lo = max(x, X.t0), h2 = min(x + len, t1);
             if (lo < h2) cover_range(S.covered, lo - X.t0, h2 - X.t0);
@@ -213,81 +226,75 @@ __device__ __forceinline__ int fast_stage(const PlpParams& P, const FastSmem& S,
             y += len;
         }
     }
+    if (nblk == 1 && !other && qs + (x - a.x) == lq - tail) fl |= STF_SIMPLE;
     if (n > 4) rec[FR_CIG0] = (uint32_t)b.x;
     rec[FR_POS] = (uint32_t)a.x;
     rec[FR_LEN] = (uint32_t)lq | ((uint32_t)n << 16);
     rec[FR_SQ] = (uint32_t)b.y;
     rec[FR_FLAGS] = fl;
+    rec[FR_QSQE] = (uint32_t)qs | ((uint32_t)(lq - tail) << 16);
     return (lq + 7) >> 3;
 }
 
-// Phase 1 over every read of the tile: stage dense batches of FCAP records, then take items from the batch-wide list.
-__device__ void fast_walk(const PlpParams& P, const FastSmem& S, const FastCtx& X, int tile, int t1, int* s_ni) {
+// Phase 1 for one chunk of 32 listed reads, handled by one warp on its own (no CTA barrier): stage the records,
+// then the lanes take the chunk's items, two in flight per lane.
+__device__ __forceinline__ void fast_count_chunk(const PlpParams& P, const FastSmem& S, const FastCtx& X, int tile, int li0,
+                                                 int l1, int t1, int lane, uint32_t* st, bool need_cov) {
     const int F = P.n_files;
-    const int l0 = P.tile_off[tile * F], l1 = P.tile_off[tile * F + F];
-    const bool need_cov = P.min_depth <= 0;
-    int parity = 0;
-    for (int base = l0; base < l1; base += FCAP, parity ^= 1) {
-        const int nb = min(FCAP, l1 - base);
-        int ni = 0;
-        for (int k = threadIdx.x; k < nb; k += FB_THREADS) {
-            const int li = base + k;
-            int f = 0;
-            while (f + 1 < F && li >= P.tile_off[tile * F + f + 1]) ++f;
-            const int r = __ldg(P.tile_list + li);
-            uint32_t* rec = S.stage + k * FREC;
-            ni = max(ni, need_cov ? fast_stage<true>(P, S, X, r, f, t1, rec) : fast_stage<false>(P, S, X, r, f, t1, rec));
-        }
-        ni = __reduce_max_sync(FULL, ni);
-        if ((threadIdx.x & 31) == 0 && ni > 0) atomicMax(&s_ni[parity], ni);
-        __syncthreads();
-        const int NI = s_ni[parity];  // item slots per record of this batch
-        if (threadIdx.x == 0) s_ni[parity ^ 1] = 0;
-        if (NI > 0) {
-            const int tot = nb * NI;
-            const uint32_t M32 = (uint32_t)((0x100000000ull + NI - 1) / NI);  // it / NI == umulhi(it, M32) while it * NI < 2^32
-            const bool mul_ok = NI > 1 && (unsigned long long)tot * NI < 0x100000000ull;
-            for (int itb = 0; itb < tot; itb += 2 * FB_THREADS) {
-                // The trip count is CTA-uniform, so the warp can be re-joined here: without it the lanes that took
-                // different paths through the previous items keep running as separate sub-warps.
-                __syncwarp();
-                // two items in flight per thread
-                const uint32_t* recA = S.stage;
-                const uint32_t* recB = S.stage;
-                int qA = 0, qB = 0;
-                uint32_t swA = 0, swB = 0;
-                uint2 qwA = make_uint2(0, 0), qwB = make_uint2(0, 0);
-                const int itA = itb + threadIdx.x, itB = itA + FB_THREADS;
-                bool okA = itA < tot, okB = itB < tot;
-                if (okA) {
-                    const int i = mul_ok ? (int)__umulhi((uint32_t)itA, M32) : itA / NI;
-                    recA = S.stage + i * FREC;
-                    qA = (itA - i * NI) << 3;
-                    okA = qA < (int)(recA[FR_LEN] & 0xffff);
-                }
-                if (okA) {
-                    const uint32_t sq = recA[FR_SQ];
-                    swA = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qA >> 1)));
-                    qwA = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qA));
-                }
-                if (okB) {
-                    const int i = mul_ok ? (int)__umulhi((uint32_t)itB, M32) : itB / NI;
-                    recB = S.stage + i * FREC;
-                    qB = (itB - i * NI) << 3;
-                    okB = qB < (int)(recB[FR_LEN] & 0xffff);
-                }
-                if (okB) {
-                    const uint32_t sq = recB[FR_SQ];
-                    swB = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qB >> 1)));
-                    qwB = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qB));
-                }
-                if (okA) fast_item(P, S, X, recA, qA, swA, qwA);
-                __syncwarp();
-                if (okB) fast_item(P, S, X, recB, qB, swB, qwB);
-            }
-        }
-        __syncthreads();
+    const int li = li0 + lane;
+    uint32_t* rec = st + lane * FREC;
+    int nq = 0;
+    if (li < l1) {
+        int f = 0;
+        while (f + 1 < F && li >= P.tile_off[tile * F + f + 1]) ++f;
+        const int r = __ldg(P.tile_list + li);
+        nq = need_cov ? fast_stage<true>(P, S, X, r, f, t1, rec) : fast_stage<false>(P, S, X, r, f, t1, rec);
     }
+    const int NI = __reduce_max_sync(FULL, nq);  // item slots per record of this chunk
+    __syncwarp();
+    if (NI > 0) {
+        const int tot = min(32, l1 - li0) * NI;
+        const uint32_t M32 = (uint32_t)((0x100000000ull + NI - 1) / NI);  // it / NI == umulhi(it, M32) while it * NI < 2^32
+        const bool mul_ok = NI > 1 && (unsigned long long)tot * NI < 0x100000000ull;
+        for (int itb = 0; itb < tot; itb += 64) {
+            // The trip count is warp-uniform, so the warp can be re-joined here: without it the lanes that took
+            // different paths through the previous items keep running as separate sub-warps.
+            __syncwarp();
+            const uint32_t* recA = st;
+            const uint32_t* recB = st;
+            int qA = 0, qB = 0;
+            uint32_t swA = 0, swB = 0;
+            uint2 qwA = make_uint2(0, 0), qwB = make_uint2(0, 0);
+            const int itA = itb + lane, itB = itA + 32;
+            bool okA = itA < tot, okB = itB < tot;
+            if (okA) {
+                const int i = mul_ok ? (int)__umulhi((uint32_t)itA, M32) : itA / NI;
+                recA = st + i * FREC;
+                qA = (itA - i * NI) << 3;
+                okA = qA < (int)(recA[FR_LEN] & 0xffff);
+            }
+            if (okA) {
+                const uint32_t sq = recA[FR_SQ];
+                swA = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qA >> 1)));
+                qwA = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qA));
+            }
+            if (okB) {
+                const int i = mul_ok ? (int)__umulhi((uint32_t)itB, M32) : itB / NI;
+                recB = st + i * FREC;
+                qB = (itB - i * NI) << 3;
+                okB = qB < (int)(recB[FR_LEN] & 0xffff);
+            }
+            if (okB) {
+                const uint32_t sq = recB[FR_SQ];
+                swB = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qB >> 1)));
+                qwB = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qB));
+            }
+            if (okA) fast_item(P, S, X, recA, qA, swA, qwA);
+            __syncwarp();
+            if (okB) fast_item(P, S, X, recB, qB, swB, qwB);
+        }
+    }
+    __syncwarp();
 }
 
 // ---- second pass: one (read, flagged position) pair per lane
@@ -300,22 +307,29 @@ __device__ __forceinline__ void fast_pair(const PlpParams& P, const FastSmem& S,
     const uint32_t* cig = n <= 4 ? rec + FR_CIG0 : P.cigar + rec[FR_CIG0];
     const int pidx = (int)S.flag_pidx[rank];
     const int p = X.t0 + pidx;
-    int x = pos, y = 0, k = 0, op = -1, len = 0;
-    for (; k < n; ++k) {
-        const uint32_t w = cig[k];
-        op = cg_op(w);
-        len = cg_len(w);
-        if ((0x18D >> op) & 1) {  // M D N = X
-            if (p < x + len) break;
-            x += len;
-            if ((0x181 >> op) & 1) y += len;
-        } else if ((0x12 >> op) & 1) {
-            y += len;
+    const int qs = (int)(rec[FR_QSQE] & 0xffff), qe = (int)(rec[FR_QSQE] >> 16);
+    int q;
+    if (fl & STF_SIMPLE) {
+        q = qs + (p - pos);
+        if (q >= qe) return;
+    } else {
+        int x = pos, y = 0, k = 0, op = -1, len = 0;
+        for (; k < n; ++k) {
+            const uint32_t w = cig[k];
+            op = cg_op(w);
+            len = cg_len(w);
+            if ((0x18D >> op) & 1) {  // M D N = X
+                if (p < x + len) break;
+                x += len;
+                if ((0x181 >> op) & 1) y += len;
+            } else if ((0x12 >> op) & 1) {
+                y += len;
+            }
         }
+        if (k >= n) return;            // past the end of the read
+        if ((0xC >> op) & 1) return;   // deletion / ref-skip at p: filtered silently (src/plp.c:571)
+        q = y + (p - x);
     }
-    if (k >= n) return;            // past the end of the read
-    if ((0xC >> op) & 1) return;   // deletion / ref-skip at p: filtered silently (src/plp.c:571)
-    const int q = y + (p - x);
     if (q >= lq) return;
     const int code = seq_code(P.seq + sq, q);
     if (code == 15) return;        // src/plp.c:718
@@ -325,12 +339,12 @@ __device__ __forceinline__ void fast_pair(const PlpParams& P, const FastSmem& S,
     const int rcode = (S.refn[a >> 3] >> ((a & 7) << 2)) & 15;
     ReadCtx c;
     c.l_qseq = lq;
-    c.qs = (int)(rec[FR_QSQE] & 0xffff);
-    c.qe = (int)(rec[FR_QSQE] >> 16);
+    c.qs = qs;
+    c.qe = qe;
     c.rev = (fl >> 16) & 1;
     c.invert = fl & RAER_RB_INVERT;
-    pass2_accumulate_core(P, T2, c, (int)(fl >> FRF_FILE_SHIFT), c.invert ? 1 : 0, ordinal, rank - X.round0, q, code,
-                          (code == rcode) & (code != 0));
+    pass2_accumulate_core(P, T2, c, (int)((fl >> FRF_FILE_SHIFT) & 0x3f), c.invert ? 1 : 0, ordinal, rank - X.round0, q, code,
+                          (code == rcode) & (code != 0), rec[FR_RCP]);
 }
 
 // One chunk of 32 listed reads, handled by one warp: stage the reads that cover a flagged site of this round,
@@ -357,30 +371,28 @@ __device__ __forceinline__ void fast_pair_chunk(const PlpParams& P, const FastSm
                 const int lq = a.w & 0xffff, n = (a.w >> 16) & 0xffff;
                 const uint32_t* cg = P.cigar + (unsigned)b.x;
                 // query_start / query_end (src/plp_utils.c:52-104): soft clips at either end, hard clips skipped
-                int qs = 0, qe = lq, k;
-                for (k = 0; k < n; ++k) {
+                int qs = 0, tail = 0, nblk = 0, other = 0, rl = 0;
+                bool lead = true;
+                for (int k = 0; k < n; ++k) {
                     const uint32_t w = __ldg(cg + k);
                     if (k < 4) rec[FR_CIG0 + k] = w;
-                    const int op = cg_op(w);
-                    if (op == OP_H) continue;
-                    if (op == OP_S) qs += cg_len(w);
-                    else break;
+                    const int op = cg_op(w), len = cg_len(w);
+                    if (op == OP_S) { if (lead) qs += len; tail += len; }
+                    else if (op != OP_H) { lead = false; tail = 0; if ((0x181 >> op) & 1) { ++nblk; rl += len; } else other = 1; }
                 }
-                for (++k; k < n && k < 4; ++k) rec[FR_CIG0 + k] = __ldg(cg + k);
-                for (k = n - 1; k >= 0; --k) {
-                    const uint32_t w = __ldg(cg + k);
-                    const int op = cg_op(w);
-                    if (op == OP_H) continue;
-                    if (op == OP_S) qe -= cg_len(w);
-                    else break;
-                }
+                const int qe = lq - tail;
+                unsigned fl = (unsigned)bits | ((unsigned)((flag >> 4) & 1) << 16) | ((unsigned)f << FRF_FILE_SHIFT);
+                if (nblk == 1 && !other && qs + rl == qe) fl |= STF_SIMPLE;
                 if (n > 4) rec[FR_CIG0] = (uint32_t)b.x;
                 rec[FR_POS] = (uint32_t)a.x;
                 rec[FR_LEN] = (uint32_t)lq | ((uint32_t)n << 16);
                 rec[FR_SQ] = (uint32_t)b.y;
-                rec[FR_FLAGS] = (unsigned)bits | ((unsigned)((flag >> 4) & 1) << 16) | ((unsigned)f << FRF_FILE_SHIFT);
+                rec[FR_FLAGS] = fl;
                 rec[FR_QSQE] = (uint32_t)qs | ((uint32_t)qe << 16);
                 rec[FR_FIRST] = (uint32_t)first;
+                // get_relative_position divides by alen + 1 = qe - qs + 1 (src/plp_utils.c:401-412): reciprocal once per read
+                const int rb = qe - qs + 1;
+                rec[FR_RCP] = rb > 1 ? (uint32_t)((0x100000000ull + rb - 1) / rb) : 0u;
             }
         }
     }
@@ -459,20 +471,21 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ int s_scan[40];
     __shared__ int s_tile, s_nflag, s_rowbase, s_deep, s_chunk;
-    __shared__ int s_ni[2];
     const int W = P.W, F = P.n_files;
     FastSmem S;
     S.WS = FWS(W);
     const int cnt_words = F * 8 * S.WS;
-    S.cnt = smem;
-    S.refn = S.cnt + cnt_words;
-    S.covered = S.refn + (W >> 3) + 4;
-    S.flag_row = (int*)(S.covered + (W >> 5) + 1);
-    S.stage = (uint32_t*)(S.flag_row + W);
-    S.fpre = (uint16_t*)(S.stage + FCAP * FREC);
-    S.flag_pidx = S.fpre + W + 2;
-    S.flag_d = (uint8_t*)(S.flag_pidx + W);
-    S.dec = S.flag_d + W;
+    // everything but the counters sits at constant offsets (no address arithmetic on W or the file count in the
+    // item loops); the counters, whose size depends on both, come last
+    S.stage = smem;
+    S.refn = S.stage + FB_THREADS / 32 * FSTAGE_WORDS;
+    S.covered = S.refn + (FWMAX >> 3) + 4;
+    S.flag_row = (int*)(S.covered + (FWMAX >> 5) + 4);
+    S.fpre = (uint16_t*)(S.flag_row + FWMAX);
+    S.flag_pidx = S.fpre + FWMAX + 8;
+    S.flag_d = (uint8_t*)(S.flag_pidx + FWMAX);
+    S.dec = S.flag_d + FWMAX;
+    S.cnt = (uint32_t*)(S.dec + FWMAX);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const CntPacked CN = {S.cnt, S.WS};
     TileSmem T2;
@@ -509,11 +522,24 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
             for (int m = 0; m < 8; ++m) w |= (uint32_t)ref_nibble(P, p0 + m) << (4 * m);
             S.refn[i] = w;
         }
-        if (threadIdx.x == 0) { s_nflag = 0; s_deep = 0; s_ni[0] = 0; s_ni[1] = 0; }
+        if (threadIdx.x == 0) { s_nflag = 0; s_deep = 0; s_chunk = 0; }
         __syncthreads();
 
         // ---- phase 1: coverage events + exceptional bases
-        fast_walk(P, S, X, tile, t1, s_ni);
+        {
+            const int l0 = P.tile_off[tile * F], l1 = P.tile_off[tile * F + F];
+            const int nchunks = (l1 - l0 + 31) >> 5;
+            const bool need_cov = P.min_depth <= 0;
+            uint32_t* st = S.stage + wid * FSTAGE_WORDS;
+            while (true) {  // warps pull chunks of 32 listed reads
+                int c = 0;
+                if (lane == 0) c = atomicAdd(&s_chunk, 1);
+                c = __shfl_sync(FULL, c, 0);
+                if (c >= nchunks) break;
+                fast_count_chunk(P, S, X, tile, l0 + (c << 5), l1, t1, lane, st, need_cov);
+            }
+        }
+        __syncthreads();
 
         // ---- coverage: prefix sum of the events, one warp per (file, strand)
         for (int a = wid; a < 2 * F; a += FB_THREADS / 32) {
@@ -607,7 +633,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
             {
                 const int l0 = P.tile_off[tile * F], l1 = P.tile_off[tile * F + F];
                 const int nchunks = (l1 - l0 + 31) >> 5;
-                uint32_t* st = S.stage + wid * (32 * FREC + 64);
+                uint32_t* st = S.stage + wid * FSTAGE_WORDS;
                 while (true) {  // warps pull chunks of 32 listed reads
                     int c = 0;
                     if (lane == 0) c = atomicAdd(&s_chunk, 1);
@@ -707,9 +733,9 @@ __global__ void k_tile_fill(PlpParams P, long long n_reads, const int* off, int*
     }
 }
 
+#define FFIXED_BYTES ((FB_THREADS / 32 * FSTAGE_WORDS + (FWMAX >> 3) + 4 + (FWMAX >> 5) + 4 + FWMAX) * 4 + (2 * FWMAX + 8) * 2 + 2 * FWMAX)
 extern "C" size_t raer_fast_smem_bytes(int n_files, int W) {
-    const size_t words = (size_t)n_files * 8 * FWS(W) + (W >> 3) + 4 + (W >> 5) + 1 + (size_t)W + (size_t)FCAP * FREC;
-    return words * 4 + (size_t)(2 * W + 2) * 2 + (size_t)W * 2 + 16;
+    return (size_t)FFIXED_BYTES + (size_t)n_files * 8 * FWS(W) * 4 + 16;
 }
 
 // widest tile (multiple of 128 positions, at most 1024) that lets two CTAs share one SM; 0 = does not fit

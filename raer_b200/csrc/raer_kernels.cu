@@ -602,7 +602,8 @@ __device__ void write_row(const PlpParams& P, const CNT cnt, int pidx, int p, in
 // Second-pass accumulation of one counted base at a flagged site: read-position histogram, strand
 // tallies, first-seen order of the variant keys.
 __device__ __forceinline__ void pass2_accumulate_core(const PlpParams& P, const TileSmem& S, const ReadCtx& c, int f, int s,
-                                                      int ordinal, int slot_index, int q, int code, int isref) {
+                                                      int ordinal, int slot_index, int q, int code, int isref,
+                                                      uint32_t rcp = 0) {
     const int HW = S.hist_words;  // 400: 32-bit bins; 200: two 16-bit bins per word (tile depth <= 65535)
     uint32_t* slot = S.cnt + (size_t)slot_index * S.slot_words;
     int cls = cls_of_code(code);
@@ -616,7 +617,9 @@ __device__ __forceinline__ void pass2_accumulate_core(const PlpParams& P, const 
     const int ra = q + 1 - c.qs, rb = alen + 1;
     int rpos;
     if (ra > 0 && rb > 0 && ra < (1 << 24)) {
-        rpos = (99 * ra) / rb;
+        // rcp = ceil(2^32 / rb), staged once per read: exact quotient while 99 * ra * rb < 2^32
+        if (rcp && ra < 4096 && rb < 4096) rpos = (int)__umulhi((uint32_t)(99 * ra), rcp);
+        else rpos = (99 * ra) / rb;
         if (rpos * rb == 99 * ra) rpos = (int)((double)ra / (double)rb * 99.0);
     } else {
         rpos = (int)((double)ra / (double)rb * 99.0);
