@@ -54,13 +54,6 @@ __device__ __forceinline__ void red_add(uint32_t* p, uint32_t v) {
 __device__ __forceinline__ void red_add_s(unsigned saddr, uint32_t v) {  // saddr: shared-window byte address
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
-// BAM packs base 2b in the high nibble of byte b; after the swap base j sits in nibble j of the word
-__device__ __forceinline__ uint32_t nib_swap(uint32_t w) { return ((w & 0x0f0f0f0fu) << 4) | ((w >> 4) & 0x0f0f0f0fu); }
-__device__ __forceinline__ uint32_t nib_nonzero(uint32_t x) {  // bit 4j set iff nibble j != 0
-    uint32_t t = x | (x >> 2);
-    t |= t >> 1;
-    return t & 0x11111111u;
-}
 // per byte: bit 7 set iff byte < m (m4 = m in every byte, m <= 128: no borrow crosses a byte)
 __device__ __forceinline__ uint32_t byte_lt(uint32_t v, uint32_t m4) { return ~(((v | 0x80808080u) - m4) | v) & 0x80808080u; }
 __device__ __forceinline__ uint32_t byte_zero(uint32_t v) { return ~(((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u; }
@@ -664,14 +657,21 @@ __device__ __forceinline__ bool tile_span(const PlpParams& P, long long r, int& 
     tl = (min(pe.y, P.t_end) - 1 - P.t_beg) / P.W;
     return true;
 }
+// Reads are coordinate sorted, so the lanes of a warp mostly share their (tile, file): one atomic per distinct key
+// and warp step instead of one per read (the tile counters would serialise them).
+#define TILE_AGG_STEPS 8  // tiles of a long read handled warp-synchronously; anything beyond takes plain atomics
 __global__ void k_tile_count(PlpParams P, long long n_reads, int* cnt) {
     const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     int f = 0, tf = 0, tl = -1;
     const bool ok = r < n_reads && tile_span(P, r, f, tf, tl);
-    const int key = ok ? tf * P.n_files + f : -1;
-    const unsigned peers = __match_any_sync(FULL, key);  // sorted reads: a warp mostly shares one (tile, file)
-    if (ok && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&cnt[key], __popc(peers));
-    for (int t = tf + 1; t <= tl; ++t) atomicAdd(&cnt[t * P.n_files + f], 1);
+    const int more = __reduce_max_sync(FULL, ok ? tl - tf : -1);
+    for (int k = 0; k <= min(more, TILE_AGG_STEPS); ++k) {
+        const int key = (ok && tf + k <= tl) ? (tf + k) * P.n_files + f : -1;
+        const unsigned peers = __match_any_sync(FULL, key);
+        if (key >= 0 && (int)(__ffs(peers) - 1) == lane) atomicAdd(&cnt[key], __popc(peers));
+    }
+    for (int t = tf + TILE_AGG_STEPS + 1; t <= tl; ++t) atomicAdd(&cnt[t * P.n_files + f], 1);
 }
 // exclusive scan of n counts into off[0..n] (one CTA), cursors cleared
 __global__ void k_tile_scan(const int* cnt, int* off, int* cur, int n, int* total) {
@@ -716,17 +716,20 @@ __global__ void k_tile_fill(PlpParams P, long long n_reads, const int* off, int*
     const int lane = threadIdx.x & 31;
     int f = 0, tf = 0, tl = -1;
     const bool ok = r < n_reads && tile_span(P, r, f, tf, tl);
-    const int key = ok ? tf * P.n_files + f : -1;
-    const unsigned peers = __match_any_sync(FULL, key);
-    const int leader = __ffs(peers) - 1;
-    int first = 0;
-    if (ok && leader == lane) first = atomicAdd(&cur[key], __popc(peers));
-    first = __shfl_sync(FULL, first, leader);
-    if (ok) {
-        const int slot = off[key] + first + __popc(peers & ((1u << lane) - 1u));
-        if (slot < cap) list[slot] = (int)r;
+    const int more = __reduce_max_sync(FULL, ok ? tl - tf : -1);
+    for (int k = 0; k <= min(more, TILE_AGG_STEPS); ++k) {
+        const int key = (ok && tf + k <= tl) ? (tf + k) * P.n_files + f : -1;
+        const unsigned peers = __match_any_sync(FULL, key);
+        const int leader = __ffs(peers) - 1;
+        int first = 0;
+        if (key >= 0 && leader == lane) first = atomicAdd(&cur[key], __popc(peers));
+        first = __shfl_sync(FULL, first, leader);
+        if (key >= 0) {
+            const int slot = off[key] + first + __popc(peers & ((1u << lane) - 1u));
+            if (slot < cap) list[slot] = (int)r;
+        }
     }
-    for (int t = tf + 1; t <= tl; ++t) {
+    for (int t = tf + TILE_AGG_STEPS + 1; t <= tl; ++t) {
         const int k2 = t * P.n_files + f;
         const int slot = off[k2] + atomicAdd(&cur[k2], 1);
         if (slot < cap) list[slot] = (int)r;

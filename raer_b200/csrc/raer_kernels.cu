@@ -56,6 +56,13 @@ __device__ __forceinline__ int d_comp_char(int c) {  // src/plp_utils.c:438-455 
     default: return c;
     }
 }
+// BAM packs base 2b in the high nibble of byte b; after the swap base j sits in nibble j of the word
+__device__ __forceinline__ uint32_t nib_swap(uint32_t w) { return ((w & 0x0f0f0f0fu) << 4) | ((w >> 4) & 0x0f0f0f0fu); }
+__device__ __forceinline__ uint32_t nib_nonzero(uint32_t x) {  // bit 4j set iff nibble j != 0
+    uint32_t t = x | (x >> 2);
+    t |= t >> 1;
+    return t & 0x11111111u;
+}
 __device__ __forceinline__ int seq_code(const uint8_t* seq, int q) { return (seq[q >> 1] >> ((~q & 1) << 2)) & 0xf; }
 
 struct ReadCtx {
@@ -226,6 +233,84 @@ __device__ int cur_next(CigCur& c) {
     return -1;
 }
 
+// per byte: min(a + b, 200), the quality two agreeing mates share (htslib tweak_overlap_quality)
+__device__ __forceinline__ uint32_t qsum200(uint32_t a, uint32_t b) {
+    const uint32_t e = __vminu2((a & 0x00ff00ffu) + (b & 0x00ff00ffu), 0x00c800c8u);
+    const uint32_t o = __vminu2(((a >> 8) & 0x00ff00ffu) + ((b >> 8) & 0x00ff00ffu), 0x00c800c8u);
+    return e | (o << 8);
+}
+
+// Apply the overlap rule to run + 1 consecutive positions: base ia0 + i of read A faces base ib0 + i of read B.
+// 8 qualities at a time: one aligned 64-bit word of A, the matching bytes of B funnelled out of two aligned
+// words, 8 packed bases of each read compared by XOR, agreeing bases summed byte-parallel; only disagreeing bases
+// run scalar code. Whole words are written back (a read owns its 8-byte quality words, raer_read_hdr.sq_off).
+__device__ __forceinline__ void overlap_run(uint8_t* a_q, uint8_t* b_q, const uint8_t* a_seq, const uint8_t* b_seq, int ia0,
+                                            int ib0, int run, int amul, int bmul, int mode) {
+    for (int i = 0; i <= run;) {
+        const int ia = ia0 + i, ib = ib0 + i;
+        const int oa = ia & 7, ob = ib & 7;
+        const int nbp = min(8 - oa, run + 1 - i);
+        uint8_t* pa = a_q + (ia - oa);
+        uint8_t* pb = b_q + (ib - ob);
+        const bool two = ob + nbp > 8;
+        const unsigned long long wa = *reinterpret_cast<const unsigned long long*>(pa);
+        const unsigned long long wb0 = *reinterpret_cast<const unsigned long long*>(pb);
+        const unsigned long long wb1 = two ? *reinterpret_cast<const unsigned long long*>(pb + 8) : 0ull;
+        const unsigned long long QA = wa >> (8 * oa);
+        const unsigned long long QB = ob ? ((wb0 >> (8 * ob)) | (wb1 << (64 - 8 * ob))) : wb0;
+        // base j of the chunk in nibble j
+        const uint32_t sa = nib_swap(*reinterpret_cast<const uint32_t*>(a_seq + ((ia - oa) >> 1))) >> (4 * oa);
+        const uint32_t sb0 = nib_swap(*reinterpret_cast<const uint32_t*>(b_seq + ((ib - ob) >> 1)));
+        const uint32_t sb1 = two ? nib_swap(*reinterpret_cast<const uint32_t*>(b_seq + ((ib - ob) >> 1) + 4)) : 0u;
+        const uint32_t xs = sa ^ (ob ? ((sb0 >> (4 * ob)) | (sb1 << (32 - 4 * ob))) : sb0);
+        const unsigned long long mk = nbp == 8 ? ~0ull : ((1ull << (8 * nbp)) - 1ull);
+        // agreeing bases: one mate gets min(qa + qb, 200), the other 0 (mode 2: always the earlier mate)
+        const unsigned long long QS = (unsigned long long)qsum200((uint32_t)QA, (uint32_t)QB) |
+                                      ((unsigned long long)qsum200((uint32_t)(QA >> 32), (uint32_t)(QB >> 32)) << 32);
+        unsigned long long NA = amul ? QS : 0ull, NB = bmul ? QS : 0ull;
+        uint32_t mm = nib_nonzero(xs) & (nbp == 8 ? 0x11111111u : ((1u << (4 * nbp)) - 1u) & 0x11111111u);
+        while (mm) {  // disagreeing bases
+            const int j = (__ffs(mm) - 1) >> 2;
+            mm &= mm - 1;
+            const int qa = (int)((QA >> (8 * j)) & 0xff), qb = (int)((QB >> (8 * j)) & 0xff);
+            int na, nb;
+            if (mode == 2) {
+                if (qa >= qb) { na = (uint8_t)(0.8 * qa); nb = 0; }
+                else { nb = (uint8_t)(0.8 * qb); na = 0; }
+            } else {
+                if (qa > qb) { na = (uint8_t)(0.8 * qa); nb = 0; }
+                else if (qa < qb) { nb = (uint8_t)(0.8 * qb); na = 0; }
+                else { na = (uint8_t)(amul * 0.8 * qa); nb = (uint8_t)(bmul * 0.8 * qb); }
+            }
+            const unsigned long long bm = 0xffull << (8 * j);
+            NA = (NA & ~bm) | ((unsigned long long)(na & 0xff) << (8 * j));
+            NB = (NB & ~bm) | ((unsigned long long)(nb & 0xff) << (8 * j));
+        }
+        NA &= mk;
+        NB &= mk;
+        *reinterpret_cast<unsigned long long*>(pa) = (wa & ~(mk << (8 * oa))) | (NA << (8 * oa));
+        *reinterpret_cast<unsigned long long*>(pb) = (wb0 & ~(mk << (8 * ob))) | (NB << (8 * ob));
+        if (two) *reinterpret_cast<unsigned long long*>(pb + 8) = (wb1 & ~(mk >> (64 - 8 * ob))) | (NB >> (64 - 8 * ob));
+        i += nbp;
+    }
+}
+
+// true iff the CIGAR is one aligned block with nothing but clips around it; qs = leading soft clip, len = block length
+__device__ __forceinline__ bool single_block(const uint32_t* cig, int n, int& qs, int& len) {
+    int nblk = 0, q = 0;
+    bool other = false;
+    len = 0;
+    for (int k = 0; k < n; ++k) {
+        const uint32_t w = cig[k];
+        const int op = cg_op(w);
+        if (op == OP_M || op == OP_EQ || op == OP_X) { ++nblk; len = cg_len(w); }
+        else if (op == OP_S) { if (!nblk) q += cg_len(w); }
+        else if (op != OP_H) other = true;
+    }
+    qs = q;
+    return nblk == 1 && !other;
+}
+
 __global__ void k_mate_overlap(const raer_read_hdr* __restrict__ hdr, const uint32_t* __restrict__ cigar,
                                const uint8_t* __restrict__ seq, uint8_t* qual, const int32_t* __restrict__ pair_b,
                                long long n_pairs, int mode) {
@@ -241,14 +326,27 @@ __global__ void k_mate_overlap(const raer_read_hdr* __restrict__ hdr, const uint
     uint8_t* a_q = qual + 2ull * ha.sq_off;
     uint8_t* b_q = qual + 2ull * hb.sq_off;
     const int apos = ha.pos, bpos = hb.pos;
+    int amul, bmul;
+    if (mode == 2 || (hb.bits & RAER_RB_KEEP_A)) { amul = 1; bmul = 0; }
+    else { amul = 0; bmul = 1; }
+    {
+        // Both mates are one aligned block: the cursors below would visit every position of the intersection in
+        // order with equal positions, i.e. one run.
+        int qsa, lena, qsb, lenb;
+        if (single_block(A.cig, A.n, qsa, lena) && single_block(B.cig, B.n, qsb, lenb)) {
+            if (bpos < apos) return;  // cur_set(A, negative): nothing to do
+            const int lo = bpos, hi = min(apos + lena, bpos + lenb);
+            const int ia0 = qsa + (lo - apos), ib0 = qsb;
+            const int run = min(hi - lo - 1, min((int)ha.l_qseq - 1 - ia0, (int)hb.l_qseq - 1 - ib0));
+            if (run >= 0) overlap_run(a_q, b_q, a_seq, b_seq, ia0, ib0, run, amul, bmul, mode);
+            return;
+        }
+    }
     int iref = bpos;
     int a_ret = cur_set(A, iref - apos);
     if (a_ret < 0) return;
     int b_ret = cur_set(B, iref - bpos);
     if (b_ret < 0) return;
-    int amul, bmul;
-    if (mode == 2 || (hb.bits & RAER_RB_KEEP_A)) { amul = 1; bmul = 0; }
-    else { amul = 0; bmul = 1; }
     while (true) {
         while (a_ret >= 0 && A.iref >= 0 && A.iref < iref - apos) a_ret = cur_next(A);
         if (a_ret < 0) break;
@@ -287,26 +385,7 @@ __global__ void k_mate_overlap(const raer_read_hdr* __restrict__ hdr, const uint
         run = min(run, min((int)ha.l_qseq - 1 - A.iseq, (int)hb.l_qseq - 1 - B.iseq));
         // (after a deletion catch-up the two cursors may sit on different positions: no run then)
         if (run < 0 || A.iref + apos != B.iref + bpos) run = 0;
-        for (int i = 0; i <= run; ++i) {
-            const int ia = A.iseq + i, ib = B.iseq + i;
-            const int qa = a_q[ia], qb = b_q[ib];
-            int na, nb;
-            if (seq_code(a_seq, ia) == seq_code(b_seq, ib)) {
-                int q = qa + qb;
-                if (q > 200) q = 200;
-                if (mode == 2) { na = q; nb = 0; }
-                else { na = amul * q; nb = bmul * q; }
-            } else if (mode == 2) {
-                if (qa >= qb) { na = (uint8_t)(0.8 * qa); nb = 0; }
-                else { nb = (uint8_t)(0.8 * qb); na = 0; }
-            } else {
-                if (qa > qb) { na = (uint8_t)(0.8 * qa); nb = 0; }
-                else if (qa < qb) { nb = (uint8_t)(0.8 * qb); na = 0; }
-                else { na = (uint8_t)(amul * 0.8 * qa); nb = (uint8_t)(bmul * 0.8 * qb); }
-            }
-            a_q[ia] = (uint8_t)na;
-            b_q[ib] = (uint8_t)nb;
-        }
+        overlap_run(a_q, b_q, a_seq, b_seq, A.iseq, B.iseq, run, amul, bmul, mode);
         A.iseq += run; A.icig += run; A.iref += run;
         B.iseq += run; B.icig += run; B.iref += run;
         iref += run;
