@@ -233,6 +233,23 @@ __device__ int cur_next(CigCur& c) {
     return -1;
 }
 
+// Same state as calling cur_next() until c.iref >= target (or the read ends), without visiting the bases of an
+// aligned block one by one: spliced mates make the literal loop step through whole reads.
+__device__ __forceinline__ int cur_skip_to(CigCur& c, int target, int ret) {
+    while (ret >= 0 && c.iref >= 0 && c.iref < target) {
+        if (c.k < c.n && c.icig >= 0) {
+            const uint32_t w = c.cig[c.k];
+            const int op = cg_op(w);
+            if (op == OP_M || op == OP_EQ || op == OP_X) {
+                const int st = min(cg_len(w) - 1 - c.icig, target - c.iref);
+                if (st > 0) { c.iseq += st; c.icig += st; c.iref += st; continue; }
+            }
+        }
+        ret = cur_next(c);
+    }
+    return ret;
+}
+
 // per byte: min(a + b, 200), the quality two agreeing mates share (htslib tweak_overlap_quality)
 __device__ __forceinline__ uint32_t qsum200(uint32_t a, uint32_t b) {
     const uint32_t e = __vminu2((a & 0x00ff00ffu) + (b & 0x00ff00ffu), 0x00c800c8u);
@@ -348,10 +365,10 @@ __global__ void k_mate_overlap(const raer_read_hdr* __restrict__ hdr, const uint
     int b_ret = cur_set(B, iref - bpos);
     if (b_ret < 0) return;
     while (true) {
-        while (a_ret >= 0 && A.iref >= 0 && A.iref < iref - apos) a_ret = cur_next(A);
+        a_ret = cur_skip_to(A, iref - apos, a_ret);
         if (a_ret < 0) break;
         if (iref < A.iref + apos) iref = A.iref + apos;
-        while (b_ret >= 0 && B.iref >= 0 && B.iref < iref - bpos) b_ret = cur_next(B);
+        b_ret = cur_skip_to(B, iref - bpos, b_ret);
         if (b_ret < 0) break;
         if (iref < B.iref + bpos) iref = B.iref + bpos;
         iref++;
