@@ -28,8 +28,10 @@
 
 #define FB_THREADS 512
 #define FSTAGE_WORDS (32 * FREC + 64)  // per warp: 32 read records, pair prefix sums, read ordinals
-#define FREC 11   // words per record (odd: lanes reading one field of different records spread over banks)
-enum { FR_POS = 0, FR_LEN, FR_SQ, FR_FLAGS, FR_QSQE, FR_FIRST, FR_RCP, FR_CIG0 };  // FR_CIG0..+3: CIGAR words, or [0] = offset if n > 4
+#define FREC 13   // words per record (odd: lanes reading one field of different records spread over banks)
+// FR_CIG0..+3: CIGAR words, or [0] = offset if n > 4. Second pass: FR_FIRST = f0 | f1 << 16, FR_B2 = f2 | c0 << 16,
+// FR_B3 = c1: first flagged rank and number of flagged sites of the first, second and remaining aligned blocks.
+enum { FR_POS = 0, FR_LEN, FR_SQ, FR_FLAGS, FR_QSQE, FR_FIRST, FR_RCP, FR_CIG0, FR_B2 = FR_CIG0 + 4, FR_B3 };
 #define STF_SIMPLE 0x400u  // one aligned block, nothing but clips around it: query q sits on pos + q - qs
 #define FWMAX 1024         // widest tile; the fixed part of the shared-memory layout is sized for it
 #define FRF_FILE_SHIFT 24
@@ -145,7 +147,7 @@ __device__ __forceinline__ void fast_item(const PlpParams& P, const FastSmem& S,
     const int q1 = min(q0 + 8, lq);
     const bool mapq_fail = (fl & STF_MAPQ_FAIL) != 0;
     const int s = fl & RAER_RB_INVERT;
-    const unsigned cbs = (unsigned)__cvta_generic_to_shared(S.cnt + (size_t)(((fl >> FRF_FILE_SHIFT) * 2 + s) * 4) * S.WS);
+    const unsigned cbs = (unsigned)__cvta_generic_to_shared(S.cnt + (size_t)((((fl >> FRF_FILE_SHIFT) & 0x3f) * 2 + s) * 4) * S.WS);
     const uint32_t rw = nib_swap(sw);
     const uint32_t NM = rw & (rw >> 1) & (rw >> 2) & (rw >> 3) & 0x11111111u;
     // nibble j: bit 0 = quality below the threshold, bit 1 = quality 0
@@ -290,54 +292,66 @@ __device__ __forceinline__ void fast_count_chunk(const PlpParams& P, const FastS
     __syncwarp();
 }
 
-// ---- second pass: one (read, flagged position) pair per lane
+// ---- second pass: one (read, flagged position) pair per lane. Called by all 32 lanes (active = this lane has a
+// pair); the lanes are re-joined after the position lookup and after the loads, so single-block reads and reads
+// that walk a CIGAR share the rest of the code.
 __device__ __forceinline__ void fast_pair(const PlpParams& P, const FastSmem& S, const FastCtx& X, const TileSmem& T2,
-                                          const uint32_t* rec, int rank, int ordinal) {
+                                          const uint32_t* rec, int rank, int ordinal, bool active) {
     const int pos = (int)rec[FR_POS];
     const int lq = (int)(rec[FR_LEN] & 0xffff), n = (int)(rec[FR_LEN] >> 16);
     const unsigned fl = rec[FR_FLAGS];
     const uint32_t sq = rec[FR_SQ];
-    const uint32_t* cig = n <= 4 ? rec + FR_CIG0 : P.cigar + rec[FR_CIG0];
-    const int pidx = (int)S.flag_pidx[rank];
-    const int p = X.t0 + pidx;
     const int qs = (int)(rec[FR_QSQE] & 0xffff), qe = (int)(rec[FR_QSQE] >> 16);
-    int q;
-    if (fl & STF_SIMPLE) {
-        q = qs + (p - pos);
-        if (q >= qe) return;
-    } else {
-        int x = pos, y = 0, k = 0, op = -1, len = 0;
-        for (; k < n; ++k) {
-            const uint32_t w = cig[k];
-            op = cg_op(w);
-            len = cg_len(w);
-            if ((0x18D >> op) & 1) {  // M D N = X
-                if (p < x + len) break;
-                x += len;
-                if ((0x181 >> op) & 1) y += len;
-            } else if ((0x12 >> op) & 1) {
-                y += len;
+    const int pidx = active ? (int)S.flag_pidx[rank] : 0;
+    const int p = X.t0 + pidx;
+    bool valid = active;
+    int q = 0;
+    if (valid) {
+        if (fl & STF_SIMPLE) {
+            q = qs + (p - pos);
+            valid = q < qe;
+        } else {
+            const uint32_t* cig = n <= 4 ? rec + FR_CIG0 : P.cigar + rec[FR_CIG0];
+            int x = pos, y = 0, k = 0, op = -1, len = 0;
+            for (; k < n; ++k) {
+                const uint32_t w = cig[k];
+                op = cg_op(w);
+                len = cg_len(w);
+                if ((0x18D >> op) & 1) {  // M D N = X
+                    if (p < x + len) break;
+                    x += len;
+                    if ((0x181 >> op) & 1) y += len;
+                } else if ((0x12 >> op) & 1) {
+                    y += len;
+                }
             }
+            // past the end of the read, or a deletion / ref-skip at p (filtered silently, src/plp.c:571)
+            valid = k < n && !((0xC >> op) & 1);
+            q = y + (p - x);
         }
-        if (k >= n) return;            // past the end of the read
-        if ((0xC >> op) & 1) return;   // deletion / ref-skip at p: filtered silently (src/plp.c:571)
-        q = y + (p - x);
+        valid = valid && q < lq;
     }
-    if (q >= lq) return;
-    const int code = seq_code(P.seq + sq, q);
-    if (code == 15) return;        // src/plp.c:718
-    const int bq = P.qual[2ull * sq + q];
-    if (bq < X.minbq) return;      // nX or dropped: not part of the statistics
-    const int a = pidx + 8;
-    const int rcode = (S.refn[a >> 3] >> ((a & 7) << 2)) & 15;
-    ReadCtx c;
-    c.l_qseq = lq;
-    c.qs = qs;
-    c.qe = qe;
-    c.rev = (fl >> 16) & 1;
-    c.invert = fl & RAER_RB_INVERT;
-    pass2_accumulate_core(P, T2, c, (int)((fl >> FRF_FILE_SHIFT) & 0x3f), c.invert ? 1 : 0, ordinal, rank - X.round0, q, code,
-                          (code == rcode) & (code != 0), rec[FR_RCP]);
+    __syncwarp();
+    int code = 15, bq = 0;
+    if (valid) {
+        code = seq_code(P.seq + sq, q);
+        bq = P.qual[2ull * sq + q];
+    }
+    // read base N (src/plp.c:718); nX or dropped bases are not part of the statistics
+    valid = valid && code != 15 && bq >= X.minbq;
+    __syncwarp();
+    if (valid) {
+        const int a = pidx + 8;
+        const int rcode = (S.refn[a >> 3] >> ((a & 7) << 2)) & 15;
+        ReadCtx c;
+        c.l_qseq = lq;
+        c.qs = qs;
+        c.qe = qe;
+        c.rev = (fl >> 16) & 1;
+        c.invert = fl & RAER_RB_INVERT;
+        pass2_accumulate_core(P, T2, c, (int)((fl >> FRF_FILE_SHIFT) & 0x3f), c.invert ? 1 : 0, ordinal, rank - X.round0, q, code,
+                              (code == rcode) & (code != 0), rec[FR_RCP]);
+    }
 }
 
 // One chunk of 32 listed reads, handled by one warp: stage the reads that cover a flagged site of this round,
@@ -355,24 +369,40 @@ __device__ __forceinline__ void fast_pair_chunk(const PlpParams& P, const FastSm
         const int4 a = __ldg(reinterpret_cast<const int4*>(P.hdr + r));
         // a read below the mapq threshold only produces nX: nothing to accumulate (src/plp.c:574)
         if (((a.z >> 16) & 0xff) >= P.min_mapq[f]) {
-            const int lo = min(max(a.x - X.t0, 0), X.tw), hi = min(max(a.y - X.t0, 0), X.tw);
-            const int first = max((int)S.fpre[lo], X.round0), last = min((int)S.fpre[hi], X.round0 + X.ns);
-            np = max(last - first, 0);
-            if (np > 0) {
-                const int4 b = __ldg(reinterpret_cast<const int4*>(P.hdr + r) + 1);
-                const int flag = a.z & 0xffff, bits = (a.z >> 24) & 0xff;
-                const int lq = a.w & 0xffff, n = (a.w >> 16) & 0xffff;
-                const uint32_t* cg = P.cigar + (unsigned)b.x;
+            const int4 b = __ldg(reinterpret_cast<const int4*>(P.hdr + r) + 1);
+            const int flag = a.z & 0xffff, bits = (a.z >> 24) & 0xff;
+            const int lq = a.w & 0xffff, n = (a.w >> 16) & 0xffff;
+            const uint32_t* cg = P.cigar + (unsigned)b.x;
+            const int r0 = X.round0, r1 = X.round0 + X.ns;
+            // Flagged sites are counted per aligned block (prefix counts, O(1) each): the first two blocks exactly,
+            // everything from the third block to the end of the read as one span. A spliced read does not pay for
+            // the flagged sites inside its introns.
+            int qs = 0, tail = 0, nblk = 0, other = 0, rl = 0, x = a.x;
+            int fb[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
+            bool lead = true;
+            for (int k = 0; k < n; ++k) {
+                const uint32_t w = __ldg(cg + k);
+                if (k < 4) rec[FR_CIG0 + k] = w;
+                const int op = cg_op(w), len = cg_len(w);
                 // query_start / query_end (src/plp_utils.c:52-104): soft clips at either end, hard clips skipped
-                int qs = 0, tail = 0, nblk = 0, other = 0, rl = 0;
-                bool lead = true;
-                for (int k = 0; k < n; ++k) {
-                    const uint32_t w = __ldg(cg + k);
-                    if (k < 4) rec[FR_CIG0 + k] = w;
-                    const int op = cg_op(w), len = cg_len(w);
-                    if (op == OP_S) { if (lead) qs += len; tail += len; }
-                    else if (op != OP_H) { lead = false; tail = 0; if ((0x181 >> op) & 1) { ++nblk; rl += len; } else other = 1; }
+                if (op == OP_S) { if (lead) qs += len; tail += len; }
+                else if (op != OP_H) { lead = false; tail = 0; if (!((0x181 >> op) & 1)) other = 1; }
+                if ((0x181 >> op) & 1) {
+                    if (nblk < 3) {
+                        const int lo = min(max(x - X.t0, 0), X.tw);
+                        const int hi = min(max((nblk < 2 ? x + len : a.y) - X.t0, 0), X.tw);
+                        fb[nblk] = max((int)S.fpre[lo], r0);
+                        cb[nblk] = max(min((int)S.fpre[hi], r1) - fb[nblk], 0);
+                    }
+                    ++nblk;
+                    rl += len;
+                    x += len;
+                } else if ((0xC >> op) & 1) {
+                    x += len;
                 }
+            }
+            np = cb[0] + cb[1] + cb[2];
+            if (np > 0) {
                 const int qe = lq - tail;
                 unsigned fl = (unsigned)bits | ((unsigned)((flag >> 4) & 1) << 16) | ((unsigned)f << FRF_FILE_SHIFT);
                 if (nblk == 1 && !other && qs + rl == qe) fl |= STF_SIMPLE;
@@ -382,7 +412,9 @@ __device__ __forceinline__ void fast_pair_chunk(const PlpParams& P, const FastSm
                 rec[FR_SQ] = (uint32_t)b.y;
                 rec[FR_FLAGS] = fl;
                 rec[FR_QSQE] = (uint32_t)qs | ((uint32_t)qe << 16);
-                rec[FR_FIRST] = (uint32_t)first;
+                rec[FR_FIRST] = (uint32_t)fb[0] | ((uint32_t)fb[1] << 16);
+                rec[FR_B2] = (uint32_t)fb[2] | ((uint32_t)cb[0] << 16);
+                rec[FR_B3] = (uint32_t)cb[1];
                 // get_relative_position divides by alen + 1 = qe - qs + 1 (src/plp_utils.c:401-412): reciprocal once per read
                 const int rb = qe - qs + 1;
                 rec[FR_RCP] = rb > 1 ? (uint32_t)((0x100000000ull + rb - 1) / rb) : 0u;
@@ -402,18 +434,20 @@ __device__ __forceinline__ void fast_pair_chunk(const PlpParams& P, const FastSm
     for (int itb = 0; itb < tot; itb += 32) {
         __syncwarp();
         const int it = itb + lane;
-        if (it < tot) {
-            int lo = 0, hh = 31;  // smallest i with pref[i] > it
+        int lo = 0, hh = 31;  // smallest i with pref[i] > it
 #pragma unroll
-            for (int step = 0; step < 5; ++step) {
-                const int mid = (lo + hh) >> 1;
-                if ((int)pref[mid] > it) hh = mid; else lo = mid + 1;
-            }
-            const int i = lo;
-            const int firstp = i ? (int)pref[i - 1] : 0;
-            const uint32_t* ri = st + i * FREC;
-            fast_pair(P, S, X, T2, ri, (int)ri[FR_FIRST] + (it - firstp), (int)pref[32 + i]);
+        for (int step = 0; step < 5; ++step) {
+            const int mid = (lo + hh) >> 1;
+            if ((int)pref[mid] > it) hh = mid; else lo = mid + 1;
         }
+        const int i = lo;
+        const int firstp = i ? (int)pref[i - 1] : 0;
+        const uint32_t* ri = st + i * FREC;
+        // pair j of the read -> flagged rank, through the per-block counts
+        const int j = it - firstp, c0 = (int)(ri[FR_B2] >> 16), c1 = (int)ri[FR_B3];
+        const int rank = j < c0 ? (int)(ri[FR_FIRST] & 0xffff) + j
+                                : (j < c0 + c1 ? (int)(ri[FR_FIRST] >> 16) + (j - c0) : (int)(ri[FR_B2] & 0xffff) + (j - c0 - c1));
+        fast_pair(P, S, X, T2, ri, rank, (int)pref[32 + i], it < tot);
     }
     __syncwarp();
 }
