@@ -276,7 +276,7 @@ def run_ours(args):
     launch_ms = k_ms.value / max(k_n.value, 1)
     achieved = alg_per_launch / (launch_ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
-    roofline = {"bound": "hbm", "kernel": "k_pileup_tiles", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_pileup_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_per_launch, "launch_ms": launch_ms,
                 "kernel_share_of_step": (k_ms.value / args.steps) / (ms / args.steps)}
@@ -301,16 +301,34 @@ def run_ours(args):
         torch.cuda.synchronize()
         d2h = [0]
 
+        pipe = L.raer_pipe_create(local)
+        if not pipe:
+            raise SystemExit(_cabi.last_error())
+
+        def collect():
+            rows = _cabi.Rows()
+            rc = L.raer_pipe_collect(pipe, C.byref(rows))
+            if rc != 0:
+                raise SystemExit(f"raer_pipe_collect failed ({rc}): {_cabi.last_error()}")
+            nb = rows.n_rows * (8 + 24 + n_bams * 36)
+            L.raer_rows_free(C.byref(rows))
+            return nb
+
         def step_host():
+            # two batches in flight: H2D of batch i + 1 overlaps the kernels of batch i and the rows of batch i - 1
             nbytes = 0
+            inflight = 0
             for H, hb in host:
-                rc = L.raer_ctx_set_reference(ctx, hb.tid, C.c_char_p(H["ref"].data_ptr()), H["ref"].numel())
-                rows = _cabi.Rows()
-                rc = rc or L.raer_batch_pileup_host(ctx, C.byref(conf), C.byref(hb), C.byref(rows))
+                if inflight == 2:
+                    nbytes += collect()
+                    inflight -= 1
+                rc = L.raer_pipe_submit(pipe, C.byref(conf), C.byref(hb), hb.tid, H["ref"].data_ptr(), H["ref"].numel())
                 if rc != 0:
-                    raise SystemExit(f"raer_batch_pileup_host failed ({rc}): {_cabi.last_error()}")
-                nbytes += rows.n_rows * (8 + 24 + n_bams * 36)
-                L.raer_rows_free(C.byref(rows))
+                    raise SystemExit(f"raer_pipe_submit failed ({rc}): {_cabi.last_error()}")
+                inflight += 1
+            while inflight:
+                nbytes += collect()
+                inflight -= 1
             d2h[0] = nbytes
 
         step_host()
@@ -326,7 +344,9 @@ def run_ours(args):
             dist.all_reduce(t_dt, op=dist.ReduceOp.MAX)
         e2e = {"value": float(bases_all.item()) / float(t_dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": float(t_dt.item()) * 1e3, "steps": n_e2e,
-               "api": "raer_batch_pileup_host (C-ABI, pinned host read batches -> rows in host memory)"}
+               "api": "raer_pipe_submit / raer_pipe_collect (C-ABI, pinned host read batches -> rows in host memory, "
+                      "two batches in flight)"}
+        L.raer_pipe_destroy(pipe)
         del host
 
     # ---- CPU baseline + file-level breakdown on a bounded BAM sample (rank 0, N=1 only)

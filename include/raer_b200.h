@@ -230,6 +230,16 @@ int raer_ctx_set_reference_device(raer_ctx* ctx, int32_t tid, const void* dseq, 
 /* e2e path: host batch -> H2D -> kernels -> D2H rows. */
 int raer_batch_pileup_host(raer_ctx* ctx, const raer_bulk_conf* conf, const raer_read_batch* host_batch,
                            raer_rows* out);
+/* Pipelined e2e path: two contexts used alternately so that the H2D copy of one batch overlaps the kernels of
+ * the previous one and the D2H of the one before. At most two batches in flight (submit returns RAER_ERR_LIMIT
+ * otherwise); batches complete in submission order; the host arrays of a batch and its reference bases (raw
+ * FASTA bytes of contig tid, host memory) must stay valid until its rows were collected. */
+typedef struct raer_pipe raer_pipe;
+raer_pipe* raer_pipe_create(int32_t device);
+void raer_pipe_destroy(raer_pipe* pipe);
+int raer_pipe_submit(raer_pipe* pipe, const raer_bulk_conf* conf, const raer_read_batch* host_batch, int32_t tid,
+                     const char* ref, int64_t ref_len);
+int raer_pipe_collect(raer_pipe* pipe, raer_rows* out);
 /* device-resident path (bench "value"): every pointer of dev_batch (except file_off) is device memory.
  * Runs the kernels on the context stream; rows stay on the device. *n_rows is read back at the end
  * unless NULL. Counts launched kernels into *launches when not NULL. */

@@ -189,6 +189,14 @@ def lib() -> C.CDLL:
         L.raer_batch_pileup_device.argtypes = [C.c_void_p, C.POINTER(BulkConf), C.POINTER(ReadBatch),
                                                C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.raer_batch_pileup_device.restype = C.c_int
+        L.raer_pipe_create.argtypes = [C.c_int32]
+        L.raer_pipe_create.restype = C.c_void_p
+        L.raer_pipe_destroy.argtypes = [C.c_void_p]
+        L.raer_pipe_destroy.restype = None
+        L.raer_pipe_submit.argtypes = [C.c_void_p, C.POINTER(BulkConf), C.POINTER(ReadBatch), C.c_int32, C.c_void_p, C.c_int64]
+        L.raer_pipe_submit.restype = C.c_int
+        L.raer_pipe_collect.argtypes = [C.c_void_p, C.POINTER(Rows)]
+        L.raer_pipe_collect.restype = C.c_int
         L.raer_rows_free.argtypes = [C.POINTER(Rows)]
         L.raer_batch_algorithmic_bytes.argtypes = [C.POINTER(ReadBatch), C.c_int64, C.c_int64]
         L.raer_batch_algorithmic_bytes.restype = C.c_int64

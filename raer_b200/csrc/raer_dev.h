@@ -22,6 +22,10 @@
 #define RAER_ALT_OAMBIG 0x10000000u // more than one distinct IUPAC key at the site: ALT shows the smallest code only
 #define RAER_SLOT_FS 8             // words per (file, strand) in a second-pass slot
 
+// internal device -> host conditions (never returned through the C ABI): the host re-runs the batch
+#define RAER_RETRY_DEEP (-100)     // k_pileup_fast met coverage > 65535: re-run with k_pileup_tiles
+#define RAER_RETRY_LISTCAP (-101)  // the tile read lists did not fit their allocation: re-run with the exact size
+
 struct PlpParams {
     // read batch (device pointers)
     const raer_read_hdr* hdr;
@@ -36,6 +40,7 @@ struct PlpParams {
     int2* tile_ranges;               // [n_tiles][n_files] {lo, hi}
     const int* tile_off;             // k_pileup_fast: [n_tiles * n_files + 1] offsets into tile_list
     const int* tile_list;            //   indices of the reads overlapping each (tile, file)
+    int tile_list_cap;               //   entries allocated (the lists are sized before their total is known)
     unsigned int* tile_counter;      // dynamic tile scheduler
     // reference of the contig
     const char* ref;

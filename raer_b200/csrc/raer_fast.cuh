@@ -551,6 +551,13 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
         }
         if (threadIdx.x == 0) { s_nflag = 0; s_deep = 0; s_chunk = 0; }
         __syncthreads();
+        if (P.tile_off[tile * F + F] > P.tile_list_cap) {  // lists overflowed their allocation: the host re-runs the batch
+            if (threadIdx.x == 0) {
+                atomicCAS(P.err_flag, 0, RAER_RETRY_LISTCAP);
+                P.tile_rows[tile] = make_int2(0, 0);
+            }
+            continue;
+        }
 
         // ---- phase 1: coverage events + exceptional bases
         {
@@ -592,7 +599,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
             }
         }
         __syncthreads();
-        if (s_deep) atomicExch(P.err_flag, RAER_ERR_LIMIT);  // 16-bit class counters cannot hold this tile
+        if (s_deep && threadIdx.x == 0) atomicCAS(P.err_flag, 0, RAER_RETRY_DEEP);  // 16-bit class counters cannot hold this tile
 
         // ---- phase 2: decide, reserve rows, write them in (pos, strand) order
         int my_rows = 0;

@@ -91,6 +91,12 @@ struct raer_ctx {
     long long row_cap = 0;
     float ms_h2d = 0, ms_kernel = 0, ms_d2h = 0;
     int64_t last_launches = 0;
+    // pipelined host path (raer_pipe_*): what is in flight on this context
+    bool pending = false;
+    raer_bulk_conf p_conf;
+    raer_read_batch p_dev;            // the batch as it sits in device memory
+    std::vector<int64_t> p_file_off;
+    const uint32_t* p_mask = nullptr;
     // optional per-launch timing of the dominant kernel (bench roofline)
     bool prof = false;
     std::vector<cudaEvent_t> pev;
@@ -168,8 +174,13 @@ static int choose_tile_width(int n_files) {
     return std::max(w, 32);
 }
 
+enum { RUN_FORCE_GENERIC = 1, RUN_SKIP_OVERLAP = 2 };
+
+// Enqueue the kernels of one batch on the context's stream. Nothing here waits for the device: conditions only
+// the device can see (tile lists larger than their allocation, coverage beyond the fast kernel's 16-bit counters)
+// come back through err_flag and finish_run() re-runs the batch accordingly.
 static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_batch* b, const uint32_t* d_mask,
-                      int64_t* launches) {
+                      int64_t* launches, int flags = 0, long long list_need = 0) {
     const int nf = b->n_files;
     PlpParams P;
     memset(&P, 0, sizeof(P));
@@ -183,7 +194,8 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
                            conf->splice_dist || conf->min_overhang || conf->indel_dist || conf->n_mm_type > 0 || conf->n_mm > 0);
     const char* kforce = getenv("RAER_KERNEL");
     const int fw = raer_fast_width(nf);
-    P.use_fast = only_bq && conf->min_bq <= 128 && fw > 0 && !(kforce && !strcmp(kforce, "generic"));
+    P.use_fast = only_bq && conf->min_bq <= 128 && fw > 0 && !(kforce && !strcmp(kforce, "generic")) &&
+                 !(flags & RUN_FORCE_GENERIC);
     P.W = P.use_fast ? fw : choose_tile_width(nf);
     if (P.use_fast && getenv("RAER_FAST_W")) P.W = std::max(32, std::min(fw, atoi(getenv("RAER_FAST_W")) & ~31));
     long long span = (long long)b->end - b->beg;
@@ -232,14 +244,15 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
         raer_tile_smem_bytes(nf, P.W, 0, &cw, &sw);
         P.S = std::max(32, cw / sw);
         if (P.S > 4096) P.S = 4096;
-        if (conf->remove_overlaps && b->n_pairs > 0) {
+        if (conf->remove_overlaps && b->n_pairs > 0 && !(flags & RUN_SKIP_OVERLAP)) {
             int r = raer_launch_overlap(b->hdr, b->cigar, b->seq, (uint8_t*)b->qual, b->pair_b, b->n_pairs,
                                         conf->remove_overlaps, c->stream);
             if (r < 0) { set_error("overlap kernel launch failed"); return RAER_ERR_CUDA; }
             nl += r;
         }
         if (P.use_fast) {
-            // per-tile read lists: count, scan, read the total back (sizes the list), fill
+            // per-tile read lists: count, scan, fill. The lists are sized from the read count (a read overlaps
+            // 1 + span / W tiles); if that guess is too small the device says so and the batch is re-run.
             const size_t ne = (size_t)P.n_tiles * nf + 1;
             if ((rc = c->tile_idx.ensure(ne * 3 * sizeof(int) + 16))) return rc;
             int* cnt = (int*)c->tile_idx.p;
@@ -247,18 +260,21 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
             int* cur = off + ne;
             int* d_total = (int*)((char*)c->small.p + 32);
             const long long n_reads = b->file_off[nf];
+            long long want = std::max(list_need, 2 * n_reads + (long long)ne + 1024);
+            if (want > INT_MAX) want = INT_MAX;
+            if ((rc = c->tile_list.ensure((size_t)want * sizeof(int)))) return rc;
+            int cap = (int)std::min<size_t>(c->tile_list.cap / sizeof(int), (size_t)INT_MAX);
+            // test hook: pretend the first guess was this small, so that the re-run path is exercised
+            if (list_need == 0 && getenv("RAER_TEST_LISTCAP")) cap = std::min(cap, std::max(1, atoi(getenv("RAER_TEST_LISTCAP"))));
             int r = raer_fast_index_count(&P, n_reads, cnt, off, cur, d_total, c->stream);
             if (r < 0) { set_error("tile index kernels failed"); return RAER_ERR_CUDA; }
             nl += r;
-            int total = 0;
-            CK(cudaMemcpyAsync(&total, d_total, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
-            if ((rc = c->tile_list.ensure((size_t)std::max(total, 1) * sizeof(int)))) return rc;
-            r = raer_fast_index_fill(&P, n_reads, off, cur, (int*)c->tile_list.p, total, c->stream);
+            r = raer_fast_index_fill(&P, n_reads, off, cur, (int*)c->tile_list.p, cap, c->stream);
             if (r < 0) { set_error("tile index kernels failed"); return RAER_ERR_CUDA; }
             nl += r;
             P.tile_off = off;
             P.tile_list = (const int*)c->tile_list.p;
+            P.tile_list_cap = cap;
         }
         int tl = 0;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -277,19 +293,47 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
     return RAER_OK;
 }
 
+struct SmallState { unsigned tc, pad; unsigned long long rows; int err; int pad2[3]; int list_total; };
+
+// Wait for the batch enqueued by run_device(), re-running it when the device asked for it. b must be the batch
+// in device memory (qualities already rewritten by the mate-overlap kernel: re-runs skip it).
+static int finish_run(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_batch* b, const uint32_t* d_mask,
+                      int64_t* launches, SmallState* out) {
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        SmallState s;
+        CK(cudaMemcpyAsync(&s, c->small.p, sizeof(s), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (s.err == RAER_RETRY_LISTCAP) {
+            int rc = run_device(c, conf, b, d_mask, launches, RUN_SKIP_OVERLAP, (long long)s.list_total + 16);
+            if (rc) return rc;
+            continue;
+        }
+        if (s.err == RAER_RETRY_DEEP) {
+            int rc = run_device(c, conf, b, d_mask, launches, RUN_SKIP_OVERLAP | RUN_FORCE_GENERIC);
+            if (rc) return rc;
+            continue;
+        }
+        if (s.err) {
+            set_error(s.err == RAER_ERR_MD ? "inconsistent MD tag with max_mismatch_type" : "device reported error %d", s.err);
+            return s.err;
+        }
+        *out = s;
+        return RAER_OK;
+    }
+    set_error("device kept asking for a re-run");
+    return RAER_ERR;
+}
+
 extern "C" int raer_batch_pileup_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_batch* b,
                                         int64_t* n_rows, int64_t* launches) {
     cudaSetDevice(c->device);
     if (conf->n_files != b->n_files || b->n_files > RAER_MAX_FILES) { set_error("bad file count"); return RAER_ERR_ARG; }
     int rc = run_device(c, conf, b, conf->site_mask, launches);
     if (rc) return rc;
-    if (n_rows) {
-        struct { unsigned tc, pad; unsigned long long rows; int err; } s;
-        CK(cudaMemcpyAsync(&s, c->small.p, sizeof(s), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        if (s.err) { set_error("device reported error %d", s.err); return s.err; }
-        *n_rows = (int64_t)s.rows;
-    }
+    SmallState s;
+    rc = finish_run(c, conf, b, conf->site_mask, launches, &s);
+    if (rc) return rc;
+    if (n_rows) *n_rows = (int64_t)s.rows;
     return RAER_OK;
 }
 
@@ -300,14 +344,7 @@ extern "C" void raer_rows_free(raer_rows* r) {
 }
 
 // download the rows of the last run in tile order (host-side ordered concatenation)
-static int fetch_rows(raer_ctx* c, int nf, raer_rows* out) {
-    struct { unsigned tc, pad; unsigned long long rows; int err; } s;
-    CK(cudaMemcpyAsync(&s, c->small.p, sizeof(s), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (s.err) {
-        set_error(s.err == RAER_ERR_MD ? "inconsistent MD tag with max_mismatch_type" : "device reported error %d", s.err);
-        return s.err;
-    }
+static int fetch_rows(raer_ctx* c, int nf, const SmallState& s, raer_rows* out) {
     memset(out, 0, sizeof(*out));
     out->n_files = nf;
     size_t n = (size_t)s.rows;
@@ -345,13 +382,10 @@ static int fetch_rows(raer_ctx* c, int nf, raer_rows* out) {
     return RAER_OK;
 }
 
-extern "C" int raer_batch_pileup_host(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_batch* hb, raer_rows* out) {
-    cudaSetDevice(c->device);
+// Host batch -> device buffers of the context and the kernels, all enqueued on the context's stream (no wait).
+// The host arrays must stay valid until host_collect() returned.
+static int host_submit(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_batch* hb) {
     const int nf = hb->n_files;
-    if (conf->n_files != nf || nf > RAER_MAX_FILES || nf < 1) { set_error("bad file count"); return RAER_ERR_ARG; }
-    memset(out, 0, sizeof(*out));
-    out->n_files = nf;
-    if (hb->n_reads == 0 || hb->end <= hb->beg) return RAER_OK;
     int rc;
     size_t nr = (size_t)hb->n_reads;
     if ((rc = c->hdr.ensure(nr * sizeof(raer_read_hdr)))) return rc;
@@ -377,22 +411,110 @@ extern "C" int raer_batch_pileup_host(raer_ctx* c, const raer_bulk_conf* conf, c
         d_mask = (const uint32_t*)c->mask.p;
     }
     cudaEventRecord(c->ev[1], c->stream);
-    raer_read_batch db = *hb;
-    db.hdr = (const raer_read_hdr*)c->hdr.p; db.maxend = (const int32_t*)c->maxend.p;
-    db.cigar = (const uint32_t*)c->cigar.p; db.seq = (const uint8_t*)c->seq.p; db.qual = (const uint8_t*)c->qual.p;
-    db.pair_b = (const int32_t*)c->pair_b.p;
+    c->p_conf = *conf;
+    c->p_dev = *hb;
+    c->p_file_off.assign(hb->file_off, hb->file_off + nf + 1);
+    c->p_dev.file_off = c->p_file_off.data();
+    c->p_dev.hdr = (const raer_read_hdr*)c->hdr.p; c->p_dev.maxend = (const int32_t*)c->maxend.p;
+    c->p_dev.cigar = (const uint32_t*)c->cigar.p; c->p_dev.seq = (const uint8_t*)c->seq.p; c->p_dev.qual = (const uint8_t*)c->qual.p;
+    c->p_dev.pair_b = (const int32_t*)c->pair_b.p;
+    c->p_mask = d_mask;
     int64_t nl = 0;
-    rc = run_device(c, conf, &db, d_mask, &nl);
+    rc = run_device(c, &c->p_conf, &c->p_dev, d_mask, &nl);
     if (rc) return rc;
     c->last_launches = nl;
     cudaEventRecord(c->ev[2], c->stream);
-    rc = fetch_rows(c, nf, out);
+    c->pending = true;
+    return RAER_OK;
+}
+
+static int host_collect(raer_ctx* c, raer_rows* out) {
+    c->pending = false;
+    SmallState st;
+    int64_t nl = 0;
+    int rc = finish_run(c, &c->p_conf, &c->p_dev, c->p_mask, &nl, &st);
+    c->last_launches += nl;
+    if (rc) return rc;
+    rc = fetch_rows(c, c->p_dev.n_files, st, out);
     cudaEventRecord(c->ev[3], c->stream);
     cudaEventSynchronize(c->ev[3]);
     cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&c->ms_kernel, c->ev[1], c->ev[2]);
     cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]);
     return rc;
+}
+
+extern "C" int raer_batch_pileup_host(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_batch* hb, raer_rows* out) {
+    cudaSetDevice(c->device);
+    const int nf = hb->n_files;
+    if (conf->n_files != nf || nf > RAER_MAX_FILES || nf < 1) { set_error("bad file count"); return RAER_ERR_ARG; }
+    memset(out, 0, sizeof(*out));
+    out->n_files = nf;
+    if (hb->n_reads == 0 || hb->end <= hb->beg) return RAER_OK;
+    int rc = host_submit(c, conf, hb);
+    if (rc) return rc;
+    return host_collect(c, out);
+}
+
+// ------------------------------------------------------------------------------------- pipelined host path
+// Two contexts (own stream, own device buffers) used alternately: the H2D copy of batch i + 1 runs while the
+// kernels of batch i execute and the rows of batch i - 1 travel back. Batches complete in submission order.
+struct raer_pipe {
+    raer_ctx* c[2] = {nullptr, nullptr};
+    int64_t submitted = 0, collected = 0;
+    bool empty[2] = {false, false};  // the slot holds a batch with no reads (nothing was enqueued)
+    int nf[2] = {0, 0};
+};
+
+extern "C" raer_pipe* raer_pipe_create(int32_t device) {
+    raer_pipe* p = new raer_pipe();
+    for (int i = 0; i < 2; ++i) {
+        p->c[i] = raer_ctx_create(device);
+        if (!p->c[i]) { if (i) raer_ctx_destroy(p->c[0]); delete p; return nullptr; }
+    }
+    return p;
+}
+extern "C" void raer_pipe_destroy(raer_pipe* p) {
+    if (!p) return;
+    for (int i = 0; i < 2; ++i) raer_ctx_destroy(p->c[i]);
+    delete p;
+}
+// Enqueue one host batch together with the reference bases of its contig (raw FASTA bytes, host memory). At most
+// two batches may be in flight: returns RAER_ERR_LIMIT if raer_pipe_collect() has to be called first.
+extern "C" int raer_pipe_submit(raer_pipe* p, const raer_bulk_conf* conf, const raer_read_batch* hb, int32_t tid,
+                                const char* ref, int64_t ref_len) {
+    if (p->submitted - p->collected >= 2) { set_error("two batches already in flight"); return RAER_ERR_LIMIT; }
+    const int k = (int)(p->submitted & 1);
+    raer_ctx* c = p->c[k];
+    cudaSetDevice(c->device);
+    const int nf = hb->n_files;
+    if (conf->n_files != nf || nf > RAER_MAX_FILES || nf < 1) { set_error("bad file count"); return RAER_ERR_ARG; }
+    p->nf[k] = nf;
+    p->empty[k] = hb->n_reads == 0 || hb->end <= hb->beg;
+    if (!p->empty[k]) {
+        int rc;
+        if (ref_len > 0) {
+            if ((rc = c->ref.ensure((size_t)ref_len))) return rc;
+            CK(cudaMemcpyAsync(c->ref.p, ref, (size_t)ref_len, cudaMemcpyHostToDevice, c->stream));
+        }
+        c->ref_ptr = ref_len > 0 ? (const char*)c->ref.p : nullptr;
+        c->ref_len = ref_len;
+        c->ref_tid = tid;
+        if ((rc = host_submit(c, conf, hb))) return rc;
+    }
+    ++p->submitted;
+    return RAER_OK;
+}
+// Rows of the oldest batch in flight.
+extern "C" int raer_pipe_collect(raer_pipe* p, raer_rows* out) {
+    if (p->submitted == p->collected) { set_error("no batch in flight"); return RAER_ERR_ARG; }
+    const int k = (int)(p->collected & 1);
+    ++p->collected;
+    memset(out, 0, sizeof(*out));
+    out->n_files = p->nf[k];
+    if (p->empty[k]) return RAER_OK;
+    cudaSetDevice(p->c[k]->device);
+    return host_collect(p->c[k], out);
 }
 
 extern "C" void raer_ctx_last_timing(raer_ctx* c, double* h2d_s, double* kernel_s, double* d2h_s) {

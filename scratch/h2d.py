@@ -1,0 +1,18 @@
+import torch, time
+n = 1 << 30
+h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+d = torch.empty(n, dtype=torch.uint8, device="cuda")
+for _ in range(2): d.copy_(h, non_blocking=True)
+torch.cuda.synchronize()
+t = time.perf_counter()
+for _ in range(5): d.copy_(h, non_blocking=True)
+torch.cuda.synchronize()
+dt = (time.perf_counter() - t) / 5
+print("H2D pinned GB/s", n / dt / 1e9)
+t = time.perf_counter()
+for _ in range(5): h.copy_(d, non_blocking=True)
+torch.cuda.synchronize()
+dt = (time.perf_counter() - t) / 5
+print("D2H pinned GB/s", n / dt / 1e9)
+import subprocess
+print(subprocess.run("nvidia-smi --query-gpu=pcie.link.gen.current,pcie.link.width.current,pcie.link.gen.max --format=csv; nproc; free -g | head -2", shell=True, capture_output=True, text=True).stdout)
