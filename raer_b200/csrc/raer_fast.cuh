@@ -139,6 +139,11 @@ __device__ __forceinline__ void fast_block_count(const FastSmem& S, const FastCt
     }
 }
 
+__device__ __noinline__ void fast_block_count_call(const FastSmem& S, const FastCtx& X, unsigned cbs, uint32_t rw, uint32_t NM,
+                                                   uint32_t LT, uint32_t Z, bool mapq_fail, int cxor, int rel, int jlo, int jhi) {
+    fast_block_count(S, X, cbs, rw, NM, LT, Z, mapq_fail, cxor, rel, jlo, jhi);
+}
+
 __device__ __forceinline__ void fast_item(const PlpParams& P, const FastSmem& S, const FastCtx& X, const uint32_t* rec, int q0,
                                           uint32_t sw, uint2 qw) {
     const int pos = (int)rec[FR_POS];
@@ -154,28 +159,48 @@ __device__ __forceinline__ void fast_item(const PlpParams& P, const FastSmem& S,
     const uint32_t Q = bytes_to_nibbles((byte_lt(qw.x, X.mb4) >> 7) | (byte_zero(qw.x) >> 6),
                                         (byte_lt(qw.y, X.mb4) >> 7) | (byte_zero(qw.y) >> 6));
     const uint32_t LT = Q & 0x11111111u, Z = (Q >> 1) & 0x11111111u & X.zall;
-    if (fl & STF_SIMPLE) {  // the aligned block is query [qs, qe)
-        const int qs = (int)(rec[FR_QSQE] & 0xffff), qe = (int)(rec[FR_QSQE] >> 16);
-        if (qe > q0 && qs < q1)
-            fast_block_count(S, X, cbs, rw, NM, LT, Z, mapq_fail, s ? 3 : 0, pos + (q0 - qs) - X.t0, qs - q0, min(qe, q1) - q0);
-        return;
-    }
     const uint32_t* cig = n <= 4 ? rec + FR_CIG0 : P.cigar + rec[FR_CIG0];
-    int x = pos, y = 0;
-    for (int k = 0; k < n && y < q1; ++k) {
-        const uint32_t w = cig[k];
-        const int op = cg_op(w), len = cg_len(w);
-        if ((0x181 >> op) & 1) {  // M = X
-            if (y + len > q0)
-                fast_block_count(S, X, cbs, rw, NM, LT, Z, mapq_fail, s ? 3 : 0, x + (q0 - y) - X.t0, y - q0,
-                                 min(y + len, q1) - q0);
-            x += len;
-            y += len;
-        } else if ((0xC >> op) & 1) {  // D N
-            x += len;
-        } else if ((0x12 >> op) & 1) {  // I S
-            y += len;
+    const bool simple = (fl & STF_SIMPLE) != 0;
+    int x = pos, y = 0, k = 0;
+    bool has = false;
+    int rel = 0, jlo = 0, jhi = 0;
+    // next aligned block that intersects the item (reads that walk their CIGAR)
+    auto next_block = [&]() {
+        has = false;
+        while (k < n && y < q1 && !has) {
+            const uint32_t w = cig[k++];
+            const int op = cg_op(w), len = cg_len(w);
+            if ((0x181 >> op) & 1) {  // M = X
+                if (y + len > q0) {
+                    has = true;
+                    rel = x + (q0 - y) - X.t0;
+                    jlo = y - q0;
+                    jhi = min(y + len, q1) - q0;
+                }
+                x += len;
+                y += len;
+            } else if ((0xC >> op) & 1) {  // D N
+                x += len;
+            } else if ((0x12 >> op) & 1) {  // I S
+                y += len;
+            }
         }
+    };
+    if (simple) {  // the aligned block is query [qs, qe)
+        const int qs = (int)(rec[FR_QSQE] & 0xffff), qe = (int)(rec[FR_QSQE] >> 16);
+        has = qe > q0 && qs < q1;
+        rel = pos + (q0 - qs) - X.t0;
+        jlo = qs - q0;
+        jhi = min(qe, q1) - q0;
+    } else {
+        next_block();
+    }
+    // one inlined copy of the block code for every kind of read ...
+    if (has) fast_block_count(S, X, cbs, rw, NM, LT, Z, mapq_fail, s ? 3 : 0, rel, jlo, jhi);
+    // ... and a call for the rare item that straddles two aligned blocks
+    while (!simple && has && k < n && y < q1) {
+        next_block();
+        if (has) fast_block_count_call(S, X, cbs, rw, NM, LT, Z, mapq_fail, s ? 3 : 0, rel, jlo, jhi);
     }
 }
 
@@ -284,9 +309,12 @@ __device__ __forceinline__ void fast_count_chunk(const PlpParams& P, const FastS
                 swB = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qB >> 1)));
                 qwB = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qB));
             }
-            if (okA) fast_item(P, S, X, recA, qA, swA, qwA);
-            __syncwarp();
-            if (okB) fast_item(P, S, X, recB, qB, swB, qwB);
+            // both loads are in flight; one copy of the item code handles them in turn
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                if (h) __syncwarp();
+                if (h ? okB : okA) fast_item(P, S, X, h ? recB : recA, h ? qB : qA, h ? swB : swA, h ? qwB : qwA);
+            }
         }
     }
     __syncwarp();
