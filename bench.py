@@ -9,7 +9,7 @@ reads on a 100 Mb reference, fr-first-strand, only_keep_variants" (SURVEY.md 8d:
   value  : input resident in HBM (synthetic batches generated on the GPU), kernels only.
   e2e    : the same batches in pinned HOST memory handed to the C-ABI (raer_batch_pileup_host):
            H2D of reads + reference, kernels, D2H of the result rows, host-side ordered concatenation.
-  roofline : k_pileup_tiles, algorithmic bytes (SURVEY.md 8d constants) / CUDA-event launch time.
+  roofline : the tile kernel (k_pileup_fast for this configuration), algorithmic bytes (SURVEY.md 8d constants) / CUDA-event launch time.
   cpu_baseline : the CPU oracle (port of the reference algorithm) on a bounded BAM sample, 1 core.
 N>1: weak scaling, every rank runs its own copy of the workload (own seeds, as if other samples);
 no collective on the data path, barrier + max-over-ranks timing only.
@@ -269,7 +269,7 @@ def run_ours(args):
         dist.all_reduce(bases_all)
     value = float(bases_all.item()) / (ms_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (k_pileup_tiles), per launch
+    # ---- roofline of the dominant kernel (the tile kernel), per launch
     rows_per_launch = rows_total[0] / max(len(batches), 1)
     alg = [L.raer_batch_algorithmic_bytes(C.byref(rb), int(rows_per_launch), contig_len) for _, rb in batches]
     alg_per_launch = sum(alg) / len(alg)
