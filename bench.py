@@ -276,8 +276,16 @@ def run_ours(args):
     launch_ms = k_ms.value / max(k_n.value, 1)
     achieved = alg_per_launch / (launch_ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per launch from the committed ncu --set full capture of this kernel (not measured live)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_k_pileup_fast.json")))
+        traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
+        traffic_src = tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "k_pileup_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_per_launch, "launch_ms": launch_ms,
                 "kernel_share_of_step": (k_ms.value / args.steps) / (ms / args.steps)}
 
