@@ -219,6 +219,7 @@ __device__ __forceinline__ int fast_stage(const PlpParams& P, const FastSmem& S,
     uint32_t* dl = S.cnt + (size_t)((f * 2 + s) * 4) * S.WS;
     int x = a.x, y = 0;
     int qs = 0, tail = 0, nblk = 0, other = 0;
+    int qlo = 0x7fffffff, qhi = 0;  // query bases whose positions fall inside the tile
     bool lead = true;
     for (int k = 0; k < n; ++k) {
         const uint32_t w = __ldg(cg + k);
@@ -237,6 +238,8 @@ __device__ __forceinline__ int fast_stage(const PlpParams& P, const FastSmem& S,
             if (lo < h2) {
                 red_add(dl + (lo - X.t0), 1u);
                 red_add(dl + (h2 - X.t0), 0xffffffffu);
+                qlo = min(qlo, y + (lo - x));
+                qhi = max(qhi, y + (h2 - x));
             }
             x += len;
             y += len;
@@ -253,7 +256,11 @@ __device__ __forceinline__ int fast_stage(const PlpParams& P, const FastSmem& S,
     rec[FR_SQ] = (uint32_t)b.y;
     rec[FR_FLAGS] = fl;
     rec[FR_QSQE] = (uint32_t)qs | ((uint32_t)(lq - tail) << 16);
-    return (lq + 7) >> 3;
+    // items (8 query bases each) that can touch the tile: a read that overlaps two tiles, or a spliced read that
+    // only passes through, does not fetch the rest of its bases here
+    const int ilo = qlo >> 3;
+    rec[FR_FIRST] = (uint32_t)ilo;
+    return qhi > qlo ? ((qhi - 1) >> 3) - ilo + 1 : 0;
 }
 
 // Phase 1 for one chunk of 32 listed reads, handled by one warp on its own (no CTA barrier): stage the records,
@@ -270,51 +277,58 @@ __device__ __forceinline__ void fast_count_chunk(const PlpParams& P, const FastS
         const int r = __ldg(P.tile_list + li);
         nq = need_cov ? fast_stage<true>(P, S, X, r, f, t1, rec) : fast_stage<false>(P, S, X, r, f, t1, rec);
     }
-    const int NI = __reduce_max_sync(FULL, nq);  // item slots per record of this chunk
+    // items of the chunk in read order: inclusive prefix of the per-read item counts
+    uint32_t* pref = st + 32 * FREC;
+    int inc = nq;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += v;
+    }
+    pref[lane] = (uint32_t)inc;
+    const int tot = __shfl_sync(FULL, inc, 31);
     __syncwarp();
-    if (NI > 0) {
-        const int tot = min(32, l1 - li0) * NI;
-        const uint32_t M32 = (uint32_t)((0x100000000ull + NI - 1) / NI);  // it / NI == umulhi(it, M32) while it * NI < 2^32
-        const bool mul_ok = NI > 1 && (unsigned long long)tot * NI < 0x100000000ull;
-        for (int itb = 0; itb < tot; itb += 64) {
-            // The trip count is warp-uniform, so the warp can be re-joined here: without it the lanes that took
-            // different paths through the previous items keep running as separate sub-warps.
-            __syncwarp();
-            const uint32_t* recA = st;
-            const uint32_t* recB = st;
-            int qA = 0, qB = 0;
-            uint32_t swA = 0, swB = 0;
-            uint2 qwA = make_uint2(0, 0), qwB = make_uint2(0, 0);
-            const int itA = itb + lane, itB = itA + 32;
-            bool okA = itA < tot, okB = itB < tot;
-            if (okA) {
-                const int i = mul_ok ? (int)__umulhi((uint32_t)itA, M32) : itA / NI;
-                recA = st + i * FREC;
-                qA = (itA - i * NI) << 3;
-                okA = qA < (int)(recA[FR_LEN] & 0xffff);
+    for (int itb = 0; itb < tot; itb += 64) {
+        // The trip count is warp-uniform, so the warp can be re-joined here: without it the lanes that took
+        // different paths through the previous items keep running as separate sub-warps.
+        __syncwarp();
+        const uint32_t* recA = st;
+        const uint32_t* recB = st;
+        int qA = 0, qB = 0;
+        uint32_t swA = 0, swB = 0;
+        uint2 qwA = make_uint2(0, 0), qwB = make_uint2(0, 0);
+        const int itA = itb + lane, itB = itA + 32;
+        const bool okA = itA < tot, okB = itB < tot;
+        if (okA) {
+            int lo = 0, hh = 31;  // smallest i with pref[i] > it
+#pragma unroll
+            for (int step = 0; step < 5; ++step) {
+                const int mid = (lo + hh) >> 1;
+                if ((int)pref[mid] > itA) hh = mid; else lo = mid + 1;
             }
-            if (okA) {
-                const uint32_t sq = recA[FR_SQ];
-                swA = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qA >> 1)));
-                qwA = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qA));
+            recA = st + lo * FREC;
+            qA = ((int)recA[FR_FIRST] + itA - (lo ? (int)pref[lo - 1] : 0)) << 3;
+            const uint32_t sq = recA[FR_SQ];
+            swA = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qA >> 1)));
+            qwA = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qA));
+        }
+        if (okB) {
+            int lo = 0, hh = 31;
+#pragma unroll
+            for (int step = 0; step < 5; ++step) {
+                const int mid = (lo + hh) >> 1;
+                if ((int)pref[mid] > itB) hh = mid; else lo = mid + 1;
             }
-            if (okB) {
-                const int i = mul_ok ? (int)__umulhi((uint32_t)itB, M32) : itB / NI;
-                recB = st + i * FREC;
-                qB = (itB - i * NI) << 3;
-                okB = qB < (int)(recB[FR_LEN] & 0xffff);
-            }
-            if (okB) {
-                const uint32_t sq = recB[FR_SQ];
-                swB = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qB >> 1)));
-                qwB = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qB));
-            }
-            // both loads are in flight; one copy of the item code handles them in turn
+            recB = st + lo * FREC;
+            qB = ((int)recB[FR_FIRST] + itB - (lo ? (int)pref[lo - 1] : 0)) << 3;
+            const uint32_t sq = recB[FR_SQ];
+            swB = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qB >> 1)));
+            qwB = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qB));
+        }
+        // both loads are in flight; one copy of the item code handles them in turn
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                if (h) __syncwarp();
-                if (h ? okB : okA) fast_item(P, S, X, h ? recB : recA, h ? qB : qA, h ? swB : swA, h ? qwB : qwA);
-            }
+        for (int h = 0; h < 2; ++h) {
+            if (h) __syncwarp();
+            if (h ? okB : okA) fast_item(P, S, X, h ? recB : recA, h ? qB : qA, h ? swB : swA, h ? qwB : qwA);
         }
     }
     __syncwarp();

@@ -755,8 +755,17 @@ bool Ingest::next_batch(PackedBatch& out) {
     while (true) {
         boundary = INT_MAX;
         bool all_done = true;
+        // The files are independent until the window boundary is taken: parse them side by side (the UMI
+        // dictionary of the single-cell path is shared, that path stays serial).
+        if (nf > 1 && !conf_.sc) {
+            std::vector<std::thread> th;
+            th.reserve(nf);
+            for (int i = 0; i < nf; ++i) th.emplace_back([this, i, want]() { parse_ahead(i, want); });
+            for (auto& t : th) t.join();
+        } else {
+            for (int i = 0; i < nf; ++i) parse_ahead(i, want);
+        }
         for (int i = 0; i < nf; ++i) {
-            parse_ahead(i, want);
             FilePending& F = *files_[i];
             bool done = !F.have_look || F.look_tid != cur_tid_;
             if (!done) {

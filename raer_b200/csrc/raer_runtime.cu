@@ -683,11 +683,16 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
         if (v > 0) ic.target_reads = v;
     }
 
+    double tm_open = raer::now_seconds();
     raer::Ingest ing(ic);
     if (!ing.open(a->bampaths, a->indexes, a->host_threads, a->region)) return RAER_ERR_IO;
+    tm_open = raer::now_seconds() - tm_open;
 
+    double tm_ctx = raer::now_seconds();
     raer_ctx* ctx = raer_ctx_create(a->device);
     if (!ctx) return RAER_ERR_NO_DEVICE;
+    tm_ctx = raer::now_seconds() - tm_ctx;
+    double tm_fasta = 0, tm_batch = 0, tm_gpu = 0, tm_sink = 0;
 
     raer_bulk_conf bc;
     memset(&bc, 0, sizeof(bc));
@@ -718,14 +723,20 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
         bool mine = a->shard_count <= 1 || (contig_no % a->shard_count) == a->shard_index;
         ++contig_no;
         std::string seq;
+        double t0f = raer::now_seconds();
         bool have_ref = raer::fasta_fetch(a->fapath, names[tid], seq);
         if (!have_ref) seq.clear();  // reference: every site reads as 'N' and is skipped
         if (mine) {
             rc = raer_ctx_set_reference(ctx, tid, seq.data(), (int64_t)seq.size());
             if (rc) break;
         }
+        tm_fasta += raer::now_seconds() - t0f;
         const raer::RegionIndex::Chr* rchr = has_ridx ? ridx.find(names[tid]) : nullptr;
-        while (rc == RAER_OK && ing.next_batch(pb)) {
+        while (rc == RAER_OK) {
+            double t0b = raer::now_seconds();
+            const bool got = ing.next_batch(pb);
+            tm_batch += raer::now_seconds() - t0b;
+            if (!got) break;
             if (!mine || pb.b.n_reads == 0 || pb.b.end <= pb.b.beg) continue;
             if (has_ridx && !rchr) continue;
             bc.reg_beg = ing.reg_tid() >= 0 ? ing.reg_beg() : 0;
@@ -745,8 +756,11 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
                 bc.mask_bits = we - wb;
             }
             raer_rows rows;
+            double t0g = raer::now_seconds();
             rc = raer_batch_pileup_host(ctx, &bc, &pb.b, &rows);
+            tm_gpu += raer::now_seconds() - t0g;
             if (rc) break;
+            double t0s = raer::now_seconds();
             out->gpu_launches += ctx->last_launches;
             out->t_h2d += ctx->ms_h2d * 1e-3; out->t_kernel += ctx->ms_kernel * 1e-3; out->t_d2h += ctx->ms_d2h * 1e-3;
             sink_reserve(sink, out->nrows + rows.n_rows);
@@ -768,6 +782,7 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             }
             out->nrows += rows.n_rows;
             raer_rows_free(&rows);
+            tm_sink += raer::now_seconds() - t0s;
         }
     }
     // compact the [file][row] stride to nrows
@@ -783,6 +798,11 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
     out->n_aligned_bases = ing.aligned_bases();
     raer_ctx_destroy(ctx);
     out->t_total = raer::now_seconds() - t_start;
+    if (getenv("RAER_TIMING"))
+        fprintf(stderr, "[raer_pileup] total %.3f s: open %.3f ctx %.3f fasta+ref %.3f next_batch %.3f (decode %.3f pack %.3f) "
+                        "gpu call %.3f (h2d %.3f kernel %.3f d2h %.3f) rows->columns %.3f\n",
+                out->t_total, tm_open, tm_ctx, tm_fasta, tm_batch, out->t_decode, out->t_pack, tm_gpu, out->t_h2d, out->t_kernel,
+                out->t_d2h, tm_sink);
     if (rc != RAER_OK) {
         raer_pileup_result_free(out);
         return rc;
