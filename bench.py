@@ -214,6 +214,8 @@ def run_ours(args):
     conf.report_multiallelic, conf.remove_overlaps, conf.want_stats = 1, 1, 1
     if os.environ.get("RAER_BENCH_NO_STATS"):  # development probe: skip the second pass (not the reference behaviour)
         conf.want_stats = 0
+    if os.environ.get("RAER_BENCH_EXT_FILTERS"):  # development probe: a typical RNA-editing FilterParam (not the C2 call)
+        conf.trim_5p, conf.trim_3p, conf.splice_dist, conf.indel_dist, conf.min_overhang = 5, 5, 4, 4, 10
     if os.environ.get("RAER_BENCH_NO_OVERLAP"):  # development probe: skip the mate-overlap kernel
         conf.remove_overlaps = 0
     for f in range(n_bams):

@@ -1,6 +1,10 @@
-// raer_fast.cuh -- k_pileup_fast: the tile kernel for the common configuration (only the mapq and
-// base-quality filters of check_read_filters are active, src/plp.c:568-586). Included from
-// raer_kernels.cu; every other configuration runs k_pileup_tiles.
+// raer_fast.cuh -- k_pileup_fast: the tile kernel for every configuration without the mismatch filter
+// (max_mismatch_type). k_pileup_fast<false>: only the mapq and base-quality filters of check_read_filters are
+// active (src/plp.c:568-586, the default FilterParam). k_pileup_fast<true>: also the trim, splice-distance,
+// splice-overhang and indel-distance filters (:588-612), which all turn a base into nX and depend on nothing
+// but the read and the query offset: trims are two bounds per read, the distance filters are evaluated per base
+// only for reads that have a ref-skip / insertion / deletion. Included from raer_kernels.cu; the mismatch
+// filter and base-quality thresholds above 128 run k_pileup_tiles.
 //
 // The reference touches a counter for every aligned base. Here a base that equals the reference and
 // passes the quality filter touches nothing:
@@ -33,6 +37,7 @@
 // FR_B3 = c1: first flagged rank and number of flagged sites of the first, second and remaining aligned blocks.
 enum { FR_POS = 0, FR_LEN, FR_SQ, FR_FLAGS, FR_QSQE, FR_FIRST, FR_RCP, FR_CIG0, FR_B2 = FR_CIG0 + 4, FR_B3 };
 #define STF_SIMPLE 0x400u  // one aligned block, nothing but clips around it: query q sits on pos + q - qs
+#define STF_SLOWFILT 0x800u  // EXT: the read has a ref-skip / indel (or the overhang over-read): distance filters per base
 #define FWMAX 1024         // widest tile; the fixed part of the shared-memory layout is sized for it
 #define FRF_FILE_SHIFT 24
 #define FWS(W) ((W) + 8)  // words per counter array: W positions + the -1 event one past the end
@@ -144,6 +149,30 @@ __device__ __noinline__ void fast_block_count_call(const FastSmem& S, const Fast
     fast_block_count(S, X, cbs, rw, NM, LT, Z, mapq_fail, cxor, rel, jlo, jhi);
 }
 
+// EXT: nibble-bit mask of the item's bases that the read-geometry filters turn into nX (check_read_filters after the
+// base-quality test, src/plp.c:588-612)
+__device__ __forceinline__ uint32_t fast_filter_mask(const PlpParams& P, const uint32_t* rec, int q0, int q1) {
+    // trims: nX iff q < qL or q >= qR (bounds staged per read)
+    const int qL = (int)(rec[FR_RCP] & 0xffff), qR = (int)(rec[FR_RCP] >> 16);
+    const int nl = min(max(qL - q0, 0), 8), nr = min(max(qR - q0, 0), 8);
+    uint32_t tx = (nl ? (0x11111111u >> ((8 - nl) << 2)) : 0u) | (nr < 8 ? (0x11111111u << (nr << 2)) : 0u);
+    const unsigned fl = rec[FR_FLAGS];
+    if (fl & STF_SLOWFILT) {
+        ReadCtx c;
+        c.n_cigar = (int)(rec[FR_LEN] >> 16);
+        c.cig = c.n_cigar <= 4 ? rec + FR_CIG0 : P.cigar + rec[FR_CIG0];
+        c.bits = (int)(fl & 0xff);
+        for (int q = q0; q < q1; ++q) {
+            bool hit = P.splice_dist && d_dist_to_splice(c, q, P.splice_dist) >= 0;
+            if (!hit && P.min_overhang) hit = d_check_splice_overhang(c, q, P.min_overhang) > 0;
+            if (!hit && P.indel_dist) hit = d_dist_to_indel(c, q, P.indel_dist) >= 0;
+            if (hit) tx |= 1u << ((q - q0) << 2);
+        }
+    }
+    return tx;
+}
+
+template <bool EXT>
 __device__ __forceinline__ void fast_item(const PlpParams& P, const FastSmem& S, const FastCtx& X, const uint32_t* rec, int q0,
                                           uint32_t sw, uint2 qw) {
     const int pos = (int)rec[FR_POS];
@@ -158,7 +187,11 @@ __device__ __forceinline__ void fast_item(const PlpParams& P, const FastSmem& S,
     // nibble j: bit 0 = quality below the threshold, bit 1 = quality 0
     const uint32_t Q = bytes_to_nibbles((byte_lt(qw.x, X.mb4) >> 7) | (byte_zero(qw.x) >> 6),
                                         (byte_lt(qw.y, X.mb4) >> 7) | (byte_zero(qw.y) >> 6));
-    const uint32_t LT = Q & 0x11111111u, Z = (Q >> 1) & 0x11111111u & X.zall;
+    uint32_t LT = Q & 0x11111111u;
+    const uint32_t Z = (Q >> 1) & 0x11111111u & X.zall;
+    // a base that fails a later filter is nX exactly like one below the quality threshold (and quality 0 below the
+    // threshold has been dropped before those filters are consulted): same mask from here on
+    if (EXT) LT |= fast_filter_mask(P, rec, q0, q1) & ~Z;
     const uint32_t* cig = n <= 4 ? rec + FR_CIG0 : P.cigar + rec[FR_CIG0];
     const bool simple = (fl & STF_SIMPLE) != 0;
     int x = pos, y = 0, k = 0;
@@ -205,7 +238,7 @@ __device__ __forceinline__ void fast_item(const PlpParams& P, const FastSmem& S,
 }
 
 // Phase 1: stage one read record (thread per read) and write the read's coverage events.
-template <bool NEEDCOV>
+template <bool NEEDCOV, bool EXT>
 __device__ __forceinline__ int fast_stage(const PlpParams& P, const FastSmem& S, const FastCtx& X, int r, int f, int t1,
                                           uint32_t* rec) {
     const int4 a = __ldg(reinterpret_cast<const int4*>(P.hdr + r));
@@ -250,6 +283,26 @@ __device__ __forceinline__ int fast_stage(const PlpParams& P, const FastSmem& S,
         }
     }
     if (nblk == 1 && !other && qs + (x - a.x) == lq - tail) fl |= STF_SIMPLE;
+    if (EXT) {
+        // check_variant_fpos / check_variant_pos (src/plp_utils.c:137-193): nX iff q < qL or q >= qR
+        const int qe = lq - tail, rev = (flag >> 4) & 1;
+        int qL = 0, qR = 65535;
+        if (P.ftrim_5p > 0 || P.ftrim_3p > 0) {
+            const int ql = qe - qs;
+            if (ql <= 0) qL = 65535;
+            const int d5 = (int)floor(P.ftrim_5p * ql), d3 = (int)ceil(P.ftrim_3p * ql);
+            qL = max(qL, (rev ? d3 : d5) + qs);
+            qR = min(qR, qe - (rev ? d5 : d3));
+        }
+        if (P.trim_5p > 0 || P.trim_3p > 0) {
+            qL = max(qL, (rev ? P.trim_3p : P.trim_5p) + qs);
+            qR = min(qR, qe - (rev ? P.trim_5p : P.trim_3p));
+        }
+        rec[FR_RCP] = (uint32_t)min(max(qL, 0), 65535) | ((uint32_t)min(max(qR, 0), 65535) << 16);
+        // the distance filters can only fire on reads with a ref-skip / insertion / deletion, or through the
+        // over-read of check_splice_overhang (RAER_RB_OHANG_N)
+        if ((P.splice_dist || P.min_overhang || P.indel_dist) && (!(fl & STF_SIMPLE) || (bits & RAER_RB_OHANG_N))) fl |= STF_SLOWFILT;
+    }
     if (n > 4) rec[FR_CIG0] = (uint32_t)b.x;
     rec[FR_POS] = (uint32_t)a.x;
     rec[FR_LEN] = (uint32_t)lq | ((uint32_t)n << 16);
@@ -265,6 +318,7 @@ __device__ __forceinline__ int fast_stage(const PlpParams& P, const FastSmem& S,
 
 // Phase 1 for one chunk of 32 listed reads, handled by one warp on its own (no CTA barrier): stage the records,
 // then the lanes take the chunk's items, two in flight per lane.
+template <bool EXT>
 __device__ __forceinline__ void fast_count_chunk(const PlpParams& P, const FastSmem& S, const FastCtx& X, int tile, int li0,
                                                  int l1, int t1, int lane, uint32_t* st, bool need_cov) {
     const int F = P.n_files;
@@ -275,7 +329,7 @@ __device__ __forceinline__ void fast_count_chunk(const PlpParams& P, const FastS
         int f = 0;
         while (f + 1 < F && li >= P.tile_off[tile * F + f + 1]) ++f;
         const int r = __ldg(P.tile_list + li);
-        nq = need_cov ? fast_stage<true>(P, S, X, r, f, t1, rec) : fast_stage<false>(P, S, X, r, f, t1, rec);
+        nq = need_cov ? fast_stage<true, EXT>(P, S, X, r, f, t1, rec) : fast_stage<false, EXT>(P, S, X, r, f, t1, rec);
     }
     // items of the chunk in read order: inclusive prefix of the per-read item counts
     uint32_t* pref = st + 32 * FREC;
@@ -328,7 +382,7 @@ __device__ __forceinline__ void fast_count_chunk(const PlpParams& P, const FastS
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             if (h) __syncwarp();
-            if (h ? okB : okA) fast_item(P, S, X, h ? recB : recA, h ? qB : qA, h ? swB : swA, h ? qwB : qwA);
+            if (h ? okB : okA) fast_item<EXT>(P, S, X, h ? recB : recA, h ? qB : qA, h ? swB : swA, h ? qwB : qwA);
         }
     }
     __syncwarp();
@@ -337,6 +391,7 @@ __device__ __forceinline__ void fast_count_chunk(const PlpParams& P, const FastS
 // ---- second pass: one (read, flagged position) pair per lane. Called by all 32 lanes (active = this lane has a
 // pair); the lanes are re-joined after the position lookup and after the loads, so single-block reads and reads
 // that walk a CIGAR share the rest of the code.
+template <bool EXT>
 __device__ __forceinline__ void fast_pair(const PlpParams& P, const FastSmem& S, const FastCtx& X, const TileSmem& T2,
                                           const uint32_t* rec, int rank, int ordinal, bool active) {
     const int pos = (int)rec[FR_POS];
@@ -381,6 +436,25 @@ __device__ __forceinline__ void fast_pair(const PlpParams& P, const FastSmem& S,
     }
     // read base N (src/plp.c:718); nX or dropped bases are not part of the statistics
     valid = valid && code != 15 && bq >= X.minbq;
+    if (EXT && valid) {  // the remaining filters of check_read_filters, as k_pileup_tiles evaluates them
+        ReadCtx c;
+        c.n_cigar = n;
+        c.cig = n <= 4 ? rec + FR_CIG0 : P.cigar + rec[FR_CIG0];
+        c.bits = (int)(fl & 0xff);
+        c.l_qseq = lq;
+        c.qs = qs;
+        c.qe = qe;
+        c.rev = (fl >> 16) & 1;
+        c.d5f = c.d3f = 0;
+        c.ftrim_all = 0;
+        if (P.ftrim_5p > 0 || P.ftrim_3p > 0) {
+            const int ql = qe - qs;
+            if (ql <= 0) c.ftrim_all = 1;
+            c.d5f = (int)floor(P.ftrim_5p * ql);
+            c.d3f = (int)ceil(P.ftrim_3p * ql);
+        }
+        valid = base_verdict(P, c, 0, q, bq) == 0;
+    }
     __syncwarp();
     if (valid) {
         const int a = pidx + 8;
@@ -398,6 +472,7 @@ __device__ __forceinline__ void fast_pair(const PlpParams& P, const FastSmem& S,
 
 // One chunk of 32 listed reads, handled by one warp: stage the reads that cover a flagged site of this round,
 // prefix-sum their pair counts, lanes take pairs.
+template <bool EXT>
 __device__ __forceinline__ void fast_pair_chunk(const PlpParams& P, const FastSmem& S, const FastCtx& X, const TileSmem& T2,
                                                 int tile, int li0, int l1, int lane, uint32_t* st) {
     uint32_t* pref = st + 32 * FREC;  // inclusive prefix of pairs per read
@@ -489,7 +564,7 @@ __device__ __forceinline__ void fast_pair_chunk(const PlpParams& P, const FastSm
         const int j = it - firstp, c0 = (int)(ri[FR_B2] >> 16), c1 = (int)ri[FR_B3];
         const int rank = j < c0 ? (int)(ri[FR_FIRST] & 0xffff) + j
                                 : (j < c0 + c1 ? (int)(ri[FR_FIRST] >> 16) + (j - c0) : (int)(ri[FR_B2] & 0xffff) + (j - c0 - c1));
-        fast_pair(P, S, X, T2, ri, rank, (int)pref[32 + i], it < tot);
+        fast_pair<EXT>(P, S, X, T2, ri, rank, (int)pref[32 + i], it < tot);
     }
     __syncwarp();
 }
@@ -536,6 +611,7 @@ __device__ void slot_stats(const PlpParams& P, const uint32_t* slot, int HW, int
     }
 }
 
+template <bool EXT>
 __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ int s_scan[40];
@@ -612,7 +688,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
                 if (lane == 0) c = atomicAdd(&s_chunk, 1);
                 c = __shfl_sync(FULL, c, 0);
                 if (c >= nchunks) break;
-                fast_count_chunk(P, S, X, tile, l0 + (c << 5), l1, t1, lane, st, need_cov);
+                fast_count_chunk<EXT>(P, S, X, tile, l0 + (c << 5), l1, t1, lane, st, need_cov);
             }
         }
         __syncthreads();
@@ -715,7 +791,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
                     if (lane == 0) c = atomicAdd(&s_chunk, 1);
                     c = __shfl_sync(FULL, c, 0);
                     if (c >= nchunks) break;
-                    fast_pair_chunk(P, S, X, T2, tile, l0 + (c << 5), l1, lane, st);
+                    fast_pair_chunk<EXT>(P, S, X, T2, tile, l0 + (c << 5), l1, lane, st);
                 }
             }
             __syncthreads();

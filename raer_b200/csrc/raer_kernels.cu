@@ -1186,14 +1186,16 @@ extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* l
         const size_t fsmem = raer_fast_smem_bytes(P->n_files, P->W);
         static size_t fconfigured = 0;
         if (fsmem > fconfigured) {
-            if (cudaFuncSetAttribute(k_pileup_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem) != cudaSuccess)
+            if (cudaFuncSetAttribute(k_pileup_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem) != cudaSuccess ||
+                cudaFuncSetAttribute(k_pileup_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem) != cudaSuccess)
                 return -1;
             fconfigured = fsmem;
         }
         int grid = n_sm * 2;
         if (grid > P->n_tiles) grid = P->n_tiles;
         if (e0) cudaEventRecord(e0, st);
-        k_pileup_fast<<<grid, FB_THREADS, fsmem, st>>>(*P);
+        if (P->fast) k_pileup_fast<false><<<grid, FB_THREADS, fsmem, st>>>(*P);
+        else k_pileup_fast<true><<<grid, FB_THREADS, fsmem, st>>>(*P);
         if (e1) cudaEventRecord(e1, st);
         ++nl;
         *launches = nl;

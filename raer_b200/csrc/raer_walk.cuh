@@ -246,7 +246,11 @@ __device__ void scan_reads(const PlpParams& P, const TileSmem& S, int f, int2 rg
                 }
             }
             const float inv_nq = uni && nq0 > 0 ? 1.0f / (float)nq0 : 0.f;
-            for (int it = lane; it < tot; it += 32) {
+            for (int itb = 0; itb < tot; itb += 32) {
+                // warp-uniform trip count: re-join the lanes that took different paths through the previous item
+                __syncwarp();
+                const int it = itb + lane;
+                if (it >= tot) continue;
                 int i, first;
                 if (uni) {
                     i = __float2int_rz(((float)it + 0.5f) * inv_nq);

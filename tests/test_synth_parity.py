@@ -68,10 +68,10 @@ def test_two_bam_parity(syn, kw):
     _assert_same(got, want)
 
 
-# The configurations with only mapq / base-quality filters run k_pileup_fast by default; RAER_KERNEL=generic
-# sends the same call through k_pileup_tiles, so both kernels are held to the oracle.
+# Every configuration without the mismatch filter runs k_pileup_fast by default; RAER_KERNEL=generic sends the
+# same call through k_pileup_tiles, so both kernels are held to the oracle.
 @pytest.mark.gpu
-@pytest.mark.parametrize("kw", [CONFIGS[i] for i in (0, 1, 2, 3, 4, 9, 12)], ids=[str(i) for i in (0, 1, 2, 3, 4, 9, 12)])
+@pytest.mark.parametrize("kw", [CONFIGS[i] for i in (0, 1, 2, 3, 4, 5, 6, 9, 12)], ids=[str(i) for i in (0, 1, 2, 3, 4, 5, 6, 9, 12)])
 def test_two_bam_parity_generic_kernel(syn, kw, monkeypatch):
     monkeypatch.setenv("RAER_KERNEL", "generic")
     fp = FilterParam(**kw)
@@ -253,13 +253,23 @@ ADV_CONFIGS = [
 ]
 
 
+ADV_CONFIGS += [
+    dict(library_type="fr-first-strand", ftrim_5p=0.15, ftrim_3p=0.2, min_base_quality=0),
+    dict(library_type="unstranded", trim_3p=6, indel_dist=5, min_base_quality=0, min_depth=0),
+    dict(library_type="fr-second-strand", splice_dist=8, min_splice_overhang=60, only_keep_variants=True),
+]
+
+
 @pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["default", "generic"])
 @pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("kw", ADV_CONFIGS, ids=[str(i) for i in range(len(ADV_CONFIGS))])
-def test_adversarial_parity(adversarial, kw, mode, monkeypatch):
+def test_adversarial_parity(adversarial, kw, mode, kernel, monkeypatch):
     bam, fa = adversarial
     from raer_b200 import _cabi, api
 
+    if kernel == "generic":
+        monkeypatch.setenv("RAER_KERNEL", "generic")
     fp = FilterParam(**kw)
     monkeypatch.setattr(oracle_backend, "OVERLAP_MODE", mode)
     want = oracle_backend.pileup_sites(bam, fa, param=fp)
