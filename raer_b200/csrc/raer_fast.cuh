@@ -162,7 +162,20 @@ __device__ __forceinline__ uint32_t fast_filter_mask(const PlpParams& P, const u
         c.n_cigar = (int)(rec[FR_LEN] >> 16);
         c.cig = c.n_cigar <= 4 ? rec + FR_CIG0 : P.cigar + rec[FR_CIG0];
         c.bits = (int)(fl & 0xff);
-        for (int q = q0; q < q1; ++q) {
+        // One pass over the CIGAR decides whether any base of the item can be hit at all: a ref-skip, insertion
+        // or deletion within the configured distance of [q0, q1), or an aligned block shorter than the overhang
+        // that touches the item. Most items of a spliced read are far from its junctions.
+        bool near = (c.bits & RAER_RB_OHANG_N) && P.min_overhang;
+        const int dmax = max(P.splice_dist, P.indel_dist);
+        for (int k = 0, ip = 0; k < c.n_cigar && !near; ++k) {
+            const uint32_t w = c.cig[k];
+            const int op = cg_op(w), cl = cg_len(w);
+            if (op == OP_N || op == OP_D) near = ip >= q0 - dmax && ip <= q1 - 1 + dmax;
+            else if (op == OP_I) near = ip + cl >= q0 - dmax && ip <= q1 - 1 + dmax;
+            else if (op == OP_M && P.min_overhang && cl < P.min_overhang) near = ip + cl >= q0 && ip <= q1 - 1;
+            if (cg_type(op) & 1) ip += cl;
+        }
+        for (int q = q0; near && q < q1; ++q) {
             bool hit = P.splice_dist && d_dist_to_splice(c, q, P.splice_dist) >= 0;
             if (!hit && P.min_overhang) hit = d_check_splice_overhang(c, q, P.min_overhang) > 0;
             if (!hit && P.indel_dist) hit = d_dist_to_indel(c, q, P.indel_dist) >= 0;
