@@ -547,7 +547,7 @@ __device__ __forceinline__ void fast_pair_chunk(const PlpParams& P, const FastSm
                 rec[FR_B3] = (uint32_t)cb[1];
                 // get_relative_position divides by alen + 1 = qe - qs + 1 (src/plp_utils.c:401-412): reciprocal once per read
                 const int rb = qe - qs + 1;
-                rec[FR_RCP] = rb > 1 ? (uint32_t)((0x100000000ull + rb - 1) / rb) : 0u;
+                rec[FR_RCP] = rb > 1 ? 0xffffffffu / (uint32_t)rb + 1u : 0u;  // ceil(2^32 / rb) without a 64-bit divide
             }
         }
     }
