@@ -261,53 +261,74 @@ __device__ __forceinline__ uint32_t qsum200(uint32_t a, uint32_t b) {
 // 8 qualities at a time: one aligned 64-bit word of A, the matching bytes of B funnelled out of two aligned
 // words, 8 packed bases of each read compared by XOR, agreeing bases summed byte-parallel; only disagreeing bases
 // run scalar code. Whole words are written back (a read owns its 8-byte quality words, raer_read_hdr.sq_off).
+// nbp <= 8 positions that share one aligned 8-byte quality word of A: base ia + j of A faces base ib + j of B.
+// B_SHARED: other lanes work on the neighbouring chunks of the same pair at the same time. A's word belongs to this
+// chunk alone, but B's bytes straddle words that the neighbours write too: B is then stored with byte / 32-bit
+// stores that cover exactly this chunk's bytes instead of a read-modify-write of whole words.
+template <bool B_SHARED>
+__device__ __forceinline__ void overlap_chunk(uint8_t* a_q, uint8_t* b_q, const uint8_t* a_seq, const uint8_t* b_seq, int ia,
+                                              int ib, int nbp, int amul, int bmul, int mode) {
+    const int oa = ia & 7, ob = ib & 7;
+    uint8_t* pa = a_q + (ia - oa);
+    uint8_t* pb = b_q + (ib - ob);
+    const bool two = ob + nbp > 8;
+    const unsigned long long wa = *reinterpret_cast<const unsigned long long*>(pa);
+    const unsigned long long wb0 = *reinterpret_cast<const unsigned long long*>(pb);
+    const unsigned long long wb1 = two ? *reinterpret_cast<const unsigned long long*>(pb + 8) : 0ull;
+    const unsigned long long QA = wa >> (8 * oa);
+    const unsigned long long QB = ob ? ((wb0 >> (8 * ob)) | (wb1 << (64 - 8 * ob))) : wb0;
+    // base j of the chunk in nibble j
+    const uint32_t sa = nib_swap(*reinterpret_cast<const uint32_t*>(a_seq + ((ia - oa) >> 1))) >> (4 * oa);
+    const uint32_t sb0 = nib_swap(*reinterpret_cast<const uint32_t*>(b_seq + ((ib - ob) >> 1)));
+    const uint32_t sb1 = two ? nib_swap(*reinterpret_cast<const uint32_t*>(b_seq + ((ib - ob) >> 1) + 4)) : 0u;
+    const uint32_t xs = sa ^ (ob ? ((sb0 >> (4 * ob)) | (sb1 << (32 - 4 * ob))) : sb0);
+    const unsigned long long mk = nbp == 8 ? ~0ull : ((1ull << (8 * nbp)) - 1ull);
+    // agreeing bases: one mate gets min(qa + qb, 200), the other 0 (mode 2: always the earlier mate)
+    const unsigned long long QS = (unsigned long long)qsum200((uint32_t)QA, (uint32_t)QB) |
+                                  ((unsigned long long)qsum200((uint32_t)(QA >> 32), (uint32_t)(QB >> 32)) << 32);
+    unsigned long long NA = amul ? QS : 0ull, NB = bmul ? QS : 0ull;
+    uint32_t mm = nib_nonzero(xs) & (nbp == 8 ? 0x11111111u : ((1u << (4 * nbp)) - 1u) & 0x11111111u);
+    while (mm) {  // disagreeing bases
+        const int j = (__ffs(mm) - 1) >> 2;
+        mm &= mm - 1;
+        const int qa = (int)((QA >> (8 * j)) & 0xff), qb = (int)((QB >> (8 * j)) & 0xff);
+        int na, nb;
+        if (mode == 2) {
+            if (qa >= qb) { na = (uint8_t)(0.8 * qa); nb = 0; }
+            else { nb = (uint8_t)(0.8 * qb); na = 0; }
+        } else {
+            if (qa > qb) { na = (uint8_t)(0.8 * qa); nb = 0; }
+            else if (qa < qb) { nb = (uint8_t)(0.8 * qb); na = 0; }
+            else { na = (uint8_t)(amul * 0.8 * qa); nb = (uint8_t)(bmul * 0.8 * qb); }
+        }
+        const unsigned long long bm = 0xffull << (8 * j);
+        NA = (NA & ~bm) | ((unsigned long long)(na & 0xff) << (8 * j));
+        NB = (NB & ~bm) | ((unsigned long long)(nb & 0xff) << (8 * j));
+    }
+    NA &= mk;
+    NB &= mk;
+    *reinterpret_cast<unsigned long long*>(pa) = (wa & ~(mk << (8 * oa))) | (NA << (8 * oa));
+    if (B_SHARED) {
+        uint8_t* d = b_q + ib;
+        int k = 0;
+        for (; k < nbp && ((ib + k) & 3); ++k) d[k] = (uint8_t)(NB >> (8 * k));
+        for (; k + 4 <= nbp; k += 4) *reinterpret_cast<uint32_t*>(d + k) = (uint32_t)(NB >> (8 * k));
+        for (; k < nbp; ++k) d[k] = (uint8_t)(NB >> (8 * k));
+    } else {
+        *reinterpret_cast<unsigned long long*>(pb) = (wb0 & ~(mk << (8 * ob))) | (NB << (8 * ob));
+        if (two) *reinterpret_cast<unsigned long long*>(pb + 8) = (wb1 & ~(mk >> (64 - 8 * ob))) | (NB >> (64 - 8 * ob));
+    }
+}
+
+// Apply the overlap rule to run + 1 consecutive positions: base ia0 + i of read A faces base ib0 + i of read B.
+// 8 qualities at a time: one aligned 64-bit word of A, the matching bytes of B funnelled out of two aligned
+// words, 8 packed bases of each read compared by XOR, agreeing bases summed byte-parallel; only disagreeing bases
+// run scalar code. Whole words are written back (a read owns its 8-byte quality words, raer_read_hdr.sq_off).
 __device__ __forceinline__ void overlap_run(uint8_t* a_q, uint8_t* b_q, const uint8_t* a_seq, const uint8_t* b_seq, int ia0,
                                             int ib0, int run, int amul, int bmul, int mode) {
     for (int i = 0; i <= run;) {
-        const int ia = ia0 + i, ib = ib0 + i;
-        const int oa = ia & 7, ob = ib & 7;
-        const int nbp = min(8 - oa, run + 1 - i);
-        uint8_t* pa = a_q + (ia - oa);
-        uint8_t* pb = b_q + (ib - ob);
-        const bool two = ob + nbp > 8;
-        const unsigned long long wa = *reinterpret_cast<const unsigned long long*>(pa);
-        const unsigned long long wb0 = *reinterpret_cast<const unsigned long long*>(pb);
-        const unsigned long long wb1 = two ? *reinterpret_cast<const unsigned long long*>(pb + 8) : 0ull;
-        const unsigned long long QA = wa >> (8 * oa);
-        const unsigned long long QB = ob ? ((wb0 >> (8 * ob)) | (wb1 << (64 - 8 * ob))) : wb0;
-        // base j of the chunk in nibble j
-        const uint32_t sa = nib_swap(*reinterpret_cast<const uint32_t*>(a_seq + ((ia - oa) >> 1))) >> (4 * oa);
-        const uint32_t sb0 = nib_swap(*reinterpret_cast<const uint32_t*>(b_seq + ((ib - ob) >> 1)));
-        const uint32_t sb1 = two ? nib_swap(*reinterpret_cast<const uint32_t*>(b_seq + ((ib - ob) >> 1) + 4)) : 0u;
-        const uint32_t xs = sa ^ (ob ? ((sb0 >> (4 * ob)) | (sb1 << (32 - 4 * ob))) : sb0);
-        const unsigned long long mk = nbp == 8 ? ~0ull : ((1ull << (8 * nbp)) - 1ull);
-        // agreeing bases: one mate gets min(qa + qb, 200), the other 0 (mode 2: always the earlier mate)
-        const unsigned long long QS = (unsigned long long)qsum200((uint32_t)QA, (uint32_t)QB) |
-                                      ((unsigned long long)qsum200((uint32_t)(QA >> 32), (uint32_t)(QB >> 32)) << 32);
-        unsigned long long NA = amul ? QS : 0ull, NB = bmul ? QS : 0ull;
-        uint32_t mm = nib_nonzero(xs) & (nbp == 8 ? 0x11111111u : ((1u << (4 * nbp)) - 1u) & 0x11111111u);
-        while (mm) {  // disagreeing bases
-            const int j = (__ffs(mm) - 1) >> 2;
-            mm &= mm - 1;
-            const int qa = (int)((QA >> (8 * j)) & 0xff), qb = (int)((QB >> (8 * j)) & 0xff);
-            int na, nb;
-            if (mode == 2) {
-                if (qa >= qb) { na = (uint8_t)(0.8 * qa); nb = 0; }
-                else { nb = (uint8_t)(0.8 * qb); na = 0; }
-            } else {
-                if (qa > qb) { na = (uint8_t)(0.8 * qa); nb = 0; }
-                else if (qa < qb) { nb = (uint8_t)(0.8 * qb); na = 0; }
-                else { na = (uint8_t)(amul * 0.8 * qa); nb = (uint8_t)(bmul * 0.8 * qb); }
-            }
-            const unsigned long long bm = 0xffull << (8 * j);
-            NA = (NA & ~bm) | ((unsigned long long)(na & 0xff) << (8 * j));
-            NB = (NB & ~bm) | ((unsigned long long)(nb & 0xff) << (8 * j));
-        }
-        NA &= mk;
-        NB &= mk;
-        *reinterpret_cast<unsigned long long*>(pa) = (wa & ~(mk << (8 * oa))) | (NA << (8 * oa));
-        *reinterpret_cast<unsigned long long*>(pb) = (wb0 & ~(mk << (8 * ob))) | (NB << (8 * ob));
-        if (two) *reinterpret_cast<unsigned long long*>(pb + 8) = (wb1 & ~(mk >> (64 - 8 * ob))) | (NB >> (64 - 8 * ob));
+        const int nbp = min(8 - ((ia0 + i) & 7), run + 1 - i);
+        overlap_chunk<false>(a_q, b_q, a_seq, b_seq, ia0 + i, ib0 + i, nbp, amul, bmul, mode);
         i += nbp;
     }
 }
@@ -328,10 +349,86 @@ __device__ __forceinline__ bool single_block(const uint32_t* cig, int n, int& qs
     return nblk == 1 && !other;
 }
 
+// Pairs whose mates are both one aligned block: the overlap is one run, known up front. The lanes of a warp pool
+// the 8-position chunks of their pairs and take one chunk each (overlaps of 1 .. 100 bases would otherwise leave
+// most lanes waiting for the longest one). Every other pair goes to `general` (compacted, warp-aggregated
+// append) for k_mate_overlap.
+__global__ void k_mate_overlap_simple(const raer_read_hdr* __restrict__ hdr, const uint32_t* __restrict__ cigar,
+                                      const uint8_t* __restrict__ seq, uint8_t* qual, const int32_t* __restrict__ pair_b,
+                                      long long n_pairs, int mode, int* general, int* n_general) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int ia0 = 0, ib0 = 0, run = -1, amul = 0, bmul = 0;
+    unsigned asq = 0, bsq = 0;
+    bool gen = false;
+    if (t < n_pairs) {
+        const raer_read_hdr hb = hdr[pair_b[t]];
+        const raer_read_hdr ha = hdr[hb.mate];
+        if (mode == 2 || (hb.bits & RAER_RB_KEEP_A)) { amul = 1; bmul = 0; }
+        else { amul = 0; bmul = 1; }
+        int qsa, lena, qsb, lenb;
+        if (single_block(cigar + ha.cigar_off, ha.n_cigar, qsa, lena) && single_block(cigar + hb.cigar_off, hb.n_cigar, qsb, lenb)) {
+            if (hb.pos >= ha.pos) {  // cur_set(A, negative) otherwise: nothing to do
+                const int lo = hb.pos, hi = min(ha.pos + lena, hb.pos + lenb);
+                ia0 = qsa + (lo - ha.pos);
+                ib0 = qsb;
+                run = min(hi - lo - 1, min((int)ha.l_qseq - 1 - ia0, (int)hb.l_qseq - 1 - ib0));
+                asq = ha.sq_off;
+                bsq = hb.sq_off;
+            }
+        } else {
+            gen = true;
+        }
+    }
+    {   // compacted list of the remaining pairs
+        const unsigned m = __ballot_sync(FULL, gen);
+        int base = 0;
+        if (m && lane == (int)(__ffs(m) - 1)) base = atomicAdd(n_general, __popc(m));
+        base = __shfl_sync(FULL, base, m ? __ffs(m) - 1 : 0);
+        if (gen) general[base + __popc(m & ((1u << lane) - 1u))] = (int)t;
+    }
+    // chunks are cut at the 8-byte boundaries of A's qualities
+    const int nch = run >= 0 ? ((ia0 + run) >> 3) - (ia0 >> 3) + 1 : 0;
+    int inc = nch;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += v;
+    }
+    const int tot = __shfl_sync(FULL, inc, 31);
+    for (int itb = 0; itb < tot; itb += 32) {
+        const int it = itb + lane;
+        // owner of chunk `it`: the first lane whose inclusive prefix exceeds it
+        int owner = 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const int v = __shfl_sync(FULL, inc, owner + o - 1);
+            if (v <= it) owner += o;
+        }
+        owner = min(owner, 31);
+        const int o_inc = __shfl_sync(FULL, inc, owner), o_nch = __shfl_sync(FULL, nch, owner);
+        const int o_ia0 = __shfl_sync(FULL, ia0, owner), o_ib0 = __shfl_sync(FULL, ib0, owner), o_run = __shfl_sync(FULL, run, owner);
+        const int o_am = __shfl_sync(FULL, amul, owner), o_bm = __shfl_sync(FULL, bmul, owner);
+        const unsigned o_asq = __shfl_sync(FULL, asq, owner), o_bsq = __shfl_sync(FULL, bsq, owner);
+        if (it < tot) {
+            const int c = it - (o_inc - o_nch);                    // chunk index inside the pair
+            const int w0 = (o_ia0 >> 3) + c;                       // A's quality word
+            const int ia = max(w0 << 3, o_ia0), ie = min((w0 << 3) + 8, o_ia0 + o_run + 1);
+            overlap_chunk<true>(qual + 2ull * o_asq, qual + 2ull * o_bsq, seq + o_asq, seq + o_bsq, ia, o_ib0 + (ia - o_ia0), ie - ia,
+                          o_am, o_bm, mode);
+        }
+    }
+}
+
+// Pairs with a CIGAR to walk: htslib's two cursors, literally (thread per pair; `list` = indices into pair_b, or
+// nullptr for all pairs).
 __global__ void k_mate_overlap(const raer_read_hdr* __restrict__ hdr, const uint32_t* __restrict__ cigar,
                                const uint8_t* __restrict__ seq, uint8_t* qual, const int32_t* __restrict__ pair_b,
-                               long long n_pairs, int mode) {
+                               long long n_pairs, int mode, const int* __restrict__ list, const int* __restrict__ n_list) {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (list) {
+        if (t >= *n_list) return;
+        t = list[t];
+    }
     if (t >= n_pairs) return;
     const raer_read_hdr hb = hdr[pair_b[t]];
     const raer_read_hdr ha = hdr[hb.mate];
@@ -1156,13 +1253,22 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
 // ---------------------------------------------------------------------------------------------
 // host-side launchers (called from raer_runtime.cpp)
 // ---------------------------------------------------------------------------------------------
+// scratch: n_pairs + 1 ints of device memory for the compacted list of CIGAR-walking pairs, or nullptr (one kernel
+// handles every pair then)
 extern "C" int raer_launch_overlap(const raer_read_hdr* hdr, const uint32_t* cigar, const uint8_t* seq, uint8_t* qual,
-                                   const int32_t* pair_b, long long n_pairs, int mode, cudaStream_t st) {
+                                   const int32_t* pair_b, long long n_pairs, int mode, cudaStream_t st, int* scratch) {
     if (n_pairs <= 0) return 0;
-    int block = 128;
-    long long grid = (n_pairs + block - 1) / block;
-    k_mate_overlap<<<(unsigned)grid, block, 0, st>>>(hdr, cigar, seq, qual, pair_b, n_pairs, mode);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    const int block = 128;
+    const long long grid = (n_pairs + block - 1) / block;
+    if (!scratch) {
+        k_mate_overlap<<<(unsigned)grid, block, 0, st>>>(hdr, cigar, seq, qual, pair_b, n_pairs, mode, nullptr, nullptr);
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
+    cudaMemsetAsync(scratch, 0, sizeof(int), st);
+    k_mate_overlap_simple<<<(unsigned)grid, block, 0, st>>>(hdr, cigar, seq, qual, pair_b, n_pairs, mode, scratch + 1, scratch);
+    // the size of the list stays on the device: launch for the worst case, surplus threads leave at once
+    k_mate_overlap<<<(unsigned)grid, block, 0, st>>>(hdr, cigar, seq, qual, pair_b, n_pairs, mode, scratch + 1, scratch);
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
 extern "C" size_t raer_tile_smem_bytes(int n_files, int W, int S, int* cnt_words, int* slot_words) {

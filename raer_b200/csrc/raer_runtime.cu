@@ -20,7 +20,7 @@ const char* last_error();
 using raer::set_error;
 
 extern "C" int raer_launch_overlap(const raer_read_hdr* hdr, const uint32_t* cigar, const uint8_t* seq, uint8_t* qual,
-                                   const int32_t* pair_b, long long n_pairs, int mode, cudaStream_t st);
+                                   const int32_t* pair_b, long long n_pairs, int mode, cudaStream_t st, int* scratch);
 extern "C" size_t raer_tile_smem_bytes(int n_files, int W, int S, int* cnt_words, int* slot_words);
 extern "C" int raer_fast_width(int n_files);
 extern "C" int raer_fast_index_count(PlpParams* P, long long n_reads, int* cnt, int* off, int* cur, int* total, cudaStream_t st);
@@ -79,6 +79,7 @@ struct raer_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6];
     DevBuf hdr, maxend, cigar, seq, qual, pair_b, mask;
+    DevBuf ov_scratch;                     // mate overlap: compacted list of the CIGAR-walking pairs
     DevBuf tile_idx, tile_list;            // k_pileup_fast: counts | offsets | cursors, and the per-tile read lists
     DevBuf tile_ranges, tile_rows, small;  // small: tile_counter(4) | pad | row_counter(8) | err(4)
     DevBuf row_pos, row_meta, row_stats, row_counts, row_alt;
@@ -119,7 +120,7 @@ extern "C" void raer_ctx_destroy(raer_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->hdr, &c->maxend, &c->cigar, &c->seq, &c->qual, &c->pair_b, &c->mask, &c->tile_ranges, &c->tile_rows, &c->tile_idx, &c->tile_list,
+    for (DevBuf* b : {&c->hdr, &c->maxend, &c->cigar, &c->seq, &c->qual, &c->pair_b, &c->mask, &c->tile_ranges, &c->tile_rows, &c->tile_idx, &c->tile_list, &c->ov_scratch,
                       &c->small, &c->row_pos, &c->row_meta, &c->row_stats, &c->row_counts, &c->row_alt, &c->ref})
         b->release();
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -247,8 +248,9 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
         P.S = std::max(32, cw / sw);
         if (P.S > 4096) P.S = 4096;
         if (conf->remove_overlaps && b->n_pairs > 0 && !(flags & RUN_SKIP_OVERLAP)) {
+            if ((rc = c->ov_scratch.ensure(((size_t)b->n_pairs + 1) * sizeof(int)))) return rc;
             int r = raer_launch_overlap(b->hdr, b->cigar, b->seq, (uint8_t*)b->qual, b->pair_b, b->n_pairs,
-                                        conf->remove_overlaps, c->stream);
+                                        conf->remove_overlaps, c->stream, (int*)c->ov_scratch.p);
             if (r < 0) { set_error("overlap kernel launch failed"); return RAER_ERR_CUDA; }
             nl += r;
         }

@@ -283,7 +283,7 @@ __global__ void k_sc_cell(const unsigned long long* __restrict__ keys, const uns
 
 // ------------------------------------------------------------------------------------- host side
 extern "C" int raer_launch_overlap(const raer_read_hdr* hdr, const uint32_t* cigar, const uint8_t* seq, uint8_t* qual,
-                                   const int32_t* pair_b, long long n_pairs, int mode, cudaStream_t st);
+                                   const int32_t* pair_b, long long n_pairs, int mode, cudaStream_t st, int* scratch);
 
 struct DBuf {
     void* p = nullptr;
@@ -433,7 +433,7 @@ extern "C" int raer_scpileup(const raer_scpileup_args* a) {
                 SCK(cudaMemsetAsync(d_tot.p, 0, (size_t)ns * 8, st));
                 if (ic.remove_overlaps && b.n_pairs > 0)
                     raer_launch_overlap((const raer_read_hdr*)d_hdr.p, (const uint32_t*)d_cigar.p, (const uint8_t*)d_seq.p,
-                                        (uint8_t*)d_qual.p, (const int32_t*)d_pair.p, b.n_pairs, ic.remove_overlaps, st);
+                                        (uint8_t*)d_qual.p, (const int32_t*)d_pair.p, b.n_pairs, ic.remove_overlaps, st, nullptr);
                 ScParams A;
                 memset(&A, 0, sizeof(A));
                 A.P.hdr = (const raer_read_hdr*)d_hdr.p; A.P.cigar = (const uint32_t*)d_cigar.p;
