@@ -1,10 +1,10 @@
-// raer_fast.cuh -- k_pileup_fast: the tile kernel for every configuration without the mismatch filter
-// (max_mismatch_type). k_pileup_fast<false>: only the mapq and base-quality filters of check_read_filters are
+// raer_fast.cuh -- k_pileup_fast: the tile kernel. k_pileup_fast<false>: only the mapq and base-quality filters of check_read_filters are
 // active (src/plp.c:568-586, the default FilterParam). k_pileup_fast<true>: also the trim, splice-distance,
 // splice-overhang and indel-distance filters (:588-612), which all turn a base into nX and depend on nothing
-// but the read and the query offset: trims are two bounds per read, the distance filters are evaluated per base
-// only for reads that have a ref-skip / insertion / deletion. Included from raer_kernels.cu; the mismatch
-// filter and base-quality thresholds above 128 run k_pileup_tiles.
+// but the read and the query offset (trims are two bounds per read, the distance filters are evaluated per base
+// only for reads that have a ref-skip / insertion / deletion), and the mismatch filter (:744-760), a per-read MD
+// verdict that drops the bases consulting it. Included from raer_kernels.cu; base-quality thresholds above 128
+// and tiles deeper than 65535 run k_pileup_tiles.
 //
 // The reference touches a counter for every aligned base. Here a base that equals the reference and
 // passes the quality filter touches nothing:
@@ -100,8 +100,10 @@ struct FastCtx {  // per-kernel constants of the item walk
 
 // ---- phase 1: one aligned block's share of an item. Bases j in [jlo, jhi) sit on tile positions rel + j.
 // NM/LT/Z: nibble-bit masks (bit 4j) of read base N, quality below the threshold, quality 0.
+// mmf: RAER_RB_MMFAIL / RAER_RB_MMERR bits of the read when the mismatch filter is configured, else 0
 __device__ __forceinline__ void fast_block_count(const FastSmem& S, const FastCtx& X, unsigned cbs, uint32_t rw, uint32_t NM,
-                                                 uint32_t LT, uint32_t Z, bool mapq_fail, int cxor, int rel, int jlo, int jhi) {
+                                                 uint32_t LT, uint32_t Z, bool mapq_fail, int cxor, int rel, int jlo, int jhi,
+                                                 int mmf = 0, int* err_flag = nullptr) {
     const int lo = max(max(jlo, -rel), 0), hi = min(min(jhi, X.tw - rel), 8);
     if (lo >= hi) return;
     const uint32_t V = (0x11111111u >> ((8 - (hi - lo)) << 2)) << (lo << 2);
@@ -116,6 +118,16 @@ __device__ __forceinline__ void fast_block_count(const FastSmem& S, const FastCt
         D = (Z | NM) & V;   // quality 0 below the threshold is dropped silently (src/plp.c:580-586), so is N
         XM = LT & V & ~D;   // nX
         MM = nib_nonzero(rw ^ refw) & V & ~(LT | D);
+        if (mmf) {
+            // src/plp.c:750: a base that passed every filter consults the read's MD verdict if the read is inverted or
+            // the base differs from the reference; a failing read drops such bases silently, an inconsistent MD tag is
+            // a hard error
+            const uint32_t consulted = cxor ? (V & ~(D | XM)) : MM;
+            if (consulted) {
+                if (mmf & RAER_RB_MMERR) atomicExch(err_flag, RAER_ERR_MD);
+                if (mmf & RAER_RB_MMFAIL) { D |= consulted; MM &= ~consulted; }
+            }
+        }
     }
     const unsigned base = cbs + ((unsigned)rel << 2);  // shared address of this item's first coverage word
     // runs of dropped bases leave the coverage: -1 where a run starts, +1 after its end
@@ -145,8 +157,9 @@ __device__ __forceinline__ void fast_block_count(const FastSmem& S, const FastCt
 }
 
 __device__ __noinline__ void fast_block_count_call(const FastSmem& S, const FastCtx& X, unsigned cbs, uint32_t rw, uint32_t NM,
-                                                   uint32_t LT, uint32_t Z, bool mapq_fail, int cxor, int rel, int jlo, int jhi) {
-    fast_block_count(S, X, cbs, rw, NM, LT, Z, mapq_fail, cxor, rel, jlo, jhi);
+                                                   uint32_t LT, uint32_t Z, bool mapq_fail, int cxor, int rel, int jlo, int jhi,
+                                                   int mmf, int* err_flag) {
+    fast_block_count(S, X, cbs, rw, NM, LT, Z, mapq_fail, cxor, rel, jlo, jhi, mmf, err_flag);
 }
 
 // EXT: nibble-bit mask of the item's bases that the read-geometry filters turn into nX (check_read_filters after the
@@ -242,11 +255,12 @@ __device__ __forceinline__ void fast_item(const PlpParams& P, const FastSmem& S,
         next_block();
     }
     // one inlined copy of the block code for every kind of read ...
-    if (has) fast_block_count(S, X, cbs, rw, NM, LT, Z, mapq_fail, s ? 3 : 0, rel, jlo, jhi);
+    const int mmf = (EXT && (P.n_mm_type > 0 || P.n_mm > 0)) ? (int)(fl & (RAER_RB_MMFAIL | RAER_RB_MMERR)) : 0;
+    if (has) fast_block_count(S, X, cbs, rw, NM, LT, Z, mapq_fail, s ? 3 : 0, rel, jlo, jhi, mmf, P.err_flag);
     // ... and a call for the rare item that straddles two aligned blocks
     while (!simple && has && k < n && y < q1) {
         next_block();
-        if (has) fast_block_count_call(S, X, cbs, rw, NM, LT, Z, mapq_fail, s ? 3 : 0, rel, jlo, jhi);
+        if (has) fast_block_count_call(S, X, cbs, rw, NM, LT, Z, mapq_fail, s ? 3 : 0, rel, jlo, jhi, mmf, P.err_flag);
     }
 }
 
@@ -472,6 +486,11 @@ __device__ __forceinline__ void fast_pair(const PlpParams& P, const FastSmem& S,
     if (valid) {
         const int a = pidx + 8;
         const int rcode = (S.refn[a >> 3] >> ((a & 7) << 2)) & 15;
+        if (EXT && (P.n_mm_type > 0 || P.n_mm > 0) && (fl & (RAER_RB_MMFAIL | RAER_RB_MMERR)) &&
+            ((fl & RAER_RB_INVERT) || !((code == rcode) & (code != 0)))) {  // src/plp.c:750, as in phase 1
+            if (fl & RAER_RB_MMERR) atomicExch(P.err_flag, RAER_ERR_MD);
+            return;
+        }
         ReadCtx c;
         c.l_qseq = lq;
         c.qs = qs;

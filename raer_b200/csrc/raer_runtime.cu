@@ -189,15 +189,14 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
     for (int i = 0; i <= nf; ++i) P.file_off[i] = b->file_off[i];
     P.n_files = nf;
     P.t_beg = b->beg; P.t_end = b->end;
-    // k_pileup_fast: everything but the mismatch filter, threshold within the byte-parallel compare's range.
+    // k_pileup_fast: every filter, as long as the threshold is within the byte-parallel compare's range.
     // RAER_KERNEL=generic forces k_pileup_tiles (tests run both kernels on the same inputs).
     const bool only_bq = !(conf->trim_5p > 0 || conf->trim_3p > 0 || conf->ftrim_5p > 0 || conf->ftrim_3p > 0 ||
                            conf->splice_dist || conf->min_overhang || conf->indel_dist || conf->n_mm_type > 0 || conf->n_mm > 0);
     const char* kforce = getenv("RAER_KERNEL");
     const int fw = raer_fast_width(nf);
-    const bool no_mm = !(conf->n_mm_type > 0 || conf->n_mm > 0);
     (void)only_bq;
-    P.use_fast = no_mm && conf->min_bq <= 128 && fw > 0 && !(kforce && !strcmp(kforce, "generic")) &&
+    P.use_fast = conf->min_bq <= 128 && fw > 0 && !(kforce && !strcmp(kforce, "generic")) &&
                  !(flags & RUN_FORCE_GENERIC);
     P.W = P.use_fast ? fw : choose_tile_width(nf);
     if (P.use_fast && getenv("RAER_FAST_W")) P.W = std::max(32, std::min(fw, atoi(getenv("RAER_FAST_W")) & ~31));

@@ -56,6 +56,8 @@ CONFIGS = [
     dict(read_bqual=(0.2, 20.0), max_depth=40),
     dict(bam_flags=scan_bam_flag(isMinusStrand=True)),
     dict(min_base_quality=0, only_keep_variants=True, min_allelic_freq=0.01),
+    dict(library_type="fr-first-strand", max_mismatch_type=(1, 2)),
+    dict(library_type="unstranded", max_mismatch_type=(2, 3), trim_5p=3, min_base_quality=10),
 ]
 
 
@@ -68,10 +70,11 @@ def test_two_bam_parity(syn, kw):
     _assert_same(got, want)
 
 
-# Every configuration without the mismatch filter runs k_pileup_fast by default; RAER_KERNEL=generic sends the
+# Every configuration runs k_pileup_fast by default; RAER_KERNEL=generic sends the
 # same call through k_pileup_tiles, so both kernels are held to the oracle.
 @pytest.mark.gpu
-@pytest.mark.parametrize("kw", [CONFIGS[i] for i in (0, 1, 2, 3, 4, 5, 6, 9, 12)], ids=[str(i) for i in (0, 1, 2, 3, 4, 5, 6, 9, 12)])
+@pytest.mark.parametrize("kw", [CONFIGS[i] for i in (0, 1, 2, 3, 4, 5, 6, 9, 12, 13, 14)],
+                         ids=[str(i) for i in (0, 1, 2, 3, 4, 5, 6, 9, 12, 13, 14)])
 def test_two_bam_parity_generic_kernel(syn, kw, monkeypatch):
     monkeypatch.setenv("RAER_KERNEL", "generic")
     fp = FilterParam(**kw)
@@ -257,6 +260,8 @@ ADV_CONFIGS += [
     dict(library_type="fr-first-strand", ftrim_5p=0.15, ftrim_3p=0.2, min_base_quality=0),
     dict(library_type="unstranded", trim_3p=6, indel_dist=5, min_base_quality=0, min_depth=0),
     dict(library_type="fr-second-strand", splice_dist=8, min_splice_overhang=60, only_keep_variants=True),
+    dict(library_type="fr-first-strand", max_mismatch_type=(1, 1), min_base_quality=0),
+    dict(library_type="unstranded", max_mismatch_type=(2, 2)),
 ]
 
 
