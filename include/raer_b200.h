@@ -151,7 +151,9 @@ typedef struct raer_read_hdr {
     uint32_t cigar_off; /* first CIGAR word in raer_read_batch.cigar */
     uint32_t sq_off;    /* byte offset of the packed sequence; qualities start at 2*sq_off */
     int32_t mate;       /* batch index of the earlier mate this read resolves its overlap with, or -1 */
-    uint32_t aux;       /* bulk: unused (0); single cell: index into cb/umi arrays == read index */
+    uint32_t aux;       /* single cell: index into cb/umi arrays == read index. Bulk UMI mode (src/plp.c:622-646): positions
+                           below aux are taken by an earlier read with the same UMI on the same strand of the same file
+                           (0 = none, 0xffffffff = the read has no UMI tag: it is skipped everywhere); else 0 */
 } raer_read_hdr;
 
 #define RAER_RB_INVERT 0x01  /* library type + flag put this read on the minus strand (plp_utils.c:331-371) */
@@ -159,6 +161,7 @@ typedef struct raer_read_hdr {
 #define RAER_RB_MMERR 0x04   /* MD tag inconsistent: hard error if the mismatch filter consults this read */
 #define RAER_RB_KEEP_A 0x08  /* mate overlap: the earlier mate keeps its qualities (qname hash, htslib >= 1.13) */
 #define RAER_RB_OHANG_N 0x10 /* the word after the CIGAR reads as a ref-skip (plp_utils.c:245-251 over-read) */
+#define RAER_RB_UMI_HOLES 0x20 /* bulk UMI mode: raer_read_batch.umi_holes lists positions below hdr.aux that stay counted */
 
 /* Struct-of-arrays read batch: all reads of all files that overlap the genomic window
  * [beg, end) of contig tid, file-major, coordinate sorted inside a file. Host or device pointers. */
@@ -180,6 +183,8 @@ typedef struct raer_read_batch {
     const int32_t* cb;         /* single cell: whitelist column (1-based) per read, 0 = none; else NULL */
     const uint32_t* umi;       /* single cell: UMI dictionary id per read, 0 = no tag; else NULL */
     int64_t n_aligned_bases;   /* M/=/X bases of the batch (metric unit), informational */
+    const int32_t* umi_holes;  /* bulk UMI mode: (read index, position) pairs sorted by read index, see RAER_RB_UMI_HOLES */
+    int64_t n_umi_holes;       /* number of pairs */
 } raer_read_batch;
 
 /* Per-call configuration of the bulk kernels (the unpacked FilterParam, src/plp.c:1094-1138). */
@@ -191,7 +196,7 @@ typedef struct raer_bulk_conf {
     int32_t report_multiallelic;
     int32_t remove_overlaps;   /* 0 none, 1 htslib >= 1.13, 2 htslib <= 1.12 */
     int32_t want_stats;        /* 1: rpbz/vdb/sor + ALT order (reference behaviour); 0 skips the second pass */
-    int32_t pad0;
+    int32_t umi_mode;          /* 1: bulk UMI mode, hdr.aux / umi_holes carry the per-read verdicts */
     double ftrim_5p, ftrim_3p, min_af;
     int32_t min_mapq[RAER_MAX_FILES];
     int32_t only_keep_variants[RAER_MAX_FILES];

@@ -130,6 +130,7 @@ class ReadBatch(C.Structure):
         ("pair_b", C.c_void_p), ("n_pairs", C.c_int64),
         ("cb", C.c_void_p), ("umi", C.c_void_p),
         ("n_aligned_bases", C.c_int64),
+        ("umi_holes", C.c_void_p), ("n_umi_holes", C.c_int64),
     ]
 
 
@@ -139,7 +140,7 @@ class BulkConf(C.Structure):
         ("trim_3p", C.c_int32), ("indel_dist", C.c_int32), ("splice_dist", C.c_int32), ("min_overhang", C.c_int32),
         ("nmer", C.c_int32), ("min_var_reads", C.c_int32), ("n_mm_type", C.c_int32), ("n_mm", C.c_int32),
         ("report_multiallelic", C.c_int32), ("remove_overlaps", C.c_int32), ("want_stats", C.c_int32),
-        ("pad0", C.c_int32),
+        ("umi_mode", C.c_int32),
         ("ftrim_5p", C.c_double), ("ftrim_3p", C.c_double), ("min_af", C.c_double),
         ("min_mapq", C.c_int32 * MAX_FILES), ("only_keep_variants", C.c_int32 * MAX_FILES),
         ("reg_beg", C.c_int32), ("reg_end", C.c_int32),

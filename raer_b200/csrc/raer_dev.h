@@ -48,6 +48,9 @@ struct PlpParams {
     // configuration
     int min_depth, min_bq, trim_5p, trim_3p, indel_dist, splice_dist, min_overhang, nmer, min_var_reads;
     int n_mm_type, n_mm, report_multiallelic, want_stats, any_okv;
+    int umi_mode;                    // bulk UMI mode: hdr.aux = end of the positions an earlier read of the same UMI takes
+    const int32_t* umi_holes;        //   (read index, position) pairs sorted by read index: positions that stay counted
+    int n_umi_holes;
     int fast;                        // only mapq / base-quality filters configured: branch-free item path
     int use_fast;                    // launch k_pileup_fast (raer_fast.cuh) instead of k_pileup_tiles
     double ftrim_5p, ftrim_3p, min_af;

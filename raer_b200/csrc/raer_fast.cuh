@@ -92,6 +92,17 @@ __device__ __forceinline__ void cover_range(uint32_t* cov, int lo, int hi) {  //
     }
 }
 
+// bulk UMI mode: true iff position p of read r stays counted although it lies below the read's hdr.aux
+__device__ __forceinline__ bool umi_is_hole(const PlpParams& P, int r, int p) {
+    int lo = 0, hi = P.n_umi_holes;
+    while (lo < hi) {  // first pair with (read, pos) >= (r, p)
+        const int mid = (lo + hi) >> 1;
+        const int mr = __ldg(P.umi_holes + 2 * mid), mp = __ldg(P.umi_holes + 2 * mid + 1);
+        if (mr < r || (mr == r && mp < p)) lo = mid + 1; else hi = mid;
+    }
+    return lo < P.n_umi_holes && __ldg(P.umi_holes + 2 * lo) == r && __ldg(P.umi_holes + 2 * lo + 1) == p;
+}
+
 struct FastCtx {  // per-kernel constants of the item walk
     int t0, tw, minbq;
     uint32_t mb4, zall;
@@ -103,7 +114,8 @@ struct FastCtx {  // per-kernel constants of the item walk
 // mmf: RAER_RB_MMFAIL / RAER_RB_MMERR bits of the read when the mismatch filter is configured, else 0
 __device__ __forceinline__ void fast_block_count(const FastSmem& S, const FastCtx& X, unsigned cbs, uint32_t rw, uint32_t NM,
                                                  uint32_t LT, uint32_t Z, bool mapq_fail, int cxor, int rel, int jlo, int jhi,
-                                                 int mmf = 0, int* err_flag = nullptr) {
+                                                 int mmf = 0, int* err_flag = nullptr, uint32_t skip = 0) {
+    // bulk UMI mode: skip = bases of a read with UMI holes that an earlier read takes (in the coverage: dropped here)
     const int lo = max(max(jlo, -rel), 0), hi = min(min(jhi, X.tw - rel), 8);
     if (lo >= hi) return;
     const uint32_t V = (0x11111111u >> ((8 - (hi - lo)) << 2)) << (lo << 2);
@@ -111,11 +123,11 @@ __device__ __forceinline__ void fast_block_count(const FastSmem& S, const FastCt
     const uint32_t refw = __funnelshift_r(S.refn[a >> 3], S.refn[(a >> 3) + 1], (a & 7) << 2);
     uint32_t D, XM, MM;
     if (mapq_fail) {  // every base of the read is nX (src/plp.c:574); read base N is counted nowhere (:718)
-        D = NM & V;
-        XM = V & ~NM;
+        D = (NM | skip) & V;
+        XM = V & ~D;
         MM = 0;
     } else {
-        D = (Z | NM) & V;   // quality 0 below the threshold is dropped silently (src/plp.c:580-586), so is N
+        D = (Z | NM | skip) & V;   // quality 0 below the threshold is dropped silently (src/plp.c:580-586), so is N
         XM = LT & V & ~D;   // nX
         MM = nib_nonzero(rw ^ refw) & V & ~(LT | D);
         if (mmf) {
@@ -158,8 +170,8 @@ __device__ __forceinline__ void fast_block_count(const FastSmem& S, const FastCt
 
 __device__ __noinline__ void fast_block_count_call(const FastSmem& S, const FastCtx& X, unsigned cbs, uint32_t rw, uint32_t NM,
                                                    uint32_t LT, uint32_t Z, bool mapq_fail, int cxor, int rel, int jlo, int jhi,
-                                                   int mmf, int* err_flag) {
-    fast_block_count(S, X, cbs, rw, NM, LT, Z, mapq_fail, cxor, rel, jlo, jhi, mmf, err_flag);
+                                                   int mmf, int* err_flag, uint32_t skip) {
+    fast_block_count(S, X, cbs, rw, NM, LT, Z, mapq_fail, cxor, rel, jlo, jhi, mmf, err_flag, skip);
 }
 
 // EXT: nibble-bit mask of the item's bases that the read-geometry filters turn into nX (check_read_filters after the
@@ -256,11 +268,26 @@ __device__ __forceinline__ void fast_item(const PlpParams& P, const FastSmem& S,
     }
     // one inlined copy of the block code for every kind of read ...
     const int mmf = (EXT && (P.n_mm_type > 0 || P.n_mm > 0)) ? (int)(fl & (RAER_RB_MMFAIL | RAER_RB_MMERR)) : 0;
-    if (has) fast_block_count(S, X, cbs, rw, NM, LT, Z, mapq_fail, s ? 3 : 0, rel, jlo, jhi, mmf, P.err_flag);
+    const bool umi = EXT && P.umi_mode;
+    const bool holes = umi && (fl & RAER_RB_UMI_HOLES);
+    const int shadow = umi ? (int)rec[FR_B2] : 0;  // positions below belong to an earlier read of the same UMI
+    auto umi_skip = [&]() -> uint32_t {            // reads with holes: per base, minus the positions that stay theirs
+        uint32_t m = 0;
+        for (int j = max(jlo, 0); j < min(jhi, 8); ++j) {
+            const int p = X.t0 + rel + j;
+            if (p < shadow && !umi_is_hole(P, (int)rec[FR_B3], p)) m |= 1u << (j << 2);
+        }
+        return m;
+    };
+    const int plo = (umi && !holes) ? min(max(shadow - X.t0, 0), X.tw) : 0;
+    // a read without holes is simply absent below plo (its coverage events were clipped there too)
+    if (has) fast_block_count(S, X, cbs, rw, NM, LT, Z, mapq_fail, s ? 3 : 0, rel, max(jlo, plo - rel), jhi, mmf, P.err_flag, holes ? umi_skip() : 0u);
     // ... and a call for the rare item that straddles two aligned blocks
     while (!simple && has && k < n && y < q1) {
         next_block();
-        if (has) fast_block_count_call(S, X, cbs, rw, NM, LT, Z, mapq_fail, s ? 3 : 0, rel, jlo, jhi, mmf, P.err_flag);
+        if (has)
+            fast_block_count_call(S, X, cbs, rw, NM, LT, Z, mapq_fail, s ? 3 : 0, rel, max(jlo, plo - rel), jhi, mmf, P.err_flag,
+                                  holes ? umi_skip() : 0u);
     }
 }
 
@@ -277,6 +304,15 @@ __device__ __forceinline__ int fast_stage(const PlpParams& P, const FastSmem& S,
     if (mapq < P.min_mapq[f]) fl |= STF_MAPQ_FAIL;
     const uint32_t* cg = P.cigar + (unsigned)b.x;
     uint32_t* dl = S.cnt + (size_t)((f * 2 + s) * 4) * S.WS;
+    // bulk UMI mode: positions below `shadow` belong to an earlier read of the same UMI (src/plp.c:738): this read is
+    // absent there. Without holes the read is simply clipped; with holes the items sort it out base by base.
+    int shadow = 0;
+    if (EXT && P.umi_mode) {
+        shadow = (unsigned)b.w == 0xffffffffu ? 0x7fffffff : b.w;
+        rec[FR_B2] = (uint32_t)shadow;
+        rec[FR_B3] = (uint32_t)r;
+        if (bits & RAER_RB_UMI_HOLES) shadow = 0;
+    }
     int x = a.x, y = 0;
     int qs = 0, tail = 0, nblk = 0, other = 0;
     int qlo = 0x7fffffff, qhi = 0;  // query bases whose positions fall inside the tile
@@ -294,7 +330,7 @@ __device__ __forceinline__ int fast_stage(const PlpParams& P, const FastSmem& S,
         }
         if ((0x181 >> op) & 1) {
             // coverage events of the aligned block, clipped to the tile (and to the bases the read really has)
-            const int lo = max(x, X.t0), h2 = min(x + min(len, lq - y), t1);
+            const int lo = max(max(x, X.t0), shadow), h2 = min(x + min(len, lq - y), t1);
             if (lo < h2) {
                 red_add(dl + (lo - X.t0), 1u);
                 red_add(dl + (h2 - X.t0), 0xffffffffu);
@@ -463,6 +499,12 @@ __device__ __forceinline__ void fast_pair(const PlpParams& P, const FastSmem& S,
     }
     // read base N (src/plp.c:718); nX or dropped bases are not part of the statistics
     valid = valid && code != 15 && bq >= X.minbq;
+    if (EXT && P.umi_mode && valid) {  // an earlier read of the same UMI takes this site (src/plp.c:738)
+        const int r = ordinal + (int)P.file_off[(fl >> FRF_FILE_SHIFT) & 0x3f];
+        const unsigned sh = __ldg(&P.hdr[r].aux);
+        const int shadow = sh == 0xffffffffu ? 0x7fffffff : (int)sh;
+        if (p < shadow && !((fl & RAER_RB_UMI_HOLES) && umi_is_hole(P, r, p))) valid = false;
+    }
     if (EXT && valid) {  // the remaining filters of check_read_filters, as k_pileup_tiles evaluates them
         ReadCtx c;
         c.n_cigar = n;

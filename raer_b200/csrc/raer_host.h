@@ -94,6 +94,7 @@ struct IngestConf {
     bool sc = false;
     const std::unordered_map<std::string, int>* cb_index = nullptr;  // barcode -> 1-based column
     std::string cb_tag, umi_tag;                                     // empty = not configured
+    bool bulk_umi = false;  // pileup_sites(umi_tag = ...): first read per UMI, site, strand and file (src/plp.c:622-646)
     int fixed_cb = 0;  // Smart-seq2 mode: every read of this BAM belongs to this whitelist column (src/sc-plp.c:245-246)
     int64_t target_reads = 1 << 21;                                  // reads per batch over all files
 };
@@ -128,6 +129,12 @@ struct FilePending {
     std::priority_queue<int, std::vector<int>, std::greater<int>> live_ends;
     int live_tid = -1;
     int64_t n_aligned_bases = 0;
+    // bulk UMI mode: earlier reads of each (strand, UMI) that can still be in the pileup, and per read the
+    // positions inside its shadow that no earlier read of its group takes (rare: needs an N in a duplicate)
+    struct UmiLive { int pos, end; bool has_n; std::vector<uint32_t> cigar; std::vector<uint8_t> seq; int l_qseq; };
+    std::unordered_map<std::string, std::vector<UmiLive>> umi_groups;
+    int umi_tid = -1;
+    std::unordered_map<int64_t, std::vector<int32_t>> umi_holes;  // ordinal -> positions
 };
 
 // Owned, host-resident batch (pinned when a device is present)
@@ -142,6 +149,7 @@ struct PackedBatch {
     int32_t* pair_b = nullptr;
     int32_t* cb = nullptr;
     uint32_t* umi = nullptr;
+    std::vector<int32_t> umi_holes;  // bulk UMI mode: (read index, position) pairs, sorted by read index
     size_t cap_reads = 0, cap_cigar = 0, cap_sq = 0, cap_pairs = 0;
     bool pinned = false;
     void reserve(size_t reads, size_t cig, size_t sq, bool sc);

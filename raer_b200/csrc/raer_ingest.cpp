@@ -552,6 +552,26 @@ int64_t Ingest::aligned_bases() const {
 }
 
 // Reads the next record that survives the prefilter into fp.look. Returns false at EOF / error.
+// nt16 code of the base a pileup entry of this read shows at reference position p (pos <= p < end), the way htslib's
+// resolve_cigar2 assigns qpos: inside an aligned block the aligned base, inside a deletion / ref-skip the next
+// query base; 15 (N) when that offset lies beyond the read.
+static int umi_code_at(const std::vector<uint32_t>& cig, const std::vector<uint8_t>& seq, int l_qseq, int pos, int p) {
+    int x = pos, y = 0;
+    for (uint32_t w : cig) {
+        const int op = (int)(w & 0xf), len = (int)(w >> 4);
+        if (op == 0 || op == 7 || op == 8) {
+            if (p < x + len) { const int q = y + (p - x); return q < l_qseq ? (seq[q >> 1] >> ((~q & 1) << 2)) & 0xf : 15; }
+            x += len; y += len;
+        } else if (op == 2 || op == 3) {
+            if (p < x + len) return y < l_qseq ? (seq[y >> 1] >> ((~y & 1) << 2)) & 0xf : 15;
+            x += len;
+        } else if (op == 1 || op == 4) {
+            y += len;
+        }
+    }
+    return 15;
+}
+
 bool Ingest::parse_one(int fi) {
     FilePending& F = *files_[fi];
     BamRecView r;
@@ -680,6 +700,69 @@ bool Ingest::parse_one(int fi) {
                     it = (it->second.tid != r.tid || it->second.end < F.prev_pos) ? F.olap.erase(it) : std::next(it);
             }
         }
+        if (conf_.bulk_umi) {
+            // check_umi (src/plp.c:622-646, called at :738 before the filter verdict is used): at every site the first
+            // entry (BAM order) of each UMI per strand and file goes on, later ones are skipped; an entry takes part if
+            // its base character is not N, whatever the filters say, deletions and ref-skips included. The reads are
+            // coordinate sorted, so for this read the positions taken by earlier reads of its group form a prefix of
+            // its span (hdr.aux), except where every earlier read shows an N (umi_holes).
+            const char* u = aux_z(r, conf_.umi_tag);
+            if (F.umi_tid != r.tid) { F.umi_groups.clear(); F.umi_tid = r.tid; }
+            if (!u) {
+                H.h.aux = 0xffffffffu;
+            } else {
+                std::string key(1, (bits & RAER_RB_INVERT) ? '-' : '+');
+                key += u;
+                auto& G = F.umi_groups[key];
+                size_t w = 0;
+                int max_end = r.pos;
+                bool any_n = false;
+                for (size_t k = 0; k < G.size(); ++k)
+                    if (G[k].end > r.pos) {
+                        max_end = std::max(max_end, G[k].end);
+                        any_n |= G[k].has_n;
+                        if (w != k) G[w] = std::move(G[k]);
+                        ++w;
+                    }
+                G.resize(w);
+                const int s_end = std::min(max_end, (int)H.h.end);
+                if (s_end > r.pos) {
+                    if (!any_n) {
+                        H.h.aux = (uint32_t)s_end;
+                    } else {
+                        std::vector<char> taken((size_t)(s_end - r.pos), 0);
+                        for (const auto& e : G) {
+                            const int hi = std::min(e.end, s_end);
+                            for (int p = r.pos; p < hi; ++p)
+                                if (!e.has_n || umi_code_at(e.cigar, e.seq, e.l_qseq, e.pos, p) != 15) taken[p - r.pos] = 1;
+                        }
+                        int last = -1;
+                        for (int p = s_end - 1; p >= r.pos; --p) if (taken[p - r.pos]) { last = p; break; }
+                        if (last >= 0) {
+                            H.h.aux = (uint32_t)(last + 1);
+                            std::vector<int32_t> holes;
+                            for (int p = r.pos; p <= last; ++p) if (!taken[p - r.pos]) holes.push_back(p);
+                            if (!holes.empty()) { bits |= RAER_RB_UMI_HOLES; F.umi_holes[H.ordinal] = std::move(holes); }
+                        }
+                    }
+                }
+                FilePending::UmiLive me;
+                me.pos = r.pos; me.end = H.h.end; me.l_qseq = r.l_qseq;
+                me.has_n = false;
+                for (int q = 0; q < r.l_qseq && !me.has_n; ++q) me.has_n = ((r.seq[q >> 1] >> ((~q & 1) << 2)) & 0xf) == 15;
+                // a read that ends in a deletion / ref-skip shows N there; treat it like a read with an N
+                if (!me.has_n && r.n_cigar) { const int lop = (int)(cig[r.n_cigar - 1] & 0xf); me.has_n = lop == 2 || lop == 3; }
+                if (me.has_n) { me.cigar = cig; me.seq.assign(r.seq, r.seq + (r.l_qseq + 1) / 2); }
+                G.push_back(std::move(me));
+                if (F.umi_groups.size() > 2000000) {  // drop the groups whose reads have all left the pileup
+                    for (auto it = F.umi_groups.begin(); it != F.umi_groups.end();) {
+                        bool live = false;
+                        for (const auto& e : it->second) live |= e.end > r.pos;
+                        it = live ? std::next(it) : F.umi_groups.erase(it);
+                    }
+                }
+            }
+        }
         H.h.bits = bits;
         F.prev_tid = r.tid;
         F.prev_pos = r.pos;
@@ -805,6 +888,7 @@ bool Ingest::next_batch(PackedBatch& out) {
         if (!any_left) return false;
     }
     out.reserve(n_reads, n_cig, n_sq, conf_.sc);
+    out.umi_holes.clear();
     out.file_off.assign(nf + 1, 0);
     size_t ro = 0, co = 0, so = 0, np = 0;
     int64_t nal = 0;
@@ -826,13 +910,18 @@ bool Ingest::next_batch(PackedBatch& out) {
                 h.cigar_off = (uint32_t)(co + (H.h.cigar_off - c0));
                 h.sq_off = (uint32_t)(so + (H.h.sq_off - s0));
                 h.mate = (H.mate_ord >= front_ord) ? (int32_t)(ro + (size_t)(H.mate_ord - front_ord)) : -1;
-                h.aux = (uint32_t)(ro + (k - F.front));
+                if (!conf_.bulk_umi) h.aux = (uint32_t)(ro + (k - F.front));  // bulk UMI mode keeps its verdict there
                 size_t bi = ro + (k - F.front);
                 out.hdr[bi] = h;
                 me = std::max(me, (int)h.end);
                 out.maxend[bi] = me;
                 if (h.mate >= 0) out.pair_b[np++] = (int32_t)bi;
                 if (conf_.sc) { out.cb[bi] = H.cb; out.umi[bi] = H.umi; }
+                if (h.bits & RAER_RB_UMI_HOLES) {
+                    auto it = F.umi_holes.find(H.ordinal);
+                    if (it != F.umi_holes.end())
+                        for (int32_t hp : it->second) { out.umi_holes.push_back((int32_t)bi); out.umi_holes.push_back(hp); }
+                }
                 if (h.end > win_beg_) max_end = std::max(max_end, (int)h.end);
             }
             ro += upto[i] - F.front;
@@ -860,11 +949,16 @@ bool Ingest::next_batch(PackedBatch& out) {
     b.cb = conf_.sc ? out.cb : nullptr;
     b.umi = conf_.sc ? out.umi : nullptr;
     b.n_aligned_bases = nal;
+    b.umi_holes = out.umi_holes.empty() ? nullptr : out.umi_holes.data();
+    b.n_umi_holes = (int64_t)(out.umi_holes.size() / 2);
     // retire reads that end before the boundary (front only, so ordinals stay contiguous) and compact pools
     win_beg_ = boundary;
     for (int i = 0; i < nf; ++i) {
         FilePending& F = *files_[i];
-        while (F.front < upto[i] && F.reads[F.front].keep_end <= boundary) ++F.front;
+        while (F.front < upto[i] && F.reads[F.front].keep_end <= boundary) {
+            if (F.reads[F.front].h.bits & RAER_RB_UMI_HOLES) F.umi_holes.erase(F.reads[F.front].ordinal);
+            ++F.front;
+        }
         if (F.front == F.reads.size()) {
             F.reads.clear(); F.front = 0; F.cigar.clear(); F.seq.clear(); F.qual.clear();
         } else if (F.front > (1u << 16) && F.front * 2 > F.reads.size()) {

@@ -79,6 +79,7 @@ struct raer_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6];
     DevBuf hdr, maxend, cigar, seq, qual, pair_b, mask;
+    DevBuf umi_holes;                      // bulk UMI mode: (read, position) pairs that stay counted
     DevBuf ov_scratch;                     // mate overlap: compacted list of the CIGAR-walking pairs
     DevBuf tile_idx, tile_list;            // k_pileup_fast: counts | offsets | cursors, and the per-tile read lists
     DevBuf tile_ranges, tile_rows, small;  // small: tile_counter(4) | pad | row_counter(8) | err(4)
@@ -120,7 +121,7 @@ extern "C" void raer_ctx_destroy(raer_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->hdr, &c->maxend, &c->cigar, &c->seq, &c->qual, &c->pair_b, &c->mask, &c->tile_ranges, &c->tile_rows, &c->tile_idx, &c->tile_list, &c->ov_scratch,
+    for (DevBuf* b : {&c->hdr, &c->maxend, &c->cigar, &c->seq, &c->qual, &c->pair_b, &c->mask, &c->tile_ranges, &c->tile_rows, &c->tile_idx, &c->tile_list, &c->ov_scratch, &c->umi_holes,
                       &c->small, &c->row_pos, &c->row_meta, &c->row_stats, &c->row_counts, &c->row_alt, &c->ref})
         b->release();
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -209,7 +210,14 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
     P.report_multiallelic = conf->report_multiallelic; P.want_stats = conf->want_stats;
     P.ftrim_5p = conf->ftrim_5p; P.ftrim_3p = conf->ftrim_3p; P.min_af = conf->min_af;
     P.any_okv = 0;
-    P.fast = !(conf->trim_5p > 0 || conf->trim_3p > 0 || conf->ftrim_5p > 0 || conf->ftrim_3p > 0 || conf->splice_dist ||
+    P.umi_mode = conf->umi_mode;
+    P.umi_holes = b->umi_holes;
+    P.n_umi_holes = (int)b->n_umi_holes;
+    if (P.umi_mode && !P.use_fast) {
+        set_error("umi_tag in pileup_sites needs the fast tile kernel (min_base_quality <= 128, coverage <= 65535)");
+        return RAER_ERR_LIMIT;
+    }
+    P.fast = !(conf->umi_mode || conf->trim_5p > 0 || conf->trim_3p > 0 || conf->ftrim_5p > 0 || conf->ftrim_3p > 0 || conf->splice_dist ||
                conf->min_overhang || conf->indel_dist || conf->n_mm_type > 0 || conf->n_mm > 0);
     for (int i = 0; i < nf; ++i) {
         P.min_mapq[i] = conf->min_mapq[i];
@@ -406,6 +414,10 @@ static int host_submit(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_
         CK(cudaMemcpyAsync(c->qual.p, hb->qual, (size_t)hb->n_sq_bytes * 2, cudaMemcpyHostToDevice, c->stream));
     }
     if (hb->n_pairs) CK(cudaMemcpyAsync(c->pair_b.p, hb->pair_b, (size_t)hb->n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+    if (hb->n_umi_holes) {
+        if ((rc = c->umi_holes.ensure((size_t)hb->n_umi_holes * 8))) return rc;
+        CK(cudaMemcpyAsync(c->umi_holes.p, hb->umi_holes, (size_t)hb->n_umi_holes * 8, cudaMemcpyHostToDevice, c->stream));
+    }
     const uint32_t* d_mask = nullptr;
     if (conf->site_mask) {
         size_t words = ((size_t)conf->mask_bits + 31) / 32;
@@ -416,6 +428,7 @@ static int host_submit(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_
     cudaEventRecord(c->ev[1], c->stream);
     c->p_conf = *conf;
     c->p_dev = *hb;
+    c->p_dev.umi_holes = hb->n_umi_holes ? (const int32_t*)c->umi_holes.p : nullptr;
     c->p_file_off.assign(hb->file_off, hb->file_off + nf + 1);
     c->p_dev.file_off = c->p_file_off.data();
     c->p_dev.hdr = (const raer_read_hdr*)c->hdr.p; c->p_dev.maxend = (const int32_t*)c->maxend.p;
@@ -648,7 +661,6 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
         set_error("invalid arguments"); return RAER_ERR_ARG;
     }
     if (a->nbam > RAER_MAX_FILES) { set_error("at most %d BAM files per call", RAER_MAX_FILES); return RAER_ERR_LIMIT; }
-    if (a->umi_tag) { set_error("umi_tag in pileup_sites is not implemented on the device path yet"); return RAER_ERR_LIMIT; }
     if (raer_device_count() <= 0) { set_error("no usable CUDA device (the product has no CPU path)"); return RAER_ERR_NO_DEVICE; }
     const int nf = a->nbam;
     out->nbam = nf;
@@ -680,6 +692,7 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
     ic.libtype.assign(a->libtype, a->libtype + nf);
     for (int lt : ic.libtype)
         if (lt < 0 || lt > 2) { set_error("invert read orientation failure"); return RAER_ERR; }
+    if (a->umi_tag) { ic.bulk_umi = true; ic.umi_tag = a->umi_tag; }
     ic.regidx = has_ridx ? &ridx : nullptr;
     if (const char* e = getenv("RAER_BATCH_READS")) {  // reads per batch (tests exercise batch seams with small values)
         long v = atol(e);
@@ -707,6 +720,7 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
     bc.report_multiallelic = a->lgl_args[0];
     bc.remove_overlaps = ic.remove_overlaps;
     bc.want_stats = 1;
+    bc.umi_mode = a->umi_tag ? 1 : 0;
     for (int i = 0; i < nf; ++i) { bc.min_mapq[i] = a->min_mapq[i]; bc.only_keep_variants[i] = a->only_keep_variants[i]; }
 
     const std::vector<std::string>& names = ing.names();
@@ -846,6 +860,7 @@ extern "C" int raer_ingest_summary(const raer_pileup_args* a, int64_t target_rea
     ic.n_mm = a->int_args[11];
     ic.min_overhang = a->int_args[7];
     ic.libtype.assign(a->libtype, a->libtype + nf);
+    if (a->umi_tag) { ic.bulk_umi = true; ic.umi_tag = a->umi_tag; }
     ic.regidx = has_ridx ? &ridx : nullptr;
     if (target_reads > 0) ic.target_reads = target_reads;
     raer::Ingest ing(ic);
