@@ -404,49 +404,41 @@ __device__ __forceinline__ void fast_count_chunk(const PlpParams& P, const FastS
     pref[lane] = (uint32_t)inc;
     const int tot = __shfl_sync(FULL, inc, 31);
     __syncwarp();
-    for (int itb = 0; itb < tot; itb += 64) {
-        // The trip count is warp-uniform, so the warp can be re-joined here: without it the lanes that took
-        // different paths through the previous items keep running as separate sub-warps.
-        __syncwarp();
-        const uint32_t* recA = st;
-        const uint32_t* recB = st;
-        int qA = 0, qB = 0;
-        uint32_t swA = 0, swB = 0;
-        uint2 qwA = make_uint2(0, 0), qwB = make_uint2(0, 0);
-        const int itA = itb + lane, itB = itA + 32;
-        const bool okA = itA < tot, okB = itB < tot;
-        if (okA) {
+    // Software pipeline: the loads of the next item are issued before the current one is processed, so one item per
+    // lane is always in flight while another is being worked on.
+    const uint32_t* recN = st;
+    int qN = 0;
+    uint32_t swN = 0;
+    uint2 qwN = make_uint2(0, 0);
+    bool okN = false;
+    auto fetch = [&](int it) {
+        okN = it < tot;
+        if (okN) {
             int lo = 0, hh = 31;  // smallest i with pref[i] > it
 #pragma unroll
             for (int step = 0; step < 5; ++step) {
                 const int mid = (lo + hh) >> 1;
-                if ((int)pref[mid] > itA) hh = mid; else lo = mid + 1;
+                if ((int)pref[mid] > it) hh = mid; else lo = mid + 1;
             }
-            recA = st + lo * FREC;
-            qA = ((int)recA[FR_FIRST] + itA - (lo ? (int)pref[lo - 1] : 0)) << 3;
-            const uint32_t sq = recA[FR_SQ];
-            swA = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qA >> 1)));
-            qwA = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qA));
+            recN = st + lo * FREC;
+            qN = ((int)recN[FR_FIRST] + it - (lo ? (int)pref[lo - 1] : 0)) << 3;
+            const uint32_t sq = recN[FR_SQ];
+            swN = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qN >> 1)));
+            qwN = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qN));
         }
-        if (okB) {
-            int lo = 0, hh = 31;
-#pragma unroll
-            for (int step = 0; step < 5; ++step) {
-                const int mid = (lo + hh) >> 1;
-                if ((int)pref[mid] > itB) hh = mid; else lo = mid + 1;
-            }
-            recB = st + lo * FREC;
-            qB = ((int)recB[FR_FIRST] + itB - (lo ? (int)pref[lo - 1] : 0)) << 3;
-            const uint32_t sq = recB[FR_SQ];
-            swB = __ldg(reinterpret_cast<const uint32_t*>(P.seq + sq + (qB >> 1)));
-            qwB = __ldg(reinterpret_cast<const uint2*>(P.qual + 2ull * sq + qB));
-        }
-        // both loads are in flight; one copy of the item code handles them in turn
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            if (h) __syncwarp();
-            if (h ? okB : okA) fast_item<EXT>(P, S, X, h ? recB : recA, h ? qB : qA, h ? swB : swA, h ? qwB : qwA);
-        }
+    };
+    fetch(lane);
+    for (int itb = 0; itb < tot; itb += 32) {
+        // The trip count is warp-uniform, so the warp can be re-joined here: without it the lanes that took
+        // different paths through the previous item keep running as separate sub-warps.
+        __syncwarp();
+        const uint32_t* rec = recN;
+        const int q0 = qN;
+        const uint32_t sw = swN;
+        const uint2 qw = qwN;
+        const bool ok = okN;
+        fetch(itb + 32 + lane);
+        if (ok) fast_item<EXT>(P, S, X, rec, q0, sw, qw);
     }
     __syncwarp();
 }
