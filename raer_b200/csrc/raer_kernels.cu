@@ -908,187 +908,6 @@ __device__ __forceinline__ void stage_ctx(const PlpParams& P, const uint32_t* re
 
 #include "raer_walk.cuh"  // scan_reads<PASS2, FAST>: the item-parallel walker
 
-#if 0  // superseded first version of the item walker (kept out of the build)
-template <bool PASS2, bool FAST>
-__device__ void scan_reads(const PlpParams& P, const TileSmem& S, int f, int2 rg, int t0, int t1, int span_lo,
-                           int span_hi, int lane, int wid, int nwarp) {
-    uint32_t* st = S.cigs + wid * (32 * ST_WORDS + 32);
-    uint32_t* pref = st + 32 * ST_WORDS;
-    const bool need_cov = !PASS2 && P.min_depth <= 0;
-    const bool mm_cfg = (P.n_mm_type > 0 || P.n_mm > 0);
-    for (long long base = rg.x + (long long)wid * 32; base < rg.y; base += (long long)nwarp * 32) {
-        long long r = base + lane;
-        int nq = 0;
-        if (r < rg.y) {
-            const int4* h = reinterpret_cast<const int4*>(P.hdr + r);
-            int4 a = __ldg(h);
-            if (a.y > span_lo && a.x < span_hi) {
-                int4 b = __ldg(h + 1);
-                int flag = a.z & 0xffff, mapq = (a.z >> 16) & 0xff, bits = (a.z >> 24) & 0xff;
-                int lq = a.w & 0xffff, n = (a.w >> 16) & 0xffff;
-                const uint32_t* cg = P.cigar + (unsigned)b.x;
-                uint32_t* rec = st + lane * ST_WORDS;
-                // query_start / query_end (src/plp_utils.c:52-104): soft clips at either end, hard clips skipped
-                int qs = 0, qe = lq, k;
-                for (k = 0; k < n; ++k) {
-                    uint32_t w = __ldg(cg + k);
-                    if (k < 4) rec[ST_CIG0 + k] = w;
-                    int op = cg_op(w);
-                    if (op == OP_H) continue;
-                    if (op == OP_S) qs += cg_len(w);
-                    else break;
-                }
-                for (++k; k < n && k < 4; ++k) rec[ST_CIG0 + k] = __ldg(cg + k);
-                for (k = n - 1; k >= 0; --k) {
-                    uint32_t w = __ldg(cg + k);
-                    int op = cg_op(w);
-                    if (op == OP_H) continue;
-                    if (op == OP_S) qe -= cg_len(w);
-                    else break;
-                }
-                unsigned fl = (unsigned)bits | ((unsigned)((flag >> 4) & 1) << 16);
-                if (mapq < P.min_mapq[f]) fl |= STF_MAPQ_FAIL;
-                int d5f = 0, d3f = 0;
-                if (P.ftrim_5p > 0 || P.ftrim_3p > 0) {  // check_variant_fpos, src/plp_utils.c:163-193
-                    int ql = qe - qs;
-                    if (ql <= 0) fl |= STF_FTRIM_ALL;
-                    d5f = (int)floor(P.ftrim_5p * ql);
-                    d3f = (int)ceil(P.ftrim_3p * ql);
-                }
-                rec[ST_POS] = (uint32_t)a.x;
-                rec[ST_LEN] = (uint32_t)lq | ((uint32_t)n << 16);
-                rec[ST_SQ] = (uint32_t)b.y;
-                rec[ST_FLAGS] = fl;
-                rec[ST_QSQE] = (uint32_t)qs | ((uint32_t)qe << 16);
-                rec[ST_FTRIM] = (uint32_t)(d5f & 0xffff) | ((uint32_t)d3f << 16);
-                rec[ST_CIGOFF] = (uint32_t)b.x;
-                rec[ST_ORD] = (uint32_t)(r - P.file_off[f]);
-                nq = (lq + 7) >> 3;
-            }
-        }
-        int inc = nq;
-        for (int o = 1; o < 32; o <<= 1) {
-            int v = __shfl_up_sync(FULL, inc, o);
-            if (lane >= o) inc += v;
-        }
-        pref[lane] = (uint32_t)inc;
-        const int total = __shfl_sync(FULL, inc, 31);
-        __syncwarp();
-        if (need_cov) {
-            // a pileup column exists wherever a read spans the position, deletions and ref-skips included
-            unsigned m = __ballot_sync(FULL, nq > 0);
-            while (m) {
-                int i = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t* rec = st + i * ST_WORDS;
-                int n = (int)(rec[ST_LEN] >> 16);
-                const uint32_t* cg = n <= 4 ? rec + ST_CIG0 : P.cigar + rec[ST_CIGOFF];
-                int x = (int)rec[ST_POS];
-                for (int k = 0; k < n; ++k) {
-                    uint32_t w = cg[k];
-                    if (cg_type(cg_op(w)) & 2) {
-                        int lo = max(x, t0), hi = min(x + cg_len(w), t1);
-                        for (int p = lo + lane; p < hi; p += 32) atomicOr(&S.covered[(p - t0) >> 5], 1u << ((p - t0) & 31));
-                        x += cg_len(w);
-                    }
-                }
-            }
-        }
-        for (int it = lane; it < total; it += 32) {
-            // owning read: smallest i with pref[i] > it
-            int lo = 0, hi = 31;
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if ((int)pref[mid] > it) hi = mid; else lo = mid + 1;
-            }
-            const uint32_t* rec = st + lo * ST_WORDS;
-            const int q0 = (it - (lo ? (int)pref[lo - 1] : 0)) << 3;
-            ReadCtx c;
-            stage_ctx(P, rec, c);
-            const int mapq_fail = (rec[ST_FLAGS] & STF_MAPQ_FAIL) != 0;
-            const int s = c.invert ? 1 : 0;
-            const bool mm_on = mm_cfg && (c.bits & (RAER_RB_MMFAIL | RAER_RB_MMERR));
-            const int ordinal = (int)rec[ST_ORD];
-            const uint32_t sw = __ldg(reinterpret_cast<const uint32_t*>(c.seq + (q0 >> 1)));
-            const uint2 qw = __ldg(reinterpret_cast<const uint2*>(c.qual + q0));
-            const int q1 = min(q0 + 8, c.l_qseq);
-            if (FAST) {
-                // Common case, branch-free: the 8 query bases lie inside one aligned block and only the
-                // mapq / base-quality filters are configured. Everything else takes the generic walk below.
-                int x = c.pos, y = 0, p0 = 0;
-                bool simple = false;
-                for (int k = 0; k < c.n_cigar; ++k) {
-                    uint32_t w = c.cig[k];
-                    int op = cg_op(w), len = cg_len(w);
-                    if (op == OP_M || op == OP_EQ || op == OP_X) {
-                        if (q0 < y + len) {
-                            simple = q0 >= y && q0 + 8 <= y + len;
-                            p0 = x + (q0 - y);
-                            break;
-                        }
-                        x += len;
-                        y += len;
-                    } else if (op == OP_D || op == OP_N) {
-                        x += len;
-                    } else if (op == OP_I || op == OP_S) {
-                        y += len;
-                        if (y > q0) break;
-                    }
-                }
-                if (simple) {
-                    const int rel = p0 - t0, tw = t1 - t0, minbq = P.min_bq, W = P.W;
-                    uint32_t* cbase = S.cnt + (size_t)((f * 2 + s) * RAER_NCLS) * W;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int pidx = rel + j;
-                        const int code = (sw >> (((j >> 1) << 3) + ((~j & 1) << 2))) & 0xf;
-                        const int bq = (int)(((j < 4 ? qw.x : qw.y) >> ((j & 3) << 3)) & 0xff);
-                        const bool lowq = bq < minbq;
-                        // src/plp.c:718 (N), :574 (mapq first), :580-586 (quality 0 is dropped silently)
-                        bool go = (unsigned)pidx < (unsigned)tw && code != 15 && (mapq_fail || !(lowq && bq == 0));
-                        if (PASS2) {
-                            go = go && !mapq_fail && !lowq && S.slot_of[go ? pidx : 0] != 0xffff;
-                            if (go) pass2_accumulate(P, S, c, f, s, ordinal, p0 + j, pidx, q0 + j, code);
-                        } else if (go) {
-                            int cls = cls_of_code(code);
-                            int k2 = (mapq_fail || lowq) ? RAER_CLS_X : ((c.invert && cls < 4) ? 3 - cls : cls);
-                            atomicAdd(cbase + k2 * W + CIDX(pidx, W), 1u);
-                        }
-                    }
-                    continue;
-                }
-            }
-            int x = c.pos, y = 0;
-            for (int k = 0; k < c.n_cigar && y < q1; ++k) {
-                uint32_t w = c.cig[k];
-                int op = cg_op(w), len = cg_len(w);
-                if (op == OP_M || op == OP_EQ || op == OP_X) {
-                    int qa = max(q0, y), qb = min(q1, y + len);
-                    for (int q = qa; q < qb; ++q) {
-                        int p = x + (q - y);
-                        if (p < t0 || p >= t1) continue;
-                        int pidx = p - t0;
-                        if (PASS2 && S.slot_of[pidx] == 0xffff) continue;
-                        int j = q - q0;
-                        int code = (sw >> (((j >> 1) << 3) + ((~j & 1) << 2))) & 0xf;
-                        if (code == 15) continue;  // read base N is not counted anywhere (src/plp.c:718)
-                        int bq = (int)(((j < 4 ? qw.x : qw.y) >> ((j & 3) << 3)) & 0xff);
-                        process_base<PASS2>(P, S, c, f, s, mapq_fail, mm_on, ordinal, p, pidx, q, code, bq);
-                    }
-                    x += len;
-                    y += len;
-                } else if (op == OP_D || op == OP_N) {
-                    x += len;
-                } else if (op == OP_I || op == OP_S) {
-                    y += len;
-                }
-            }
-        }
-        __syncwarp();
-    }
-}
-
-#endif
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* scratch) {
     // RAER_BLOCK threads, warp shuffle scan + smem across warps
