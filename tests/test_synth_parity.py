@@ -93,6 +93,33 @@ def test_fast_kernel_tile_width_does_not_change_results(syn, fast_w, monkeypatch
     _assert_same(got, want)
 
 
+@pytest.fixture(scope="module")
+def syn5(tmp_path_factory):
+    from raer_b200 import synth
+
+    d = tmp_path_factory.mktemp("syn5")
+    return synth.make_bulk_dataset(str(d), n_bams=5, n_contigs=2, contig_len=60_000, pairs_per_contig=2500, seed=77)
+
+
+# More files = narrower tiles (the counters of all files share the CTA's shared memory) and more (file, strand)
+# counter blocks: 5 BAMs with mixed per-file options.
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["default", "generic"])
+@pytest.mark.parametrize("kw", [
+    dict(library_type="fr-first-strand", only_keep_variants=[True, False, False, True, False], min_mapq=[0, 255, 3, 0, 0]),
+    dict(library_type=["unstranded", "fr-first-strand", "fr-second-strand", "unstranded", "fr-first-strand"], min_depth=3,
+         trim_5p=4, min_allelic_freq=0.05),
+])
+def test_five_bam_parity(syn5, kw, kernel, monkeypatch):
+    if kernel == "generic":
+        monkeypatch.setenv("RAER_KERNEL", "generic")
+    fp = FilterParam(**kw)
+    want = oracle_backend.pileup_sites(syn5["bams"], syn5["fasta"], param=fp)
+    got = _cuda()(syn5["bams"], syn5["fasta"], param=fp)
+    _assert_same(got, want)
+    assert len(want) > 300
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("batch_reads", [40, 333, 5000])
 def test_batch_seams_do_not_change_results(syn, batch_reads, monkeypatch):
