@@ -1,0 +1,85 @@
+"""calc_AEI() (reference R/calc_AEI.R:68-323) on the bundled BAMs: the assertions of the reference's
+tests/testthat/test_aei.R:22-68 on the oracle (CPU), and CUDA == oracle for every one of the 12 indices
+and their per-file (alt, ref) sums (BASELINE.json config C4 as a parity case)."""
+import math
+
+import pytest
+
+import bamtools  # noqa: F401  (tests/ on sys.path)
+import oracle_backend
+from raer_b200 import FilterParam
+from raer_b200.glue import Sites
+
+
+def _whole_contigs(fasta):
+    names, lens = [], []
+    for line in open(fasta + ".fai"):
+        f = line.split("\t")
+        names.append(f[0])
+        lens.append(int(f[1]))
+    return Sites(names, [1] * len(names), lens)
+
+
+def _mock_snps(fasta, chrom="SPCS3"):
+    """every A of one contig, as test_aei.R:16 builds it"""
+    seq, cur = [], None
+    for line in open(fasta):
+        if line.startswith(">"):
+            cur = line[1:].split()[0]
+        elif cur == chrom:
+            seq.append(line.strip())
+    s = "".join(seq)
+    pos = [i + 1 for i, c in enumerate(s) if c == "A"]
+    return Sites([chrom] * len(pos), pos)
+
+
+def test_calc_aei_reference_assertions_on_the_oracle(ext):  # test_aei.R:22-68
+    bams = [ext.bam1, ext.bam2]  # ko, wt
+    alu = _whole_contigs(ext.fasta)
+    fp = FilterParam(library_type="fr-first-strand")
+    aei = oracle_backend.calc_AEI(bams, ext.fasta, alu, param=fp)
+    assert len(aei) == 2 and len(aei["AEI"]) == 2
+    ko, wt = (aei["AEI"][k] for k in aei["AEI"])
+    assert len(ko) == 12 and len(wt) == 12
+    assert wt["A_G"] > ko["A_G"]
+    # the index is 100 * alt / (alt + ref) of the per-file sums
+    for name, idx in aei["AEI"].items():
+        for pair, v in idx.items():
+            alt, ref = aei["AEI_per_chrom"][name][pair]
+            assert (math.isnan(v) and alt + ref == 0) or v == 100.0 * alt / (alt + ref)
+    # SNP mask: with every A of SPCS3 masked the A_* sums shrink, the other pairs are untouched
+    snp = oracle_backend.calc_AEI(bams, ext.fasta, alu, snp_db=_mock_snps(ext.fasta), param=fp)
+    for name in aei["AEI"]:
+        a0, r0 = aei["AEI_per_chrom"][name]["A_G"]
+        a1, r1 = snp["AEI_per_chrom"][name]["A_G"]
+        assert r1 < r0 and a1 <= a0
+        assert snp["AEI_per_chrom"][name]["C_T"] == aei["AEI_per_chrom"][name]["C_T"]
+    # unstranded data needs gene annotation
+    with pytest.raises(ValueError):
+        oracle_backend.calc_AEI(bams, ext.fasta, alu, param=FilterParam(library_type="unstranded"))
+    genes = _whole_contigs(ext.fasta)
+    genes.strand = ["-", "+", "-"]
+    us = oracle_backend.calc_AEI(bams, ext.fasta, alu, genes, param=FilterParam(library_type="unstranded"))
+    for idx in us["AEI"].values():
+        assert idx["A_G"] > idx["T_C"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lt", ["fr-first-strand", "unstranded"])
+def test_calc_aei_cuda_equals_oracle(ext, lt):
+    from raer_b200 import api
+
+    bams = [ext.bam1, ext.bam2]
+    alu = _whole_contigs(ext.fasta)
+    genes = None
+    if lt == "unstranded":
+        genes = _whole_contigs(ext.fasta)
+        genes.strand = ["-", "+", "-"]
+    fp = FilterParam(library_type=lt)
+    want = oracle_backend.calc_AEI(bams, ext.fasta, alu, genes, snp_db=_mock_snps(ext.fasta, "DHFR"), param=fp)
+    got = api.calc_AEI(bams, ext.fasta, alu, genes, snp_db=_mock_snps(ext.fasta, "DHFR"), param=fp)
+    assert got["AEI_per_chrom"] == want["AEI_per_chrom"]
+    for name in want["AEI"]:
+        for pair, v in want["AEI"][name].items():
+            g = got["AEI"][name][pair]
+            assert (math.isnan(v) and math.isnan(g)) or g == v
