@@ -94,6 +94,31 @@ def test_fast_kernel_tile_width_does_not_change_results(syn, fast_w, monkeypatch
 
 
 @pytest.fixture(scope="module")
+def syn_deep(tmp_path_factory):
+    from raer_b200 import synth
+
+    d = tmp_path_factory.mktemp("syn_deep")
+    # 200x per BAM like the C2 workload: tiles with more flagged sites than one second-pass round holds, dense
+    # mate overlaps, many reads per tile list chunk
+    return synth.make_bulk_dataset(str(d), n_bams=2, n_contigs=2, contig_len=40_000, pairs_per_contig=40_000, seed=4711)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [
+    dict(library_type="fr-first-strand", only_keep_variants=True),  # the C2 call
+    dict(library_type="fr-second-strand", min_base_quality=30, min_depth=0),
+    dict(library_type="unstranded", trim_5p=6, trim_3p=6, splice_dist=5, indel_dist=4, min_splice_overhang=12,
+         only_keep_variants=True),
+])
+def test_c2_depth_parity(syn_deep, kw):
+    fp = FilterParam(**kw)
+    want = oracle_backend.pileup_sites(syn_deep["bams"], syn_deep["fasta"], param=fp)
+    got = _cuda()(syn_deep["bams"], syn_deep["fasta"], param=fp)
+    _assert_same(got, want)
+    assert len(want) > 5000
+
+
+@pytest.fixture(scope="module")
 def syn5(tmp_path_factory):
     from raer_b200 import synth
 
