@@ -873,10 +873,11 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
 }
 
 // ---- per-tile read lists: every read that overlaps the tile [t_beg + t*W, +W), per (tile, file)
-__device__ __forceinline__ bool tile_span(const PlpParams& P, long long r, int& f, int& tf, int& tl) {
+__device__ __forceinline__ bool tile_span(const PlpParams& P, long long r, int& f, int& tf, int& tl, int* cplx = nullptr) {
     f = 0;
     while (f + 1 < P.n_files && r >= P.file_off[f + 1]) ++f;
-    const int2 pe = __ldg(reinterpret_cast<const int2*>(P.hdr + r));
+    const int4 pe = __ldg(reinterpret_cast<const int4*>(P.hdr + r));
+    if (cplx) *cplx = ((pe.w >> 16) & 0xffff) != 1;  // more than one CIGAR operation
     if (pe.y <= P.t_beg || pe.x >= P.t_end || pe.y <= pe.x) return false;
     tf = (max(pe.x, P.t_beg) - P.t_beg) / P.W;
     tl = (min(pe.y, P.t_end) - 1 - P.t_beg) / P.W;
@@ -930,34 +931,40 @@ __global__ void k_tile_scan(const int* cnt, int* off, int* cur, int n, int* tota
             off[i] = s_carry + s_w[wid] + x - v;
             cur[i] = 0;
         }
+        // (the counts themselves are cleared by the caller once the scan is done: k_tile_fill uses them as back cursors)
         __syncthreads();
         if (threadIdx.x == 0) s_carry += s_w[32];
         __syncthreads();
     }
     if (threadIdx.x == 0) { off[n] = s_carry; *total = s_carry; }
 }
-__global__ void k_tile_fill(PlpParams P, long long n_reads, const int* off, int* cur, int* list, int cap) {
+// A (tile, file) list is filled from both ends: reads with a single CIGAR operation from the front, the others from
+// the back, so that the chunks of 32 reads the tile kernel takes are (but for one per list) all of one kind and
+// the lanes of a warp do not wait for each other's CIGAR walks.
+__global__ void k_tile_fill(PlpParams P, long long n_reads, const int* off, int* cur, int* cur_back, int* list, int cap) {
     const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    int f = 0, tf = 0, tl = -1;
-    const bool ok = r < n_reads && tile_span(P, r, f, tf, tl);
+    int f = 0, tf = 0, tl = -1, cplx = 0;
+    const bool ok = r < n_reads && tile_span(P, r, f, tf, tl, &cplx);
     const int more = __reduce_max_sync(FULL, ok ? tl - tf : -1);
     for (int k = 0; k <= min(more, TILE_AGG_STEPS); ++k) {
         const int key = (ok && tf + k <= tl) ? (tf + k) * P.n_files + f : -1;
-        const unsigned peers = __match_any_sync(FULL, key);
+        const unsigned peers = __match_any_sync(FULL, key < 0 ? -1 : key * 2 + cplx);
         const int leader = __ffs(peers) - 1;
         int first = 0;
-        if (key >= 0 && leader == lane) first = atomicAdd(&cur[key], __popc(peers));
+        if (key >= 0 && leader == lane) first = atomicAdd(cplx ? &cur_back[key] : &cur[key], __popc(peers));
         first = __shfl_sync(FULL, first, leader);
         if (key >= 0) {
-            const int slot = off[key] + first + __popc(peers & ((1u << lane) - 1u));
-            if (slot < cap) list[slot] = (int)r;
+            const int rank = first + __popc(peers & ((1u << lane) - 1u));
+            const int slot = cplx ? off[key + 1] - 1 - rank : off[key] + rank;
+            if (slot >= 0 && slot < cap) list[slot] = (int)r;
         }
     }
     for (int t = tf + TILE_AGG_STEPS + 1; t <= tl; ++t) {
         const int k2 = t * P.n_files + f;
-        const int slot = off[k2] + atomicAdd(&cur[k2], 1);
-        if (slot < cap) list[slot] = (int)r;
+        const int rank = atomicAdd(cplx ? &cur_back[k2] : &cur[k2], 1);
+        const int slot = cplx ? off[k2 + 1] - 1 - rank : off[k2] + rank;
+        if (slot >= 0 && slot < cap) list[slot] = (int)r;
     }
 }
 
@@ -987,9 +994,10 @@ extern "C" int raer_fast_index_count(PlpParams* P, long long n_reads, int* cnt, 
     k_tile_scan<<<1, 1024, 0, st>>>(cnt, off, cur, n, total);
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
-extern "C" int raer_fast_index_fill(PlpParams* P, long long n_reads, const int* off, int* cur, int* list, int cap,
+extern "C" int raer_fast_index_fill(PlpParams* P, long long n_reads, const int* off, int* cur, int* cur_back, int* list, int cap,
                                     cudaStream_t st) {
-    if (n_reads > 0) k_tile_fill<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(*P, n_reads, off, cur, list, cap);
+    cudaMemsetAsync(cur_back, 0, (size_t)P->n_tiles * P->n_files * sizeof(int), st);
+    if (n_reads > 0) k_tile_fill<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(*P, n_reads, off, cur, cur_back, list, cap);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

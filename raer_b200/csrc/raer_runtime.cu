@@ -24,7 +24,8 @@ extern "C" int raer_launch_overlap(const raer_read_hdr* hdr, const uint32_t* cig
 extern "C" size_t raer_tile_smem_bytes(int n_files, int W, int S, int* cnt_words, int* slot_words);
 extern "C" int raer_fast_width(int n_files);
 extern "C" int raer_fast_index_count(PlpParams* P, long long n_reads, int* cnt, int* off, int* cur, int* total, cudaStream_t st);
-extern "C" int raer_fast_index_fill(PlpParams* P, long long n_reads, const int* off, int* cur, int* list, int cap, cudaStream_t st);
+extern "C" int raer_fast_index_fill(PlpParams* P, long long n_reads, const int* off, int* cur, int* cur_back, int* list, int cap,
+                                    cudaStream_t st);
 extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* launches, cudaEvent_t e0, cudaEvent_t e1);
 
 #define CK(call)                                                                              \
@@ -280,7 +281,7 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
             int r = raer_fast_index_count(&P, n_reads, cnt, off, cur, d_total, c->stream);
             if (r < 0) { set_error("tile index kernels failed"); return RAER_ERR_CUDA; }
             nl += r;
-            r = raer_fast_index_fill(&P, n_reads, off, cur, (int*)c->tile_list.p, cap, c->stream);
+            r = raer_fast_index_fill(&P, n_reads, off, cur, cnt, (int*)c->tile_list.p, cap, c->stream);
             if (r < 0) { set_error("tile index kernels failed"); return RAER_ERR_CUDA; }
             nl += r;
             P.tile_off = off;
