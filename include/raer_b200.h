@@ -224,7 +224,7 @@ raer_ctx* raer_ctx_create(int32_t device);
 void raer_ctx_destroy(raer_ctx* ctx);
 /* stream used by the context (cudaStream_t) so that callers can time with events on it */
 void* raer_ctx_stream(raer_ctx* ctx);
-/* per-launch CUDA-event timing of the dominant kernel (k_pileup_tiles) for the roofline figure */
+/* per-launch CUDA-event timing of the dominant kernel (the tile kernel: k_pileup_fast or k_pileup_tiles) for the roofline figure */
 void raer_ctx_profile(raer_ctx* ctx, int on);
 int raer_ctx_profile_read(raer_ctx* ctx, double* ms_sum, int64_t* n_launches);
 /* install the reference bases of one contig (raw FASTA bytes, case preserved) for later batches */
