@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <future>
 #include <queue>
 #include <string>
 #include <unordered_map>
@@ -49,7 +50,8 @@ public:
     int64_t records_read() const { return n_records_; }
 
 private:
-    bool fill();  // inflate the next group of BGZF blocks into ubuf_
+    bool fill();  // next group of inflated BGZF blocks into ubuf_; the group after it is inflated in the background
+    int produce(std::vector<uint8_t>& out);  // read + inflate one group into out: 1 data, 0 end of file, -1 error
     bool read_header();
     bool need(size_t n);
     FILE* fp_ = nullptr;
@@ -65,6 +67,11 @@ private:
     int r_tid_ = -1, r_beg_ = 0, r_end_ = 0;
     double t_decode_ = 0;
     int64_t n_records_ = 0;
+    // prefetch: while the parser walks ubuf_, a task inflates the following group (it owns fp_, cbuf_, c_off_,
+    // file_eof_ and t_decode_ until fill() collects it)
+    std::vector<uint8_t> pf_buf_;
+    std::future<int> pf_;
+    bool drained_ = false;  // produce() reported the end of the file
 };
 
 // sorted, merged-on-query interval index (htslib regidx semantics: 0-based inclusive)

@@ -43,6 +43,7 @@ static inline uint64_t le64(const uint8_t* p) { return (uint64_t)le32(p) | ((uin
 
 // ------------------------------------------------------------------------------------- BamStream
 BamStream::~BamStream() {
+    if (pf_.valid()) pf_.wait();  // the prefetch task reads fp_
     if (fp_) fclose(fp_);
 }
 
@@ -53,98 +54,120 @@ struct BlockJob {
     uint32_t u_len;
 };
 
-bool BamStream::fill() {
+int BamStream::produce(std::vector<uint8_t>& out) {
     double t0 = now_seconds();
-    const size_t kChunk = 32u << 20, kMaxOut = 96u << 20;
-    // refill the compressed buffer
-    if (!file_eof_ && cbuf_.size() - c_off_ < (1u << 20)) {
-        if (c_off_ > 0) {
-            cbuf_.erase(cbuf_.begin(), cbuf_.begin() + c_off_);
-            c_off_ = 0;
-        }
-        size_t old = cbuf_.size();
-        cbuf_.resize(old + kChunk);
-        size_t got = fread(cbuf_.data() + old, 1, kChunk, fp_);
-        cbuf_.resize(old + got);
-        if (got < kChunk) file_eof_ = true;
-    }
+    const size_t kChunk = 32u << 20, kMaxOut = 12u << 20;  // small groups: the next one inflates while this one is parsed
+    out.clear();
     std::vector<BlockJob> jobs;
-    size_t leftover = ubuf_.size() - u_off_;
-    size_t out_off = leftover, o = c_off_;
-    while (o + 18 <= cbuf_.size() && out_off < kMaxOut) {
-        const uint8_t* h = cbuf_.data() + o;
-        if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { set_error("corrupt BGZF block"); return false; }
-        int xlen = le16(h + 10);
-        if (o + 12 + xlen > cbuf_.size()) break;
-        int bsize = -1;
-        for (int e = 0; e + 4 <= xlen;) {
-            int slen = le16(h + 12 + e + 2);
-            if (h[12 + e] == 'B' && h[13 + e] == 'C' && slen == 2) bsize = le16(h + 12 + e + 4);
-            e += 4 + slen;
-        }
-        if (bsize < 0) { set_error("BGZF block without BC field"); return false; }
-        if (o + bsize + 1 > cbuf_.size()) break;
-        uint32_t isize = le32(h + bsize + 1 - 4);
-        BlockJob j;
-        j.c_off = o + 12 + xlen;
-        j.c_len = (uint32_t)(bsize + 1 - 12 - xlen - 8);
-        j.u_off = out_off;
-        j.u_len = isize;
-        if (isize) jobs.push_back(j);
-        out_off += isize;
-        o += bsize + 1;
-    }
-    if (o == c_off_) {
-        if (file_eof_ && cbuf_.size() - c_off_ > 0 && cbuf_.size() - c_off_ < 18) return false;
-        if (file_eof_) return false;
-        // a block larger than what is buffered cannot happen (blocks are <= 64 KiB); force another read
-        if (cbuf_.size() - c_off_ >= (1u << 20)) { set_error("BGZF framing error"); return false; }
-    }
-    c_off_ = o;
-    // compact the inflated buffer and make room
-    if (u_off_ > 0) {
-        memmove(ubuf_.data(), ubuf_.data() + u_off_, leftover);
-        u_off_ = 0;
-    }
-    ubuf_.resize(out_off);
-    if (!jobs.empty()) {
-        int nt = std::max(1, std::min<int>(threads_, (int)jobs.size() / 4 + 1));
-        std::vector<int> status(nt, 0);
-        auto work = [&](int t) {
-            z_stream zs;
-            memset(&zs, 0, sizeof(zs));
-            if (inflateInit2(&zs, -15) != Z_OK) { status[t] = -1; return; }
-            for (size_t i = t; i < jobs.size(); i += nt) {
-                const BlockJob& j = jobs[i];
-                inflateReset(&zs);
-                zs.next_in = cbuf_.data() + j.c_off;
-                zs.avail_in = j.c_len;
-                zs.next_out = ubuf_.data() + j.u_off;
-                zs.avail_out = j.u_len;
-                int zr = inflate(&zs, Z_FINISH);
-                if (zr != Z_STREAM_END || zs.avail_out != 0) { status[t] = -1; break; }
+    size_t out_off = 0;
+    while (true) {
+        // refill the compressed buffer
+        if (!file_eof_ && cbuf_.size() - c_off_ < (1u << 20)) {
+            if (c_off_ > 0) {
+                cbuf_.erase(cbuf_.begin(), cbuf_.begin() + c_off_);
+                c_off_ = 0;
             }
-            inflateEnd(&zs);
-        };
-        if (nt == 1) work(0);
-        else {
-            std::vector<std::thread> th;
-            for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
-            for (auto& x : th) x.join();
+            size_t old = cbuf_.size();
+            cbuf_.resize(old + kChunk);
+            size_t got = fread(cbuf_.data() + old, 1, kChunk, fp_);
+            cbuf_.resize(old + got);
+            if (got < kChunk) file_eof_ = true;
         }
-        for (int s : status)
-            if (s) { set_error("inflate failed"); return false; }
+        size_t o = c_off_;
+        while (o + 18 <= cbuf_.size() && out_off < kMaxOut) {
+            const uint8_t* h = cbuf_.data() + o;
+            if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { set_error("corrupt BGZF block"); return -1; }
+            int xlen = le16(h + 10);
+            if (o + 12 + xlen > cbuf_.size()) break;
+            int bsize = -1;
+            for (int e = 0; e + 4 <= xlen;) {
+                int slen = le16(h + 12 + e + 2);
+                if (h[12 + e] == 'B' && h[13 + e] == 'C' && slen == 2) bsize = le16(h + 12 + e + 4);
+                e += 4 + slen;
+            }
+            if (bsize < 0) { set_error("BGZF block without BC field"); return -1; }
+            if (o + bsize + 1 > cbuf_.size()) break;
+            uint32_t isize = le32(h + bsize + 1 - 4);
+            BlockJob j;
+            j.c_off = o + 12 + xlen;
+            j.c_len = (uint32_t)(bsize + 1 - 12 - xlen - 8);
+            j.u_off = out_off;
+            j.u_len = isize;
+            if (isize) jobs.push_back(j);
+            out_off += isize;
+            o += bsize + 1;
+        }
+        const bool progressed = o != c_off_;
+        c_off_ = o;
+        if (!jobs.empty()) break;
+        if (file_eof_) {
+            // nothing but (possibly) empty blocks and a tail shorter than a block header are left
+            if (!progressed || c_off_ + 18 > cbuf_.size()) { t_decode_ += now_seconds() - t0; return 0; }
+            continue;
+        }
+        // a block larger than what is buffered cannot happen (blocks are <= 64 KiB); only empty blocks so far: read on
+        if (!progressed && cbuf_.size() - c_off_ >= (1u << 20)) { set_error("BGZF framing error"); return -1; }
     }
+    out.resize(out_off);
+    int nt = std::max(1, std::min<int>(threads_, (int)jobs.size() / 4 + 1));
+    std::vector<int> status(nt, 0);
+    auto work = [&](int t) {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) { status[t] = -1; return; }
+        for (size_t i = t; i < jobs.size(); i += nt) {
+            const BlockJob& j = jobs[i];
+            inflateReset(&zs);
+            zs.next_in = cbuf_.data() + j.c_off;
+            zs.avail_in = j.c_len;
+            zs.next_out = out.data() + j.u_off;
+            zs.avail_out = j.u_len;
+            int zr = inflate(&zs, Z_FINISH);
+            if (zr != Z_STREAM_END || zs.avail_out != 0) { status[t] = -1; break; }
+        }
+        inflateEnd(&zs);
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    for (int s : status)
+        if (s) { set_error("inflate failed"); return -1; }
     t_decode_ += now_seconds() - t0;
-    return out_off > leftover || !file_eof_;
+    return 1;
+}
+
+bool BamStream::fill() {
+    if (drained_) return false;
+    int rc;
+    std::vector<uint8_t> grp;
+    if (pf_.valid()) {
+        rc = pf_.get();
+        grp.swap(pf_buf_);
+    } else {
+        rc = produce(grp);
+    }
+    if (rc <= 0) { drained_ = true; return false; }
+    // keep the unread tail of the previous group (a record can straddle two groups) in front of the new bytes
+    const size_t leftover = ubuf_.size() - u_off_;
+    if (leftover == 0) {
+        ubuf_.swap(grp);
+    } else {
+        if (u_off_ > 0) memmove(ubuf_.data(), ubuf_.data() + u_off_, leftover);
+        ubuf_.resize(leftover);
+        ubuf_.insert(ubuf_.end(), grp.begin(), grp.end());
+    }
+    u_off_ = 0;
+    // the next group is inflated while the caller parses this one
+    pf_ = std::async(std::launch::async, [this]() { return produce(pf_buf_); });
+    return true;
 }
 
 bool BamStream::need(size_t n) {
-    while (ubuf_.size() - u_off_ < n) {
-        size_t before = ubuf_.size() - u_off_;
+    while (ubuf_.size() - u_off_ < n)
         if (!fill()) return false;
-        if (ubuf_.size() - u_off_ == before && file_eof_ && c_off_ >= cbuf_.size()) return false;
-    }
     return true;
 }
 
@@ -230,6 +253,9 @@ bool BamStream::set_region(const char* bai_path, int tid, int beg, int end) {
         o += 8L * n_intv;
     }
     if (!found) { region_done_ = true; return true; }  // no alignments on that contig
+    if (pf_.valid()) pf_.get();  // the prefetch started after the header holds bytes from the wrong place
+    pf_buf_.clear();
+    drained_ = false;
     if (fseek(fp_, (long)(voff >> 16), SEEK_SET) != 0) return false;
     cbuf_.clear(); c_off_ = 0; file_eof_ = false;
     ubuf_.clear(); u_off_ = 0;
@@ -890,45 +916,72 @@ bool Ingest::next_batch(PackedBatch& out) {
     out.reserve(n_reads, n_cig, n_sq, conf_.sc);
     out.umi_holes.clear();
     out.file_off.assign(nf + 1, 0);
-    size_t ro = 0, co = 0, so = 0, np = 0;
-    int64_t nal = 0;
+    // where each file's share of the batch starts, then the files are copied side by side
+    std::vector<size_t> ro_of(nf + 1, 0), co_of(nf + 1, 0), so_of(nf + 1, 0);
     for (int i = 0; i < nf; ++i) {
         FilePending& F = *files_[i];
-        out.file_off[i] = (int64_t)ro;
+        size_t nr_i = 0, nc_i = 0, ns_i = 0;
         if (upto[i] > F.front) {
             size_t c0 = F.reads[F.front].h.cigar_off, s0 = F.reads[F.front].h.sq_off;
             size_t c1 = upto[i] < F.reads.size() ? F.reads[upto[i]].h.cigar_off : F.cigar.size();
             size_t s1 = upto[i] < F.reads.size() ? F.reads[upto[i]].h.sq_off : F.seq.size();
-            memcpy(out.cigar + co, F.cigar.data() + c0, (c1 - c0) * 4);
-            memcpy(out.seq + so, F.seq.data() + s0, s1 - s0);
-            memcpy(out.qual + 2 * so, F.qual.data() + 2 * s0, 2 * (s1 - s0));
-            int64_t front_ord = F.reads[F.front].ordinal;
-            int me = INT_MIN;
-            for (size_t k = F.front; k < upto[i]; ++k) {
-                const HostRead& H = F.reads[k];
-                raer_read_hdr h = H.h;
-                h.cigar_off = (uint32_t)(co + (H.h.cigar_off - c0));
-                h.sq_off = (uint32_t)(so + (H.h.sq_off - s0));
-                h.mate = (H.mate_ord >= front_ord) ? (int32_t)(ro + (size_t)(H.mate_ord - front_ord)) : -1;
-                if (!conf_.bulk_umi) h.aux = (uint32_t)(ro + (k - F.front));  // bulk UMI mode keeps its verdict there
-                size_t bi = ro + (k - F.front);
-                out.hdr[bi] = h;
-                me = std::max(me, (int)h.end);
-                out.maxend[bi] = me;
-                if (h.mate >= 0) out.pair_b[np++] = (int32_t)bi;
-                if (conf_.sc) { out.cb[bi] = H.cb; out.umi[bi] = H.umi; }
-                if (h.bits & RAER_RB_UMI_HOLES) {
-                    auto it = F.umi_holes.find(H.ordinal);
-                    if (it != F.umi_holes.end())
-                        for (int32_t hp : it->second) { out.umi_holes.push_back((int32_t)bi); out.umi_holes.push_back(hp); }
-                }
-                if (h.end > win_beg_) max_end = std::max(max_end, (int)h.end);
-            }
-            ro += upto[i] - F.front;
-            co += c1 - c0;
-            so += s1 - s0;
+            nr_i = upto[i] - F.front; nc_i = c1 - c0; ns_i = s1 - s0;
         }
+        ro_of[i + 1] = ro_of[i] + nr_i; co_of[i + 1] = co_of[i] + nc_i; so_of[i + 1] = so_of[i] + ns_i;
+        out.file_off[i] = (int64_t)ro_of[i];
     }
+    std::vector<std::vector<int32_t>> pairs_of(nf), holes_of(nf);
+    std::vector<int> max_end_of(nf, INT_MIN);
+    auto pack_file = [&](int i) {
+        FilePending& F = *files_[i];
+        if (upto[i] <= F.front) return;
+        const size_t ro = ro_of[i], co = co_of[i], so = so_of[i];
+        size_t c0 = F.reads[F.front].h.cigar_off, s0 = F.reads[F.front].h.sq_off;
+        size_t c1 = upto[i] < F.reads.size() ? F.reads[upto[i]].h.cigar_off : F.cigar.size();
+        size_t s1 = upto[i] < F.reads.size() ? F.reads[upto[i]].h.sq_off : F.seq.size();
+        memcpy(out.cigar + co, F.cigar.data() + c0, (c1 - c0) * 4);
+        memcpy(out.seq + so, F.seq.data() + s0, s1 - s0);
+        memcpy(out.qual + 2 * so, F.qual.data() + 2 * s0, 2 * (s1 - s0));
+        int64_t front_ord = F.reads[F.front].ordinal;
+        int me = INT_MIN, mx = INT_MIN;
+        for (size_t k = F.front; k < upto[i]; ++k) {
+            const HostRead& H = F.reads[k];
+            raer_read_hdr h = H.h;
+            h.cigar_off = (uint32_t)(co + (H.h.cigar_off - c0));
+            h.sq_off = (uint32_t)(so + (H.h.sq_off - s0));
+            h.mate = (H.mate_ord >= front_ord) ? (int32_t)(ro + (size_t)(H.mate_ord - front_ord)) : -1;
+            if (!conf_.bulk_umi) h.aux = (uint32_t)(ro + (k - F.front));  // bulk UMI mode keeps its verdict there
+            size_t bi = ro + (k - F.front);
+            out.hdr[bi] = h;
+            me = std::max(me, (int)h.end);
+            out.maxend[bi] = me;
+            if (h.mate >= 0) pairs_of[i].push_back((int32_t)bi);
+            if (conf_.sc) { out.cb[bi] = H.cb; out.umi[bi] = H.umi; }
+            if (h.bits & RAER_RB_UMI_HOLES) {
+                auto it = F.umi_holes.find(H.ordinal);
+                if (it != F.umi_holes.end())
+                    for (int32_t hp : it->second) { holes_of[i].push_back((int32_t)bi); holes_of[i].push_back(hp); }
+            }
+            if (h.end > win_beg_) mx = std::max(mx, (int)h.end);
+        }
+        max_end_of[i] = mx;
+    };
+    if (nf > 1) {
+        std::vector<std::thread> th;
+        th.reserve(nf);
+        for (int i = 0; i < nf; ++i) th.emplace_back(pack_file, i);
+        for (auto& t : th) t.join();
+    } else {
+        pack_file(0);
+    }
+    size_t np = 0;
+    for (int i = 0; i < nf; ++i) {
+        for (int32_t v : pairs_of[i]) out.pair_b[np++] = v;
+        out.umi_holes.insert(out.umi_holes.end(), holes_of[i].begin(), holes_of[i].end());
+        max_end = std::max(max_end, max_end_of[i]);
+    }
+    const size_t ro = ro_of[nf], co = co_of[nf], so = so_of[nf];
+    int64_t nal = 0;
     out.file_off[nf] = (int64_t)ro;
     raer_read_batch& b = out.b;
     memset(&b, 0, sizeof(b));
