@@ -93,6 +93,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the CPUs next to its GPU (NVML's ideal CPU affinity), so that its pinned host batches are
+    allocated on that NUMA node and the H2D copies of the e2e leg do not cross the socket link. Best effort."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {i for i in range(ncpu) if (int(words[i // 64]) >> (i % 64)) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -175,6 +195,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: raer_b200 has no CPU path")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -366,7 +387,7 @@ def run_ours(args):
             dist.all_reduce(t_dt, op=dist.ReduceOp.MAX)
         e2e = {"value": float(bases_all.item()) / float(t_dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": float(t_dt.item()) * 1e3, "steps": n_e2e,
-               "distinct_host_batches": n_host, "batches_per_step": len(batches),
+               "distinct_host_batches": n_host, "batches_per_step": len(batches), "cpus_bound_to_gpu_node": numa,
                "api": "raer_pipe_submit / raer_pipe_collect (C-ABI, pinned host read batches -> rows in host memory, "
                       "two batches in flight)"}
         L.raer_pipe_destroy(pipe)
