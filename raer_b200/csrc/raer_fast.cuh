@@ -754,7 +754,8 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
                 if (lane == 0) c = atomicAdd(&s_chunk, 1);
                 c = __shfl_sync(FULL, c, 0);
                 if (c >= nchunks) break;
-                fast_count_chunk<EXT>(P, S, X, tile, l0 + (c << 5), l1, t1, lane, st, need_cov);
+                // from the back of the list: the chunks of CIGAR-walking reads are the slow ones, they go first
+                fast_count_chunk<EXT>(P, S, X, tile, l0 + ((nchunks - 1 - c) << 5), l1, t1, lane, st, need_cov);
             }
         }
         __syncthreads();
@@ -810,11 +811,13 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
                 const int d = pidx < W ? S.dec[pidx] : 0;
                 const int n = (d & 1) + ((d >> 1) & 1);
                 const bool fl = P.want_stats && (((d & 1) && (d & 4)) || ((d & 2) && (d & 8)));
-                int tot, ftot;
-                const int off = block_exclusive_scan(n, &tot, s_scan) + carried;
-                const int rank = block_exclusive_scan(fl ? 1 : 0, &ftot, s_scan) + fcarried;  // position-sorted
-                carried += tot;
-                fcarried += ftot;
+                // one scan for both: rows in the low half, flagged sites in the high half (a tile has < 2^15 of either)
+                int ptot;
+                const int pex = block_exclusive_scan(n | ((fl ? 1 : 0) << 16), &ptot, s_scan);
+                const int off = (pex & 0xffff) + carried;
+                const int rank = (pex >> 16) + fcarried;  // position-sorted
+                carried += ptot & 0xffff;
+                fcarried += ptot >> 16;
                 if (pidx < W) S.fpre[pidx] = (uint16_t)rank;
                 if (n) {
                     const long long row = rowbase + off;
@@ -857,7 +860,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
                     if (lane == 0) c = atomicAdd(&s_chunk, 1);
                     c = __shfl_sync(FULL, c, 0);
                     if (c >= nchunks) break;
-                    fast_pair_chunk<EXT>(P, S, X, T2, tile, l0 + (c << 5), l1, lane, st);
+                    fast_pair_chunk<EXT>(P, S, X, T2, tile, l0 + ((nchunks - 1 - c) << 5), l1, lane, st);
                 }
             }
             __syncthreads();
