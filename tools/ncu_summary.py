@@ -1,4 +1,4 @@
-# usage: python scratch/ncu_summary.py <report.ncu-rep> <mangled kernel name> "<header line>" > profiles/<name>.txt
+# usage: python tools/ncu_summary.py <report.ncu-rep> <mangled kernel name> "<header line>" > profiles/<name>.txt
 import csv, subprocess, sys, os
 rep, kern, title = sys.argv[1], sys.argv[2], sys.argv[3]
 os.system(f"ncu -i {rep} --page raw --csv 2>/dev/null > /tmp/raws.csv")
