@@ -1109,7 +1109,11 @@ extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* l
     }
     if (P->use_fast) {
         const size_t fsmem = raer_fast_smem_bytes(P->n_files, P->W);
-        static size_t fconfigured = 0;
+        // the opt-in shared-memory size is a per-device attribute of the function
+        static size_t fconfigured_dev[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        size_t& fconfigured = fconfigured_dev[dev & 63];
         if (fsmem > fconfigured) {
             if (cudaFuncSetAttribute(k_pileup_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem) != cudaSuccess ||
                 cudaFuncSetAttribute(k_pileup_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem) != cudaSuccess)
@@ -1127,7 +1131,10 @@ extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* l
         return cudaGetLastError() == cudaSuccess ? 0 : -1;
     }
     size_t smem = raer_tile_smem_bytes(P->n_files, P->W, P->S, &P->cnt_words, &P->slot_words);
-    static size_t configured = 0;
+    static size_t configured_dev[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& configured = configured_dev[dev & 63];
     if (smem > configured) {
         if (cudaFuncSetAttribute(k_pileup_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return -1;
