@@ -307,7 +307,7 @@ def run_ours(args):
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "k_pileup_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
+                "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_per_launch, "launch_ms": launch_ms,
                 "kernel_share_of_step": (k_ms.value / args.steps) / (ms / args.steps)}
