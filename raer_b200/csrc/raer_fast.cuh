@@ -317,8 +317,11 @@ __device__ __forceinline__ int fast_stage(const PlpParams& P, const FastSmem& S,
     int qs = 0, tail = 0, nblk = 0, other = 0;
     int qlo = 0x7fffffff, qhi = 0;  // query bases whose positions fall inside the tile
     bool lead = true;
+    // One operation that consumes as many reference as query bases is an aligned block (M, = or X): when only the
+    // mapq / base-quality filters are active nothing asks which of the three, so the CIGAR word is not fetched.
+    const bool one_block = !EXT && n == 1 && a.y - a.x == lq && lq > 0;
     for (int k = 0; k < n; ++k) {
-        const uint32_t w = __ldg(cg + k);
+        const uint32_t w = one_block ? ((uint32_t)lq << 4) : __ldg(cg + k);
         if (k < 4) rec[FR_CIG0 + k] = w;
         const int op = cg_op(w), len = cg_len(w);
         // query_start / query_end (src/plp_utils.c:52-104): soft clips at either end, hard clips skipped
@@ -563,8 +566,9 @@ __device__ __forceinline__ void fast_pair_chunk(const PlpParams& P, const FastSm
             int qs = 0, tail = 0, nblk = 0, other = 0, rl = 0, x = a.x;
             int fb[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
             bool lead = true;
+            const bool one_block = !EXT && n == 1 && a.y - a.x == lq && lq > 0;  // see fast_stage
             for (int k = 0; k < n; ++k) {
-                const uint32_t w = __ldg(cg + k);
+                const uint32_t w = one_block ? ((uint32_t)lq << 4) : __ldg(cg + k);
                 if (k < 4) rec[FR_CIG0 + k] = w;
                 const int op = cg_op(w), len = cg_len(w);
                 // query_start / query_end (src/plp_utils.c:52-104): soft clips at either end, hard clips skipped
