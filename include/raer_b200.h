@@ -72,6 +72,10 @@ typedef struct raer_pileup_args {
     int32_t host_threads;            /* BGZF inflate threads; 0 = hardware concurrency */
     int32_t shard_index;             /* multi-GPU: this process handles contig-tiles i where       */
     int32_t shard_count;             /*   i % shard_count == shard_index; 0/1 = everything         */
+    int32_t aei_mode;                /* 1: no rows; raer_pileup_result.aei = per file, the counts of the rows that would have
+                                        been written, summed by (REF of the row, counted base): all calc_AEI() needs
+                                        (reference R/calc_AEI.R:274-323). Needs the fast tile kernel. */
+    int32_t pad1;
 } raer_pileup_args;
 
 /* Column layout of the .Call(".pileup") result (src/plp_data.c:285-289, 321-361). Every file has
@@ -94,6 +98,7 @@ typedef struct raer_pileup_result {
     /* timing breakdown of this call, seconds (BASELINE.json: "host decode and H2D broken out") */
     double t_decode, t_pack, t_h2d, t_kernel, t_d2h, t_total;
     int64_t n_records, n_aligned_bases, gpu_launches;
+    int64_t* aei;     /* aei_mode: [nbam][4][4], index [REF of the row: A C G T][nA nC nG nT], else NULL */
 } raer_pileup_result;
 
 int raer_pileup(const raer_pileup_args* args, raer_pileup_result* out);
@@ -197,6 +202,8 @@ typedef struct raer_bulk_conf {
     int32_t remove_overlaps;   /* 0 none, 1 htslib >= 1.13, 2 htslib <= 1.12 */
     int32_t want_stats;        /* 1: rpbz/vdb/sor + ALT order (reference behaviour); 0 skips the second pass */
     int32_t umi_mode;          /* 1: bulk UMI mode, hdr.aux / umi_holes carry the per-read verdicts */
+    int32_t aei_mode;          /* 1: no rows, only the 4 x 4 (REF, base) sums per file: raer_ctx_last_aei() */
+    int32_t pad0;
     double ftrim_5p, ftrim_3p, min_af;
     int32_t min_mapq[RAER_MAX_FILES];
     int32_t only_keep_variants[RAER_MAX_FILES];
@@ -245,6 +252,8 @@ void raer_pipe_destroy(raer_pipe* pipe);
 int raer_pipe_submit(raer_pipe* pipe, const raer_bulk_conf* conf, const raer_read_batch* host_batch, int32_t tid,
                      const char* ref, int64_t ref_len);
 int raer_pipe_collect(raer_pipe* pipe, raer_rows* out);
+/* aei_mode: the sums of the batch collected last on this context, n_files x 16 values */
+int raer_ctx_last_aei(raer_ctx* ctx, int64_t* sums, int32_t n_files);
 /* device-resident path (bench "value"): every pointer of dev_batch (except file_off) is device memory.
  * Runs the kernels on the context stream; rows stay on the device. *n_rows is read back at the end
  * unless NULL. Counts launched kernels into *launches when not NULL. */

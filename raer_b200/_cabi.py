@@ -46,6 +46,8 @@ class PileupArgs(C.Structure):
         ("host_threads", C.c_int32),
         ("shard_index", C.c_int32),
         ("shard_count", C.c_int32),
+        ("aei_mode", C.c_int32),
+        ("pad1", C.c_int32),
     ]
 
 
@@ -73,6 +75,7 @@ class PileupResult(C.Structure):
         ("n_records", C.c_int64),
         ("n_aligned_bases", C.c_int64),
         ("gpu_launches", C.c_int64),
+        ("aei", C.POINTER(C.c_int64)),
     ]
 
 
@@ -140,7 +143,7 @@ class BulkConf(C.Structure):
         ("trim_3p", C.c_int32), ("indel_dist", C.c_int32), ("splice_dist", C.c_int32), ("min_overhang", C.c_int32),
         ("nmer", C.c_int32), ("min_var_reads", C.c_int32), ("n_mm_type", C.c_int32), ("n_mm", C.c_int32),
         ("report_multiallelic", C.c_int32), ("remove_overlaps", C.c_int32), ("want_stats", C.c_int32),
-        ("umi_mode", C.c_int32),
+        ("umi_mode", C.c_int32), ("aei_mode", C.c_int32), ("pad0", C.c_int32),
         ("ftrim_5p", C.c_double), ("ftrim_3p", C.c_double), ("min_af", C.c_double),
         ("min_mapq", C.c_int32 * MAX_FILES), ("only_keep_variants", C.c_int32 * MAX_FILES),
         ("reg_beg", C.c_int32), ("reg_end", C.c_int32),
@@ -230,7 +233,7 @@ def _ints(xs):
 LAST_TIMING = {}
 
 
-def pileup(pc, device: int = 0, host_threads: int = 0, overlap_mode: int = 1, shard=(0, 1)) -> dict:
+def pileup(pc, device: int = 0, host_threads: int = 0, overlap_mode: int = 1, shard=(0, 1), aei: bool = False) -> dict:
     """.Call(".pileup", ...) -> column dict (same layout as the reference's list-of-lists)."""
     L = lib()
     n = pc.n
@@ -254,6 +257,7 @@ def pileup(pc, device: int = 0, host_threads: int = 0, overlap_mode: int = 1, sh
     a.device = device
     a.host_threads = host_threads
     a.shard_index, a.shard_count = shard
+    a.aei_mode = 1 if aei else 0
     r = PileupResult()
     rc = L.raer_pileup(C.byref(a), C.byref(r))
     if rc != 0:
@@ -296,6 +300,8 @@ def pileup(pc, device: int = 0, host_threads: int = 0, overlap_mode: int = 1, sh
                                 t_d2h=r.t_d2h, t_total=r.t_total, n_records=int(r.n_records),
                                 n_aligned_bases=int(r.n_aligned_bases), gpu_launches=int(r.gpu_launches)))
         out["timing"] = dict(LAST_TIMING)
+        if aei and r.aei:
+            out["aei"] = np.ctypeslib.as_array(r.aei, shape=(n, 4, 4)).astype(np.int64, copy=True)
         return out
     finally:
         L.raer_pileup_result_free(C.byref(r))

@@ -243,8 +243,57 @@ def pileup_cells(bamfiles, sites: Sites, cell_barcodes: Sequence[str], output_di
 _AEI_PAIRS = [(r, a) for r in "ACGT" for a in "ACGT" if r != a]
 
 
+def _sites_minus_snps(alu: Sites, snp_db: Optional[Sites], chroms) -> Sites:
+    """alu_ranges restricted to `chroms`, with the SNP positions cut out (1-based inclusive pieces)."""
+    import bisect
+    from collections import defaultdict
+
+    snps = defaultdict(list)
+    if snp_db is not None:
+        for sn, p0, p1 in zip(snp_db.seqnames, snp_db.start, snp_db.end):
+            snps[sn].extend(range(int(p0), int(p1) + 1))
+        for v in snps.values():
+            v.sort()
+    names, starts, ends = [], [], []
+    keep = set(chroms)
+    for sn, a, b in zip(alu.seqnames, alu.start, alu.end):
+        if sn not in keep:
+            continue
+        cur = int(a)
+        ps = snps.get(sn, [])
+        for p in ps[bisect.bisect_left(ps, cur):bisect.bisect_right(ps, int(b))]:
+            if p > cur:
+                names.append(sn); starts.append(cur); ends.append(p - 1)
+            cur = max(cur, p + 1)
+        if cur <= int(b):
+            names.append(sn); starts.append(cur); ends.append(int(b))
+    return Sites(names, starts, ends)
+
+
+def _calc_aei_fused(fused_call, bamfiles, fasta, alu_ranges, snp_db, param, indexes):
+    """Stranded libraries: one device call per BAM returns the 4 x 4 (REF of the row, counted base) sums of the rows
+    pileup_sites() would have produced inside alu_ranges minus the SNP positions (raer_pileup_args.aei_mode)."""
+    aei, per = {}, {}
+    idx = {"A": 0, "C": 1, "G": 2, "T": 3}
+    for bi, bam in enumerate(bamfiles):
+        chroms, _, _ = glue.setup_valid_regions(bam, None, None, fasta)
+        alu_chroms = set(alu_ranges.seqnames)
+        chroms = [c for c in chroms if c in alu_chroms]
+        sites = _sites_minus_snps(alu_ranges, snp_db, chroms)
+        name = os.path.basename(bam)
+        tot = {p: (0, 0) for p in _AEI_PAIRS}
+        if len(sites) > 0:
+            ix = None if indexes is None else [indexes[bi]]
+            pc = glue.prepare_pileup_call([bam], fasta, sites, None, None, param, None, ix)
+            m = fused_call(pc)["aei"][0]
+            tot = {(r, a): (int(m[idx[r], idx[a]]), int(m[idx[r], idx[r]])) for r, a in _AEI_PAIRS}
+        aei[name] = {f"{r}_{a}": (100.0 * alt / (alt + ref) if alt + ref > 0 else float("nan")) for (r, a), (alt, ref) in tot.items()}
+        per[name] = {f"{r}_{a}": v for (r, a), v in tot.items()}
+    return {"AEI": aei, "AEI_per_chrom": per}
+
+
 def _calc_aei_impl(call, bamfiles, fasta, alu_ranges: Optional[Sites] = None, txdb_genes: Optional[Sites] = None,
-                   snp_db: Optional[Sites] = None, param: Optional[FilterParam] = None, indexes=None):
+                   snp_db: Optional[Sites] = None, param: Optional[FilterParam] = None, indexes=None, fused_call=None):
     """calc_AEI() (R/calc_AEI.R:68-323): per BAM, per chromosome pileup with min_depth=1 and
     only_keep_variants=FALSE, then per (REF, ALT) pair: sum(n<ALT>) / (sum(n<ALT>) + sum(n<REF>)) * 100.
     """
@@ -260,6 +309,8 @@ def _calc_aei_impl(call, bamfiles, fasta, alu_ranges: Optional[Sites] = None, tx
     unstranded = param.library_type[0] == "unstranded"
     if unstranded and txdb_genes is None:
         raise ValueError("txdb required for processing unstranded data")
+    if fused_call is not None and not unstranded:
+        return _calc_aei_fused(fused_call, bamfiles, fasta, alu_ranges, snp_db, param, indexes)
     snp_keys = None
     if snp_db is not None:
         snp_keys = set(zip(snp_db.seqnames, snp_db.start))
@@ -321,4 +372,7 @@ def calc_AEI(bamfiles, fasta, alu_ranges=None, txdb=None, snp_db=None, param=Non
     """Mirror of ``calc_AEI()`` (R/calc_AEI.R:68)."""
     from . import _cabi
 
-    return _calc_aei_impl(_cabi.pileup, bamfiles, fasta, alu_ranges, txdb, snp_db, param, indexes)
+    # stranded libraries take the fused device reduction (SURVEY.md section 8f-2); unstranded ones need the gene
+    # annotation per site and go through the rows like the reference
+    return _calc_aei_impl(_cabi.pileup, bamfiles, fasta, alu_ranges, txdb, snp_db, param, indexes,
+                          fused_call=lambda pc: _cabi.pileup(pc, aei=True))

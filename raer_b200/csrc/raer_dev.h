@@ -51,6 +51,8 @@ struct PlpParams {
     int umi_mode;                    // bulk UMI mode: hdr.aux = end of the positions an earlier read of the same UMI takes
     const int32_t* umi_holes;        //   (read index, position) pairs sorted by read index: positions that stay counted
     int n_umi_holes;
+    int aei_mode;                    // no rows: per file the 4 x 4 (REF of the row, counted base) sums of the rows a tile would write
+    unsigned long long* aei_out;     //   [n_files][16]
     int fast;                        // only mapq / base-quality filters configured: branch-free item path
     int use_fast;                    // launch k_pileup_fast (raer_fast.cuh) instead of k_pileup_tiles
     double ftrim_5p, ftrim_3p, min_af;

@@ -798,6 +798,45 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
             S.dec[pidx] = (uint8_t)d;
             my_rows += (d & 1) + ((d >> 1) & 1);
         }
+        if (P.aei_mode) {
+            // calc_AEI (reference R/calc_AEI.R:274-323) sums, per file, n<base> over the rows whose REF is a given base:
+            // a 4 x 4 matrix per file is all that leaves the tile. flag_row (unused here) holds the tile's sums.
+            uint32_t* acc_s = reinterpret_cast<uint32_t*>(S.flag_row);
+            for (int i = threadIdx.x; i < F * 16; i += blockDim.x) acc_s[i] = 0;
+            __syncthreads();
+            for (int f = 0; f < F; ++f) {
+                int acc[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] = 0;
+                for (int pidx = threadIdx.x; pidx < W; pidx += blockDim.x) {
+                    const int d = S.dec[pidx];
+                    if (!(d & 3)) continue;
+                    const int pc = cls_of_ref(d_upper((unsigned char)P.ref[t0 + pidx]));
+                    if (pc >= 4) continue;  // REF outside A C G T takes part in no (REF, ALT) pair
+                    for (int st2 = 0; st2 < 2; ++st2) {
+                        if (!((d >> st2) & 1)) continue;
+                        int cc[RAER_NCLS];
+                        CN.get(f, st2, pidx, pc, cc);
+                        const int rc = st2 == 0 ? pc : 3 - pc;  // REF of the row on that strand
+#pragma unroll
+                        for (int r4 = 0; r4 < 4; ++r4)
+#pragma unroll
+                            for (int b4 = 0; b4 < 4; ++b4) acc[r4 * 4 + b4] += (r4 == rc) ? cc[b4] : 0;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int v = __reduce_add_sync(FULL, acc[i]);
+                    if (lane == 0 && v) atomicAdd(&acc_s[f * 16 + i], (uint32_t)v);
+                }
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < F * 16; i += blockDim.x)
+                if (acc_s[i]) atomicAdd(&P.aei_out[i], (unsigned long long)acc_s[i]);
+            if (threadIdx.x == 0) P.tile_rows[tile] = make_int2(0, 0);
+            __syncthreads();
+            continue;
+        }
         int tile_rows_total;
         block_exclusive_scan(my_rows, &tile_rows_total, s_scan);
         if (threadIdx.x == 0) {

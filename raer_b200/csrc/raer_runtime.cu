@@ -80,6 +80,8 @@ struct raer_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6];
     DevBuf hdr, maxend, cigar, seq, qual, pair_b, mask;
+    DevBuf aei;                            // aei_mode: [n_files][16] sums of the batch
+    std::vector<int64_t> last_aei;
     DevBuf umi_holes;                      // bulk UMI mode: (read, position) pairs that stay counted
     DevBuf ov_scratch;                     // mate overlap: compacted list of the CIGAR-walking pairs
     DevBuf tile_idx, tile_list;            // k_pileup_fast: counts | offsets | cursors, and the per-tile read lists
@@ -122,7 +124,7 @@ extern "C" void raer_ctx_destroy(raer_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->hdr, &c->maxend, &c->cigar, &c->seq, &c->qual, &c->pair_b, &c->mask, &c->tile_ranges, &c->tile_rows, &c->tile_idx, &c->tile_list, &c->ov_scratch, &c->umi_holes,
+    for (DevBuf* b : {&c->hdr, &c->maxend, &c->cigar, &c->seq, &c->qual, &c->pair_b, &c->mask, &c->tile_ranges, &c->tile_rows, &c->tile_idx, &c->tile_list, &c->ov_scratch, &c->umi_holes, &c->aei,
                       &c->small, &c->row_pos, &c->row_meta, &c->row_stats, &c->row_counts, &c->row_alt, &c->ref})
         b->release();
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -211,6 +213,14 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
     P.report_multiallelic = conf->report_multiallelic; P.want_stats = conf->want_stats;
     P.ftrim_5p = conf->ftrim_5p; P.ftrim_3p = conf->ftrim_3p; P.min_af = conf->min_af;
     P.any_okv = 0;
+    P.aei_mode = conf->aei_mode;
+    if (P.aei_mode) {
+        if (!P.use_fast) { set_error("aei_mode needs the fast tile kernel"); return RAER_ERR_LIMIT; }
+        int rc2 = c->aei.ensure((size_t)RAER_MAX_FILES * 16 * sizeof(unsigned long long));
+        if (rc2) return rc2;
+        CK(cudaMemsetAsync(c->aei.p, 0, (size_t)nf * 16 * sizeof(unsigned long long), c->stream));
+        P.aei_out = (unsigned long long*)c->aei.p;
+    }
     P.umi_mode = conf->umi_mode;
     P.umi_holes = b->umi_holes;
     P.n_umi_holes = (int)b->n_umi_holes;
@@ -453,6 +463,11 @@ static int host_collect(raer_ctx* c, raer_rows* out) {
     c->last_launches += nl;
     if (rc) return rc;
     rc = fetch_rows(c, c->p_dev.n_files, st, out);
+    if (rc == RAER_OK && c->p_conf.aei_mode) {
+        c->last_aei.assign((size_t)c->p_dev.n_files * 16, 0);
+        CK(cudaMemcpyAsync(c->last_aei.data(), c->aei.p, c->last_aei.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
     cudaEventRecord(c->ev[3], c->stream);
     cudaEventSynchronize(c->ev[3]);
     cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]);
@@ -532,6 +547,12 @@ extern "C" int raer_pipe_collect(raer_pipe* p, raer_rows* out) {
     if (p->empty[k]) return RAER_OK;
     cudaSetDevice(p->c[k]->device);
     return host_collect(p->c[k], out);
+}
+
+extern "C" int raer_ctx_last_aei(raer_ctx* c, int64_t* sums, int32_t n_files) {
+    if (!c || !sums || (size_t)n_files * 16 != c->last_aei.size()) { set_error("no AEI sums for %d files on this context", n_files); return RAER_ERR_ARG; }
+    memcpy(sums, c->last_aei.data(), c->last_aei.size() * sizeof(int64_t));
+    return RAER_OK;
 }
 
 extern "C" void raer_ctx_last_timing(raer_ctx* c, double* h2d_s, double* kernel_s, double* d2h_s) {
@@ -646,7 +667,7 @@ static void sink_reserve(ResultSink& s, int64_t need) {
 extern "C" void raer_pileup_result_free(raer_pileup_result* r) {
     if (!r) return;
     free(r->tid); free(r->pos); free(r->strand); free(r->ref); free(r->rpbz); free(r->vdb); free(r->sor);
-    free(r->alt); free(r->counts);
+    free(r->alt); free(r->counts); free(r->aei);
     if (r->target_names) {
         for (int i = 0; i < r->n_targets; ++i) free(r->target_names[i]);
         free(r->target_names);
@@ -722,6 +743,8 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
     bc.remove_overlaps = ic.remove_overlaps;
     bc.want_stats = 1;
     bc.umi_mode = a->umi_tag ? 1 : 0;
+    bc.aei_mode = a->aei_mode ? 1 : 0;
+    if (bc.aei_mode) out->aei = (int64_t*)calloc((size_t)nf * 16, sizeof(int64_t));
     for (int i = 0; i < nf; ++i) { bc.min_mapq[i] = a->min_mapq[i]; bc.only_keep_variants[i] = a->only_keep_variants[i]; }
 
     const std::vector<std::string>& names = ing.names();
@@ -778,6 +801,12 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             rc = raer_batch_pileup_host(ctx, &bc, &pb.b, &rows);
             tm_gpu += raer::now_seconds() - t0g;
             if (rc) break;
+            if (bc.aei_mode) {
+                std::vector<int64_t> sums((size_t)nf * 16);
+                rc = raer_ctx_last_aei(ctx, sums.data(), nf);
+                if (rc) break;
+                for (size_t i = 0; i < sums.size(); ++i) out->aei[i] += sums[i];
+            }
             double t0s = raer::now_seconds();
             out->gpu_launches += ctx->last_launches;
             out->t_h2d += ctx->ms_h2d * 1e-3; out->t_kernel += ctx->ms_kernel * 1e-3; out->t_d2h += ctx->ms_d2h * 1e-3;

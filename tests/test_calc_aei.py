@@ -83,3 +83,32 @@ def test_calc_aei_cuda_equals_oracle(ext, lt):
         for pair, v in want["AEI"][name].items():
             g = got["AEI"][name][pair]
             assert (math.isnan(v) and math.isnan(g)) or g == v
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [
+    dict(library_type="fr-first-strand"),
+    dict(library_type="fr-second-strand", min_base_quality=10, trim_5p=3, min_mapq=3),
+])
+def test_fused_device_reduction_equals_row_based_calc_aei(tmp_path, kw):
+    """The device-side 4 x 4 reduction (raer_pileup_args.aei_mode) against calc_AEI computed from the
+    rows, on synthetic BAMs with interval sites and a SNP list."""
+    import numpy as np
+
+    from raer_b200 import _cabi, api, synth
+
+    ds = synth.make_bulk_dataset(str(tmp_path), n_bams=2, n_contigs=3, contig_len=60_000, pairs_per_contig=8000, seed=31)
+    rng = np.random.default_rng(3)
+    names, starts, ends = [], [], []
+    for c in ds["names"][:2]:  # the third contig has no interval: it must not contribute
+        for s in sorted(rng.choice(59_000, size=40, replace=False)):
+            names.append(c); starts.append(int(s) + 1); ends.append(int(s) + int(rng.integers(100, 400)))
+    alu = Sites(names, starts, ends)
+    snp_pos = sorted(set(int(x) for x in rng.choice(60_000, size=3000, replace=False)))
+    snps = Sites([ds["names"][0]] * len(snp_pos), [p + 1 for p in snp_pos])
+    fp = FilterParam(**kw)
+    fused = api.calc_AEI(ds["bams"], ds["fasta"], alu, snp_db=snps, param=fp)
+    rows = api._calc_aei_impl(_cabi.pileup, ds["bams"], ds["fasta"], alu, None, snps, fp)
+    want = oracle_backend.calc_AEI(ds["bams"], ds["fasta"], alu, snp_db=snps, param=fp)
+    assert fused["AEI_per_chrom"] == rows["AEI_per_chrom"] == want["AEI_per_chrom"]
+    assert sum(a + r for v in fused["AEI_per_chrom"].values() for a, r in v.values()) > 10_000
