@@ -237,6 +237,13 @@ def run_ours(args):
         conf.want_stats = 0
     if os.environ.get("RAER_BENCH_EXT_FILTERS"):  # development probe: a typical RNA-editing FilterParam (not the C2 call)
         conf.trim_5p, conf.trim_3p, conf.splice_dist, conf.indel_dist, conf.min_overhang = 5, 5, 4, 4, 10
+    if os.environ.get("RAER_BENCH_ALL_SITES"):  # development probe: calc_AEI-like call, a row for every covered site
+        for f in range(n_bams):
+            conf.only_keep_variants[f] = 0
+    if os.environ.get("RAER_BENCH_AEI"):  # development probe: the same with the fused 4 x 4 reduction instead of rows
+        for f in range(n_bams):
+            conf.only_keep_variants[f] = 0
+        conf.aei_mode = 1
     if os.environ.get("RAER_BENCH_NO_OVERLAP"):  # development probe: skip the mate-overlap kernel
         conf.remove_overlaps = 0
     for f in range(n_bams):
