@@ -223,6 +223,10 @@ typedef struct raer_rows {
     double* stats;       /* [n_rows][3]: rpbz, vdb, sor */
     int32_t* counts;     /* [n_rows][n_files][8] */
     uint32_t* altcode;   /* [n_rows][n_files] */
+    /* [file * 2 + strand]: first 0-based position of the batch at which the variant table of that file and strand
+     * grew from 4 to 8 khash buckets at a site that wrote no row for the strand (src/plp.c:487: every variant read is a
+     * kh_put, written or not); INT32_MAX if none. raer_altcode_to_string callers apply it to the rows behind it. */
+    int32_t grow_pos[64];
 } raer_rows;
 void raer_rows_free(raer_rows* r);
 

@@ -156,6 +156,7 @@ class Rows(C.Structure):
         ("n_rows", C.c_int64), ("n_files", C.c_int32),
         ("pos", C.POINTER(C.c_int32)), ("meta", C.POINTER(C.c_uint32)), ("stats", C.POINTER(C.c_double)),
         ("counts", C.POINTER(C.c_int32)), ("altcode", C.POINTER(C.c_uint32)),
+        ("grow_pos", C.c_int32 * 64),
     ]
 
 

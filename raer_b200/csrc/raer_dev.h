@@ -71,6 +71,8 @@ struct PlpParams {
     unsigned long long* row_counter;
     int2* tile_rows;                 // per tile {first row, n rows}
     int* err_flag;
+    int* grow;                       // [n_files * 2]: 0x7fffffff - first position at which the puts of an UNWRITTEN
+                                     // (file, strand) grew its khash from 4 to 8 buckets (0 = none)
     // shared memory plan
     int S;                           // second-pass site slots per round
     int cnt_words;                   // words of the counter region (>= S * slot_words)

@@ -640,16 +640,18 @@ __device__ __forceinline__ void fast_pair_chunk(const PlpParams& P, const FastSm
 }
 
 // rpbz / vdb / sor and the ALT order codes of one second-pass slot (shared by both tile kernels)
-__device__ void slot_stats(const PlpParams& P, const uint32_t* slot, int HW, int rowp, int rowm) {
+__device__ void slot_stats(const PlpParams& P, const uint32_t* slot, int HW, int rowp, int rowm, int growmask, int pos) {
     const double sor = d_calc_sor((int)slot[HW], (int)slot[HW + 1], (int)slot[HW + 2], (int)slot[HW + 3]);
     for (int s = 0; s < 2; ++s) {
         const long long row = s == 0 ? rowp : rowm;
-        if (row < 0) continue;
-        const HistView hr = {slot, (s * 2) * RAER_NHIST, HW != 4 * RAER_NHIST};
-        const HistView ha = {slot, (s * 2 + 1) * RAER_NHIST, HW != 4 * RAER_NHIST};
-        P.row_stats[row * 3 + 0] = d_calc_mwu_z(hr, ha);
-        P.row_stats[row * 3 + 1] = d_calc_vdb(ha);
-        P.row_stats[row * 3 + 2] = sor;
+        if (row < 0 && !((growmask >> s) & 1)) continue;
+        if (row >= 0) {
+            const HistView hr = {slot, (s * 2) * RAER_NHIST, HW != 4 * RAER_NHIST};
+            const HistView ha = {slot, (s * 2 + 1) * RAER_NHIST, HW != 4 * RAER_NHIST};
+            P.row_stats[row * 3 + 0] = d_calc_mwu_z(hr, ha);
+            P.row_stats[row * 3 + 1] = d_calc_vdb(ha);
+            P.row_stats[row * 3 + 2] = sor;
+        }
         for (int f = 0; f < P.n_files; ++f) {
             const uint32_t* fs = slot + HW + 4 + (f * 2 + s) * RAER_SLOT_FS;
             // order the (at most 5) variant keys by first-seen ordinal: 0..3 = ACGT, 4 = IUPAC key
@@ -667,11 +669,17 @@ __device__ void slot_stats(const PlpParams& P, const uint32_t* slot, int HW, int
                 ord[best] = 0xffffffffu;
                 ++nins;
             }
+            // kh_put resizes 4 -> 8 buckets when a put arrives with 3 keys occupied (khash.h)
+            const bool grows = nins >= 3 && fs[4] > third + 1u;
+            if (row < 0) {
+                // no row carries the flag: the host gets the first such position of the (file, strand)
+                if (grows) atomicMax(&P.grow[f * 2 + s], 0x7fffffff - pos);
+                continue;
+            }
             unsigned alt = P.row_alt[row * P.n_files + f] & (RAER_ALT_MASK | RAER_ALT_OTHER);
             alt |= code << RAER_ALT_ORDER_SHIFT;
             alt |= (unsigned)nins << RAER_ALT_NINS_SHIFT;
-            // kh_put resizes 4 -> 8 buckets when a put arrives with 3 keys occupied (khash.h)
-            if (nins >= 3 && fs[4] > third + 1u) alt |= RAER_ALT_GROW;
+            if (grows) alt |= RAER_ALT_GROW;
             if (fs[5] != 0xffffffffu) {
                 alt |= (fs[6] & 0xfu) << RAER_ALT_OCODE_SHIFT;
                 if (fs[6] != fs[7]) alt |= RAER_ALT_OAMBIG;
@@ -796,7 +804,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
             int d = 0;
             if (t0 + pidx < t1) d = decide_site(P, CN, S.covered, pidx, t0 + pidx);
             S.dec[pidx] = (uint8_t)d;
-            my_rows += (d & 1) + ((d >> 1) & 1);
+            my_rows += (d & 1) + ((d >> 1) & 1) + ((d & 48) ? 0x10000 : 0);
         }
         if (P.aei_mode) {
             // calc_AEI (reference R/calc_AEI.R:274-323) sums, per file, n<base> over the rows whose REF is a given base:
@@ -837,8 +845,11 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
             __syncthreads();
             continue;
         }
-        int tile_rows_total;
-        block_exclusive_scan(my_rows, &tile_rows_total, s_scan);
+        // rows in the low half; sites that only need the second pass for the khash state in the high half
+        int tile_tot;
+        block_exclusive_scan(my_rows, &tile_tot, s_scan);
+        const int tile_rows_total = tile_tot & 0xffff;
+        const bool tile_grow = (tile_tot >> 16) != 0;
         if (threadIdx.x == 0) {
             long long base = (long long)atomicAdd(P.row_counter, (unsigned long long)tile_rows_total);
             if (base + tile_rows_total > P.row_cap) { atomicExch(P.err_flag, RAER_ERR_LIMIT); base = -1; }
@@ -847,13 +858,13 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
         }
         __syncthreads();
         const long long rowbase = s_rowbase;
-        if (rowbase >= 0 && tile_rows_total > 0) {
+        if (rowbase >= 0 && (tile_rows_total > 0 || tile_grow)) {
             int carried = 0, fcarried = 0;
             for (int chunk = 0; chunk < W; chunk += blockDim.x) {
                 const int pidx = chunk + threadIdx.x;
                 const int d = pidx < W ? S.dec[pidx] : 0;
                 const int n = (d & 1) + ((d >> 1) & 1);
-                const bool fl = P.want_stats && (((d & 1) && (d & 4)) || ((d & 2) && (d & 8)));
+                const bool fl = P.want_stats && (((d & 1) && (d & 4)) || ((d & 2) && (d & 8)) || (d & 48));
                 // one scan for both: rows in the low half, flagged sites in the high half (a tile has < 2^15 of either)
                 int ptot;
                 const int pex = block_exclusive_scan(n | ((fl ? 1 : 0) << 16), &ptot, s_scan);
@@ -862,7 +873,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
                 carried += ptot & 0xffff;
                 fcarried += ptot >> 16;
                 if (pidx < W) S.fpre[pidx] = (uint16_t)rank;
-                if (n) {
+                if (n || fl) {
                     const long long row = rowbase + off;
                     if (d & 1) write_row(P, CN, pidx, t0 + pidx, 0, row);
                     if (d & 2) write_row(P, CN, pidx, t0 + pidx, 1, row + (d & 1));
@@ -910,7 +921,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
             for (int i = threadIdx.x; i < ns; i += blockDim.x) {
                 const int d = S.flag_d[round0 + i], row = S.flag_row[round0 + i];
                 slot_stats(P, S.cnt + (size_t)i * SW, HW, ((d & 1) && (d & 4)) ? row : -1,
-                           ((d & 2) && (d & 8)) ? row + (d & 1) : -1);
+                           ((d & 2) && (d & 8)) ? row + (d & 1) : -1, d >> 4, t0 + (int)S.flag_pidx[round0 + i]);
             }
             __syncthreads();
         }

@@ -726,7 +726,9 @@ __device__ int decide_site(const PlpParams& P, const CNT cnt, const uint32_t* co
     if (P.min_depth <= 0 && !((covered[pidx >> 5] >> (pidx & 31)) & 1u)) return 0;  // no pileup column here
     int pc = cls_of_ref(pref);
     int write_s[2] = {0, 0}, has_v[2] = {0, 0}, is_ma[2] = {0, 0}, any_var[2] = {0, 0};
+    int three[2] = {0, 0}, raw_ok = 0;
     for (int f = 0; f < P.n_files; ++f) {
+        int raw = 0;
         for (int s = 0; s < 2; ++s) {
             int cc[RAER_NCLS];
             cnt.get(f, s, pidx, pc, cc);
@@ -735,6 +737,12 @@ __device__ int decide_site(const PlpParams& P, const CNT cnt, const uint32_t* co
             int rc = s == 0 ? pc : (pc < 4 ? 3 - pc : 4);
             int nr = rc < 4 ? cc[rc] : 0;
             int nv = total - nr;
+            raw += total + cc[5];
+            // three distinct variant keys and a further put resize the file's khash (src/plp.c:487, khash.h)
+            // whether or not the site is written: such sites take the second pass for the put order
+            int keys = co > 0;
+            for (int b = 0; b < 4; ++b) keys += (b != rc && cc[b] > 0);
+            if (keys >= 3 && nv > 3) three[s] = 1;
             if (total >= P.min_depth && nv >= P.min_var_reads) write_s[s] = 1;
             if (nv > 0) any_var[s] = 1;
             int vs = 0;
@@ -749,6 +757,9 @@ __device__ int decide_site(const PlpParams& P, const CNT cnt, const uint32_t* co
                 if (vs > 1) is_ma[s] = 1;
             }
         }
+        // the reference counts a site when one file's column holds min_depth entries (src/plp.c:697-704); the
+        // counted bases of the file are a lower bound of its column
+        if (raw >= P.min_depth) raw_ok = 1;
     }
     int out = 0;
     for (int s = 0; s < 2; ++s) {
@@ -757,6 +768,7 @@ __device__ int decide_site(const PlpParams& P, const CNT cnt, const uint32_t* co
         if (!P.report_multiallelic) w = w && !is_ma[s];
         if (w) out |= 1 << s;
         if (any_var[s]) out |= 4 << s;
+        if (!w && three[s] && raw_ok && P.want_stats && !P.aei_mode) out |= 16 << s;
     }
     return out;
 }
@@ -983,10 +995,12 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
             int d = 0;
             if (t0 + pidx < t1) d = decide_site(P, CntPlain{S.cnt, W}, S.covered, pidx, t0 + pidx);
             S.dec[pidx] = (uint8_t)d;
-            my_rows += (d & 1) + ((d >> 1) & 1);
+            my_rows += (d & 1) + ((d >> 1) & 1) + ((d & 48) ? 0x10000 : 0);
         }
-        int tile_rows_total;
-        block_exclusive_scan(my_rows, &tile_rows_total, s_scan);
+        int tile_tot;
+        block_exclusive_scan(my_rows, &tile_tot, s_scan);
+        const int tile_rows_total = tile_tot & 0xffff;
+        const bool tile_grow = (tile_tot >> 16) != 0;
         if (threadIdx.x == 0) {
             long long base = (long long)atomicAdd(P.row_counter, (unsigned long long)tile_rows_total);
             if (base + tile_rows_total > P.row_cap) { atomicExch(P.err_flag, RAER_ERR_LIMIT); base = -1; }
@@ -995,19 +1009,19 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
         }
         __syncthreads();
         const long long rowbase = s_rowbase;
-        if (rowbase >= 0 && tile_rows_total > 0) {
+        if (rowbase >= 0 && (tile_rows_total > 0 || tile_grow)) {
             int carried = 0, fcarried = 0;
             for (int chunk = 0; chunk < W; chunk += blockDim.x) {
                 int pidx = chunk + threadIdx.x;
                 int d = pidx < W ? S.dec[pidx] : 0;
                 int n = (d & 1) + ((d >> 1) & 1);
-                bool fl = P.want_stats && (((d & 1) && (d & 4)) || ((d & 2) && (d & 8)));
+                bool fl = P.want_stats && (((d & 1) && (d & 4)) || ((d & 2) && (d & 8)) || (d & 48));
                 int tot, ftot;
                 int off = block_exclusive_scan(n, &tot, s_scan) + carried;
                 int slot = block_exclusive_scan(fl ? 1 : 0, &ftot, s_scan) + fcarried;  // position-sorted flag list
                 carried += tot;
                 fcarried += ftot;
-                if (n) {
+                if (n || fl) {
                     long long row = rowbase + off;
                     int rp = -1, rm = -1;
                     if (d & 1) { write_row(P, CntPlain{S.cnt, W}, pidx, t0 + pidx, 0, row); rp = (int)row; ++row; }
@@ -1062,7 +1076,8 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
             }
             __syncthreads();
             for (int i = threadIdx.x; i < ns; i += blockDim.x)
-                slot_stats(P, S.cnt + (size_t)i * SW, HW, S.flag_rowp[round0 + i], S.flag_rowm[round0 + i]);
+                slot_stats(P, S.cnt + (size_t)i * SW, HW, S.flag_rowp[round0 + i], S.flag_rowm[round0 + i],
+                           S.dec[S.flag_pidx[round0 + i]] >> 4, t0 + (int)S.flag_pidx[round0 + i]);
             __syncthreads();
         }
         __syncthreads();

@@ -168,6 +168,11 @@ extern "C" int raer_ctx_set_reference_device(raer_ctx* c, int32_t tid, const voi
 }
 
 // choose the tile width: counters [file][strand][6][W] x 4 B must fit, leave room for 2 CTAs/SM when cheap
+// the small device block of a run: tile_counter | row_counter | err | list total | khash growth positions
+struct SmallState { unsigned tc, pad; unsigned long long rows; int err; int pad2[3]; int list_total; int pad3[7];
+                    int grow[2 * RAER_MAX_FILES]; };
+static_assert(offsetof(SmallState, grow) == 64, "SmallState layout");
+
 static int choose_tile_width(int n_files) {
     // 227 KB per CTA minus the per-warp read stages (raer_tile_smem_bytes) and slack
     int cw, sw;
@@ -240,11 +245,12 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
     c->n_tiles = P.n_tiles; c->W = P.W;
     int nl = 0;
     int rc;
-    if ((rc = c->small.ensure(64))) return rc;
-    CK(cudaMemsetAsync(c->small.p, 0, 64, c->stream));
+    if ((rc = c->small.ensure(sizeof(SmallState)))) return rc;
+    CK(cudaMemsetAsync(c->small.p, 0, sizeof(SmallState), c->stream));
     P.tile_counter = (unsigned int*)c->small.p;
     P.row_counter = (unsigned long long*)((char*)c->small.p + 8);
     P.err_flag = (int*)((char*)c->small.p + 16);
+    P.grow = (int*)((char*)c->small.p + offsetof(SmallState, grow));
     if (P.n_tiles > 0) {
         if ((rc = c->tile_ranges.ensure((size_t)P.n_tiles * nf * sizeof(int2)))) return rc;
         if ((rc = c->tile_rows.ensure((size_t)P.n_tiles * sizeof(int2)))) return rc;
@@ -315,7 +321,6 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
     return RAER_OK;
 }
 
-struct SmallState { unsigned tc, pad; unsigned long long rows; int err; int pad2[3]; int list_total; };
 
 // Wait for the batch enqueued by run_device(), re-running it when the device asked for it. b must be the batch
 // in device memory (qualities already rewritten by the mate-overlap kernel: re-runs skip it).
@@ -371,6 +376,7 @@ static int fetch_rows(raer_ctx* c, int nf, const SmallState& s, raer_rows* out) 
     out->n_files = nf;
     size_t n = (size_t)s.rows;
     out->n_rows = (int64_t)n;
+    for (int k = 0; k < 2 * RAER_MAX_FILES; ++k) out->grow_pos[k] = s.grow[k] ? 0x7fffffff - s.grow[k] : INT32_MAX;
     if (n == 0 || c->n_tiles == 0) return RAER_OK;
     std::vector<int2> tr(c->n_tiles);
     std::vector<int> pos(n);
@@ -814,6 +820,9 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             for (int64_t i = 0; i < rows.n_rows; ++i) {
                 int64_t o = out->nrows + i;
                 int s = rows.meta[i] & 1;
+                // tables grown by the puts of a site that wrote no row for that strand (src/plp.c:487)
+                for (int f = 0; f < nf; ++f)
+                    if (kh[f * 2 + s] == 4 && rows.grow_pos[f * 2 + s] < rows.pos[i]) kh[f * 2 + s] = 8;
                 out->tid[o] = tid;
                 out->pos[o] = rows.pos[i] + 1;
                 out->strand[o] = s ? '-' : '+';
@@ -827,6 +836,8 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
                                            out->alt + ((size_t)f * sink.cap + o) * 12);
                 }
             }
+            for (int k = 0; k < nf * 2; ++k)
+                if (kh[k] == 4 && rows.grow_pos[k] != INT32_MAX) kh[k] = 8;
             out->nrows += rows.n_rows;
             raer_rows_free(&rows);
             tm_sink += raer::now_seconds() - t0s;

@@ -346,3 +346,61 @@ def test_adversarial_oracle_runs(adversarial):
     oracle_backend.OVERLAP_MODE = 1
     assert len(res[1]) > 300
     assert len(res[1]) == len(res[2])
+
+
+# ---- khash growth at a site that writes no row (src/plp.c:487: every variant read is a kh_put) ------------------
+@pytest.fixture(scope="module")
+def growth(tmp_path_factory):
+    """Two BAMs. Site 30 (REF A) shows C, G, T in both; in the second file a fourth variant read follows, which
+    resizes that file's variant table from 4 to 8 buckets. min_variant_reads = 5 keeps the site out of the result.
+    Site 80 (REF C) shows T and A six times: the printed ALT order tells the table size (T,A with 4 buckets,
+    A,T with 8)."""
+    d = tmp_path_factory.mktemp("growth")
+    rng = np.random.default_rng(5)
+    ref = list("".join(rng.choice(list("ACGT"), size=400)))
+    ref[30], ref[80] = "A", "C"
+    ref = "".join(ref)
+    fa = str(d / "g.fa")
+    _write_ref(fa, {"c1": ref, "c2": "ACGT" * 75})
+    bams = []
+    for fno, first in enumerate([["C", "G", "T"], ["C", "G", "T", "C"]]):
+        lines = []
+        for i in range(10):
+            s = ref[10:50]
+            if i < len(first):
+                s = s[:20] + first[i] + s[21:]
+            lines.append(_sam(f"a{i}", 0, "c1", 11, 60, "40M", 0, 0, s, "I" * 40))
+        for i in range(10):
+            s = ref[60:100]
+            if i < 6:
+                s = s[:20] + ("T" if i % 2 == 0 else "A") + s[21:]
+            lines.append(_sam(f"b{i}", 0, "c1", 61, 60, "40M", 0, 0, s, "I" * 40))
+        bams.append(bamtools.sam_to_bam(str(d / f"g{fno}.bam"), HDR, lines))
+    return bams, fa
+
+
+def _growth_alt(res):
+    i = int(np.flatnonzero(res.pos == 81)[0])
+    return [str(x) for x in res.assay("ALT")[i]]
+
+
+def test_khash_growth_oracle(growth):
+    bams, fa = growth
+    res = oracle_backend.pileup_sites(bams, fa, param=FilterParam(library_type="unstranded", min_variant_reads=5))
+    assert list(res.pos) == [81]
+    assert _growth_alt(res) == ["T,A", "A,T"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["default", "generic"])
+def test_khash_growth_at_unwritten_site(growth, kernel, monkeypatch):
+    bams, fa = growth
+    if kernel == "generic":
+        monkeypatch.setenv("RAER_KERNEL", "generic")
+    for kw in (dict(min_variant_reads=5), dict(min_variant_reads=5, only_keep_variants=True), dict(min_depth=11)):
+        fp = FilterParam(library_type="unstranded", **kw)
+        want = oracle_backend.pileup_sites(bams, fa, param=fp)
+        got = _cuda()(bams, fa, param=fp)
+        _assert_same(got, want)
+    fp = FilterParam(library_type="unstranded", min_variant_reads=5)
+    assert _growth_alt(_cuda()(bams, fa, param=fp)) == ["T,A", "A,T"]
