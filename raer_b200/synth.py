@@ -300,6 +300,79 @@ def make_bulk_dataset(outdir: str, *, n_bams=2, n_contigs=2, contig_len=200_000,
     return {"fasta": fa, "bams": bams, "names": names, "lens": lens, "aligned_bases": n_bases}
 
 
+def make_sc_dataset(outdir: str, *, n_contigs=2, contig_len=60_000, reads_per_contig=20_000, n_cb=60, n_sites=400,
+                    seed=5001, gene_block=5_000, edit_frac=0.02) -> dict:
+    """Reference, one 10x-shaped BAM and a site list of the C5 shape at a chosen size: single-end
+    reads, flags 0/16 by gene block (+1024 on 20 %), CB:Z drawn Zipf(s=1) from `n_cb` whitelist barcodes with 1 %
+    of the reads without the tag and 1 % off the list, UB:Z 12-mers with about 3 reads per (CB, UMI, 150-base locus)
+    (2 % without the tag), sites = A positions of plus genes / T positions of minus genes (REF A, ALT G in the
+    strand's own orientation) plus a few C>T sites."""
+    os.makedirs(outdir, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    names = [f"chr{i + 1}" for i in range(n_contigs)]
+    lens = [contig_len] * n_contigs
+    refs = make_reference(lens, seed)
+    fa = os.path.join(outdir, "ref.fa")
+    write_fasta(fa, names, refs)
+    acgt = np.array(list("ACGT"))
+    whitelist = ["".join(acgt[rng.integers(0, 4, 16)]) + "-1" for _ in range(n_cb)]
+    zipf = 1.0 / np.arange(1, n_cb + 1)
+    zipf /= zipf.sum()
+    per, cbs, ubs = [], [], []
+    for t in range(n_contigs):
+        r = gen_contig(refs[t], reads_per_contig, seed + 17 * (t + 1), single_end=True, gene_block=gene_block,
+                       edit_frac=edit_frac)
+        n = r.pos.numel()
+        dup = torch.from_numpy(rng.random(n) < 0.2)
+        r.flag = r.flag | (dup.int() * 1024)
+        per.append(r)
+        cb_idx = rng.choice(n_cb, size=n, p=zipf)
+        # reads of one molecule start within 150 bases of each other, so that their sites overlap
+        locus = r.pos.numpy() // 150
+        key = cb_idx.astype(np.int64) * 1_000_000 + locus
+        _, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
+        k = np.maximum(cnt[inv] // 3, 1)
+        u = (rng.random(n) * k).astype(np.int64)
+        h = (key * 1_000_003 + u * 7919 + 12345) % (1 << 24)
+        u_cb, u_ub = rng.random(n), rng.random(n)
+        for i in range(n):
+            if u_cb[i] < 0.01:
+                cbs.append(None)
+            elif u_cb[i] < 0.02:
+                cbs.append("".join(acgt[rng.integers(0, 4, 16)]) + "-9")
+            else:
+                cbs.append(whitelist[cb_idx[i]])
+            ubs.append(None if u_ub[i] < 0.02 else "".join(acgt[(int(h[i]) >> (2 * j)) & 3] for j in range(12)))
+    bam = os.path.join(outdir, "sc.bam")
+    write_bam(bam, names, lens, per, qname_prefix="sc_", tags={"CB": cbs, "UB": ubs})
+    sn, sp, ss, sr, sa = [], [], [], [], []
+    for t in range(n_contigs):
+        ref = refs[t].numpy()
+        # half of the candidates are positions gen_contig edits (same generator and seed as its `editable` mask)
+        g2 = torch.Generator()
+        g2.manual_seed((seed + 17 * (t + 1)) * 7919 + 13)
+        ed = np.flatnonzero((torch.rand(contig_len, generator=g2) < edit_frac).numpy())
+        ed = ed[(ed >= 200) & (ed < contig_len - 200)]
+        rnd = rng.choice(np.arange(200, contig_len - 200), size=min(4 * n_sites, contig_len - 400), replace=False)
+        pos = np.unique(np.concatenate([ed, rnd]))
+        took = 0
+        for p0 in pos:
+            minus = (p0 // gene_block) % 2 == 1
+            b = ref[p0]
+            if (not minus and b == 0) or (minus and b == 3):
+                ra = ("A", "G")
+            elif took % 7 == 0 and ((not minus and b == 1) or (minus and b == 2)):
+                ra = ("C", "T")
+            else:
+                continue
+            sn.append(names[t]); sp.append(int(p0) + 1); ss.append("-" if minus else "+"); sr.append(ra[0]); sa.append(ra[1])
+            took += 1
+            if took >= n_sites:
+                break
+    return {"fasta": fa, "bam": bam, "barcodes": whitelist, "names": names,
+            "sites": dict(seqnames=sn, start=sp, strand=ss, ref=sr, alt=sa)}
+
+
 # --------------------------------------------------------------------------------------- device batches
 def pack_device_batch(per_file: List[Reads], tid: int, beg: int, end: int, remove_overlaps: bool = True):
     """Lay out the reads of one contig (all files) as a raer_read_batch in the memory of their
