@@ -39,12 +39,16 @@ CONFIGS = [
 
 
 def test_sc_dataset_is_informative(sc, tmp_path):
-    fp = FilterParam(library_type="fr-second-strand", min_mapq=255, min_variant_reads=1)
+    fp = FilterParam(library_type="fr-second-strand", min_depth=0)
     sce = oracle_backend.pileup_cells(sc["bam"], sc["gr"], sc["barcodes"], str(tmp_path), param=fp)
     assert sce.shape == (len(sc["gr"]), len(sc["barcodes"]))
-    assert sce.nRef.sum() > 1000 and sce.nAlt.sum() > 20
+    assert sce.nRef.sum() > 1000 and sce.nAlt.sum() > 200
     noumi = oracle_backend.pileup_cells(sc["bam"], sc["gr"], sc["barcodes"], str(tmp_path), umi_tag=None, param=fp)
-    assert noumi.nRef.sum() > sce.nRef.sum()  # UMI consensus collapses duplicates
+    assert noumi.nRef.sum() > 1.2 * sce.nRef.sum()  # UMI consensus collapses duplicates
+    # the C5 call keeps the sites with a variant read only
+    fp = FilterParam(library_type="fr-second-strand", min_mapq=255, min_variant_reads=1)
+    c5 = oracle_backend.pileup_cells(sc["bam"], sc["gr"], sc["barcodes"], str(tmp_path), param=fp)
+    assert 100 < c5.shape[0] < len(sc["gr"])
 
 
 @pytest.mark.gpu
