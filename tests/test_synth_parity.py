@@ -404,3 +404,40 @@ def test_khash_growth_at_unwritten_site(growth, kernel, monkeypatch):
         _assert_same(got, want)
     fp = FilterParam(library_type="unstranded", min_variant_reads=5)
     assert _growth_alt(_cuda()(bams, fa, param=fp)) == ["T,A", "A,T"]
+
+
+# ---- C3 shape: eight BAMs, a list of A (+) / T (-) reference positions as width-1 sites, min_depth = 2,
+# as one eight-file call and as eight one-file calls
+@pytest.fixture(scope="module")
+def syn8(tmp_path_factory):
+    from raer_b200 import synth
+
+    d = tmp_path_factory.mktemp("syn8")
+    ds = synth.make_bulk_dataset(str(d), n_bams=8, n_contigs=2, contig_len=50_000, pairs_per_contig=3000, seed=3001)
+    rng = np.random.default_rng(3000)
+    names, pos = [], []
+    for t, nm in enumerate(ds["names"]):
+        ref = synth.make_reference(ds["lens"], 3001)[t].numpy()
+        cand = np.flatnonzero((ref == 0) | (ref == 3))
+        pick = np.sort(rng.choice(cand, size=5000, replace=False))
+        names += [nm] * len(pick)
+        pos += (pick + 1).tolist()
+    ds["sites"] = Sites(names, pos)
+    return ds
+
+
+@pytest.mark.gpu
+def test_known_sites_eight_bams(syn8):
+    fp = FilterParam(min_depth=2)
+    want = oracle_backend.pileup_sites(syn8["bams"], syn8["fasta"], syn8["sites"], param=fp)
+    got = _cuda()(syn8["bams"], syn8["fasta"], syn8["sites"], param=fp)
+    _assert_same(got, want)
+    assert 1000 < len(want) <= 2 * len(syn8["sites"])
+    assert set(np.unique(want.REF)) <= {"A", "T"}
+    # one file per call (one BAM per GPU in the C3 layout): the same counts as that file's column wherever both have the row
+    one = _cuda()(syn8["bams"][3], syn8["fasta"], syn8["sites"], param=fp)
+    _assert_same(one, oracle_backend.pileup_sites(syn8["bams"][3], syn8["fasta"], syn8["sites"], param=fp))
+    key = {(s, p, st): i for i, (s, p, st) in enumerate(zip(want.seqnames, want.pos, want.strand))}
+    idx = np.array([key[(s, p, st)] for s, p, st in zip(one.seqnames, one.pos, one.strand)])
+    for k in ("nRef", "nAlt", "nA", "nT", "nC", "nG"):
+        assert np.array_equal(one.assay(k)[:, 0], want.assay(k)[idx, 3])
