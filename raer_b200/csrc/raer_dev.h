@@ -71,6 +71,7 @@ struct PlpParams {
     unsigned long long* row_counter;
     int2* tile_rows;                 // per tile {first row, n rows}
     int* err_flag;
+    unsigned long long* phase_clk;   // development (RAER_PHASE_PROF): per-phase clock sums of the fast tile kernel, or nullptr
     int* grow;                       // [n_files * 2]: 0x7fffffff - first position at which the puts of an UNWRITTEN
                                      // (file, strand) grew its khash from 4 to 8 buckets (0 = none)
     // shared memory plan

@@ -689,6 +689,27 @@ __device__ void slot_stats(const PlpParams& P, const uint32_t* slot, int HW, int
     }
 }
 
+// development aid: thread 0 adds the cycles since the previous mark to phase_clk[k]
+#define PHASE_MARK(k)                                                                   \
+    do {                                                                                \
+        if (P.phase_clk && threadIdx.x == 0) {                                          \
+            const long long now_ = clock64();                                           \
+            atomicAdd(&P.phase_clk[k], (unsigned long long)(now_ - ph_t));              \
+            ph_t = now_;                                                                \
+        }                                                                               \
+    } while (0)
+// ... and lane 0 of every warp the cycles it waited at the barrier that ends a warp-autonomous phase
+#define PHASE_BARRIER(k)                                                                \
+    do {                                                                                \
+        if (P.phase_clk) {                                                              \
+            const long long a_ = clock64();                                             \
+            __syncthreads();                                                            \
+            if (lane == 0) atomicAdd(&P.phase_clk[k], (unsigned long long)(clock64() - a_)); \
+        } else {                                                                        \
+            __syncthreads();                                                            \
+        }                                                                               \
+    } while (0)
+
 template <bool EXT>
 __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -723,12 +744,14 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
     X.SW = T2.slot_words;
     X.round0 = 0;
     X.ns = 0;
+    long long ph_t = clock64();
 
     while (true) {
         if (threadIdx.x == 0) s_tile = (int)atomicAdd(P.tile_counter, 1u);
         __syncthreads();
         const int tile = s_tile;
         if (tile >= P.n_tiles) break;
+        PHASE_MARK(0);  // tile fetch (and what follows the last mark of the previous tile)
         const int t0 = P.t_beg + tile * W;
         const int t1 = min(t0 + W, P.t_end);
         X.t0 = t0;
@@ -747,6 +770,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
         }
         if (threadIdx.x == 0) { s_nflag = 0; s_deep = 0; s_chunk = 0; }
         __syncthreads();
+        PHASE_MARK(1);  // clear + reference packing
         if (P.tile_off[tile * F + F] > P.tile_list_cap) {  // lists overflowed their allocation: the host re-runs the batch
             if (threadIdx.x == 0) {
                 atomicCAS(P.err_flag, 0, RAER_RETRY_LISTCAP);
@@ -770,7 +794,8 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
                 fast_count_chunk<EXT>(P, S, X, tile, l0 + ((nchunks - 1 - c) << 5), l1, t1, lane, st, need_cov);
             }
         }
-        __syncthreads();
+        PHASE_BARRIER(8);
+        PHASE_MARK(2);  // phase 1
 
         // ---- coverage: prefix sum of the events, one warp per (file, strand)
         for (int a = wid; a < 2 * F; a += FB_THREADS / 32) {
@@ -796,6 +821,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
             }
         }
         __syncthreads();
+        PHASE_MARK(3);  // coverage prefix sums
         if (s_deep && threadIdx.x == 0) atomicCAS(P.err_flag, 0, RAER_RETRY_DEEP);  // 16-bit class counters cannot hold this tile
 
         // ---- phase 2: decide, reserve rows, write them in (pos, strand) order
@@ -887,6 +913,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
             if (threadIdx.x == 0) { s_nflag = fcarried; S.fpre[W] = (uint16_t)fcarried; }
         }
         __syncthreads();
+        PHASE_MARK(4);  // decide + rows
 
         // ---- phases 3+4: second pass over the sites that carry a variant, `spr` sites per round
         const int nflag = s_nflag;
@@ -917,13 +944,15 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
                     fast_pair_chunk<EXT>(P, S, X, T2, tile, l0 + ((nchunks - 1 - c) << 5), l1, lane, st);
                 }
             }
-            __syncthreads();
+            PHASE_BARRIER(9);
+            PHASE_MARK(5);  // second pass (slot clear + pairs)
             for (int i = threadIdx.x; i < ns; i += blockDim.x) {
                 const int d = S.flag_d[round0 + i], row = S.flag_row[round0 + i];
                 slot_stats(P, S.cnt + (size_t)i * SW, HW, ((d & 1) && (d & 4)) ? row : -1,
                            ((d & 2) && (d & 8)) ? row + (d & 1) : -1, d >> 4, t0 + (int)S.flag_pidx[round0 + i]);
             }
             __syncthreads();
+            PHASE_MARK(6);  // statistics
         }
         __syncthreads();
     }

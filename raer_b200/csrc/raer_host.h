@@ -47,6 +47,7 @@ public:
     const std::vector<int32_t>& lengths() const { return lens_; }
     int name2tid(const std::string& n) const;
     double decode_seconds() const { return t_decode_; }
+    double wait_seconds() const { return t_wait_; }  // time the parser waited for an inflated group
     int64_t records_read() const { return n_records_; }
 
 private:
@@ -66,6 +67,7 @@ private:
     bool has_region_ = false, region_done_ = false;
     int r_tid_ = -1, r_beg_ = 0, r_end_ = 0;
     double t_decode_ = 0;
+    double t_wait_ = 0;
     int64_t n_records_ = 0;
     // prefetch: while the parser walks ubuf_, a task inflates the following group (it owns fp_, cbuf_, c_off_,
     // file_eof_ and t_decode_ until fill() collects it)
@@ -115,6 +117,76 @@ struct HostRead {
     uint32_t umi;
 };
 
+// qname -> the earlier mate waiting for its partner (htslib overlap_push's khash). Open addressing with the names in
+// an arena: no allocation per read. Entries whose read has left the pileup buffer are dead; find() callers treat them
+// as absent and rebuild() drops them.
+struct QnameTable {
+    struct Ent {
+        uint64_t h;
+        uint32_t off;
+        uint16_t len;
+        uint8_t state;  // 0 empty, 1 live, 2 deleted
+        bool keep_a;
+        int64_t ordinal;
+        int32_t tid, end;
+    };
+    std::vector<Ent> tab;
+    std::vector<char> arena;
+    size_t live = 0, used = 0;  // used = live + deleted slots
+    static uint64_t hash(const char* s, size_t n) {
+        uint64_t h = 1469598103934665603ull;
+        for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)s[i]; h *= 1099511628211ull; }
+        return h ^ (h >> 29);
+    }
+    size_t size() const { return live; }
+    void clear() { tab.clear(); arena.clear(); live = used = 0; }
+    Ent* find(const char* q, size_t n, uint64_t h) {
+        if (tab.empty()) return nullptr;
+        const size_t mask = tab.size() - 1;
+        for (size_t i = h & mask; tab[i].state; i = (i + 1) & mask)
+            if (tab[i].state == 1 && tab[i].h == h && tab[i].len == n && !memcmp(arena.data() + tab[i].off, q, n)) return &tab[i];
+        return nullptr;
+    }
+    void erase(Ent* e) { e->state = 2; --live; }
+    template <class Dead>
+    void rebuild(Dead dead) {
+        std::vector<Ent> keep;
+        keep.reserve(live);
+        for (const Ent& e : tab)
+            if (e.state == 1 && !dead(e)) keep.push_back(e);
+        size_t cap = 4096;
+        while (cap < 4 * keep.size()) cap <<= 1;
+        std::vector<char> na;
+        na.reserve(arena.size() / 2 + 64);
+        tab.assign(cap, Ent{});
+        const size_t mask = cap - 1;
+        for (Ent e : keep) {
+            const uint32_t off = (uint32_t)na.size();
+            na.insert(na.end(), arena.data() + e.off, arena.data() + e.off + e.len);
+            e.off = off;
+            size_t i = e.h & mask;
+            while (tab[i].state) i = (i + 1) & mask;
+            tab[i] = e;
+        }
+        arena.swap(na);
+        live = used = keep.size();
+    }
+    // the key must be absent (find() returned nullptr)
+    template <class Dead>
+    void insert(const char* q, size_t n, uint64_t h, int64_t ordinal, int tid, int end, bool keep_a, Dead dead) {
+        if (tab.empty() || (used + 1) * 10 > tab.size() * 7 || arena.size() > 64 * tab.size()) rebuild(dead);
+        const size_t mask = tab.size() - 1;
+        size_t i = h & mask;
+        while (tab[i].state == 1) i = (i + 1) & mask;
+        if (tab[i].state == 0) ++used;
+        Ent& e = tab[i];
+        e.h = h; e.off = (uint32_t)arena.size(); e.len = (uint16_t)n; e.state = 1; e.keep_a = keep_a;
+        e.ordinal = ordinal; e.tid = tid; e.end = end;
+        arena.insert(arena.end(), q, q + n);
+        ++live;
+    }
+};
+
 struct FilePending {
     BamStream bs;
     std::vector<HostRead> reads;
@@ -126,14 +198,17 @@ struct FilePending {
     bool have_look = false;  // a parsed record waiting in `look`
     HostRead look;
     std::vector<uint32_t> look_cigar;
-    std::vector<uint8_t> look_seq, look_qual;
+    const uint8_t* look_seq = nullptr;   // into the stream buffer: valid until the next record is read
+    const uint8_t* look_qual = nullptr;
     int look_tid = -1;
     // stream-order state (bam_plp_push emulation)
     int64_t next_ordinal = 0;
     int prev_tid = 0, prev_pos = 0;
-    struct OlEnt { int64_t ordinal; int tid; int end; bool keep_a; };
-    std::unordered_map<std::string, OlEnt> olap;
-    std::priority_queue<int, std::vector<int>, std::greater<int>> live_ends;
+    QnameTable olap;
+    // ends of the reads pushed on the current contig; entries below the iterator position are dead and are
+    // dropped lazily (the count is only needed when a read starts where the previous one did)
+    std::vector<int32_t> live_ends;
+    size_t live_compact_at = 4096;
     int live_tid = -1;
     int64_t n_aligned_bases = 0;
     // bulk UMI mode: earlier reads of each (strand, UMI) that can still be in the pileup, and per read the
@@ -179,6 +254,8 @@ public:
     int reg_end() const { return reg_end_; }
     double decode_seconds() const;
     double pack_seconds() const { return t_pack_; }
+    double parse_seconds() const { return t_parse_; }  // wall time of the parse section of next_batch (all files side by side)
+    double wait_seconds() const;
     int64_t records() const;
     int64_t aligned_bases() const;
     std::unordered_map<std::string, uint32_t>& umi_dict() { return umi_dict_; }
@@ -195,6 +272,7 @@ private:
     int reg_tid_ = -1, reg_beg_ = 0, reg_end_ = INT32_MAX;
     bool has_region_ = false;
     double t_pack_ = 0;
+    double t_parse_ = 0;
     std::unordered_map<std::string, uint32_t> umi_dict_;
 };
 

@@ -144,7 +144,9 @@ bool BamStream::fill() {
     int rc;
     std::vector<uint8_t> grp;
     if (pf_.valid()) {
+        const double tw = now_seconds();
         rc = pf_.get();
+        t_wait_ += now_seconds() - tw;
         grp.swap(pf_buf_);
     } else {
         rc = produce(grp);
@@ -561,6 +563,11 @@ bool Ingest::open(const char* const* paths, const char* const* indexes, int thre
     return true;
 }
 
+double Ingest::wait_seconds() const {
+    double t = 0;
+    for (auto* f : files_) t += f->bs.wait_seconds();
+    return t;
+}
 double Ingest::decode_seconds() const {
     double t = 0;
     for (auto* f : files_) t += f->bs.decode_seconds();
@@ -646,15 +653,22 @@ bool Ingest::parse_one(int fi) {
 
         // ---- stream-order decisions of bam_plp_push
         if (F.live_tid != r.tid) {
-            while (!F.live_ends.empty()) F.live_ends.pop();
+            F.live_ends.clear();
             F.live_tid = r.tid;
-        } else {
-            while (!F.live_ends.empty() && F.live_ends.top() < F.prev_pos) F.live_ends.pop();
         }
-        int cnt = (int)F.live_ends.size() + 1;
-        if (F.prev_tid == r.tid && F.prev_pos == r.pos && cnt > conf_.max_depth) {
-            if (conf_.remove_overlaps) F.olap.erase(std::string(r.qname));
-            continue;  // dropped by maxcnt
+        // the mempool count of bam_plp_push: reads still in the buffer (end >= position of the last pushed read) + 1.
+        // It only matters for a read that starts where the previous one did, and only once that many were pushed.
+        if (F.prev_tid == r.tid && F.prev_pos == r.pos && (int64_t)F.live_ends.size() + 1 > conf_.max_depth) {
+            const int32_t lim = F.prev_pos;
+            F.live_ends.erase(std::remove_if(F.live_ends.begin(), F.live_ends.end(), [lim](int32_t e) { return e < lim; }),
+                              F.live_ends.end());
+            if ((int64_t)F.live_ends.size() + 1 > conf_.max_depth) {
+                if (conf_.remove_overlaps) {
+                    const size_t qn = strlen(r.qname);
+                    if (QnameTable::Ent* e = F.olap.find(r.qname, qn, QnameTable::hash(r.qname, qn))) F.olap.erase(e);
+                }
+                continue;  // dropped by maxcnt
+            }
         }
         HostRead& H = F.look;
         memset(&H, 0, sizeof(H));
@@ -703,27 +717,26 @@ bool Ingest::parse_one(int fi) {
             long long isz = r.isize < 0 ? -(long long)r.isize : r.isize;
             if ((r.mtid >= 0 && r.tid != r.mtid) || (isz >= 2LL * r.l_qseq && r.mpos >= H.h.end)) eligible = false;
             if (eligible) {
-                std::string q(r.qname);
-                auto it = F.olap.find(q);
+                const size_t qn = strlen(r.qname);
+                const uint64_t qh = QnameTable::hash(r.qname, qn);
                 // an entry is gone once its read left the pileup buffer (end < position of the last pushed read)
-                if (it != F.olap.end() && (it->second.tid != r.tid || it->second.end < F.prev_pos)) {
+                const int cur_tid = r.tid, cur_prev = F.prev_pos;
+                auto dead = [cur_tid, cur_prev](const QnameTable::Ent& e) { return e.tid != cur_tid || e.end < cur_prev; };
+                QnameTable::Ent* it = F.olap.find(r.qname, qn, qh);
+                if (it && dead(*it)) {
                     F.olap.erase(it);
-                    it = F.olap.end();
+                    it = nullptr;
                 }
-                if (it == F.olap.end()) {
+                if (!it) {
                     if (r.mpos >= r.pos || ((r.flag & 1) && r.mpos == -1)) {
                         bool keep_a = (wang(x31(r.qname)) & 1) != 0;
-                        F.olap[q] = {H.ordinal, r.tid, H.h.end, keep_a};
+                        F.olap.insert(r.qname, qn, qh, H.ordinal, r.tid, H.h.end, keep_a, dead);
                     }
                 } else {
-                    H.mate_ord = it->second.ordinal;
-                    if (it->second.keep_a) bits |= RAER_RB_KEEP_A;
+                    H.mate_ord = it->ordinal;
+                    if (it->keep_a) bits |= RAER_RB_KEEP_A;
                     F.olap.erase(it);
                 }
-            }
-            if (F.olap.size() > 4000000) {  // purge entries whose reads have left the buffer
-                for (auto it = F.olap.begin(); it != F.olap.end();)
-                    it = (it->second.tid != r.tid || it->second.end < F.prev_pos) ? F.olap.erase(it) : std::next(it);
             }
         }
         if (conf_.bulk_umi) {
@@ -792,7 +805,13 @@ bool Ingest::parse_one(int fi) {
         H.h.bits = bits;
         F.prev_tid = r.tid;
         F.prev_pos = r.pos;
-        F.live_ends.push(H.h.end);
+        F.live_ends.push_back(H.h.end);
+        if (F.live_ends.size() > F.live_compact_at) {  // every later check asks for ends >= a position >= this one
+            const int32_t lim = r.pos;
+            F.live_ends.erase(std::remove_if(F.live_ends.begin(), F.live_ends.end(), [lim](int32_t e) { return e < lim; }),
+                              F.live_ends.end());
+            F.live_compact_at = std::max<size_t>(4096, 2 * F.live_ends.size());
+        }
         if (conf_.sc) {
             if (!conf_.umi_tag.empty()) {
                 const char* u = aux_z(r, conf_.umi_tag);
@@ -802,8 +821,8 @@ bool Ingest::parse_one(int fi) {
                 }
             }
         }
-        F.look_seq.assign(r.seq, r.seq + (r.l_qseq + 1) / 2);
-        F.look_qual.assign(r.qual, r.qual + r.l_qseq);
+        F.look_seq = r.seq;  // the stream buffer keeps the record until the next one is asked for
+        F.look_qual = r.qual;
         F.look_tid = r.tid;
         F.have_look = true;
         return true;
@@ -823,11 +842,11 @@ bool Ingest::parse_ahead(int fi, size_t want) {
         H.h.cigar_off = (uint32_t)(F.cigar.size());
         H.h.sq_off = (uint32_t)(F.seq.size());
         F.cigar.insert(F.cigar.end(), F.look_cigar.begin(), F.look_cigar.end());
-        F.seq.insert(F.seq.end(), F.look_seq.begin(), F.look_seq.end());
+        F.seq.insert(F.seq.end(), F.look_seq, F.look_seq + (H.h.l_qseq + 1) / 2);
         // every read starts on a 4-byte (sequence) / 8-byte (quality) boundary: the kernels fetch 8 bases
         // per load; qualities live at 2 * sq_off
         while (F.seq.size() & 3) F.seq.push_back(0xff);
-        F.qual.insert(F.qual.end(), F.look_qual.begin(), F.look_qual.end());
+        F.qual.insert(F.qual.end(), F.look_qual, F.look_qual + H.h.l_qseq);
         F.qual.resize(2 * F.seq.size(), 0);
         if (H.mate_ord >= 0 && F.front < F.reads.size()) {
             // htslib's overlap pass can rewrite qualities of the later mate far beyond the earlier mate's
@@ -861,6 +880,7 @@ bool Ingest::next_batch(PackedBatch& out) {
     const int nf = conf_.n_files;
     size_t want = (size_t)std::max<int64_t>(16, conf_.target_reads / nf);
     int boundary;
+    const double t0p = now_seconds();
     while (true) {
         boundary = INT_MAX;
         bool all_done = true;
@@ -886,6 +906,7 @@ bool Ingest::next_batch(PackedBatch& out) {
         want *= 2;  // every pending read starts at the window start: look further
     }
     double t0 = now_seconds();
+    t_parse_ += t0 - t0p;
     // reads of each file starting before the boundary
     std::vector<size_t> upto(nf);
     size_t n_reads = 0, n_cig = 0, n_sq = 0;

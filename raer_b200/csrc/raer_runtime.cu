@@ -80,6 +80,7 @@ struct raer_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6];
     DevBuf hdr, maxend, cigar, seq, qual, pair_b, mask;
+    DevBuf phase_clk;                      // RAER_PHASE_PROF: 16 clock sums of k_pileup_fast
     DevBuf aei;                            // aei_mode: [n_files][16] sums of the batch
     std::vector<int64_t> last_aei;
     DevBuf umi_holes;                      // bulk UMI mode: (read, position) pairs that stay counted
@@ -123,6 +124,18 @@ extern "C" raer_ctx* raer_ctx_create(int32_t device) {
 extern "C" void raer_ctx_destroy(raer_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->phase_clk.p) {
+        unsigned long long v[16];
+        cudaDeviceSynchronize();
+        if (cudaMemcpy(v, c->phase_clk.p, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            double tot = 0;
+            for (int k = 0; k < 7; ++k) tot += (double)v[k];
+            fprintf(stderr, "[raer phase prof] CTA cycles: fetch %.1f%% clear %.1f%% phase1 %.1f%% coverage %.1f%% decide+rows %.1f%% "
+                            "pass2 %.1f%% stats %.1f%% | barrier wait, warp cycles / (16 x CTA cycles): phase1 %.1f%% pass2 %.1f%%\n",
+                    100 * v[0] / tot, 100 * v[1] / tot, 100 * v[2] / tot, 100 * v[3] / tot, 100 * v[4] / tot, 100 * v[5] / tot,
+                    100 * v[6] / tot, 100 * v[8] / (16 * tot), 100 * v[9] / (16 * tot));
+        }
+    }
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->hdr, &c->maxend, &c->cigar, &c->seq, &c->qual, &c->pair_b, &c->mask, &c->tile_ranges, &c->tile_rows, &c->tile_idx, &c->tile_list, &c->ov_scratch, &c->umi_holes, &c->aei,
                       &c->small, &c->row_pos, &c->row_meta, &c->row_stats, &c->row_counts, &c->row_alt, &c->ref})
@@ -251,6 +264,14 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
     P.row_counter = (unsigned long long*)((char*)c->small.p + 8);
     P.err_flag = (int*)((char*)c->small.p + 16);
     P.grow = (int*)((char*)c->small.p + offsetof(SmallState, grow));
+    P.phase_clk = nullptr;
+    if (getenv("RAER_PHASE_PROF")) {
+        if (!c->phase_clk.p) {
+            if ((rc = c->phase_clk.ensure(16 * 8))) return rc;
+            CK(cudaMemsetAsync(c->phase_clk.p, 0, 16 * 8, c->stream));
+        }
+        P.phase_clk = (unsigned long long*)c->phase_clk.p;
+    }
     if (P.n_tiles > 0) {
         if ((rc = c->tile_ranges.ensure((size_t)P.n_tiles * nf * sizeof(int2)))) return rc;
         if ((rc = c->tile_rows.ensure((size_t)P.n_tiles * sizeof(int2)))) return rc;
@@ -927,6 +948,10 @@ extern "C" int raer_ingest_summary(const raer_pileup_args* a, int64_t target_rea
     }
     out[5] = ing.aligned_bases();
     out[6] = ing.records();
+    if (getenv("RAER_TIMING"))
+        fprintf(stderr, "[raer ingest] parse sections %.3f s (of which the parsers waited %.3f s, summed over files, for inflate), "
+                        "pack sections %.3f s, inflate tasks %.3f s summed over files\n",
+                ing.parse_seconds(), ing.wait_seconds(), ing.pack_seconds(), ing.decode_seconds());
     return RAER_OK;
 }
 
