@@ -37,7 +37,8 @@ struct BamRecView {  // points into the stream's inflate buffer; valid until the
 class BamStream {
 public:
     ~BamStream();
-    bool open(const char* path, int threads);
+    // light: the caller will seek with set_region(): read the header in small groups, no read-ahead before the seek
+    bool open(const char* path, int threads, bool light = false);
     // restrict to [beg, end) of tid using the BAI linear index; returns false on a missing/bad index
     bool set_region(const char* bai_path, int tid, int beg, int end);
     // 0 ok, -1 EOF (or past the region), -2 error
@@ -74,6 +75,7 @@ private:
     std::vector<uint8_t> pf_buf_;
     std::future<int> pf_;
     bool drained_ = false;  // produce() reported the end of the file
+    bool light_ = false;
 };
 
 // sorted, merged-on-query interval index (htslib regidx semantics: 0-based inclusive)

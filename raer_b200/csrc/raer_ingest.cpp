@@ -56,7 +56,8 @@ struct BlockJob {
 
 int BamStream::produce(std::vector<uint8_t>& out) {
     double t0 = now_seconds();
-    const size_t kChunk = 32u << 20, kMaxOut = 12u << 20;  // small groups: the next one inflates while this one is parsed
+    // small groups: the next one inflates while this one is parsed (light: just the header, a seek follows)
+    const size_t kChunk = light_ ? (1u << 20) : (32u << 20), kMaxOut = light_ ? (256u << 10) : (12u << 20);
     out.clear();
     std::vector<BlockJob> jobs;
     size_t out_off = 0;
@@ -163,7 +164,7 @@ bool BamStream::fill() {
     }
     u_off_ = 0;
     // the next group is inflated while the caller parses this one
-    pf_ = std::async(std::launch::async, [this]() { return produce(pf_buf_); });
+    if (!light_) pf_ = std::async(std::launch::async, [this]() { return produce(pf_buf_); });
     return true;
 }
 
@@ -194,10 +195,11 @@ bool BamStream::read_header() {
     return true;
 }
 
-bool BamStream::open(const char* path, int threads) {
+bool BamStream::open(const char* path, int threads, bool light) {
     fp_ = fopen(path, "rb");
     if (!fp_) { set_error("failed to open %s", path); return false; }
     threads_ = threads > 0 ? threads : 1;
+    light_ = light;
     return read_header();
 }
 
@@ -254,6 +256,7 @@ bool BamStream::set_region(const char* bai_path, int tid, int beg, int end) {
         }
         o += 8L * n_intv;
     }
+    light_ = false;
     if (!found) { region_done_ = true; return true; }  // no alignments on that contig
     if (pf_.valid()) pf_.get();  // the prefetch started after the header holds bytes from the wrong place
     pf_buf_.clear();
@@ -540,7 +543,7 @@ bool Ingest::open(const char* const* paths, const char* const* indexes, int thre
     for (int i = 0; i < conf_.n_files; ++i) {
         FilePending* f = new FilePending();
         files_.push_back(f);
-        if (!f->bs.open(paths[i], threads)) return false;
+        if (!f->bs.open(paths[i], threads, region != nullptr)) return false;
     }
     if (region) {
         int rb, re;

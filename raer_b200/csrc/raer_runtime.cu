@@ -7,6 +7,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -782,87 +788,239 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
     ResultSink sink;
     sink.r = out;
     std::vector<int32_t> kh(nf * 2, 4);  // khash bucket count of every (file, strand) variant table
-    raer::PackedBatch pb;
     std::vector<uint32_t> mask;
     int rc = RAER_OK;
-    int tid;
-    int contig_no = 0;
-    while (rc == RAER_OK && (tid = ing.next_contig()) >= 0) {
-        bool mine = a->shard_count <= 1 || (contig_no % a->shard_count) == a->shard_index;
-        ++contig_no;
-        std::string seq;
-        double t0f = raer::now_seconds();
-        bool have_ref = raer::fasta_fetch(a->fapath, names[tid], seq);
-        if (!have_ref) seq.clear();  // reference: every site reads as 'N' and is skipped
-        if (mine) {
-            rc = raer_ctx_set_reference(ctx, tid, seq.data(), (int64_t)seq.size());
-            if (rc) break;
-        }
-        tm_fasta += raer::now_seconds() - t0f;
-        const raer::RegionIndex::Chr* rchr = has_ridx ? ridx.find(names[tid]) : nullptr;
-        while (rc == RAER_OK) {
-            double t0b = raer::now_seconds();
-            const bool got = ing.next_batch(pb);
-            tm_batch += raer::now_seconds() - t0b;
-            if (!got) break;
-            if (!mine || pb.b.n_reads == 0 || pb.b.end <= pb.b.beg) continue;
-            if (has_ridx && !rchr) continue;
-            bc.reg_beg = ing.reg_tid() >= 0 ? ing.reg_beg() : 0;
-            bc.reg_end = ing.reg_tid() >= 0 ? ing.reg_end() : INT_MAX;
-            bc.site_mask = nullptr;
-            if (has_ridx) {  // bitmap of eligible positions inside the batch window
-                int wb = pb.b.beg, we = pb.b.end;
-                size_t words = ((size_t)(we - wb) + 31) / 32;
-                mask.assign(words, 0);
-                size_t k = std::lower_bound(rchr->maxend.begin(), rchr->maxend.end(), wb) - rchr->maxend.begin();
-                for (; k < rchr->beg.size() && rchr->beg[k] < we; ++k) {
-                    int lo = std::max(rchr->beg[k], wb), hi = std::min(rchr->end[k] + 1, we);
-                    for (int p = lo; p < hi; ++p) mask[(p - wb) >> 5] |= 1u << ((p - wb) & 31);
-                }
-                bc.site_mask = mask.data();
-                bc.mask_beg = wb;
-                bc.mask_bits = we - wb;
+
+    // One batch on the device: region / site bitmap, kernels, rows back in host memory.
+    auto gpu_batch = [&](const raer::RegionIndex::Chr* rchr, int reg_beg, int reg_end, raer::PackedBatch& pb, raer_rows* rows) -> int {
+        bc.reg_beg = reg_beg;
+        bc.reg_end = reg_end;
+        bc.site_mask = nullptr;
+        if (has_ridx) {  // bitmap of eligible positions inside the batch window
+            int wb = pb.b.beg, we = pb.b.end;
+            size_t words = ((size_t)(we - wb) + 31) / 32;
+            mask.assign(words, 0);
+            size_t k = std::lower_bound(rchr->maxend.begin(), rchr->maxend.end(), wb) - rchr->maxend.begin();
+            for (; k < rchr->beg.size() && rchr->beg[k] < we; ++k) {
+                int lo = std::max(rchr->beg[k], wb), hi = std::min(rchr->end[k] + 1, we);
+                for (int p = lo; p < hi; ++p) mask[(p - wb) >> 5] |= 1u << ((p - wb) & 31);
             }
-            raer_rows rows;
-            double t0g = raer::now_seconds();
-            rc = raer_batch_pileup_host(ctx, &bc, &pb.b, &rows);
-            tm_gpu += raer::now_seconds() - t0g;
-            if (rc) break;
-            if (bc.aei_mode) {
-                std::vector<int64_t> sums((size_t)nf * 16);
-                rc = raer_ctx_last_aei(ctx, sums.data(), nf);
+            bc.site_mask = mask.data();
+            bc.mask_beg = wb;
+            bc.mask_bits = we - wb;
+        }
+        double t0g = raer::now_seconds();
+        int r = raer_batch_pileup_host(ctx, &bc, &pb.b, rows);
+        tm_gpu += raer::now_seconds() - t0g;
+        if (r) return r;
+        if (bc.aei_mode) {
+            std::vector<int64_t> sums((size_t)nf * 16);
+            r = raer_ctx_last_aei(ctx, sums.data(), nf);
+            if (r) return r;
+            for (size_t i = 0; i < sums.size(); ++i) out->aei[i] += sums[i];
+        }
+        out->gpu_launches += ctx->last_launches;
+        out->t_h2d += ctx->ms_h2d * 1e-3; out->t_kernel += ctx->ms_kernel * 1e-3; out->t_d2h += ctx->ms_d2h * 1e-3;
+        return RAER_OK;
+    };
+    // Rows of one batch into the result columns. Batches must arrive in (contig, position) order: the ALT strings
+    // depend on the khash state the earlier rows of the call left behind.
+    auto emit_rows = [&](int tid, raer_rows& rows) {
+        double t0s = raer::now_seconds();
+        sink_reserve(sink, out->nrows + rows.n_rows);
+        for (int64_t i = 0; i < rows.n_rows; ++i) {
+            int64_t o = out->nrows + i;
+            int s = rows.meta[i] & 1;
+            // tables grown by the puts of a site that wrote no row for that strand (src/plp.c:487)
+            for (int f = 0; f < nf; ++f)
+                if (kh[f * 2 + s] == 4 && rows.grow_pos[f * 2 + s] < rows.pos[i]) kh[f * 2 + s] = 8;
+            out->tid[o] = tid;
+            out->pos[o] = rows.pos[i] + 1;
+            out->strand[o] = s ? '-' : '+';
+            out->ref[o] = (char)((rows.meta[i] >> 8) & 0xff);
+            out->rpbz[o] = rows.stats[i * 3];
+            out->vdb[o] = rows.stats[i * 3 + 1];
+            out->sor[o] = rows.stats[i * 3 + 2];
+            for (int f = 0; f < nf; ++f) {
+                memcpy(out->counts + ((size_t)f * sink.cap + o) * 8, rows.counts + ((size_t)i * nf + f) * 8, 32);
+                raer_altcode_to_string(rows.altcode[i * nf + f], out->ref[o], &kh[f * 2 + s],
+                                       out->alt + ((size_t)f * sink.cap + o) * 12);
+            }
+        }
+        for (int k = 0; k < nf * 2; ++k)
+            if (kh[k] == 4 && rows.grow_pos[k] != INT32_MAX) kh[k] = 8;
+        out->nrows += rows.n_rows;
+        raer_rows_free(&rows);
+        tm_sink += raer::now_seconds() - t0s;
+    };
+
+    // ---- contig-parallel ingest: the record parser of a file is serial (stream-order decisions of bam_plp_push), but
+    // contigs are independent, so several workers each stream one contig through the BAI index and hand their batches
+    // to this thread, which owns the device. Rows are kept per contig and turned into columns in contig order.
+    int hw = a->host_threads > 0 ? a->host_threads : (int)std::thread::hardware_concurrency();
+    if (hw <= 0) hw = 4;
+    int n_workers = std::min<int>((int)names.size(), std::min(16, hw / (nf + 1)));
+    bool parallel = !a->region && a->shard_count <= 1 && n_workers >= 2 && !getenv("RAER_SERIAL_INGEST");
+    if (parallel)
+        for (int i = 0; i < nf && parallel; ++i) {  // every file needs its index for the seeks
+            std::string bai = (a->indexes && a->indexes[i]) ? a->indexes[i] : std::string(a->bampaths[i]) + ".bai";
+            FILE* fp = fopen(bai.c_str(), "rb");
+            if (fp) fclose(fp); else parallel = false;
+        }
+    if (parallel) {
+        struct Slot {
+            raer::PackedBatch pb;
+            int tid = -1;
+            std::shared_ptr<std::string> ref;
+            bool busy = false;
+        };
+        std::vector<Slot> slots((size_t)n_workers * 2);
+        std::mutex mu;
+        std::condition_variable cv_ready, cv_free;
+        std::deque<Slot*> ready;
+        int workers_left = n_workers;
+        bool stop = false;
+        int worker_rc = RAER_OK;
+        std::atomic<int> next_idx{0};
+        // longest contigs first: the wall time is bounded below by the longest contig's serial parse
+        std::vector<int> order(names.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+        const std::vector<int32_t>& lens = ing.lengths();
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return lens[x] > lens[y]; });
+        raer::IngestConf icw = ic;
+        if (!getenv("RAER_BATCH_READS")) icw.target_reads = 1 << 19;  // two batches per worker are in flight
+        const int inflate_threads = std::max(1, hw / (n_workers * nf));
+        double w_decode = 0, w_pack = 0;
+        int64_t w_records = 0, w_bases = 0;
+        auto worker = [&](int w) {
+            int my_rc = RAER_OK;
+            while (my_rc == RAER_OK) {
+                const int oi = next_idx.fetch_add(1);
+                if (oi >= (int)order.size()) break;
+                const int c = order[oi];
+                if (has_ridx && !ridx.find(names[c])) continue;  // no site on this contig: nothing can be written
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (stop) break;
+                }
+                raer::Ingest wi(icw);
+                if (!wi.open(a->bampaths, a->indexes, inflate_threads, names[c].c_str())) { my_rc = RAER_ERR_IO; break; }
+                std::shared_ptr<std::string> ref;
+                while (my_rc == RAER_OK && wi.next_contig() >= 0) {
+                    if (!ref) {
+                        ref = std::make_shared<std::string>();
+                        if (!raer::fasta_fetch(a->fapath, names[c], *ref)) ref->clear();  // every site reads as 'N' and is skipped
+                    }
+                    while (true) {
+                        Slot* sl = nullptr;
+                        {
+                            std::unique_lock<std::mutex> lk(mu);
+                            cv_free.wait(lk, [&]() { return stop || !slots[2 * w].busy || !slots[2 * w + 1].busy; });
+                            if (stop) break;
+                            sl = !slots[2 * w].busy ? &slots[2 * w] : &slots[2 * w + 1];
+                        }
+                        if (!wi.next_batch(sl->pb)) break;
+                        if (sl->pb.b.n_reads == 0 || sl->pb.b.end <= sl->pb.b.beg) continue;
+                        sl->tid = c;
+                        sl->ref = ref;
+                        std::lock_guard<std::mutex> lk(mu);
+                        sl->busy = true;
+                        ready.push_back(sl);
+                        cv_ready.notify_one();
+                    }
+                    {
+                        std::lock_guard<std::mutex> lk(mu);
+                        if (stop) break;
+                    }
+                }
+                std::lock_guard<std::mutex> lk(mu);
+                w_decode += wi.decode_seconds(); w_pack += wi.pack_seconds();
+                w_records += wi.records(); w_bases += wi.aligned_bases();
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            if (my_rc != RAER_OK && worker_rc == RAER_OK) { worker_rc = my_rc; stop = true; cv_free.notify_all(); }
+            --workers_left;
+            cv_ready.notify_one();
+        };
+        std::vector<std::thread> th;
+        for (int w = 0; w < n_workers; ++w) th.emplace_back(worker, w);
+        std::vector<std::vector<raer_rows>> stash(names.size());
+        int ref_tid = -1;
+        while (true) {
+            Slot* sl = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                double t0b = raer::now_seconds();
+                cv_ready.wait(lk, [&]() { return !ready.empty() || workers_left == 0; });
+                tm_batch += raer::now_seconds() - t0b;
+                if (ready.empty()) break;
+                sl = ready.front();
+                ready.pop_front();
+            }
+            if (rc == RAER_OK) {
+                if (sl->tid != ref_tid) {
+                    double t0f = raer::now_seconds();
+                    rc = raer_ctx_set_reference(ctx, sl->tid, sl->ref->data(), (int64_t)sl->ref->size());
+                    tm_fasta += raer::now_seconds() - t0f;
+                    ref_tid = sl->tid;
+                }
+                if (rc == RAER_OK) {
+                    raer_rows rows;
+                    rc = gpu_batch(has_ridx ? ridx.find(names[sl->tid]) : nullptr, 0, INT_MAX, sl->pb, &rows);
+                    if (rc == RAER_OK) stash[sl->tid].push_back(rows);
+                }
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            sl->busy = false;
+            sl->ref.reset();
+            if (rc != RAER_OK) stop = true;
+            cv_free.notify_all();
+        }
+        for (auto& t : th) t.join();
+        if (rc == RAER_OK) rc = worker_rc;
+        for (size_t c = 0; c < stash.size(); ++c)
+            for (raer_rows& rows : stash[c]) {
+                if (rc == RAER_OK) emit_rows((int)c, rows);
+                else raer_rows_free(&rows);
+            }
+        out->t_decode = w_decode;
+        out->t_pack = w_pack;
+        out->n_records = w_records;
+        out->n_aligned_bases = w_bases;
+    } else {
+        raer::PackedBatch pb;
+        int tid;
+        int contig_no = 0;
+        while (rc == RAER_OK && (tid = ing.next_contig()) >= 0) {
+            bool mine = a->shard_count <= 1 || (contig_no % a->shard_count) == a->shard_index;
+            ++contig_no;
+            std::string seq;
+            double t0f = raer::now_seconds();
+            bool have_ref = raer::fasta_fetch(a->fapath, names[tid], seq);
+            if (!have_ref) seq.clear();  // reference: every site reads as 'N' and is skipped
+            if (mine) {
+                rc = raer_ctx_set_reference(ctx, tid, seq.data(), (int64_t)seq.size());
                 if (rc) break;
-                for (size_t i = 0; i < sums.size(); ++i) out->aei[i] += sums[i];
             }
-            double t0s = raer::now_seconds();
-            out->gpu_launches += ctx->last_launches;
-            out->t_h2d += ctx->ms_h2d * 1e-3; out->t_kernel += ctx->ms_kernel * 1e-3; out->t_d2h += ctx->ms_d2h * 1e-3;
-            sink_reserve(sink, out->nrows + rows.n_rows);
-            for (int64_t i = 0; i < rows.n_rows; ++i) {
-                int64_t o = out->nrows + i;
-                int s = rows.meta[i] & 1;
-                // tables grown by the puts of a site that wrote no row for that strand (src/plp.c:487)
-                for (int f = 0; f < nf; ++f)
-                    if (kh[f * 2 + s] == 4 && rows.grow_pos[f * 2 + s] < rows.pos[i]) kh[f * 2 + s] = 8;
-                out->tid[o] = tid;
-                out->pos[o] = rows.pos[i] + 1;
-                out->strand[o] = s ? '-' : '+';
-                out->ref[o] = (char)((rows.meta[i] >> 8) & 0xff);
-                out->rpbz[o] = rows.stats[i * 3];
-                out->vdb[o] = rows.stats[i * 3 + 1];
-                out->sor[o] = rows.stats[i * 3 + 2];
-                for (int f = 0; f < nf; ++f) {
-                    memcpy(out->counts + ((size_t)f * sink.cap + o) * 8, rows.counts + ((size_t)i * nf + f) * 8, 32);
-                    raer_altcode_to_string(rows.altcode[i * nf + f], out->ref[o], &kh[f * 2 + s],
-                                           out->alt + ((size_t)f * sink.cap + o) * 12);
-                }
+            tm_fasta += raer::now_seconds() - t0f;
+            const raer::RegionIndex::Chr* rchr = has_ridx ? ridx.find(names[tid]) : nullptr;
+            while (rc == RAER_OK) {
+                double t0b = raer::now_seconds();
+                const bool got = ing.next_batch(pb);
+                tm_batch += raer::now_seconds() - t0b;
+                if (!got) break;
+                if (!mine || pb.b.n_reads == 0 || pb.b.end <= pb.b.beg) continue;
+                if (has_ridx && !rchr) continue;
+                raer_rows rows;
+                rc = gpu_batch(rchr, ing.reg_tid() >= 0 ? ing.reg_beg() : 0, ing.reg_tid() >= 0 ? ing.reg_end() : INT_MAX, pb, &rows);
+                if (rc) break;
+                emit_rows(tid, rows);
             }
-            for (int k = 0; k < nf * 2; ++k)
-                if (kh[k] == 4 && rows.grow_pos[k] != INT32_MAX) kh[k] = 8;
-            out->nrows += rows.n_rows;
-            raer_rows_free(&rows);
-            tm_sink += raer::now_seconds() - t0s;
         }
+        out->t_decode = ing.decode_seconds();
+        out->t_pack = ing.pack_seconds();
+        out->n_records = ing.records();
+        out->n_aligned_bases = ing.aligned_bases();
     }
     // compact the [file][row] stride to nrows
     if (sink.cap != out->nrows && out->nrows > 0) {
@@ -871,10 +1029,6 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             memmove(out->counts + (size_t)f * out->nrows * 8, out->counts + (size_t)f * sink.cap * 8, (size_t)out->nrows * 32);
         }
     }
-    out->t_decode = ing.decode_seconds();
-    out->t_pack = ing.pack_seconds();
-    out->n_records = ing.records();
-    out->n_aligned_bases = ing.aligned_bases();
     raer_ctx_destroy(ctx);
     out->t_total = raer::now_seconds() - t_start;
     if (getenv("RAER_TIMING"))

@@ -441,3 +441,20 @@ def test_known_sites_eight_bams(syn8):
     idx = np.array([key[(s, p, st)] for s, p, st in zip(one.seqnames, one.pos, one.strand)])
     for k in ("nRef", "nAlt", "nA", "nT", "nC", "nG"):
         assert np.array_equal(one.assay(k)[:, 0], want.assay(k)[idx, 3])
+
+
+# raer_pileup streams the contigs of a call through several workers (BAI seeks) when the host has the cores for it;
+# RAER_SERIAL_INGEST keeps the single-stream path. Both must give the oracle's result, rows in contig order.
+@pytest.mark.gpu
+@pytest.mark.parametrize("serial", [False, True])
+@pytest.mark.parametrize("batch_reads", [None, 700])
+def test_serial_and_contig_parallel_ingest(syn5, serial, batch_reads, monkeypatch):
+    if serial:
+        monkeypatch.setenv("RAER_SERIAL_INGEST", "1")
+    if batch_reads:
+        monkeypatch.setenv("RAER_BATCH_READS", str(batch_reads))
+    fp = FilterParam(library_type="fr-first-strand", min_variant_reads=2)
+    want = oracle_backend.pileup_sites(syn5["bams"][:3], syn5["fasta"], param=fp)
+    got = _cuda()(syn5["bams"][:3], syn5["fasta"], param=fp)
+    _assert_same(got, want)
+    assert list(got.seqnames) == sorted(got.seqnames, key=lambda s: int(s[3:]))
