@@ -73,6 +73,7 @@ private:
     // prefetch: while the parser walks ubuf_, a task inflates the following group (it owns fp_, cbuf_, c_off_,
     // file_eof_ and t_decode_ until fill() collects it)
     std::vector<uint8_t> pf_buf_;
+    std::vector<uint8_t> grp_;  // the group fill() hands over; a member so that its storage is recycled
     std::future<int> pf_;
     bool drained_ = false;  // produce() reported the end of the file
     bool light_ = false;
@@ -236,6 +237,7 @@ struct PackedBatch {
     std::vector<int32_t> umi_holes;  // bulk UMI mode: (read index, position) pairs, sorted by read index
     size_t cap_reads = 0, cap_cigar = 0, cap_sq = 0, cap_pairs = 0;
     bool pinned = false;
+    bool want_pinned = true;  // false: plain host memory (workers that must not enter the CUDA driver)
     void reserve(size_t reads, size_t cig, size_t sq, bool sc);
     void release();
     ~PackedBatch() { release(); }

@@ -143,7 +143,7 @@ int BamStream::produce(std::vector<uint8_t>& out) {
 bool BamStream::fill() {
     if (drained_) return false;
     int rc;
-    std::vector<uint8_t> grp;
+    std::vector<uint8_t>& grp = grp_;
     if (pf_.valid()) {
         const double tw = now_seconds();
         rc = pf_.get();
@@ -509,7 +509,8 @@ void PackedBatch::reserve(size_t reads, size_t cig, size_t sq, bool sc) {
     int pin = 0;
     auto grow = [&](void** p, size_t bytes) {
         raer_pinned_free(*p, pinned);
-        *p = raer_pinned_alloc(bytes ? bytes : 16, &pin);
+        if (want_pinned) *p = raer_pinned_alloc(bytes ? bytes : 16, &pin);
+        else *p = malloc(bytes ? bytes : 16);
     };
     if (reads > cap_reads || !hdr) {
         size_t n = reads + reads / 4 + 1024;

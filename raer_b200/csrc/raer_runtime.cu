@@ -875,6 +875,9 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             bool busy = false;
         };
         std::vector<Slot> slots((size_t)n_workers * 2);
+        // plain host memory: page-locking from several threads serialises on the driver and the kernel's mm locks
+        // and stalls every other thread of the process; the device thread copies from pageable memory instead
+        for (Slot& sl : slots) sl.pb.want_pinned = false;
         std::mutex mu;
         std::condition_variable cv_ready, cv_free;
         std::deque<Slot*> ready;
@@ -888,8 +891,20 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
         const std::vector<int32_t>& lens = ing.lengths();
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return lens[x] > lens[y]; });
         raer::IngestConf icw = ic;
-        if (!getenv("RAER_BATCH_READS")) icw.target_reads = 1 << 19;  // two batches per worker are in flight
-        const int inflate_threads = std::max(1, hw / (n_workers * nf));
+        if (!getenv("RAER_BATCH_READS")) {
+            // two batches per worker are in flight, each in its own pinned buffers: size them by the input (about 50
+            // compressed bytes per record) so that a small call does not pin more memory than it reads
+            int64_t bytes = 0;
+            for (int i = 0; i < nf; ++i) {
+                FILE* fp = fopen(a->bampaths[i], "rb");
+                if (fp) { fseek(fp, 0, SEEK_END); bytes += ftell(fp); fclose(fp); }
+            }
+            const int64_t est = bytes / 50 / (4 * n_workers);
+            icw.target_reads = std::min<int64_t>(1 << 19, std::max<int64_t>(1 << 16, est));
+        }
+        // a stream's parser is one thread, its inflate costs about three times the parser's CPU time: give the inflate
+        // of every stream two threads (the host is slightly oversubscribed, which keeps every core busy)
+        const int inflate_threads = std::max(2, (hw + n_workers * nf - 1) / (n_workers * nf));
         double w_decode = 0, w_pack = 0;
         int64_t w_records = 0, w_bases = 0;
         auto worker = [&](int w) {
