@@ -689,159 +689,6 @@ __device__ void slot_stats(const PlpParams& P, const uint32_t* slot, int HW, int
     }
 }
 
-// ---- slot_stats with one warp per slot (k_pileup_fast): the serial version costs the tile one thread's latency.
-// calc_mwu_biasZ (bcftools-ext.c:144-212): every sum is an integer sum (int arithmetic wraps the same way in any
-// order), so the 100 bins are spread over 25 lanes, 4 consecutive bins each, and reduced.
-__device__ __forceinline__ double warp_mwu_z(const HistView a, const HistView b, int lane) {
-    int av[4] = {0, 0, 0, 0}, bv[4] = {0, 0, 0, 0};
-    if (lane < RAER_NHIST / 4) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { av[k] = a[4 * lane + k]; bv[k] = b[4 * lane + k]; }
-    }
-    const int bsum = bv[0] + bv[1] + bv[2] + bv[3];
-    // number of b entries in the bins above this lane's (the serial loop walks the bins downwards)
-    int above = bsum;
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_down_sync(FULL, above, o);
-        if (lane + o < 32) above += v;
-    }
-    above -= bsum;
-    unsigned e = 0, l = 0;
-    long long t = 0;
-    int nb_run = above;
-#pragma unroll
-    for (int k = 3; k >= 0; --k) {
-        e += (unsigned)(av[k] * bv[k]);
-        l += (unsigned)(av[k] * nb_run);
-        nb_run += bv[k];
-        const int p = av[k] + bv[k];
-        t += (long long)((p * p - 1) * p);
-    }
-    e = __reduce_add_sync(FULL, e);
-    l = __reduce_add_sync(FULL, l);
-    const int na = (int)__reduce_add_sync(FULL, (unsigned)(av[0] + av[1] + av[2] + av[3]));
-    const int nb = (int)__reduce_add_sync(FULL, (unsigned)bsum);
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
-    if (!na || !nb) return CUDART_INF;  // covers the empty-b branch of the reference as well
-    const double U = (int)l + (int)e * 0.5;
-    const double m = na * nb / 2.0;
-    const double var2 = (na * nb) / 12.0 * ((na + nb + 1) - t / (double)((na + nb) * (na + nb - 1)));
-    if (var2 <= 0) return 0;
-    return (U - m) / sqrt(var2);
-}
-
-// calc_vdb (bcftools-ext.c:51-111): the float accumulations depend on the order of the bins, so every lane walks the
-// non-empty bins in ascending order (found by ballots, values broadcast) and computes the same value.
-__device__ __forceinline__ double warp_vdb(const HistView pos, int lane) {
-    const float prm[15][3] = {{3, 0.079f, 18},    {4, 0.09f, 19.8f},  {5, 0.1f, 20.5f},   {6, 0.11f, 21.5f},
-                              {7, 0.125f, 21.6f}, {8, 0.135f, 22},    {9, 0.14f, 22.2f},  {10, 0.153f, 22.3f},
-                              {15, 0.19f, 22.8f}, {20, 0.22f, 23.2f}, {30, 0.26f, 23.4f}, {40, 0.29f, 23.5f},
-                              {50, 0.35f, 23.65f}, {100, 0.5f, 23.7f}, {200, 0.7f, 23.7f}};
-    int v[4];
-    unsigned nz[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = lane + 32 * k;
-        v[k] = i < RAER_NHIST ? (int)pos[i] : 0;
-        nz[k] = __ballot_sync(FULL, v[k] != 0);
-    }
-    int dp = 0;
-    float mean_pos = 0, mean_diff = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        for (unsigned m = nz[k]; m; m &= m - 1) {
-            const int src = __ffs(m) - 1;
-            const int val = __shfl_sync(FULL, v[k], src);
-            dp += val;
-            mean_pos += (float)(val * (src + 32 * k));
-        }
-    if (dp < 2) return CUDART_INF;
-    mean_pos /= (float)dp;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        for (unsigned m = nz[k]; m; m &= m - 1) {
-            const int src = __ffs(m) - 1;
-            const int val = __shfl_sync(FULL, v[k], src);
-            // float += int * fabs(float): evaluated in double, rounded back to float
-            mean_diff = (float)((double)mean_diff + (double)val * fabs((double)((float)(src + 32 * k) - mean_pos)));
-        }
-    mean_diff /= (float)dp;
-    const int ipos = (int)mean_diff;
-    if (dp == 2) return (double)((2 * 100 - 2 * (ipos + 1) - 1) * (ipos + 1) / 99) / (100 * 0.5);
-    int i;
-    if (dp >= 200) i = 15;
-    else
-        for (i = 0; i < 15; ++i)
-            if (prm[i][0] >= (float)dp) break;
-    float pshift, pscale;
-    if (i == 15) { pscale = prm[14][1]; pshift = prm[14][2]; }
-    else if (i > 0 && prm[i][0] != (float)dp) {
-        pscale = (float)((double)(prm[i - 1][1] + prm[i][1]) * 0.5);
-        pshift = (float)((double)(prm[i - 1][2] + prm[i][2]) * 0.5);
-    } else { pscale = prm[i][1]; pshift = prm[i][2]; }
-    return 0.5 * d_kf_erfc((double)(-(mean_diff - pshift) * pscale));
-}
-
-// all 32 lanes call this for the same slot; lane f takes the ALT order code of file f
-struct StatsOut {  // by value: a reference to the kernel parameters would force them into local memory
-    double* row_stats;
-    unsigned* row_alt;
-    int* grow;
-    int n_files;
-};
-__device__ __forceinline__ void slot_stats_warp(const StatsOut P, const uint32_t* slot, int HW, int rowp, int rowm, int growmask,
-                                             int pos, int lane) {
-    const double sor = d_calc_sor((int)slot[HW], (int)slot[HW + 1], (int)slot[HW + 2], (int)slot[HW + 3]);
-    for (int s = 0; s < 2; ++s) {
-        const long long row = s == 0 ? rowp : rowm;
-        if (row < 0 && !((growmask >> s) & 1)) continue;
-        if (row >= 0) {
-            const HistView hr = {slot, (s * 2) * RAER_NHIST, HW != 4 * RAER_NHIST};
-            const HistView ha = {slot, (s * 2 + 1) * RAER_NHIST, HW != 4 * RAER_NHIST};
-            const double z = warp_mwu_z(hr, ha, lane);
-            const double vdb = warp_vdb(ha, lane);
-            if (lane == 0) {
-                P.row_stats[row * 3 + 0] = z;
-                P.row_stats[row * 3 + 1] = vdb;
-                P.row_stats[row * 3 + 2] = sor;
-            }
-        }
-        for (int f = lane; f < P.n_files; f += 32) {
-            const uint32_t* fs = slot + HW + 4 + (f * 2 + s) * RAER_SLOT_FS;
-            // order the (at most 5) variant keys by first-seen ordinal: 0..3 = ACGT, 4 = IUPAC key
-            unsigned ord[5] = {fs[0], fs[1], fs[2], fs[3], fs[5]};
-            unsigned code = 0;
-            int nins = 0;
-            unsigned third = 0;
-            for (int k = 0; k < 5; ++k) {
-                int best = -1;
-                for (int b = 0; b < 5; ++b)
-                    if (ord[b] != 0xffffffffu && (best < 0 || ord[b] < ord[best])) best = b;
-                if (best < 0) break;
-                code |= (unsigned)best << (3 * nins);
-                if (nins == 2) third = ord[best];
-                ord[best] = 0xffffffffu;
-                ++nins;
-            }
-            // kh_put resizes 4 -> 8 buckets when a put arrives with 3 keys occupied (khash.h)
-            const bool grows = nins >= 3 && fs[4] > third + 1u;
-            if (row < 0) {
-                if (grows) atomicMax(&P.grow[f * 2 + s], 0x7fffffff - pos);
-                continue;
-            }
-            unsigned alt = P.row_alt[row * P.n_files + f] & (RAER_ALT_MASK | RAER_ALT_OTHER);
-            alt |= code << RAER_ALT_ORDER_SHIFT;
-            alt |= (unsigned)nins << RAER_ALT_NINS_SHIFT;
-            if (grows) alt |= RAER_ALT_GROW;
-            if (fs[5] != 0xffffffffu) {
-                alt |= (fs[6] & 0xfu) << RAER_ALT_OCODE_SHIFT;
-                if (fs[6] != fs[7]) alt |= RAER_ALT_OAMBIG;
-            }
-            P.row_alt[row * P.n_files + f] = alt;
-        }
-    }
-}
-
 // development aid: thread 0 adds the cycles since the previous mark to phase_clk[k]
 #define PHASE_MARK(k)                                                                   \
     do {                                                                                \
@@ -1099,11 +946,10 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_pileup_fast(PlpParams P) {
             }
             PHASE_BARRIER(9);
             PHASE_MARK(5);  // second pass (slot clear + pairs)
-            for (int i = wid; i < ns; i += FB_THREADS / 32) {  // one warp per slot
+            for (int i = threadIdx.x; i < ns; i += blockDim.x) {
                 const int d = S.flag_d[round0 + i], row = S.flag_row[round0 + i];
-                slot_stats_warp(StatsOut{P.row_stats, P.row_alt, P.grow, P.n_files}, S.cnt + (size_t)i * SW, HW,
-                                ((d & 1) && (d & 4)) ? row : -1,
-                                ((d & 2) && (d & 8)) ? row + (d & 1) : -1, d >> 4, t0 + (int)S.flag_pidx[round0 + i], lane);
+                slot_stats(P, S.cnt + (size_t)i * SW, HW, ((d & 1) && (d & 4)) ? row : -1,
+                           ((d & 2) && (d & 8)) ? row + (d & 1) : -1, d >> 4, t0 + (int)S.flag_pidx[round0 + i]);
             }
             __syncthreads();
             PHASE_MARK(6);  // statistics
