@@ -137,6 +137,20 @@ typedef struct raer_scpileup_args {
 /* returns the status the reference returns through ScalarInteger (>= 0 ok, < 0 failure) */
 int raer_scpileup(const raer_scpileup_args* args);
 
+/* The same call with the nonzero cells handed back in memory, in the order of the lines of the counts file
+ * (src/sc-plp.c:410-437 writes "<site_idx> <cb_idx> <nRef> <nAlt>"; R re-reads that file with read.table,
+ * R/sc-pileup.R:390-467: this entry point removes the round trip). The three text files are
+ * written as well when all of args->outfns are set, and skipped when they are NULL. */
+typedef struct raer_sc_triplets {
+    int64_t n;
+    int32_t* site_idx; /* 1-based index column of the site (raer_scpileup_args.site_idx) */
+    int32_t* cb_idx;   /* 1-based barcode column */
+    int32_t* n_ref;
+    int32_t* n_alt;
+} raer_sc_triplets;
+int raer_scpileup_triplets(const raer_scpileup_args* args, raer_sc_triplets* out);
+void raer_sc_triplets_free(raer_sc_triplets* t);
+
 /* .Call(".get_region", region): hts_parse_reg semantics; *beg 0-based, *end exclusive */
 int raer_get_region(const char* region, char* chrom, int32_t chrom_cap, int32_t* beg, int32_t* end);
 /* .Call(".fisher_exact", mat): mat is 4 x ncol column-major (a_ref, a_alt, b_ref, b_alt) */

@@ -308,9 +308,43 @@ def pileup(pc, device: int = 0, host_threads: int = 0, overlap_mode: int = 1, sh
         L.raer_pileup_result_free(C.byref(r))
 
 
+class ScTriplets(C.Structure):
+    _fields_ = [("n", C.c_int64), ("site_idx", C.POINTER(C.c_int32)), ("cb_idx", C.POINTER(C.c_int32)),
+                ("n_ref", C.POINTER(C.c_int32)), ("n_alt", C.POINTER(C.c_int32))]
+
+
+def scpileup_triplets(sc, device: int = 0, host_threads: int = 0, overlap_mode: int = 1, write_files: bool = False):
+    """raer_scpileup_triplets(): the nonzero cells as (site_idx, cb_idx, nRef, nAlt) arrays, 1-based indices like
+    the lines of the counts file; the three text files are only written when write_files is set."""
+    L = lib()
+    L.raer_scpileup_triplets.argtypes = [C.POINTER(ScArgs), C.POINTER(ScTriplets)]
+    L.raer_sc_triplets_free.argtypes = [C.POINTER(ScTriplets)]
+    a, keep = _sc_args(sc, device, host_threads, overlap_mode)
+    if not write_files:
+        a.outfns = (C.c_char_p * 3)(None, None, None)
+    t = ScTriplets()
+    rc = L.raer_scpileup_triplets(C.byref(a), C.byref(t))
+    if rc < 0:
+        raise RaerError(f"[raer internal] error detected during pileup (code {rc}): {last_error()}")
+    try:
+        n = int(t.n)
+        get = lambda ptr: np.ctypeslib.as_array(ptr, shape=(n,)).astype(np.int64, copy=True) if n else np.zeros(0, dtype=np.int64)  # noqa: E731
+        return get(t.site_idx), get(t.cb_idx), get(t.n_ref), get(t.n_alt)
+    finally:
+        L.raer_sc_triplets_free(C.byref(t))
+
+
 def scpileup(sc, device: int = 0, host_threads: int = 0, overlap_mode: int = 1) -> int:
     """.Call(".scpileup", ...): writes the three output files, returns the status integer."""
     L = lib()
+    a, keep = _sc_args(sc, device, host_threads, overlap_mode)
+    rc = L.raer_scpileup(C.byref(a))
+    if rc < 0:
+        raise RaerError(f"[raer internal] error detected during pileup (code {rc}): {last_error()}")
+    return rc
+
+
+def _sc_args(sc, device, host_threads, overlap_mode):
     a = ScArgs()
     keep = [_strs(sc.bampaths), _strs(sc.indexes)]
     a.nbam = len(sc.bampaths)
@@ -335,10 +369,7 @@ def scpileup(sc, device: int = 0, host_threads: int = 0, overlap_mode: int = 1) 
     a.overlap_mode = overlap_mode
     a.device = device
     a.host_threads = host_threads
-    rc = L.raer_scpileup(C.byref(a))
-    if rc < 0:
-        raise RaerError(f"[raer internal] error detected during pileup (code {rc}): {last_error()}")
-    return rc
+    return a, keep
 
 
 def get_region(region: str):

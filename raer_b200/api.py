@@ -121,9 +121,16 @@ def _get_sc_pileup(call, bamfn, index, ident, sites: Sites, barcodes, outfile_pr
                                          param)
     try:
         res = call(sc_call)
-        if res < 0:
-            raise RuntimeError("pileup failed")
-        sc = read_sparray(*sc_call.outfns, site_format="index")
+        if isinstance(res, tuple):
+            # triplets in memory (raer_scpileup_triplets): what read_sparray() would rebuild from the three files; the
+            # sites file lists the sites by contig in order of appearance and position (src/sc-plp.c:852-869)
+            site_idx, cb_idx, nref, nalt = res
+            sc = SparseCounts(n_sites=len(sites), barcodes=list(barcodes), row=site_idx - 1, col=cb_idx - 1,
+                              nRef=nref, nAlt=nalt)
+        else:
+            if res < 0:
+                raise RuntimeError("pileup failed")
+            sc = read_sparray(*sc_call.outfns, site_format="index")
     finally:
         for f in sc_call.outfns:
             if os.path.exists(f):
@@ -145,7 +152,7 @@ def _get_sc_pileup(call, bamfn, index, ident, sites: Sites, barcodes, outfile_pr
 
 def _pileup_cells_impl(call, bamfiles, sites: Sites, cell_barcodes, output_directory, chroms=None, umi_tag="UB",
                        cb_tag="CB", param: Optional[FilterParam] = None, return_sce: bool = True, indexes=None,
-                       workers: int = 1):
+                       workers: int = 1, write_files: bool = True):
     param = param or FilterParam()
     if isinstance(bamfiles, str):
         bamfiles = [bamfiles]
@@ -225,7 +232,8 @@ def _pileup_cells_impl(call, bamfiles, sites: Sites, cell_barcodes, output_direc
     if param.min_variant_reads > 0:
         keep &= sce.row_sums("nAlt") >= param.min_variant_reads
     sce = sce.subset_rows(keep)
-    write_sparray(sce, outfns["counts"], outfns["sites"], outfns["bc"])
+    if write_files:
+        write_sparray(sce, outfns["counts"], outfns["sites"], outfns["bc"])
     return sce if return_sce else outfns
 
 
@@ -237,6 +245,20 @@ def pileup_cells(bamfiles, sites: Sites, cell_barcodes: Sequence[str], output_di
 
     return _pileup_cells_impl(_cabi.scpileup, bamfiles, sites, cell_barcodes, output_directory, chroms, umi_tag,
                               cb_tag, param, return_sce, indexes)
+
+
+def pileup_cells_triplets(bamfiles, sites: Sites, cell_barcodes: Sequence[str], chroms=None, umi_tag: Optional[str] = "UB",
+                          cb_tag: Optional[str] = "CB", param: Optional[FilterParam] = None, indexes=None):
+    """``pileup_cells()`` without the text-file round trip of the reference (C writes three files, R reads them back,
+    R/sc-pileup.R:334, 390-467): the nonzero cells come back from the engine in memory. Same
+    arguments minus ``output_directory``; returns the same object as ``pileup_cells(..., return_sce=True)``."""
+    import tempfile
+
+    from . import _cabi
+
+    with tempfile.TemporaryDirectory() as d:  # only names are derived from it; nothing is written
+        return _pileup_cells_impl(_cabi.scpileup_triplets, bamfiles, sites, cell_barcodes, d, chroms, umi_tag, cb_tag,
+                                  param, True, indexes, write_files=False)
 
 
 # ----------------------------------------------------------------------------- calc_AEI

@@ -305,25 +305,29 @@ static int bits_for(unsigned long long maxval) {
     return b;
 }
 
-extern "C" int raer_scpileup(const raer_scpileup_args* a) {
+// One engine behind both entry points: text files (the reference's contract), triplets in memory, or both.
+static int sc_run(const raer_scpileup_args* a, bool want_files, raer_sc_triplets* trip_out) {
     // check_sc_plp_args, src/sc-plp.c:874-940
-    if (!a || a->nbam < 1 || !a->bampaths || a->n_sites < 1 || a->n_barcodes < 1 || !a->barcodes || !a->outfns[0] ||
-        !a->outfns[1] || !a->outfns[2]) {
+    if (!a || a->nbam < 1 || !a->bampaths || a->n_sites < 1 || a->n_barcodes < 1 || !a->barcodes ||
+        (want_files && (!a->outfns[0] || !a->outfns[1] || !a->outfns[2]))) {
         set_error("invalid arguments");
         return RAER_ERR_ARG;
     }
+    std::vector<int32_t> mem_site, mem_cb, mem_ref, mem_alt;
     if (raer_device_count() <= 0) { set_error("no usable CUDA device (the product has no CPU path)"); return RAER_ERR_NO_DEVICE; }
     const bool is_ss2 = a->nbam > 1;
     if (is_ss2 && a->n_barcodes < a->nbam) { set_error("one barcode per BAM is required"); return RAER_ERR_ARG; }
-    FILE* fps[3];
-    for (int i = 0; i < 3; ++i) fps[i] = fopen(a->outfns[i], "w");
+    FILE* fps[3] = {nullptr, nullptr, nullptr};
+    if (want_files)
+        for (int i = 0; i < 3; ++i) fps[i] = fopen(a->outfns[i], "w");
     auto close_all = [&]() { for (int i = 0; i < 3; ++i) if (fps[i]) fclose(fps[i]); };
-    if (!fps[0] || !fps[1] || !fps[2]) { close_all(); set_error("cannot open output files"); return RAER_ERR_IO; }
+    if (want_files && (!fps[0] || !fps[1] || !fps[2])) { close_all(); set_error("cannot open output files"); return RAER_ERR_IO; }
 
     // barcode whitelist: first occurrence wins (src/sc-plp.c:814-826)
     std::unordered_map<std::string, int> cbidx;
     for (int i = 0; i < a->n_barcodes; ++i) cbidx.emplace(a->barcodes[i], i + 1);
-    for (int i = 0; i < a->n_barcodes; ++i) fprintf(fps[2], "%s\n", a->barcodes[i]);
+    if (fps[2])
+        for (int i = 0; i < a->n_barcodes; ++i) fprintf(fps[2], "%s\n", a->barcodes[i]);
 
     // sites per contig, sorted by position (stable), as regidx keeps them
     std::vector<std::string> chr_order;
@@ -335,10 +339,11 @@ extern "C" int raer_scpileup(const raer_scpileup_args* a) {
     }
     for (auto& kv : by_chr)
         std::stable_sort(kv.second.begin(), kv.second.end(), [&](int x, int y) { return a->site_pos[x] < a->site_pos[y]; });
-    for (auto& nm : chr_order)
-        for (int s : by_chr[nm])
-            fprintf(fps[1], "%d\t%s\t%d\t%d\t%s\t%s\n", a->site_idx[s], nm.c_str(), a->site_pos[s], a->site_strand[s],
-                    a->site_ref[s], a->site_alt[s]);
+    if (fps[1])
+        for (auto& nm : chr_order)
+            for (int s : by_chr[nm])
+                fprintf(fps[1], "%d\t%s\t%d\t%d\t%s\t%s\n", a->site_idx[s], nm.c_str(), a->site_pos[s], a->site_strand[s],
+                        a->site_ref[s], a->site_alt[s]);
     raer::RegionIndex ridx;
     {
         std::vector<int32_t> b0(a->n_sites);
@@ -498,7 +503,11 @@ extern "C" int raer_scpileup(const raer_scpileup_args* a) {
                 for (const int4& t : trip) {
                     int2 tt = tot[t.x];
                     if (!(min_counts == 0 || (tt.x + tt.y >= min_counts && tt.y >= min_var_reads))) continue;
-                    fprintf(fps[0], "%d %d %d %d\n", a->site_idx[(*sites)[t.x]], t.y, t.z, t.w);
+                    if (fps[0]) fprintf(fps[0], "%d %d %d %d\n", a->site_idx[(*sites)[t.x]], t.y, t.z, t.w);
+                    if (trip_out) {
+                        mem_site.push_back(a->site_idx[(*sites)[t.x]]); mem_cb.push_back(t.y);
+                        mem_ref.push_back(t.z); mem_alt.push_back(t.w);
+                    }
                 }
             }
         }
@@ -506,5 +515,32 @@ extern "C" int raer_scpileup(const raer_scpileup_args* a) {
     cudaStreamDestroy(st);
     close_all();
     if (rc != RAER_OK) return rc < 0 ? rc : RAER_ERR;
+    if (trip_out) {
+        const size_t n = mem_site.size();
+        trip_out->n = (int64_t)n;
+        trip_out->site_idx = (int32_t*)malloc((n ? n : 1) * 4);
+        trip_out->cb_idx = (int32_t*)malloc((n ? n : 1) * 4);
+        trip_out->n_ref = (int32_t*)malloc((n ? n : 1) * 4);
+        trip_out->n_alt = (int32_t*)malloc((n ? n : 1) * 4);
+        if (n) {
+            memcpy(trip_out->site_idx, mem_site.data(), n * 4); memcpy(trip_out->cb_idx, mem_cb.data(), n * 4);
+            memcpy(trip_out->n_ref, mem_ref.data(), n * 4); memcpy(trip_out->n_alt, mem_alt.data(), n * 4);
+        }
+    }
     return 0;
+}
+
+extern "C" int raer_scpileup(const raer_scpileup_args* a) { return sc_run(a, true, nullptr); }
+
+extern "C" int raer_scpileup_triplets(const raer_scpileup_args* a, raer_sc_triplets* out) {
+    if (!out) { set_error("invalid arguments"); return RAER_ERR_ARG; }
+    memset(out, 0, sizeof(*out));
+    const bool files = a && a->outfns[0] && a->outfns[1] && a->outfns[2];
+    return sc_run(a, files, out);
+}
+
+extern "C" void raer_sc_triplets_free(raer_sc_triplets* t) {
+    if (!t) return;
+    free(t->site_idx); free(t->cb_idx); free(t->n_ref); free(t->n_alt);
+    memset(t, 0, sizeof(*t));
 }

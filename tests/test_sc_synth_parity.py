@@ -71,3 +71,30 @@ def test_sc_synth_barcode_subset_and_chroms(sc, tmp_path):
     want = oracle_backend.pileup_cells(sc["bam"], sc["gr"], sub, str(tmp_path / "o"), chroms=["chr2"], param=fp)
     got = api.pileup_cells(sc["bam"], sc["gr"], sub, str(tmp_path / "c"), chroms=["chr2"], param=fp)
     assert _triplets(got) == _triplets(want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw,ckw", CONFIGS[:3], ids=["0", "1", "2"])
+def test_triplets_in_memory_equal_the_file_round_trip(sc, kw, ckw, tmp_path):
+    """raer_scpileup_triplets: same cells as the three text files read back."""
+    from raer_b200 import api
+
+    fp = FilterParam(**kw)
+    files = api.pileup_cells(sc["bam"], sc["gr"], sc["barcodes"], str(tmp_path / "c"), param=fp, **ckw)
+    mem = api.pileup_cells_triplets(sc["bam"], sc["gr"], sc["barcodes"], param=fp, **ckw)
+    assert _triplets(mem) == _triplets(files)
+
+
+@pytest.mark.gpu
+def test_triplets_on_the_bundled_10x_bam(ext, tmp_path):
+    import bamtools
+    from raer_b200 import api
+
+    _, _, recs = bamtools.read_bam(ext.scbam)
+    cbs = list(dict.fromkeys(r.tag_z("CB") for r in recs if r.tag_z("CB") is not None))
+    gr = Sites(["2"] * 5, [579, 589, 601, 625, 645], strand=["-"] * 5, ref=["A", "A", "T", "A", "A"], alt=["G", "G", "C", "G", "G"])
+    fp = FilterParam(library_type="fr-second-strand", min_depth=0)
+    files = api.pileup_cells(ext.scbam, gr, cbs, str(tmp_path), param=fp)
+    mem = api.pileup_cells_triplets(ext.scbam, gr, cbs, param=fp)
+    assert _triplets(mem) == _triplets(files)
+    assert list(zip(mem.row_sums("nRef"), mem.row_sums("nAlt"))) == [(103, 127), (273, 7), (3, 277), (149, 135), (0, 0)]
