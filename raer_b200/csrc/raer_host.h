@@ -284,6 +284,7 @@ private:
 bool fasta_fetch(const char* fa, const std::string& name, std::string& out);
 int parse_region(const char* s, int* beg, int* end);  // hts_parse_reg; returns length of the name part or -1
 double now_seconds();
+int usable_cpus();  // CPUs this process may run on (affinity mask), not the machine's count
 
 }  // namespace raer
 #endif

@@ -9,6 +9,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sched.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -31,6 +32,19 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+int usable_cpus() {
+#ifdef __linux__
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+        const int n = CPU_COUNT(&set);
+        if (n > 0) return n;
+    }
+#endif
+    const int n = (int)std::thread::hardware_concurrency();
+    return n > 0 ? n : 4;
+}
 
 double now_seconds() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -547,7 +561,7 @@ Ingest::~Ingest() {
 }
 
 bool Ingest::open(const char* const* paths, const char* const* indexes, int threads, const char* region) {
-    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = usable_cpus();
     if (threads <= 0) threads = 4;
     for (int i = 0; i < conf_.n_files; ++i) {
         FilePending* f = new FilePending();

@@ -857,7 +857,7 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
     // ---- contig-parallel ingest: the record parser of a file is serial (stream-order decisions of bam_plp_push), but
     // contigs are independent, so several workers each stream one contig through the BAI index and hand their batches
     // to this thread, which owns the device. Rows are kept per contig and turned into columns in contig order.
-    int hw = a->host_threads > 0 ? a->host_threads : (int)std::thread::hardware_concurrency();
+    int hw = a->host_threads > 0 ? a->host_threads : raer::usable_cpus();
     if (hw <= 0) hw = 4;
     int n_workers = std::min<int>((int)names.size(), std::min(16, hw / (nf + 1)));
     bool parallel = !a->region && a->shard_count <= 1 && n_workers >= 2 && !getenv("RAER_SERIAL_INGEST");
