@@ -865,7 +865,9 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
         for (int i = 0; i < nf && parallel; ++i) {  // every file needs its index for the seeks
             std::string bai = (a->indexes && a->indexes[i]) ? a->indexes[i] : std::string(a->bampaths[i]) + ".bai";
             FILE* fp = fopen(bai.c_str(), "rb");
-            if (fp) fclose(fp); else parallel = false;
+            char magic[4] = {0, 0, 0, 0};
+            if (!fp || fread(magic, 1, 4, fp) != 4 || memcmp(magic, "BAI\1", 4)) parallel = false;  // single stream: no index needed
+            if (fp) fclose(fp);
         }
     if (parallel) {
         struct Slot {
@@ -884,6 +886,7 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
         int workers_left = n_workers;
         bool stop = false;
         int worker_rc = RAER_OK;
+        std::string worker_msg;
         std::atomic<int> next_idx{0};
         // longest contigs first: the wall time is bounded below by the longest contig's serial parse
         std::vector<int> order(names.size());
@@ -953,7 +956,12 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
                 w_records += wi.records(); w_bases += wi.aligned_bases();
             }
             std::lock_guard<std::mutex> lk(mu);
-            if (my_rc != RAER_OK && worker_rc == RAER_OK) { worker_rc = my_rc; stop = true; cv_free.notify_all(); }
+            if (my_rc != RAER_OK && worker_rc == RAER_OK) {
+                worker_rc = my_rc;
+                worker_msg = raer::last_error();  // the message buffer is per thread: hand it to the calling thread
+                stop = true;
+                cv_free.notify_all();
+            }
             --workers_left;
             cv_ready.notify_one();
         };
@@ -992,7 +1000,10 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             cv_free.notify_all();
         }
         for (auto& t : th) t.join();
-        if (rc == RAER_OK) rc = worker_rc;
+        if (rc == RAER_OK && worker_rc != RAER_OK) {
+            rc = worker_rc;
+            set_error("%s", worker_msg.c_str());
+        }
         for (size_t c = 0; c < stash.size(); ++c)
             for (raer_rows& rows : stash[c]) {
                 if (rc == RAER_OK) emit_rows((int)c, rows);
@@ -1055,7 +1066,6 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
         raer_pileup_result_free(out);
         return rc;
     }
-    if (raer::last_error()[0] && ing.records() == 0 && false) return RAER_ERR_IO;
     return RAER_OK;
 }
 

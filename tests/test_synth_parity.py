@@ -458,3 +458,21 @@ def test_serial_and_contig_parallel_ingest(syn5, serial, batch_reads, monkeypatc
     got = _cuda()(syn5["bams"][:3], syn5["fasta"], param=fp)
     _assert_same(got, want)
     assert list(got.seqnames) == sorted(got.seqnames, key=lambda s: int(s[3:]))
+
+
+@pytest.mark.gpu
+def test_unusable_index_falls_back_to_the_single_stream(syn5, tmp_path):
+    """Without `region` the reference never opens the index; a call whose .bai is unreadable must still work."""
+    import shutil
+
+    bams = []
+    for i, b in enumerate(syn5["bams"][:2]):
+        dst = str(tmp_path / f"b{i}.bam")
+        shutil.copy(b, dst)
+        with open(dst + ".bai", "wb") as fh:
+            fh.write(b"not an index")
+        bams.append(dst)
+    fp = FilterParam(library_type="fr-first-strand")
+    want = oracle_backend.pileup_sites(syn5["bams"][:2], syn5["fasta"], param=fp)
+    got = _cuda()(bams, syn5["fasta"], param=fp)
+    _assert_same(got, want)
