@@ -895,8 +895,8 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return lens[x] > lens[y]; });
         raer::IngestConf icw = ic;
         if (!getenv("RAER_BATCH_READS")) {
-            // two batches per worker are in flight, each in its own pinned buffers: size them by the input (about 50
-            // compressed bytes per record) so that a small call does not pin more memory than it reads
+            // two batches per worker are in flight, each in its own host buffers: size them by the input (about 50
+            // compressed bytes per record) so that a small call does not hold more memory than it reads
             int64_t bytes = 0;
             for (int i = 0; i < nf; ++i) {
                 FILE* fp = fopen(a->bampaths[i], "rb");
@@ -968,6 +968,9 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
         std::vector<std::thread> th;
         for (int w = 0; w < n_workers; ++w) th.emplace_back(worker, w);
         std::vector<std::vector<raer_rows>> stash(names.size());
+        // batches of different contigs interleave: every contig's reference is uploaded once and stays on the device
+        // for the rest of the call (a genome is small next to 180 GB of HBM)
+        std::unordered_map<int, void*> dref;
         int ref_tid = -1;
         while (true) {
             Slot* sl = nullptr;
@@ -983,7 +986,24 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             if (rc == RAER_OK) {
                 if (sl->tid != ref_tid) {
                     double t0f = raer::now_seconds();
-                    rc = raer_ctx_set_reference(ctx, sl->tid, sl->ref->data(), (int64_t)sl->ref->size());
+                    const int64_t rlen = (int64_t)sl->ref->size();
+                    if (rlen == 0) {
+                        rc = raer_ctx_set_reference(ctx, sl->tid, nullptr, 0);
+                    } else {
+                        auto it = dref.find(sl->tid);
+                        if (it == dref.end()) {
+                            void* dp = nullptr;
+                            if (cudaMalloc(&dp, (size_t)rlen) != cudaSuccess ||
+                                cudaMemcpy(dp, sl->ref->data(), (size_t)rlen, cudaMemcpyHostToDevice) != cudaSuccess) {
+                                if (dp) cudaFree(dp);
+                                set_error("reference upload failed");
+                                rc = RAER_ERR_CUDA;
+                            } else {
+                                it = dref.emplace(sl->tid, dp).first;
+                            }
+                        }
+                        if (rc == RAER_OK) rc = raer_ctx_set_reference_device(ctx, sl->tid, it->second, rlen);
+                    }
                     tm_fasta += raer::now_seconds() - t0f;
                     ref_tid = sl->tid;
                 }
@@ -1000,6 +1020,9 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             cv_free.notify_all();
         }
         for (auto& t : th) t.join();
+        cudaStreamSynchronize((cudaStream_t)raer_ctx_stream(ctx));
+        for (auto& kv : dref) cudaFree(kv.second);
+        raer_ctx_set_reference(ctx, -1, nullptr, 0);
         if (rc == RAER_OK && worker_rc != RAER_OK) {
             rc = worker_rc;
             set_error("%s", worker_msg.c_str());
