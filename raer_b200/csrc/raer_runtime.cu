@@ -907,7 +907,7 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
         }
         // a stream's parser is one thread, its inflate costs about three times the parser's CPU time: give the inflate
         // of every stream two threads (the host is slightly oversubscribed, which keeps every core busy)
-        const int inflate_threads = std::max(2, (hw + n_workers * nf - 1) / (n_workers * nf));
+        const int inflate_threads = std::min(4, std::max(2, (hw + n_workers * nf - 1) / (n_workers * nf)));
         double w_decode = 0, w_pack = 0;
         int64_t w_records = 0, w_bases = 0;
         auto worker = [&](int w) {

@@ -466,8 +466,8 @@ def test_unusable_index_falls_back_to_the_single_stream(syn5, tmp_path):
     import shutil
 
     bams = []
-    for i, b in enumerate(syn5["bams"][:2]):
-        dst = str(tmp_path / f"b{i}.bam")
+    for b in syn5["bams"][:2]:
+        dst = str(tmp_path / os.path.basename(b))  # sample names come from the file names
         shutil.copy(b, dst)
         with open(dst + ".bai", "wb") as fh:
             fh.write(b"not an index")
