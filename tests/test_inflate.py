@@ -36,3 +36,12 @@ def test_bam_through_own_inflate_equals_zlib(ext):
         assert p.returncode == 0, p.stderr
         outs.append(p.stdout)
     assert outs[0] == outs[1] and "records" in outs[0]
+
+
+def test_qname_table_matches_unordered_map(tmp_path):
+    """The parser's allocation-free mate table (QnameTable, raer_host.h) against std::unordered_map."""
+    exe = str(tmp_path / "qname_table_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "raer_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "qname_table_check.cpp"), "-o", exe], check=True)
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0 and "0 differences" in p.stdout, p.stdout + p.stderr
