@@ -24,6 +24,7 @@
 
 // internal device -> host conditions (never returned through the C ABI): the host re-runs the batch
 #define RAER_RETRY_DEEP (-100)     // k_pileup_fast met coverage > 65535: re-run with k_pileup_tiles
+#define RAER_LANE_MW 5             // k_pileup_lane: mask words per read
 #define RAER_RETRY_LISTCAP (-101)  // the tile read lists did not fit their allocation: re-run with the exact size
 
 struct PlpParams {
@@ -55,6 +56,12 @@ struct PlpParams {
     unsigned long long* aei_out;     //   [n_files][16]
     int fast;                        // only mapq / base-quality filters configured: branch-free item path
     int use_fast;                    // launch k_pileup_fast (raer_fast.cuh) instead of k_pileup_tiles
+    int use_lane;                    // launch k_pileup_lane (raer_lane.cuh): lane per read, TMA-staged chunks
+    int carry_only;                  //   the tile lists hold only the reads that started in an earlier tile
+    const int* tile_first;           //   [(n_tiles + 1) * n_files] first read that starts at or behind the tile's first position
+    uint32_t* pmask_own;             //   [n_reads][RAER_LANE_MW] counted-reference-match masks of the tiles' own reads
+    uint32_t* pmask_cin;             //   [tile_list_cap][RAER_LANE_MW] ... of the carry-in list entries
+    int stage_bytes;                 //   per-warp staging slice (sequence span | quality span | masks)
     double ftrim_5p, ftrim_3p, min_af;
     int min_mapq[RAER_MAX_FILES];
     int okv[RAER_MAX_FILES];

@@ -976,14 +976,17 @@ __global__ void k_tile_count(PlpParams P, long long n_reads, int* cnt) {
     const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int f = 0, tf = 0, tl = -1;
-    const bool ok = r < n_reads && tile_span(P, r, f, tf, tl);
+    bool ok = r < n_reads && tile_span(P, r, f, tf, tl);
+    // k_pileup_lane: a tile finds the reads that start inside it by range (tile_first); only the tiles behind a read's
+    // first one list it
+    if (ok && P.carry_only && __ldg(&P.hdr[r].pos) >= P.t_beg) { ++tf; ok = tf <= tl; }
     const int more = __reduce_max_sync(FULL, ok ? tl - tf : -1);
     for (int k = 0; k <= min(more, TILE_AGG_STEPS); ++k) {
         const int key = (ok && tf + k <= tl) ? (tf + k) * P.n_files + f : -1;
         const unsigned peers = __match_any_sync(FULL, key);
         if (key >= 0 && (int)(__ffs(peers) - 1) == lane) atomicAdd(&cnt[key], __popc(peers));
     }
-    for (int t = tf + TILE_AGG_STEPS + 1; t <= tl; ++t) atomicAdd(&cnt[t * P.n_files + f], 1);
+    for (int t = tf + TILE_AGG_STEPS + 1; ok && t <= tl; ++t) atomicAdd(&cnt[t * P.n_files + f], 1);
 }
 // exclusive scan of n counts into off[0..n] (one CTA), cursors cleared
 __global__ void k_tile_scan(const int* cnt, int* off, int* cur, int n, int* total) {
@@ -1031,7 +1034,8 @@ __global__ void k_tile_fill(PlpParams P, long long n_reads, const int* off, int*
     const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int f = 0, tf = 0, tl = -1, cplx = 0;
-    const bool ok = r < n_reads && tile_span(P, r, f, tf, tl, &cplx);
+    bool ok = r < n_reads && tile_span(P, r, f, tf, tl, &cplx);
+    if (ok && P.carry_only && __ldg(&P.hdr[r].pos) >= P.t_beg) { ++tf; ok = tf <= tl; }
     const int more = __reduce_max_sync(FULL, ok ? tl - tf : -1);
     for (int k = 0; k <= min(more, TILE_AGG_STEPS); ++k) {
         const int key = (ok && tf + k <= tl) ? (tf + k) * P.n_files + f : -1;
@@ -1046,7 +1050,7 @@ __global__ void k_tile_fill(PlpParams P, long long n_reads, const int* off, int*
             if (slot >= 0 && slot < cap) list[slot] = (int)r;
         }
     }
-    for (int t = tf + TILE_AGG_STEPS + 1; t <= tl; ++t) {
+    for (int t = tf + TILE_AGG_STEPS + 1; ok && t <= tl; ++t) {
         const int k2 = t * P.n_files + f;
         const int rank = atomicAdd(cplx ? &cur_back[k2] : &cur[k2], 1);
         const int slot = cplx ? off[k2 + 1] - 1 - rank : off[k2] + rank;

@@ -949,7 +949,8 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* scra
     return res;
 }
 
-#include "raer_fast.cuh"  // k_pileup_fast: the mapq / base-quality-only configuration
+#include "raer_fast.cuh"  // k_pileup_fast: item-parallel tile kernel, every filter
+#include "raer_lane.cuh"  // k_pileup_lane: lane per read, TMA-staged chunks (mapq / base-quality filters only)
 
 __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -1105,6 +1106,12 @@ extern "C" int raer_launch_overlap(const raer_read_hdr* hdr, const uint32_t* cig
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
+extern "C" int raer_lane_first(PlpParams* P, int* first, cudaStream_t st) {
+    const int n = (P->n_tiles + 1) * P->n_files;
+    k_tile_first<<<(n + 127) / 128, 128, 0, st>>>(*P, first);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 extern "C" size_t raer_tile_smem_bytes(int n_files, int W, int S, int* cnt_words, int* slot_words) {
     int sw = 404 + 2 * RAER_SLOT_FS * n_files;
     int cw = n_files * 2 * RAER_NCLS * WPAD(W);
@@ -1121,6 +1128,25 @@ extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* l
         int n = P->n_tiles * P->n_files;
         k_tile_ranges<<<(n + 255) / 256, 256, 0, st>>>(*P);
         ++nl;
+    }
+    if (P->use_lane) {
+        const size_t lsmem = raer_lane_fixed_bytes(P->n_files, P->W) + (size_t)LN_WARPS * P->stage_bytes;
+        static size_t lconfigured_dev[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        size_t& lconfigured = lconfigured_dev[dev & 63];
+        if (lsmem > lconfigured) {
+            if (cudaFuncSetAttribute(k_pileup_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem) != cudaSuccess) return -1;
+            lconfigured = lsmem;
+        }
+        int grid = n_sm;
+        if (grid > P->n_tiles) grid = P->n_tiles;
+        if (e0) cudaEventRecord(e0, st);
+        k_pileup_lane<<<grid, LN_THREADS, lsmem, st>>>(*P);
+        if (e1) cudaEventRecord(e1, st);
+        ++nl;
+        *launches = nl;
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;
     }
     if (P->use_fast) {
         const size_t fsmem = raer_fast_smem_bytes(P->n_files, P->W);

@@ -33,6 +33,8 @@ extern "C" int raer_fast_index_count(PlpParams* P, long long n_reads, int* cnt, 
 extern "C" int raer_fast_index_fill(PlpParams* P, long long n_reads, const int* off, int* cur, int* cur_back, int* list, int cap,
                                     cudaStream_t st);
 extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* launches, cudaEvent_t e0, cudaEvent_t e1);
+extern "C" int raer_lane_plan(int n_files, int* stage_bytes);
+extern "C" int raer_lane_first(PlpParams* P, int* first, cudaStream_t st);
 
 #define CK(call)                                                                              \
     do {                                                                                      \
@@ -92,6 +94,7 @@ struct raer_ctx {
     DevBuf umi_holes;                      // bulk UMI mode: (read, position) pairs that stay counted
     DevBuf ov_scratch;                     // mate overlap: compacted list of the CIGAR-walking pairs
     DevBuf tile_idx, tile_list;            // k_pileup_fast: counts | offsets | cursors, and the per-tile read lists
+    DevBuf tile_first, pmask_own, pmask_cin;  // k_pileup_lane: own ranges of the tiles, counted-match masks of phase 1
     DevBuf tile_ranges, tile_rows, small;  // small: tile_counter(4) | pad | row_counter(8) | err(4)
     DevBuf row_pos, row_meta, row_stats, row_counts, row_alt;
     DevBuf ref;
@@ -143,7 +146,7 @@ extern "C" void raer_ctx_destroy(raer_ctx* c) {
         }
     }
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->hdr, &c->maxend, &c->cigar, &c->seq, &c->qual, &c->pair_b, &c->mask, &c->tile_ranges, &c->tile_rows, &c->tile_idx, &c->tile_list, &c->ov_scratch, &c->umi_holes, &c->aei,
+    for (DevBuf* b : {&c->hdr, &c->maxend, &c->cigar, &c->seq, &c->qual, &c->pair_b, &c->mask, &c->tile_ranges, &c->tile_rows, &c->tile_idx, &c->tile_list, &c->tile_first, &c->pmask_own, &c->pmask_cin, &c->ov_scratch, &c->umi_holes, &c->aei,
                       &c->small, &c->row_pos, &c->row_meta, &c->row_stats, &c->row_counts, &c->row_alt, &c->ref})
         b->release();
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -227,7 +230,16 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
     P.use_fast = conf->min_bq <= 128 && fw > 0 && !(kforce && !strcmp(kforce, "generic")) &&
                  !(flags & RUN_FORCE_GENERIC);
     P.W = P.use_fast ? fw : choose_tile_width(nf);
-    if (P.use_fast && getenv("RAER_FAST_W")) P.W = std::max(32, std::min(fw, atoi(getenv("RAER_FAST_W")) & ~31));
+    P.fast = !(conf->umi_mode || conf->trim_5p > 0 || conf->trim_3p > 0 || conf->ftrim_5p > 0 || conf->ftrim_3p > 0 || conf->splice_dist ||
+               conf->min_overhang || conf->indel_dist || conf->n_mm_type > 0 || conf->n_mm > 0);
+    // k_pileup_lane (lane per read, TMA-staged chunks) when only the mapq / base-quality filters are configured;
+    // RAER_KERNEL=fast keeps k_pileup_fast for those calls too
+    if (P.use_fast && P.fast && !(kforce && !strcmp(kforce, "fast"))) {
+        int sb = 0;
+        const int lw = raer_lane_plan(nf, &sb);
+        if (lw > 0) { P.use_lane = 1; P.carry_only = 1; P.W = lw; P.stage_bytes = sb; }
+    }
+    if (P.use_fast && getenv("RAER_FAST_W")) P.W = std::max(32, std::min(P.W, atoi(getenv("RAER_FAST_W")) & ~31));
     long long span = (long long)b->end - b->beg;
     P.n_tiles = span > 0 ? (int)((span + P.W - 1) / P.W) : 0;
     P.ref = c->ref_ptr; P.ref_len = (int)std::min<int64_t>(c->ref_len, INT_MAX);
@@ -252,8 +264,6 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
         set_error("umi_tag in pileup_sites needs the fast tile kernel (min_base_quality <= 128, coverage <= 65535)");
         return RAER_ERR_LIMIT;
     }
-    P.fast = !(conf->umi_mode || conf->trim_5p > 0 || conf->trim_3p > 0 || conf->ftrim_5p > 0 || conf->ftrim_3p > 0 || conf->splice_dist ||
-               conf->min_overhang || conf->indel_dist || conf->n_mm_type > 0 || conf->n_mm > 0);
     for (int i = 0; i < nf; ++i) {
         P.min_mapq[i] = conf->min_mapq[i];
         P.okv[i] = conf->only_keep_variants[i];
@@ -315,7 +325,7 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
             int* cur = off + ne;
             int* d_total = (int*)((char*)c->small.p + 32);
             const long long n_reads = b->file_off[nf];
-            long long want = std::max(list_need, 2 * n_reads + (long long)ne + 1024);
+            long long want = std::max(list_need, (P.carry_only ? 1 : 2) * n_reads + (long long)ne + 1024);
             if (want > INT_MAX) want = INT_MAX;
             if ((rc = c->tile_list.ensure((size_t)want * sizeof(int)))) return rc;
             int cap = (int)std::min<size_t>(c->tile_list.cap / sizeof(int), (size_t)INT_MAX);
@@ -330,6 +340,19 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
             P.tile_off = off;
             P.tile_list = (const int*)c->tile_list.p;
             P.tile_list_cap = cap;
+            if (P.use_lane) {
+                if ((rc = c->tile_first.ensure(((size_t)P.n_tiles + 1) * nf * sizeof(int)))) return rc;
+                if (P.want_stats && !P.aei_mode) {
+                    if ((rc = c->pmask_own.ensure((size_t)n_reads * RAER_LANE_MW * 4 + 16))) return rc;
+                    if ((rc = c->pmask_cin.ensure(((size_t)cap + 32) * RAER_LANE_MW * 4 + 16))) return rc;
+                }
+                P.tile_first = (const int*)c->tile_first.p;
+                P.pmask_own = (uint32_t*)c->pmask_own.p;
+                P.pmask_cin = (uint32_t*)c->pmask_cin.p;
+                r = raer_lane_first(&P, (int*)c->tile_first.p, c->stream);
+                if (r < 0) { set_error("tile index kernels failed"); return RAER_ERR_CUDA; }
+                nl += r;
+            }
         }
         int tl = 0;
         cudaEvent_t e0 = nullptr, e1 = nullptr;

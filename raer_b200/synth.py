@@ -374,9 +374,31 @@ def make_sc_dataset(outdir: str, *, n_contigs=2, contig_len=60_000, reads_per_co
 
 
 # --------------------------------------------------------------------------------------- device batches
-def pack_device_batch(per_file: List[Reads], tid: int, beg: int, end: int, remove_overlaps: bool = True):
+def qname_coin(qname: bytes) -> bool:
+    """htslib >= 1.13 overlap tie-break: Wang_hash(X31_hash(qname)) & 1 (true: the earlier mate keeps its qualities)."""
+    h = qname[0]
+    if h > 127:
+        h -= 256
+    h &= 0xFFFFFFFF
+    for c in qname[1:]:
+        h = ((h << 5) - h + (c if c < 128 else c - 256)) & 0xFFFFFFFF
+    k = h
+    k = (k + (~(k << 15) & 0xFFFFFFFF)) & 0xFFFFFFFF
+    k ^= k >> 10
+    k = (k + (k << 3)) & 0xFFFFFFFF
+    k ^= k >> 6
+    k = (k + (~(k << 11) & 0xFFFFFFFF)) & 0xFFFFFFFF
+    k ^= k >> 16
+    return bool(k & 1)
+
+
+def pack_device_batch(per_file: List[Reads], tid: int, beg: int, end: int, remove_overlaps: bool = True,
+                      qname_prefixes: Optional[List[str]] = None):
     """Lay out the reads of one contig (all files) as a raer_read_batch in the memory of their
-    device (HBM when generated on cuda). Returns (dict of tensors kept alive, fields for ReadBatch)."""
+    device (HBM when generated on cuda). Returns (dict of tensors kept alive, fields for ReadBatch).
+    qname_prefixes: per file, the prefix write_bam() gives the read names of these records; the mate-overlap coin is
+    then htslib's hash of the real name "<prefix><pair_id + (tid << 40)>" instead of the integer stand-in (tests
+    that hold a packed batch against the oracle on the BAM written from the same records)."""
     from . import _cabi
 
     dev = per_file[0].pos.device
@@ -414,7 +436,16 @@ def pack_device_batch(per_file: List[Reads], tid: int, beg: int, end: int, remov
             ok = later & ~((r.isize.abs() >= 2 * rl) & (r.mate_pos >= r.end))
             ok &= mend >= r.pos                              # entry still alive in the pileup buffer
             mate = torch.where(ok, m + ro, mate)
-            keep_a = _keep_a_bits(r.pair_id[m.clamp(min=0)])
+            if qname_prefixes is not None:
+                pfx = qname_prefixes[len(hdrs)]
+                pids = (r.pair_id[m.clamp(min=0)] + (tid << 40)).cpu().numpy()
+                okn = ok.cpu().numpy()
+                coin = np.zeros(n, dtype=bool)
+                for i in np.flatnonzero(okn):
+                    coin[i] = qname_coin(f"{pfx}{int(pids[i])}".encode())
+                keep_a = torch.from_numpy(coin).to(dev)
+            else:
+                keep_a = _keep_a_bits(r.pair_id[m.clamp(min=0)])
             h[:, 2] |= (ok & keep_a).int() << (24 + 3)
             pairs.append((idx[ok] + ro).int())
             del mpos

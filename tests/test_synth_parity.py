@@ -83,6 +83,19 @@ def test_two_bam_parity_generic_kernel(syn, kw, monkeypatch):
     _assert_same(got, want)
 
 
+# Calls with only the mapq / base-quality filters run k_pileup_lane by default; RAER_KERNEL=fast keeps them on
+# k_pileup_fast<false>, so that kernel stays held to the oracle as well.
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [CONFIGS[i] for i in (0, 1, 2, 3, 4, 7, 8, 9, 10, 12)],
+                         ids=[str(i) for i in (0, 1, 2, 3, 4, 7, 8, 9, 10, 12)])
+def test_two_bam_parity_item_kernel(syn, kw, monkeypatch):
+    monkeypatch.setenv("RAER_KERNEL", "fast")
+    fp = FilterParam(**kw)
+    want = oracle_backend.pileup_sites(syn["bams"], syn["fasta"], param=fp)
+    got = _cuda()(syn["bams"], syn["fasta"], param=fp)
+    _assert_same(got, want)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("fast_w", [32, 160, 512])
 def test_fast_kernel_tile_width_does_not_change_results(syn, fast_w, monkeypatch):
