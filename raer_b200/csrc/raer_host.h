@@ -11,6 +11,7 @@
 #include <stdio.h>
 
 #include <future>
+#include <mutex>
 #include <queue>
 #include <string>
 #include <unordered_map>
@@ -50,8 +51,15 @@ public:
     double decode_seconds() const { return t_decode_; }
     double wait_seconds() const { return t_wait_; }  // time the parser waited for an inflated group
     int64_t records_read() const { return n_records_; }
+    // a read, framing, inflate, checksum or record-layout error stopped the stream (sticky; distinct from the end of the file)
+    bool failed() const { return failed_; }
+    std::string error() const { std::lock_guard<std::mutex> g(err_mu_); return err_; }
 
 private:
+    int fail(const char* fmt, ...);  // records the message in the object (the prefetch task runs on another thread); returns -1
+    bool failed_ = false;
+    std::string err_;
+    mutable std::mutex err_mu_;
     bool fill();  // next group of inflated BGZF blocks into ubuf_; the group after it is inflated in the background
     int produce(std::vector<uint8_t>& out);  // read + inflate one group into out: 1 data, 0 end of file, -1 error
     bool read_header();
@@ -198,6 +206,9 @@ struct FilePending {
     std::vector<uint8_t> seq, qual;
     size_t cig_base = 0, sq_base = 0;  // pool offsets already compacted away
     bool eof = false;
+    bool failed = false;     // the stream or a record was corrupt / the input is not coordinate sorted: the call must fail
+    std::string err;
+    int sort_tid = -1, sort_pos = -1;  // last read handed to the pileup (htslib bam_plp_push: max_tid, max_pos)
     bool have_look = false;  // a parsed record waiting in `look`
     HostRead look;
     std::vector<uint32_t> look_cigar;
@@ -256,6 +267,10 @@ public:
     int reg_tid() const { return reg_tid_; }
     int reg_beg() const { return reg_beg_; }
     int reg_end() const { return reg_end_; }
+    // a file could not be read to its end, a record was corrupt, or the input is not coordinate sorted: the rows
+    // produced so far are not the result of the call (the reference raises Rf_error, src/plp.c:1195)
+    bool failed() const;
+    std::string error() const;
     double decode_seconds() const;
     double pack_seconds() const { return t_pack_; }
     double parse_seconds() const { return t_parse_; }  // wall time of the parse section of next_batch (all files side by side)

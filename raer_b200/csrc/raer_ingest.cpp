@@ -67,7 +67,19 @@ struct BlockJob {
     uint32_t c_len; // payload bytes
     size_t u_off;   // destination in ubuf_
     uint32_t u_len;
+    uint32_t crc;   // CRC32 of the inflated bytes (BGZF block trailer)
 };
+
+int BamStream::fail(const char* fmt, ...) {
+    char buf[400];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    std::lock_guard<std::mutex> g(err_mu_);
+    err_ = buf;
+    return -1;
+}
 
 int BamStream::produce(std::vector<uint8_t>& out) {
     double t0 = now_seconds();
@@ -92,7 +104,7 @@ int BamStream::produce(std::vector<uint8_t>& out) {
         size_t o = c_off_;
         while (o + 18 <= cbuf_.size() && out_off < kMaxOut) {
             const uint8_t* h = cbuf_.data() + o;
-            if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { set_error("corrupt BGZF block"); return -1; }
+            if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) return fail("corrupt BGZF block header");
             int xlen = le16(h + 10);
             if (o + 12 + xlen > cbuf_.size()) break;
             int bsize = -1;
@@ -101,10 +113,14 @@ int BamStream::produce(std::vector<uint8_t>& out) {
                 if (h[12 + e] == 'B' && h[13 + e] == 'C' && slen == 2) bsize = le16(h + 12 + e + 4);
                 e += 4 + slen;
             }
-            if (bsize < 0) { set_error("BGZF block without BC field"); return -1; }
+            if (bsize < 0) return fail("BGZF block without BC field");
+            // header (12) + extra field + at least two payload bytes + CRC32 and ISIZE
+            if (bsize + 1 < 12 + xlen + 2 + 8) return fail("corrupt BGZF block (BSIZE smaller than its own header)");
             if (o + bsize + 1 > cbuf_.size()) break;
             uint32_t isize = le32(h + bsize + 1 - 4);
+            if (isize > 65536u) return fail("corrupt BGZF block (ISIZE above 64 KiB)");
             BlockJob j;
+            j.crc = le32(h + bsize + 1 - 8);
             j.c_off = o + 12 + xlen;
             j.c_len = (uint32_t)(bsize + 1 - 12 - xlen - 8);
             j.u_off = out_off;
@@ -117,12 +133,13 @@ int BamStream::produce(std::vector<uint8_t>& out) {
         c_off_ = o;
         if (!jobs.empty()) break;
         if (file_eof_) {
-            // nothing but (possibly) empty blocks and a tail shorter than a block header are left
-            if (!progressed || c_off_ + 18 > cbuf_.size()) { t_decode_ += now_seconds() - t0; return 0; }
+            if (c_off_ >= cbuf_.size()) { t_decode_ += now_seconds() - t0; return 0; }  // every byte of the file was a whole block
+            // bytes that do not make a whole block: the file was cut (htslib: "truncated file")
+            if (!progressed) return fail("truncated BGZF file (incomplete block at the end)");
             continue;
         }
         // a block larger than what is buffered cannot happen (blocks are <= 64 KiB); only empty blocks so far: read on
-        if (!progressed && cbuf_.size() - c_off_ >= (1u << 20)) { set_error("BGZF framing error"); return -1; }
+        if (!progressed && cbuf_.size() - c_off_ >= (1u << 20)) return fail("BGZF framing error");
     }
     out.resize(out_off);
     int nt = std::max(1, std::min<int>(threads_, (int)jobs.size() / 4 + 1));
@@ -131,22 +148,24 @@ int BamStream::produce(std::vector<uint8_t>& out) {
     // takes the last block of the buffer (the decoder wants 16 readable bytes behind a payload), anything the decoder
     // refuses, and everything when RAER_ZLIB_INFLATE is set
     static const bool own_inflate = getenv("RAER_ZLIB_INFLATE") == nullptr;
+    static const bool check_crc = getenv("RAER_SKIP_CRC") == nullptr;  // htslib verifies every block's CRC32 too
     auto work = [&](int t) {
         z_stream zs;
         memset(&zs, 0, sizeof(zs));
         if (inflateInit2(&zs, -15) != Z_OK) { status[t] = -1; return; }
         for (size_t i = t; i < jobs.size(); i += nt) {
             const BlockJob& j = jobs[i];
-            if (own_inflate && j.c_off + j.c_len + 16 <= cbuf_.size() &&
-                inflate_raw(cbuf_.data() + j.c_off, j.c_len, out.data() + j.u_off, j.u_len) == 0)
-                continue;
-            inflateReset(&zs);
-            zs.next_in = cbuf_.data() + j.c_off;
-            zs.avail_in = j.c_len;
-            zs.next_out = out.data() + j.u_off;
-            zs.avail_out = j.u_len;
-            int zr = inflate(&zs, Z_FINISH);
-            if (zr != Z_STREAM_END || zs.avail_out != 0) { status[t] = -1; break; }
+            if (!(own_inflate && j.c_off + j.c_len + 16 <= cbuf_.size() &&
+                  inflate_raw(cbuf_.data() + j.c_off, j.c_len, out.data() + j.u_off, j.u_len) == 0)) {
+                inflateReset(&zs);
+                zs.next_in = cbuf_.data() + j.c_off;
+                zs.avail_in = j.c_len;
+                zs.next_out = out.data() + j.u_off;
+                zs.avail_out = j.u_len;
+                int zr = inflate(&zs, Z_FINISH);
+                if (zr != Z_STREAM_END || zs.avail_out != 0) { status[t] = -1; break; }
+            }
+            if (check_crc && (uint32_t)crc32(0L, out.data() + j.u_off, j.u_len) != j.crc) { status[t] = -2; break; }
         }
         inflateEnd(&zs);
     };
@@ -157,7 +176,7 @@ int BamStream::produce(std::vector<uint8_t>& out) {
         for (auto& x : th) x.join();
     }
     for (int s : status)
-        if (s) { set_error("inflate failed"); return -1; }
+        if (s) return fail(s == -2 ? "BGZF block CRC32 mismatch" : "inflate failed (corrupt BGZF block)");
     t_decode_ += now_seconds() - t0;
     return 1;
 }
@@ -174,6 +193,7 @@ bool BamStream::fill() {
     } else {
         rc = produce(grp);
     }
+    if (rc < 0) { failed_ = true; set_error("%s", error().c_str()); }
     if (rc <= 0) { drained_ = true; return false; }
     // keep the unread tail of the previous group (a record can straddle two groups) in front of the new bytes
     const size_t leftover = ubuf_.size() - u_off_;
@@ -247,22 +267,30 @@ bool BamStream::set_region(const char* bai_path, int tid, int beg, int end) {
     long o = 8;
     uint64_t voff = 0;
     bool found = false;
-    for (int t = 0; t < n_ref && o + 4 <= sz; ++t) {
+    // every count and offset comes from the file: nothing is read beyond its size
+    auto room = [&](long bytes) { return bytes >= 0 && o >= 0 && o <= sz && bytes <= sz - o; };
+    bool bad = n_ref < 0;
+    for (int t = 0; !bad && t < n_ref && o + 4 <= sz; ++t) {
         int n_bin = (int)le32(d.data() + o);
         o += 4;
+        if (n_bin < 0) { bad = true; break; }
         uint64_t min_chunk = UINT64_MAX;
         for (int b = 0; b < n_bin; ++b) {
+            if (!room(8)) { bad = true; break; }
             uint32_t bin = le32(d.data() + o);
             int n_chunk = (int)le32(d.data() + o + 4);
             o += 8;
+            if (n_chunk < 0 || !room(16L * n_chunk)) { bad = true; break; }
             for (int c = 0; c < n_chunk; ++c) {
                 uint64_t cb = le64(d.data() + o);
                 if (bin != 37450 && cb < min_chunk) min_chunk = cb;
                 o += 16;
             }
         }
+        if (bad || !room(4)) { bad = true; break; }
         int n_intv = (int)le32(d.data() + o);
         o += 4;
+        if (n_intv < 0 || !room(8L * n_intv)) { bad = true; break; }
         if (t == tid) {
             int w = beg >> 14;
             uint64_t v = 0;
@@ -278,6 +306,7 @@ bool BamStream::set_region(const char* bai_path, int tid, int beg, int end) {
         }
         o += 8L * n_intv;
     }
+    if (bad) { set_error("corrupt BAI index %s", bai_path); return false; }
     light_ = false;
     if (!found) { region_done_ = true; return true; }  // no alignments on that contig
     if (pf_.valid()) pf_.get();  // the prefetch started after the header holds bytes from the wrong place
@@ -294,10 +323,18 @@ bool BamStream::set_region(const char* bai_path, int tid, int beg, int end) {
 int BamStream::next(BamRecView& r) {
     while (true) {
         if (region_done_) return -1;
-        if (!need(4)) return -1;
+        if (!need(4)) {
+            if (failed_) return -2;
+            if (ubuf_.size() != u_off_) { failed_ = true; fail("truncated BAM record"); set_error("%s", error().c_str()); return -2; }
+            return -1;
+        }
         uint32_t bs = le32(ubuf_.data() + u_off_);
-        if (bs < 32) { set_error("corrupt BAM record"); return -2; }
-        if (!need(4 + (size_t)bs)) { set_error("truncated BAM record"); return -2; }
+        if (bs < 32) { failed_ = true; fail("corrupt BAM record"); set_error("%s", error().c_str()); return -2; }
+        if (!need(4 + (size_t)bs)) {
+            if (!failed_) { failed_ = true; fail("truncated BAM record"); }
+            set_error("%s", error().c_str());
+            return -2;
+        }
         const uint8_t* p = ubuf_.data() + u_off_ + 4;
         u_off_ += 4 + bs;
         ++n_records_;
@@ -311,8 +348,9 @@ int BamStream::next(BamRecView& r) {
         r.mtid = (int32_t)le32(p + 20);
         r.mpos = (int32_t)le32(p + 24);
         r.isize = (int32_t)le32(p + 28);
-        size_t fixed = (size_t)r.l_qname + 4u * r.n_cigar + (size_t)(r.l_qseq + 1) / 2 + r.l_qseq;
-        if (32 + fixed > bs) { set_error("corrupt BAM record layout"); return -2; }
+        if (r.l_qseq < 0) { failed_ = true; fail("corrupt BAM record (negative l_seq)"); set_error("%s", error().c_str()); return -2; }
+        size_t fixed = (size_t)r.l_qname + 4u * r.n_cigar + ((size_t)r.l_qseq + 1) / 2 + (size_t)r.l_qseq;
+        if (32 + fixed > bs) { failed_ = true; fail("corrupt BAM record layout"); set_error("%s", error().c_str()); return -2; }
         r.qname = (const char*)p + 32;
         r.cigar_bytes = p + 32 + r.l_qname;
         r.seq = r.cigar_bytes + 4u * r.n_cigar;
@@ -599,6 +637,16 @@ double Ingest::decode_seconds() const {
     for (auto* f : files_) t += f->bs.decode_seconds();
     return t;
 }
+bool Ingest::failed() const {
+    for (auto* f : files_)
+        if (f->failed) return true;
+    return false;
+}
+std::string Ingest::error() const {
+    for (auto* f : files_)
+        if (f->failed) return f->err.empty() ? std::string("BAM read error") : f->err;
+    return std::string();
+}
 int64_t Ingest::records() const {
     int64_t n = 0;
     for (auto* f : files_) n += f->bs.records_read();
@@ -637,7 +685,14 @@ bool Ingest::parse_one(int fi) {
     std::vector<uint32_t>& cig = F.look_cigar;
     while (true) {
         int rc = F.bs.next(r);
-        if (rc < 0) { F.eof = true; F.have_look = false; return false; }
+        if (rc < 0) {
+            // -1 is the end of the file (or of the region); anything else -- or a stream that stopped on a read /
+            // inflate / checksum error -- fails the call: the reference raises an error here (src/plp.c:1195)
+            if (rc != -1 || F.bs.failed()) { F.failed = true; F.err = F.bs.error(); }
+            F.eof = true;
+            F.have_look = false;
+            return false;
+        }
         if (r.tid < 0 || (r.flag & 4)) continue;
         int rlen = 0;
         int64_t nal = 0;
@@ -675,7 +730,14 @@ bool Ingest::parse_one(int fi) {
             double frac = (double)lq / r.l_qseq;
             if (!(frac <= (float)conf_.rq_pct)) continue;
         }
-        if (r.l_qseq > 65535 || r.n_cigar > 65535) { set_error("read longer than 65535 bases is not supported"); F.eof = true; F.have_look = false; return false; }
+        if (r.l_qseq > 65535 || r.n_cigar > 65535) {
+            F.failed = true;
+            F.err = "read longer than 65535 bases is not supported";
+            set_error("%s", F.err.c_str());
+            F.eof = true;
+            F.have_look = false;
+            return false;
+        }
 
         // ---- stream-order decisions of bam_plp_push
         if (F.live_tid != r.tid) {
@@ -696,6 +758,18 @@ bool Ingest::parse_one(int fi) {
                 continue;  // dropped by maxcnt
             }
         }
+        // htslib bam_plp_push refuses input that is not coordinate sorted ("the input is not sorted"): everything below
+        // -- batch windows, maxend prefixes, mate pairing, the max_depth count -- relies on the order
+        if (r.tid < F.sort_tid || (r.tid == F.sort_tid && r.pos < F.sort_pos)) {
+            F.failed = true;
+            F.err = r.tid < F.sort_tid ? "the input is not sorted (chromosomes out of order)" : "the input is not sorted (reads out of order)";
+            set_error("%s", F.err.c_str());
+            F.eof = true;
+            F.have_look = false;
+            return false;
+        }
+        F.sort_tid = r.tid;
+        F.sort_pos = r.pos;
         HostRead& H = F.look;
         memset(&H, 0, sizeof(H));
         H.h.pos = r.pos;

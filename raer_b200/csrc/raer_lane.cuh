@@ -30,9 +30,7 @@
 #define LN_HASMM 0x40000000u         // last mask word: the read has a counted mismatch inside this tile
 #define LN_NOMASK 0x80000000u        //                 the read is longer than the mask: the second pass looks at its bases
 #define LN_MASK_BYTES (32 * LN_MW * 4)
-#define LREC (FREC + LN_MW + 1)      // second pass: staged record + mask words (odd stride)
-#define FR_MASK FREC
-#define LN_REC2_WORDS (32 * LREC + 64)  // per warp: records, pair prefix sums, read ordinals
+#define LN_REC2_WORDS (32 * LN_MW + 32)  // second pass, per warp: the masks of its 32 reads
 #define LN_PAD 16                    // reference bases packed in front of the tile
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -133,13 +131,17 @@ __device__ __forceinline__ uint32_t lane_chunk(const FastSmem& S, const LaneCtx&
     return CM;
 }
 
-// Phase 1 for one read, one lane: coverage events and chunks of every aligned block that reaches into the tile.
-// sp / qp: the read's packed sequence / qualities (shared memory when STAGED, else global); mk: LN_MW mask words.
+// Phase 1 for up to 32 reads, one per lane, called by the whole warp (have: this lane has a read): coverage events and
+// chunks of every aligned block that reaches into the tile. The lanes walk their CIGARs on their own, but they take
+// their chunks in lock step -- the ballot at the top of the loop re-joins the warp before every chunk, so the long
+// straight-line chunk code runs with all lanes that still have work (without it lanes that once diverged would keep
+// running as separate sub-warps). sp / qp: the read's packed sequence / qualities (shared memory when STAGED, else
+// global); mk: LN_MW mask words.
 template <bool STAGED>
-__device__ __forceinline__ void lane_read(const PlpParams& P, const FastSmem& S, const LaneCtx& X, const int4 a, const int4 b, int f,
-                                          const uint8_t* sp, const uint8_t* qp, uint32_t* mk) {
+__device__ __forceinline__ void warp_reads(const PlpParams& P, const FastSmem& S, const LaneCtx& X, bool have, const int4 a, const int4 b,
+                                           int f, const uint8_t* sp, const uint8_t* qp, uint32_t* mk) {
     const int mapq = (a.z >> 16) & 0xff, bits = (a.z >> 24) & 0xff;
-    const int lq = a.w & 0xffff, n = (a.w >> 16) & 0xffff;
+    const int lq = a.w & 0xffff, n = have ? (a.w >> 16) & 0xffff : 0;
     const int s = bits & RAER_RB_INVERT;
     const bool mapq_fail = mapq < P.min_mapq[f];
     uint32_t* dl = S.cnt + (size_t)((f * 2 + s) * 4) * S.WS;
@@ -149,229 +151,184 @@ __device__ __forceinline__ void lane_read(const PlpParams& P, const FastSmem& S,
     const bool one_block = n == 1 && a.y - a.x == lq && lq > 0;
     const bool masked = X.want_mask && lq <= LN_MAXQ;
     uint32_t hasmm = 0;
-    if (X.want_mask) {
+    if (X.want_mask && have) {
 #pragma unroll
         for (int i = 0; i < LN_MW; ++i) mk[i] = 0;
     }
-    int x = a.x, y = 0;
-    for (int k = 0; k < n; ++k) {
-        const uint32_t w = one_block ? ((uint32_t)lq << 4) : __ldg(cg + k);
-        const int op = cg_op(w), len = cg_len(w);
-        if (X.need_cov && (cg_type(op) & 2)) {
-            const int lo = max(x, X.t0), h2 = min(x + len, X.t1);
-            if (lo < h2) cover_range(S.covered, lo - X.t0, h2 - X.t0);
+    int x = a.x, y = 0, k = 0;
+    int q0 = 0, qa = 0, qb = 0, rel_a = 0;  // current aligned block inside the tile: query bases [qa, qb), next chunk at q0
+    while (true) {
+        while (q0 >= qb && k < n) {  // next aligned block that reaches into the tile
+            const uint32_t w = one_block ? ((uint32_t)lq << 4) : __ldg(cg + k);
+            ++k;
+            const int op = cg_op(w), len = cg_len(w);
+            if (X.need_cov && (cg_type(op) & 2)) {
+                const int lo = max(x, X.t0), h2 = min(x + len, X.t1);
+                if (lo < h2) cover_range(S.covered, lo - X.t0, h2 - X.t0);
+            }
+            if ((0x181 >> op) & 1) {  // M = X
+                const int lo = max(x, X.t0), hi = min(x + min(len, lq - y), X.t1);
+                if (lo < hi) {
+                    red_add(dl + (lo - X.t0), 1u);
+                    red_add(dl + (hi - X.t0), 0xffffffffu);
+                    qa = y + (lo - x);  // query bases [qa, qb) sit on tile positions rel_a ...
+                    qb = y + (hi - x);
+                    rel_a = lo - X.t0;
+                    q0 = qa & ~15;
+                }
+                x += len;
+                y += len;
+            } else if ((0xC >> op) & 1) {  // D N
+                x += len;
+            } else if ((0x12 >> op) & 1) {  // I S
+                y += len;
+            }
         }
-        if ((0x181 >> op) & 1) {  // M = X
-            const int lo = max(x, X.t0), hi = min(x + min(len, lq - y), X.t1);
-            if (lo < hi) {
-                red_add(dl + (lo - X.t0), 1u);
-                red_add(dl + (hi - X.t0), 0xffffffffu);
-                const int qa = y + (lo - x), qb = y + (hi - x);  // query bases [qa, qb) sit on tile positions lo - t0 ...
-                for (int q0 = qa & ~15; q0 < qb; q0 += 16) {
-                    const bool two = q0 + 8 < lq;
-                    uint32_t s0, s1 = 0xffffffffu;
-                    uint2 u0, u1 = make_uint2(0, 0);
-                    if (STAGED) {
-                        s0 = *reinterpret_cast<const uint32_t*>(sp + (q0 >> 1));
-                        u0 = *reinterpret_cast<const uint2*>(qp + q0);
-                        if (two) {
-                            s1 = *reinterpret_cast<const uint32_t*>(sp + (q0 >> 1) + 4);
-                            u1 = *reinterpret_cast<const uint2*>(qp + q0 + 8);
-                        }
-                    } else {
-                        s0 = __ldg(reinterpret_cast<const uint32_t*>(sp + (q0 >> 1)));
-                        u0 = __ldg(reinterpret_cast<const uint2*>(qp + q0));
-                        if (two) {
-                            s1 = __ldg(reinterpret_cast<const uint32_t*>(sp + (q0 >> 1) + 4));
-                            u1 = __ldg(reinterpret_cast<const uint2*>(qp + q0 + 8));
-                        }
-                    }
-                    const uint32_t cm = lane_chunk(S, X, cbs, nib_swap(s0), nib_swap(s1), u0, u1, (lo - X.t0) + (q0 - qa),
-                                                   max(qa - q0, 0), min(qb - q0, 16), mapq_fail, s ? 3 : 0, hasmm);
-                    if (masked) mk[q0 >> 5] |= cm << (q0 & 16);
+        const bool act = q0 < qb;
+        if (!__ballot_sync(FULL, act)) break;
+        if (act) {
+            const bool two = q0 + 8 < lq;
+            uint32_t s0, s1 = 0xffffffffu;
+            uint2 u0, u1 = make_uint2(0, 0);
+            if (STAGED) {
+                s0 = *reinterpret_cast<const uint32_t*>(sp + (q0 >> 1));
+                u0 = *reinterpret_cast<const uint2*>(qp + q0);
+                if (two) {
+                    s1 = *reinterpret_cast<const uint32_t*>(sp + (q0 >> 1) + 4);
+                    u1 = *reinterpret_cast<const uint2*>(qp + q0 + 8);
+                }
+            } else {
+                s0 = __ldg(reinterpret_cast<const uint32_t*>(sp + (q0 >> 1)));
+                u0 = __ldg(reinterpret_cast<const uint2*>(qp + q0));
+                if (two) {
+                    s1 = __ldg(reinterpret_cast<const uint32_t*>(sp + (q0 >> 1) + 4));
+                    u1 = __ldg(reinterpret_cast<const uint2*>(qp + q0 + 8));
                 }
             }
-            x += len;
-            y += len;
-        } else if ((0xC >> op) & 1) {  // D N
-            x += len;
-        } else if ((0x12 >> op) & 1) {  // I S
-            y += len;
+            const uint32_t cm = lane_chunk(S, X, cbs, nib_swap(s0), nib_swap(s1), u0, u1, rel_a + (q0 - qa), max(qa - q0, 0),
+                                           min(qb - q0, 16), mapq_fail, s ? 3 : 0, hasmm);
+            if (masked) mk[q0 >> 5] |= cm << (q0 & 16);
+            q0 += 16;
         }
     }
-    if (X.want_mask) {
+    if (X.want_mask && have) {
         if (!masked) mk[LN_MW - 1] = LN_NOMASK;
         else if (hasmm) mk[LN_MW - 1] |= LN_HASMM;
     }
 }
 
-// ---- second pass: one (read, flagged position) pair per lane, answered from the read's mask
-__device__ __forceinline__ void lane_pair(const PlpParams& P, const FastSmem& S, const LaneCtx& X, const TileSmem& T2,
-                                          const uint32_t* rec, int rank, int ordinal, bool active) {
-    const int pos = (int)rec[FR_POS];
-    const int lq = (int)(rec[FR_LEN] & 0xffff), n = (int)(rec[FR_LEN] >> 16);
-    const unsigned fl = rec[FR_FLAGS];
-    const int qs = (int)(rec[FR_QSQE] & 0xffff), qe = (int)(rec[FR_QSQE] >> 16);
-    const int pidx = active ? (int)S.flag_pidx[rank] : 0;
-    const int p = X.t0 + pidx;
-    bool valid = active;
-    int q = 0;
-    if (valid) {
-        if (fl & STF_SIMPLE) {
-            q = qs + (p - pos);
-            valid = q < qe;
-        } else {
-            const uint32_t* cig = n <= 4 ? rec + FR_CIG0 : P.cigar + rec[FR_CIG0];
-            int x = pos, y = 0, k = 0, op = -1, len = 0;
-            for (; k < n; ++k) {
-                const uint32_t w = cig[k];
-                op = cg_op(w);
-                len = cg_len(w);
-                if ((0x18D >> op) & 1) {  // M D N = X
-                    if (p < x + len) break;
-                    x += len;
-                    if ((0x181 >> op) & 1) y += len;
-                } else if ((0x12 >> op) & 1) {
-                    y += len;
-                }
-            }
-            // past the end of the read, or a deletion / ref-skip at p (filtered silently, src/plp.c:571)
-            valid = k < n && !((0xC >> op) & 1);
-            q = y + (p - x);
-        }
-        valid = valid && q < lq;
-    }
-    __syncwarp();
-    int code = 0, isref = 1;
-    if (valid) {
-        const uint32_t top = rec[FR_MASK + LN_MW - 1];
-        if (!(top & LN_NOMASK) && ((rec[FR_MASK + (q >> 5)] >> (q & 31)) & 1u)) {
-            // counted in phase 1 as a base that equals the reference
-        } else if (top & (LN_NOMASK | LN_HASMM)) {
-            // the read carries a variant base somewhere in the tile (or has no mask): look at this base
-            const uint32_t sq = rec[FR_SQ];
-            code = seq_code(P.seq + sq, q);
-            const int bq = P.qual[2ull * sq + q];
-            const int a = pidx + LN_PAD;
-            const int rcode = (S.refn[a >> 3] >> ((a & 7) << 2)) & 15;
-            // read base N (src/plp.c:718); nX or dropped bases are not part of the statistics
-            valid = code != 15 && bq >= X.minbq;
-            isref = (code == rcode) & (code != 0);
-        } else {
-            valid = false;
-        }
-    }
-    __syncwarp();
-    if (valid) {
-        ReadCtx c;
-        c.l_qseq = lq;
-        c.qs = qs;
-        c.qe = qe;
-        c.rev = (fl >> 16) & 1;
-        c.invert = fl & RAER_RB_INVERT;
-        pass2_accumulate_core(P, T2, c, (int)((fl >> FRF_FILE_SHIFT) & 0x3f), c.invert ? 1 : 0, ordinal, rank - X.round0, q, code,
-                              isref, rec[FR_RCP]);
-    }
-}
-
-// One chunk of up to 32 reads, handled by one warp: stage the reads that cover a flagged site of this round together
-// with their masks, prefix-sum their pair counts, lanes take pairs. r < 0: the lane has no read.
-__device__ __forceinline__ void lane_pair_chunk(const PlpParams& P, const FastSmem& S, const LaneCtx& X, const TileSmem& T2, int r,
-                                                int f, const uint32_t* maskp, int lane, uint32_t* st) {
-    uint32_t* pref = st + 32 * LREC;  // inclusive prefix of pairs per read
-    uint32_t* rec = st + lane * LREC;
-    int np = 0;
-    if (r >= 0) {
-        const int4 a = __ldg(reinterpret_cast<const int4*>(P.hdr + r));
+// ---- second pass for up to 32 reads, one per lane and called by the whole warp (r < 0: this lane has no read): every
+// flagged site of the round that the read covers, answered from the read's mask. A lane walks its CIGAR; the prefix
+// count of flagged positions gives each aligned block its range of flagged ranks in O(1) (a spliced read does not pay
+// for the sites inside its introns); the lanes then take their sites in lock step (ballot at the top of the loop, see
+// warp_reads). mk: the lane's LN_MW words in the warp's shared-memory slice.
+__device__ __forceinline__ void warp_pairs(const PlpParams& P, const FastSmem& S, const LaneCtx& X, const TileSmem& T2, int r, int f,
+                                           const uint32_t* maskp, uint32_t* mk) {
+    bool have = r >= 0;
+    int4 a = make_int4(0, 0, 0, 0), b = make_int4(0, 0, 0, 0);
+    if (have) {
+        a = __ldg(reinterpret_cast<const int4*>(P.hdr + r));
         // a read below the mapq threshold only produces nX: nothing to accumulate (src/plp.c:574)
-        if (((a.z >> 16) & 0xff) >= P.min_mapq[f]) {
-            const int4 b = __ldg(reinterpret_cast<const int4*>(P.hdr + r) + 1);
-            const int flag = a.z & 0xffff, bits = (a.z >> 24) & 0xff;
-            const int lq = a.w & 0xffff, n = (a.w >> 16) & 0xffff;
-            const uint32_t* cg = P.cigar + (unsigned)b.x;
-            const int r0 = X.round0, r1 = X.round0 + X.ns;
-            // flagged sites per aligned block from the prefix counts: the first two blocks exactly, the rest as one span
-            int qs = 0, tail = 0, nblk = 0, other = 0, rl = 0, x = a.x;
-            int fb[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
+        have = ((a.z >> 16) & 0xff) >= P.min_mapq[f];
+    }
+    const int lq = a.w & 0xffff, n = have ? (a.w >> 16) & 0xffff : 0;
+    const bool one_block = n == 1 && a.y - a.x == lq && lq > 0;
+    uint32_t top = 0;
+    ReadCtx c;
+    c.l_qseq = lq;
+    c.qs = 0;
+    c.qe = lq;
+    const uint32_t* cg = P.cigar;
+    uint32_t sq = 0;
+    if (have) {
+        b = __ldg(reinterpret_cast<const int4*>(P.hdr + r) + 1);
+        cg = P.cigar + (unsigned)b.x;
+        sq = (uint32_t)b.y;
+#pragma unroll
+        for (int i = 0; i < LN_MW; ++i) mk[i] = __ldcg(maskp + i);  // written by this kernel: not through the read-only path
+        top = mk[LN_MW - 1];
+        if (!one_block) {
+            // query_start / query_end (src/plp_utils.c:52-104): soft clips at either end, hard clips skipped
+            int qs = 0, tail = 0;
             bool lead = true;
-            const bool one_block = n == 1 && a.y - a.x == lq && lq > 0;
             for (int k = 0; k < n; ++k) {
-                const uint32_t w = one_block ? ((uint32_t)lq << 4) : __ldg(cg + k);
-                if (k < 4) rec[FR_CIG0 + k] = w;
-                const int op = cg_op(w), len = cg_len(w);
-                // query_start / query_end (src/plp_utils.c:52-104): soft clips at either end, hard clips skipped
-                if (op == OP_S) { if (lead) qs += len; tail += len; }
-                else if (op != OP_H) { lead = false; tail = 0; if (!((0x181 >> op) & 1)) other = 1; }
-                if ((0x181 >> op) & 1) {
-                    if (nblk < 3) {
-                        const int lo = min(max(x - X.t0, 0), X.tw);
-                        const int hi = min(max((nblk < 2 ? x + len : a.y) - X.t0, 0), X.tw);
-                        fb[nblk] = max((int)S.fpre[lo], r0);
-                        cb[nblk] = max(min((int)S.fpre[hi], r1) - fb[nblk], 0);
-                    }
-                    ++nblk;
-                    rl += len;
-                    x += len;
-                } else if ((0xC >> op) & 1) {
-                    x += len;
+                const uint32_t w = __ldg(cg + k);
+                const int op = cg_op(w);
+                if (op == OP_S) { if (lead) qs += cg_len(w); tail += cg_len(w); }
+                else if (op != OP_H) { lead = false; tail = 0; }
+            }
+            c.qs = qs;
+            c.qe = lq - tail;
+        }
+    }
+    const int flag = a.z & 0xffff, bits = (a.z >> 24) & 0xff;
+    c.rev = (flag >> 4) & 1;
+    c.invert = bits & RAER_RB_INVERT;
+    // get_relative_position divides by alen + 1 = qe - qs + 1 (src/plp_utils.c:401-412): reciprocal once per read
+    const int rb = c.qe - c.qs + 1;
+    const uint32_t rcp = rb > 1 ? 0xffffffffu / (uint32_t)rb + 1u : 0u;  // ceil(2^32 / rb) without a 64-bit divide
+    const int ordinal = r - (int)P.file_off[f];  // position of the read inside its file: what "first seen" means in BAM order
+    const int r0 = X.round0, r1 = X.round0 + X.ns;
+    int x = a.x, y = 0, k = 0, cur = 0, end = 0, qoff = 0;
+    while (true) {
+        while (cur >= end && k < n) {  // next aligned block with flagged sites of this round
+            const uint32_t w = one_block ? ((uint32_t)lq << 4) : __ldg(cg + k);
+            ++k;
+            const int op = cg_op(w), len = cg_len(w);
+            if ((0x181 >> op) & 1) {  // M = X
+                const int lo = min(max(x - X.t0, 0), X.tw), hi = min(max(x + min(len, lq - y) - X.t0, 0), X.tw);
+                if (lo < hi) {
+                    const int c0 = max((int)S.fpre[lo], r0), c1 = min((int)S.fpre[hi], r1);
+                    if (c0 < c1) { cur = c0; end = c1; qoff = y - x; }
                 }
-            }
-            np = cb[0] + cb[1] + cb[2];
-            if (np > 0) {
-                const int qe = lq - tail;
-                unsigned fl = (unsigned)bits | ((unsigned)((flag >> 4) & 1) << 16) | ((unsigned)f << FRF_FILE_SHIFT);
-                if (nblk == 1 && !other && qs + rl == qe) fl |= STF_SIMPLE;
-                if (n > 4) rec[FR_CIG0] = (uint32_t)b.x;
-                rec[FR_POS] = (uint32_t)a.x;
-                rec[FR_LEN] = (uint32_t)lq | ((uint32_t)n << 16);
-                rec[FR_SQ] = (uint32_t)b.y;
-                rec[FR_FLAGS] = fl;
-                rec[FR_QSQE] = (uint32_t)qs | ((uint32_t)qe << 16);
-                rec[FR_FIRST] = (uint32_t)fb[0] | ((uint32_t)fb[1] << 16);
-                rec[FR_B2] = (uint32_t)fb[2] | ((uint32_t)cb[0] << 16);
-                rec[FR_B3] = (uint32_t)cb[1];
-                // get_relative_position divides by alen + 1 = qe - qs + 1 (src/plp_utils.c:401-412): reciprocal once per read
-                const int rb = qe - qs + 1;
-                rec[FR_RCP] = rb > 1 ? 0xffffffffu / (uint32_t)rb + 1u : 0u;  // ceil(2^32 / rb) without a 64-bit divide
-#pragma unroll
-                for (int i = 0; i < LN_MW; ++i) rec[FR_MASK + i] = __ldcg(maskp + i);  // written by this kernel: not through the read-only path
+                x += len;
+                y += len;
+            } else if ((0xC >> op) & 1) {  // D N
+                x += len;
+            } else if ((0x12 >> op) & 1) {  // I S
+                y += len;
             }
         }
-    }
-    int inc = np;
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(FULL, inc, o);
-        if (lane >= o) inc += v;
-    }
-    pref[lane] = (uint32_t)inc;
-    // ordinal of the read inside its file: what "first seen" means in BAM order
-    pref[32 + lane] = (uint32_t)(r >= 0 ? r - (int)P.file_off[f] : 0);
-    const int tot = __shfl_sync(FULL, inc, 31);
-    __syncwarp();
-    for (int itb = 0; itb < tot; itb += 32) {
-        __syncwarp();
-        const int it = itb + lane;
-        int lo = 0, hh = 31;  // smallest i with pref[i] > it
-#pragma unroll
-        for (int step = 0; step < 5; ++step) {
-            const int mid = (lo + hh) >> 1;
-            if ((int)pref[mid] > it) hh = mid; else lo = mid + 1;
+        const bool act = cur < end;
+        if (!__ballot_sync(FULL, act)) break;
+        if (act) {
+            const int rank = cur++;
+            const int pidx = (int)S.flag_pidx[rank];
+            const int q = X.t0 + pidx + qoff;
+            int code = 0, isref = 1;
+            bool valid = true;
+            if (!(top & LN_NOMASK) && ((mk[q >> 5] >> (q & 31)) & 1u)) {
+                // counted in phase 1 as a base that equals the reference
+            } else if (top & (LN_NOMASK | LN_HASMM)) {
+                // the read carries a variant base somewhere in the tile (or has no mask): look at this base
+                code = seq_code(P.seq + sq, q);
+                const int bq = P.qual[2ull * sq + q];
+                const int ai = pidx + LN_PAD;
+                const int rcode = (S.refn[ai >> 3] >> ((ai & 7) << 2)) & 15;
+                // read base N (src/plp.c:718); nX or dropped bases are not part of the statistics
+                valid = code != 15 && bq >= X.minbq;
+                isref = (code == rcode) & (code != 0);
+            } else {
+                valid = false;
+            }
+            if (valid) pass2_accumulate_core(P, T2, c, f, c.invert ? 1 : 0, ordinal, rank - r0, q, code, isref, rcp);
         }
-        const int i = lo;
-        const int firstp = i ? (int)pref[i - 1] : 0;
-        const uint32_t* ri = st + i * LREC;
-        // pair j of the read -> flagged rank, through the per-block counts
-        const int j = it - firstp, c0 = (int)(ri[FR_B2] >> 16), c1 = (int)ri[FR_B3];
-        const int rank = j < c0 ? (int)(ri[FR_FIRST] & 0xffff) + j
-                                : (j < c0 + c1 ? (int)(ri[FR_FIRST] >> 16) + (j - c0) : (int)(ri[FR_B2] & 0xffff) + (j - c0 - c1));
-        lane_pair(P, S, X, T2, ri, rank, (int)pref[32 + i], it < tot);
     }
-    __syncwarp();
 }
 
 // ---- slot_stats with one warp per slot. calc_mwu_biasZ (bcftools-ext.c:144-212): every sum is an integer sum (int
 // arithmetic wraps the same way in any order), so the 100 bins are spread over 25 lanes, 4 consecutive bins each.
-__device__ __forceinline__ double warp_mwu_z(const HistView a, const HistView b, int lane) {
+struct MwuSums { int e, l, na, nb; long long t; };
+__device__ __forceinline__ double finish_mwu(const MwuSums m) {
+    const int na = m.na, nb = m.nb;
+    if (!na || !nb) return CUDART_INF;  // covers the empty-b branch of the reference as well
+    const double U = m.l + m.e * 0.5;
+    const double mm = na * nb / 2.0;
+    const double var2 = (na * nb) / 12.0 * ((na + nb + 1) - m.t / (double)((na + nb) * (na + nb - 1)));
+    if (var2 <= 0) return 0;
+    return (U - mm) / sqrt(var2);
+}
+__device__ __forceinline__ MwuSums warp_mwu_sums(const HistView a, const HistView b, int lane) {
     int av[4] = {0, 0, 0, 0}, bv[4] = {0, 0, 0, 0};
     if (lane < RAER_NHIST / 4) {
 #pragma unroll
@@ -401,21 +358,36 @@ __device__ __forceinline__ double warp_mwu_z(const HistView a, const HistView b,
     const int na = (int)__reduce_add_sync(FULL, (unsigned)(av[0] + av[1] + av[2] + av[3]));
     const int nb = (int)__reduce_add_sync(FULL, (unsigned)bsum);
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
-    if (!na || !nb) return CUDART_INF;  // covers the empty-b branch of the reference as well
-    const double U = (int)l + (int)e * 0.5;
-    const double m = na * nb / 2.0;
-    const double var2 = (na * nb) / 12.0 * ((na + nb + 1) - t / (double)((na + nb) * (na + nb - 1)));
-    if (var2 <= 0) return 0;
-    return (U - m) / sqrt(var2);
+    MwuSums m;
+    m.e = (int)e; m.l = (int)l; m.na = na; m.nb = nb; m.t = t;
+    return m;
 }
 
 // calc_vdb (bcftools-ext.c:51-111): the float accumulations depend on the order of the bins, so every lane walks the
 // non-empty bins in ascending order (found by ballots, values broadcast) and computes the same value.
-__device__ __forceinline__ double warp_vdb(const HistView pos, int lane) {
+// the part of calc_vdb behind the two histogram loops: dp reads, mean_diff already divided by dp
+__device__ __forceinline__ double finish_vdb(int dp, float mean_diff) {
     const float prm[15][3] = {{3, 0.079f, 18},    {4, 0.09f, 19.8f},  {5, 0.1f, 20.5f},   {6, 0.11f, 21.5f},
                               {7, 0.125f, 21.6f}, {8, 0.135f, 22},    {9, 0.14f, 22.2f},  {10, 0.153f, 22.3f},
                               {15, 0.19f, 22.8f}, {20, 0.22f, 23.2f}, {30, 0.26f, 23.4f}, {40, 0.29f, 23.5f},
                               {50, 0.35f, 23.65f}, {100, 0.5f, 23.7f}, {200, 0.7f, 23.7f}};
+    if (dp < 2) return CUDART_INF;
+    const int ipos = (int)mean_diff;
+    if (dp == 2) return (double)((2 * 100 - 2 * (ipos + 1) - 1) * (ipos + 1) / 99) / (100 * 0.5);
+    int i;
+    if (dp >= 200) i = 15;
+    else
+        for (i = 0; i < 15; ++i)
+            if (prm[i][0] >= (float)dp) break;
+    float pshift, pscale;
+    if (i == 15) { pscale = prm[14][1]; pshift = prm[14][2]; }
+    else if (i > 0 && prm[i][0] != (float)dp) {
+        pscale = (float)((double)(prm[i - 1][1] + prm[i][1]) * 0.5);
+        pshift = (float)((double)(prm[i - 1][2] + prm[i][2]) * 0.5);
+    } else { pscale = prm[i][1]; pshift = prm[i][2]; }
+    return 0.5 * d_kf_erfc((double)(-(mean_diff - pshift) * pscale));
+}
+__device__ __forceinline__ void warp_vdb_sums(const HistView pos, int lane, int& dp_out, float& md_out) {
     int v[4];
     unsigned nz[4];
 #pragma unroll
@@ -434,7 +406,9 @@ __device__ __forceinline__ double warp_vdb(const HistView pos, int lane) {
             dp += val;
             mean_pos += (float)(val * (src + 32 * k));
         }
-    if (dp < 2) return CUDART_INF;
+    dp_out = dp;
+    md_out = 0;
+    if (dp < 2) return;
     mean_pos /= (float)dp;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -445,38 +419,34 @@ __device__ __forceinline__ double warp_vdb(const HistView pos, int lane) {
             mean_diff = (float)((double)mean_diff + (double)val * fabs((double)((float)(src + 32 * k) - mean_pos)));
         }
     mean_diff /= (float)dp;
-    const int ipos = (int)mean_diff;
-    if (dp == 2) return (double)((2 * 100 - 2 * (ipos + 1) - 1) * (ipos + 1) / 99) / (100 * 0.5);
-    int i;
-    if (dp >= 200) i = 15;
-    else
-        for (i = 0; i < 15; ++i)
-            if (prm[i][0] >= (float)dp) break;
-    float pshift, pscale;
-    if (i == 15) { pscale = prm[14][1]; pshift = prm[14][2]; }
-    else if (i > 0 && prm[i][0] != (float)dp) {
-        pscale = (float)((double)(prm[i - 1][1] + prm[i][1]) * 0.5);
-        pshift = (float)((double)(prm[i - 1][2] + prm[i][2]) * 0.5);
-    } else { pscale = prm[i][1]; pshift = prm[i][2]; }
-    return 0.5 * d_kf_erfc((double)(-(mean_diff - pshift) * pscale));
+    md_out = mean_diff;
 }
 
-// all 32 lanes call this for the same slot; lane f takes the ALT order code of file f
-__device__ __forceinline__ void slot_stats_warp(const PlpParams& P, const uint32_t* slot, int HW, int rowp, int rowm, int growmask,
-                                                int pos, int lane) {
-    const double sor = d_calc_sor((int)slot[HW], (int)slot[HW + 1], (int)slot[HW + 2], (int)slot[HW + 3]);
+// Statistics of one slot in two steps. slot_sums_warp (all 32 lanes, one warp per slot): the integer sums of
+// calc_mwu_biasZ and the two float accumulations of calc_vdb for both strands, parked in the slot's own first words
+// (LN_SUM_WORDS per strand; the histogram of strand 1 starts at word 100, so strand 0's summary does not touch what is
+// still to be read), and the ALT order codes (lane f takes file f). slot_finish (one thread per slot and strand, all
+// slots of the round side by side): the fp64 tails -- square root, erfc, logarithms -- whose latency a warp per slot
+// would pay once per slot instead of once per round.
+#define LN_SUM_WORDS 8
+__device__ __forceinline__ void slot_sums_warp(const PlpParams& P, uint32_t* slot, int HW, int rowp, int rowm, int growmask, int pos,
+                                               int lane) {
     for (int s = 0; s < 2; ++s) {
         const long long row = s == 0 ? rowp : rowm;
         if (row < 0 && !((growmask >> s) & 1)) continue;
         if (row >= 0) {
             const HistView hr = {slot, (s * 2) * RAER_NHIST, HW != 4 * RAER_NHIST};
             const HistView ha = {slot, (s * 2 + 1) * RAER_NHIST, HW != 4 * RAER_NHIST};
-            const double z = warp_mwu_z(hr, ha, lane);
-            const double vdb = warp_vdb(ha, lane);
+            const MwuSums m = warp_mwu_sums(hr, ha, lane);
+            int dp;
+            float md;
+            warp_vdb_sums(ha, lane, dp, md);
+            __syncwarp();  // every lane has read its bins of this strand
             if (lane == 0) {
-                P.row_stats[row * 3 + 0] = z;
-                P.row_stats[row * 3 + 1] = vdb;
-                P.row_stats[row * 3 + 2] = sor;
+                uint32_t* o = slot + s * LN_SUM_WORDS;
+                o[0] = (uint32_t)m.e; o[1] = (uint32_t)m.l; o[2] = (uint32_t)m.na; o[3] = (uint32_t)m.nb;
+                o[4] = (uint32_t)(unsigned long long)m.t; o[5] = (uint32_t)((unsigned long long)m.t >> 32);
+                o[6] = (uint32_t)dp; o[7] = __float_as_uint(md);
             }
         }
         for (int f = lane; f < P.n_files; f += 32) {
@@ -515,6 +485,15 @@ __device__ __forceinline__ void slot_stats_warp(const PlpParams& P, const uint32
         }
     }
 }
+__device__ __forceinline__ void slot_finish(const PlpParams& P, const uint32_t* slot, int HW, int s, long long row) {
+    const uint32_t* o = slot + s * LN_SUM_WORDS;
+    MwuSums m;
+    m.e = (int)o[0]; m.l = (int)o[1]; m.na = (int)o[2]; m.nb = (int)o[3];
+    m.t = (long long)((unsigned long long)o[4] | ((unsigned long long)o[5] << 32));
+    P.row_stats[row * 3 + 0] = finish_mwu(m);
+    P.row_stats[row * 3 + 1] = finish_vdb((int)o[6], __uint_as_float(o[7]));
+    P.row_stats[row * 3 + 2] = d_calc_sor((int)slot[HW], (int)slot[HW + 1], (int)slot[HW + 2], (int)slot[HW + 3]);
+}
 
 // file of own-range chunk c (chunks of the files are numbered one file after the other) and its first read
 __device__ __forceinline__ int own_chunk(const int* s_first, const int* s_coff, int F, int c, int& f, int& n) {
@@ -526,7 +505,7 @@ __device__ __forceinline__ int own_chunk(const int* s_first, const int* s_coff, 
 }
 
 __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
-    extern __shared__ __align__(128) uint32_t smem[];
+    extern __shared__ __align__(16) uint32_t smem[];
     __shared__ int s_scan[40];
     __shared__ int s_first[2 * RAER_MAX_FILES], s_coff[RAER_MAX_FILES + 1];
     __shared__ int s_tile, s_nflag, s_rowbase, s_deep, s_chunk;
@@ -683,10 +662,8 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
                 qp = P.qual + 2ull * (unsigned)b.y;
                 mdst = P.pmask_cin + (size_t)li0 * LN_MW;
             }
-            if (have) {
-                if (staged) lane_read<true>(P, S, X, a, b, f, sp, qp, w_mask + lane * LN_MW);
-                else lane_read<false>(P, S, X, a, b, f, sp, qp, w_mask + lane * LN_MW);
-            }
+            if (staged) warp_reads<true>(P, S, X, have, a, b, f, sp, qp, w_mask + lane * LN_MW);
+            else warp_reads<false>(P, S, X, have, a, b, f, sp, qp, w_mask + lane * LN_MW);
             __syncwarp();
             if (X.want_mask)
                 for (int i = lane; i < n * LN_MW; i += 32) mdst[i] = w_mask[i];
@@ -841,7 +818,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
                     if (c < n_own) {
                         int f, n;
                         const int r0 = own_chunk(s_first, s_coff, F, c, f, n);
-                        lane_pair_chunk(P, S, X, T2, lane < n ? r0 + lane : -1, f, P.pmask_own + (size_t)(r0 + lane) * LN_MW, lane, st);
+                        warp_pairs(P, S, X, T2, lane < n ? r0 + lane : -1, f, P.pmask_own + (size_t)(r0 + lane) * LN_MW, st + lane * LN_MW);
                     } else {
                         const int li = l0 + ((c - n_own) << 5) + lane;
                         int f = 0, r = -1;
@@ -849,16 +826,23 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
                             while (f + 1 < F && li >= P.tile_off[tile * F + f + 1]) ++f;
                             r = __ldg(P.tile_list + li);
                         }
-                        lane_pair_chunk(P, S, X, T2, r, f, P.pmask_cin + (size_t)li * LN_MW, lane, st);
+                        warp_pairs(P, S, X, T2, r, f, P.pmask_cin + (size_t)li * LN_MW, st + lane * LN_MW);
                     }
                 }
             }
             PHASE_BARRIER(9);
             PHASE_MARK(5);  // second pass (slot clear + pairs)
-            for (int i = wid; i < ns; i += LN_WARPS) {  // one warp per slot
+            for (int i = wid; i < ns; i += LN_WARPS) {  // one warp per slot: integer sums, ALT order codes
                 const int d = S.flag_d[round0 + i], row = S.flag_row[round0 + i];
-                slot_stats_warp(P, slot0 + (size_t)i * SW, HW, ((d & 1) && (d & 4)) ? row : -1,
-                                ((d & 2) && (d & 8)) ? row + (d & 1) : -1, d >> 4, t0 + (int)S.flag_pidx[round0 + i], lane);
+                slot_sums_warp(P, slot0 + (size_t)i * SW, HW, ((d & 1) && (d & 4)) ? row : -1,
+                               ((d & 2) && (d & 8)) ? row + (d & 1) : -1, d >> 4, t0 + (int)S.flag_pidx[round0 + i], lane);
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < 2 * ns; i += blockDim.x) {  // one thread per slot and strand: the fp64 tails
+                const int sl = i >> 1, s2 = i & 1;
+                const int d = S.flag_d[round0 + sl], row = S.flag_row[round0 + sl];
+                const long long rw = s2 == 0 ? (((d & 1) && (d & 4)) ? row : -1) : (((d & 2) && (d & 8)) ? row + (d & 1) : -1);
+                if (rw >= 0) slot_finish(P, slot0 + (size_t)sl * SW, HW, s2, rw);
             }
             __syncthreads();
             PHASE_MARK(6);  // statistics

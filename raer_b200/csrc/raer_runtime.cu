@@ -974,6 +974,10 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
                         if (stop) break;
                     }
                 }
+                if (my_rc == RAER_OK && wi.failed()) {  // a stream stopped on an error: not the end of the contig
+                    my_rc = RAER_ERR_IO;
+                    set_error("%s", wi.error().c_str());
+                }
                 std::lock_guard<std::mutex> lk(mu);
                 w_decode += wi.decode_seconds(); w_pack += wi.pack_seconds();
                 w_records += wi.records(); w_bases += wi.aligned_bases();
@@ -1089,6 +1093,12 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
                 emit_rows(tid, rows);
             }
         }
+        // a stream that stopped on a read / inflate / checksum / record / sort-order error looks like the end of the input
+        // to the loops above: the rows so far are not the result of the call (src/plp.c:1195 raises an error)
+        if (rc == RAER_OK && ing.failed()) {
+            set_error("%s", ing.error().c_str());
+            rc = RAER_ERR_IO;
+        }
         out->t_decode = ing.decode_seconds();
         out->t_pack = ing.pack_seconds();
         out->n_records = ing.records();
@@ -1173,6 +1183,7 @@ extern "C" int raer_ingest_summary(const raer_pileup_args* a, int64_t target_rea
     }
     out[5] = ing.aligned_bases();
     out[6] = ing.records();
+    if (ing.failed()) { set_error("%s", ing.error().c_str()); return RAER_ERR_IO; }
     if (getenv("RAER_TIMING"))
         fprintf(stderr, "[raer ingest] parse sections %.3f s (of which the parsers waited %.3f s, summed over files, for inflate), "
                         "pack sections %.3f s, inflate tasks %.3f s summed over files\n",

@@ -511,6 +511,10 @@ static int sc_run(const raer_scpileup_args* a, bool want_files, raer_sc_triplets
                 }
             }
         }
+        if (rc == RAER_OK && ing.failed()) {  // the stream stopped on an error, not at the end of the file
+            set_error("%s", ing.error().c_str());
+            rc = RAER_ERR_IO;
+        }
     }
     cudaStreamDestroy(st);
     close_all();
