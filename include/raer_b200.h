@@ -284,6 +284,51 @@ int64_t raer_batch_algorithmic_bytes(const raer_read_batch* b, int64_t n_rows, i
  * (file, strand) variant table (4 or 8 buckets, src/plp.c:193-215). out needs 12 bytes. */
 void raer_altcode_to_string(uint32_t altcode, int ref_char, int32_t* khash_buckets, char* out);
 
+/* ------------------------------------------------------------------ layer 2, single cell (pileup_cells)
+ * The batch layer under raer_scpileup(): a read batch with the cb / umi arrays filled plus the sites of its contig go
+ * to the device kernels that replace process_one_site / count_record / count_consensus_base / write_counts
+ * (src/sc-plp.c:528-597, 235-309, 321-348, 410-437); what comes back are the nonzero (site, barcode) cells. */
+typedef struct raer_sc_conf {
+    int32_t min_bq, min_mapq;
+    int32_t trim_5p, trim_3p, indel_dist, splice_dist, min_overhang;
+    int32_t remove_overlaps;    /* 0 none, 1 htslib >= 1.13, 2 htslib <= 1.12 */
+    int32_t has_umi;            /* 1: consensus per (site, barcode, UMI) on summed base qualities (src/sc-plp.c:321-348) */
+    int32_t n_barcodes;         /* whitelist size: raer_read_batch.cb holds 1 .. n_barcodes (0 = not on the list) */
+    uint32_t n_umi;             /* raer_read_batch.umi holds 1 .. n_umi (0 = read without the tag) */
+    int32_t n_sites;            /* sites of the batch's contig, sorted by position; payloads may share a position */
+    double ftrim_5p, ftrim_3p;
+    const int32_t* site_pos;    /* 0-based; same memory space as the batch */
+    const uint8_t* site_strand; /* 1 '+', 2 '-' */
+    const uint8_t* site_ref;    /* first character of REF */
+    const uint8_t* site_alt;    /* first character of ALT */
+} raer_sc_conf;
+
+/* nonzero cells of one batch in host memory, sorted by (site, barcode) */
+typedef struct raer_sc_cells {
+    int64_t n;
+    int32_t* cells;             /* [n][4]: index into the site list, 1-based barcode column, nRef, nAlt */
+    int64_t n_sites;
+    int32_t* site_totals;       /* [n_sites][2]: nRef, nAlt summed over the cells of a site (the min_counts rule, src/sc-plp.c:586-588) */
+} raer_sc_cells;
+void raer_sc_cells_free(raer_sc_cells* c);
+
+typedef struct raer_sc_ctx raer_sc_ctx; /* one per device: stream and scratch buffers of the single-cell kernels */
+raer_sc_ctx* raer_sc_ctx_create(int32_t device);
+void raer_sc_ctx_destroy(raer_sc_ctx* ctx);
+void* raer_sc_ctx_stream(raer_sc_ctx* ctx);
+/* device-resident path: every pointer of dev_batch (except file_off) and of conf is device memory; the cells stay on
+ * the device. *n_cells and *n_tuples (emitted (site, barcode, UMI) observations) are read back unless NULL. */
+int raer_sc_batch_device(raer_sc_ctx* ctx, const raer_sc_conf* conf, const raer_read_batch* dev_batch, int64_t* n_cells,
+                         int64_t* n_tuples, int64_t* launches);
+/* host path: H2D of the batch and the sites, kernels, D2H of the cells */
+int raer_sc_batch_host(raer_sc_ctx* ctx, const raer_sc_conf* conf, const raer_read_batch* host_batch, raer_sc_cells* out);
+/* per-kernel-class CUDA-event timing since raer_sc_ctx_profile(ctx, 1): ms[0..3] / n[0..3] = tuple emission, radix
+ * sort (all passes), consensus + cell reduction, mate overlap */
+void raer_sc_ctx_profile(raer_sc_ctx* ctx, int on);
+int raer_sc_ctx_profile_read(raer_sc_ctx* ctx, double* ms, int64_t* n);
+/* algorithmic bytes of a single-cell batch (2.04 B per aligned base model + 16 B per output cell) */
+int64_t raer_sc_algorithmic_bytes(const raer_read_batch* b, int64_t n_cells);
+
 /* Host-only probe of the ingest used by raer_pileup() (no device needed): streams the BAMs, applies
  * the read-level prefilter, packs batches of about target_reads reads and reports
  * out[0..7] = reads handed to the device (halo reads once per batch), mate pairs, CIGAR words,

@@ -151,6 +151,22 @@ class BulkConf(C.Structure):
     ]
 
 
+class ScConf(C.Structure):
+    _fields_ = [
+        ("min_bq", C.c_int32), ("min_mapq", C.c_int32), ("trim_5p", C.c_int32), ("trim_3p", C.c_int32),
+        ("indel_dist", C.c_int32), ("splice_dist", C.c_int32), ("min_overhang", C.c_int32),
+        ("remove_overlaps", C.c_int32), ("has_umi", C.c_int32), ("n_barcodes", C.c_int32), ("n_umi", C.c_uint32),
+        ("n_sites", C.c_int32),
+        ("ftrim_5p", C.c_double), ("ftrim_3p", C.c_double),
+        ("site_pos", C.c_void_p), ("site_strand", C.c_void_p), ("site_ref", C.c_void_p), ("site_alt", C.c_void_p),
+    ]
+
+
+class ScCells(C.Structure):
+    _fields_ = [("n", C.c_int64), ("cells", C.POINTER(C.c_int32)), ("n_sites", C.c_int64),
+                ("site_totals", C.POINTER(C.c_int32))]
+
+
 class Rows(C.Structure):
     _fields_ = [
         ("n_rows", C.c_int64), ("n_files", C.c_int32),
@@ -210,6 +226,25 @@ def lib() -> C.CDLL:
         L.raer_ctx_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.raer_ctx_profile_read.restype = C.c_int
         L.raer_altcode_to_string.argtypes = [C.c_uint32, C.c_int, C.POINTER(C.c_int32), C.c_char_p]
+        L.raer_sc_ctx_create.argtypes = [C.c_int32]
+        L.raer_sc_ctx_create.restype = C.c_void_p
+        L.raer_sc_ctx_destroy.argtypes = [C.c_void_p]
+        L.raer_sc_ctx_destroy.restype = None
+        L.raer_sc_ctx_stream.argtypes = [C.c_void_p]
+        L.raer_sc_ctx_stream.restype = C.c_void_p
+        L.raer_sc_batch_device.argtypes = [C.c_void_p, C.POINTER(ScConf), C.POINTER(ReadBatch), C.POINTER(C.c_int64),
+                                           C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.raer_sc_batch_device.restype = C.c_int
+        L.raer_sc_batch_host.argtypes = [C.c_void_p, C.POINTER(ScConf), C.POINTER(ReadBatch), C.POINTER(ScCells)]
+        L.raer_sc_batch_host.restype = C.c_int
+        L.raer_sc_cells_free.argtypes = [C.POINTER(ScCells)]
+        L.raer_sc_cells_free.restype = None
+        L.raer_sc_ctx_profile.argtypes = [C.c_void_p, C.c_int]
+        L.raer_sc_ctx_profile.restype = None
+        L.raer_sc_ctx_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        L.raer_sc_ctx_profile_read.restype = C.c_int
+        L.raer_sc_algorithmic_bytes.argtypes = [C.POINTER(ReadBatch), C.c_int64]
+        L.raer_sc_algorithmic_bytes.restype = C.c_int64
         L.raer_ctx_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                            C.POINTER(C.c_double)]
         _LIB = L

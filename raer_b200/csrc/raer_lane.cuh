@@ -31,7 +31,8 @@
 #define LN_NOMASK 0x80000000u        //                 the read is longer than the mask: the second pass looks at its bases
 #define LN_MASK_BYTES (32 * LN_MW * 4)
 #define LN_REC2_WORDS (32 * LN_MW + 32)  // second pass, per warp: the masks of its 32 reads
-#define LN_PAD 16                    // reference bases packed in front of the tile
+#define LN_DEFER 768                 // reads with several aligned blocks a tile can set aside for dense chunks of their own
+#define LN_PAD 32                    // reference bases packed in front of the tile
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -71,72 +72,88 @@ struct LaneCtx {
     int round0, ns;
 };
 
-// One chunk of 16 query bases of one aligned block. Bases j in [jlo, jhi) are part of the block and sit on tile
-// positions rel0 + j. rw0 / rw1: the bases, nibble j of rw0 = base j, of rw1 = base 8 + j; qa / qb: their qualities.
+// bits 8j + 7 of `hi` and of `lo` (j = 0..3) -> bits 4 + j and j: one multiply gathers both words
+__device__ __forceinline__ uint32_t msb8_to_c8(uint32_t lo, uint32_t hi) { return ((hi | (lo >> 4)) * 0x00204081u) >> 24; }
+
+// One step of 32 query bases of one aligned block. Bases j in [jlo, jhi) are part of the block and sit on tile
+// positions rel0 + j. sw[i]: packed bases 8i .. 8i + 7 as they lie in the BAM record; qw[i]: their qualities.
 // Returns the mask of the bases that were counted as reference matches.
-__device__ __forceinline__ uint32_t lane_chunk(const FastSmem& S, const LaneCtx& X, unsigned cbs, uint32_t rw0, uint32_t rw1,
-                                               uint2 qa, uint2 qb, int rel0, int jlo, int jhi, bool mapq_fail, int cxor,
-                                               uint32_t& hasmm) {
-    const uint32_t V = (0xffffu >> (16 - jhi)) & (0xffffu << jlo);
-    const int a = rel0 + LN_PAD;  // >= 1: index of the chunk's first base in the packed reference
+__device__ __forceinline__ uint32_t lane_step(const FastSmem& S, const LaneCtx& X, unsigned cbs, const uint32_t (&sw)[4],
+                                              const uint2 (&qw)[4], const uint8_t* sb, int rel0, int jlo, int jhi, bool mapq_fail,
+                                              int cxor, uint32_t& hasmm) {
+    // sb: the packed bases of the step once more, as bytes: the rare per-base lookups read them from there instead of
+    // indexing the register copies with a run-time index
+    const uint32_t V = (0xffffffffu >> (32 - jhi)) & (0xffffffffu << jlo);
+    const int a = rel0 + LN_PAD;  // >= 1: index of the step's first base in the packed reference
     const int wi = a >> 3, sh = (a & 7) << 2;
-    const uint32_t r0 = S.refn[wi], r1 = S.refn[wi + 1], r2 = S.refn[wi + 2];
-    const uint32_t x0 = rw0 ^ __funnelshift_r(r0, r1, sh), x1 = rw1 ^ __funnelshift_r(r1, r2, sh);
-    const uint32_t E = (nibbits_to_c8(nib_nonzero(x0)) | (nibbits_to_c8(nib_nonzero(x1)) << 8)) & V;  // differs from the reference
-    uint32_t LTc = 0, D0 = 0;
+    uint32_t rf[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) rf[i] = S.refn[wi + i];
+    uint32_t E = 0, LTc = 0, D = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        E |= nibbits_to_c8(nib_nonzero(nib_swap(sw[i]) ^ __funnelshift_r(rf[i], rf[i + 1], sh))) << (8 * i);
+    E &= V;  // differs from the reference (read base N among them: the reference is never N where a row is written)
     if (!mapq_fail) {
-        LTc = msb4_to_c4(byte_lt(qa.x, X.mb4)) | (msb4_to_c4(byte_lt(qa.y, X.mb4)) << 4) | (msb4_to_c4(byte_lt(qb.x, X.mb4)) << 8) |
-              (msb4_to_c4(byte_lt(qb.y, X.mb4)) << 12);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) LTc |= msb8_to_c8(byte_lt(qw[i].x, X.mb4), byte_lt(qw[i].y, X.mb4)) << (8 * i);
         // quality 0 below the threshold is dropped silently (src/plp.c:580-586)
-        if (X.zall)
-            D0 = (msb4_to_c4(byte_zero(qa.x)) | (msb4_to_c4(byte_zero(qa.y)) << 4) | (msb4_to_c4(byte_zero(qb.x)) << 8) |
-                  (msb4_to_c4(byte_zero(qb.y)) << 12)) & V;
-    }
-    const unsigned base = cbs + ((unsigned)rel0 << 2);  // shared address of the coverage word of base 0
-    uint32_t D = D0;
-    // bases that differ from the reference: N is counted nowhere (src/plp.c:718); one that passes the filters is a
-    // variant base; the others are handled as nX / dropped below
-    for (uint32_t e = E; e;) {
-        const int j = __ffs(e) - 1;
-        e &= e - 1;
-        const int code = ((j < 8 ? rw0 : rw1) >> ((j & 7) << 2)) & 15;
-        if (code == 15) {
-            D |= 1u << j;
-        } else if (!mapq_fail && !(((LTc | D0) >> j) & 1u)) {
-            // A=1 C=2 G=4 T=8 -> 0..3; complement on the minus strand = xor 3; any other code -> other
-            int cls = ((code >> 1) - (code >> 3)) ^ cxor;
-            if (__popc(code) != 1) cls = RAER_CLS_OTHER;
-            red_add_s(base + (unsigned)((1 + (cls >> 1)) * S.WS) * 4 + (j << 2), 1u << ((cls & 1) << 4));
-            hasmm = 1;
+        if (X.zall) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) D |= msb8_to_c8(byte_zero(qw[i].x), byte_zero(qw[i].y)) << (8 * i);
+            D &= V;
         }
     }
+    const unsigned base = cbs + ((unsigned)rel0 << 2);  // shared address of the coverage word of base 0
+    // a base that differs from the reference and passes the filters is a variant base (rare); read base N is counted
+    // nowhere (src/plp.c:718): it leaves the coverage like a dropped base
+    for (uint32_t e = mapq_fail ? 0u : (E & ~(LTc | D)); e;) {
+        const int j = __ffs(e) - 1;
+        e &= e - 1;
+        const int code = (sb[j >> 1] >> ((~j & 1) << 2)) & 15;
+        if (code == 15) {
+            red_add_s(base + (j << 2), 0xffffffffu);
+            red_add_s(base + (j << 2) + 4, 1u);
+            continue;
+        }
+        // A=1 C=2 G=4 T=8 -> 0..3; complement on the minus strand = xor 3; any other code -> other
+        int cls = ((code >> 1) - (code >> 3)) ^ cxor;
+        if (__popc(code) != 1) cls = RAER_CLS_OTHER;
+        red_add_s(base + (unsigned)((1 + (cls >> 1)) * S.WS) * 4 + (j << 2), 1u << ((cls & 1) << 4));
+        hasmm = 1;
+    }
     // every base of a read below the mapq threshold is nX (src/plp.c:574)
-    uint32_t XM = (mapq_fail ? V : LTc & V) & ~D;
-    // runs of dropped bases leave the coverage: -1 where a run starts, +1 after its end
-    uint32_t rs = D & ~(D << 1), re = D & ~(D >> 1);
-    while (rs) {
-        const int b1 = __ffs(rs) - 1, b2 = __ffs(re) - 1;
-        rs &= rs - 1;
-        re &= re - 1;
-        red_add_s(base + (b1 << 2), 0xffffffffu);
-        red_add_s(base + (b2 << 2) + 4, 1u);
-    }
+    const uint32_t XM = (mapq_fail ? V : LTc & V) & ~D;
     const unsigned xb = base + (unsigned)(3 * S.WS) * 4;
-    const uint32_t CM = mapq_fail ? 0u : (V & ~(LTc | D | E));
-    while (XM) {
-        const int b = __ffs(XM) - 1;
-        XM &= XM - 1;
-        red_add_s(xb + (b << 2), 0x10000u);
+    // One loop for both kinds of events (their bits are disjoint): nX bases, and the starts of the runs of dropped
+    // bases, which leave the coverage with -1 where the run starts and +1 behind its end
+    for (uint32_t u = XM | (D & ~(D << 1)); u;) {
+        const int b1 = __ffs(u) - 1;
+        u &= u - 1;
+        if ((XM >> b1) & 1u) {
+            // an nX base that differs from the reference may be an N: dropped, whatever its quality
+            if (((E >> b1) & 1u) && ((sb[b1 >> 1] >> ((~b1 & 1) << 2)) & 15) == 15) {
+                red_add_s(base + (b1 << 2), 0xffffffffu);
+                red_add_s(base + (b1 << 2) + 4, 1u);
+            } else {
+                red_add_s(xb + (b1 << 2), 0x10000u);
+            }
+        } else {
+            const uint32_t above = ~(D >> b1);  // first zero above the start = length of the run; none: all 32 bases dropped
+            const int run = above ? __ffs(above) - 1 : 32;
+            red_add_s(base + (b1 << 2), 0xffffffffu);
+            red_add_s(base + ((b1 + run) << 2), 1u);
+        }
     }
-    return CM;
+    return mapq_fail ? 0u : (V & ~(LTc | D | E));
 }
 
 // Phase 1 for up to 32 reads, one per lane, called by the whole warp (have: this lane has a read): coverage events and
-// chunks of every aligned block that reaches into the tile. The lanes walk their CIGARs on their own, but they take
-// their chunks in lock step -- the ballot at the top of the loop re-joins the warp before every chunk, so the long
-// straight-line chunk code runs with all lanes that still have work (without it lanes that once diverged would keep
-// running as separate sub-warps). sp / qp: the read's packed sequence / qualities (shared memory when STAGED, else
-// global); mk: LN_MW mask words.
+// steps of 32 query bases of every aligned block that reaches into the tile. The lanes walk their CIGARs on their own,
+// but they take their steps in lock step -- the ballot at the top of the loop re-joins the warp before every step, so
+// the long straight-line step code runs with all lanes that still have work (without it lanes that once diverged would
+// keep running as separate sub-warps). sp / qp: the read's packed sequence / qualities (shared memory when STAGED,
+// else global); mk: LN_MW mask words.
 template <bool STAGED>
 __device__ __forceinline__ void warp_reads(const PlpParams& P, const FastSmem& S, const LaneCtx& X, bool have, const int4 a, const int4 b,
                                            int f, const uint8_t* sp, const uint8_t* qp, uint32_t* mk) {
@@ -156,7 +173,7 @@ __device__ __forceinline__ void warp_reads(const PlpParams& P, const FastSmem& S
         for (int i = 0; i < LN_MW; ++i) mk[i] = 0;
     }
     int x = a.x, y = 0, k = 0;
-    int q0 = 0, qa = 0, qb = 0, rel_a = 0;  // current aligned block inside the tile: query bases [qa, qb), next chunk at q0
+    int q0 = 0, qa = 0, qb = 0, rel_a = 0;  // current aligned block inside the tile: query bases [qa, qb), next step at q0
     while (true) {
         while (q0 >= qb && k < n) {  // next aligned block that reaches into the tile
             const uint32_t w = one_block ? ((uint32_t)lq << 4) : __ldg(cg + k);
@@ -174,7 +191,7 @@ __device__ __forceinline__ void warp_reads(const PlpParams& P, const FastSmem& S
                     qa = y + (lo - x);  // query bases [qa, qb) sit on tile positions rel_a ...
                     qb = y + (hi - x);
                     rel_a = lo - X.t0;
-                    q0 = qa & ~15;
+                    q0 = qa & ~31;
                 }
                 x += len;
                 y += len;
@@ -187,28 +204,27 @@ __device__ __forceinline__ void warp_reads(const PlpParams& P, const FastSmem& S
         const bool act = q0 < qb;
         if (!__ballot_sync(FULL, act)) break;
         if (act) {
-            const bool two = q0 + 8 < lq;
-            uint32_t s0, s1 = 0xffffffffu;
-            uint2 u0, u1 = make_uint2(0, 0);
+            uint32_t sw[4];
+            uint2 qw[4];
             if (STAGED) {
-                s0 = *reinterpret_cast<const uint32_t*>(sp + (q0 >> 1));
-                u0 = *reinterpret_cast<const uint2*>(qp + q0);
-                if (two) {
-                    s1 = *reinterpret_cast<const uint32_t*>(sp + (q0 >> 1) + 4);
-                    u1 = *reinterpret_cast<const uint2*>(qp + q0 + 8);
+                // the staged spans end with 32 readable bytes of slack: no guard for the words behind the read's last base
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    sw[i] = *reinterpret_cast<const uint32_t*>(sp + (q0 >> 1) + 4 * i);
+                    qw[i] = *reinterpret_cast<const uint2*>(qp + q0 + 8 * i);
                 }
             } else {
-                s0 = __ldg(reinterpret_cast<const uint32_t*>(sp + (q0 >> 1)));
-                u0 = __ldg(reinterpret_cast<const uint2*>(qp + q0));
-                if (two) {
-                    s1 = __ldg(reinterpret_cast<const uint32_t*>(sp + (q0 >> 1) + 4));
-                    u1 = __ldg(reinterpret_cast<const uint2*>(qp + q0 + 8));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool in = q0 + 8 * i < lq;
+                    sw[i] = in ? __ldg(reinterpret_cast<const uint32_t*>(sp + (q0 >> 1) + 4 * i)) : 0xffffffffu;
+                    qw[i] = in ? __ldg(reinterpret_cast<const uint2*>(qp + q0 + 8 * i)) : make_uint2(0, 0);
                 }
             }
-            const uint32_t cm = lane_chunk(S, X, cbs, nib_swap(s0), nib_swap(s1), u0, u1, rel_a + (q0 - qa), max(qa - q0, 0),
-                                           min(qb - q0, 16), mapq_fail, s ? 3 : 0, hasmm);
-            if (masked) mk[q0 >> 5] |= cm << (q0 & 16);
-            q0 += 16;
+            const uint32_t cm = lane_step(S, X, cbs, sw, qw, sp + (q0 >> 1), rel_a + (q0 - qa), max(qa - q0, 0), min(qb - q0, 32),
+                                          mapq_fail, s ? 3 : 0, hasmm);
+            if (masked && cm) atomicOr(&mk[q0 >> 5], cm);  // a word can be visited from two aligned blocks
+            q0 += 32;
         }
     }
     if (X.want_mask && have) {
@@ -508,7 +524,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ int s_scan[40];
     __shared__ int s_first[2 * RAER_MAX_FILES], s_coff[RAER_MAX_FILES + 1];
-    __shared__ int s_tile, s_nflag, s_rowbase, s_deep, s_chunk;
+    __shared__ int s_tile, s_nflag, s_rowbase, s_deep, s_chunk, s_ndefer, s_own_seen;
     const int W = P.W, F = P.n_files;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     FastSmem S;
@@ -520,13 +536,15 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
     S.stage = smem;
     S.cnt = smem + LN_WARPS * stage_words;
     S.refn = S.cnt + cnt_words;
-    S.covered = S.refn + (FWMAX >> 3) + 8;
+    S.covered = S.refn + (FWMAX >> 3) + 12;
     S.flag_row = (int*)(S.covered + (FWMAX >> 5) + 4);
     S.fpre = (uint16_t*)(S.flag_row + FWMAX);
     S.flag_pidx = S.fpre + FWMAX + 8;
     S.flag_d = (uint8_t*)(S.flag_pidx + FWMAX);
     S.dec = S.flag_d + FWMAX;
     uint64_t* mbars = (uint64_t*)(S.dec + FWMAX);
+    int* const s_defer = (int*)(mbars + LN_WARPS);
+    uint8_t* const s_defer_f = (uint8_t*)(s_defer + LN_DEFER);
     const CntPacked CN = {S.cnt, S.WS};
     uint32_t* const slot0 = smem + LN_WARPS * LN_REC2_WORDS;
     const int slot_region_words = LN_WARPS * (stage_words - LN_REC2_WORDS) + cnt_words;
@@ -571,7 +589,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
             for (int i = threadIdx.x; i < (cnt_words >> 2); i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
         }
         for (int i = threadIdx.x; i < (W >> 5) + 1; i += blockDim.x) S.covered[i] = 0;
-        for (int i = threadIdx.x; i < (W >> 3) + 5; i += blockDim.x) {
+        for (int i = threadIdx.x; i < (W >> 3) + 9; i += blockDim.x) {
             uint32_t w = 0;
             const int p0 = t0 - LN_PAD + 8 * i;
 #pragma unroll
@@ -585,7 +603,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
             s_first[2 * f] = r0;
             s_first[2 * f + 1] = r1;
         }
-        if (threadIdx.x == 0) { s_nflag = 0; s_deep = 0; s_chunk = 0; }
+        if (threadIdx.x == 0) { s_nflag = 0; s_deep = 0; s_chunk = 0; s_ndefer = 0; s_own_seen = 0; }
         __syncthreads();
         if (threadIdx.x == 0) {
             int c = 0;
@@ -605,17 +623,21 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
         const int n_own = s_coff[F];
         const int n_cin = (l1 - l0 + 31) >> 5;
 
-        // ---- phase 1: coverage events + exceptional bases, one lane per read
+        // ---- phase 1: coverage events + exceptional bases, one lane per read. Chunk ids: the tile's own reads, the
+        // carry-in lists, then the reads set aside by the own chunks. A warp's steps last as long as its slowest lane:
+        // reads with several aligned blocks (spliced, indels: n_cigar >= 3) would hold up the single-block reads they sit
+        // between, so an own chunk puts them on a list and they are walked together, 32 of a kind, at the end.
         while (true) {
             int c = 0;
             if (lane == 0) c = atomicAdd(&s_chunk, 1);
             c = __shfl_sync(FULL, c, 0);
-            if (c >= n_own + n_cin) break;
             bool have, staged = false;
             int4 a = make_int4(0, 0, 0, 0), b = make_int4(0, 0, 0, 0);
             int f = 0, n;
+            unsigned dmask = 0;  // own chunk: lanes whose read was set aside
             const uint8_t *sp, *qp;
             uint32_t* mdst;
+            bool scattered = false;  // masks go to their reads one by one
             if (c < n_own) {
                 const int r0 = own_chunk(s_first, s_coff, F, c, f, n);
                 have = lane < n;
@@ -623,6 +645,23 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
                     a = __ldg(reinterpret_cast<const int4*>(P.hdr + r0 + lane));
                     b = __ldg(reinterpret_cast<const int4*>(P.hdr + r0 + lane) + 1);
                 }
+                const bool dfr = have && ((a.w >> 16) & 0xffff) >= 3;
+                dmask = __ballot_sync(FULL, dfr);
+                if (dmask) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_ndefer, __popc(dmask));
+                    base = __shfl_sync(FULL, base, 0);
+                    const int slot = base + __popc(dmask & ((1u << lane) - 1u));
+                    if (dfr && slot < LN_DEFER) {
+                        s_defer[slot] = r0 + lane;
+                        s_defer_f[slot] = (uint8_t)f;
+                        have = false;
+                    }
+                    dmask = __ballot_sync(FULL, dfr && !have);  // a full list leaves the read with this chunk
+                    __threadfence_block();
+                }
+                __syncwarp();
+                if (lane == 0) atomicAdd(&s_own_seen, 1);
                 // the chunk's packed sequences are one span of the batch's sequence array (every read starts on a
                 // 4-byte boundary and occupies a multiple of 4 bytes; qualities live at twice the offsets)
                 const unsigned sq = (unsigned)b.y;
@@ -630,7 +669,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
                 const unsigned lo = __reduce_min_sync(FULL, have ? sq : 0xffffffffu) & ~15u;
                 const unsigned hi = __reduce_max_sync(FULL, have ? sqe : 0u);
                 const unsigned len = (hi - lo + 15) & ~15u;
-                staged = can_stage && hi > lo && len <= (unsigned)SB;
+                staged = can_stage && hi > lo && len + 32 <= (unsigned)SB;  // 32 bytes of slack behind the span (see warp_reads)
                 if (staged) {
                     if (lane == 0) {
                         fence_async_smem();
@@ -647,7 +686,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
                     qp = P.qual + 2ull * sq;
                 }
                 mdst = P.pmask_own + (size_t)r0 * LN_MW;
-            } else {
+            } else if (c < n_own + n_cin) {
                 const int li0 = l0 + ((c - n_own) << 5);
                 const int li = li0 + lane;
                 n = min(32, l1 - li0);
@@ -661,12 +700,41 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
                 sp = P.seq + (unsigned)b.y;
                 qp = P.qual + 2ull * (unsigned)b.y;
                 mdst = P.pmask_cin + (size_t)li0 * LN_MW;
+            } else {
+                // the list is complete once every own chunk has been through its hand-over (which comes first thing in a
+                // chunk: nobody waits here for long)
+                if (lane == 0)
+                    while (*(volatile int*)&s_own_seen < n_own) {}
+                __syncwarp();
+                const int nd = min(*(volatile int*)&s_ndefer, LN_DEFER);
+                const int i0 = (c - n_own - n_cin) << 5;
+                if (i0 >= nd) break;
+                n = min(32, nd - i0);
+                have = lane < n;
+                int r = 0;
+                if (have) {
+                    r = s_defer[i0 + lane];
+                    f = s_defer_f[i0 + lane];
+                    a = __ldg(reinterpret_cast<const int4*>(P.hdr + r));
+                    b = __ldg(reinterpret_cast<const int4*>(P.hdr + r) + 1);
+                }
+                sp = P.seq + (unsigned)b.y;
+                qp = P.qual + 2ull * (unsigned)b.y;
+                mdst = P.pmask_own + (size_t)r * LN_MW;
+                scattered = true;
             }
             if (staged) warp_reads<true>(P, S, X, have, a, b, f, sp, qp, w_mask + lane * LN_MW);
             else warp_reads<false>(P, S, X, have, a, b, f, sp, qp, w_mask + lane * LN_MW);
             __syncwarp();
-            if (X.want_mask)
-                for (int i = lane; i < n * LN_MW; i += 32) mdst[i] = w_mask[i];
+            if (X.want_mask) {
+                if (scattered) {
+                    if (have)
+                        for (int i = 0; i < LN_MW; ++i) mdst[i] = w_mask[lane * LN_MW + i];
+                } else {
+                    for (int i = lane; i < n * LN_MW; i += 32)
+                        if (!((dmask >> (i / LN_MW)) & 1u)) mdst[i] = w_mask[i];
+                }
+            }
             __syncwarp();
         }
         PHASE_BARRIER(8);
@@ -700,12 +768,16 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
         if (s_deep && threadIdx.x == 0) atomicCAS(P.err_flag, 0, RAER_RETRY_DEEP);  // 16-bit class counters cannot hold this tile
 
         // ---- phase 2: decide, reserve rows, write them in (pos, strand) order
-        int my_rows = 0;
-        for (int pidx = threadIdx.x; pidx < W; pidx += blockDim.x) {
+        // every thread takes a run of consecutive positions, so one block scan places rows and flagged sites in position order
+        const int KP = (W + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int p_lo = min((int)threadIdx.x * KP, W), p_hi = min(p_lo + KP, W);
+        int my_rows = 0;  // rows in the low half, flagged sites in the high half (a tile has < 2^15 of either)
+        for (int pidx = p_lo; pidx < p_hi; ++pidx) {
             int d = 0;
             if (t0 + pidx < t1) d = decide_site(P, CN, S.covered, pidx, t0 + pidx);
             S.dec[pidx] = (uint8_t)d;
-            my_rows += (d & 1) + ((d >> 1) & 1) + ((d & 48) ? 0x10000 : 0);
+            const bool fl = P.want_stats && (((d & 1) && (d & 4)) || ((d & 2) && (d & 8)) || (d & 48));
+            my_rows += (d & 1) + ((d >> 1) & 1) + (fl ? 0x10000 : 0);
         }
         if (P.aei_mode) {
             // calc_AEI (reference R/calc_AEI.R:274-323): per file the 4 x 4 (REF of the row, counted base) sums of the rows
@@ -746,11 +818,9 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
             __syncthreads();
             continue;
         }
-        // rows in the low half; sites that only need the second pass for the khash state in the high half
         int tile_tot;
-        block_exclusive_scan(my_rows, &tile_tot, s_scan);
-        const int tile_rows_total = tile_tot & 0xffff;
-        const bool tile_grow = (tile_tot >> 16) != 0;
+        const int my_ex = block_exclusive_scan(my_rows, &tile_tot, s_scan);
+        const int tile_rows_total = tile_tot & 0xffff, tile_flagged = tile_tot >> 16;
         if (threadIdx.x == 0) {
             long long base = (long long)atomicAdd(P.row_counter, (unsigned long long)tile_rows_total);
             if (base + tile_rows_total > P.row_cap) { atomicExch(P.err_flag, RAER_ERR_LIMIT); base = -1; }
@@ -759,21 +829,13 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
         }
         __syncthreads();
         const long long rowbase = s_rowbase;
-        if (rowbase >= 0 && (tile_rows_total > 0 || tile_grow)) {
-            int carried = 0, fcarried = 0;
-            for (int chunk = 0; chunk < W; chunk += blockDim.x) {
-                const int pidx = chunk + threadIdx.x;
-                const int d = pidx < W ? S.dec[pidx] : 0;
+        if (rowbase >= 0 && (tile_rows_total > 0 || tile_flagged > 0)) {
+            int off = my_ex & 0xffff, rank = my_ex >> 16;  // position-sorted
+            for (int pidx = p_lo; pidx < p_hi; ++pidx) {
+                const int d = S.dec[pidx];
                 const int n = (d & 1) + ((d >> 1) & 1);
                 const bool fl = P.want_stats && (((d & 1) && (d & 4)) || ((d & 2) && (d & 8)) || (d & 48));
-                // one scan for both: rows in the low half, flagged sites in the high half (a tile has < 2^15 of either)
-                int ptot;
-                const int pex = block_exclusive_scan(n | ((fl ? 1 : 0) << 16), &ptot, s_scan);
-                const int off = (pex & 0xffff) + carried;
-                const int rank = (pex >> 16) + fcarried;  // position-sorted
-                carried += ptot & 0xffff;
-                fcarried += ptot >> 16;
-                if (pidx < W) S.fpre[pidx] = (uint16_t)rank;
+                S.fpre[pidx] = (uint16_t)rank;
                 if (n || fl) {
                     const long long row = rowbase + off;
                     if (d & 1) write_row(P, CN, pidx, t0 + pidx, 0, row);
@@ -784,8 +846,10 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
                         S.flag_d[rank] = (uint8_t)d;
                     }
                 }
+                off += n;
+                rank += fl ? 1 : 0;
             }
-            if (threadIdx.x == 0) { s_nflag = fcarried; S.fpre[W] = (uint16_t)fcarried; }
+            if (threadIdx.x == 0) { s_nflag = tile_flagged; S.fpre[W] = (uint16_t)tile_flagged; }
         }
         __syncthreads();
         PHASE_MARK(4);  // decide + rows
@@ -799,12 +863,13 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
             const int ns = min(spr, nflag - round0);
             X.round0 = round0;
             X.ns = ns;
-            for (int i = threadIdx.x; i < ns * SW; i += blockDim.x) {
-                const int wsl = i % SW;
-                // first-seen ordinals (and the minimum IUPAC code) start at +inf, everything else at 0
-                const int fw = (wsl - (HW + 4)) % RAER_SLOT_FS;
-                const bool is_fs = wsl >= HW + 4 && (fw < 4 || fw == 5 || fw == 6);
-                slot0[i] = is_fs ? 0xffffffffu : 0u;
+            for (int i = wid; i < ns; i += LN_WARPS) {  // a warp per slot
+                uint32_t* sl = slot0 + (size_t)i * SW;
+                for (int w = lane; w < SW; w += 32) {
+                    // first-seen ordinals (and the minimum IUPAC code) start at +inf, everything else at 0
+                    const int fw = (w - (HW + 4)) & (RAER_SLOT_FS - 1);
+                    sl[w] = (w >= HW + 4 && (fw < 4 || fw == 5 || fw == 6)) ? 0xffffffffu : 0u;
+                }
             }
             if (threadIdx.x == 0) s_chunk = 0;
             __syncthreads();
@@ -868,8 +933,8 @@ __global__ void k_tile_first(PlpParams P, int* first) {
 
 // per-CTA shared memory of k_pileup_lane without the staging slices
 extern "C" size_t raer_lane_fixed_bytes(int n_files, int W) {
-    return (size_t)n_files * 8 * FWS(W) * 4 + ((FWMAX >> 3) + 8 + (FWMAX >> 5) + 4 + FWMAX) * 4 + (2 * FWMAX + 8) * 2 + 2 * FWMAX +
-           LN_WARPS * 8 + 128;
+    return (size_t)n_files * 8 * FWS(W) * 4 + ((FWMAX >> 3) + 12 + (FWMAX >> 5) + 4 + FWMAX) * 4 + (2 * FWMAX + 8) * 2 + 2 * FWMAX +
+           LN_WARPS * 8 + LN_DEFER * 5 + 128;
 }
 // widest tile (multiple of 128, at most 1024) that leaves every warp a staging slice of at least `min_stage` bytes;
 // *stage_bytes = the slice the remaining shared memory allows (capped)

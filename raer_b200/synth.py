@@ -69,11 +69,27 @@ class Reads:
     isize: torch.Tensor      # int32
     mate_idx: torch.Tensor   # int64 index of the mate inside this contig's sorted order
 
+    def window(self, beg: int, end: int) -> "Reads":
+        """The records that overlap [beg, end): what a region-sharded call hands to the device for a tile of a contig (the
+        reads of the tile plus its halo). A mate that stays outside loses the link: the bases the two share lie outside
+        the window as well."""
+        keep = (self.end > beg) & (self.pos < end)
+        idx = keep.nonzero().flatten()
+        new_of_old = torch.full((self.pos.numel(),), -1, dtype=torch.int64, device=self.pos.device)
+        new_of_old[idx] = torch.arange(idx.numel(), device=self.pos.device)
+        m = self.mate_idx[idx]
+        mate = torch.where(m >= 0, new_of_old[m.clamp(min=0)], torch.full_like(m, -1))
+        return Reads(pos=self.pos[idx], end=self.end[idx], flag=self.flag[idx], mapq=self.mapq[idx], cigar=self.cigar[idx],
+                     n_cigar=self.n_cigar[idx], seq=self.seq[idx], qual=self.qual[idx], pair_id=self.pair_id[idx],
+                     mate_pos=self.mate_pos[idx], isize=self.isize[idx], mate_idx=mate)
+
 
 def gen_contig(ref: torch.Tensor, n_pairs: int, seed: int, *, edit_frac=1e-3, gene_block=50_000,
                p_splice=0.12, p_clip=0.04, p_ins=0.02, p_del=0.02, intron=(100, 5000), device="cpu",
-               qual_mix=(0.90, 0.08, 0.02), mapq_mix=(0.95, 0.03, 0.02), single_end=False) -> Reads:
-    """2x100 bp pairs on one contig (or single-end 91 bp style reads when single_end)."""
+               qual_mix=(0.90, 0.08, 0.02), mapq_mix=(0.95, 0.03, 0.02), single_end=False,
+               starts: Optional[torch.Tensor] = None, read_len: int = READ_LEN) -> Reads:
+    """2x100 bp pairs on one contig (or single-end 91 bp style reads when single_end). starts: fragment starts to use
+    instead of uniform ones (n_pairs int64 values on `device`; the C4 workload puts 70 % of them inside intervals)."""
     dev = torch.device(device)
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
@@ -82,12 +98,14 @@ def gen_contig(ref: torch.Tensor, n_pairs: int, seed: int, *, edit_frac=1e-3, ge
     U = lambda *s: torch.rand(*s, generator=g, device=dev)  # noqa: E731
     frag = (180 + 40 * torch.randn(n, generator=g, device=dev)).round().clamp(100, 400).long()
     if single_end:
-        frag = torch.full((n,), READ_LEN, device=dev, dtype=torch.long)
-    max_span = READ_LEN + intron[1] + 8
+        frag = torch.full((n,), read_len, device=dev, dtype=torch.long)
+    max_span = read_len + intron[1] + 8
     start = (U(n) * max(L - 400 - max_span, 1)).long()
+    if starts is not None:
+        start = starts.to(dev).long().clamp(0, max(L - 400 - max_span, 1) - 1)
     # left mate starts at the fragment start, right mate ends at the fragment end
     lpos = start
-    rpos = start + frag - READ_LEN
+    rpos = start + frag - read_len
     gene_minus = ((start // gene_block) % 2 == 1)
     n_reads = n if single_end else 2 * n
     pos0 = lpos if single_end else torch.cat([lpos, rpos])
@@ -115,7 +133,7 @@ def gen_contig(ref: torch.Tensor, n_pairs: int, seed: int, *, edit_frac=1e-3, ge
     nlen = (intron[0] + U(n_reads) * (intron[1] - intron[0])).long()
     clip_left = U(n_reads) < 0.5
     k_clip = (1 + U(n_reads) * 20).long()
-    j = torch.arange(READ_LEN, device=dev).unsqueeze(0)     # [1, RL]
+    j = torch.arange(read_len, device=dev).unsqueeze(0)     # [1, RL]
     A = a.unsqueeze(1)
     K = k.unsqueeze(1)
     KC = k_clip.unsqueeze(1)
@@ -124,37 +142,37 @@ def gen_contig(ref: torch.Tensor, n_pairs: int, seed: int, *, edit_frac=1e-3, ge
     T = ctype.unsqueeze(1)
     CL = clip_left.unsqueeze(1)
     # reference offset of query base j (or -1 when the base is clipped / inserted)
-    off = j.expand(n_reads, READ_LEN).clone()
+    off = j.expand(n_reads, read_len).clone()
     off = torch.where(T == 1, j + (j >= A) * NL, off)
     off = torch.where((T == 2) & CL, torch.where(j < KC, torch.full_like(off, -1), j - KC), off)
-    off = torch.where((T == 2) & ~CL, torch.where(j >= READ_LEN - KC, torch.full_like(off, -1), off), off)
+    off = torch.where((T == 2) & ~CL, torch.where(j >= read_len - KC, torch.full_like(off, -1), off), off)
     off = torch.where(T == 3, torch.where(j < A, j, torch.where(j < A + K, torch.full_like(off, -1), j - K)), off)
     off = torch.where(T == 4, j + (j >= A) * K, off)
     refpos = torch.where(off >= 0, P0 + off, torch.full_like(off, -1))
     refpos = refpos.clamp(max=L - 1)
-    span = torch.full((n_reads,), READ_LEN, device=dev, dtype=torch.long)
-    span = torch.where(ctype == 1, READ_LEN + nlen, span)
-    span = torch.where(ctype == 2, READ_LEN - k_clip, span)
-    span = torch.where(ctype == 3, READ_LEN - k, span)
-    span = torch.where(ctype == 4, READ_LEN + k, span)
+    span = torch.full((n_reads,), read_len, device=dev, dtype=torch.long)
+    span = torch.where(ctype == 1, read_len + nlen, span)
+    span = torch.where(ctype == 2, read_len - k_clip, span)
+    span = torch.where(ctype == 3, read_len - k, span)
+    span = torch.where(ctype == 4, read_len + k, span)
     # CIGAR words (len << 4 | op): M0 I1 D2 N3 S4
     w = lambda ln, op: (ln << 4) | op  # noqa: E731
     z = torch.zeros(n_reads, dtype=torch.long, device=dev)
-    cig = torch.stack([w(torch.full_like(z, READ_LEN), 0), z, z], dim=1)
+    cig = torch.stack([w(torch.full_like(z, read_len), 0), z, z], dim=1)
     m = ctype == 1
-    cig[m] = torch.stack([w(a, 0), w(nlen, 3), w(READ_LEN - a, 0)], dim=1)[m]
+    cig[m] = torch.stack([w(a, 0), w(nlen, 3), w(read_len - a, 0)], dim=1)[m]
     m = (ctype == 2) & clip_left
-    cig[m] = torch.stack([w(k_clip, 4), w(READ_LEN - k_clip, 0), z], dim=1)[m]
+    cig[m] = torch.stack([w(k_clip, 4), w(read_len - k_clip, 0), z], dim=1)[m]
     m = (ctype == 2) & ~clip_left
-    cig[m] = torch.stack([w(READ_LEN - k_clip, 0), w(k_clip, 4), z], dim=1)[m]
+    cig[m] = torch.stack([w(read_len - k_clip, 0), w(k_clip, 4), z], dim=1)[m]
     m = ctype == 3
-    cig[m] = torch.stack([w(a, 0), w(k, 1), w(READ_LEN - a - k, 0)], dim=1)[m]
+    cig[m] = torch.stack([w(a, 0), w(k, 1), w(read_len - a - k, 0)], dim=1)[m]
     m = ctype == 4
-    cig[m] = torch.stack([w(a, 0), w(k, 2), w(READ_LEN - a, 0)], dim=1)[m]
+    cig[m] = torch.stack([w(a, 0), w(k, 2), w(read_len - a, 0)], dim=1)[m]
     n_cig = torch.where(ctype == 0, 1, torch.where(ctype == 2, 2, 3)).int()
     # bases: reference, then A->G editing (T->C for minus genes), then sequencing errors
     base = ref[refpos.clamp(min=0)].long()
-    rnd_base = (U(n_reads, READ_LEN) * 4).long().clamp(0, 3)
+    rnd_base = (U(n_reads, read_len) * 4).long().clamp(0, 3)
     base = torch.where(refpos >= 0, base, rnd_base)
     g2 = torch.Generator(device=dev)
     g2.manual_seed(seed * 7919 + 13)
@@ -162,17 +180,17 @@ def gen_contig(ref: torch.Tensor, n_pairs: int, seed: int, *, edit_frac=1e-3, ge
     level = 0.05 + 0.45 * torch.rand(L, generator=g2, device=dev)
     editable = site_u < edit_frac
     rp = refpos.clamp(min=0)
-    ed_hit = editable[rp] & (refpos >= 0) & (U(n_reads, READ_LEN) < level[rp])
+    ed_hit = editable[rp] & (refpos >= 0) & (U(n_reads, read_len) < level[rp])
     GM = gm.unsqueeze(1)
     base = torch.where(ed_hit & ~GM & (base == 0), torch.full_like(base, 2), base)   # A->G on plus genes
     base = torch.where(ed_hit & GM & (base == 3), torch.full_like(base, 1), base)    # T->C on minus genes
-    uq = U(n_reads, READ_LEN)
-    qual = torch.full((n_reads, READ_LEN), 37, dtype=torch.long, device=dev)
-    qual = torch.where(uq < qual_mix[1] + qual_mix[2], (11 + U(n_reads, READ_LEN) * 15).long(), qual)
+    uq = U(n_reads, read_len)
+    qual = torch.full((n_reads, read_len), 37, dtype=torch.long, device=dev)
+    qual = torch.where(uq < qual_mix[1] + qual_mix[2], (11 + U(n_reads, read_len) * 15).long(), qual)
     qual = torch.where(uq < qual_mix[2], torch.full_like(qual, 2), qual)
     perr = torch.pow(10.0, -qual.float() / 10.0)
-    err = U(n_reads, READ_LEN) < perr
-    base = torch.where(err, (base + 1 + (U(n_reads, READ_LEN) * 3).long().clamp(0, 2)) % 4, base)
+    err = U(n_reads, read_len) < perr
+    base = torch.where(err, (base + 1 + (U(n_reads, read_len) * 3).long().clamp(0, 2)) % 4, base)
     codes = _CODE_OF_IDX.to(dev)[base]
     um = U(n)
     mq = torch.full((n,), 255, dtype=torch.long, device=dev)
@@ -300,6 +318,85 @@ def make_bulk_dataset(outdir: str, *, n_bams=2, n_contigs=2, contig_len=200_000,
     return {"fasta": fa, "bams": bams, "names": names, "lens": lens, "aligned_bases": n_bases}
 
 
+def known_sites_mask(ref: torch.Tensor, seed: int, frac: float = 0.4, gene_block: int = 50_000) -> torch.Tensor:
+    """C3 site list as a bool tensor over the contig: A positions of plus genes / T positions of minus genes (the
+    positions A-to-I editing can show at, seen from the plus strand), a fraction `frac` of them (0.4 -> 10 % of all
+    positions: 10^7 sites on the 100 Mb reference)."""
+    g = torch.Generator(device=ref.device)
+    g.manual_seed(seed)
+    L = ref.numel()
+    minus = (torch.arange(L, device=ref.device) // gene_block) % 2 == 1
+    cand = torch.where(minus, ref == 3, ref == 0)
+    return cand & (torch.rand(L, generator=g, device=ref.device) < frac)
+
+
+def alu_intervals(L: int, seed: int, device="cpu", slot: int = 1000, len_lo: int = 280, len_hi: int = 320):
+    """C4 intervals of one contig: one per `slot` positions, non-overlapping, length U[len_lo, len_hi]
+    (10^6 of them on the 1 Gb reference). Returns (start0, end0_exclusive) int64 tensors."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    n = L // slot
+    ln = torch.randint(len_lo, len_hi + 1, (n,), generator=g, device=device)
+    st = torch.arange(n, device=device) * slot + (torch.rand(n, generator=g, device=device) * (slot - len_hi)).long()
+    return st, st + ln
+
+
+def interval_mask(L: int, st: torch.Tensor, en: torch.Tensor) -> torch.Tensor:
+    d = torch.zeros(L + 1, dtype=torch.int32, device=st.device)
+    d.index_add_(0, st, torch.ones_like(st, dtype=torch.int32))
+    d.index_add_(0, en, -torch.ones_like(en, dtype=torch.int32))
+    return torch.cumsum(d[:L], 0) > 0
+
+
+def interval_starts(n_pairs: int, L: int, st: torch.Tensor, en: torch.Tensor, seed: int, inside: float = 0.7) -> torch.Tensor:
+    """fragment starts of the C4 BAM: `inside` of the fragments start within 60 bases in front of an interval or
+    inside it, the rest anywhere"""
+    dev = st.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    pick = torch.randint(0, st.numel(), (n_pairs,), generator=g, device=dev)
+    ln = (en - st)[pick]
+    s_in = st[pick] - 60 + (torch.rand(n_pairs, generator=g, device=dev) * (ln + 60).float()).long()
+    s_any = (torch.rand(n_pairs, generator=g, device=dev) * max(L - 6000, 1)).long()
+    return torch.where(torch.rand(n_pairs, generator=g, device=dev) < inside, s_in.clamp(min=0), s_any)
+
+
+def pack_bitmap(mask: torch.Tensor) -> torch.Tensor:
+    """bool tensor -> uint32 words (as int32), bit (p & 31) of word p >> 5: the site_mask layout of raer_bulk_conf"""
+    L = mask.numel()
+    pad = (-L) % 32
+    if pad:
+        mask = torch.cat([mask, torch.zeros(pad, dtype=torch.bool, device=mask.device)])
+    w = (mask.view(-1, 32).long() << torch.arange(32, device=mask.device)).sum(1)
+    return (w & 0xFFFFFFFF).to(torch.int64).where(w < 2**31, w - 2**32).to(torch.int32).contiguous()
+
+
+def make_aei_dataset(outdir: str, *, n_contigs=2, contig_len=200_000, pairs_per_contig=20_000, seed=4001) -> dict:
+    """Reference, one BAM of the C4 shape (70 % of the fragments at the intervals) and the interval list."""
+    os.makedirs(outdir, exist_ok=True)
+    names = [f"chr{i + 1}" for i in range(n_contigs)]
+    lens = [contig_len] * n_contigs
+    refs = make_reference(lens, seed)
+    fa = os.path.join(outdir, "ref.fa")
+    write_fasta(fa, names, refs)
+    per, n_bases = [], 0
+    sn, ss, se = [], [], []
+    for t in range(n_contigs):
+        st, en = alu_intervals(contig_len, seed + 10 + t)
+        starts = interval_starts(pairs_per_contig, contig_len, st, en, seed + 100 + t)
+        r = gen_contig(refs[t], pairs_per_contig, seed + 1000 + t, starts=starts)
+        per.append(r)
+        c = r.cigar
+        n_bases += int(((c >> 4) * ((c & 0xF) == 0)).sum())
+        sn += [names[t]] * st.numel()
+        ss += (st + 1).tolist()
+        se += en.tolist()
+    bam = os.path.join(outdir, "aei.bam")
+    write_bam(bam, names, lens, per, qname_prefix="a_")
+    return {"fasta": fa, "bam": bam, "names": names, "lens": lens, "aligned_bases": n_bases,
+            "intervals": dict(seqnames=sn, start=ss, end=se)}
+
+
 def make_sc_dataset(outdir: str, *, n_contigs=2, contig_len=60_000, reads_per_contig=20_000, n_cb=60, n_sites=400,
                     seed=5001, gene_block=5_000, edit_frac=0.02) -> dict:
     """Reference, one 10x-shaped BAM and a site list of the C5 shape at a chosen size: single-end
@@ -393,7 +490,8 @@ def qname_coin(qname: bytes) -> bool:
 
 
 def pack_device_batch(per_file: List[Reads], tid: int, beg: int, end: int, remove_overlaps: bool = True,
-                      qname_prefixes: Optional[List[str]] = None):
+                      qname_prefixes: Optional[List[str]] = None, libtype: int = 1, cb: Optional[torch.Tensor] = None,
+                      umi: Optional[torch.Tensor] = None):
     """Lay out the reads of one contig (all files) as a raer_read_batch in the memory of their
     device (HBM when generated on cuda). Returns (dict of tensors kept alive, fields for ReadBatch).
     qname_prefixes: per file, the prefix write_bam() gives the read names of these records; the mate-overlap coin is
@@ -418,7 +516,11 @@ def pack_device_batch(per_file: List[Reads], tid: int, beg: int, end: int, remov
         rev = (fl & 16) != 0
         paired = (fl & 1) != 0
         r1 = (~paired) | ((fl & 64) != 0)
-        inv = torch.where(r1, ~rev, rev)
+        inv = torch.where(r1, ~rev, rev)  # fr-first-strand
+        if libtype == 2:
+            inv = ~inv
+        elif libtype == 0:
+            inv = torch.zeros_like(inv)
         bits |= inv.int() * 1
         h[:, 2] = (fl & 0xFFFF) | (r.mapq.int() << 16) | (bits << 24)
         h[:, 3] = rl | (r.n_cigar << 16)
@@ -482,6 +584,47 @@ def pack_device_batch(per_file: List[Reads], tid: int, beg: int, end: int, remov
     b.seq, b.qual = T["seq"].data_ptr(), T["qual"].data_ptr()
     b.n_cigar_words, b.n_sq_bytes = co, so
     b.pair_b, b.n_pairs = T["pair_b"].data_ptr(), T["pair_b"].numel()
+    if cb is not None:  # single cell: whitelist column (1-based, 0 = none) and UMI id (0 = no tag) per read
+        T["cb"] = cb.to(torch.int32).contiguous()
+        T["umi"] = (umi if umi is not None else torch.zeros_like(cb)).to(torch.int32).contiguous()
+        b.cb, b.umi = T["cb"].data_ptr(), T["umi"].data_ptr()
+    return T, b
+
+
+def gen_sc_batch(ref: torch.Tensor, n_reads: int, seed: int, *, n_cb=10_000, n_site_frac=0.01, read_len=91, gene_block=50_000,
+                 tid=0):
+    """One C5-shaped batch on the device of `ref`: single-end reads (flags 0 / 16 by gene block, +1024 on 20 %), CB
+    drawn Zipf(s = 1) from n_cb barcodes with 2 % of the reads off the list, UMI ids with about 3 reads per (barcode,
+    150-base locus, UMI), and the site list (A positions of plus genes / T positions of minus genes, REF A / ALT G in
+    the strand's own orientation, n_site_frac of all positions). Returns (tensors, ReadBatch, sites dict)."""
+    dev = ref.device
+    L = ref.numel()
+    r = gen_contig(ref, n_reads, seed, device=dev, single_end=True, gene_block=gene_block, read_len=read_len, edit_frac=0.02)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed * 31 + 5)
+    n = r.pos.numel()
+    r.flag = r.flag | ((torch.rand(n, generator=g, device=dev) < 0.2).int() * 1024)
+    zipf = 1.0 / torch.arange(1, n_cb + 1, device=dev, dtype=torch.float64)
+    cb_idx = torch.multinomial((zipf / zipf.sum()).float(), n, replacement=True, generator=g)
+    cb = torch.where(torch.rand(n, generator=g, device=dev) < 0.02, torch.zeros_like(cb_idx), cb_idx + 1)
+    locus = r.pos.long() // 150
+    key = cb_idx * 1_000_000 + locus
+    u = (torch.rand(n, generator=g, device=dev) * 3).long()
+    umi = (key * 1_000_003 + u * 7919 + 12345) % (1 << 24)
+    umi = torch.where(torch.rand(n, generator=g, device=dev) < 0.02, torch.zeros_like(umi), umi + 1)
+    T, b = pack_device_batch([r], tid, 0, L, remove_overlaps=False, libtype=2, cb=cb, umi=umi)
+    minus = (torch.arange(L, device=dev) // gene_block) % 2 == 1
+    cand = torch.where(minus, ref == 3, ref == 0)
+    sel = cand & (torch.rand(L, generator=g, device=dev) < n_site_frac * 4)
+    sel[:200] = False
+    sel[L - 200:] = False
+    pos = sel.nonzero().flatten()
+    T["site_pos"] = pos.to(torch.int32).contiguous()
+    T["site_strand"] = torch.where(minus[pos], 2, 1).to(torch.uint8).contiguous()
+    T["site_ref"] = torch.full((pos.numel(),), ord("A"), dtype=torch.uint8, device=dev)
+    T["site_alt"] = torch.full((pos.numel(),), ord("G"), dtype=torch.uint8, device=dev)
+    c = r.cigar
+    T["aligned_bases"] = int(((c >> 4) * ((c & 0xF) == 0)).sum())
     return T, b
 
 
