@@ -36,6 +36,13 @@ extern "C" {
 #define RAER_ERR_CUDA -5       /* CUDA runtime error, see raer_last_error() */
 #define RAER_ERR_MD -6         /* MD tag inconsistent with CIGAR while max_mismatch_type is active */
 #define RAER_ERR_LIMIT -7      /* input exceeds a documented limit (files per call, read length) */
+#define RAER_ERR_INTERRUPT -8  /* the caller's poll callback asked to stop (user interrupt); everything was released */
+
+/* Interrupt hook. The reference polls R_CheckUserInterrupt every 2^18 pileup columns (src/plp.c:925-931,
+ * src/plp_utils.c:7-12). Here the CALLING thread invokes poll(poll_ctx) between read batches (never a worker thread:
+ * the R API is single threaded); a nonzero return stops the call, which releases its resources and returns
+ * RAER_ERR_INTERRUPT. NULL = never polled. */
+typedef int (*raer_poll_fn)(void* poll_ctx);
 
 #define RAER_MAX_FILES 32      /* BAM files per raer_pileup call (shared-memory counter budget) */
 
@@ -76,6 +83,8 @@ typedef struct raer_pileup_args {
                                         been written, summed by (REF of the row, counted base): all calc_AEI() needs
                                         (reference R/calc_AEI.R:274-323). Needs the fast tile kernel. */
     int32_t pad1;
+    raer_poll_fn poll;               /* interrupt hook, see raer_poll_fn; NULL = none */
+    void* poll_ctx;
 } raer_pileup_args;
 
 /* Column layout of the .Call(".pileup") result (src/plp_data.c:285-289, 321-361). Every file has
@@ -132,6 +141,9 @@ typedef struct raer_scpileup_args {
     int32_t overlap_mode;
     int32_t device;
     int32_t host_threads;
+    int32_t pad1;
+    raer_poll_fn poll;               /* interrupt hook, see raer_poll_fn; NULL = none */
+    void* poll_ctx;
 } raer_scpileup_args;
 
 /* returns the status the reference returns through ScalarInteger (>= 0 ok, < 0 failure) */

@@ -48,7 +48,12 @@ class PileupArgs(C.Structure):
         ("shard_count", C.c_int32),
         ("aei_mode", C.c_int32),
         ("pad1", C.c_int32),
+        ("poll", C.c_void_p),
+        ("poll_ctx", C.c_void_p),
     ]
+
+
+POLL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)  # raer_poll_fn: nonzero return stops the call (RAER_ERR_INTERRUPT)
 
 
 class PileupResult(C.Structure):
@@ -106,6 +111,9 @@ class ScArgs(C.Structure):
         ("overlap_mode", C.c_int32),
         ("device", C.c_int32),
         ("host_threads", C.c_int32),
+        ("pad1", C.c_int32),
+        ("poll", C.c_void_p),
+        ("poll_ctx", C.c_void_p),
     ]
 
 

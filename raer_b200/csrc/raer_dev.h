@@ -25,6 +25,7 @@
 // internal device -> host conditions (never returned through the C ABI): the host re-runs the batch
 #define RAER_RETRY_DEEP (-100)     // k_pileup_fast met coverage > 65535: re-run with k_pileup_tiles
 #define RAER_LANE_MW 5             // k_pileup_lane: mask words per read
+#define RAER_RETRY_ROWCAP (-102)   // more rows than the row buffers hold (they are sized from the reads, not the span): re-run with the count
 #define RAER_RETRY_LISTCAP (-101)  // the tile read lists did not fit their allocation: re-run with the exact size
 
 struct PlpParams {

@@ -1004,7 +1004,7 @@ __global__ void __launch_bounds__(RAER_BLOCK, 1) k_pileup_tiles(PlpParams P) {
         const bool tile_grow = (tile_tot >> 16) != 0;
         if (threadIdx.x == 0) {
             long long base = (long long)atomicAdd(P.row_counter, (unsigned long long)tile_rows_total);
-            if (base + tile_rows_total > P.row_cap) { atomicExch(P.err_flag, RAER_ERR_LIMIT); base = -1; }
+            if (base + tile_rows_total > P.row_cap) { atomicCAS(P.err_flag, 0, RAER_RETRY_ROWCAP); base = -1; }  // row_counter keeps the total: the host re-runs with that many
             s_rowbase = (int)base;
             P.tile_rows[tile] = make_int2((int)base, base < 0 ? 0 : tile_rows_total);
         }

@@ -579,6 +579,16 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
         const int tile = s_tile;
         if (tile >= P.n_tiles) break;
         PHASE_MARK(0);  // tile fetch (and what follows the last mark of the previous tile)
+        {
+            // a tile no read reaches writes no row (a sparse BAM or a site-list call on a long contig is mostly such tiles)
+            bool any = P.tile_off[tile * F + F] > P.tile_off[tile * F];
+            for (int f = 0; f < F && !any; ++f) any = __ldg(P.tile_first + (tile + 1) * F + f) > __ldg(P.tile_first + tile * F + f);
+            if (!any) {
+                if (threadIdx.x == 0) P.tile_rows[tile] = make_int2(0, 0);
+                __syncthreads();  // everybody has read s_tile before the next tile overwrites it
+                continue;
+            }
+        }
         const int t0 = P.t_beg + tile * W;
         const int t1 = min(t0 + W, P.t_end);
         X.t0 = t0;
@@ -823,7 +833,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_pileup_lane(PlpParams P) {
         const int tile_rows_total = tile_tot & 0xffff, tile_flagged = tile_tot >> 16;
         if (threadIdx.x == 0) {
             long long base = (long long)atomicAdd(P.row_counter, (unsigned long long)tile_rows_total);
-            if (base + tile_rows_total > P.row_cap) { atomicExch(P.err_flag, RAER_ERR_LIMIT); base = -1; }
+            if (base + tile_rows_total > P.row_cap) { atomicCAS(P.err_flag, 0, RAER_RETRY_ROWCAP); base = -1; }  // row_counter keeps the total: the host re-runs with that many
             s_rowbase = (int)base;
             P.tile_rows[tile] = make_int2((int)base, base < 0 ? 0 : tile_rows_total);
         }

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <condition_variable>
 #include <deque>
@@ -212,7 +213,7 @@ enum { RUN_FORCE_GENERIC = 1, RUN_SKIP_OVERLAP = 2 };
 // the device can see (tile lists larger than their allocation, coverage beyond the fast kernel's 16-bit counters)
 // come back through err_flag and finish_run() re-runs the batch accordingly.
 static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_batch* b, const uint32_t* d_mask,
-                      int64_t* launches, int flags = 0, long long list_need = 0) {
+                      int64_t* launches, int flags = 0, long long list_need = 0, long long row_need = 0) {
     const int nf = b->n_files;
     PlpParams P;
     memset(&P, 0, sizeof(P));
@@ -291,7 +292,14 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
     if (P.n_tiles > 0) {
         if ((rc = c->tile_ranges.ensure((size_t)P.n_tiles * nf * sizeof(int2)))) return rc;
         if ((rc = c->tile_rows.ensure((size_t)P.n_tiles * sizeof(int2)))) return rc;
+        // Row buffers: a site writes at most two rows, and only where a read lies, so the packed bases of the batch bound
+        // the rows far below 2 x span for a sparse BAM or a site-list call on a long contig (40 B x files + 32 B per row:
+        // sizing by span asked for tens of GB there). The bound is loose on purpose and not exact (deletions, min_depth 0
+        // inside ref-skips): the device keeps counting past the end of the buffers and the batch is re-run with the count.
         long long cap = 2 * span + 64;
+        if (row_need > 0) cap = std::min(cap, row_need + 64);
+        else cap = std::min(cap, std::max<long long>(1 << 16, 4 * (long long)b->n_sq_bytes + 64));
+        if (getenv("RAER_TEST_ROWCAP") && row_need == 0) cap = std::min<long long>(cap, std::max(1, atoi(getenv("RAER_TEST_ROWCAP"))));
         if ((rc = c->row_pos.ensure((size_t)cap * 4))) return rc;
         if ((rc = c->row_meta.ensure((size_t)cap * 4))) return rc;
         if ((rc = c->row_stats.ensure((size_t)cap * 24))) return rc;
@@ -376,26 +384,24 @@ static int run_device(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_b
 // in device memory (qualities already rewritten by the mate-overlap kernel: re-runs skip it).
 static int finish_run(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_batch* b, const uint32_t* d_mask,
                       int64_t* launches, SmallState* out) {
-    for (int attempt = 0; attempt < 4; ++attempt) {
+    int flags = RUN_SKIP_OVERLAP;  // what the re-runs have learnt so far
+    long long list_need = 0, row_need = 0;
+    for (int attempt = 0; attempt < 6; ++attempt) {
         SmallState s;
         CK(cudaMemcpyAsync(&s, c->small.p, sizeof(s), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        if (s.err == RAER_RETRY_LISTCAP) {
-            int rc = run_device(c, conf, b, d_mask, launches, RUN_SKIP_OVERLAP, (long long)s.list_total + 16);
-            if (rc) return rc;
-            continue;
-        }
-        if (s.err == RAER_RETRY_DEEP) {
-            int rc = run_device(c, conf, b, d_mask, launches, RUN_SKIP_OVERLAP | RUN_FORCE_GENERIC);
-            if (rc) return rc;
-            continue;
-        }
-        if (s.err) {
+        if (s.err == RAER_RETRY_LISTCAP) list_need = (long long)s.list_total + 16;
+        else if (s.err == RAER_RETRY_DEEP) flags |= RUN_FORCE_GENERIC;
+        else if (s.err == RAER_RETRY_ROWCAP) row_need = (long long)s.rows;
+        else if (s.err) {
             set_error(s.err == RAER_ERR_MD ? "inconsistent MD tag with max_mismatch_type" : "device reported error %d", s.err);
             return s.err;
+        } else {
+            *out = s;
+            return RAER_OK;
         }
-        *out = s;
-        return RAER_OK;
+        int rc = run_device(c, conf, b, d_mask, launches, flags, list_need, row_need);
+        if (rc) return rc;
     }
     set_error("device kept asking for a re-run");
     return RAER_ERR;
@@ -1004,11 +1010,23 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             {
                 std::unique_lock<std::mutex> lk(mu);
                 double t0b = raer::now_seconds();
-                cv_ready.wait(lk, [&]() { return !ready.empty() || workers_left == 0; });
+                // wake up twice a second to give the interrupt hook a chance while the workers are still decoding
+                while (!cv_ready.wait_for(lk, std::chrono::milliseconds(500), [&]() { return !ready.empty() || workers_left == 0; })) {
+                    if (rc == RAER_OK && a->poll) {
+                        lk.unlock();
+                        const bool stop_now = a->poll(a->poll_ctx) != 0;
+                        lk.lock();
+                        if (stop_now) { set_error("interrupted"); rc = RAER_ERR_INTERRUPT; stop = true; cv_free.notify_all(); }
+                    }
+                }
                 tm_batch += raer::now_seconds() - t0b;
                 if (ready.empty()) break;
                 sl = ready.front();
                 ready.pop_front();
+            }
+            if (rc == RAER_OK && a->poll && a->poll(a->poll_ctx)) {  // the calling thread polls between batches (src/plp.c:925-931)
+                set_error("interrupted");
+                rc = RAER_ERR_INTERRUPT;
             }
             if (rc == RAER_OK) {
                 if (sl->tid != ref_tid) {
@@ -1085,6 +1103,11 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
                 const bool got = ing.next_batch(pb);
                 tm_batch += raer::now_seconds() - t0b;
                 if (!got) break;
+                if (a->poll && a->poll(a->poll_ctx)) {  // the calling thread polls between batches (src/plp.c:925-931)
+                    set_error("interrupted");
+                    rc = RAER_ERR_INTERRUPT;
+                    break;
+                }
                 if (!mine || pb.b.n_reads == 0 || pb.b.end <= pb.b.beg) continue;
                 if (has_ridx && !rchr) continue;
                 raer_rows rows;
@@ -1167,6 +1190,7 @@ extern "C" int raer_ingest_summary(const raer_pileup_args* a, int64_t target_rea
     while (ing.next_contig() >= 0) {
         prev_boundary = INT_MIN;
         while (ing.next_batch(pb)) {
+            if (a->poll && a->poll(a->poll_ctx)) { set_error("interrupted"); return RAER_ERR_INTERRUPT; }
             out[0] += pb.b.n_reads;
             out[1] += pb.b.n_pairs;
             out[2] += pb.b.n_cigar_words;

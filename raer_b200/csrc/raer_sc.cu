@@ -746,6 +746,11 @@ static int sc_run(const raer_scpileup_args* a, bool want_files, raer_sc_triplets
             conf.site_pos = sp.data(); conf.site_strand = ss.data(); conf.site_ref = sr.data(); conf.site_alt = sa.data();
             while (rc == RAER_OK && ing.next_batch(pb)) {
                 const raer_read_batch& b = pb.b;
+                if (a->poll && a->poll(a->poll_ctx)) {  // the calling thread polls between batches (src/sc-plp.c:707-712)
+                    set_error("interrupted");
+                    rc = RAER_ERR_INTERRUPT;
+                    break;
+                }
                 if (!ns || b.n_reads == 0 || b.end <= b.beg) continue;
                 conf.n_umi = (uint32_t)ing.umi_dict().size();
                 raer_sc_cells cells;

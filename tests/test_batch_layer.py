@@ -151,6 +151,23 @@ def test_tile_list_overflow_is_rerun(small_batch, monkeypatch):
     _same(_run_host(H, hb, conf, 2), want)
 
 
+@pytest.mark.parametrize("kernel", ["lane", "fast", "generic"])
+def test_row_buffers_smaller_than_the_rows_are_rerun(small_batch, monkeypatch, kernel):
+    # the row buffers are sized from the reads, not from the genomic span; when the guess is too small the device
+    # reports how many rows there are and the batch runs again (here the first guess is forced down to 100 rows)
+    H, hb = small_batch
+    conf = _conf(2, okv=0)
+    if kernel != "lane":
+        monkeypatch.setenv("RAER_KERNEL", kernel)
+    want = _run_host(H, hb, conf, 2)
+    assert want["pos"].size > 50_000
+    monkeypatch.setenv("RAER_TEST_ROWCAP", "100")
+    _same(_run_host(H, hb, conf, 2), want)
+    # both guesses too small at once: tile lists and rows
+    monkeypatch.setenv("RAER_TEST_LISTCAP", "1000")
+    _same(_run_host(H, hb, conf, 2), want)
+
+
 def test_coverage_beyond_16_bit_counters_falls_back(monkeypatch):
     # ~1.3e5 reads over 150 positions on one strand block: coverage above 65535 per (file, strand)
     H, hb = _host_batch(1, 250, 100_000, 5)

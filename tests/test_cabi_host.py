@@ -36,8 +36,9 @@ def test_struct_layouts_match_header():
     src = r'''
     #include <stdio.h>
     #include "raer_b200.h"
-    int main(void){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(raer_pileup_args), sizeof(raer_pileup_result),
-        sizeof(raer_scpileup_args), sizeof(raer_read_batch), sizeof(raer_bulk_conf), sizeof(raer_rows)); return 0; }
+    int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(raer_pileup_args), sizeof(raer_pileup_result),
+        sizeof(raer_scpileup_args), sizeof(raer_read_batch), sizeof(raer_bulk_conf), sizeof(raer_rows),
+        sizeof(raer_sc_conf), sizeof(raer_sc_cells)); return 0; }
     '''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
@@ -45,7 +46,7 @@ def test_struct_layouts_match_header():
                        check=True)
         out = subprocess.run([os.path.join(d, "t")], check=True, capture_output=True, text=True).stdout.split()
     want = [C.sizeof(x) for x in (_cabi.PileupArgs, _cabi.PileupResult, _cabi.ScArgs, _cabi.ReadBatch, _cabi.BulkConf,
-                                  _cabi.Rows)]
+                                  _cabi.Rows, _cabi.ScConf, _cabi.ScCells)]
     assert [int(x) for x in out] == want
 
 
