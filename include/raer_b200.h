@@ -108,6 +108,9 @@ typedef struct raer_pileup_result {
     double t_decode, t_pack, t_h2d, t_kernel, t_d2h, t_total;
     int64_t n_records, n_aligned_bases, gpu_launches;
     int64_t* aei;     /* aei_mode: [nbam][4][4], index [REF of the row: A C G T][nA nC nG nT], else NULL */
+    int64_t n_inflated_bytes; /* BGZF payload inflated by the call, all files (drops when a site list lets the ingest skip
+                                 through the BAI index) */
+    int64_t n_seeks;          /* index jumps taken between the intervals of a site / region list */
 } raer_pileup_result;
 
 int raer_pileup(const raer_pileup_args* args, raer_pileup_result* out);
@@ -344,7 +347,8 @@ int64_t raer_sc_algorithmic_bytes(const raer_read_batch* b, int64_t n_cells);
 /* Host-only probe of the ingest used by raer_pileup() (no device needed): streams the BAMs, applies
  * the read-level prefilter, packs batches of about target_reads reads and reports
  * out[0..7] = reads handed to the device (halo reads once per batch), mate pairs, CIGAR words,
- * packed sequence bytes, batches, aligned bases of all mapped records, records read, distinct reads. */
+ * packed sequence bytes, batches, aligned bases of all mapped records, records read, distinct reads;
+ * out[8] = BGZF bytes inflated, out[9] = index jumps taken (site lists). out must hold 16 values. */
 int raer_ingest_summary(const raer_pileup_args* args, int64_t target_reads, int64_t* out);
 /* seconds spent in H2D copies, kernels and D2H copies by the last raer_batch_pileup_host() call */
 void raer_ctx_last_timing(raer_ctx* ctx, double* h2d_s, double* kernel_s, double* d2h_s);

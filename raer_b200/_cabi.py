@@ -81,6 +81,8 @@ class PileupResult(C.Structure):
         ("n_aligned_bases", C.c_int64),
         ("gpu_launches", C.c_int64),
         ("aei", C.POINTER(C.c_int64)),
+        ("n_inflated_bytes", C.c_int64),
+        ("n_seeks", C.c_int64),
     ]
 
 
@@ -342,7 +344,8 @@ def pileup(pc, device: int = 0, host_threads: int = 0, overlap_mode: int = 1, sh
         LAST_TIMING.clear()
         LAST_TIMING.update(dict(t_decode=r.t_decode, t_pack=r.t_pack, t_h2d=r.t_h2d, t_kernel=r.t_kernel,
                                 t_d2h=r.t_d2h, t_total=r.t_total, n_records=int(r.n_records),
-                                n_aligned_bases=int(r.n_aligned_bases), gpu_launches=int(r.gpu_launches)))
+                                n_aligned_bases=int(r.n_aligned_bases), gpu_launches=int(r.gpu_launches),
+                                n_inflated_bytes=int(r.n_inflated_bytes), n_seeks=int(r.n_seeks)))
         out["timing"] = dict(LAST_TIMING)
         if aei and r.aei:
             out["aei"] = np.ctypeslib.as_array(r.aei, shape=(n, 4, 4)).astype(np.int64, copy=True)

@@ -42,6 +42,13 @@ public:
     bool open(const char* path, int threads, bool light = false);
     // restrict to [beg, end) of tid using the BAI linear index; returns false on a missing/bad index
     bool set_region(const char* bai_path, int tid, int beg, int end);
+    // After set_region(): only the records that overlap one of these intervals (0-based, half open, sorted, disjoint)
+    // are wanted. The stream skips the gaps between them through the linear index -- forward only, so every record
+    // comes out at most once -- whenever the next interval starts far enough ahead in the file to pay for a seek
+    // (site lists and sparse region lists: src/plp.c:856-882 queries the index per region through sam_itr_querys).
+    void set_jumps(const std::vector<std::pair<int32_t, int32_t>>& intervals);
+    int64_t inflated_bytes() const { return n_inflated_; }
+    int64_t seeks() const { return n_seeks_; }
     // 0 ok, -1 EOF (or past the region), -2 error
     int next(BamRecView& r);
     int n_targets() const { return (int)names_.size(); }
@@ -61,7 +68,6 @@ private:
     std::string err_;
     mutable std::mutex err_mu_;
     bool fill();  // next group of inflated BGZF blocks into ubuf_; the group after it is inflated in the background
-    int produce(std::vector<uint8_t>& out);  // read + inflate one group into out: 1 data, 0 end of file, -1 error
     bool read_header();
     bool need(size_t n);
     FILE* fp_ = nullptr;
@@ -75,6 +81,20 @@ private:
     std::vector<int32_t> lens_;
     bool has_region_ = false, region_done_ = false;
     int r_tid_ = -1, r_beg_ = 0, r_end_ = 0;
+    // jump list (set_jumps) and what it needs: the linear index of r_tid_, and the file offset of every inflated
+    // block still in ubuf_, so that the virtual offset of the record being parsed is known exactly (bgzf_tell)
+    std::vector<std::pair<int32_t, int32_t>> jumps_;
+    size_t jk_ = 0;
+    std::vector<uint64_t> lin_;
+    struct BlkPos { int64_t u_off; uint64_t c_off; };  // offset in ubuf_ (negative: the block began before the kept tail)
+    std::vector<BlkPos> blk_, grp_blk_, pf_blk_;
+    uint64_t cbuf_base_ = 0;  // file offset of cbuf_[0]
+    uint64_t stop_coff_ = 0;  // set_region: file offset of the last block that can hold a record of the contig (0 = unknown)
+    bool small_groups_ = false;
+    int64_t n_inflated_ = 0, n_seeks_ = 0;
+    uint64_t tell() const;     // virtual offset of ubuf_[u_off_]
+    bool seek_voffset(uint64_t v);
+    int produce(std::vector<uint8_t>& out, std::vector<BlkPos>& pos);
     double t_decode_ = 0;
     double t_wait_ = 0;
     int64_t n_records_ = 0;
@@ -257,7 +277,9 @@ struct PackedBatch {
 class Ingest {
 public:
     Ingest(const IngestConf& c) : conf_(c) {}
-    bool open(const char* const* paths, const char* const* indexes, int threads, const char* region);
+    // jumps: the sorted, disjoint intervals wanted on the region's contig (site / region lists, see BamStream::set_jumps)
+    bool open(const char* const* paths, const char* const* indexes, int threads, const char* region,
+              const std::vector<std::pair<int32_t, int32_t>>* jumps = nullptr);
     // next contig with reads in any file (ascending tid of file 0's header); -1 when done
     int next_contig();
     // pack the next batch of the current contig; false when the contig is exhausted
@@ -277,6 +299,10 @@ public:
     double wait_seconds() const;
     int64_t records() const;
     int64_t aligned_bases() const;
+    int64_t inflated_bytes() const;
+    int64_t seeks() const;
+    // site / region lists: let every file skip what lies between the intervals of the open region's contig
+    void set_jumps(const std::vector<std::pair<int32_t, int32_t>>& intervals);
     std::unordered_map<std::string, uint32_t>& umi_dict() { return umi_dict_; }
     ~Ingest();
 
@@ -294,6 +320,11 @@ private:
     double t_parse_ = 0;
     std::unordered_map<std::string, uint32_t> umi_dict_;
 };
+
+// true iff every file has a readable .bai (explicit path or "<bam>.bai")
+bool indexes_usable(const char* const* paths, const char* const* indexes, int n);
+// jump list of one contig of a region index (see Ingest::set_jumps)
+std::vector<std::pair<int32_t, int32_t>> jump_intervals(const RegionIndex::Chr* c, int32_t gap = 1 << 16);
 
 // FASTA via .fai, whole contig, case preserved (faidx_fetch_seq64 semantics)
 bool fasta_fetch(const char* fa, const std::string& name, std::string& out);

@@ -81,18 +81,23 @@ int BamStream::fail(const char* fmt, ...) {
     return -1;
 }
 
-int BamStream::produce(std::vector<uint8_t>& out) {
+int BamStream::produce(std::vector<uint8_t>& out, std::vector<BlkPos>& pos) {
     double t0 = now_seconds();
-    // small groups: the next one inflates while this one is parsed (light: just the header, a seek follows)
-    const size_t kChunk = light_ ? (1u << 20) : (32u << 20), kMaxOut = light_ ? (256u << 10) : (12u << 20);
+    // small groups: the next one inflates while this one is parsed (light: just the header, a seek follows; jump list:
+    // the next seek is never far)
+    const bool small = light_ || small_groups_;
+    const size_t kChunk = small_groups_ ? (256u << 10) : small ? (1u << 20) : (32u << 20);
+    const size_t kMaxOut = small_groups_ ? (192u << 10) : small ? (256u << 10) : (12u << 20);
     out.clear();
+    pos.clear();
     std::vector<BlockJob> jobs;
     size_t out_off = 0;
     while (true) {
         // refill the compressed buffer
-        if (!file_eof_ && cbuf_.size() - c_off_ < (1u << 20)) {
+        if (!file_eof_ && cbuf_.size() - c_off_ < (small_groups_ ? (128u << 10) : (1u << 20))) {
             if (c_off_ > 0) {
                 cbuf_.erase(cbuf_.begin(), cbuf_.begin() + c_off_);
+                cbuf_base_ += c_off_;
                 c_off_ = 0;
             }
             size_t old = cbuf_.size();
@@ -102,7 +107,9 @@ int BamStream::produce(std::vector<uint8_t>& out) {
             if (got < kChunk) file_eof_ = true;
         }
         size_t o = c_off_;
+        bool at_stop = false;
         while (o + 18 <= cbuf_.size() && out_off < kMaxOut) {
+            if (stop_coff_ && cbuf_base_ + o > stop_coff_) { at_stop = true; break; }  // behind the region's contig
             const uint8_t* h = cbuf_.data() + o;
             if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) return fail("corrupt BGZF block header");
             int xlen = le16(h + 10);
@@ -126,12 +133,14 @@ int BamStream::produce(std::vector<uint8_t>& out) {
             j.u_off = out_off;
             j.u_len = isize;
             if (isize) jobs.push_back(j);
+            pos.push_back(BlkPos{(int64_t)out_off, cbuf_base_ + o});
             out_off += isize;
             o += bsize + 1;
         }
         const bool progressed = o != c_off_;
         c_off_ = o;
         if (!jobs.empty()) break;
+        if (at_stop) { t_decode_ += now_seconds() - t0; return 0; }
         if (file_eof_) {
             if (c_off_ >= cbuf_.size()) { t_decode_ += now_seconds() - t0; return 0; }  // every byte of the file was a whole block
             // bytes that do not make a whole block: the file was cut (htslib: "truncated file")
@@ -139,7 +148,7 @@ int BamStream::produce(std::vector<uint8_t>& out) {
             continue;
         }
         // a block larger than what is buffered cannot happen (blocks are <= 64 KiB); only empty blocks so far: read on
-        if (!progressed && cbuf_.size() - c_off_ >= (1u << 20)) return fail("BGZF framing error");
+        if (!progressed && cbuf_.size() - c_off_ >= (128u << 10)) return fail("BGZF framing error");
     }
     out.resize(out_off);
     int nt = std::max(1, std::min<int>(threads_, (int)jobs.size() / 4 + 1));
@@ -177,6 +186,7 @@ int BamStream::produce(std::vector<uint8_t>& out) {
     }
     for (int s : status)
         if (s) return fail(s == -2 ? "BGZF block CRC32 mismatch" : "inflate failed (corrupt BGZF block)");
+    n_inflated_ += (int64_t)out_off;
     t_decode_ += now_seconds() - t0;
     return 1;
 }
@@ -190,13 +200,25 @@ bool BamStream::fill() {
         rc = pf_.get();
         t_wait_ += now_seconds() - tw;
         grp.swap(pf_buf_);
+        grp_blk_.swap(pf_blk_);
     } else {
-        rc = produce(grp);
+        rc = produce(grp, grp_blk_);
     }
     if (rc < 0) { failed_ = true; set_error("%s", error().c_str()); }
     if (rc <= 0) { drained_ = true; return false; }
     // keep the unread tail of the previous group (a record can straddle two groups) in front of the new bytes
     const size_t leftover = ubuf_.size() - u_off_;
+    {
+        // block positions relative to the new ubuf_: the blocks the unread tail still lies in keep their (now possibly
+        // negative) start, the new group's blocks follow behind the tail
+        std::vector<BlkPos> keep;
+        for (size_t i = 0; i < blk_.size(); ++i) {
+            const int64_t nxt = i + 1 < blk_.size() ? blk_[i + 1].u_off : (int64_t)ubuf_.size();
+            if (leftover > 0 && nxt > (int64_t)u_off_) keep.push_back(BlkPos{blk_[i].u_off - (int64_t)u_off_, blk_[i].c_off});
+        }
+        for (const BlkPos& b : grp_blk_) keep.push_back(BlkPos{b.u_off + (int64_t)leftover, b.c_off});
+        blk_.swap(keep);
+    }
     if (leftover == 0) {
         ubuf_.swap(grp);
     } else {
@@ -206,8 +228,43 @@ bool BamStream::fill() {
     }
     u_off_ = 0;
     // the next group is inflated while the caller parses this one
-    if (!light_) pf_ = std::async(std::launch::async, [this]() { return produce(pf_buf_); });
+    // (not with a jump list: the next seek would throw the work away)
+    if (!light_ && !small_groups_) pf_ = std::async(std::launch::async, [this]() { return produce(pf_buf_, pf_blk_); });
     return true;
+}
+
+uint64_t BamStream::tell() const {
+    // bgzf_tell: compressed offset of the block the byte lies in << 16 | offset inside the inflated block
+    const int64_t u = (int64_t)u_off_;
+    size_t lo = 0, hi = blk_.size();
+    while (lo < hi) {  // last block with u_off <= u
+        const size_t mid = (lo + hi) >> 1;
+        if (blk_[mid].u_off <= u) lo = mid + 1; else hi = mid;
+    }
+    if (lo == 0) return 0;
+    return (blk_[lo - 1].c_off << 16) | (uint64_t)(u - blk_[lo - 1].u_off);
+}
+
+bool BamStream::seek_voffset(uint64_t v) {
+    if (pf_.valid()) pf_.get();  // the prefetch task owns fp_ and the compressed buffer
+    pf_buf_.clear();
+    pf_blk_.clear();
+    drained_ = false;
+    if (fseek(fp_, (long)(v >> 16), SEEK_SET) != 0) { failed_ = true; fail("seek failed"); return false; }
+    cbuf_.clear(); c_off_ = 0; file_eof_ = false;
+    cbuf_base_ = v >> 16;
+    ubuf_.clear(); u_off_ = 0;
+    blk_.clear();
+    ++n_seeks_;
+    if (!fill()) return false;
+    u_off_ = (size_t)(v & 0xffff);
+    return true;
+}
+
+void BamStream::set_jumps(const std::vector<std::pair<int32_t, int32_t>>& intervals) {
+    jumps_ = intervals;
+    jk_ = 0;
+    small_groups_ = jumps_.size() > 1;
 }
 
 bool BamStream::need(size_t n) {
@@ -274,7 +331,7 @@ bool BamStream::set_region(const char* bai_path, int tid, int beg, int end) {
         int n_bin = (int)le32(d.data() + o);
         o += 4;
         if (n_bin < 0) { bad = true; break; }
-        uint64_t min_chunk = UINT64_MAX;
+        uint64_t min_chunk = UINT64_MAX, max_chunk_end = 0;
         for (int b = 0; b < n_bin; ++b) {
             if (!room(8)) { bad = true; break; }
             uint32_t bin = le32(d.data() + o);
@@ -284,6 +341,7 @@ bool BamStream::set_region(const char* bai_path, int tid, int beg, int end) {
             for (int c = 0; c < n_chunk; ++c) {
                 uint64_t cb = le64(d.data() + o);
                 if (bin != 37450 && cb < min_chunk) min_chunk = cb;
+                if (bin != 37450) max_chunk_end = std::max<uint64_t>(max_chunk_end, le64(d.data() + o + 8));
                 o += 16;
             }
         }
@@ -302,6 +360,11 @@ bool BamStream::set_region(const char* bai_path, int tid, int beg, int end) {
             if (v == 0 && min_chunk != UINT64_MAX) v = min_chunk;
             voff = v;
             found = v != 0;
+            lin_.resize((size_t)n_intv);
+            for (int k = 0; k < n_intv; ++k) lin_[k] = le64(d.data() + o + 8L * k);
+            // no record of this contig lies in a block behind the end of its last chunk: the stream stops reading there
+            // instead of inflating into the next contig
+            stop_coff_ = max_chunk_end ? (max_chunk_end >> 16) : 0;
             break;
         }
         o += 8L * n_intv;
@@ -309,14 +372,12 @@ bool BamStream::set_region(const char* bai_path, int tid, int beg, int end) {
     if (bad) { set_error("corrupt BAI index %s", bai_path); return false; }
     light_ = false;
     if (!found) { region_done_ = true; return true; }  // no alignments on that contig
-    if (pf_.valid()) pf_.get();  // the prefetch started after the header holds bytes from the wrong place
-    pf_buf_.clear();
-    drained_ = false;
-    if (fseek(fp_, (long)(voff >> 16), SEEK_SET) != 0) return false;
-    cbuf_.clear(); c_off_ = 0; file_eof_ = false;
-    ubuf_.clear(); u_off_ = 0;
-    if (!fill()) { region_done_ = true; return true; }
-    u_off_ = (size_t)(voff & 0xffff);
+    // (a prefetch started after the header holds bytes from the wrong place: seek_voffset drops it)
+    if (!seek_voffset(voff)) {
+        if (failed_) return false;
+        region_done_ = true;
+    }
+    --n_seeks_;  // the positioning of a region is not a jump
     return true;
 }
 
@@ -369,6 +430,23 @@ int BamStream::next(BamRecView& r) {
             }
             if ((r.flag & 4) || r.n_cigar == 0 || rlen == 0) rlen = 1;
             if (r.pos + rlen <= r_beg_) continue;
+            if (!jumps_.empty()) {
+                while (jk_ < jumps_.size() && jumps_[jk_].second <= r.pos) ++jk_;  // intervals this record starts behind
+                if (jk_ == jumps_.size()) { region_done_ = true; return -1; }
+                if (r.pos + rlen <= jumps_[jk_].first) {
+                    // The record lies in the gap in front of the next interval. The linear index gives the offset of
+                    // the first record that reaches the 16 kb window the interval starts in; go there if that is well
+                    // ahead of where the stream stands (never backwards: what lies between is unread, nothing repeats).
+                    const size_t w = (size_t)(jumps_[jk_].first >> 14);
+                    uint64_t v = w < lin_.size() ? lin_[w] : 0;
+                    for (size_t k = w; v == 0 && k + 1 < lin_.size(); ) v = lin_[++k];  // windows without records
+                    const uint64_t here = tell();
+                    if (v != 0 && (v >> 16) > (here >> 16) + (192u << 10)) {
+                        if (!seek_voffset(v)) { if (failed_) return -2; region_done_ = true; return -1; }
+                    }
+                    continue;
+                }
+            }
         }
         return 0;
     }
@@ -598,7 +676,8 @@ Ingest::~Ingest() {
     for (auto* f : files_) delete f;
 }
 
-bool Ingest::open(const char* const* paths, const char* const* indexes, int threads, const char* region) {
+bool Ingest::open(const char* const* paths, const char* const* indexes, int threads, const char* region,
+                  const std::vector<std::pair<int32_t, int32_t>>* jumps) {
     if (threads <= 0) threads = usable_cpus();
     if (threads <= 0) threads = 4;
     for (int i = 0; i < conf_.n_files; ++i) {
@@ -616,12 +695,20 @@ bool Ingest::open(const char* const* paths, const char* const* indexes, int thre
         if (tid < 0) { set_error("fail to parse region '%s'", region); return false; }
         has_region_ = true;
         reg_tid_ = tid; reg_beg_ = rb; reg_end_ = re;
+        int seek_beg = rb, seek_end = re;
+        if (jumps && !jumps->empty()) {
+            // a site / region list on this contig: small inflate groups from the start, and the stream is positioned at
+            // the first interval, not at the start of the contig (rows still come from [reg_beg_, reg_end_) only)
+            for (auto* f : files_) f->bs.set_jumps(*jumps);
+            seek_beg = std::max(rb, (int)jumps->front().first);
+            seek_end = std::min(re, (int)jumps->back().second);
+        }
         for (int i = 0; i < conf_.n_files; ++i) {
             std::string bai = (indexes && indexes[i]) ? indexes[i] : std::string(paths[i]) + ".bai";
             // each file resolves the name in its own header, like sam_itr_querys
             int ftid = files_[i]->bs.name2tid(tid < (int)names().size() ? names()[tid] : "");
             if (ftid < 0) { set_error("fail to parse region '%s' with %s", region, paths[i]); return false; }
-            if (!files_[i]->bs.set_region(bai.c_str(), ftid, rb, re)) return false;
+            if (!files_[i]->bs.set_region(bai.c_str(), ftid, seek_beg, seek_end)) return false;
         }
     }
     return true;
@@ -656,6 +743,55 @@ int64_t Ingest::aligned_bases() const {
     int64_t n = 0;
     for (auto* f : files_) n += f->n_aligned_bases;
     return n;
+}
+int64_t Ingest::inflated_bytes() const {
+    int64_t n = 0;
+    for (auto* f : files_) n += f->bs.inflated_bytes();
+    return n;
+}
+int64_t Ingest::seeks() const {
+    int64_t n = 0;
+    for (auto* f : files_) n += f->bs.seeks();
+    return n;
+}
+void Ingest::set_jumps(const std::vector<std::pair<int32_t, int32_t>>& intervals) {
+    if (!has_region_) return;  // the linear index of the region's contig is what the jumps go through
+    for (auto* f : files_) f->bs.set_jumps(intervals);
+}
+
+bool indexes_usable(const char* const* paths, const char* const* indexes, int n) {
+    for (int i = 0; i < n; ++i) {
+        std::string bai = (indexes && indexes[i]) ? indexes[i] : std::string(paths[i]) + ".bai";
+        FILE* fp = fopen(bai.c_str(), "rb");
+        char magic[4] = {0, 0, 0, 0};
+        const bool ok = fp && fread(magic, 1, 4, fp) == 4 && !memcmp(magic, "BAI\1", 4);
+        if (fp) fclose(fp);
+        if (!ok) return false;
+    }
+    return true;
+}
+
+// The intervals of one contig of a region index as a jump list: padded by one position on either side (the prefilter's
+// overlap test counts a read that ends where an interval starts, src/plp.c:56-60), neighbours closer than `gap` merged
+// (a seek only pays across a few index windows). Empty when the intervals cover so much of their span that streaming
+// is the better plan.
+std::vector<std::pair<int32_t, int32_t>> jump_intervals(const RegionIndex::Chr* c, int32_t gap) {
+    std::vector<std::pair<int32_t, int32_t>> out;
+    if (!c || c->beg.empty()) return out;
+    int64_t covered = 0;
+    for (size_t i = 0; i < c->beg.size(); ++i) {
+        const int32_t b = c->beg[i] > 0 ? c->beg[i] - 1 : 0, e = c->end[i] < INT32_MAX - 2 ? c->end[i] + 2 : INT32_MAX;
+        if (!out.empty() && b <= out.back().second + gap) out.back().second = std::max(out.back().second, e);
+        else out.emplace_back(b, e);
+    }
+    for (auto& iv : out) covered += (int64_t)iv.second - iv.first;
+    const int64_t span = (int64_t)out.back().second - out.front().first;
+    if (out.size() == 1 || covered * 2 > span) {
+        // dense list: one interval from the first to the last site still saves the two ends of the contig
+        const std::pair<int32_t, int32_t> all(out.front().first, out.back().second);
+        out.assign(1, all);
+    }
+    return out;
 }
 
 // Reads the next record that survives the prefilter into fp.look. Returns false at EOF / error.

@@ -889,15 +889,12 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
     int hw = a->host_threads > 0 ? a->host_threads : raer::usable_cpus();
     if (hw <= 0) hw = 4;
     int n_workers = std::min<int>((int)names.size(), std::min(16, hw / (nf + 1)));
-    bool parallel = !a->region && a->shard_count <= 1 && n_workers >= 2 && !getenv("RAER_SERIAL_INGEST");
-    if (parallel)
-        for (int i = 0; i < nf && parallel; ++i) {  // every file needs its index for the seeks
-            std::string bai = (a->indexes && a->indexes[i]) ? a->indexes[i] : std::string(a->bampaths[i]) + ".bai";
-            FILE* fp = fopen(bai.c_str(), "rb");
-            char magic[4] = {0, 0, 0, 0};
-            if (!fp || fread(magic, 1, 4, fp) != 4 || memcmp(magic, "BAI\1", 4)) parallel = false;  // single stream: no index needed
-            if (fp) fclose(fp);
-        }
+    // a site / region list goes contig by contig through the index even with one worker: the streams skip what lies
+    // between the intervals (Ingest::set_jumps; src/plp.c:856-882 queries the index per region)
+    if (has_ridx && n_workers < 1) n_workers = 1;
+    bool parallel = !a->region && a->shard_count <= 1 && (n_workers >= 2 || (has_ridx && n_workers >= 1)) &&
+                    !getenv("RAER_SERIAL_INGEST");
+    if (parallel) parallel = raer::indexes_usable(a->bampaths, a->indexes, nf);  // single stream: no index needed
     if (parallel) {
         struct Slot {
             raer::PackedBatch pb;
@@ -938,7 +935,7 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
         // of every stream two threads (the host is slightly oversubscribed, which keeps every core busy)
         const int inflate_threads = std::min(4, std::max(2, (hw + n_workers * nf - 1) / (n_workers * nf)));
         double w_decode = 0, w_pack = 0;
-        int64_t w_records = 0, w_bases = 0;
+        int64_t w_records = 0, w_bases = 0, w_inflated = 0, w_seeks = 0;
         auto worker = [&](int w) {
             int my_rc = RAER_OK;
             while (my_rc == RAER_OK) {
@@ -951,7 +948,9 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
                     if (stop) break;
                 }
                 raer::Ingest wi(icw);
-                if (!wi.open(a->bampaths, a->indexes, inflate_threads, names[c].c_str())) { my_rc = RAER_ERR_IO; break; }
+                std::vector<std::pair<int32_t, int32_t>> jl;
+                if (has_ridx) jl = raer::jump_intervals(ridx.find(names[c]));
+                if (!wi.open(a->bampaths, a->indexes, inflate_threads, names[c].c_str(), has_ridx ? &jl : nullptr)) { my_rc = RAER_ERR_IO; break; }
                 std::shared_ptr<std::string> ref;
                 while (my_rc == RAER_OK && wi.next_contig() >= 0) {
                     if (!ref) {
@@ -987,6 +986,7 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
                 std::lock_guard<std::mutex> lk(mu);
                 w_decode += wi.decode_seconds(); w_pack += wi.pack_seconds();
                 w_records += wi.records(); w_bases += wi.aligned_bases();
+                w_inflated += wi.inflated_bytes(); w_seeks += wi.seeks();
             }
             std::lock_guard<std::mutex> lk(mu);
             if (my_rc != RAER_OK && worker_rc == RAER_OK) {
@@ -1081,6 +1081,8 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
         out->t_pack = w_pack;
         out->n_records = w_records;
         out->n_aligned_bases = w_bases;
+        out->n_inflated_bytes = w_inflated;
+        out->n_seeks = w_seeks;
     } else {
         raer::PackedBatch pb;
         int tid;
@@ -1126,6 +1128,8 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
         out->t_pack = ing.pack_seconds();
         out->n_records = ing.records();
         out->n_aligned_bases = ing.aligned_bases();
+        out->n_inflated_bytes = ing.inflated_bytes();
+        out->n_seeks = ing.seeks();
     }
     // compact the [file][row] stride to nrows
     if (sink.cap != out->nrows && out->nrows > 0) {
@@ -1153,7 +1157,7 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
 // reads counted once per batch), mate pairs, CIGAR words, packed sequence bytes, batches, aligned
 // bases of all mapped records, records read, distinct kept reads.
 extern "C" int raer_ingest_summary(const raer_pileup_args* a, int64_t target_reads, int64_t* out) {
-    memset(out, 0, 8 * sizeof(int64_t));
+    memset(out, 0, 16 * sizeof(int64_t));
     if (!a || a->nbam < 1 || a->nbam > RAER_MAX_FILES) return RAER_ERR_ARG;
     const int nf = a->nbam;
     raer::RegionIndex ridx;
@@ -1183,31 +1187,57 @@ extern "C" int raer_ingest_summary(const raer_pileup_args* a, int64_t target_rea
     if (a->umi_tag) { ic.bulk_umi = true; ic.umi_tag = a->umi_tag; }
     ic.regidx = has_ridx ? &ridx : nullptr;
     if (target_reads > 0) ic.target_reads = target_reads;
-    raer::Ingest ing(ic);
-    if (!ing.open(a->bampaths, a->indexes, a->host_threads, a->region)) return RAER_ERR_IO;
-    raer::PackedBatch pb;
-    int prev_boundary = 0;
-    while (ing.next_contig() >= 0) {
-        prev_boundary = INT_MIN;
-        while (ing.next_batch(pb)) {
-            if (a->poll && a->poll(a->poll_ctx)) { set_error("interrupted"); return RAER_ERR_INTERRUPT; }
-            out[0] += pb.b.n_reads;
-            out[1] += pb.b.n_pairs;
-            out[2] += pb.b.n_cigar_words;
-            out[3] += pb.b.n_sq_bytes;
-            out[4] += 1;
-            for (int64_t i = 0; i < pb.b.n_reads; ++i)
-                if (pb.hdr[i].pos >= prev_boundary) out[7] += 1;  // first appearance of the read
-            if (pb.b.n_reads) {
-                int mx = INT_MIN;
-                for (int64_t i = 0; i < pb.b.n_reads; ++i) mx = std::max(mx, (int)pb.hdr[i].pos);
-                prev_boundary = mx + 1 > prev_boundary ? mx + 1 : prev_boundary;
+    // one pass over `ing`: what raer_pileup() does with the batches, minus the device
+    auto drain = [&](raer::Ingest& ing) -> int {
+        raer::PackedBatch pb;
+        int prev_boundary = 0;
+        while (ing.next_contig() >= 0) {
+            prev_boundary = INT_MIN;
+            while (ing.next_batch(pb)) {
+                if (a->poll && a->poll(a->poll_ctx)) { set_error("interrupted"); return RAER_ERR_INTERRUPT; }
+                out[0] += pb.b.n_reads;
+                out[1] += pb.b.n_pairs;
+                out[2] += pb.b.n_cigar_words;
+                out[3] += pb.b.n_sq_bytes;
+                out[4] += 1;
+                for (int64_t i = 0; i < pb.b.n_reads; ++i)
+                    if (pb.hdr[i].pos >= prev_boundary) out[7] += 1;  // first appearance of the read
+                if (pb.b.n_reads) {
+                    int mx = INT_MIN;
+                    for (int64_t i = 0; i < pb.b.n_reads; ++i) mx = std::max(mx, (int)pb.hdr[i].pos);
+                    prev_boundary = mx + 1 > prev_boundary ? mx + 1 : prev_boundary;
+                }
             }
         }
+        out[5] += ing.aligned_bases();
+        out[6] += ing.records();
+        out[8] += ing.inflated_bytes();
+        out[9] += ing.seeks();
+        if (ing.failed()) { set_error("%s", ing.error().c_str()); return RAER_ERR_IO; }
+        return RAER_OK;
+    };
+    if (has_ridx && !a->region && raer::indexes_usable(a->bampaths, a->indexes, nf) && !getenv("RAER_SERIAL_INGEST")) {
+        // a site / region list: contig by contig through the index, skipping what lies between the intervals
+        raer::BamStream hs;
+        if (!hs.open(a->bampaths[0], 1, true)) return RAER_ERR_IO;
+        const std::vector<std::string> names = hs.names();
+        for (const std::string& nm : names) {
+            const raer::RegionIndex::Chr* rc = ridx.find(nm);
+            if (!rc) continue;
+            raer::Ingest ing(ic);
+            const std::vector<std::pair<int32_t, int32_t>> jl = raer::jump_intervals(rc);
+            if (!ing.open(a->bampaths, a->indexes, a->host_threads, nm.c_str(), &jl)) return RAER_ERR_IO;
+            int rc2 = drain(ing);
+            if (rc2) return rc2;
+        }
+        return RAER_OK;
     }
-    out[5] = ing.aligned_bases();
-    out[6] = ing.records();
-    if (ing.failed()) { set_error("%s", ing.error().c_str()); return RAER_ERR_IO; }
+    raer::Ingest ing(ic);
+    if (!ing.open(a->bampaths, a->indexes, a->host_threads, a->region)) return RAER_ERR_IO;
+    {
+        int rc2 = drain(ing);
+        if (rc2) return rc2;
+    }
     if (getenv("RAER_TIMING"))
         fprintf(stderr, "[raer ingest] parse sections %.3f s (of which the parsers waited %.3f s, summed over files, for inflate), "
                         "pack sections %.3f s, inflate tasks %.3f s summed over files\n",

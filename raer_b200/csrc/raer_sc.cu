@@ -722,57 +722,78 @@ static int sc_run(const raer_scpileup_args* a, bool want_files, raer_sc_triplets
             auto it = cbidx.find(a->barcodes[bi]);
             ic.fixed_cb = it == cbidx.end() ? 0 : it->second;
         }
-        raer::Ingest ing(ic);
         const char* one_bam[1] = {a->bampaths[bi]};
         const char* one_idx[1] = {a->indexes ? a->indexes[bi] : nullptr};
-        if (!ing.open(one_bam, one_idx, a->host_threads, a->region)) { rc = RAER_ERR_IO; break; }
-        const std::vector<std::string>& names = ing.names();
-        raer::PackedBatch pb;
-        int tid;
-        while (rc == RAER_OK && (tid = ing.next_contig()) >= 0) {
-            auto cit = by_chr.find(names[tid]);
-            const std::vector<int>* sites = cit == by_chr.end() ? nullptr : &cit->second;
-            const int ns = sites ? (int)sites->size() : 0;
-            std::vector<int32_t> sp(ns);
-            std::vector<uint8_t> ss(ns), sr(ns), sa(ns);
-            for (int k = 0; k < ns; ++k) {
-                const int s = (*sites)[k];
-                sp[k] = a->site_pos[s] - 1;
-                ss[k] = (uint8_t)a->site_strand[s];
-                sr[k] = (uint8_t)a->site_ref[s][0];
-                sa[k] = (uint8_t)a->site_alt[s][0];
-            }
-            conf.n_sites = ns;
-            conf.site_pos = sp.data(); conf.site_strand = ss.data(); conf.site_ref = sr.data(); conf.site_alt = sa.data();
-            while (rc == RAER_OK && ing.next_batch(pb)) {
-                const raer_read_batch& b = pb.b;
-                if (a->poll && a->poll(a->poll_ctx)) {  // the calling thread polls between batches (src/sc-plp.c:707-712)
-                    set_error("interrupted");
-                    rc = RAER_ERR_INTERRUPT;
-                    break;
+        // One pass over an opened ingest: its contigs, their sites, their batches.
+        auto drain = [&](raer::Ingest& ing) -> int {
+            int rc2 = RAER_OK;
+            const std::vector<std::string>& names = ing.names();
+            raer::PackedBatch pb;
+            int tid;
+            while (rc2 == RAER_OK && (tid = ing.next_contig()) >= 0) {
+                auto cit = by_chr.find(names[tid]);
+                const std::vector<int>* sites = cit == by_chr.end() ? nullptr : &cit->second;
+                const int ns = sites ? (int)sites->size() : 0;
+                std::vector<int32_t> sp(ns);
+                std::vector<uint8_t> ss(ns), sr(ns), sa(ns);
+                for (int k = 0; k < ns; ++k) {
+                    const int s = (*sites)[k];
+                    sp[k] = a->site_pos[s] - 1;
+                    ss[k] = (uint8_t)a->site_strand[s];
+                    sr[k] = (uint8_t)a->site_ref[s][0];
+                    sa[k] = (uint8_t)a->site_alt[s][0];
                 }
-                if (!ns || b.n_reads == 0 || b.end <= b.beg) continue;
-                conf.n_umi = (uint32_t)ing.umi_dict().size();
-                raer_sc_cells cells;
-                rc = raer_sc_batch_host(c, &conf, &b, &cells);
-                if (rc) break;
-                // site rule, src/sc-plp.c:586-596; the cells arrive sorted by (site, barcode)
-                for (int64_t i = 0; i < cells.n; ++i) {
-                    const int32_t* t = cells.cells + 4 * i;
-                    const int32_t* tt = cells.site_totals + 2 * t[0];
-                    if (!(min_counts == 0 || (tt[0] + tt[1] >= min_counts && tt[1] >= min_var_reads))) continue;
-                    if (fps.f[0]) fprintf(fps.f[0], "%d %d %d %d\n", a->site_idx[(*sites)[t[0]]], t[1], t[2], t[3]);
-                    if (trip_out) {
-                        mem_site.push_back(a->site_idx[(*sites)[t[0]]]); mem_cb.push_back(t[1]);
-                        mem_ref.push_back(t[2]); mem_alt.push_back(t[3]);
+                conf.n_sites = ns;
+                conf.site_pos = sp.data(); conf.site_strand = ss.data(); conf.site_ref = sr.data(); conf.site_alt = sa.data();
+                while (rc2 == RAER_OK && ing.next_batch(pb)) {
+                    const raer_read_batch& b = pb.b;
+                    if (a->poll && a->poll(a->poll_ctx)) {  // the calling thread polls between batches (src/sc-plp.c:707-712)
+                        set_error("interrupted");
+                        return RAER_ERR_INTERRUPT;
                     }
+                    if (!ns || b.n_reads == 0 || b.end <= b.beg) continue;
+                    conf.n_umi = (uint32_t)ing.umi_dict().size();
+                    raer_sc_cells cells;
+                    rc2 = raer_sc_batch_host(c, &conf, &b, &cells);
+                    if (rc2) break;
+                    // site rule, src/sc-plp.c:586-596; the cells arrive sorted by (site, barcode)
+                    for (int64_t i = 0; i < cells.n; ++i) {
+                        const int32_t* t = cells.cells + 4 * i;
+                        const int32_t* tt = cells.site_totals + 2 * t[0];
+                        if (!(min_counts == 0 || (tt[0] + tt[1] >= min_counts && tt[1] >= min_var_reads))) continue;
+                        if (fps.f[0]) fprintf(fps.f[0], "%d %d %d %d\n", a->site_idx[(*sites)[t[0]]], t[1], t[2], t[3]);
+                        if (trip_out) {
+                            mem_site.push_back(a->site_idx[(*sites)[t[0]]]); mem_cb.push_back(t[1]);
+                            mem_ref.push_back(t[2]); mem_alt.push_back(t[3]);
+                        }
+                    }
+                    raer_sc_cells_free(&cells);
                 }
-                raer_sc_cells_free(&cells);
             }
-        }
-        if (rc == RAER_OK && ing.failed()) {  // the stream stopped on an error, not at the end of the file
-            set_error("%s", ing.error().c_str());
-            rc = RAER_ERR_IO;
+            if (rc2 == RAER_OK && ing.failed()) {  // the stream stopped on an error, not at the end of the file
+                set_error("%s", ing.error().c_str());
+                rc2 = RAER_ERR_IO;
+            }
+            return rc2;
+        };
+        if (!a->region && raer::indexes_usable(one_bam, one_idx, 1) && !getenv("RAER_SERIAL_INGEST")) {
+            // the sites are a list of positions: contig by contig through the BAI index, skipping what lies between them
+            // (src/sc-plp.c:648-669 queries the index too)
+            raer::BamStream hs;
+            if (!hs.open(one_bam[0], 1, true)) { rc = RAER_ERR_IO; break; }
+            const std::vector<std::string> names = hs.names();
+            for (size_t ci = 0; ci < names.size() && rc == RAER_OK; ++ci) {
+                const raer::RegionIndex::Chr* rchr = ridx.find(names[ci]);
+                if (!rchr) continue;
+                const std::vector<std::pair<int32_t, int32_t>> jl = raer::jump_intervals(rchr);
+                raer::Ingest ing(ic);
+                if (!ing.open(one_bam, one_idx, a->host_threads, names[ci].c_str(), &jl)) { rc = RAER_ERR_IO; break; }
+                rc = drain(ing);
+            }
+        } else {
+            raer::Ingest ing(ic);
+            if (!ing.open(one_bam, one_idx, a->host_threads, a->region)) { rc = RAER_ERR_IO; break; }
+            rc = drain(ing);
         }
     }
     if (rc != RAER_OK) return rc < 0 ? rc : RAER_ERR;

@@ -32,7 +32,7 @@ def _summary(bam, fasta, region=None, index=None):
     a.lgl_args = (C.c_int32 * 2)(*[int(x) for x in pc.lgl_args])
     keep += [_cabi._ints(pc.libtype), _cabi._ints([int(x) for x in pc.only_keep_variants]), _cabi._ints(pc.min_mapq)]
     a.libtype, a.only_keep_variants, a.min_mapq = keep[-3:]
-    out = (C.c_int64 * 8)()
+    out = (C.c_int64 * 16)()
     rc = L.raer_ingest_summary(C.byref(a), 0, out)
     return rc, _cabi.last_error(), int(out[6])
 

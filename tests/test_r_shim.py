@@ -212,7 +212,7 @@ def test_poll_callback_stops_the_ingest(ext):
         return 1 if len(calls) >= 3 else 0
 
     a.poll = C.cast(poll, C.c_void_p)
-    out = (C.c_int64 * 8)()
+    out = (C.c_int64 * 16)()
     rc = L.raer_ingest_summary(C.byref(a), 40, out)  # 40 reads per batch: many batches
     assert rc == -8 and len(calls) == 3 and "interrupted" in _cabi.last_error()  # RAER_ERR_INTERRUPT
     a.poll = None
