@@ -745,6 +745,12 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
         set_error("invalid arguments"); return RAER_ERR_ARG;
     }
     if (a->nbam > RAER_MAX_FILES) { set_error("at most %d BAM files per call", RAER_MAX_FILES); return RAER_ERR_LIMIT; }
+    // documented limit, refused before any file or device work: the UMI shadows and the fused AEI reduction live in the
+    // fast tile kernels, whose byte-parallel quality compare handles thresholds up to 128
+    if ((a->umi_tag || a->aei_mode) && a->int_args[2] > 128) {
+        set_error("%s needs min_base_quality <= 128", a->umi_tag ? "umi_tag in pileup_sites" : "the fused AEI reduction");
+        return RAER_ERR_LIMIT;
+    }
     if (raer_device_count() <= 0) { set_error("no usable CUDA device (the product has no CPU path)"); return RAER_ERR_NO_DEVICE; }
     const int nf = a->nbam;
     out->nbam = nf;

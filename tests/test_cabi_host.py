@@ -184,3 +184,14 @@ def test_ingest_mate_pairs(ext):
         prev_pos, prev_tid = r.pos, r.tid
     assert s["pairs"] == pairs
     assert pairs > 40
+
+
+def test_documented_limit_is_refused_before_any_work(ext):
+    """umi_tag / the fused AEI reduction with min_base_quality > 128: RAER_ERR_LIMIT up front, with or
+    without a device, instead of failing after the qualities were rewritten"""
+    pc = prepare_pileup_call(ext.bam1, ext.fasta, param=FilterParam(min_base_quality=200), umi_tag="UB")
+    with pytest.raises(_cabi.RaerError, match="needs min_base_quality <= 128"):
+        _cabi.pileup(pc)
+    pc = prepare_pileup_call(ext.bam1, ext.fasta, param=FilterParam(min_base_quality=200))
+    with pytest.raises(_cabi.RaerError, match="needs min_base_quality <= 128"):
+        _cabi.pileup(pc, aei=True)
