@@ -111,6 +111,8 @@ typedef struct raer_pileup_result {
     int64_t n_inflated_bytes; /* BGZF payload inflated by the call, all files (drops when a site list lets the ingest skip
                                  through the BAI index) */
     int64_t n_seeks;          /* index jumps taken between the intervals of a site / region list */
+    int64_t n_device_contigs; /* contigs whose BGZF blocks were inflated, parsed and packed by kernels (raer_gingest.cu) */
+    int64_t n_host_contigs;   /* contigs the device ingest handed back to the host stream (device ingest) */
 } raer_pileup_result;
 
 int raer_pileup(const raer_pileup_args* args, raer_pileup_result* out);
@@ -352,6 +354,18 @@ int64_t raer_sc_algorithmic_bytes(const raer_read_batch* b, int64_t n_cells);
 int raer_ingest_summary(const raer_pileup_args* args, int64_t target_reads, int64_t* out);
 /* seconds spent in H2D copies, kernels and D2H copies by the last raer_batch_pileup_host() call */
 void raer_ctx_last_timing(raer_ctx* ctx, double* h2d_s, double* kernel_s, double* d2h_s);
+
+
+/* Device DEFLATE decoder used by the device ingest (one warp per BGZF block), exposed for tests and measurements:
+ * n_blocks raw DEFLATE payloads at comp + c_off[i] (c_len[i] bytes, host memory) are inflated to out + u_off[i]
+ * (u_len[i] bytes expected, host memory). status[i] = 0 or a negative decoder code (bad block type, bad code lengths,
+ * distance too far, output length mismatch ...). Replaces what htslib's bgzf_read_block / zlib inflate do per block under
+ * sam_itr_next (reference: src/plp.c:32-78 readaln -> sam_itr_next / sam_read1). */
+int raer_gpu_inflate(const uint8_t* comp, int64_t comp_len, const int64_t* c_off, const int32_t* c_len, const int64_t* u_off,
+                     const int32_t* u_len, int32_t n_blocks, uint8_t* out, int64_t out_len, int32_t* status, double* kernel_ms);
+/* same batch entry as raer_batch_pileup_device(), rows downloaded (what the device ingest calls per contig) */
+int raer_batch_pileup_device_rows(raer_ctx* ctx, const raer_bulk_conf* conf, const raer_read_batch* dev_batch, raer_rows* out,
+                                  int64_t* launches);
 
 #ifdef __cplusplus
 }

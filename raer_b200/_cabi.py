@@ -83,6 +83,8 @@ class PileupResult(C.Structure):
         ("aei", C.POINTER(C.c_int64)),
         ("n_inflated_bytes", C.c_int64),
         ("n_seeks", C.c_int64),
+        ("n_device_contigs", C.c_int64),
+        ("n_host_contigs", C.c_int64),
     ]
 
 
@@ -345,7 +347,8 @@ def pileup(pc, device: int = 0, host_threads: int = 0, overlap_mode: int = 1, sh
         LAST_TIMING.update(dict(t_decode=r.t_decode, t_pack=r.t_pack, t_h2d=r.t_h2d, t_kernel=r.t_kernel,
                                 t_d2h=r.t_d2h, t_total=r.t_total, n_records=int(r.n_records),
                                 n_aligned_bases=int(r.n_aligned_bases), gpu_launches=int(r.gpu_launches),
-                                n_inflated_bytes=int(r.n_inflated_bytes), n_seeks=int(r.n_seeks)))
+                                n_inflated_bytes=int(r.n_inflated_bytes), n_seeks=int(r.n_seeks),
+                                n_device_contigs=int(r.n_device_contigs), n_host_contigs=int(r.n_host_contigs)))
         out["timing"] = dict(LAST_TIMING)
         if aei and r.aei:
             out["aei"] = np.ctypeslib.as_array(r.aei, shape=(n, 4, 4)).astype(np.int64, copy=True)
@@ -439,3 +442,30 @@ def fisher_exact(mat: np.ndarray) -> np.ndarray:
     lib().raer_fisher_exact(flat.ctypes.data_as(C.POINTER(C.c_int32)), mat.shape[1],
                             out.ctypes.data_as(C.POINTER(C.c_double)))
     return out
+
+
+def gpu_inflate(payloads, sizes):
+    """Test / bench entry of the device DEFLATE decoder (raer_ginflate.cuh): raw DEFLATE `payloads` (bytes objects) of
+    known inflated `sizes` -> (list of inflated bytes, status array, kernel milliseconds)."""
+    L = lib()
+    n = len(payloads)
+    c_len = np.array([len(p) for p in payloads], dtype=np.int32)
+    c_off = np.zeros(n, dtype=np.int64)
+    c_off[1:] = np.cumsum(c_len[:-1], dtype=np.int64)
+    u_len = np.asarray(sizes, dtype=np.int32)
+    u_off = np.zeros(n, dtype=np.int64)
+    u_off[1:] = np.cumsum(u_len[:-1], dtype=np.int64)
+    comp = np.frombuffer(b"".join(payloads) + b"\0" * 8, dtype=np.uint8)
+    out_len = int(u_len.sum())
+    out = np.zeros(out_len + 8, dtype=np.uint8)
+    status = np.zeros(n, dtype=np.int32)
+    ms = C.c_double(0)
+    L.raer_gpu_inflate.restype = C.c_int
+    L.raer_gpu_inflate.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                   C.c_int64, C.c_void_p, C.POINTER(C.c_double)]
+    rc = L.raer_gpu_inflate(comp.ctypes.data, len(comp) - 8, c_off.ctypes.data, c_len.ctypes.data, u_off.ctypes.data,
+                            u_len.ctypes.data, n, out.ctypes.data, out_len, status.ctypes.data, C.byref(ms))
+    if rc != 0:
+        raise RaerError(last_error())
+    res = [out[int(u_off[i]):int(u_off[i]) + int(u_len[i])].tobytes() for i in range(n)]
+    return res, status, ms.value

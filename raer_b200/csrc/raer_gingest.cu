@@ -1,0 +1,967 @@
+// raer_gingest.cu -- BGZF/BAM ingest on the device: what the reference gets from htslib's
+// sam_read1 + readaln() (src/plp.c:32-78) + the stream-order parts of bam_plp_push / overlap_push, for one contig of
+// one BAM file at a time, without the inflated bytes ever visiting the host:
+//
+//   host   reads the compressed byte range of the contig (BAI: first chunk begin .. last chunk end), walks the BGZF
+//          block headers (18 bytes each) and turns the linear index of the contig into record-aligned start points
+//   k_gi_inflate   one warp per BGZF block: raw DEFLATE into one contiguous buffer of inflated records (raer_ginflate.cuh)
+//   k_gw_*         one thread per start point chains through block_size fields: record offsets, in file order
+//   k_gp_pass      one thread per record: the read-level prefilter of readaln (flags, region / site bitmap, mapq,
+//                  paired-not-proper, read_bqual), reference span and aligned bases from the CIGAR
+//   k_gp_kept      bam_plp_push's "can still produce a column" rule against the previous pushed read; sizes of what the
+//                  read will occupy in the batch; sort-order and max_depth guards
+//   k_gp_write     struct-of-arrays read batch (raer_read_hdr, CIGAR words, 4-bit sequence, qualities) written in place
+//   k_gp_pair      overlap_push: reads sharing a name meet through a sort of the name hashes; every name's records are
+//                  replayed in file order against the one-entry-per-name table htslib keeps
+// Exclusive scans between the stages keep everything in file (= coordinate) order. Anything this path does not cover
+// (bulk UMI mode, the MD mismatch filter, reads longer than 65535, a contig whose depth could reach max_depth, hash
+// collisions between different names) is reported as RAER_GI_FALLBACK and the caller streams that contig on the host.
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "raer_dev.h"
+#include "raer_host.h"
+#include "raer_ginflate.cuh"
+#include "raer_radix.cuh"
+
+using raer::set_error;
+
+#define GCK(call)                                                                             \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            set_error("CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__);  \
+            return RAER_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+#define RAER_GI_FALLBACK 1  // not an error: this contig goes through the host ingest
+
+// ------------------------------------------------------------------------------------- scans
+#define SC_BLOCK 256
+#define SC_ITEMS 16
+template <bool MAX>
+__global__ void k_sc_sum(const uint32_t* __restrict__ in, long long n, uint32_t* __restrict__ bsum) {
+    __shared__ uint32_t s[SC_BLOCK / 32];
+    const long long base = (long long)blockIdx.x * SC_BLOCK * SC_ITEMS + (long long)threadIdx.x * SC_ITEMS;
+    uint32_t v = 0;
+    for (int k = 0; k < SC_ITEMS; ++k)
+        if (base + k < n) v = MAX ? max(v, in[base + k]) : v + in[base + k];
+    v = MAX ? __reduce_max_sync(0xffffffffu, v) : __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < SC_BLOCK / 32; ++w) t = MAX ? max(t, s[w]) : t + s[w];
+        bsum[blockIdx.x] = t;
+    }
+}
+// exclusive scan (sum) or running maximum of the block values in place, one CTA; *total = sum / maximum of all
+template <bool MAX>
+__global__ void k_sc_top(uint32_t* bsum, int nb, unsigned long long* total) {
+    __shared__ uint32_t part[256];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 256) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < nb ? bsum[i] : 0;
+        part[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {
+            const uint32_t t = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+            __syncthreads();
+            part[threadIdx.x] = MAX ? max(part[threadIdx.x], t) : part[threadIdx.x] + t;
+            __syncthreads();
+        }
+        const uint32_t inc = part[threadIdx.x];
+        // exclusive value: everything before this block
+        const uint32_t before = threadIdx.x ? part[threadIdx.x - 1] : 0;
+        if (i < nb) bsum[i] = MAX ? max(carry, before) : carry + before;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = MAX ? max(carry, inc) : carry + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+// out[i] = exclusive sum / inclusive running maximum
+template <bool MAX>
+__global__ void k_sc_apply(const uint32_t* __restrict__ in, long long n, const uint32_t* __restrict__ bsum, uint32_t* __restrict__ out) {
+    __shared__ uint32_t part[SC_BLOCK];
+    const long long base = (long long)blockIdx.x * SC_BLOCK * SC_ITEMS + (long long)threadIdx.x * SC_ITEMS;
+    uint32_t v = 0;
+    for (int k = 0; k < SC_ITEMS; ++k)
+        if (base + k < n) v = MAX ? max(v, in[base + k]) : v + in[base + k];
+    part[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < SC_BLOCK; o <<= 1) {
+        const uint32_t t = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] = MAX ? max(part[threadIdx.x], t) : part[threadIdx.x] + t;
+        __syncthreads();
+    }
+    const uint32_t before_t = threadIdx.x ? part[threadIdx.x - 1] : 0;
+    uint32_t run = MAX ? max(bsum[blockIdx.x], before_t) : bsum[blockIdx.x] + before_t;
+    for (int k = 0; k < SC_ITEMS; ++k) {
+        const long long i = base + k;
+        if (i >= n) break;
+        const uint32_t x = in[i];
+        if (MAX) { run = max(run, x); out[i] = run; }
+        else { out[i] = run; run += x; }
+    }
+}
+
+// ------------------------------------------------------------------------------------- records
+__device__ __forceinline__ uint32_t ld32u(const uint8_t* p) {  // unaligned little-endian load
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+__device__ __forceinline__ uint32_t ld16u(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+
+// start point k chains through the records that begin in [sp[k], sp[k + 1]); FILL writes their offsets
+template <bool FILL>
+__global__ void k_gw_walk(const uint8_t* __restrict__ ub, unsigned long long total, const unsigned long long* __restrict__ sp, int nsp,
+                          uint32_t* cnt, const uint32_t* __restrict__ base, uint32_t* __restrict__ rec_off, int* flags) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nsp) return;
+    unsigned long long off = sp[k];
+    const unsigned long long end = sp[k + 1];
+    uint32_t n = 0;
+    const uint32_t b0 = FILL ? base[k] : 0;
+    while (off < end) {
+        if (off + 36 > total) { atomicOr(flags, 1); break; }  // a record header does not fit: corrupt or truncated
+        const uint32_t bs = ld32u(ub + off);
+        if (bs < 32 || off + 4 + bs > total) { atomicOr(flags, 1); break; }
+        if (FILL) rec_off[b0 + n] = (uint32_t)off;
+        ++n;
+        off += 4ull + bs;
+    }
+    if (!FILL) cnt[k] = n;
+}
+
+struct GpConf {
+    int tid;                 // contig of this pass (the file's own numbering)
+    uint32_t keep0, keep1;   // scanBamFlag masks
+    int min_global_mq;
+    int rq_minq;
+    float rq_pct;
+    int has_rq;
+    int libtype;
+    int remove_overlaps;
+    int min_overhang;
+    int max_depth;
+    // positions some interval of the call's region list covers, as a bitmap over the contig + the number of set bits in
+    // front of every word (a read is kept if [pos, endpos] holds a set bit: inclusive end, src/plp.c:56-60)
+    const uint32_t* site_bits;
+    const uint32_t* site_pre;
+    int site_len;
+};
+
+// per record: does it pass readaln? pos / end / aligned bases. One thread per record.
+__global__ void k_gp_pass(const uint8_t* __restrict__ ub, const uint32_t* __restrict__ rec_off, long long n_rec, GpConf C,
+                          uint32_t* __restrict__ pass, int32_t* __restrict__ r_pos, int32_t* __restrict__ r_end,
+                          unsigned long long* stats, int* flags) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_rec) return;
+    const uint8_t* p = ub + rec_off[i] + 4;
+    const int tid = (int)ld32u(p), pos = (int)ld32u(p + 4);
+    const int l_qname = p[8], mapq = p[9];
+    const int n_cigar = (int)ld16u(p + 12), flag = (int)ld16u(p + 14);
+    const int l_qseq = (int)ld32u(p + 16);
+    const uint32_t bs = ld32u(p - 4);
+    uint32_t ok = 1;
+    if (l_qseq < 0 || 32ull + l_qname + 4ull * n_cigar + ((unsigned long long)l_qseq + 1) / 2 + (unsigned long long)l_qseq > bs) {
+        atomicOr(flags, 1);  // corrupt record layout
+        pass[i] = 0; r_pos[i] = 0; r_end[i] = 0;
+        return;
+    }
+    if (tid != C.tid || (flag & 4)) ok = 0;  // another contig's record inside the byte range, or unmapped
+    int rlen = 0;
+    unsigned nal = 0;
+    const uint8_t* cg = p + 32 + l_qname;
+    for (int k = 0; k < n_cigar; ++k) {
+        const uint32_t w = ld32u(cg + 4 * k);
+        const int op = (int)(w & 0xf);
+        if ((0x3C1A7 >> (op << 1)) & 2) rlen += (int)(w >> 4);
+        if (op == 0 || op == 7 || op == 8) nal += (w >> 4);
+    }
+    {   // unit of the bench metric: aligned bases of every mapped record, before filters; longest reference span
+        const unsigned am = __activemask();
+        const unsigned tot = __reduce_add_sync(am, ok ? nal : 0u);
+        const unsigned mx = __reduce_max_sync(am, (unsigned)max(rlen, 1));
+        if ((int)(threadIdx.x & 31) == __ffs(am) - 1) {
+            if (tot) atomicAdd(&stats[0], (unsigned long long)tot);
+            atomicMax(&stats[1], (unsigned long long)mx);
+        }
+    }
+    const uint32_t test = (C.keep0 & ~(uint32_t)flag) | (C.keep1 & (uint32_t)flag);
+    if (~test & 2047u) ok = 0;
+    const int endpos = pos + ((n_cigar == 0 || rlen == 0) ? 1 : rlen);
+    if (ok && C.site_bits) {
+        // any listed position in [pos, endpos] (inclusive)?
+        const int lo = max(pos, 0), hi = min(endpos, C.site_len - 1);
+        bool hit = false;
+        if (lo <= hi) {
+            const int w0 = lo >> 5, w1 = hi >> 5;
+            const uint32_t m0 = 0xffffffffu << (lo & 31), m1 = 0xffffffffu >> (31 - (hi & 31));
+            if (w0 == w1) hit = (C.site_bits[w0] & m0 & m1) != 0;
+            else hit = (C.site_bits[w0] & m0) || (C.site_bits[w1] & m1) || (C.site_pre[w1] - C.site_pre[w0 + 1]) != 0;
+        }
+        if (!hit) ok = 0;
+    }
+    if (mapq < C.min_global_mq) ok = 0;
+    if ((flag & 1) && !(flag & 2)) ok = 0;
+    if (ok && C.has_rq) {  // read_base_quality (src/plp_utils.c:310-328): double ratio against a float threshold
+        if (!l_qseq) ok = 0;
+        else {
+            const uint8_t* q = cg + 4 * n_cigar + (l_qseq + 1) / 2;
+            int lq = 0;
+            for (int k = 0; k < l_qseq; ++k) lq += q[k] < C.rq_minq;
+            const double frac = (double)lq / l_qseq;
+            if (!(frac <= C.rq_pct)) ok = 0;
+        }
+    }
+    if (ok && (l_qseq > 65535 || n_cigar > 65535)) { atomicOr(flags, 2); ok = 0; }  // documented limit: host path reports it
+    pass[i] = ok;
+    r_pos[i] = pos;
+    r_end[i] = pos + rlen;
+}
+
+// positions of the passing reads in their own (compact) numbering: the "previous pushed read" of read P is P - 1
+__global__ void k_gp_cpos(const uint32_t* __restrict__ pass, const uint32_t* __restrict__ pidx, const int32_t* __restrict__ r_pos,
+                          long long n_rec, int32_t* __restrict__ cpos) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n_rec && pass[i]) cpos[pidx[i]] = r_pos[i];
+}
+
+// bam_plp_push keeps a read only if it can still produce a column (end > position of the previous pushed read);
+// sizes of the kept reads; guards
+__global__ void k_gp_kept(const uint8_t* __restrict__ ub, const uint32_t* __restrict__ rec_off, const uint32_t* __restrict__ pass,
+                          const uint32_t* __restrict__ pidx, const int32_t* __restrict__ r_pos, const int32_t* __restrict__ r_end,
+                          const int32_t* __restrict__ cpos, long long n_rec, long long n_pass, GpConf C, int max_span,
+                          uint32_t* __restrict__ kept, uint32_t* __restrict__ ncig, uint32_t* __restrict__ sqb,
+                          uint32_t* __restrict__ elig, int32_t* __restrict__ prevpos, int* flags) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_rec) return;
+    uint32_t k = 0, nc = 0, sb = 0, el = 0;
+    int pp = INT_MIN;
+    if (pass[i]) {
+        const long long P = pidx[i];
+        const int pos = r_pos[i], end = r_end[i];
+        pp = P > 0 ? cpos[P - 1] : INT_MIN;
+        if (P > 0 && pos < pp) atomicOr(flags, 4);  // htslib: "the input is not sorted"
+        k = (P == 0) || (end > pp);
+        // max_depth (bam_plp_push drops a read that starts where the previous one did once the buffer holds more than
+        // max_depth reads): reads still in the buffer all started within max_span positions in front of this one
+        if (P > 0 && pos == pp) {
+            long long lo = 0, hi = P;  // first passing read with position >= pos - max_span
+            const int from = pos - max_span;
+            while (lo < hi) {
+                const long long mid = (lo + hi) >> 1;
+                if (cpos[mid] < from) lo = mid + 1; else hi = mid;
+            }
+            if (P - lo + 1 > C.max_depth) atomicOr(flags, 8);  // cannot be ruled out here: the host replays the stream
+        }
+        if (k) {
+            const uint8_t* p = ub + rec_off[i] + 4;
+            const int flag = (int)ld16u(p + 14), l_qseq = (int)ld32u(p + 16);
+            nc = ld16u(p + 12);
+            sb = (uint32_t)((((l_qseq + 1) >> 1) + 3) & ~3);
+            if (C.remove_overlaps) {  // overlap_push: who takes part
+                const int mtid = (int)ld32u(p + 20), mpos = (int)ld32u(p + 24);
+                const int isz0 = (int)ld32u(p + 28);
+                const long long isz = isz0 < 0 ? -(long long)isz0 : isz0;
+                el = !(flag & 8) && (flag & 2);
+                if ((mtid >= 0 && C.tid != mtid) || (isz >= 2LL * l_qseq && mpos >= end)) el = 0;
+            }
+        }
+    }
+    kept[i] = k;
+    ncig[i] = nc;
+    sqb[i] = sb;
+    elig[i] = el;
+    prevpos[i] = pp;
+}
+
+__device__ __forceinline__ uint32_t x31_hash(const uint8_t* s) {  // khash __ac_X31_hash_string (htslib overlap hash)
+    uint32_t h = (uint32_t)(int)(signed char)*s;
+    if (h)
+        for (++s; *s; ++s) h = (h << 5) - h + (uint32_t)(int)(signed char)*s;
+    return h;
+}
+__device__ __forceinline__ uint32_t wang_hash(uint32_t key) {
+    key += ~(key << 15);
+    key ^= (key >> 10);
+    key += (key << 3);
+    key ^= (key >> 6);
+    key += ~(key << 11);
+    key ^= (key >> 16);
+    return key;
+}
+
+struct GpOut {  // the batch arrays (device), this file's first read / CIGAR word / sequence byte
+    raer_read_hdr* hdr;
+    uint32_t* cigar;
+    uint8_t* seq;
+    uint8_t* qual;
+    long long r0, c0, s0;
+};
+
+// one thread per kept record: header, CIGAR words, packed sequence, qualities; read-name hash of the reads that take
+// part in the mate-overlap pairing
+__global__ void k_gp_write(const uint8_t* __restrict__ ub, const uint32_t* __restrict__ rec_off, const uint32_t* __restrict__ kept,
+                           const uint32_t* __restrict__ kidx, const uint32_t* __restrict__ coff, const uint32_t* __restrict__ soff,
+                           const uint32_t* __restrict__ elig, const uint32_t* __restrict__ eidx, const int32_t* __restrict__ r_end,
+                           const int32_t* __restrict__ prevpos, long long n_rec, GpConf C, GpOut O,
+                           unsigned long long* __restrict__ pkey, uint32_t* __restrict__ pval, uint32_t* __restrict__ krec,
+                           int32_t* __restrict__ kprev) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_rec || !kept[i]) return;
+    const uint8_t* p = ub + rec_off[i] + 4;
+    const int pos = (int)ld32u(p + 4);
+    const int l_qname = p[8], mapq = p[9];
+    const int n_cigar = (int)ld16u(p + 12), flag = (int)ld16u(p + 14);
+    const int l_qseq = (int)ld32u(p + 16);
+    const uint8_t* cg = p + 32 + l_qname;
+    const uint8_t* sq = cg + 4 * n_cigar;
+    const uint8_t* ql = sq + ((l_qseq + 1) >> 1);
+    const uint32_t K = kidx[i];
+    int bits = 0;
+    {  // invert_read_orientation (src/plp_utils.c:331-371)
+        const int lt = C.libtype, rev = (flag & 16) != 0;
+        int inv = 0;
+        if (lt == 1 || lt == 2) {
+            int r1 = -1;
+            if (!(flag & 1)) r1 = 1;
+            else if (flag & 64) r1 = 1;
+            else if (flag & 128) r1 = 0;
+            if (r1 >= 0) {
+                const int when_rev = (lt == 2);
+                inv = r1 ? (rev == when_rev) : (rev != when_rev);
+            }
+        }
+        if (inv) bits |= RAER_RB_INVERT;
+    }
+    if (C.min_overhang && l_qseq >= 2 && (sq[0] & 0xf) == 3) bits |= RAER_RB_OHANG_N;
+    raer_read_hdr h;
+    h.pos = pos;
+    h.end = r_end[i];
+    h.flag = (uint16_t)flag;
+    h.mapq = (uint8_t)mapq;
+    h.bits = (uint8_t)bits;
+    h.l_qseq = (uint16_t)l_qseq;
+    h.n_cigar = (uint16_t)n_cigar;
+    h.cigar_off = (uint32_t)(O.c0 + coff[i]);
+    h.sq_off = (uint32_t)(O.s0 + soff[i]);
+    h.mate = -1;
+    h.aux = (uint32_t)(O.r0 + K);  // its own batch index, like the host packer (bulk UMI mode never comes here)
+    O.hdr[O.r0 + K] = h;
+    uint32_t* co = O.cigar + O.c0 + coff[i];
+    for (int k = 0; k < n_cigar; ++k) co[k] = ld32u(cg + 4 * k);
+    const int nsb = (l_qseq + 1) >> 1, padded = (nsb + 3) & ~3;
+    uint8_t* so = O.seq + O.s0 + soff[i];
+    for (int k = 0; k < nsb; ++k) so[k] = sq[k];
+    for (int k = nsb; k < padded; ++k) so[k] = 0xff;
+    uint8_t* qo = O.qual + 2 * (O.s0 + soff[i]);
+    for (int k = 0; k < l_qseq; ++k) qo[k] = ql[k];
+    for (int k = l_qseq; k < 2 * padded; ++k) qo[k] = 0;
+    krec[K] = rec_off[i];
+    kprev[K] = prevpos[i];
+    if (elig[i]) {
+        // 64-bit FNV-1a of the read name: the sort key under which the records of one name meet
+        unsigned long long hh = 1469598103934665603ull;
+        for (const uint8_t* q = p + 32; *q; ++q) { hh ^= *q; hh *= 1099511628211ull; }
+        pkey[eidx[i]] = hh ^ (hh >> 29);
+        pval[eidx[i]] = K;
+    }
+}
+
+// overlap_push (htslib): per read name one table entry at a time. The records of a name arrive here side by side
+// (sorted by name hash, stable: file order inside a name) and are replayed: a record that finds a live entry pairs
+// with it and deletes it; otherwise it becomes the entry if its mate lies ahead (mpos >= pos, or mpos == -1 of a
+// paired read). An entry is dead once its read has left the pileup buffer (end < position of the previous pushed read).
+__global__ void k_gp_pair(const unsigned long long* __restrict__ pkey, const uint32_t* __restrict__ pval, long long n,
+                          const uint8_t* __restrict__ ub, const uint32_t* __restrict__ krec, const int32_t* __restrict__ kprev,
+                          raer_read_hdr* hdr, long long r0, int32_t* __restrict__ pair_b, unsigned long long* n_pairs, int* flags) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const unsigned long long key = pkey[e];
+    if (e > 0 && pkey[e - 1] == key) return;  // not the head of its run
+    long long entry = -1;                     // kept index of the record waiting for its mate
+    for (long long j = e; j < n && pkey[j] == key; ++j) {
+        const uint32_t K = pval[j];
+        const uint8_t* p = ub + krec[K] + 4;
+        if (j > e) {  // same hash: must be the same name, else this is a collision the host has to sort out
+            const uint8_t* a = ub + krec[pval[e]] + 4 + 32;
+            const uint8_t* b = p + 32;
+            bool same = true;
+            for (int k = 0;; ++k) {
+                if (a[k] != b[k]) { same = false; break; }
+                if (!a[k]) break;
+            }
+            if (!same) { atomicOr(flags, 16); return; }
+        }
+        if (entry >= 0 && hdr[r0 + entry].end < kprev[K]) entry = -1;  // its read left the buffer before this one came
+        if (entry < 0) {
+            const int pos = (int)ld32u(p + 4), flag = (int)ld16u(p + 14), mpos = (int)ld32u(p + 24);
+            if (mpos >= pos || ((flag & 1) && mpos == -1)) entry = K;
+        } else {
+            raer_read_hdr* h = hdr + r0 + K;
+            h->mate = (int32_t)(r0 + entry);
+            // htslib >= 1.13: the earlier mate keeps its qualities iff Wang(X31(name)) & 1
+            if (wang_hash(x31_hash(ub + krec[entry] + 4 + 32)) & 1u) h->bits |= RAER_RB_KEEP_A;
+            pair_b[atomicAdd(n_pairs, 1ull)] = (int32_t)(r0 + K);
+            entry = -1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------- host side
+namespace {
+
+static inline uint32_t h_le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static inline uint64_t h_le64(const uint8_t* p) { return (uint64_t)h_le32(p) | ((uint64_t)h_le32(p + 4) << 32); }
+
+struct BaiRef {
+    uint64_t vbeg = 0, vend = 0;  // first chunk begin / last chunk end of the contig (0 / 0: no records)
+    std::vector<uint64_t> lin;
+};
+
+// the whole .bai: per reference the extent of its records in the file and its linear index
+static bool load_bai(const char* path, std::vector<BaiRef>& out) {
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return false;
+    fseek(fp, 0, SEEK_END);
+    const long sz = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    std::vector<uint8_t> d((size_t)std::max<long>(sz, 0));
+    const bool rd = sz >= 8 && fread(d.data(), 1, (size_t)sz, fp) == (size_t)sz;
+    fclose(fp);
+    if (!rd || memcmp(d.data(), "BAI\1", 4)) return false;
+    const int n_ref = (int)h_le32(d.data() + 4);
+    if (n_ref < 0) return false;
+    long o = 8;
+    auto room = [&](long bytes) { return bytes >= 0 && o >= 0 && o <= sz && bytes <= sz - o; };
+    out.assign((size_t)n_ref, BaiRef());
+    for (int t = 0; t < n_ref; ++t) {
+        if (!room(4)) return false;
+        const int n_bin = (int)h_le32(d.data() + o);
+        o += 4;
+        if (n_bin < 0) return false;
+        uint64_t vb = UINT64_MAX, ve = 0;
+        for (int b = 0; b < n_bin; ++b) {
+            if (!room(8)) return false;
+            const uint32_t bin = h_le32(d.data() + o);
+            const int n_chunk = (int)h_le32(d.data() + o + 4);
+            o += 8;
+            if (n_chunk < 0 || !room(16L * n_chunk)) return false;
+            for (int c = 0; c < n_chunk; ++c) {
+                if (bin != 37450) {
+                    vb = std::min(vb, h_le64(d.data() + o));
+                    ve = std::max(ve, h_le64(d.data() + o + 8));
+                }
+                o += 16;
+            }
+        }
+        if (!room(4)) return false;
+        const int n_intv = (int)h_le32(d.data() + o);
+        o += 4;
+        if (n_intv < 0 || !room(8L * n_intv)) return false;
+        BaiRef& R = out[(size_t)t];
+        if (vb != UINT64_MAX && ve > vb) { R.vbeg = vb; R.vend = ve; }
+        R.lin.resize((size_t)n_intv);
+        for (int k = 0; k < n_intv; ++k) R.lin[(size_t)k] = h_le64(d.data() + o + 8L * k);
+        o += 8L * n_intv;
+    }
+    return true;
+}
+
+struct DBufG {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap && p) return 0;
+        if (p) cudaFree(p);
+        const size_t want = n + n / 8 + 4096;
+        if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; cap = 0; cudaGetLastError(); set_error("cudaMalloc(%zu) failed", want); return RAER_ERR_CUDA; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    ~DBufG() { release(); }
+};
+
+struct PinnedBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t n) {
+        if (n <= cap) return true;
+        if (p) cudaFreeHost(p);
+        cap = n + n / 8 + 4096;
+        if (cudaHostAlloc((void**)&p, cap, cudaHostAllocDefault) != cudaSuccess) { p = nullptr; cap = 0; cudaGetLastError(); return false; }
+        return true;
+    }
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+};
+
+// everything one file contributes to the batch of a contig, still in its own buffers
+struct FileStage {
+    DBufG comp, blk, ubuf, status, sp, cnt, base, rec_off, pass, pidx, r_pos, r_end, cpos, kept, kidx, ncig, coff, sqb, soff, elig, eidx,
+        prevpos, bsum, krec, kprev, pkey, pval, pkey2, pval2, hist;
+    PinnedBuf hcomp;
+    long long n_rec = 0, n_pass = 0, n_kept = 0, n_cig = 0, n_sq = 0, n_elig = 0;
+    unsigned long long u_total = 0;
+    int64_t aligned_bases = 0;
+    int max_span = 0;
+};
+
+}  // namespace
+
+struct raer_gi {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    int nf = 0;
+    std::vector<FILE*> fp;
+    std::vector<std::vector<BaiRef>> bai;
+    std::vector<long long> fsize;
+    std::vector<FileStage> stage;
+    DBufG small, site_bits, site_pre, hdr, maxend, cigar, seq, qual, pair_b, endtmp;
+    unsigned long long* h_small = nullptr;  // pinned, 8 counters
+    int64_t launches = 0, inflated = 0, compressed = 0, records = 0;
+    double t_read = 0, t_inflate = 0;
+    ~raer_gi() {
+        for (FILE* f : fp) if (f) fclose(f);
+        if (h_small) cudaFreeHost(h_small);
+        if (st) cudaStreamDestroy(st);
+    }
+};
+
+extern "C" void raer_gi_destroy(raer_gi* g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    if (g->st) cudaStreamSynchronize(g->st);
+    delete g;
+}
+
+// opens the files and their indexes; nullptr (with the error set) if any index is missing or unreadable
+extern "C" raer_gi* raer_gi_create(int device, int nf, const char* const* paths, const char* const* indexes) {
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
+    raer_gi* g = new raer_gi();
+    g->device = device;
+    g->nf = nf;
+    g->stage.resize((size_t)nf);
+    g->bai.resize((size_t)nf);
+    for (int i = 0; i < nf; ++i) {
+        FILE* f = fopen(paths[i], "rb");
+        g->fp.push_back(f);
+        if (!f) { set_error("failed to open %s", paths[i]); delete g; return nullptr; }
+        fseek(f, 0, SEEK_END);
+        g->fsize.push_back(ftell(f));
+        const std::string bp = (indexes && indexes[i]) ? indexes[i] : std::string(paths[i]) + ".bai";
+        if (!load_bai(bp.c_str(), g->bai[(size_t)i])) { set_error("fail to load bamfile index %s", bp.c_str()); delete g; return nullptr; }
+    }
+    if (cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc((void**)&g->h_small, 64, cudaHostAllocDefault) != cudaSuccess) {
+        set_error("stream / pinned memory");
+        delete g;
+        return nullptr;
+    }
+    return g;
+}
+
+template <bool MAX>
+static int g_scan(raer_gi* g, FileStage& S, const uint32_t* in, uint32_t* out, long long n, unsigned long long* d_total) {
+    if (n <= 0) {
+        if (d_total) cudaMemsetAsync(d_total, 0, 8, g->st);
+        return 0;
+    }
+    const unsigned nb = (unsigned)((n + (long long)SC_BLOCK * SC_ITEMS - 1) / ((long long)SC_BLOCK * SC_ITEMS));
+    int rc = S.bsum.ensure((size_t)nb * 4 + 16);
+    if (rc) return rc;
+    k_sc_sum<MAX><<<nb, SC_BLOCK, 0, g->st>>>(in, n, (uint32_t*)S.bsum.p);
+    k_sc_top<MAX><<<1, 256, 0, g->st>>>((uint32_t*)S.bsum.p, (int)nb, d_total);
+    k_sc_apply<MAX><<<nb, SC_BLOCK, 0, g->st>>>(in, n, (const uint32_t*)S.bsum.p, out);
+    g->launches += 3;
+    return 0;
+}
+
+// Stage 1 for one file: compressed range -> inflated records -> record table -> prefilter -> kept reads and their sizes.
+// Returns RAER_OK, RAER_GI_FALLBACK or an error.
+static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
+    FileStage& S = g->stage[(size_t)f];
+    S.n_rec = S.n_pass = S.n_kept = S.n_cig = S.n_sq = S.n_elig = 0;
+    S.aligned_bases = 0;
+    S.u_total = 0;
+    if (ftid < 0 || ftid >= (int)g->bai[(size_t)f].size()) return RAER_OK;
+    const BaiRef& R = g->bai[(size_t)f][(size_t)ftid];
+    if (R.vend <= R.vbeg) return RAER_OK;  // no records of this contig in this file
+    cudaStream_t st = g->st;
+    int rc;
+    // ---- compressed bytes of the contig: from the block of the first record to the block its last record ends in
+    const long long c_beg = (long long)(R.vbeg >> 16);
+    long long c_last = (long long)(R.vend >> 16);
+    if ((R.vend & 0xffff) == 0) c_last -= 1;  // the range ends exactly where a block starts: that block is not needed
+    long long c_end = std::min<long long>(c_last + 65536 + 32, g->fsize[(size_t)f]);
+    if (c_end <= c_beg) return RAER_OK;
+    const size_t nbytes = (size_t)(c_end - c_beg);
+    const double t0 = raer::now_seconds();
+    if (!S.hcomp.ensure(nbytes + 64)) { set_error("pinned allocation of %zu bytes failed", nbytes); return RAER_ERR_CUDA; }
+    if (fseek(g->fp[(size_t)f], (long)c_beg, SEEK_SET) != 0 || fread(S.hcomp.p, 1, nbytes, g->fp[(size_t)f]) != nbytes) {
+        set_error("read error in BAM file");
+        return RAER_ERR_IO;
+    }
+    memset(S.hcomp.p + nbytes, 0, 64);
+    // ---- BGZF block table (18-byte headers chained through BSIZE)
+    std::vector<GiBlock> blocks;
+    std::vector<long long> blk_c;  // file offset of every block
+    unsigned long long u = 0;
+    size_t o = 0;
+    while (o + 18 <= nbytes && (long long)o + c_beg <= c_last) {
+        const uint8_t* h = S.hcomp.p + o;
+        if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { set_error("corrupt BGZF block header"); return RAER_ERR_IO; }
+        const int xlen = h[10] | (h[11] << 8);
+        if (o + 12 + (size_t)xlen > nbytes) { set_error("truncated BGZF file (incomplete block at the end)"); return RAER_ERR_IO; }
+        int bsize = -1;
+        for (int e = 0; e + 4 <= xlen;) {
+            const int slen = h[12 + e + 2] | (h[12 + e + 3] << 8);
+            if (h[12 + e] == 'B' && h[13 + e] == 'C' && slen == 2) bsize = h[12 + e + 4] | (h[12 + e + 5] << 8);
+            e += 4 + slen;
+        }
+        if (bsize < 0 || bsize + 1 < 12 + xlen + 2 + 8) { set_error("corrupt BGZF block (BSIZE)"); return RAER_ERR_IO; }
+        if (o + (size_t)bsize + 1 > nbytes) { set_error("truncated BGZF file (incomplete block at the end)"); return RAER_ERR_IO; }
+        const uint32_t isize = h_le32(h + bsize + 1 - 4);
+        if (isize > 65536u) { set_error("corrupt BGZF block (ISIZE above 64 KiB)"); return RAER_ERR_IO; }
+        GiBlock b;
+        b.c_off = o + 12 + (size_t)xlen;
+        b.c_len = (uint32_t)(bsize + 1 - 12 - xlen - 8);
+        b.u_off = u;
+        b.u_len = isize;
+        blocks.push_back(b);
+        blk_c.push_back(c_beg + (long long)o);
+        u += isize;
+        o += (size_t)bsize + 1;
+    }
+    if (blocks.empty()) return RAER_OK;
+    if (u >= (1ull << 32) - 65536) return RAER_GI_FALLBACK;  // record offsets are 32 bit here
+    S.u_total = u;
+    g->t_read += raer::now_seconds() - t0;
+    g->compressed += (int64_t)o;
+    g->inflated += (int64_t)u;
+    // ---- start points: the first record, and every linear-index entry inside the range, as inflated offsets
+    auto v2u = [&](uint64_t v, unsigned long long* out) -> bool {
+        const long long c = (long long)(v >> 16);
+        const size_t k = std::lower_bound(blk_c.begin(), blk_c.end(), c) - blk_c.begin();
+        if (k == blk_c.size() || blk_c[k] != c) {
+            if (k == blk_c.size() && (v & 0xffff) == 0 && c >= blk_c.back()) { *out = u; return true; }  // behind the last block
+            return false;
+        }
+        if ((v & 0xffff) > blocks[k].u_len) return false;
+        *out = blocks[k].u_off + (v & 0xffff);
+        return true;
+    };
+    std::vector<unsigned long long> sp;
+    unsigned long long u_first = 0, u_last = u;
+    if (!v2u(R.vbeg, &u_first)) return RAER_GI_FALLBACK;
+    if (!v2u(R.vend, &u_last)) u_last = u;
+    sp.push_back(u_first);
+    for (uint64_t v : R.lin) {
+        unsigned long long x;
+        if (v > R.vbeg && v < R.vend && v2u(v, &x) && x > u_first && x < u_last) sp.push_back(x);
+    }
+    std::sort(sp.begin(), sp.end());
+    sp.erase(std::unique(sp.begin(), sp.end()), sp.end());
+    const int nsp = (int)sp.size();
+    sp.push_back(u_last);
+    // ---- device: inflate
+    if ((rc = S.comp.ensure(nbytes + 64)) || (rc = S.blk.ensure(blocks.size() * sizeof(GiBlock))) || (rc = S.ubuf.ensure((size_t)u + 64)) ||
+        (rc = S.status.ensure(blocks.size() * 4)) || (rc = S.sp.ensure(sp.size() * 8)) || (rc = S.cnt.ensure((size_t)nsp * 4 + 16)) ||
+        (rc = S.base.ensure((size_t)nsp * 4 + 16)) || (rc = g->small.ensure(256)))
+        return rc;
+    GCK(cudaMemcpyAsync(S.comp.p, S.hcomp.p, nbytes + 64, cudaMemcpyHostToDevice, st));
+    GCK(cudaMemcpyAsync(S.blk.p, blocks.data(), blocks.size() * sizeof(GiBlock), cudaMemcpyHostToDevice, st));
+    GCK(cudaMemcpyAsync(S.sp.p, sp.data(), sp.size() * 8, cudaMemcpyHostToDevice, st));
+    GCK(cudaMemsetAsync(g->small.p, 0, 256, st));
+    unsigned long long* d_small = (unsigned long long*)g->small.p;  // [0] queue, [1] flags, [2] aligned bases, [3] max span, [4..] totals
+    {
+        static int n_sm = 0;
+        if (!n_sm) {
+            cudaDeviceProp prop;
+            n_sm = cudaGetDeviceProperties(&prop, g->device) == cudaSuccess ? prop.multiProcessorCount : 148;
+            cudaFuncSetAttribute(k_gi_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_WARPS * GI_WARP_WORDS * 4);
+        }
+        const int grid = std::min<int>(n_sm, (int)((blocks.size() + GI_WARPS - 1) / GI_WARPS));
+        k_gi_inflate<<<grid, GI_WARPS * 32, GI_WARPS * GI_WARP_WORDS * 4, st>>>((const uint8_t*)S.comp.p, (const GiBlock*)S.blk.p,
+                                                                              (int)blocks.size(), (uint8_t*)S.ubuf.p, (int*)S.status.p,
+                                                                              (unsigned*)d_small);
+        ++g->launches;
+    }
+    // ---- record table
+    int* d_flags = (int*)(d_small + 1);
+    k_gw_walk<false><<<(nsp + 127) / 128, 128, 0, st>>>((const uint8_t*)S.ubuf.p, u_last, (const unsigned long long*)S.sp.p, nsp,
+                                                         (uint32_t*)S.cnt.p, nullptr, nullptr, d_flags);
+    ++g->launches;
+    if ((rc = g_scan<false>(g, S, (const uint32_t*)S.cnt.p, (uint32_t*)S.base.p, nsp, d_small + 4))) return rc;
+    std::vector<int> status(blocks.size());
+    GCK(cudaMemcpyAsync(status.data(), S.status.p, blocks.size() * 4, cudaMemcpyDeviceToHost, st));
+    GCK(cudaMemcpyAsync(g->h_small, d_small, 64, cudaMemcpyDeviceToHost, st));
+    GCK(cudaStreamSynchronize(st));
+    for (size_t k = 0; k < status.size(); ++k)
+        if (status[k] != 0) { set_error("inflate failed (corrupt BGZF block, device code %d)", status[k]); return RAER_ERR_IO; }
+    if (g->h_small[1] & 1) { set_error("corrupt BAM record"); return RAER_ERR_IO; }
+    S.n_rec = (long long)g->h_small[4];
+    g->records += S.n_rec;
+    if (S.n_rec == 0) return RAER_OK;
+    const size_t nr = (size_t)S.n_rec;
+    if ((rc = S.rec_off.ensure(nr * 4)) || (rc = S.pass.ensure(nr * 4)) || (rc = S.pidx.ensure(nr * 4)) || (rc = S.r_pos.ensure(nr * 4)) ||
+        (rc = S.r_end.ensure(nr * 4)) || (rc = S.cpos.ensure(nr * 4)) || (rc = S.kept.ensure(nr * 4)) || (rc = S.kidx.ensure(nr * 4)) ||
+        (rc = S.ncig.ensure(nr * 4)) || (rc = S.coff.ensure(nr * 4)) || (rc = S.sqb.ensure(nr * 4)) || (rc = S.soff.ensure(nr * 4)) ||
+        (rc = S.elig.ensure(nr * 4)) || (rc = S.eidx.ensure(nr * 4)) || (rc = S.prevpos.ensure(nr * 4)))
+        return rc;
+    k_gw_walk<true><<<(nsp + 127) / 128, 128, 0, st>>>((const uint8_t*)S.ubuf.p, u_last, (const unsigned long long*)S.sp.p, nsp, nullptr,
+                                                        (const uint32_t*)S.base.p, (uint32_t*)S.rec_off.p, d_flags);
+    GpConf C = C0;
+    C.tid = ftid;
+    const unsigned gr = (unsigned)((nr + 255) / 256);
+    k_gp_pass<<<gr, 256, 0, st>>>((const uint8_t*)S.ubuf.p, (const uint32_t*)S.rec_off.p, S.n_rec, C, (uint32_t*)S.pass.p,
+                                  (int32_t*)S.r_pos.p, (int32_t*)S.r_end.p, d_small + 2, d_flags);
+    g->launches += 2;
+    if ((rc = g_scan<false>(g, S, (const uint32_t*)S.pass.p, (uint32_t*)S.pidx.p, S.n_rec, d_small + 5))) return rc;
+    k_gp_cpos<<<gr, 256, 0, st>>>((const uint32_t*)S.pass.p, (const uint32_t*)S.pidx.p, (const int32_t*)S.r_pos.p, S.n_rec,
+                                  (int32_t*)S.cpos.p);
+    ++g->launches;
+    GCK(cudaMemcpyAsync(g->h_small, d_small, 64, cudaMemcpyDeviceToHost, st));
+    GCK(cudaStreamSynchronize(st));
+    if (g->h_small[1] & 1) { set_error("corrupt BAM record"); return RAER_ERR_IO; }
+    if (g->h_small[1] & 2) return RAER_GI_FALLBACK;  // a read beyond the documented limits: the host path reports it
+    S.aligned_bases = (int64_t)g->h_small[2];
+    S.max_span = (int)g->h_small[3];
+    S.n_pass = (long long)g->h_small[5];
+    k_gp_kept<<<gr, 256, 0, st>>>((const uint8_t*)S.ubuf.p, (const uint32_t*)S.rec_off.p, (const uint32_t*)S.pass.p,
+                                  (const uint32_t*)S.pidx.p, (const int32_t*)S.r_pos.p, (const int32_t*)S.r_end.p,
+                                  (const int32_t*)S.cpos.p, S.n_rec, S.n_pass, C, S.max_span, (uint32_t*)S.kept.p, (uint32_t*)S.ncig.p,
+                                  (uint32_t*)S.sqb.p, (uint32_t*)S.elig.p, (int32_t*)S.prevpos.p, d_flags);
+    ++g->launches;
+    if ((rc = g_scan<false>(g, S, (const uint32_t*)S.kept.p, (uint32_t*)S.kidx.p, S.n_rec, d_small + 4)) ||
+        (rc = g_scan<false>(g, S, (const uint32_t*)S.ncig.p, (uint32_t*)S.coff.p, S.n_rec, d_small + 5)) ||
+        (rc = g_scan<false>(g, S, (const uint32_t*)S.sqb.p, (uint32_t*)S.soff.p, S.n_rec, d_small + 6)) ||
+        (rc = g_scan<false>(g, S, (const uint32_t*)S.elig.p, (uint32_t*)S.eidx.p, S.n_rec, d_small + 7)))
+        return rc;
+    GCK(cudaMemcpyAsync(g->h_small, d_small, 64, cudaMemcpyDeviceToHost, st));
+    GCK(cudaStreamSynchronize(st));
+    if (g->h_small[1] & 4) { set_error("the input is not sorted (reads out of order)"); return RAER_ERR_IO; }
+    if (g->h_small[1] & 8) return RAER_GI_FALLBACK;  // depth may reach max_depth: the stateful drop needs the stream replayed
+    S.n_kept = (long long)g->h_small[4];
+    S.n_cig = (long long)g->h_small[5];
+    S.n_sq = (long long)g->h_small[6];
+    S.n_elig = (long long)g->h_small[7];
+    return RAER_OK;
+}
+
+static int gi_maxend(raer_gi* g, raer_read_batch* b);
+
+// Builds the read batch of contig `tid` (numbering of file 0; `ftid[f]` = the same contig in file f's header) on the device.
+// site: the contig's intervals of the call's region list or nullptr. On RAER_OK *b describes device arrays owned by g
+// (valid until the next call); *site_mask_dev is the device bitmap of the listed positions (nullptr without a list).
+extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_len, const raer::IngestConf* ic,
+                              const raer::RegionIndex::Chr* site, raer_read_batch* b, int64_t* file_off /* nf + 1 */,
+                              const uint32_t** site_mask_dev, int64_t* aligned_bases) {
+    cudaSetDevice(g->device);
+    cudaStream_t st = g->st;
+    const int nf = g->nf;
+    int rc;
+    GpConf C;
+    memset(&C, 0, sizeof(C));
+    C.keep0 = ic->keep_flag[0];
+    C.keep1 = ic->keep_flag[1];
+    C.min_global_mq = ic->min_global_mq;
+    C.has_rq = ic->rq_pct && ic->rq_minq;
+    C.rq_minq = ic->rq_minq;
+    C.rq_pct = (float)ic->rq_pct;
+    C.remove_overlaps = ic->remove_overlaps;
+    C.min_overhang = ic->min_overhang;
+    C.max_depth = ic->max_depth;
+    *site_mask_dev = nullptr;
+    if (site) {
+        const size_t words = ((size_t)contig_len + 31) / 32 + 1;
+        std::vector<uint32_t> bits(words, 0), pre(words + 1, 0);
+        for (size_t k = 0; k < site->beg.size(); ++k) {
+            const int lo = std::max(site->beg[k], 0), hi = std::min(site->end[k], contig_len - 1);
+            for (int p = lo; p <= hi; ++p) bits[(size_t)p >> 5] |= 1u << (p & 31);
+        }
+        for (size_t w = 0; w < words; ++w) pre[w + 1] = pre[w] + (uint32_t)__builtin_popcount(bits[w]);
+        if ((rc = g->site_bits.ensure(words * 4)) || (rc = g->site_pre.ensure((words + 1) * 4))) return rc;
+        GCK(cudaMemcpyAsync(g->site_bits.p, bits.data(), words * 4, cudaMemcpyHostToDevice, st));
+        GCK(cudaMemcpyAsync(g->site_pre.p, pre.data(), (words + 1) * 4, cudaMemcpyHostToDevice, st));
+        GCK(cudaStreamSynchronize(st));  // the vectors go out of scope
+        C.site_bits = (const uint32_t*)g->site_bits.p;
+        C.site_pre = (const uint32_t*)g->site_pre.p;
+        C.site_len = contig_len;
+        *site_mask_dev = C.site_bits;
+    }
+    long long n_reads = 0, n_cig = 0, n_sq = 0, n_elig_max = 0;
+    *aligned_bases = 0;
+    for (int f = 0; f < nf; ++f) {
+        C.libtype = ic->libtype[(size_t)f];
+        rc = gi_file_stage(g, f, ftid[f], C);
+        if (rc) return rc;
+        const FileStage& S = g->stage[(size_t)f];
+        file_off[f] = n_reads;
+        n_reads += S.n_kept;
+        n_cig += S.n_cig;
+        n_sq += S.n_sq;
+        n_elig_max = std::max(n_elig_max, S.n_elig);
+        *aligned_bases += S.aligned_bases;
+    }
+    file_off[nf] = n_reads;
+    memset(b, 0, sizeof(*b));
+    b->n_files = nf;
+    b->tid = tid;
+    b->beg = 0;
+    b->end = contig_len;
+    b->n_reads = n_reads;
+    b->file_off = file_off;
+    if (n_reads == 0) return RAER_OK;
+    if (n_reads >= INT_MAX || n_cig >= (1ll << 32) || n_sq >= (1ll << 31)) return RAER_GI_FALLBACK;  // 32-bit offsets in raer_read_hdr
+    if ((rc = g->hdr.ensure((size_t)n_reads * sizeof(raer_read_hdr))) || (rc = g->maxend.ensure((size_t)n_reads * 4)) ||
+        (rc = g->endtmp.ensure((size_t)n_reads * 4)) || (rc = g->cigar.ensure((size_t)n_cig * 4 + 16)) ||
+        (rc = g->seq.ensure((size_t)n_sq + 16)) || (rc = g->qual.ensure((size_t)n_sq * 2 + 16)) ||
+        (rc = g->pair_b.ensure((size_t)n_reads * 4 + 16)))
+        return rc;
+    unsigned long long* d_small = (unsigned long long*)g->small.p;
+    GCK(cudaMemsetAsync(d_small, 0, 256, st));
+    long long c0 = 0, s0 = 0;
+    for (int f = 0; f < nf; ++f) {
+        FileStage& S = g->stage[(size_t)f];
+        if (S.n_kept == 0) continue;
+        C.libtype = ic->libtype[(size_t)f];
+        C.tid = ftid[f];
+        const size_t nk = (size_t)S.n_kept, ne = (size_t)S.n_elig;
+        if ((rc = S.krec.ensure(nk * 4)) || (rc = S.kprev.ensure(nk * 4)) || (rc = S.pkey.ensure(ne * 8 + 16)) ||
+            (rc = S.pval.ensure(ne * 4 + 16)) || (rc = S.pkey2.ensure(ne * 8 + 16)) || (rc = S.pval2.ensure(ne * 4 + 16)))
+            return rc;
+        GpOut O;
+        O.hdr = (raer_read_hdr*)g->hdr.p;
+        O.cigar = (uint32_t*)g->cigar.p;
+        O.seq = (uint8_t*)g->seq.p;
+        O.qual = (uint8_t*)g->qual.p;
+        O.r0 = file_off[f];
+        O.c0 = c0;
+        O.s0 = s0;
+        const unsigned gr = (unsigned)((S.n_rec + 255) / 256);
+        k_gp_write<<<gr, 256, 0, st>>>((const uint8_t*)S.ubuf.p, (const uint32_t*)S.rec_off.p, (const uint32_t*)S.kept.p,
+                                       (const uint32_t*)S.kidx.p, (const uint32_t*)S.coff.p, (const uint32_t*)S.soff.p,
+                                       (const uint32_t*)S.elig.p, (const uint32_t*)S.eidx.p, (const int32_t*)S.r_end.p,
+                                       (const int32_t*)S.prevpos.p, S.n_rec, C, O, (unsigned long long*)S.pkey.p, (uint32_t*)S.pval.p,
+                                       (uint32_t*)S.krec.p, (int32_t*)S.kprev.p);
+        ++g->launches;
+        if (S.n_elig > 0) {
+            const unsigned nblk = (unsigned)((S.n_elig + (long long)RS_BLOCK * RS_ITEMS - 1) / ((long long)RS_BLOCK * RS_ITEMS));
+            if ((rc = S.hist.ensure((size_t)nblk * 256 * 4 + 1024))) return rc;
+            unsigned long long* k_in = (unsigned long long*)S.pkey.p;
+            unsigned* v_in = (unsigned*)S.pval.p;
+            unsigned long long* k_out = (unsigned long long*)S.pkey2.p;
+            unsigned* v_out = (unsigned*)S.pval2.p;
+            g->launches += rs_sort(k_in, v_in, k_out, v_out, S.n_elig, 64, (unsigned*)S.hist.p, st);
+            k_gp_pair<<<(unsigned)((S.n_elig + 255) / 256), 256, 0, st>>>(k_in, v_in, S.n_elig, (const uint8_t*)S.ubuf.p,
+                                                                          (const uint32_t*)S.krec.p, (const int32_t*)S.kprev.p,
+                                                                          (raer_read_hdr*)g->hdr.p, file_off[f], (int32_t*)g->pair_b.p,
+                                                                          d_small + 4, (int*)(d_small + 1));
+            ++g->launches;
+        }
+        c0 += S.n_cig;
+        s0 += S.n_sq;
+    }
+    GCK(cudaMemcpyAsync(g->h_small, d_small, 64, cudaMemcpyDeviceToHost, st));
+    GCK(cudaStreamSynchronize(st));
+    if (cudaGetLastError() != cudaSuccess) { set_error("device ingest kernels failed"); return RAER_ERR_CUDA; }
+    if (g->h_small[1] & 16) return RAER_GI_FALLBACK;  // two read names with one 64-bit hash: the host's string table decides
+    b->hdr = (const raer_read_hdr*)g->hdr.p;
+    b->cigar = (const uint32_t*)g->cigar.p;
+    b->seq = (const uint8_t*)g->seq.p;
+    b->qual = (const uint8_t*)g->qual.p;
+    b->n_cigar_words = n_cig;
+    b->n_sq_bytes = n_sq;
+    b->pair_b = (const int32_t*)g->pair_b.p;
+    b->n_pairs = (int64_t)g->h_small[4];
+    b->n_aligned_bases = *aligned_bases;
+    return gi_maxend(g, b);
+}
+
+__global__ void k_gp_ends(const raer_read_hdr* __restrict__ hdr, long long n, uint32_t* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)max(hdr[i].end, 0);
+}
+// running maximum of hdr.end inside every file range (what k_tile_ranges of the generic tile kernel searches)
+static int gi_maxend(raer_gi* g, raer_read_batch* b) {
+    cudaSetDevice(g->device);
+    for (int f = 0; f < b->n_files; ++f) {
+        const long long lo = b->file_off[f], n = b->file_off[f + 1] - lo;
+        if (n <= 0) continue;
+        k_gp_ends<<<(unsigned)((n + 255) / 256), 256, 0, g->st>>>(b->hdr + lo, n, (uint32_t*)g->endtmp.p + lo);
+        int rc = g_scan<true>(g, g->stage[0], (const uint32_t*)g->endtmp.p + lo, (uint32_t*)g->maxend.p + lo, n, nullptr);
+        if (rc) return rc;
+    }
+    GCK(cudaStreamSynchronize(g->st));
+    b->maxend = (const int32_t*)g->maxend.p;
+    return RAER_OK;
+}
+
+extern "C" void raer_gi_stats(raer_gi* g, int64_t* launches, int64_t* inflated, int64_t* compressed, int64_t* records) {
+    *launches = g->launches;
+    *inflated = g->inflated;
+    *compressed = g->compressed;
+    *records = g->records;
+}
+
+// test / bench entry: inflate n raw DEFLATE payloads that lie in one host buffer; status[i] = 0 or the decoder's code
+extern "C" int raer_gpu_inflate(const uint8_t* comp, int64_t comp_len, const int64_t* c_off, const int32_t* c_len, const int64_t* u_off,
+                                const int32_t* u_len, int32_t n_blocks, uint8_t* out, int64_t out_len, int32_t* status, double* kernel_ms) {
+    if (n_blocks <= 0) return RAER_OK;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); set_error("no usable CUDA device (the product has no CPU path)"); return RAER_ERR_NO_DEVICE; }
+    std::vector<GiBlock> blk((size_t)n_blocks);
+    for (int i = 0; i < n_blocks; ++i) {
+        blk[(size_t)i].c_off = (unsigned long long)c_off[i];
+        blk[(size_t)i].c_len = (uint32_t)c_len[i];
+        blk[(size_t)i].u_off = (unsigned long long)u_off[i];
+        blk[(size_t)i].u_len = (uint32_t)u_len[i];
+    }
+    DBufG d_comp, d_blk, d_out, d_status, d_q;
+    int rc;
+    if ((rc = d_comp.ensure((size_t)comp_len + 64)) || (rc = d_blk.ensure(blk.size() * sizeof(GiBlock))) ||
+        (rc = d_out.ensure((size_t)out_len + 64)) || (rc = d_status.ensure((size_t)n_blocks * 4)) || (rc = d_q.ensure(64)))
+        return rc;
+    GCK(cudaMemset(d_comp.p, 0, (size_t)comp_len + 64));
+    GCK(cudaMemcpy(d_comp.p, comp, (size_t)comp_len, cudaMemcpyHostToDevice));
+    GCK(cudaMemcpy(d_blk.p, blk.data(), blk.size() * sizeof(GiBlock), cudaMemcpyHostToDevice));
+    GCK(cudaMemset(d_q.p, 0, 64));
+    cudaDeviceProp prop;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int n_sm = cudaGetDeviceProperties(&prop, dev) == cudaSuccess ? prop.multiProcessorCount : 148;
+    cudaFuncSetAttribute(k_gi_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_WARPS * GI_WARP_WORDS * 4);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int grid = std::min<int>(n_sm, (n_blocks + GI_WARPS - 1) / GI_WARPS);
+    cudaEventRecord(e0);
+    k_gi_inflate<<<grid, GI_WARPS * 32, GI_WARPS * GI_WARP_WORDS * 4>>>((const uint8_t*)d_comp.p, (const GiBlock*)d_blk.p, n_blocks,
+                                                                       (uint8_t*)d_out.p, (int*)d_status.p, (unsigned*)d_q.p);
+    cudaEventRecord(e1);
+    GCK(cudaDeviceSynchronize());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (kernel_ms) *kernel_ms = ms;
+    GCK(cudaMemcpy(out, d_out.p, (size_t)out_len, cudaMemcpyDeviceToHost));
+    GCK(cudaMemcpy(status, d_status.p, (size_t)n_blocks * 4, cudaMemcpyDeviceToHost));
+    return RAER_OK;
+}

@@ -36,6 +36,13 @@ extern "C" int raer_fast_index_fill(PlpParams* P, long long n_reads, const int* 
 extern "C" int raer_launch_tiles(PlpParams* P, int n_sm, cudaStream_t st, int* launches, cudaEvent_t e0, cudaEvent_t e1);
 extern "C" int raer_lane_plan(int n_files, int* stage_bytes);
 extern "C" int raer_lane_first(PlpParams* P, int* first, cudaStream_t st);
+struct raer_gi;
+extern "C" raer_gi* raer_gi_create(int device, int nf, const char* const* paths, const char* const* indexes);
+extern "C" void raer_gi_destroy(raer_gi* g);
+extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_len, const raer::IngestConf* ic,
+                              const raer::RegionIndex::Chr* site, raer_read_batch* b, int64_t* file_off, const uint32_t** site_mask_dev,
+                              int64_t* aligned_bases);
+extern "C" void raer_gi_stats(raer_gi* g, int64_t* launches, int64_t* inflated, int64_t* compressed, int64_t* records);
 
 #define CK(call)                                                                              \
     do {                                                                                      \
@@ -418,6 +425,37 @@ extern "C" int raer_batch_pileup_device(raer_ctx* c, const raer_bulk_conf* conf,
     if (rc) return rc;
     if (n_rows) *n_rows = (int64_t)s.rows;
     return RAER_OK;
+}
+
+static int fetch_rows(raer_ctx* c, int nf, const SmallState& s, raer_rows* out);
+// device-resident batch -> rows in host memory (GPU ingest: the batch was packed by kernels, nothing to upload)
+extern "C" int raer_batch_pileup_device_rows(raer_ctx* c, const raer_bulk_conf* conf, const raer_read_batch* b, raer_rows* out,
+                                             int64_t* launches) {
+    cudaSetDevice(c->device);
+    memset(out, 0, sizeof(*out));
+    out->n_files = b->n_files;
+    for (int k = 0; k < 2 * RAER_MAX_FILES; ++k) out->grow_pos[k] = INT32_MAX;
+    if (conf->n_files != b->n_files || b->n_files > RAER_MAX_FILES) { set_error("bad file count"); return RAER_ERR_ARG; }
+    if (b->n_reads == 0 || b->end <= b->beg) return RAER_OK;
+    cudaEventRecord(c->ev[1], c->stream);
+    int rc = run_device(c, conf, b, conf->site_mask, launches);
+    if (rc) return rc;
+    cudaEventRecord(c->ev[2], c->stream);
+    SmallState s;
+    rc = finish_run(c, conf, b, conf->site_mask, launches, &s);
+    if (rc) return rc;
+    rc = fetch_rows(c, b->n_files, s, out);
+    if (rc == RAER_OK && conf->aei_mode) {
+        c->last_aei.assign((size_t)b->n_files * 16, 0);
+        CK(cudaMemcpyAsync(c->last_aei.data(), c->aei.p, c->last_aei.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    cudaEventRecord(c->ev[3], c->stream);
+    cudaEventSynchronize(c->ev[3]);
+    c->ms_h2d = 0;
+    cudaEventElapsedTime(&c->ms_kernel, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]);
+    return rc;
 }
 
 extern "C" void raer_rows_free(raer_rows* r) {
@@ -901,7 +939,104 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
     bool parallel = !a->region && a->shard_count <= 1 && (n_workers >= 2 || (has_ridx && n_workers >= 1)) &&
                     !getenv("RAER_SERIAL_INGEST");
     if (parallel) parallel = raer::indexes_usable(a->bampaths, a->indexes, nf);  // single stream: no index needed
-    if (parallel) {
+    // ---- device ingest (raer_gingest.cu): whole contigs are inflated, parsed, filtered and packed by kernels; what that
+    // path does not cover falls back, contig by contig, to the host stream below
+    bool use_gi = !a->region && a->shard_count <= 1 && !a->umi_tag && ic.n_mm_type == 0 && ic.n_mm == 0 &&
+                  !getenv("RAER_SERIAL_INGEST") && !getenv("RAER_BATCH_READS");
+    if (const char* e = getenv("RAER_GPU_INGEST")) use_gi = use_gi && atoi(e) != 0;
+    if (use_gi) use_gi = raer::indexes_usable(a->bampaths, a->indexes, nf);
+    if (use_gi) {
+        raer_gi* gi = raer_gi_create(a->device, nf, a->bampaths, a->indexes);
+        if (!gi) rc = RAER_ERR_IO;
+        const std::vector<int32_t>& lens = ing.lengths();
+        std::vector<int> ftid((size_t)nf);
+        std::vector<int64_t> file_off((size_t)nf + 1);
+        int64_t n_fallback = 0, fb_records = 0, fb_bases = 0, fb_inflated = 0, fb_seeks = 0;
+        // the host stream for one contig (same as a worker of the contig-parallel path, on this thread)
+        auto host_contig = [&](int c) -> int {
+            raer::Ingest wi(ic);
+            std::vector<std::pair<int32_t, int32_t>> jl;
+            if (has_ridx) jl = raer::jump_intervals(ridx.find(names[c]));
+            if (!wi.open(a->bampaths, a->indexes, a->host_threads, names[c].c_str(), has_ridx ? &jl : nullptr)) return RAER_ERR_IO;
+            raer::PackedBatch pb;
+            int r = RAER_OK;
+            while (r == RAER_OK && wi.next_contig() >= 0) {
+                std::string seq;
+                if (!raer::fasta_fetch(a->fapath, names[c], seq)) seq.clear();
+                if ((r = raer_ctx_set_reference(ctx, c, seq.data(), (int64_t)seq.size()))) break;
+                while (r == RAER_OK && wi.next_batch(pb)) {
+                    if (a->poll && a->poll(a->poll_ctx)) { set_error("interrupted"); r = RAER_ERR_INTERRUPT; break; }
+                    if (pb.b.n_reads == 0 || pb.b.end <= pb.b.beg) continue;
+                    raer_rows rows;
+                    r = gpu_batch(has_ridx ? ridx.find(names[c]) : nullptr, 0, INT_MAX, pb, &rows);
+                    if (r == RAER_OK) emit_rows(c, rows);
+                }
+            }
+            if (r == RAER_OK && wi.failed()) { set_error("%s", wi.error().c_str()); r = RAER_ERR_IO; }
+            fb_records += wi.records(); fb_bases += wi.aligned_bases(); fb_inflated += wi.inflated_bytes(); fb_seeks += wi.seeks();
+            return r;
+        };
+        for (int c = 0; rc == RAER_OK && c < (int)names.size(); ++c) {
+            const raer::RegionIndex::Chr* rchr = has_ridx ? ridx.find(names[c]) : nullptr;
+            if (has_ridx && !rchr) continue;  // no site on this contig: nothing can be written
+            if (a->poll && a->poll(a->poll_ctx)) { set_error("interrupted"); rc = RAER_ERR_INTERRUPT; break; }
+            for (int f = 0; f < nf; ++f) ftid[(size_t)f] = c;
+            raer_read_batch b;
+            const uint32_t* d_sites = nullptr;
+            int64_t bases = 0;
+            double t0b = raer::now_seconds();
+            int r = raer_gi_contig(gi, c, ftid.data(), lens[(size_t)c], &ic, rchr, &b, file_off.data(), &d_sites, &bases);
+            tm_batch += raer::now_seconds() - t0b;
+            if (r == 1) {  // RAER_GI_FALLBACK
+                ++n_fallback;
+                ++out->n_host_contigs;
+                rc = host_contig(c);
+                continue;
+            }
+            if (r) { rc = r; break; }
+            out->n_aligned_bases += bases;
+            ++out->n_device_contigs;
+            if (b.n_reads == 0) continue;
+            std::string seq;
+            double t0f = raer::now_seconds();
+            if (!raer::fasta_fetch(a->fapath, names[c], seq)) seq.clear();
+            rc = raer_ctx_set_reference(ctx, c, seq.data(), (int64_t)seq.size());
+            tm_fasta += raer::now_seconds() - t0f;
+            if (rc) break;
+            bc.reg_beg = 0;
+            bc.reg_end = INT_MAX;
+            bc.site_mask = d_sites;  // device pointer: the bitmap the prefilter used, over the whole contig
+            bc.mask_beg = 0;
+            bc.mask_bits = lens[(size_t)c];
+            raer_rows rows;
+            int64_t launches = 0;
+            double t0g = raer::now_seconds();
+            rc = raer_batch_pileup_device_rows(ctx, &bc, &b, &rows, &launches);
+            tm_gpu += raer::now_seconds() - t0g;
+            if (rc) break;
+            if (bc.aei_mode) {
+                std::vector<int64_t> sums((size_t)nf * 16);
+                if ((rc = raer_ctx_last_aei(ctx, sums.data(), nf))) { raer_rows_free(&rows); break; }
+                for (size_t i = 0; i < sums.size(); ++i) out->aei[i] += sums[i];
+            }
+            out->gpu_launches += launches;
+            out->t_kernel += ctx->ms_kernel * 1e-3;
+            out->t_d2h += ctx->ms_d2h * 1e-3;
+            emit_rows(c, rows);
+        }
+        if (gi) {
+            int64_t gl = 0, gin = 0, gco = 0, grec = 0;
+            raer_gi_stats(gi, &gl, &gin, &gco, &grec);
+            out->gpu_launches += gl;
+            out->n_records = grec + fb_records;
+            out->n_aligned_bases += fb_bases;
+            out->n_inflated_bytes = gin + fb_inflated;
+            out->n_seeks = fb_seeks;
+            raer_gi_destroy(gi);
+        }
+        raer_ctx_set_reference(ctx, -1, nullptr, 0);
+        if (getenv("RAER_TIMING")) fprintf(stderr, "[raer_pileup] device ingest: %lld contig(s) fell back to the host stream\n", (long long)n_fallback);
+    } else if (parallel) {
         struct Slot {
             raer::PackedBatch pb;
             int tid = -1;
