@@ -2,22 +2,28 @@
 //
 // A BGZF block is an independent DEFLATE stream of at most 64 KiB of output whose compressed payload and exact output
 // size are known before decoding starts (BSIZE / ISIZE), so thousands of blocks decode side by side. Huffman decoding
-// itself is a serial chain of table lookups: lane 0 of the warp walks the symbols, the other lanes help where the work
-// is wide (clearing and filling the decode tables). The tables of the block live in the warp's slice of shared
-// memory (10-bit primary table for literals / lengths, 8-bit for distances, second-level tables behind them); the
-// compressed bytes are read through a 64-bit bit buffer refilled 32 bits at a time from aligned words; the output goes
-// straight to the block's window in global memory, where the matches read it back from (L1 / L2 hits: the window was
-// just written by the same thread). Same table layout and the same acceptance rules as the host decoder
-// (raer_inflate.cpp); a block the decoder refuses is reported through `status` and the host decides what to do.
+// itself is a serial chain of table lookups: lane 0 of the warp walks the symbols and turns them into tokens (a literal,
+// or a match of `len` bytes `dist` bytes back), GI_TOK at a time, in the warp's slice of shared memory. The whole warp
+// then writes the bytes of the batch: a prefix sum over the token lengths gives every token its place, every lane takes
+// output bytes lane, lane + 32, ..., finds the token a byte belongs to and follows match references (inside the batch
+// through the token table, before the batch through one L2 load) until it reaches a literal or a byte that is already
+// in memory. So the copy loop of a match -- a chain of dependent loads from memory the same thread has just written --
+// is replaced by independent loads, 32 at a time, and the stores of a batch coalesce.
+// The tables of the block live in shared memory as well (10-bit primary table for literals / lengths, 8-bit for
+// distances, second-level tables behind them); the compressed bytes are read through a 64-bit bit buffer refilled 32 bits
+// at a time from aligned words, one word ahead of its use. Same table layout and the same acceptance rules as the host
+// decoder (raer_inflate.cpp); a block the decoder refuses is reported through `status` and the host decides what to do.
 #ifndef RAER_GINFLATE_CUH
 #define RAER_GINFLATE_CUH
 
 #define GI_LL_BITS 10
 #define GI_D_BITS 8
-#define GI_LL_SIZE ((1 << GI_LL_BITS) + 1536)
+#define GI_LL_SIZE ((1 << GI_LL_BITS) + 320)  // zlib's ENOUGH_LENS bound for a 10-bit root: 1332 entries
 #define GI_D_SIZE ((1 << GI_D_BITS) + 512)
-#define GI_WARP_WORDS (GI_LL_SIZE + GI_D_SIZE)  // shared-memory words per warp
-#define GI_WARPS 16                             // warps (= blocks in flight) per CTA, one CTA per SM
+#define GI_TOK 64                               // tokens per batch
+#define GI_CTRL 4                               // control words lane 0 hands to the warp
+#define GI_WARP_WORDS (GI_LL_SIZE + GI_D_SIZE + GI_TOK + GI_TOK + 4 + GI_CTRL)  // shared-memory words per warp
+#define GI_WARPS 24                             // warps (= blocks in flight) per CTA, one CTA per SM
 
 // table entry: bits 0-4 code length to consume (sub-table entries: length beyond the primary bits),
 // bits 5-7 kind, bits 8-12 number of extra bits (or sub-table index bits), bits 16-31 value
@@ -103,67 +109,82 @@ __device__ int gi_build_table(const uint8_t* lens, int n, int tbits, uint32_t* t
     return used;
 }
 
-struct GiBits {  // LSB-first bit reader over aligned 32-bit words of global memory
-    const uint32_t* w;      // next word to load
+struct GiBits {  // LSB-first bit reader over aligned 32-bit words of global memory, one word of look-ahead
+    const uint32_t* w;      // next word to load (the word after `nxt`)
     const uint32_t* w_end;  // first word that must not be loaded (a few words of slack lie behind the payload)
     unsigned long long bb;
+    uint32_t nxt;
     int bc;
-    bool over;
+    __device__ __forceinline__ uint32_t fetch() {
+        const uint32_t v = w < w_end ? __ldg(w) : 0u;  // zeros behind the payload: the caller checks byte_pos() at the end
+        ++w;
+        return v;
+    }
     __device__ __forceinline__ void init(const uint8_t* p, size_t n) {
         const size_t a = (size_t)p & 3;
         w = reinterpret_cast<const uint32_t*>(p - a);
         w_end = reinterpret_cast<const uint32_t*>((((size_t)(p + n)) + 3) & ~(size_t)3) + 2;
-        bb = 0;
-        bc = 0;
-        over = false;
-        need(32);
+        bb = fetch();
+        bc = 32;
+        nxt = fetch();
         drop((int)a * 8);
     }
     __device__ __forceinline__ void need(int n) {  // n <= 32
-        while (bc < n) {
-            uint32_t v = 0;
-            if (w < w_end) v = __ldg(w);
-            else over = true;
-            ++w;
-            bb |= (unsigned long long)v << bc;
+        if (bc < n) {
+            bb |= (unsigned long long)nxt << bc;
             bc += 32;
+            nxt = fetch();
         }
     }
     __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)bb & ((1u << n) - 1u); }
     __device__ __forceinline__ void drop(int n) { bb >>= n; bc -= n; }
-    // bytes of the payload consumed so far (whole bytes still in the buffer are not)
-    __device__ __forceinline__ const uint8_t* byte_pos() const { return reinterpret_cast<const uint8_t*>(w) - (bc >> 3); }
+    // first byte of the payload not consumed yet (whole bytes still in the buffer are not consumed)
+    __device__ __forceinline__ const uint8_t* byte_pos() const { return reinterpret_cast<const uint8_t*>(w - 1) - (bc >> 3); }
 };
 
-// Decodes one raw DEFLATE stream (executed by ONE thread). in / in_len: the payload; out / out_len: exactly the bytes it
-// must produce. tab: GI_WARP_WORDS words of shared memory. Returns 0, or a negative code.
-__device__ int gi_inflate_block(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len, uint32_t* tab) {
+// decoder state of one block, in the registers of lane 0
+struct GiState {
+    GiBits B;
+    const uint8_t* in;
+    size_t in_len;
+    uint32_t op;       // output bytes produced so far, tokens of the current batch included
+    uint32_t out_len;
+    int last;          // BFINAL of the deflate block being decoded
+    int in_symbols;    // tables are built, symbols follow
+};
+
+// token: bits 0-8 length (1 = literal), bits 9-16 the literal, bits 17-31 distance - 1
+__device__ __forceinline__ uint32_t gi_tok_lit(uint32_t v) { return 1u | (v << 9); }
+__device__ __forceinline__ uint32_t gi_tok_match(uint32_t len, uint32_t dist) { return len | ((dist - 1u) << 17); }
+
+// Lane 0: decodes until GI_TOK tokens are waiting, a deflate block ends or something is wrong. Stored blocks are copied
+// right here (nothing is pending when one starts). Returns 0 = more to come, 1 = stream finished, negative = refused.
+__device__ int gi_decode_batch(GiState& S, uint8_t* out, uint32_t* tab, uint32_t* tok, int* n_tok) {
     uint32_t* const LL = tab;
     uint32_t* const DD = tab + GI_LL_SIZE;
-    GiBits B;
-    B.init(in, in_len);
-    size_t op = 0;
-    uint8_t lens[286 + 30 + 140];
-    uint8_t sub_bits[1 << GI_LL_BITS];
-    uint16_t codes[320];
-    int last;
-    do {
+    GiBits& B = S.B;
+    int n = 0;
+    *n_tok = 0;
+    if (!S.in_symbols) {
+        uint8_t lens[286 + 30 + 140];
+        uint8_t sub_bits[1 << GI_LL_BITS];
+        uint16_t codes[320];
         B.need(3);
-        last = (int)B.peek(1);
+        S.last = (int)B.peek(1);
         const int type = (int)(B.peek(3) >> 1);
         B.drop(3);
         if (type == 0) {  // stored
             B.drop(B.bc & 7);
             const uint8_t* ip = B.byte_pos();
-            if (ip + 4 > in + in_len) return -2;
+            if (ip + 4 > S.in + S.in_len) return -2;
             const unsigned len = ip[0] | (ip[1] << 8), nlen = ip[2] | (ip[3] << 8);
             ip += 4;
             if ((len ^ 0xffffu) != nlen) return -3;
-            if (ip + len > in + in_len || op + len > out_len) return -4;
-            for (unsigned i = 0; i < len; ++i) out[op + i] = ip[i];
-            op += len;
-            B.init(ip + len, (size_t)((in + in_len) - (ip + len)));
-            continue;
+            if (ip + len > S.in + S.in_len || S.op + len > S.out_len) return -4;
+            for (unsigned i = 0; i < len; ++i) out[S.op + i] = ip[i];
+            S.op += len;
+            B.init(ip + len, (size_t)((S.in + S.in_len) - (ip + len)));
+            return S.last ? 1 : 0;
         }
         if (type == 3) return -5;
         if (type == 1) {  // fixed codes
@@ -193,75 +214,81 @@ __device__ int gi_inflate_block(const uint8_t* in, size_t in_len, uint8_t* out, 
             }
             uint32_t* cltab = DD;  // 128 entries, free until the distance table is built
             if (gi_build_table(cl, 19, 7, cltab, 1 << 7, 2, sub_bits, codes) < 0) return -8;
-            int n = 0;
+            int k = 0;
             const int total = hlit + hdist;
-            while (n < total) {
+            while (k < total) {
                 B.need(14);
                 const uint32_t e = cltab[B.peek(7)];
                 if (((e >> 5) & 7) != GK_LIT) return -9;
                 B.drop((int)(e & 31));
                 const int sym = (int)(e >> 16);
-                if (sym < 16) { lens[n++] = (uint8_t)sym; continue; }
+                if (sym < 16) { lens[k++] = (uint8_t)sym; continue; }
                 int rep, val = 0;
                 if (sym == 16) {
-                    if (n == 0) return -10;
-                    val = lens[n - 1];
+                    if (k == 0) return -10;
+                    val = lens[k - 1];
                     rep = 3 + (int)B.peek(2); B.drop(2);
                 } else if (sym == 17) {
                     rep = 3 + (int)B.peek(3); B.drop(3);
                 } else {
                     rep = 11 + (int)B.peek(7); B.drop(7);
                 }
-                if (n + rep > total) return -11;
-                for (int i = 0; i < rep; ++i) lens[n + i] = (uint8_t)val;
-                n += rep;
+                if (k + rep > total) return -11;
+                for (int i = 0; i < rep; ++i) lens[k + i] = (uint8_t)val;
+                k += rep;
             }
             if (lens[256] == 0) return -12;
             if (gi_build_table(lens, hlit, GI_LL_BITS, LL, GI_LL_SIZE, 0, sub_bits, codes) < 0) return -13;
             if (gi_build_table(lens + hlit, hdist, GI_D_BITS, DD, GI_D_SIZE, 1, sub_bits, codes) < 0) return -14;
         }
-        // ---- the block's symbols
-        while (true) {
-            B.need(32);  // a literal / length code (15) + its extra bits (5) fit
-            uint32_t e = LL[B.peek(GI_LL_BITS)];
-            int kind = (int)((e >> 5) & 7);
-            if (kind == GK_SUB) {
-                B.drop(GI_LL_BITS);
-                e = LL[(e >> 16) + B.peek((int)((e >> 8) & 31))];
-                kind = (int)((e >> 5) & 7);
-            }
-            B.drop((int)(e & 31));
-            if (kind == GK_LIT) {
-                if (op >= out_len) return -15;
-                out[op++] = (uint8_t)(e >> 16);
-                continue;
-            }
-            if (kind == GK_EOB) break;
-            if (kind != GK_LEN) return -16;
-            const int xl = (int)((e >> 8) & 31);
-            const unsigned len = (e >> 16) + B.peek(xl);
-            B.drop(xl);
-            B.need(32);  // a distance code (15) + its extra bits (13)
-            uint32_t de = DD[B.peek(GI_D_BITS)];
-            if (((de >> 5) & 7) == GK_SUB) {
-                B.drop(GI_D_BITS);
-                de = DD[(de >> 16) + B.peek((int)((de >> 8) & 31))];
-            }
-            if (((de >> 5) & 7) != GK_LEN) return -17;
-            B.drop((int)(de & 31));
-            const int xd = (int)((de >> 8) & 31);
-            const unsigned dist = (de >> 16) + B.peek(xd);
-            B.drop(xd);
-            if (dist > op || len > out_len - op) return -18;
-            const uint8_t* src = out + op - dist;
-            uint8_t* dst = out + op;
-            for (unsigned i = 0; i < len; ++i) dst[i] = src[i];
-            op += len;
+        S.in_symbols = 1;
+    }
+    // ---- symbols of the deflate block
+    uint32_t op = S.op;
+    int rc = 0;
+    while (n < GI_TOK) {
+        B.need(32);  // a literal / length code (15) + its extra bits (5) fit
+        uint32_t e = LL[B.peek(GI_LL_BITS)];
+        int kind = (int)((e >> 5) & 7);
+        if (kind == GK_SUB) {
+            B.drop(GI_LL_BITS);
+            e = LL[(e >> 16) + B.peek((int)((e >> 8) & 31))];
+            kind = (int)((e >> 5) & 7);
         }
-    } while (!last);
-    if (op != out_len) return -19;
-    if (B.over || B.byte_pos() > in + in_len) return -20;
-    return 0;
+        B.drop((int)(e & 31));
+        if (kind == GK_LIT) {
+            tok[n++] = gi_tok_lit(e >> 16);
+            ++op;
+            continue;
+        }
+        if (kind == GK_EOB) {
+            S.in_symbols = 0;
+            rc = S.last ? 1 : 0;
+            break;
+        }
+        if (kind != GK_LEN) { rc = -16; break; }
+        const int xl = (int)((e >> 8) & 31);
+        const unsigned len = (e >> 16) + B.peek(xl);
+        B.drop(xl);
+        B.need(32);  // a distance code (15) + its extra bits (13)
+        uint32_t de = DD[B.peek(GI_D_BITS)];
+        if (((de >> 5) & 7) == GK_SUB) {
+            B.drop(GI_D_BITS);
+            de = DD[(de >> 16) + B.peek((int)((de >> 8) & 31))];
+        }
+        if (((de >> 5) & 7) != GK_LEN) { rc = -17; break; }
+        B.drop((int)(de & 31));
+        const int xd = (int)((de >> 8) & 31);
+        const unsigned dist = (de >> 16) + B.peek(xd);
+        B.drop(xd);
+        if (dist > op || len > S.out_len - op) { rc = -18; break; }
+        tok[n++] = gi_tok_match(len, dist);
+        op += len;
+    }
+    if (rc >= 0 && op > S.out_len) rc = -15;
+    S.op = op;
+    *n_tok = rc < 0 ? 0 : n;
+    return rc;
 }
 
 struct GiBlock {
@@ -270,19 +297,97 @@ struct GiBlock {
     uint32_t c_len, u_len;
 };
 
-// persistent: warps pull blocks from an atomic queue; lane 0 decodes
+// persistent: warps pull blocks from an atomic queue; lane 0 decodes, the warp writes
 __global__ void __launch_bounds__(GI_WARPS * 32, 1) k_gi_inflate(const uint8_t* __restrict__ comp, const GiBlock* __restrict__ blk,
                                                                  int n_blocks, uint8_t* out, int* __restrict__ status,
                                                                  unsigned* queue) {
     extern __shared__ __align__(16) uint32_t gi_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane != 0) return;  // the decode chain is serial: one thread per warp, no divergence inside the warp
     uint32_t* tab = gi_smem + (size_t)wid * GI_WARP_WORDS;
+    uint32_t* tok = tab + GI_LL_SIZE + GI_D_SIZE;
+    uint32_t* pre = tok + GI_TOK;          // GI_TOK + 1 offsets (+ padding)
+    volatile uint32_t* ctrl = pre + GI_TOK + 4;  // [0] tokens in the batch, [1] decoder verdict
     while (true) {
-        const int b = (int)atomicAdd(queue, 1u);
+        int b = 0;
+        if (lane == 0) b = (int)atomicAdd(queue, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
         if (b >= n_blocks) break;
         const GiBlock k = blk[b];
-        status[b] = k.u_len ? gi_inflate_block(comp + k.c_off, k.c_len, out + k.u_off, k.u_len, tab) : 0;
+        uint8_t* const dst = out + k.u_off;
+        GiState S;
+        if (lane == 0) {
+            S.in = comp + k.c_off;
+            S.in_len = k.c_len;
+            S.op = 0;
+            S.out_len = k.u_len;
+            S.last = 0;
+            S.in_symbols = 0;
+            S.B.init(S.in, S.in_len);
+        }
+        int verdict = 0;
+        uint32_t base = 0;  // output offset of the batch
+        if (k.u_len == 0) verdict = 1;
+        while (verdict == 0) {
+            if (lane == 0) {
+                int n = 0;
+                const uint32_t before = S.op;
+                const int rc = gi_decode_batch(S, dst, tab, tok, &n);
+                ctrl[0] = (uint32_t)n;
+                ctrl[1] = (uint32_t)rc;
+                ctrl[2] = n ? before : S.op;  // where the batch starts (a stored block has moved op on its own)
+            }
+            __syncwarp();
+            const int n = (int)ctrl[0];
+            verdict = (int)ctrl[1];
+            base = ctrl[2];
+            if (n > 0) {
+                // place of every token: lane handles tokens 2 * lane and 2 * lane + 1
+                const uint32_t l0 = 2 * lane < n ? (tok[2 * lane] & 511u) : 0u;
+                const uint32_t l1 = 2 * lane + 1 < n ? (tok[2 * lane + 1] & 511u) : 0u;
+                uint32_t inc = l0 + l1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                pre[2 * lane] = inc - l0 - l1;
+                pre[2 * lane + 1] = inc - l1;
+                if (lane == 31) pre[GI_TOK] = inc;
+                const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+                __syncwarp();
+                if (total == (uint32_t)n) {  // literals only
+                    for (uint32_t j = lane; j < total; j += 32) dst[base + j] = (uint8_t)(tok[j] >> 9);
+                } else {
+                    for (uint32_t j = lane; j < total; j += 32) {
+                        int pos = (int)j;
+                        uint32_t val;
+                        while (true) {
+                            int t = 0;  // last token with pre[t] <= pos
+#pragma unroll
+                            for (int step = GI_TOK / 2; step > 0; step >>= 1)
+                                if (pre[t + step] <= (uint32_t)pos) t += step;
+                            const uint32_t tk = tok[t];
+                            if ((tk & 511u) == 1u) { val = (tk >> 9) & 255u; break; }
+                            const int dist = (int)(tk >> 17) + 1;
+                            int within = pos - (int)pre[t];
+                            if (within >= dist) within %= dist;
+                            pos = (int)pre[t] - dist + within;
+                            if (pos < 0) { val = __ldcg(dst + (int)base + pos); break; }  // written by an earlier batch
+                        }
+                        dst[base + j] = (uint8_t)val;
+                    }
+                }
+            }
+            __syncwarp();  // the bytes of this batch are in memory before the next batch refers to them
+        }
+        if (lane == 0) {
+            int rc = verdict == 1 ? 0 : verdict;
+            if (rc == 0 && k.u_len) {
+                if (S.op != S.out_len) rc = -19;
+                else if (S.B.byte_pos() > S.in + S.in_len) rc = -20;
+            }
+            status[b] = rc;
+        }
     }
 }
 

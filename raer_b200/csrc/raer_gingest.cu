@@ -23,8 +23,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "raer_dev.h"
@@ -143,6 +149,7 @@ __global__ void k_gw_walk(const uint8_t* __restrict__ ub, unsigned long long tot
         ++n;
         off += 4ull + bs;
     }
+    if (off != end) atomicOr(flags, 32);  // the chain must land exactly on the next start point
     if (!FILL) cnt[k] = n;
 }
 
@@ -514,8 +521,8 @@ struct PinnedBuf {
 // everything one file contributes to the batch of a contig, still in its own buffers
 struct FileStage {
     DBufG comp, blk, ubuf, status, sp, cnt, base, rec_off, pass, pidx, r_pos, r_end, cpos, kept, kidx, ncig, coff, sqb, soff, elig, eidx,
-        prevpos, bsum, krec, kprev, pkey, pval, pkey2, pval2, hist;
-    PinnedBuf hcomp;
+        prevpos, bsum, krec, kprev, pkey, pval, pkey2, pval2, hist, queue;
+    PinnedBuf hblk;
     long long n_rec = 0, n_pass = 0, n_kept = 0, n_cig = 0, n_sq = 0, n_elig = 0;
     unsigned long long u_total = 0;
     int64_t aligned_bases = 0;
@@ -524,20 +531,29 @@ struct FileStage {
 
 }  // namespace
 
+#define GI_CHUNK ((size_t)8 << 20)
+#define GI_OVERLAP ((size_t)65536 + 4096)
+struct GiReader {
+    PinnedBuf buf;
+    cudaStream_t st = nullptr;
+};
+
 struct raer_gi {
     int device = 0;
     cudaStream_t st = nullptr;
     int nf = 0;
+    std::vector<GiReader> readers;
     std::vector<FILE*> fp;
     std::vector<std::vector<BaiRef>> bai;
     std::vector<long long> fsize;
     std::vector<FileStage> stage;
     DBufG small, site_bits, site_pre, hdr, maxend, cigar, seq, qual, pair_b, endtmp;
     unsigned long long* h_small = nullptr;  // pinned, 8 counters
-    int64_t launches = 0, inflated = 0, compressed = 0, records = 0;
-    double t_read = 0, t_inflate = 0;
+    int64_t launches = 0, inflated = 0, compressed = 0, records = 0, walk_retries = 0;
+    double t_read = 0, t_table = 0, t_alloc = 0, t_inflate = 0, t_pass = 0, t_kept = 0, t_write = 0;  // host wall seconds per stage
     ~raer_gi() {
         for (FILE* f : fp) if (f) fclose(f);
+        for (GiReader& r : readers) if (r.st) cudaStreamDestroy(r.st);
         if (h_small) cudaFreeHost(h_small);
         if (st) cudaStreamDestroy(st);
     }
@@ -547,6 +563,11 @@ extern "C" void raer_gi_destroy(raer_gi* g) {
     if (!g) return;
     cudaSetDevice(g->device);
     if (g->st) cudaStreamSynchronize(g->st);
+    if (getenv("RAER_TIMING"))
+        fprintf(stderr, "[device ingest] %.1f MB compressed -> %.1f MB, %lld records: read %.3f s, block table %.3f, alloc %.3f, "
+                        "h2d+inflate+walk %.3f, prefilter %.3f, kept+scans %.3f, write+sort+pair %.3f; %lld walk(s) redone from the index\n",
+                g->compressed / 1e6, g->inflated / 1e6, (long long)g->records, g->t_read, g->t_table, g->t_alloc, g->t_inflate, g->t_pass,
+                g->t_kept, g->t_write, (long long)g->walk_retries);
     delete g;
 }
 
@@ -573,6 +594,15 @@ extern "C" raer_gi* raer_gi_create(int device, int nf, const char* const* paths,
         delete g;
         return nullptr;
     }
+    int n_readers = 4;
+    if (const char* e = getenv("RAER_GI_READERS")) n_readers = std::max(1, std::min(16, atoi(e)));
+    g->readers.resize((size_t)n_readers);
+    for (GiReader& r : g->readers)
+        if (!r.buf.ensure(GI_CHUNK + GI_OVERLAP) || cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking) != cudaSuccess) {
+            set_error("stream / pinned memory");
+            delete g;
+            return nullptr;
+        }
     return g;
 }
 
@@ -611,47 +641,190 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     long long c_end = std::min<long long>(c_last + 65536 + 32, g->fsize[(size_t)f]);
     if (c_end <= c_beg) return RAER_OK;
     const size_t nbytes = (size_t)(c_end - c_beg);
+    // The range is read in chunks of 8 MB by a few threads. Each has one small pinned buffer and a stream of its own:
+    // pread -> H2D copy -> (in chunk order) the BGZF block headers of its chunk, 18 bytes each, chained through BSIZE. A
+    // chunk is read with 64 KiB of overlap so that every block that starts in it is complete. This thread collects the
+    // block tables and launches the inflate kernel whenever a wave of blocks is ready, so the device inflates while the
+    // rest of the range is still being read.
     const double t0 = raer::now_seconds();
-    if (!S.hcomp.ensure(nbytes + 64)) { set_error("pinned allocation of %zu bytes failed", nbytes); return RAER_ERR_CUDA; }
-    if (fseek(g->fp[(size_t)f], (long)c_beg, SEEK_SET) != 0 || fread(S.hcomp.p, 1, nbytes, g->fp[(size_t)f]) != nbytes) {
-        set_error("read error in BAM file");
-        return RAER_ERR_IO;
-    }
-    memset(S.hcomp.p + nbytes, 0, 64);
-    // ---- BGZF block table (18-byte headers chained through BSIZE)
+    const size_t CH = GI_CHUNK, OV = GI_OVERLAP;
+    const int n_chunks = (int)((nbytes + CH - 1) / CH);
+    const int n_readers = std::max(1, std::min((int)g->readers.size(), n_chunks));
+    const size_t blk_guess = nbytes / 4096 + 1024;
+    if ((rc = S.comp.ensure(nbytes + OV + 64)) || (rc = S.ubuf.ensure(std::max(S.ubuf.cap, nbytes * 5 + (1u << 20)))) ||
+        (rc = S.blk.ensure(blk_guess * sizeof(GiBlock))) || (rc = S.status.ensure(blk_guess * 4)) ||
+        (rc = S.queue.ensure(((size_t)n_chunks + 2) * 4)) || (rc = g->small.ensure(256)))
+        return rc;
+    if (!S.hblk.ensure(blk_guess * sizeof(GiBlock))) { set_error("pinned allocation failed"); return RAER_ERR_CUDA; }
+    GCK(cudaMemsetAsync(S.queue.p, 0, ((size_t)n_chunks + 2) * 4, st));
+    GCK(cudaMemsetAsync((uint8_t*)S.comp.p + nbytes, 0, 64, st));
+    GCK(cudaStreamSynchronize(st));  // the readers copy on their own streams
+    g->t_alloc += raer::now_seconds() - t0;
+    const double t1 = raer::now_seconds();
     std::vector<GiBlock> blocks;
     std::vector<long long> blk_c;  // file offset of every block
+    blocks.reserve(nbytes / 12000 + 64);
+    blk_c.reserve(nbytes / 12000 + 64);
     unsigned long long u = 0;
-    size_t o = 0;
-    while (o + 18 <= nbytes && (long long)o + c_beg <= c_last) {
-        const uint8_t* h = S.hcomp.p + o;
-        if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { set_error("corrupt BGZF block header"); return RAER_ERR_IO; }
-        const int xlen = h[10] | (h[11] << 8);
-        if (o + 12 + (size_t)xlen > nbytes) { set_error("truncated BGZF file (incomplete block at the end)"); return RAER_ERR_IO; }
-        int bsize = -1;
-        for (int e = 0; e + 4 <= xlen;) {
-            const int slen = h[12 + e + 2] | (h[12 + e + 3] << 8);
-            if (h[12 + e] == 'B' && h[13 + e] == 'C' && slen == 2) bsize = h[12 + e + 4] | (h[12 + e + 5] << 8);
-            e += 4 + slen;
+    size_t o = 0;            // next block header, relative to c_beg
+    int turn = 0;            // chunk whose headers are scanned next
+    bool scan_done = false;  // the block that holds the last record of the contig has been seen
+    int fail = 0;
+    std::string fail_msg;
+    std::mutex mu;
+    std::condition_variable cv;
+    const int fd = fileno(g->fp[(size_t)f]);
+    uint8_t* const d_comp = (uint8_t*)S.comp.p;
+    auto reader = [&](int t) {
+        cudaSetDevice(g->device);
+        GiReader& RD = g->readers[(size_t)t];
+        for (int i = t; i < n_chunks; i += n_readers) {
+            const size_t lo = (size_t)i * CH, len = std::min(CH + OV, nbytes - lo);
+            const char* why = nullptr;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (fail || scan_done) break;
+            }
+            size_t got = 0;
+            while (got < len) {
+                const ssize_t r = pread(fd, RD.buf.p + got, len - got, (off_t)(c_beg + (long long)(lo + got)));
+                if (r <= 0) break;
+                got += (size_t)r;
+            }
+            if (got != len) why = "read error in BAM file";
+            if (!why && (cudaMemcpyAsync(d_comp + lo, RD.buf.p, len, cudaMemcpyHostToDevice, RD.st) != cudaSuccess ||
+                         cudaStreamSynchronize(RD.st) != cudaSuccess))
+                why = "H2D copy of compressed blocks failed";
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&]() { return turn == i || fail || scan_done; });
+            if (fail || scan_done) break;
+            const size_t hi = std::min(lo + CH, nbytes);  // blocks that start before hi are this chunk's
+            while (!why && o < hi) {
+                if (!(o + 18 <= nbytes && (long long)o + c_beg <= c_last)) { scan_done = true; break; }
+                const uint8_t* h = RD.buf.p + (o - lo);
+                const size_t avail = lo + len;
+                if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { why = "corrupt BGZF block header"; break; }
+                const int xlen = h[10] | (h[11] << 8);
+                if (o + 12 + (size_t)xlen > avail) { why = "truncated BGZF file (incomplete block at the end)"; break; }
+                int bsize = -1;
+                for (int e = 0; e + 4 <= xlen;) {
+                    const int slen = h[12 + e + 2] | (h[12 + e + 3] << 8);
+                    if (h[12 + e] == 'B' && h[13 + e] == 'C' && slen == 2) bsize = h[12 + e + 4] | (h[12 + e + 5] << 8);
+                    e += 4 + slen;
+                }
+                if (bsize < 0 || bsize + 1 < 12 + xlen + 2 + 8) { why = "corrupt BGZF block (BSIZE)"; break; }
+                if (o + (size_t)bsize + 1 > avail) { why = "truncated BGZF file (incomplete block at the end)"; break; }
+                const uint32_t isize = h_le32(h + bsize + 1 - 4);
+                if (isize > 65536u) { why = "corrupt BGZF block (ISIZE above 64 KiB)"; break; }
+                GiBlock b;
+                b.c_off = o + 12 + (size_t)xlen;
+                b.c_len = (uint32_t)(bsize + 1 - 12 - xlen - 8);
+                b.u_off = u;
+                b.u_len = isize;
+                blocks.push_back(b);
+                blk_c.push_back(c_beg + (long long)o);
+                u += isize;
+                o += (size_t)bsize + 1;
+            }
+            if (why) { fail = 1; fail_msg = why; }
+            turn = i + 1;
+            lk.unlock();
+            cv.notify_all();
         }
-        if (bsize < 0 || bsize + 1 < 12 + xlen + 2 + 8) { set_error("corrupt BGZF block (BSIZE)"); return RAER_ERR_IO; }
-        if (o + (size_t)bsize + 1 > nbytes) { set_error("truncated BGZF file (incomplete block at the end)"); return RAER_ERR_IO; }
-        const uint32_t isize = h_le32(h + bsize + 1 - 4);
-        if (isize > 65536u) { set_error("corrupt BGZF block (ISIZE above 64 KiB)"); return RAER_ERR_IO; }
-        GiBlock b;
-        b.c_off = o + 12 + (size_t)xlen;
-        b.c_len = (uint32_t)(bsize + 1 - 12 - xlen - 8);
-        b.u_off = u;
-        b.u_len = isize;
-        blocks.push_back(b);
-        blk_c.push_back(c_beg + (long long)o);
-        u += isize;
-        o += (size_t)bsize + 1;
+    };
+    std::vector<std::thread> readers;
+    for (int t = 0; t < n_readers; ++t) readers.emplace_back(reader, t);
+    struct Joiner {
+        std::vector<std::thread>& th;
+        std::mutex& mu;
+        std::condition_variable& cv;
+        int& fail;
+        ~Joiner() {
+            { std::lock_guard<std::mutex> lk(mu); if (!fail) fail = 2; }
+            cv.notify_all();
+            for (auto& t : th) if (t.joinable()) t.join();
+        }
+    };
+    static int n_sm = 0;
+    if (!n_sm) {
+        cudaDeviceProp prop;
+        n_sm = cudaGetDeviceProperties(&prop, g->device) == cudaSuccess ? prop.multiProcessorCount : 148;
+        cudaFuncSetAttribute(k_gi_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_WARPS * GI_WARP_WORDS * 4);
     }
+    // b_lo .. b_hi: entries already staged in S.hblk (or, beyond its capacity, passed in `extra`)
+    int n_launch = 0;
+    auto launch_inflate = [&](size_t b_lo, size_t b_hi, const GiBlock* extra) -> int {
+        if (b_hi <= b_lo) return 0;
+        int r2;
+        if (b_hi * sizeof(GiBlock) > S.blk.cap || b_hi * 4 > S.status.cap) {  // more (smaller) blocks than guessed: regrow, keep contents
+            DBufG nb, ns;
+            if ((r2 = nb.ensure(b_hi * 2 * sizeof(GiBlock))) || (r2 = ns.ensure(b_hi * 2 * 4))) return r2;
+            GCK(cudaStreamSynchronize(st));
+            GCK(cudaMemcpy(nb.p, S.blk.p, b_lo * sizeof(GiBlock), cudaMemcpyDeviceToDevice));
+            GCK(cudaMemcpy(ns.p, S.status.p, b_lo * 4, cudaMemcpyDeviceToDevice));
+            std::swap(nb.p, S.blk.p); std::swap(nb.cap, S.blk.cap);
+            std::swap(ns.p, S.status.p); std::swap(ns.cap, S.status.cap);
+        }
+        const GiBlock* src = extra ? extra : (const GiBlock*)S.hblk.p + b_lo;  // pinned: a pageable source would wait for the stream
+        GCK(cudaMemcpyAsync((GiBlock*)S.blk.p + b_lo, src, (b_hi - b_lo) * sizeof(GiBlock), cudaMemcpyHostToDevice, st));
+        const int nbk = (int)(b_hi - b_lo);
+        const int grid = std::min<int>(n_sm, nbk);
+        k_gi_inflate<<<grid, GI_WARPS * 32, GI_WARPS * GI_WARP_WORDS * 4, st>>>((const uint8_t*)S.comp.p, (const GiBlock*)S.blk.p + b_lo, nbk,
+                                                                              (uint8_t*)S.ubuf.p, (int*)S.status.p + b_lo,
+                                                                              (unsigned*)S.queue.p + n_launch);
+        ++n_launch;
+        ++g->launches;
+        return 0;
+    };
+    size_t launched = 0;
+    bool too_small = false;
+    double t_wait = 0;
+    {
+        Joiner joiner{readers, mu, cv, fail};
+        const size_t wave = (size_t)n_sm * GI_WARPS;
+        while (true) {
+            size_t have;
+            bool finished;
+            std::vector<GiBlock> extra;
+            {
+                const double tw = raer::now_seconds();
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&]() { return fail || scan_done || turn == n_chunks || blocks.size() - launched >= wave; });
+                t_wait += raer::now_seconds() - tw;
+                if (fail) { set_error("%s", fail_msg.c_str()); return fail_msg.find("H2D") != std::string::npos ? RAER_ERR_CUDA : RAER_ERR_IO; }
+                have = blocks.size();
+                finished = scan_done || turn == n_chunks;
+                if (u + 64 > S.ubuf.cap) too_small = true;
+                if (!too_small && have > launched) {
+                    if (have * sizeof(GiBlock) <= S.hblk.cap)
+                        memcpy(S.hblk.p + launched * sizeof(GiBlock), blocks.data() + launched, (have - launched) * sizeof(GiBlock));
+                    else
+                        extra.assign(blocks.begin() + (long)launched, blocks.begin() + (long)have);
+                }
+            }
+            if (!too_small && have > launched && (finished || have - launched >= wave)) {
+                if (n_launch >= n_chunks + 1) { GCK(cudaStreamSynchronize(st)); GCK(cudaMemsetAsync(S.queue.p, 0, ((size_t)n_chunks + 2) * 4, st)); n_launch = 0; }
+                if ((rc = launch_inflate(launched, have, extra.empty() ? nullptr : extra.data()))) return rc;
+                if (!extra.empty()) GCK(cudaStreamSynchronize(st));
+                launched = have;
+            }
+            if (finished) break;
+        }
+    }
+    if (!scan_done && (o + 18 <= nbytes && (long long)o + c_beg <= c_last)) { set_error("truncated BGZF file (incomplete block at the end)"); return RAER_ERR_IO; }
+    g->t_read += t_wait;
+    g->t_table += raer::now_seconds() - t1 - t_wait;
     if (blocks.empty()) return RAER_OK;
     if (u >= (1ull << 32) - 65536) return RAER_GI_FALLBACK;  // record offsets are 32 bit here
+    if (too_small) {  // inflated size beyond the guess: the compressed bytes are on the device, inflate everything again
+        GCK(cudaStreamSynchronize(st));
+        if ((rc = S.ubuf.ensure((size_t)u + 64))) return rc;
+        GCK(cudaMemsetAsync(S.queue.p, 0, 8, st));
+        n_launch = 0;
+        if ((rc = launch_inflate(0, blocks.size(), blocks.data()))) return rc;
+        GCK(cudaStreamSynchronize(st));
+    }
     S.u_total = u;
-    g->t_read += raer::now_seconds() - t0;
     g->compressed += (int64_t)o;
     g->inflated += (int64_t)u;
     // ---- start points: the first record, and every linear-index entry inside the range, as inflated offsets
@@ -666,64 +839,78 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
         *out = blocks[k].u_off + (v & 0xffff);
         return true;
     };
-    std::vector<unsigned long long> sp;
     unsigned long long u_first = 0, u_last = u;
     if (!v2u(R.vbeg, &u_first)) return RAER_GI_FALLBACK;
     if (!v2u(R.vend, &u_last)) u_last = u;
-    sp.push_back(u_first);
+    // Start points of the record walk. htslib-style writers never let a record straddle two BGZF blocks (bgzf_flush_try
+    // before every record), so every block start is a record start: try those first -- the walk verifies the guess,
+    // every chain has to land exactly on the next start point -- and fall back to the linear index of the .bai, whose
+    // entries are record starts by construction (one per 16 kb window that has reads).
+    std::vector<unsigned long long> sp_blk, sp_lin;
+    sp_blk.push_back(u_first);
+    for (const GiBlock& b : blocks)
+        if (b.u_off > u_first && b.u_off < u_last && b.u_len) sp_blk.push_back(b.u_off);
+    sp_lin.push_back(u_first);
     for (uint64_t v : R.lin) {
         unsigned long long x;
-        if (v > R.vbeg && v < R.vend && v2u(v, &x) && x > u_first && x < u_last) sp.push_back(x);
+        if (v > R.vbeg && v < R.vend && v2u(v, &x) && x > u_first && x < u_last) sp_lin.push_back(x);
     }
-    std::sort(sp.begin(), sp.end());
-    sp.erase(std::unique(sp.begin(), sp.end()), sp.end());
-    const int nsp = (int)sp.size();
-    sp.push_back(u_last);
-    // ---- device: inflate
-    if ((rc = S.comp.ensure(nbytes + 64)) || (rc = S.blk.ensure(blocks.size() * sizeof(GiBlock))) || (rc = S.ubuf.ensure((size_t)u + 64)) ||
-        (rc = S.status.ensure(blocks.size() * 4)) || (rc = S.sp.ensure(sp.size() * 8)) || (rc = S.cnt.ensure((size_t)nsp * 4 + 16)) ||
-        (rc = S.base.ensure((size_t)nsp * 4 + 16)) || (rc = g->small.ensure(256)))
-        return rc;
-    GCK(cudaMemcpyAsync(S.comp.p, S.hcomp.p, nbytes + 64, cudaMemcpyHostToDevice, st));
-    GCK(cudaMemcpyAsync(S.blk.p, blocks.data(), blocks.size() * sizeof(GiBlock), cudaMemcpyHostToDevice, st));
+    std::sort(sp_lin.begin(), sp_lin.end());
+    sp_lin.erase(std::unique(sp_lin.begin(), sp_lin.end()), sp_lin.end());
+    sp_blk.push_back(u_last);
+    sp_lin.push_back(u_last);
+    const bool try_blocks = !getenv("RAER_GI_LINEAR_WALK");
+    std::vector<unsigned long long>& sp = try_blocks ? sp_blk : sp_lin;
+    int nsp = (int)sp.size() - 1;
+    const size_t sp_cap = std::max(sp_blk.size(), sp_lin.size());
+    const double t2 = raer::now_seconds();
+    if ((rc = S.sp.ensure(sp_cap * 8)) || (rc = S.cnt.ensure(sp_cap * 4 + 16)) || (rc = S.base.ensure(sp_cap * 4 + 16))) return rc;
+    g->t_alloc += raer::now_seconds() - t2;
+    const double t3 = raer::now_seconds();
     GCK(cudaMemcpyAsync(S.sp.p, sp.data(), sp.size() * 8, cudaMemcpyHostToDevice, st));
     GCK(cudaMemsetAsync(g->small.p, 0, 256, st));
-    unsigned long long* d_small = (unsigned long long*)g->small.p;  // [0] queue, [1] flags, [2] aligned bases, [3] max span, [4..] totals
-    {
-        static int n_sm = 0;
-        if (!n_sm) {
-            cudaDeviceProp prop;
-            n_sm = cudaGetDeviceProperties(&prop, g->device) == cudaSuccess ? prop.multiProcessorCount : 148;
-            cudaFuncSetAttribute(k_gi_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_WARPS * GI_WARP_WORDS * 4);
-        }
-        const int grid = std::min<int>(n_sm, (int)((blocks.size() + GI_WARPS - 1) / GI_WARPS));
-        k_gi_inflate<<<grid, GI_WARPS * 32, GI_WARPS * GI_WARP_WORDS * 4, st>>>((const uint8_t*)S.comp.p, (const GiBlock*)S.blk.p,
-                                                                              (int)blocks.size(), (uint8_t*)S.ubuf.p, (int*)S.status.p,
-                                                                              (unsigned*)d_small);
-        ++g->launches;
-    }
+    unsigned long long* d_small = (unsigned long long*)g->small.p;  // [1] flags, [2] aligned bases, [3] max span, [4..] totals
     // ---- record table
     int* d_flags = (int*)(d_small + 1);
-    k_gw_walk<false><<<(nsp + 127) / 128, 128, 0, st>>>((const uint8_t*)S.ubuf.p, u_last, (const unsigned long long*)S.sp.p, nsp,
-                                                         (uint32_t*)S.cnt.p, nullptr, nullptr, d_flags);
-    ++g->launches;
-    if ((rc = g_scan<false>(g, S, (const uint32_t*)S.cnt.p, (uint32_t*)S.base.p, nsp, d_small + 4))) return rc;
     std::vector<int> status(blocks.size());
     GCK(cudaMemcpyAsync(status.data(), S.status.p, blocks.size() * 4, cudaMemcpyDeviceToHost, st));
-    GCK(cudaMemcpyAsync(g->h_small, d_small, 64, cudaMemcpyDeviceToHost, st));
-    GCK(cudaStreamSynchronize(st));
-    for (size_t k = 0; k < status.size(); ++k)
-        if (status[k] != 0) { set_error("inflate failed (corrupt BGZF block, device code %d)", status[k]); return RAER_ERR_IO; }
-    if (g->h_small[1] & 1) { set_error("corrupt BAM record"); return RAER_ERR_IO; }
+    for (int attempt = try_blocks ? 0 : 1; attempt < 2; ++attempt) {
+        std::vector<unsigned long long>& pts = attempt == 0 ? sp_blk : sp_lin;
+        nsp = (int)pts.size() - 1;
+        if (attempt == 1) {
+            GCK(cudaMemcpyAsync(S.sp.p, pts.data(), pts.size() * 8, cudaMemcpyHostToDevice, st));
+            GCK(cudaMemsetAsync(d_flags, 0, 8, st));
+        }
+        k_gw_walk<false><<<(nsp + 127) / 128, 128, 0, st>>>((const uint8_t*)S.ubuf.p, u_last, (const unsigned long long*)S.sp.p, nsp,
+                                                             (uint32_t*)S.cnt.p, nullptr, nullptr, d_flags);
+        ++g->launches;
+        if ((rc = g_scan<false>(g, S, (const uint32_t*)S.cnt.p, (uint32_t*)S.base.p, nsp, d_small + 4))) return rc;
+        GCK(cudaMemcpyAsync(g->h_small, d_small, 64, cudaMemcpyDeviceToHost, st));
+        GCK(cudaStreamSynchronize(st));
+        if (attempt == 0)  // the inflate results are in by now
+            for (size_t k = 0; k < status.size(); ++k)
+                if (status[k] != 0) { set_error("inflate failed (corrupt BGZF block, device code %d)", status[k]); return RAER_ERR_IO; }
+        if (!(g->h_small[1] & (1 | 32))) break;
+        if (attempt == 0) { ++g->walk_retries; continue; }  // some record straddles two blocks: walk from the index entries
+        if (g->h_small[1] & 1) { set_error("corrupt BAM record"); return RAER_ERR_IO; }
+        return RAER_GI_FALLBACK;  // the index and the records disagree: the host stream reads them one by one
+    }
+    if (!try_blocks)
+        for (size_t k = 0; k < status.size(); ++k)
+            if (status[k] != 0) { set_error("inflate failed (corrupt BGZF block, device code %d)", status[k]); return RAER_ERR_IO; }
     S.n_rec = (long long)g->h_small[4];
     g->records += S.n_rec;
+    g->t_inflate += raer::now_seconds() - t3;
     if (S.n_rec == 0) return RAER_OK;
+    const double t4 = raer::now_seconds();
     const size_t nr = (size_t)S.n_rec;
     if ((rc = S.rec_off.ensure(nr * 4)) || (rc = S.pass.ensure(nr * 4)) || (rc = S.pidx.ensure(nr * 4)) || (rc = S.r_pos.ensure(nr * 4)) ||
         (rc = S.r_end.ensure(nr * 4)) || (rc = S.cpos.ensure(nr * 4)) || (rc = S.kept.ensure(nr * 4)) || (rc = S.kidx.ensure(nr * 4)) ||
         (rc = S.ncig.ensure(nr * 4)) || (rc = S.coff.ensure(nr * 4)) || (rc = S.sqb.ensure(nr * 4)) || (rc = S.soff.ensure(nr * 4)) ||
         (rc = S.elig.ensure(nr * 4)) || (rc = S.eidx.ensure(nr * 4)) || (rc = S.prevpos.ensure(nr * 4)))
         return rc;
+    g->t_alloc += raer::now_seconds() - t4;
+    const double t5 = raer::now_seconds();
     k_gw_walk<true><<<(nsp + 127) / 128, 128, 0, st>>>((const uint8_t*)S.ubuf.p, u_last, (const unsigned long long*)S.sp.p, nsp, nullptr,
                                                         (const uint32_t*)S.base.p, (uint32_t*)S.rec_off.p, d_flags);
     GpConf C = C0;
@@ -743,6 +930,8 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     S.aligned_bases = (int64_t)g->h_small[2];
     S.max_span = (int)g->h_small[3];
     S.n_pass = (long long)g->h_small[5];
+    g->t_pass += raer::now_seconds() - t5;
+    const double t6 = raer::now_seconds();
     k_gp_kept<<<gr, 256, 0, st>>>((const uint8_t*)S.ubuf.p, (const uint32_t*)S.rec_off.p, (const uint32_t*)S.pass.p,
                                   (const uint32_t*)S.pidx.p, (const int32_t*)S.r_pos.p, (const int32_t*)S.r_end.p,
                                   (const int32_t*)S.cpos.p, S.n_rec, S.n_pass, C, S.max_span, (uint32_t*)S.kept.p, (uint32_t*)S.ncig.p,
@@ -761,6 +950,7 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     S.n_cig = (long long)g->h_small[5];
     S.n_sq = (long long)g->h_small[6];
     S.n_elig = (long long)g->h_small[7];
+    g->t_kept += raer::now_seconds() - t6;
     return RAER_OK;
 }
 
@@ -836,6 +1026,7 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
         return rc;
     unsigned long long* d_small = (unsigned long long*)g->small.p;
     GCK(cudaMemsetAsync(d_small, 0, 256, st));
+    const double t7 = raer::now_seconds();
     long long c0 = 0, s0 = 0;
     for (int f = 0; f < nf; ++f) {
         FileStage& S = g->stage[(size_t)f];
@@ -891,7 +1082,9 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
     b->pair_b = (const int32_t*)g->pair_b.p;
     b->n_pairs = (int64_t)g->h_small[4];
     b->n_aligned_bases = *aligned_bases;
-    return gi_maxend(g, b);
+    rc = gi_maxend(g, b);
+    g->t_write += raer::now_seconds() - t7;
+    return rc;
 }
 
 __global__ void k_gp_ends(const raer_read_hdr* __restrict__ hdr, long long n, uint32_t* __restrict__ out) {

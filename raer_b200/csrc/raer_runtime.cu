@@ -980,6 +980,17 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             const raer::RegionIndex::Chr* rchr = has_ridx ? ridx.find(names[c]) : nullptr;
             if (has_ridx && !rchr) continue;  // no site on this contig: nothing can be written
             if (a->poll && a->poll(a->poll_ctx)) { set_error("interrupted"); rc = RAER_ERR_INTERRUPT; break; }
+            if (has_ridx) {
+                // a sparse site list reads a few blocks per site through the index (Ingest::set_jumps); inflating the
+                // whole contig pays only when the intervals to visit cover most of it anyway
+                int64_t covered = 0;
+                for (const auto& iv : raer::jump_intervals(rchr)) covered += (int64_t)iv.second - iv.first;
+                if (covered * 2 < (int64_t)lens[(size_t)c]) {
+                    ++out->n_host_contigs;
+                    rc = host_contig(c);
+                    continue;
+                }
+            }
             for (int f = 0; f < nf; ++f) ftid[(size_t)f] = c;
             raer_read_batch b;
             const uint32_t* d_sites = nullptr;

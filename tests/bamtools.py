@@ -211,6 +211,68 @@ def write_bam(path, header_text: str, refs, recs: List[Rec], block_payload: int 
     return path
 
 
+def write_bam_straddling(path, header_text: str, refs, recs: List[Rec], block_payload: int = 3000):
+    """Like write_bam, but the record stream is cut into blocks of exactly block_payload bytes wherever that falls, so
+    records straddle BGZF blocks (legal BAM; htsjdk-style writers produce it). Writes <path> and <path>.bai."""
+    hdr = bytearray(b"BAM\x01")
+    tb = header_text.encode()
+    hdr += struct.pack("<i", len(tb)) + tb + struct.pack("<i", len(refs))
+    for name, L in refs:
+        nb = name.encode() + b"\0"
+        hdr += struct.pack("<i", len(nb)) + nb + struct.pack("<i", L)
+    out = bytearray(_bgzf_block(bytes(hdr)))
+    stream = bytearray()
+    starts = []
+    for r in recs:
+        starts.append(len(stream))
+        stream += struct.pack("<i", len(r.raw)) + r.raw
+    coffs = []
+    for k in range(0, len(stream), block_payload):
+        coffs.append(len(out))
+        out += _bgzf_block(bytes(stream[k:k + block_payload]))
+    coffs.append(len(out))
+    out += _EOF
+
+    def voff(x):
+        return (coffs[x // block_payload] << 16) | (x % block_payload)
+
+    bins = [dict() for _ in refs]
+    lin = [dict() for _ in refs]
+    for i, r in enumerate(recs):
+        if r.tid < 0:
+            continue
+        vbeg = voff(starts[i])
+        vend = voff(starts[i + 1]) if i + 1 < len(recs) else voff(len(stream))
+        end = r.pos + (r.ref_len() or 1)
+        ch = bins[r.tid].setdefault(_reg2bin(r.pos, end), [])
+        if ch and ch[-1][1] == vbeg:
+            ch[-1][1] = vend
+        else:
+            ch.append([vbeg, vend])
+        for w in range(r.pos >> 14, ((end - 1) >> 14) + 1):
+            if w not in lin[r.tid] or vbeg < lin[r.tid][w]:
+                lin[r.tid][w] = vbeg
+    with open(path, "wb") as fh:
+        fh.write(out)
+    bai = bytearray(b"BAI\x01" + struct.pack("<i", len(refs)))
+    for t in range(len(refs)):
+        bai += struct.pack("<i", len(bins[t]))
+        for b, chunks in sorted(bins[t].items()):
+            bai += struct.pack("<Ii", b, len(chunks))
+            for vb, ve in chunks:
+                bai += struct.pack("<QQ", vb, ve)
+        n_intv = (max(lin[t]) + 1) if lin[t] else 0
+        bai += struct.pack("<i", n_intv)
+        last = 0
+        for w in range(n_intv):
+            if w in lin[t]:
+                last = lin[t][w]
+            bai += struct.pack("<Q", last)
+    with open(path + ".bai", "wb") as fh:
+        fh.write(bai)
+    return path
+
+
 def filter_bam(src: str, dst: str, keep: Callable[[Rec], bool]):
     text, refs, recs = read_bam(src)
     return write_bam(dst, text, refs, [r for r in recs if keep(r)])

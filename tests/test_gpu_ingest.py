@@ -132,3 +132,25 @@ def test_device_ingest_falls_back_where_it_must(ext, monkeypatch):
     dev, host = _both(pc, monkeypatch)
     assert dev["timing"]["n_host_contigs"] >= 1
     _columns_equal(dev, host)
+
+
+def test_records_straddling_bgzf_blocks(ext, tmp_path, monkeypatch):
+    """the record walk first assumes every BGZF block starts with a record (htslib writers) and verifies it; a file
+    whose records straddle blocks fails that check and is walked from the linear index of the .bai instead"""
+    hdr, refs, recs = bamtools.read_bam(ext.bam1)
+    p = str(tmp_path / "straddle.bam")
+    bamtools.write_bam_straddling(p, hdr, refs, recs, block_payload=3000)
+    pc = prepare_pileup_call(p, ext.fasta)
+    dev, host = _both(pc, monkeypatch)
+    assert dev["timing"]["n_device_contigs"] >= 1 and dev["timing"]["n_host_contigs"] == 0
+    _columns_equal(dev, host)
+    base = _cabi.pileup(prepare_pileup_call(ext.bam1, ext.fasta))
+    _columns_equal(dev, base)
+
+
+def test_linear_index_walk(ext, monkeypatch):
+    monkeypatch.setenv("RAER_GI_LINEAR_WALK", "1")
+    pc = prepare_pileup_call([ext.bam1, ext.bam2], ext.fasta)
+    dev, host = _both(pc, monkeypatch)
+    assert dev["timing"]["n_device_contigs"] >= 1
+    _columns_equal(dev, host)
