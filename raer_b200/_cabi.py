@@ -319,25 +319,32 @@ def pileup(pc, device: int = 0, host_threads: int = 0, overlap_mode: int = 1, sh
                 return np.zeros(0, dtype=dt)
             return np.ctypeslib.as_array(ptr, shape=(cnt,)).astype(dt, copy=True)
 
+        def chars(ptr, width, cnt):
+            """fixed-width ASCII column -> numpy unicode array (bytes widened to UCS4 in one vectorised pass)"""
+            if cnt == 0:
+                return np.zeros(0, dtype=f"<U{width}")
+            raw = np.frombuffer(C.string_at(ptr, cnt * width), dtype=np.uint8)
+            return raw.astype("<u4").view(f"<U{width}")
+
         tid = arr(r.tid, np.int32, nr)
         out = {
-            "nrows": nr, "contigs": names, "tid": tid, "seqname": [names[t] for t in tid],
+            "nrows": nr, "contigs": names, "tid": tid,
+            "seqname": np.asarray(names, dtype=str)[tid] if nr else np.zeros(0, dtype=str),
             "pos": arr(r.pos, np.int32, nr),
-            "strand": np.frombuffer(C.string_at(r.strand, nr), dtype="S1").astype(str) if nr else np.zeros(0, dtype=str),
-            "REF": np.frombuffer(C.string_at(r.ref, nr), dtype="S1").astype(str) if nr else np.zeros(0, dtype=str),
+            "strand": chars(r.strand, 1, nr),
+            "REF": chars(r.ref, 1, nr),
             "rpbz": arr(r.rpbz, np.float64, nr), "vdb": arr(r.vdb, np.float64, nr), "sor": arr(r.sor, np.float64, nr),
             "files": [],
         }
         if nr:
-            alt_raw = C.string_at(r.alt, nr * n * 12)
+            alt = chars(r.alt, 12, nr * n)
             cnt = np.ctypeslib.as_array(r.counts, shape=(n, nr, 8)).copy()
         for f in range(n):
             d = {}
             if nr:
-                blk = np.frombuffer(alt_raw[f * nr * 12:(f + 1) * nr * 12], dtype="S12")
-                d["ALT"] = blk.astype(str)
+                d["ALT"] = alt[f * nr:(f + 1) * nr]
                 for k, nm in enumerate(COUNT_COLS):
-                    d[nm] = cnt[f, :, k].astype(np.int32)
+                    d[nm] = cnt[f, :, k]
             else:
                 d["ALT"] = np.zeros(0, dtype=str)
                 for nm in COUNT_COLS:

@@ -358,23 +358,36 @@ __global__ void __launch_bounds__(GI_WARPS * 32, 1) k_gi_inflate(const uint8_t* 
                 if (total == (uint32_t)n) {  // literals only
                     for (uint32_t j = lane; j < total; j += 32) dst[base + j] = (uint8_t)(tok[j] >> 9);
                 } else {
-                    for (uint32_t j = lane; j < total; j += 32) {
-                        int pos = (int)j;
-                        uint32_t val;
-                        while (true) {
-                            int t = 0;  // last token with pre[t] <= pos
+                    // four bytes per lane in flight: the loads of the bytes that lie before the batch are independent
+                    for (uint32_t j0 = lane; j0 < total; j0 += 128) {
+                        int src[4];
+                        uint32_t val[4];
 #pragma unroll
-                            for (int step = GI_TOK / 2; step > 0; step >>= 1)
-                                if (pre[t + step] <= (uint32_t)pos) t += step;
-                            const uint32_t tk = tok[t];
-                            if ((tk & 511u) == 1u) { val = (tk >> 9) & 255u; break; }
-                            const int dist = (int)(tk >> 17) + 1;
-                            int within = pos - (int)pre[t];
-                            if (within >= dist) within %= dist;
-                            pos = (int)pre[t] - dist + within;
-                            if (pos < 0) { val = __ldcg(dst + (int)base + pos); break; }  // written by an earlier batch
+                        for (int q = 0; q < 4; ++q) {
+                            int pos = (int)(j0 + 32 * q);
+                            src[q] = 0;
+                            val[q] = 0;
+                            if ((uint32_t)pos >= total) continue;
+                            while (true) {
+                                int t = 0;  // last token with pre[t] <= pos
+#pragma unroll
+                                for (int step = GI_TOK / 2; step > 0; step >>= 1)
+                                    if (pre[t + step] <= (uint32_t)pos) t += step;
+                                const uint32_t tk = tok[t];
+                                if ((tk & 511u) == 1u) { val[q] = (tk >> 9) & 255u; break; }
+                                const int dist = (int)(tk >> 17) + 1;
+                                int within = pos - (int)pre[t];
+                                if (within >= dist) within %= dist;
+                                pos = (int)pre[t] - dist + within;
+                                if (pos < 0) { src[q] = pos; break; }  // written by an earlier batch
+                            }
                         }
-                        dst[base + j] = (uint8_t)val;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (src[q] < 0) val[q] = __ldcg(dst + (int)base + src[q]);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (j0 + 32 * q < total) dst[base + j0 + 32 * q] = (uint8_t)val[q];
                     }
                 }
             }

@@ -92,7 +92,7 @@ def result_from_columns(cols: dict, sample_names: List[str]) -> PileupResult:
         m = np.stack(mats, axis=1) if len(mats[0]) else np.zeros((0, n), dtype=mats[0].dtype)
         (assays if name in ASSAY_COLS else extra)[name] = m
     return PileupResult(
-        seqnames=np.asarray(cols["seqname"], dtype=object).astype(str) if len(cols["seqname"]) else np.zeros(0, dtype=str),
+        seqnames=np.asarray(cols["seqname"], dtype=str) if len(cols["seqname"]) else np.zeros(0, dtype=str),
         pos=np.asarray(cols["pos"], dtype=np.int32), strand=np.asarray(cols["strand"]).astype(str),
         REF=np.asarray(cols["REF"]).astype(str), rpbz=np.asarray(cols["rpbz"], dtype=np.float64),
         vdb=np.asarray(cols["vdb"], dtype=np.float64), sor=np.asarray(cols["sor"], dtype=np.float64),
