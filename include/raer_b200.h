@@ -363,6 +363,10 @@ void raer_ctx_last_timing(raer_ctx* ctx, double* h2d_s, double* kernel_s, double
  * sam_itr_next (reference: src/plp.c:32-78 readaln -> sam_itr_next / sam_read1). */
 int raer_gpu_inflate(const uint8_t* comp, int64_t comp_len, const int64_t* c_off, const int32_t* c_len, const int64_t* u_off,
                      const int32_t* u_len, int32_t n_blocks, uint8_t* out, int64_t out_len, int32_t* status, double* kernel_ms);
+/* The device ingest allocates from the device's stream-ordered memory pool and keeps up to 8 GB of it, and a few
+ * page-locked staging buffers, for the next call of the process. This hands both back to the driver (e.g. from the
+ * unload hook of a binding). */
+void raer_trim_device_cache(int32_t device);
 /* same batch entry as raer_batch_pileup_device(), rows downloaded (what the device ingest calls per contig) */
 int raer_batch_pileup_device_rows(raer_ctx* ctx, const raer_bulk_conf* conf, const raer_read_batch* dev_batch, raer_rows* out,
                                   int64_t* launches);

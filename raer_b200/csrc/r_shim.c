@@ -410,3 +410,9 @@ void R_init_raer(DllInfo* dll) {
     R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);
     R_useDynamicSymbols(dll, FALSE);
 }
+
+/* library.dynam.unload(): give the device memory pool and the page-locked staging buffers back */
+void R_unload_raer(DllInfo* dll) {
+    (void)dll;
+    if (raer_device_count() > 0) raer_trim_device_cache(0);
+}

@@ -280,6 +280,9 @@ public:
     // jumps: the sorted, disjoint intervals wanted on the region's contig (site / region lists, see BamStream::set_jumps)
     bool open(const char* const* paths, const char* const* indexes, int threads, const char* region,
               const std::vector<std::pair<int32_t, int32_t>>* jumps = nullptr);
+    // headers only (names(), lengths(), file_names()): nothing is inflated beyond the header blocks, no batches can be read
+    bool open_headers(const char* const* paths);
+    const std::vector<std::string>& file_names(int i) const { return files_[i]->bs.names(); }
     // next contig with reads in any file (ascending tid of file 0's header); -1 when done
     int next_contig();
     // pack the next batch of the current contig; false when the contig is exhausted

@@ -714,6 +714,15 @@ bool Ingest::open(const char* const* paths, const char* const* indexes, int thre
     return true;
 }
 
+bool Ingest::open_headers(const char* const* paths) {
+    for (int i = 0; i < conf_.n_files; ++i) {
+        FilePending* f = new FilePending();
+        files_.push_back(f);
+        if (!f->bs.open(paths[i], 1, true)) return false;
+    }
+    return true;
+}
+
 double Ingest::wait_seconds() const {
     double t = 0;
     for (auto* f : files_) t += f->bs.wait_seconds();

@@ -827,9 +827,28 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
         if (v > 0) ic.target_reads = v;
     }
 
+    // ---- device ingest (raer_gingest.cu): whole contigs are inflated, parsed, filtered and packed by kernels; what that
+    // path does not cover falls back, contig by contig, to the host stream
+    // (a `region` is fine when it names a whole contig -- the per-chromosome calls of R/pileup.R:208-243 -- which is known
+    // once the headers are read; a coordinate range goes through the host stream and the index)
+    bool use_gi = a->shard_count <= 1 && !a->umi_tag && ic.n_mm_type == 0 && ic.n_mm == 0 &&
+                  !(a->region && strchr(a->region, ':')) && !getenv("RAER_SERIAL_INGEST") && !getenv("RAER_BATCH_READS");
+    if (const char* e = getenv("RAER_GPU_INGEST")) use_gi = use_gi && atoi(e) != 0;
+    if (use_gi) use_gi = raer::indexes_usable(a->bampaths, a->indexes, nf);
+
     double tm_open = raer::now_seconds();
+    int gi_only_contig = -1;
+    if (use_gi && a->region) {
+        raer::Ingest probe(ic);
+        if (!probe.open_headers(a->bampaths)) return RAER_ERR_IO;
+        const std::vector<std::string>& hn = probe.names();
+        for (size_t k = 0; k < hn.size() && gi_only_contig < 0; ++k)
+            if (hn[k] == a->region) gi_only_contig = (int)k;
+        if (gi_only_contig < 0) use_gi = false;  // not a plain contig name: the host path parses (or refuses) it
+    }
     raer::Ingest ing(ic);
-    if (!ing.open(a->bampaths, a->indexes, a->host_threads, a->region)) return RAER_ERR_IO;
+    // the device ingest reads the files itself: only the headers are needed here
+    if (!(use_gi ? ing.open_headers(a->bampaths) : ing.open(a->bampaths, a->indexes, a->host_threads, a->region))) return RAER_ERR_IO;
     tm_open = raer::now_seconds() - tm_open;
 
     double tm_ctx = raer::now_seconds();
@@ -939,15 +958,11 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
     bool parallel = !a->region && a->shard_count <= 1 && (n_workers >= 2 || (has_ridx && n_workers >= 1)) &&
                     !getenv("RAER_SERIAL_INGEST");
     if (parallel) parallel = raer::indexes_usable(a->bampaths, a->indexes, nf);  // single stream: no index needed
-    // ---- device ingest (raer_gingest.cu): whole contigs are inflated, parsed, filtered and packed by kernels; what that
-    // path does not cover falls back, contig by contig, to the host stream below
-    bool use_gi = !a->region && a->shard_count <= 1 && !a->umi_tag && ic.n_mm_type == 0 && ic.n_mm == 0 &&
-                  !getenv("RAER_SERIAL_INGEST") && !getenv("RAER_BATCH_READS");
-    if (const char* e = getenv("RAER_GPU_INGEST")) use_gi = use_gi && atoi(e) != 0;
-    if (use_gi) use_gi = raer::indexes_usable(a->bampaths, a->indexes, nf);
     if (use_gi) {
+        double t0c = raer::now_seconds();
         raer_gi* gi = raer_gi_create(a->device, nf, a->bampaths, a->indexes);
         if (!gi) rc = RAER_ERR_IO;
+        const double tm_gi_create = raer::now_seconds() - t0c;
         const std::vector<int32_t>& lens = ing.lengths();
         std::vector<int> ftid((size_t)nf);
         std::vector<int64_t> file_off((size_t)nf + 1);
@@ -979,6 +994,7 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
         for (int c = 0; rc == RAER_OK && c < (int)names.size(); ++c) {
             const raer::RegionIndex::Chr* rchr = has_ridx ? ridx.find(names[c]) : nullptr;
             if (has_ridx && !rchr) continue;  // no site on this contig: nothing can be written
+            if (gi_only_contig >= 0 && c != gi_only_contig) continue;
             if (a->poll && a->poll(a->poll_ctx)) { set_error("interrupted"); rc = RAER_ERR_INTERRUPT; break; }
             if (has_ridx) {
                 // a sparse site list reads a few blocks per site through the index (Ingest::set_jumps); inflating the
@@ -991,7 +1007,17 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
                     continue;
                 }
             }
-            for (int f = 0; f < nf; ++f) ftid[(size_t)f] = c;
+            for (int f = 0; f < nf; ++f) {  // each file resolves the name in its own header, like sam_itr_querys
+                ftid[(size_t)f] = c;
+                const std::vector<std::string>& fn = ing.file_names(f);
+                if (f > 0 && !((size_t)c < fn.size() && fn[(size_t)c] == names[c])) {
+                    ftid[(size_t)f] = -1;
+                    for (size_t k = 0; k < fn.size(); ++k)
+                        if (fn[k] == names[c]) { ftid[(size_t)f] = (int)k; break; }
+                    if (ftid[(size_t)f] < 0) { set_error("fail to parse region '%s' with %s", names[c].c_str(), a->bampaths[f]); rc = RAER_ERR_IO; }
+                }
+            }
+            if (rc) break;
             raer_read_batch b;
             const uint32_t* d_sites = nullptr;
             int64_t bases = 0;
@@ -1043,10 +1069,14 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             out->n_aligned_bases += fb_bases;
             out->n_inflated_bytes = gin + fb_inflated;
             out->n_seeks = fb_seeks;
+            t0c = raer::now_seconds();
             raer_gi_destroy(gi);
+            t0c = raer::now_seconds() - t0c;
         }
         raer_ctx_set_reference(ctx, -1, nullptr, 0);
-        if (getenv("RAER_TIMING")) fprintf(stderr, "[raer_pileup] device ingest: %lld contig(s) fell back to the host stream\n", (long long)n_fallback);
+        if (getenv("RAER_TIMING"))
+            fprintf(stderr, "[raer_pileup] device ingest: %lld contig(s) fell back to the host stream; create %.3f s, destroy %.3f s\n",
+                    (long long)n_fallback, tm_gi_create, t0c);
     } else if (parallel) {
         struct Slot {
             raer::PackedBatch pb;
@@ -1290,8 +1320,11 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             memmove(out->counts + (size_t)f * out->nrows * 8, out->counts + (size_t)f * sink.cap * 8, (size_t)out->nrows * 32);
         }
     }
+    double tm_destroy = raer::now_seconds();
     raer_ctx_destroy(ctx);
+    tm_destroy = raer::now_seconds() - tm_destroy;
     out->t_total = raer::now_seconds() - t_start;
+    if (getenv("RAER_TIMING")) fprintf(stderr, "[raer_pileup] ctx destroy %.3f s\n", tm_destroy);
     if (getenv("RAER_TIMING"))
         fprintf(stderr, "[raer_pileup] total %.3f s: open %.3f ctx %.3f fasta+ref %.3f next_batch %.3f (decode %.3f pack %.3f) "
                         "gpu call %.3f (h2d %.3f kernel %.3f d2h %.3f) rows->columns %.3f\n",

@@ -305,16 +305,23 @@ def make_bulk_dataset(outdir: str, *, n_bams=2, n_contigs=2, contig_len=200_000,
     refs = make_reference(lens, seed)
     fa = os.path.join(outdir, "ref.fa")
     write_fasta(fa, names, refs)
-    bams, n_bases = [], 0
-    for b in range(n_bams):
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(b):  # the deflate loop of the writer runs outside the GIL: the BAMs are written side by side
         per = [gen_contig(refs[t], pairs_per_contig, seed + 1000 * (b + 1) + t, **gen_kw) for t in range(n_contigs)]
         p = os.path.join(outdir, f"s{b + 1}.bam")
         write_bam(p, names, lens, per, qname_prefix=f"b{b}_")
+        nb = 0
         for r in per:
             c = r.cigar
             op, ln = c & 0xF, c >> 4
-            n_bases += int((ln * (op == 0)).sum())
-        bams.append(p)
+            nb += int((ln * (op == 0)).sum())
+        return p, nb
+
+    with ThreadPoolExecutor(max_workers=max(1, min(n_bams, 4))) as ex:
+        done = list(ex.map(one, range(n_bams)))
+    bams = [p for p, _ in done]
+    n_bases = sum(nb for _, nb in done)
     return {"fasta": fa, "bams": bams, "names": names, "lens": lens, "aligned_bases": n_bases}
 
 

@@ -154,3 +154,17 @@ def test_linear_index_walk(ext, monkeypatch):
     dev, host = _both(pc, monkeypatch)
     assert dev["timing"]["n_device_contigs"] >= 1
     _columns_equal(dev, host)
+
+
+def test_whole_contig_region_uses_the_device_ingest(ext, monkeypatch):
+    """pileup_sites(chroms = ...) / BiocParallel over chromosomes call with region = a contig name (R/pileup.R:208-243)"""
+    pc = prepare_pileup_call([ext.bam1, ext.bam2], ext.fasta, region="SPCS3")
+    dev, host = _both(pc, monkeypatch)
+    assert dev["timing"]["n_device_contigs"] == 1 and dev["timing"]["n_host_contigs"] == 0
+    assert dev["nrows"] > 0 and set(dev["seqname"]) == {"SPCS3"}
+    _columns_equal(dev, host)
+    # a coordinate range stays with the host stream and the index
+    pc = prepare_pileup_call(ext.bam1, ext.fasta, region="SPCS3:100-300")
+    dev, host = _both(pc, monkeypatch)
+    assert dev["timing"]["n_device_contigs"] == 0
+    _columns_equal(dev, host)
