@@ -7,10 +7,14 @@
 //   k_sc_emit      one thread per read: binary-search the sorted site list for positions inside the
 //                  read's span, locate the query base through the CIGAR, apply the shared read/base
 //                  filters, and emit one tuple (site, cell barcode, UMI | class, base quality) per
-//                  matching payload. Runs twice: count, then write (exact allocation).
-//   k_rs_*         LSD radix sort of the 64-bit tuple keys (8-bit digits, stable block scatter).
+//                  matching payload. One pass: a warp reserves room for its tuples with one atomic; a
+//                  buffer that turns out too small re-runs the batch with the size the device counted.
+//   rs_sort        LSD radix sort of the 64-bit tuple keys over the used key bits (raer_radix.cuh:
+//                  8-bit digits, stable block scatter).
 //   k_sc_umi/cell  segmented reduce over the sorted tuples: (site, CB, UMI) quality sums -> consensus
-//                  vote (ties go to alt, src/sc-plp.c:338) -> (site, CB) nRef/nAlt + per-site totals.
+//                  vote (ties go to alt, src/sc-plp.c:338) -> (site, CB) nRef/nAlt + per-site totals;
+//                  k_cp_* compact the nonzero cells in order.
+// Batch layer (raer_sc_ctx, raer_sc_batch_device / _host): the C-ABI entry bench.py drives.
 // The host applies the min_counts / min_variant_reads site rule (src/sc-plp.c:586-596) and writes the
 // three text files the R side reads back.
 #define RAER_HELPERS_ONLY
