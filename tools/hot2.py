@@ -2,7 +2,8 @@
 import re,csv,collections,sys,os
 rep=sys.argv[1]; kern=sys.argv[2] if len(sys.argv)>2 else '_Z13k_pileup_fast9PlpParams'
 ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.system("cd /tmp && rm -rf cub && mkdir cub && cd cub && cuobjdump -xelf all "+ROOT+"/raer_b200/libraer_b200.so >/dev/null 2>&1 && nvdisasm -g raer_kernels.sm_100a.cubin > /tmp/all.sass 2>/dev/null")
+os.system("cd /tmp && rm -rf cub && mkdir cub && cd cub && cuobjdump -xelf all "+ROOT+"/raer_b200/libraer_b200.so >/dev/null 2>&1 && "
+          "for c in *.cubin; do nvdisasm -g $c > $c.sass 2>/dev/null; done; for c in *.sass; do if grep -q '^.text."+kern+":' $c; then cp $c /tmp/all.sass; fi; done")
 os.system(f"ncu -i {rep} --page source --csv 2>/dev/null > /tmp/sass_m.csv")
 lines=open('/tmp/all.sass').read().split('\n')
 start=[i for i,l in enumerate(lines) if l.startswith('.text.'+kern+':')][0]
@@ -20,7 +21,7 @@ def ranges(path):
         m=re.match(r'^(?:template.*\n)?(?:static )?(?:__device__|__global__|extern "C").*?(\w+)\(',l)
         if m and not l.startswith(' '): out.append((i+1,m.group(1)))
     return out
-R={f:ranges(ROOT+'/raer_b200/csrc/'+f) for f in ('raer_fast.cuh','raer_kernels.cu','raer_walk.cuh','raer_lane.cuh')}
+R={f:ranges(ROOT+'/raer_b200/csrc/'+f) for f in ('raer_fast.cuh','raer_kernels.cu','raer_walk.cuh','raer_lane.cuh','raer_ginflate.cuh','raer_gingest.cu','raer_sc.cu','raer_radix.cuh')}
 def fn(ln):
     if not ln: return '?'
     f,n=ln
