@@ -950,10 +950,7 @@ def run_ours_sc(args):
                 L.raer_sc_cells_free(C.byref(cells))
             d2h[0] = nb
 
-        want_digests[0] = partitioned and n_host == len(batches)
-        step_host()
-        unit_digests = list(digests)
-        want_digests[0] = False
+        step_host()  # warm-up
         barrier()
         n_e2e = max(1, min(args.steps, 2))
         t0 = time.perf_counter()
@@ -964,44 +961,6 @@ def run_ours_sc(args):
         t_dt = torch.tensor([dt], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t_dt, op=dist.ReduceOp.MAX)
-        # ---- partition check: the rows of the tiles, gathered on rank 0 in (contig, tile) order, against the rows of the
-        # same contigs computed whole (what one GPU computes), for every contig rank 0 holds a tile of
-        if partitioned:
-            mine = {(t, ub, ue): d for (t, ub, ue), d in zip(units, unit_digests)} if unit_digests else {}
-            gathered = [None] * world if rank == 0 else None
-            dist.gather_object(mine, gathered, dst=0)
-            if rank == 0:
-                allu = {}
-                for g in gathered:
-                    allu.update(g or {})
-                checked = bad = 0
-                for t, (Tf, rbf) in keep_full.items():
-                    Hf = {k: torch.empty(Tf[k].shape, dtype=Tf[k].dtype, pin_memory=True) for k in keys}
-                    for k in Hf:
-                        Hf[k].copy_(Tf[k])
-                    hb = _cabi.ReadBatch()
-                    C.memmove(C.byref(hb), C.byref(rbf), C.sizeof(hb))
-                    hb.hdr, hb.maxend, hb.cigar = Hf["hdr"].data_ptr(), Hf["maxend"].data_ptr(), Hf["cigar"].data_ptr()
-                    hb.seq, hb.qual, hb.pair_b = Hf["seq"].data_ptr(), Hf["qual0"].data_ptr(), Hf["pair_b"].data_ptr()
-                    hb.file_off = Tf["file_off"].ctypes.data
-                    conf = make_conf(Hf["mask"].data_ptr() if "mask" in Hf else None)
-                    rc = L.raer_pipe_submit(pipe, C.byref(conf), C.byref(hb), hb.tid, Hf["ref"].data_ptr(), Hf["ref"].numel())
-                    if rc != 0:
-                        raise SystemExit(f"raer_pipe_submit failed ({rc}): {_cabi.last_error()}")
-                    rows = _cabi.Rows()
-                    if L.raer_pipe_collect(pipe, C.byref(rows)) != 0:
-                        raise SystemExit(_cabi.last_error())
-                    for (ut, ub, ue), d in sorted(allu.items(), key=lambda kv: (kv[0][0], kv[0][1] or 0)):
-                        if ut != t or ub is None:
-                            continue
-                        checked += 1
-                        bad += rows_digest(rows, ub, ue) != tuple(d)
-                    L.raer_rows_free(C.byref(rows))
-                    del Hf
-                partition_check = {"tiles_checked": checked, "tiles_total": sum(len(p) for p in plan),
-                                   "identical_to_single_gpu_rows": bool(checked > 0 and bad == 0) if checked else None,
-                                   "how": "sha1 over pos/meta/stats/counts/altcode of every tile's rows vs the same positions of "
-                                          "the contig run as one batch, for the contigs rank 0 holds a tile of"}
         e2e = {"value": float(bases_all.item()) / float(t_dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": float(t_dt.item()) * 1e3, "steps": n_e2e,
                "distinct_host_batches": n_host, "batches_per_step": len(batches), "cpus_bound_to_gpu_node": numa,

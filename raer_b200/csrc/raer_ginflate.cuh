@@ -22,7 +22,8 @@
 #define GI_D_SIZE ((1 << GI_D_BITS) + 512)
 #define GI_TOK 64                               // tokens per batch
 #define GI_CTRL 4                               // control words lane 0 hands to the warp
-#define GI_WARP_WORDS (GI_LL_SIZE + GI_D_SIZE + GI_TOK + GI_TOK + 4 + GI_CTRL)  // shared-memory words per warp
+#define GI_DSCR 80                              // scratch of the distance-table build (256 prefix bytes + 30 codes)
+#define GI_WARP_WORDS (GI_LL_SIZE + GI_D_SIZE + GI_TOK + GI_TOK + 4 + GI_CTRL + GI_DSCR)  // shared-memory words per warp
 #define GI_WARPS 24                             // warps (= blocks in flight) per CTA, one CTA per SM
 
 // table entry: bits 0-4 code length to consume (sub-table entries: length beyond the primary bits),
@@ -37,75 +38,101 @@ __constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49
 __constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-// Canonical Huffman decode table, built by one thread. what: 0 literal/length alphabet, 1 distance alphabet,
-// 2 code-length alphabet. Returns the number of table entries used, or -1 for an over-subscribed / unusable code or
-// a table that does not fit `cap`.
+// Canonical Huffman decode table, built by the whole warp (every lane calls). what: 0 literal/length alphabet, 1 distance
+// alphabet, 2 code-length alphabet. lens / sub_bits / codes live in shared memory. Lane 0 does what is serial by nature
+// (code counts, first codes, the code of every symbol: a few instructions per symbol); clearing the table, laying out the
+// second-level tables and replicating the entries -- nine tenths of a one-thread build -- are spread over the lanes.
+// Returns the number of table entries used, or -1 for an over-subscribed / unusable code or a table that does not fit `cap`.
 __device__ int gi_build_table(const uint8_t* lens, int n, int tbits, uint32_t* tab, int cap, int what, uint8_t* sub_bits,
-                              uint16_t* codes) {
-    int count[16];
-    for (int i = 0; i < 16; ++i) count[i] = 0;
-    for (int i = 0; i < n; ++i) ++count[lens[i]];
-    count[0] = 0;
-    int left = 1, used_syms = 0;
-    for (int l = 1; l <= 15; ++l) {
-        left = (left << 1) - count[l];
-        if (left < 0) return -1;
-        used_syms += count[l];
-    }
+                              uint16_t* codes, int lane) {
     const int primary = 1 << tbits;
-    for (int i = 0; i < primary; ++i) tab[i] = gi_mk(1, GK_BAD, 0, 0);
-    if (used_syms == 0) return primary;
-    // incomplete codes are legal only with a single code (RFC 1951 / zlib accept one distance code of one bit)
-    if (left > 0 && !(used_syms == 1)) return -1;
-    uint32_t next_code[16];
-    uint32_t code = 0;
-    for (int l = 1; l <= 15; ++l) { code = (code + count[l - 1]) << 1; next_code[l] = code; }
-    for (int i = 0; i < primary; ++i) sub_bits[i] = 0;
-    for (int s = 0; s < n; ++s) {
-        const int l = lens[s];
-        if (!l) continue;
-        const uint32_t r = __brev(next_code[l]++) >> (32 - l);
-        codes[s] = (uint16_t)r;
-        if (l > tbits) {
-            const uint32_t p = r & (primary - 1);
-            if (l - tbits > sub_bits[p]) sub_bits[p] = (uint8_t)(l - tbits);
+    for (int i = lane; i < primary; i += 32) tab[i] = gi_mk(1, GK_BAD, 0, 0);
+    for (int i = lane; i < primary / 4; i += 32) reinterpret_cast<uint32_t*>(sub_bits)[i] = 0u;
+    __syncwarp();
+    int rc = 0;  // lane 0: -1 refused, 1 no symbol at all, 0 go on
+    if (lane == 0) {
+        int count[16];
+        for (int i = 0; i < 16; ++i) count[i] = 0;
+        for (int i = 0; i < n; ++i) ++count[lens[i]];
+        count[0] = 0;
+        int left = 1, used_syms = 0;
+        for (int l = 1; l <= 15; ++l) {
+            left = (left << 1) - count[l];
+            if (left < 0) rc = -1;
+            used_syms += count[l];
+        }
+        if (rc == 0 && used_syms == 0) rc = 1;
+        // incomplete codes are legal only with a single code (RFC 1951 / zlib accept one distance code of one bit)
+        if (rc == 0 && left > 0 && used_syms != 1) rc = -1;
+        if (rc == 0) {
+            uint32_t next_code[16];
+            uint32_t code = 0;
+            for (int l = 1; l <= 15; ++l) { code = (code + count[l - 1]) << 1; next_code[l] = code; }
+            for (int sy = 0; sy < n; ++sy) {
+                const int l = lens[sy];
+                if (!l) continue;
+                const uint32_t r = __brev(next_code[l]++) >> (32 - l);
+                codes[sy] = (uint16_t)r;
+                if (l > tbits) {
+                    const uint32_t p = r & (primary - 1);
+                    if (l - tbits > sub_bits[p]) sub_bits[p] = (uint8_t)(l - tbits);
+                }
+            }
         }
     }
-    int used = primary;
-    for (int p = 0; p < primary; ++p)
+    rc = __shfl_sync(0xffffffffu, rc, 0);
+    if (rc < 0) return -1;
+    if (rc == 1) return primary;
+    __syncwarp();
+    // second-level tables: lane q lays out the prefixes q * chunk .. in order behind the primary table
+    const int chunk = primary / 32;
+    int mine = 0;
+    for (int p = lane * chunk; p < (lane + 1) * chunk; ++p)
+        if (sub_bits[p]) mine += 1 << sub_bits[p];
+    int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const int used = primary + __shfl_sync(0xffffffffu, inc, 31);
+    if (used > cap) return -1;
+    int base = primary + inc - mine;
+    for (int p = lane * chunk; p < (lane + 1) * chunk; ++p)
         if (sub_bits[p]) {
             const int sz = 1 << sub_bits[p];
-            if (used + sz > cap) return -1;
-            tab[p] = gi_mk(tbits, GK_SUB, sub_bits[p], used);
-            for (int i = 0; i < sz; ++i) tab[used + i] = gi_mk(1, GK_BAD, 0, 0);
-            used += sz;
+            tab[p] = gi_mk(tbits, GK_SUB, sub_bits[p], base);
+            for (int i = 0; i < sz; ++i) tab[base + i] = gi_mk(1, GK_BAD, 0, 0);
+            base += sz;
         }
-    for (int s = 0; s < n; ++s) {
-        const int l = lens[s];
+    __syncwarp();
+    for (int sy = lane; sy < n; sy += 32) {
+        const int l = lens[sy];
         if (!l) continue;
         uint32_t e;
         if (what == 0) {
-            if (s < 256) e = gi_mk(0, GK_LIT, 0, s);
-            else if (s == 256) e = gi_mk(0, GK_EOB, 0, 0);
-            else if (s <= 285) e = gi_mk(0, GK_LEN, c_len_extra[s - 257], c_len_base[s - 257]);
+            if (sy < 256) e = gi_mk(0, GK_LIT, 0, sy);
+            else if (sy == 256) e = gi_mk(0, GK_EOB, 0, 0);
+            else if (sy <= 285) e = gi_mk(0, GK_LEN, c_len_extra[sy - 257], c_len_base[sy - 257]);
             else e = gi_mk(0, GK_BAD, 0, 0);
         } else if (what == 1) {
-            e = s < 30 ? gi_mk(0, GK_LEN, c_dist_extra[s], c_dist_base[s]) : gi_mk(0, GK_BAD, 0, 0);
+            e = sy < 30 ? gi_mk(0, GK_LEN, c_dist_extra[sy], c_dist_base[sy]) : gi_mk(0, GK_BAD, 0, 0);
         } else {
-            e = gi_mk(0, GK_LIT, 0, s);
+            e = gi_mk(0, GK_LIT, 0, sy);
         }
-        const uint32_t r = codes[s];
+        const uint32_t r = codes[sy];
         if (l <= tbits) {
             e |= (uint32_t)l;
             for (uint32_t i = r; i < (uint32_t)primary; i += 1u << l) tab[i] = e;
         } else {
             const uint32_t p = r & (primary - 1);
             const int sb = sub_bits[p];
-            const int base = (int)(tab[p] >> 16);
+            const int tb = (int)(tab[p] >> 16);
             e |= (uint32_t)(l - tbits);
-            for (uint32_t i = r >> tbits; i < (1u << sb); i += 1u << (l - tbits)) tab[base + i] = e;
+            for (uint32_t i = r >> tbits; i < (1u << sb); i += 1u << (l - tbits)) tab[tb + i] = e;
         }
     }
+    __syncwarp();
     return used;
 }
 
@@ -157,93 +184,93 @@ struct GiState {
 __device__ __forceinline__ uint32_t gi_tok_lit(uint32_t v) { return 1u | (v << 9); }
 __device__ __forceinline__ uint32_t gi_tok_match(uint32_t len, uint32_t dist) { return len | ((dist - 1u) << 17); }
 
-// Lane 0: decodes until GI_TOK tokens are waiting, a deflate block ends or something is wrong. Stored blocks are copied
-// right here (nothing is pending when one starts). Returns 0 = more to come, 1 = stream finished, negative = refused.
-__device__ int gi_decode_batch(GiState& S, uint8_t* out, uint32_t* tab, uint32_t* tok, int* n_tok) {
+// Lane 0, at the start of a deflate block: reads the block header. Returns a negative code, or
+//   0  stored block: copied right here (nothing is pending when one starts), S.op moved on
+//   1  fixed codes: code lengths written to `lens` (288 literal/length, then 32 distance)
+//   2  dynamic codes: *hlit / *hdist set, the 19 code-length code lengths written to `cl`
+__device__ int gi_block_header(GiState& S, uint8_t* out, uint8_t* lens, uint8_t* cl, int* hlit, int* hdist) {
+    GiBits& B = S.B;
+    B.need(3);
+    S.last = (int)B.peek(1);
+    const int type = (int)(B.peek(3) >> 1);
+    B.drop(3);
+    if (type == 0) {
+        B.drop(B.bc & 7);
+        const uint8_t* ip = B.byte_pos();
+        if (ip + 4 > S.in + S.in_len) return -2;
+        const unsigned len = ip[0] | (ip[1] << 8), nlen = ip[2] | (ip[3] << 8);
+        ip += 4;
+        if ((len ^ 0xffffu) != nlen) return -3;
+        if (ip + len > S.in + S.in_len || S.op + len > S.out_len) return -4;
+        for (unsigned i = 0; i < len; ++i) out[S.op + i] = ip[i];
+        S.op += len;
+        B.init(ip + len, (size_t)((S.in + S.in_len) - (ip + len)));
+        return 0;
+    }
+    if (type == 3) return -5;
+    if (type == 1) {
+        int i = 0;
+        for (; i < 144; ++i) lens[i] = 8;
+        for (; i < 256; ++i) lens[i] = 9;
+        for (; i < 280; ++i) lens[i] = 7;
+        for (; i < 288; ++i) lens[i] = 8;
+        for (i = 0; i < 32; ++i) lens[288 + i] = 5;
+        *hlit = 288;
+        *hdist = 32;
+        return 1;
+    }
+    B.need(14);
+    *hlit = (int)B.peek(5) + 257;
+    B.drop(5);
+    *hdist = (int)B.peek(5) + 1;
+    B.drop(5);
+    const int hclen = (int)B.peek(4) + 4;
+    B.drop(4);
+    if (*hlit > 286 || *hdist > 30) return -7;
+    for (int i = 0; i < 19; ++i) cl[i] = 0;
+    for (int i = 0; i < hclen; ++i) {
+        B.need(3);
+        cl[c_cl_order[i]] = (uint8_t)B.peek(3);
+        B.drop(3);
+    }
+    return 2;
+}
+
+// Lane 0: the code lengths of a dynamic block, through the code-length table
+__device__ int gi_code_lengths(GiState& S, const uint32_t* cltab, uint8_t* lens, int total) {
+    GiBits& B = S.B;
+    int k = 0;
+    while (k < total) {
+        B.need(14);
+        const uint32_t e = cltab[B.peek(7)];
+        if (((e >> 5) & 7) != GK_LIT) return -9;
+        B.drop((int)(e & 31));
+        const int sym = (int)(e >> 16);
+        if (sym < 16) { lens[k++] = (uint8_t)sym; continue; }
+        int rep, val = 0;
+        if (sym == 16) {
+            if (k == 0) return -10;
+            val = lens[k - 1];
+            rep = 3 + (int)B.peek(2); B.drop(2);
+        } else if (sym == 17) {
+            rep = 3 + (int)B.peek(3); B.drop(3);
+        } else {
+            rep = 11 + (int)B.peek(7); B.drop(7);
+        }
+        if (k + rep > total) return -11;
+        for (int i = 0; i < rep; ++i) lens[k + i] = (uint8_t)val;
+        k += rep;
+    }
+    return 0;
+}
+
+// Lane 0: decodes symbols until GI_TOK tokens are waiting, the deflate block ends or something is wrong.
+// Returns 0 = more to come, 1 = stream finished, negative = refused.
+__device__ int gi_decode_batch(GiState& S, uint32_t* tab, uint32_t* tok, int* n_tok) {
     uint32_t* const LL = tab;
     uint32_t* const DD = tab + GI_LL_SIZE;
     GiBits& B = S.B;
     int n = 0;
-    *n_tok = 0;
-    if (!S.in_symbols) {
-        uint8_t lens[286 + 30 + 140];
-        uint8_t sub_bits[1 << GI_LL_BITS];
-        uint16_t codes[320];
-        B.need(3);
-        S.last = (int)B.peek(1);
-        const int type = (int)(B.peek(3) >> 1);
-        B.drop(3);
-        if (type == 0) {  // stored
-            B.drop(B.bc & 7);
-            const uint8_t* ip = B.byte_pos();
-            if (ip + 4 > S.in + S.in_len) return -2;
-            const unsigned len = ip[0] | (ip[1] << 8), nlen = ip[2] | (ip[3] << 8);
-            ip += 4;
-            if ((len ^ 0xffffu) != nlen) return -3;
-            if (ip + len > S.in + S.in_len || S.op + len > S.out_len) return -4;
-            for (unsigned i = 0; i < len; ++i) out[S.op + i] = ip[i];
-            S.op += len;
-            B.init(ip + len, (size_t)((S.in + S.in_len) - (ip + len)));
-            return S.last ? 1 : 0;
-        }
-        if (type == 3) return -5;
-        if (type == 1) {  // fixed codes
-            int i = 0;
-            for (; i < 144; ++i) lens[i] = 8;
-            for (; i < 256; ++i) lens[i] = 9;
-            for (; i < 280; ++i) lens[i] = 7;
-            for (; i < 288; ++i) lens[i] = 8;
-            if (gi_build_table(lens, 288, GI_LL_BITS, LL, GI_LL_SIZE, 0, sub_bits, codes) < 0) return -6;
-            for (i = 0; i < 32; ++i) lens[i] = 5;
-            if (gi_build_table(lens, 32, GI_D_BITS, DD, GI_D_SIZE, 1, sub_bits, codes) < 0) return -6;
-        } else {  // dynamic codes
-            B.need(14);
-            const int hlit = (int)B.peek(5) + 257;
-            B.drop(5);
-            const int hdist = (int)B.peek(5) + 1;
-            B.drop(5);
-            const int hclen = (int)B.peek(4) + 4;
-            B.drop(4);
-            if (hlit > 286 || hdist > 30) return -7;
-            uint8_t cl[19];
-            for (int i = 0; i < 19; ++i) cl[i] = 0;
-            for (int i = 0; i < hclen; ++i) {
-                B.need(3);
-                cl[c_cl_order[i]] = (uint8_t)B.peek(3);
-                B.drop(3);
-            }
-            uint32_t* cltab = DD;  // 128 entries, free until the distance table is built
-            if (gi_build_table(cl, 19, 7, cltab, 1 << 7, 2, sub_bits, codes) < 0) return -8;
-            int k = 0;
-            const int total = hlit + hdist;
-            while (k < total) {
-                B.need(14);
-                const uint32_t e = cltab[B.peek(7)];
-                if (((e >> 5) & 7) != GK_LIT) return -9;
-                B.drop((int)(e & 31));
-                const int sym = (int)(e >> 16);
-                if (sym < 16) { lens[k++] = (uint8_t)sym; continue; }
-                int rep, val = 0;
-                if (sym == 16) {
-                    if (k == 0) return -10;
-                    val = lens[k - 1];
-                    rep = 3 + (int)B.peek(2); B.drop(2);
-                } else if (sym == 17) {
-                    rep = 3 + (int)B.peek(3); B.drop(3);
-                } else {
-                    rep = 11 + (int)B.peek(7); B.drop(7);
-                }
-                if (k + rep > total) return -11;
-                for (int i = 0; i < rep; ++i) lens[k + i] = (uint8_t)val;
-                k += rep;
-            }
-            if (lens[256] == 0) return -12;
-            if (gi_build_table(lens, hlit, GI_LL_BITS, LL, GI_LL_SIZE, 0, sub_bits, codes) < 0) return -13;
-            if (gi_build_table(lens + hlit, hdist, GI_D_BITS, DD, GI_D_SIZE, 1, sub_bits, codes) < 0) return -14;
-        }
-        S.in_symbols = 1;
-    }
-    // ---- symbols of the deflate block
     uint32_t op = S.op;
     int rc = 0;
     while (n < GI_TOK) {
@@ -327,19 +354,68 @@ __global__ void __launch_bounds__(GI_WARPS * 32, 1) k_gi_inflate(const uint8_t* 
         int verdict = 0;
         uint32_t base = 0;  // output offset of the batch
         if (k.u_len == 0) verdict = 1;
+        // scratch of the table builds: code lengths (and the 19 code-length code lengths behind them) in the token area,
+        // which is idle while a block header is read; prefix bits / codes of the literal table in the distance table's
+        // space (built afterwards), those of the distance table in a scratch of their own
+        uint8_t* const lens = reinterpret_cast<uint8_t*>(tok);
+        uint8_t* const cl = lens + 460;
+        uint32_t* const DD = tab + GI_LL_SIZE;
+        uint32_t* const dscr = const_cast<uint32_t*>(ctrl) + GI_CTRL;
+        int in_symbols = 0;  // warp-uniform copy of lane 0's S.in_symbols
         while (verdict == 0) {
+            if (!in_symbols) {
+                if (lane == 0) {
+                    int hlit = 0, hdist = 0;
+                    const int rc = gi_block_header(S, dst, lens, cl, &hlit, &hdist);
+                    ctrl[0] = (uint32_t)rc;
+                    ctrl[1] = (uint32_t)hlit;
+                    ctrl[2] = (uint32_t)hdist;
+                    ctrl[3] = (uint32_t)S.last;
+                }
+                __syncwarp();
+                int hrc = (int)ctrl[0];
+                const int hlit = (int)ctrl[1], hdist = (int)ctrl[2];
+                const int last = (int)ctrl[3];
+                __syncwarp();
+                if (hrc < 0) { verdict = hrc; break; }
+                if (hrc == 0) {  // stored block, already copied
+                    if (last) verdict = 1;
+                    continue;
+                }
+                if (hrc == 2) {
+                    if (gi_build_table(cl, 19, 7, DD, 1 << 7, 2, reinterpret_cast<uint8_t*>(DD + 128),
+                                       reinterpret_cast<uint16_t*>(DD + 128 + 32), lane) < 0) { verdict = -8; break; }
+                    if (lane == 0) {
+                        int rc = gi_code_lengths(S, DD, lens, hlit + hdist);
+                        if (rc == 0 && lens[256] == 0) rc = -12;
+                        ctrl[0] = (uint32_t)rc;
+                    }
+                    __syncwarp();
+                    hrc = (int)ctrl[0];
+                    __syncwarp();
+                    if (hrc < 0) { verdict = hrc; break; }
+                }
+                if (gi_build_table(lens, hlit, GI_LL_BITS, tab, GI_LL_SIZE, 0, reinterpret_cast<uint8_t*>(DD),
+                                   reinterpret_cast<uint16_t*>(DD + 256), lane) < 0) { verdict = -13; break; }
+                if (gi_build_table(lens + hlit, hdist, GI_D_BITS, DD, GI_D_SIZE, 1, reinterpret_cast<uint8_t*>(dscr),
+                                   reinterpret_cast<uint16_t*>(dscr + 64), lane) < 0) { verdict = -14; break; }
+                in_symbols = 1;
+                if (lane == 0) S.in_symbols = 1;
+            }
             if (lane == 0) {
                 int n = 0;
                 const uint32_t before = S.op;
-                const int rc = gi_decode_batch(S, dst, tab, tok, &n);
+                const int rc = gi_decode_batch(S, tab, tok, &n);
                 ctrl[0] = (uint32_t)n;
                 ctrl[1] = (uint32_t)rc;
-                ctrl[2] = n ? before : S.op;  // where the batch starts (a stored block has moved op on its own)
+                ctrl[2] = before;
+                ctrl[3] = (uint32_t)S.in_symbols;
             }
             __syncwarp();
             const int n = (int)ctrl[0];
             verdict = (int)ctrl[1];
             base = ctrl[2];
+            in_symbols = (int)ctrl[3];
             if (n > 0) {
                 // place of every token: lane handles tokens 2 * lane and 2 * lane + 1
                 const uint32_t l0 = 2 * lane < n ? (tok[2 * lane] & 511u) : 0u;
