@@ -502,16 +502,12 @@ def run_ours(args):
             """(number of rows, sha1 over every row field) of the rows with lo <= pos < hi"""
             n = rows.n_rows
             if n == 0:
-                return (0, hashlib.sha1(b"").hexdigest())
+                return (0,) + (hashlib.sha1(b"").hexdigest(),) * 5
             pos = np.ctypeslib.as_array(rows.pos, (n,))
             a, b = (0, n) if lo is None else (int(np.searchsorted(pos, lo, "left")), int(np.searchsorted(pos, hi, "left")))
-            h = hashlib.sha1()
-            h.update(pos[a:b].tobytes())
-            h.update(np.ctypeslib.as_array(rows.meta, (n,))[a:b].tobytes())
-            h.update(np.ctypeslib.as_array(rows.stats, (n, 3))[a:b].tobytes())
-            h.update(np.ctypeslib.as_array(rows.counts, (n, n_bams, 8))[a:b].tobytes())
-            h.update(np.ctypeslib.as_array(rows.altcode, (n, n_bams))[a:b].tobytes())
-            return (b - a, h.hexdigest())
+            parts = (pos[a:b], np.ctypeslib.as_array(rows.meta, (n,))[a:b], np.ctypeslib.as_array(rows.stats, (n, 3))[a:b],
+                     np.ctypeslib.as_array(rows.counts, (n, n_bams, 8))[a:b], np.ctypeslib.as_array(rows.altcode, (n, n_bams))[a:b])
+            return (b - a,) + tuple(hashlib.sha1(x.tobytes()).hexdigest() for x in parts)
 
         digests = []  # per batch of the last host step, in submission order
 
@@ -571,6 +567,7 @@ def run_ours(args):
                 for g in gathered:
                     allu.update(g or {})
                 checked = bad = 0
+                bad_fields = set()
                 for t, (Tf, rbf) in keep_full.items():
                     Hf = {k: torch.empty(Tf[k].shape, dtype=Tf[k].dtype, pin_memory=True) for k in keys}
                     for k in Hf:
@@ -591,11 +588,17 @@ def run_ours(args):
                         if ut != t or ub is None:
                             continue
                         checked += 1
-                        bad += rows_digest(rows, ub, ue) != tuple(d)
+                        whole = rows_digest(rows, ub, ue)
+                        if whole != tuple(d):
+                            bad += 1
+                            for nm, x, y in zip(("n_rows", "pos", "meta", "stats", "counts", "altcode"), whole, tuple(d)):
+                                if x != y:
+                                    bad_fields.add(nm)
                     L.raer_rows_free(C.byref(rows))
                     del Hf
                 partition_check = {"tiles_checked": checked, "tiles_total": sum(len(p) for p in plan),
                                    "identical_to_single_gpu_rows": bool(checked > 0 and bad == 0) if checked else None,
+                                   "tiles_differing": bad, "fields_differing": sorted(bad_fields),
                                    "how": "sha1 over pos/meta/stats/counts/altcode of every tile's rows vs the same positions of "
                                           "the contig run as one batch, for the contigs rank 0 holds a tile of"}
         e2e = {"value": float(bases_all.item()) / float(t_dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),

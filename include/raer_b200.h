@@ -358,11 +358,13 @@ void raer_ctx_last_timing(raer_ctx* ctx, double* h2d_s, double* kernel_s, double
 
 /* Device DEFLATE decoder used by the device ingest (one warp per BGZF block), exposed for tests and measurements:
  * n_blocks raw DEFLATE payloads at comp + c_off[i] (c_len[i] bytes, host memory) are inflated to out + u_off[i]
- * (u_len[i] bytes expected, host memory). status[i] = 0 or a negative decoder code (bad block type, bad code lengths,
- * distance too far, output length mismatch ...). Replaces what htslib's bgzf_read_block / zlib inflate do per block under
+ * (u_len[i] bytes expected, host memory); crc[i] (NULL: not checked) is the CRC-32 the inflated bytes must have.
+ * status[i] = 0 or a negative decoder code (bad block type, bad code lengths, distance too far, output length
+ * mismatch, -21 CRC mismatch ...). Replaces what htslib's bgzf_read_block / zlib inflate do per block under
  * sam_itr_next (reference: src/plp.c:32-78 readaln -> sam_itr_next / sam_read1). */
 int raer_gpu_inflate(const uint8_t* comp, int64_t comp_len, const int64_t* c_off, const int32_t* c_len, const int64_t* u_off,
-                     const int32_t* u_len, int32_t n_blocks, uint8_t* out, int64_t out_len, int32_t* status, double* kernel_ms);
+                     const int32_t* u_len, const uint32_t* crc, int32_t n_blocks, uint8_t* out, int64_t out_len, int32_t* status,
+                     double* kernel_ms);
 /* The device ingest allocates from the device's stream-ordered memory pool and keeps up to 8 GB of it, and a few
  * page-locked staging buffers, for the next call of the process. This hands both back to the driver (e.g. from the
  * unload hook of a binding). */

@@ -451,7 +451,7 @@ def fisher_exact(mat: np.ndarray) -> np.ndarray:
     return out
 
 
-def gpu_inflate(payloads, sizes):
+def gpu_inflate(payloads, sizes, crcs=None):
     """Test / bench entry of the device DEFLATE decoder (raer_ginflate.cuh): raw DEFLATE `payloads` (bytes objects) of
     known inflated `sizes` -> (list of inflated bytes, status array, kernel milliseconds)."""
     L = lib()
@@ -468,10 +468,12 @@ def gpu_inflate(payloads, sizes):
     status = np.zeros(n, dtype=np.int32)
     ms = C.c_double(0)
     L.raer_gpu_inflate.restype = C.c_int
-    L.raer_gpu_inflate.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
-                                   C.c_int64, C.c_void_p, C.POINTER(C.c_double)]
+    L.raer_gpu_inflate.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                   C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_double)]
+    crc = None if crcs is None else np.asarray(crcs, dtype=np.uint32)
     rc = L.raer_gpu_inflate(comp.ctypes.data, len(comp) - 8, c_off.ctypes.data, c_len.ctypes.data, u_off.ctypes.data,
-                            u_len.ctypes.data, n, out.ctypes.data, out_len, status.ctypes.data, C.byref(ms))
+                            u_len.ctypes.data, None if crc is None else crc.ctypes.data, n, out.ctypes.data, out_len,
+                            status.ctypes.data, C.byref(ms))
     if rc != 0:
         raise RaerError(last_error())
     res = [out[int(u_off[i]):int(u_off[i]) + int(u_len[i])].tobytes() for i in range(n)]

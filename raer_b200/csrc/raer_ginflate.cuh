@@ -322,14 +322,93 @@ struct GiBlock {
     unsigned long long c_off;  // payload offset in the compressed buffer
     unsigned long long u_off;  // destination offset in the inflated buffer
     uint32_t c_len, u_len;
+    uint32_t crc;              // CRC-32 of the inflated bytes (BGZF footer)
+    uint32_t check_crc;        // 0: do not verify
 };
 
+// ---- CRC-32 (the gzip polynomial, reflected 0xEDB88320) of a block's output by the whole warp. The block is cut into
+// chunks of 4 KB, a lane takes 128 consecutive bytes of every chunk (one cache line) and runs the byte-wise table method
+// on them; pieces are joined with the shift operator of the CRC (multiplication by x^(8n) modulo the polynomial, the
+// algorithm behind zlib's crc32_combine): crc(A || B) = shift(crc(A), |B|) ^ crc(B), linear over XOR, so a lane
+// accumulates its own pieces Horner-style across chunks and the 32 lanes are joined once per block.
+#define GI_CRC_POLY 0xedb88320u
+#define GI_CRC_CHUNK 4096u
+#define GI_CRC_WORDS (256 + 32)  // shared per CTA: byte table, x^(2^k) table
+__device__ __forceinline__ uint32_t gi_multmodp(uint32_t a, uint32_t b) {  // a(x) * b(x) mod p(x), reflected bit order
+    uint32_t m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) {
+            p ^= b;
+            if ((a & (m - 1)) == 0) break;
+        }
+        m >>= 1;
+        b = (b & 1u) ? (b >> 1) ^ GI_CRC_POLY : b >> 1;
+    }
+    return p;
+}
+// x^(8 n) mod p: x2n[k] = x^(2^k) mod p
+__device__ __forceinline__ uint32_t gi_xpow8(uint32_t n_bytes, const uint32_t* x2n) {
+    uint32_t p = 1u << 31;  // x^0
+    int k = 3;
+    while (n_bytes) {
+        if (n_bytes & 1u) p = gi_multmodp(x2n[k & 31], p);
+        n_bytes >>= 1;
+        ++k;
+    }
+    return p;
+}
+__device__ void gi_crc_tables(uint32_t* crc_smem) {  // whole CTA; the caller synchronises afterwards
+    if (threadIdx.x < 256) {
+        uint32_t c = threadIdx.x;
+        for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ GI_CRC_POLY : c >> 1;
+        crc_smem[threadIdx.x] = c;
+    }
+    if (threadIdx.x == 256) {
+        uint32_t p = 1u << 30;  // x^1
+        crc_smem[256] = p;
+        for (int k = 1; k < 32; ++k) { p = gi_multmodp(p, p); crc_smem[256 + k] = p; }
+    }
+}
+__device__ uint32_t gi_crc32_warp(const uint8_t* p, uint32_t len, const uint32_t* crc_smem, int lane) {
+    const uint32_t* T0 = crc_smem;
+    const uint32_t* x2n = crc_smem + 256;
+    const uint32_t per = GI_CRC_CHUNK / 32;
+    const uint32_t n_full = len / GI_CRC_CHUNK, rem = len - n_full * GI_CRC_CHUNK;
+    const uint32_t x_chunk = gi_xpow8(GI_CRC_CHUNK, x2n);
+    uint32_t acc = 0;  // finalised CRC of this lane's pieces so far, as if they were contiguous in chunk steps
+    for (uint32_t c = 0; c < n_full; ++c) {
+        const uint8_t* q = p + (size_t)c * GI_CRC_CHUNK + lane * per;
+        uint32_t r = 0xffffffffu;
+        for (uint32_t i = 0; i < per; ++i) r = T0[(r ^ q[i]) & 0xffu] ^ (r >> 8);
+        acc = gi_multmodp(x_chunk, acc) ^ (r ^ 0xffffffffu);
+    }
+    uint32_t total = 0;
+    if (n_full) {  // bytes behind this lane's last full-chunk piece: the rest of that chunk and the partial chunk
+        const uint32_t after = rem + GI_CRC_CHUNK - per * (lane + 1);
+        total = gi_multmodp(gi_xpow8(after, x2n), acc);
+    }
+    if (rem) {
+        const uint32_t beg = min(lane * per, rem), end = min(lane * per + per, rem);
+        if (end > beg) {
+            const uint8_t* q = p + (size_t)n_full * GI_CRC_CHUNK;
+            uint32_t r = 0xffffffffu;
+            for (uint32_t i = beg; i < end; ++i) r = T0[(r ^ q[i]) & 0xffu] ^ (r >> 8);
+            total ^= gi_multmodp(gi_xpow8(rem - end, x2n), r ^ 0xffffffffu);
+        }
+    }
+    return __reduce_xor_sync(0xffffffffu, total);
+}
+
+#define GI_SMEM_BYTES ((GI_WARPS * GI_WARP_WORDS + GI_CRC_WORDS) * 4)
 // persistent: warps pull blocks from an atomic queue; lane 0 decodes, the warp writes
 __global__ void __launch_bounds__(GI_WARPS * 32, 1) k_gi_inflate(const uint8_t* __restrict__ comp, const GiBlock* __restrict__ blk,
                                                                  int n_blocks, uint8_t* out, int* __restrict__ status,
                                                                  unsigned* queue) {
     extern __shared__ __align__(16) uint32_t gi_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t* const crc_smem = gi_smem + (size_t)GI_WARPS * GI_WARP_WORDS;
+    gi_crc_tables(crc_smem);
+    __syncthreads();
     uint32_t* tab = gi_smem + (size_t)wid * GI_WARP_WORDS;
     uint32_t* tok = tab + GI_LL_SIZE + GI_D_SIZE;
     uint32_t* pre = tok + GI_TOK;          // GI_TOK + 1 offsets (+ padding)
@@ -469,14 +548,17 @@ __global__ void __launch_bounds__(GI_WARPS * 32, 1) k_gi_inflate(const uint8_t* 
             }
             __syncwarp();  // the bytes of this batch are in memory before the next batch refers to them
         }
-        if (lane == 0) {
-            int rc = verdict == 1 ? 0 : verdict;
-            if (rc == 0 && k.u_len) {
-                if (S.op != S.out_len) rc = -19;
-                else if (S.B.byte_pos() > S.in + S.in_len) rc = -20;
-            }
-            status[b] = rc;
+        int rc = verdict == 1 ? 0 : verdict;
+        if (lane == 0 && rc == 0 && k.u_len) {
+            if (S.op != S.out_len) rc = -19;
+            else if (S.B.byte_pos() > S.in + S.in_len) rc = -20;
         }
+        rc = __shfl_sync(0xffffffffu, rc, 0);
+        if (rc == 0 && k.check_crc) {  // gzip members carry the CRC-32 of their content: verified like htslib does
+            __syncwarp();
+            if (gi_crc32_warp(dst, k.u_len, crc_smem, lane) != k.crc) rc = -21;
+        }
+        if (lane == 0) status[b] = rc;
     }
 }
 

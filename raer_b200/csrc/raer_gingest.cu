@@ -566,6 +566,7 @@ struct raer_gi {
     int device = 0;
     cudaStream_t st = nullptr;
     int nf = 0;
+    uint32_t check_crc = 1;  // RAER_SKIP_CRC=1 turns the CRC-32 check of the inflated blocks off, as in the host ingest
     std::vector<GiReader> readers;
     std::vector<FILE*> fp;
     std::vector<std::vector<BaiRef>> bai;
@@ -643,6 +644,7 @@ extern "C" raer_gi* raer_gi_create(int device, int nf, const char* const* paths,
         delete g;
         return nullptr;
     }
+    if (getenv("RAER_SKIP_CRC")) g->check_crc = 0;
     int n_readers = 4;
     if (const char* e = getenv("RAER_GI_READERS")) n_readers = std::max(1, std::min(16, atoi(e)));
     g->readers.resize((size_t)n_readers);
@@ -770,6 +772,8 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
                 b.c_len = (uint32_t)(bsize + 1 - 12 - xlen - 8);
                 b.u_off = u;
                 b.u_len = isize;
+                b.crc = h_le32(h + bsize + 1 - 8);
+                b.check_crc = g->check_crc;
                 blocks.push_back(b);
                 blk_c.push_back(c_beg + (long long)o);
                 u += isize;
@@ -798,7 +802,7 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     if (!n_sm) {
         cudaDeviceProp prop;
         n_sm = cudaGetDeviceProperties(&prop, g->device) == cudaSuccess ? prop.multiProcessorCount : 148;
-        cudaFuncSetAttribute(k_gi_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_WARPS * GI_WARP_WORDS * 4);
+        cudaFuncSetAttribute(k_gi_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM_BYTES);
     }
     // b_lo .. b_hi: entries already staged in S.hblk (or, beyond its capacity, passed in `extra`)
     int n_launch = 0;
@@ -818,7 +822,7 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
         GCK(cudaMemcpyAsync((GiBlock*)S.blk.p + b_lo, src, (b_hi - b_lo) * sizeof(GiBlock), cudaMemcpyHostToDevice, st));
         const int nbk = (int)(b_hi - b_lo);
         const int grid = std::min<int>(n_sm, nbk);
-        k_gi_inflate<<<grid, GI_WARPS * 32, GI_WARPS * GI_WARP_WORDS * 4, st>>>((const uint8_t*)S.comp.p, (const GiBlock*)S.blk.p + b_lo, nbk,
+        k_gi_inflate<<<grid, GI_WARPS * 32, GI_SMEM_BYTES, st>>>((const uint8_t*)S.comp.p, (const GiBlock*)S.blk.p + b_lo, nbk,
                                                                               (uint8_t*)S.ubuf.p, (int*)S.status.p + b_lo,
                                                                               (unsigned*)S.queue.p + n_launch);
         ++n_launch;
@@ -1177,7 +1181,8 @@ extern "C" void raer_gi_stats(raer_gi* g, int64_t* launches, int64_t* inflated, 
 
 // test / bench entry: inflate n raw DEFLATE payloads that lie in one host buffer; status[i] = 0 or the decoder's code
 extern "C" int raer_gpu_inflate(const uint8_t* comp, int64_t comp_len, const int64_t* c_off, const int32_t* c_len, const int64_t* u_off,
-                                const int32_t* u_len, int32_t n_blocks, uint8_t* out, int64_t out_len, int32_t* status, double* kernel_ms) {
+                                const int32_t* u_len, const uint32_t* crc, int32_t n_blocks, uint8_t* out, int64_t out_len,
+                                int32_t* status, double* kernel_ms) {
     if (n_blocks <= 0) return RAER_OK;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); set_error("no usable CUDA device (the product has no CPU path)"); return RAER_ERR_NO_DEVICE; }
@@ -1187,6 +1192,8 @@ extern "C" int raer_gpu_inflate(const uint8_t* comp, int64_t comp_len, const int
         blk[(size_t)i].c_len = (uint32_t)c_len[i];
         blk[(size_t)i].u_off = (unsigned long long)u_off[i];
         blk[(size_t)i].u_len = (uint32_t)u_len[i];
+        blk[(size_t)i].crc = crc ? crc[i] : 0u;
+        blk[(size_t)i].check_crc = crc ? 1u : 0u;
     }
     DBufG d_comp, d_blk, d_out, d_status, d_q;
     int rc;
@@ -1201,13 +1208,13 @@ extern "C" int raer_gpu_inflate(const uint8_t* comp, int64_t comp_len, const int
     int dev = 0;
     cudaGetDevice(&dev);
     const int n_sm = cudaGetDeviceProperties(&prop, dev) == cudaSuccess ? prop.multiProcessorCount : 148;
-    cudaFuncSetAttribute(k_gi_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_WARPS * GI_WARP_WORDS * 4);
+    cudaFuncSetAttribute(k_gi_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM_BYTES);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     const int grid = std::min<int>(n_sm, (n_blocks + GI_WARPS - 1) / GI_WARPS);
     cudaEventRecord(e0);
-    k_gi_inflate<<<grid, GI_WARPS * 32, GI_WARPS * GI_WARP_WORDS * 4>>>((const uint8_t*)d_comp.p, (const GiBlock*)d_blk.p, n_blocks,
+    k_gi_inflate<<<grid, GI_WARPS * 32, GI_SMEM_BYTES>>>((const uint8_t*)d_comp.p, (const GiBlock*)d_blk.p, n_blocks,
                                                                        (uint8_t*)d_out.p, (int*)d_status.p, (unsigned*)d_q.p);
     cudaEventRecord(e1);
     GCK(cudaDeviceSynchronize());
