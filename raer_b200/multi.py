@@ -8,9 +8,11 @@ The reference parallelises the same way one level up: one .Call per chromosome t
 in R (R/pileup.R:208-243); calc_AEI and Smart-seq2 runs fan out per BAM file (R/calc_AEI.R:176-236, R/sc-pileup.R:185-230).
 A tile is one .Call with region = "contig:beg-end": the engine fetches the reads that overlap it through the index (the
 halo of a tile) and writes the rows of its positions only (src/plp.c:918), so the tiles' rows concatenate to the
-contig's rows. Two pieces of state do not cross a tile boundary, exactly as they do not cross a chromosome boundary
-in the reference's own parallel mode: the max_depth buffer count and the khash size behind the ALT column's order
-(relevant only after a site with four distinct variant keys).
+contig's rows. Three pieces of state do not cross a tile boundary, exactly as they do not cross a region boundary
+in the reference: the max_depth buffer count, the khash size behind the ALT column's order (relevant only after a site
+with four distinct variant keys), and the mate-overlap correction of a read whose earlier mate ends before the tile
+(htslib's overlap pass can change qualities of the later mate beyond the earlier mate's end; a region query does not
+fetch that mate, here or in the reference).
 """
 from __future__ import annotations
 

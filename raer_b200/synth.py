@@ -70,10 +70,15 @@ class Reads:
     mate_idx: torch.Tensor   # int64 index of the mate inside this contig's sorted order
 
     def window(self, beg: int, end: int) -> "Reads":
-        """The records that overlap [beg, end): what a region-sharded call hands to the device for a tile of a contig (the
-        reads of the tile plus its halo). A mate that stays outside loses the link: the bases the two share lie outside
-        the window as well."""
+        """The records a tile [beg, end) of a partitioned contig needs: the reads that overlap it (the tile's reads plus
+        their halo) and, so that the tiles' rows add up to exactly the rows of the whole contig, the mates of those reads:
+        htslib's overlap pass walks both mates from their starts, and its deletion / ref-skip catch-up can change
+        qualities of the later mate beyond the earlier mate's end, i.e. inside a tile the earlier mate does not reach.
+        (A call with region = "contig:beg-end" through the BAM index -- the reference's own region mode -- does not see
+        such a mate either; there the rows of a region can differ from the whole-contig rows at those rare sites.)"""
         keep = (self.end > beg) & (self.pos < end)
+        has_mate = self.mate_idx >= 0
+        keep = keep | (has_mate & keep[self.mate_idx.clamp(min=0)])
         idx = keep.nonzero().flatten()
         new_of_old = torch.full((self.pos.numel(),), -1, dtype=torch.int64, device=self.pos.device)
         new_of_old[idx] = torch.arange(idx.numel(), device=self.pos.device)
