@@ -50,6 +50,9 @@ using raer::set_error;
     } while (0)
 
 #define RAER_GI_FALLBACK 1  // not an error: this contig goes through the host ingest
+// what the kernels report through the `flags` word: 1 corrupt record layout, 2 read beyond the documented limits,
+// 4 reads out of order, 8 depth may reach max_depth, 16 two read names with one hash, 32 a record chain did not land on
+// the next start point, 64 a record of another contig inside the contig's byte range (chromosomes out of order)
 
 // ------------------------------------------------------------------------------------- scans
 #define SC_BLOCK 256
@@ -189,7 +192,10 @@ __global__ void k_gp_pass(const uint8_t* __restrict__ ub, const uint32_t* __rest
         pass[i] = 0; r_pos[i] = 0; r_end[i] = 0;
         return;
     }
-    if (tid != C.tid || (flag & 4)) ok = 0;  // another contig's record inside the byte range, or unmapped
+    // In a coordinate-sorted file the byte range of a contig (first record .. end of the last one) holds nothing else:
+    // a record of another contig means the input is not sorted (htslib: "chromosomes out of order")
+    if (tid != C.tid) { atomicOr(flags, 64); ok = 0; }
+    if (flag & 4) ok = 0;
     int rlen = 0;
     unsigned nal = 0;
     const uint8_t* cg = p + 32 + l_qname;
@@ -690,7 +696,10 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     long long c_last = (long long)(R.vend >> 16);
     if ((R.vend & 0xffff) == 0) c_last -= 1;  // the range ends exactly where a block starts: that block is not needed
     long long c_end = std::min<long long>(c_last + 65536 + 32, g->fsize[(size_t)f]);
-    if (c_end <= c_beg) return RAER_OK;
+    if (c_end <= c_beg || c_last >= g->fsize[(size_t)f]) {  // the index describes records the file does not hold
+        set_error("truncated BGZF file (the index points beyond the end of the file)");
+        return RAER_ERR_IO;
+    }
     const size_t nbytes = (size_t)(c_end - c_beg);
     // The range is read in chunks of 8 MB by a few threads. Each has one small pinned buffer and a stream of its own:
     // pread -> H2D copy -> (in chunk order) the BGZF block headers of its chunk, 18 bytes each, chained through BSIZE. A
@@ -751,7 +760,8 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
             if (fail || scan_done) break;
             const size_t hi = std::min(lo + CH, nbytes);  // blocks that start before hi are this chunk's
             while (!why && o < hi) {
-                if (!(o + 18 <= nbytes && (long long)o + c_beg <= c_last)) { scan_done = true; break; }
+                if ((long long)o + c_beg > c_last) { scan_done = true; break; }  // the block that ends the contig has been seen
+                if (o + 18 > nbytes) { why = "truncated BGZF file (the index points beyond the end of the file)"; break; }
                 const uint8_t* h = RD.buf + (o - lo);
                 const size_t avail = lo + len;
                 if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { why = "corrupt BGZF block header"; break; }
@@ -864,7 +874,7 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
             if (finished) break;
         }
     }
-    if (!scan_done && (o + 18 <= nbytes && (long long)o + c_beg <= c_last)) { set_error("truncated BGZF file (incomplete block at the end)"); return RAER_ERR_IO; }
+    if (!scan_done && (long long)o + c_beg <= c_last) { set_error("truncated BGZF file (incomplete block at the end)"); return RAER_ERR_IO; }
     g->t_read += t_wait;
     g->t_table += raer::now_seconds() - t1 - t_wait;
     if (blocks.empty()) return RAER_OK;
@@ -979,6 +989,7 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     GCK(cudaMemcpyAsync(g->h_small, d_small, 64, cudaMemcpyDeviceToHost, st));
     GCK(cudaStreamSynchronize(st));
     if (g->h_small[1] & 1) { set_error("corrupt BAM record"); return RAER_ERR_IO; }
+    if (g->h_small[1] & 64) { set_error("the input is not sorted (chromosomes out of order)"); return RAER_ERR_IO; }
     if (g->h_small[1] & 2) return RAER_GI_FALLBACK;  // a read beyond the documented limits: the host path reports it
     S.aligned_bases = (int64_t)g->h_small[2];
     S.max_span = (int)g->h_small[3];

@@ -835,6 +835,18 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
                   !(a->region && strchr(a->region, ':')) && !getenv("RAER_SERIAL_INGEST") && !getenv("RAER_BATCH_READS");
     if (const char* e = getenv("RAER_GPU_INGEST")) use_gi = use_gi && atoi(e) != 0;
     if (use_gi) use_gi = raer::indexes_usable(a->bampaths, a->indexes, nf);
+    // The device ingest reads the byte ranges the index names and nothing else, so a file that lost its tail would go
+    // unnoticed where the single stream runs into the cut. A complete BGZF file ends with the 28-byte empty block
+    // (htslib's bgzf_check_EOF): without it the call takes the host path, which reads to the end and reports what it finds.
+    for (int i = 0; use_gi && i < nf; ++i) {
+        static const unsigned char eof_blk[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43,
+                                                  0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned char tail[28];
+        FILE* fp = fopen(a->bampaths[i], "rb");
+        const bool ok = fp && fseek(fp, -28, SEEK_END) == 0 && fread(tail, 1, 28, fp) == 28 && memcmp(tail, eof_blk, 28) == 0;
+        if (fp) fclose(fp);
+        if (!ok) use_gi = false;
+    }
 
     double tm_open = raer::now_seconds();
     int gi_only_contig = -1;

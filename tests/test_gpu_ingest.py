@@ -168,3 +168,110 @@ def test_whole_contig_region_uses_the_device_ingest(ext, monkeypatch):
     dev, host = _both(pc, monkeypatch)
     assert dev["timing"]["n_device_contigs"] == 0
     _columns_equal(dev, host)
+
+
+# ---- a BAM that cannot be read to its end fails the call on the device path too (src/plp.c:1195; tests/test_ingest_errors.py
+# holds the host path to the same rules)
+def _device_call_fails(bam, fasta, monkeypatch, match):
+    monkeypatch.setenv("RAER_GPU_INGEST", "1")
+    pc = prepare_pileup_call(bam, fasta)
+    with pytest.raises(_cabi.RaerError, match=match):
+        _cabi.pileup(pc)
+
+
+def _last_mapped_coffset(bai_path):
+    """file offset of the block in which the last indexed (mapped) record ends"""
+    import struct
+
+    d = open(bai_path, "rb").read()
+    n_ref = struct.unpack_from("<i", d, 4)[0]
+    o, last = 8, 0
+    for _ in range(n_ref):
+        n_bin = struct.unpack_from("<i", d, o)[0]
+        o += 4
+        for _ in range(n_bin):
+            b, n_chunk = struct.unpack_from("<Ii", d, o)
+            o += 8
+            for _ in range(n_chunk):
+                vb, ve = struct.unpack_from("<QQ", d, o)
+                o += 16
+                if b != 37450:
+                    last = max(last, ve >> 16)
+        n_intv = struct.unpack_from("<i", d, o)[0]
+        o += 4 + 8 * n_intv
+    return last
+
+
+@pytest.mark.parametrize("frac", [0.3, 0.8])
+def test_device_ingest_truncated_file_fails(ext, tmp_path, monkeypatch, frac):
+    """cuts inside the mapped records (a cut in the unmapped tail is not seen by an indexed read, here or in htslib)"""
+    import shutil
+
+    p = str(tmp_path / "cut.bam")
+    data = open(ext.bam1, "rb").read()
+    frac = frac * _last_mapped_coffset(ext.bam1 + ".bai") / len(data)
+    open(p, "wb").write(data[: int(len(data) * frac)])
+    shutil.copy(ext.bam1 + ".bai", p + ".bai")
+    # without the BGZF end-of-file block the call goes to the host stream, which reads to the cut and reports it
+    _device_call_fails(p, ext.fasta, monkeypatch, "truncated|corrupt|inflate failed")
+    # a file that keeps its end-of-file block but lost blocks in front of it: the index points beyond the data
+    if frac < 0.5:
+        open(p, "wb").write(data[: int(len(data) * frac)] + bamtools._EOF)
+        _device_call_fails(p, ext.fasta, monkeypatch, "truncated|corrupt|inflate failed|not sorted")
+
+
+def test_device_ingest_flipped_payload_bytes_fail(tmp_path, monkeypatch):
+    """a flipped bit in a block's payload either breaks the DEFLATE stream or the block's CRC-32 (verified by the inflate
+    kernel): never silently other bytes. The file is large enough that the header read does not touch the damaged block."""
+    import random
+    import shutil
+
+    ds = synth.make_bulk_dataset(str(tmp_path / "d"), n_bams=1, n_contigs=1, contig_len=400_000, pairs_per_contig=45_000, seed=5)
+    src = ds["bams"][0]
+    data = open(src, "rb").read()
+    offs, o = [], 0
+    while o + 18 <= len(data):
+        bsize = int.from_bytes(data[o + 16:o + 18], "little")
+        offs.append((o, bsize + 1))
+        o += bsize + 1
+    last = _last_mapped_coffset(src + ".bai")
+    inner = [(bo, bl) for bo, bl in offs if bo > (1 << 20) and bo + bl < last]
+    assert len(inner) > 20
+    rng = random.Random(11)
+    p = str(tmp_path / "flip.bam")
+    shutil.copy(src + ".bai", p + ".bai")
+    for _ in range(6):
+        bo, bl = inner[rng.randrange(len(inner))]
+        d = bytearray(data)
+        d[bo + 18 + rng.randrange(0, bl - 18 - 8)] ^= 1 << rng.randrange(8)
+        open(p, "wb").write(d)
+        _device_call_fails(p, ds["fasta"], monkeypatch, "inflate failed")
+    # the CRC itself: a damaged footer is noticed as well
+    bo, bl = inner[3]
+    d = bytearray(data)
+    d[bo + bl - 8] ^= 0x10
+    open(p, "wb").write(d)
+    _device_call_fails(p, ds["fasta"], monkeypatch, r"inflate failed .*-21")
+    monkeypatch.setenv("RAER_SKIP_CRC", "1")  # the check can be switched off like on the host
+    assert _cabi.pileup(prepare_pileup_call(p, ds["fasta"]))["nrows"] > 0
+
+
+def test_device_ingest_unsorted_input_fails(ext, tmp_path, monkeypatch):
+    hdr, refs, recs = bamtools.read_bam(ext.bam1)
+    mapped = [i for i, r in enumerate(recs) if r.tid == 0 and not (r.flag & (4 | 256 | 512 | 1024 | 2048))
+              and (not (r.flag & 1) or (r.flag & 2))]
+    i, j = mapped[10], mapped[len(mapped) // 2]
+    assert recs[i].pos != recs[j].pos
+    recs[i], recs[j] = recs[j], recs[i]
+    p = str(tmp_path / "unsorted.bam")
+    bamtools.write_bam(p, hdr, refs, recs)
+    _device_call_fails(p, ext.fasta, monkeypatch, "not sorted")
+    # chromosomes out of order
+    hdr, refs, recs = bamtools.read_bam(ext.bam1)
+    tids = sorted({r.tid for r in recs if r.tid >= 0})
+    first = [r for r in recs if r.tid == tids[0]]
+    second = [r for r in recs if r.tid == tids[1]]
+    rest = [r for r in recs if r.tid not in (tids[0], tids[1])]
+    half = len(first) // 2
+    bamtools.write_bam(p, hdr, refs, first[:half] + second + first[half:] + rest)
+    _device_call_fails(p, ext.fasta, monkeypatch, "not sorted")
