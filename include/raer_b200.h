@@ -339,6 +339,10 @@ int raer_sc_batch_device(raer_sc_ctx* ctx, const raer_sc_conf* conf, const raer_
                          int64_t* n_tuples, int64_t* launches);
 /* host path: H2D of the batch and the sites, kernels, D2H of the cells */
 int raer_sc_batch_host(raer_sc_ctx* ctx, const raer_sc_conf* conf, const raer_read_batch* host_batch, raer_sc_cells* out);
+/* host site arrays in conf, batch already in device memory (what the device ingest produces): kernels, D2H of the cells */
+int raer_sc_batch_device_cells(raer_sc_ctx* ctx, const raer_sc_conf* conf, const raer_read_batch* dev_batch, raer_sc_cells* out);
+/* contigs the last raer_scpileup() / raer_scpileup_triplets() call of this process took through the device ingest */
+int64_t raer_sc_last_device_contigs(void);
 /* per-kernel-class CUDA-event timing since raer_sc_ctx_profile(ctx, 1): ms[0..3] / n[0..3] = tuple emission, radix
  * sort (all passes), consensus + cell reduction, mate overlap */
 void raer_sc_ctx_profile(raer_sc_ctx* ctx, int on);

@@ -478,3 +478,10 @@ def gpu_inflate(payloads, sizes, crcs=None):
         raise RaerError(last_error())
     res = [out[int(u_off[i]):int(u_off[i]) + int(u_len[i])].tobytes() for i in range(n)]
     return res, status, ms.value
+
+
+def sc_last_device_contigs() -> int:
+    """contigs the last scpileup call took through the device ingest"""
+    L = lib()
+    L.raer_sc_last_device_contigs.restype = C.c_int64
+    return int(L.raer_sc_last_device_contigs())

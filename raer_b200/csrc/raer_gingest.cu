@@ -52,7 +52,8 @@ using raer::set_error;
 #define RAER_GI_FALLBACK 1  // not an error: this contig goes through the host ingest
 // what the kernels report through the `flags` word: 1 corrupt record layout, 2 read beyond the documented limits,
 // 4 reads out of order, 8 depth may reach max_depth, 16 two read names with one hash, 32 a record chain did not land on
-// the next start point, 64 a record of another contig inside the contig's byte range (chromosomes out of order)
+// the next start point, 64 a record of another contig inside the contig's byte range (chromosomes out of order),
+// 256 a UMI the 2-bit code does not cover
 
 // ------------------------------------------------------------------------------------- scans
 #define SC_BLOCK 256
@@ -129,6 +130,7 @@ __global__ void k_sc_apply(const uint32_t* __restrict__ in, long long n, const u
 }
 
 // ------------------------------------------------------------------------------------- records
+typedef unsigned long long recoff_t;  // offset of a record in the inflated buffer of its file range (may exceed 4 GB)
 __device__ __forceinline__ uint32_t ld32u(const uint8_t* p) {  // unaligned little-endian load
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
@@ -137,7 +139,7 @@ __device__ __forceinline__ uint32_t ld16u(const uint8_t* p) { return (uint32_t)p
 // start point k chains through the records that begin in [sp[k], sp[k + 1]); FILL writes their offsets
 template <bool FILL>
 __global__ void k_gw_walk(const uint8_t* __restrict__ ub, unsigned long long total, const unsigned long long* __restrict__ sp, int nsp,
-                          uint32_t* cnt, const uint32_t* __restrict__ base, uint32_t* __restrict__ rec_off, int* flags) {
+                          uint32_t* cnt, const uint32_t* __restrict__ base, recoff_t* __restrict__ rec_off, int* flags) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nsp) return;
     unsigned long long off = sp[k];
@@ -148,7 +150,7 @@ __global__ void k_gw_walk(const uint8_t* __restrict__ ub, unsigned long long tot
         if (off + 36 > total) { atomicOr(flags, 1); break; }  // a record header does not fit: corrupt or truncated
         const uint32_t bs = ld32u(ub + off);
         if (bs < 32 || off + 4 + bs > total) { atomicOr(flags, 1); break; }
-        if (FILL) rec_off[b0 + n] = (uint32_t)off;
+        if (FILL) rec_off[b0 + n] = off;
         ++n;
         off += 4ull + bs;
     }
@@ -172,12 +174,67 @@ struct GpConf {
     const uint32_t* site_bits;
     const uint32_t* site_pre;
     int site_len;
+    // single cell (screadaln, src/sc-plp.c:449-511): the cell-barcode tag has to be on the whitelist (open-addressing table
+    // of FNV-1a name hashes, strings compared on a hit), or every read of the file belongs to one column (Smart-seq2)
+    int sc, has_cb_tag, has_umi_tag, fixed_cb;
+    uint8_t cb_tag[2], umi_tag[2];
+    const unsigned long long* wl_key;  // 0 = empty slot
+    const int32_t* wl_col;             // 1-based whitelist column
+    const uint32_t* wl_off;            // offset of the barcode string in wl_pool (NUL terminated)
+    const uint8_t* wl_pool;
+    uint32_t wl_mask;
+    int* umi_len;                      // length of the UMIs seen so far (0: none yet); all have to agree
 };
 
+// BAM auxiliary fields: the value of tag t0 t1 (pointer to its type byte) or nullptr; same walk as the host's aux_get
+__device__ const uint8_t* gp_aux_find(const uint8_t* p, const uint8_t* end, uint8_t t0, uint8_t t1) {
+    while (p + 3 <= end) {
+        const bool hit = p[0] == t0 && p[1] == t1;
+        const int t = p[2];
+        const uint8_t* v = p + 2;
+        p += 3;
+        if (t == 'Z' || t == 'H') {
+            while (p < end && *p) ++p;
+            ++p;
+        } else if (t == 'B') {
+            if (p + 5 > end) return nullptr;
+            const int e = p[0];
+            const int sz = (e == 'c' || e == 'C' || e == 'A') ? 1 : (e == 's' || e == 'S') ? 2 : (e == 'i' || e == 'I' || e == 'f') ? 4 : e == 'd' ? 8 : 0;
+            const uint32_t cnt = ld32u(p + 1);
+            p += 5 + (size_t)sz * cnt;
+        } else {
+            const int sz = (t == 'c' || t == 'C' || t == 'A') ? 1 : (t == 's' || t == 'S') ? 2 : (t == 'i' || t == 'I' || t == 'f') ? 4 : t == 'd' ? 8 : 0;
+            if (!sz) return nullptr;
+            p += sz;
+        }
+        if (p > end) return nullptr;
+        if (hit) return v;
+    }
+    return nullptr;
+}
+__device__ __forceinline__ unsigned long long gp_fnv(const uint8_t* s) {
+    unsigned long long h = 1469598103934665603ull;
+    for (; *s; ++s) { h ^= *s; h *= 1099511628211ull; }
+    return h ? h : 1ull;
+}
+// whitelist column of the NUL-terminated barcode s, 0 if it is not listed
+__device__ int gp_wl_lookup(const GpConf& C, const uint8_t* s) {
+    const unsigned long long h = gp_fnv(s);
+    for (uint32_t slot = (uint32_t)h & C.wl_mask;; slot = (slot + 1) & C.wl_mask) {
+        const unsigned long long k = C.wl_key[slot];
+        if (k == 0) return 0;
+        if (k != h) continue;
+        const uint8_t* w = C.wl_pool + C.wl_off[slot];
+        int i = 0;
+        while (w[i] && w[i] == s[i]) ++i;
+        if (w[i] == s[i]) return C.wl_col[slot];
+    }
+}
+
 // per record: does it pass readaln? pos / end / aligned bases. One thread per record.
-__global__ void k_gp_pass(const uint8_t* __restrict__ ub, const uint32_t* __restrict__ rec_off, long long n_rec, GpConf C,
+__global__ void k_gp_pass(const uint8_t* __restrict__ ub, const recoff_t* __restrict__ rec_off, long long n_rec, GpConf C,
                           uint32_t* __restrict__ pass, int32_t* __restrict__ r_pos, int32_t* __restrict__ r_end,
-                          unsigned long long* stats, int* flags) {
+                          unsigned long long* stats, int* flags, int32_t* __restrict__ rec_cb) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n_rec) return;
     const uint8_t* p = ub + rec_off[i] + 4;
@@ -190,6 +247,7 @@ __global__ void k_gp_pass(const uint8_t* __restrict__ ub, const uint32_t* __rest
     if (l_qseq < 0 || 32ull + l_qname + 4ull * n_cigar + ((unsigned long long)l_qseq + 1) / 2 + (unsigned long long)l_qseq > bs) {
         atomicOr(flags, 1);  // corrupt record layout
         pass[i] = 0; r_pos[i] = 0; r_end[i] = 0;
+        if (C.sc) rec_cb[i] = 0;
         return;
     }
     // In a coordinate-sorted file the byte range of a contig (first record .. end of the last one) holds nothing else:
@@ -213,6 +271,19 @@ __global__ void k_gp_pass(const uint8_t* __restrict__ ub, const uint32_t* __rest
             if (tot) atomicAdd(&stats[0], (unsigned long long)tot);
             atomicMax(&stats[1], (unsigned long long)mx);
         }
+    }
+    if (C.sc) {  // src/sc-plp.c:464-477: reads without a listed cell barcode are skipped before anything else
+        int col = 0;
+        if (C.has_cb_tag) {
+            if (ok) {
+                const uint8_t* aux = cg + 4 * n_cigar + (l_qseq + 1) / 2 + l_qseq;
+                const uint8_t* v = gp_aux_find(aux, p + bs, C.cb_tag[0], C.cb_tag[1]);
+                if (v && (*v == 'Z' || *v == 'H')) col = gp_wl_lookup(C, v + 1);
+                if (!col) ok = 0;
+            }
+        }
+        if (C.fixed_cb) col = C.fixed_cb;
+        rec_cb[i] = col;
     }
     const uint32_t test = (C.keep0 & ~(uint32_t)flag) | (C.keep1 & (uint32_t)flag);
     if (~test & 2047u) ok = 0;
@@ -256,7 +327,7 @@ __global__ void k_gp_cpos(const uint32_t* __restrict__ pass, const uint32_t* __r
 
 // bam_plp_push keeps a read only if it can still produce a column (end > position of the previous pushed read);
 // sizes of the kept reads; guards
-__global__ void k_gp_kept(const uint8_t* __restrict__ ub, const uint32_t* __restrict__ rec_off, const uint32_t* __restrict__ pass,
+__global__ void k_gp_kept(const uint8_t* __restrict__ ub, const recoff_t* __restrict__ rec_off, const uint32_t* __restrict__ pass,
                           const uint32_t* __restrict__ pidx, const int32_t* __restrict__ r_pos, const int32_t* __restrict__ r_end,
                           const int32_t* __restrict__ cpos, long long n_rec, long long n_pass, GpConf C, int max_span,
                           uint32_t* __restrict__ kept, uint32_t* __restrict__ ncig, uint32_t* __restrict__ sqb,
@@ -324,17 +395,19 @@ struct GpOut {  // the batch arrays (device), this file's first read / CIGAR wor
     uint32_t* cigar;
     uint8_t* seq;
     uint8_t* qual;
+    int32_t* cb;     // single cell: whitelist column / UMI code of every read
+    uint32_t* umi;
     long long r0, c0, s0;
 };
 
 // one thread per kept record: header, CIGAR words, packed sequence, qualities; read-name hash of the reads that take
 // part in the mate-overlap pairing
-__global__ void k_gp_write(const uint8_t* __restrict__ ub, const uint32_t* __restrict__ rec_off, const uint32_t* __restrict__ kept,
+__global__ void k_gp_write(const uint8_t* __restrict__ ub, const recoff_t* __restrict__ rec_off, const uint32_t* __restrict__ kept,
                            const uint32_t* __restrict__ kidx, const uint32_t* __restrict__ coff, const uint32_t* __restrict__ soff,
                            const uint32_t* __restrict__ elig, const uint32_t* __restrict__ eidx, const int32_t* __restrict__ r_end,
                            const int32_t* __restrict__ prevpos, long long n_rec, GpConf C, GpOut O,
-                           unsigned long long* __restrict__ pkey, uint32_t* __restrict__ pval, uint32_t* __restrict__ krec,
-                           int32_t* __restrict__ kprev) {
+                           unsigned long long* __restrict__ pkey, uint32_t* __restrict__ pval, recoff_t* __restrict__ krec,
+                           int32_t* __restrict__ kprev, const int32_t* __restrict__ rec_cb, int* flags) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n_rec || !kept[i]) return;
     const uint8_t* p = ub + rec_off[i] + 4;
@@ -385,6 +458,34 @@ __global__ void k_gp_write(const uint8_t* __restrict__ ub, const uint32_t* __res
     uint8_t* qo = O.qual + 2 * (O.s0 + soff[i]);
     for (int k = 0; k < l_qseq; ++k) qo[k] = ql[k];
     for (int k = l_qseq; k < 2 * padded; ++k) qo[k] = 0;
+    if (C.sc) {
+        O.cb[O.r0 + K] = rec_cb[i];
+        uint32_t code = 0;
+        if (C.has_umi_tag) {
+            // The host keeps a dictionary string -> id; all the kernels need is that equal UMIs get equal ids. UMIs are
+            // short runs of ACGT of one length: 2 bits per base + 1 is such an id without a dictionary. Anything else
+            // (other letters, more than 15 bases, mixed lengths) sends the contig to the host.
+            const uint8_t* aux = ql + l_qseq;
+            const uint8_t* v = gp_aux_find(aux, p + ld32u(p - 4), C.umi_tag[0], C.umi_tag[1]);
+            if (v && (*v == 'Z' || *v == 'H')) {
+                uint32_t x = 0;
+                int n = 0;
+                bool good = true;
+                for (const uint8_t* q = v + 1; *q; ++q, ++n) {
+                    const int c = *q == 'A' ? 0 : *q == 'C' ? 1 : *q == 'G' ? 2 : *q == 'T' ? 3 : -1;
+                    if (c < 0 || n >= 15) { good = false; break; }
+                    x = (x << 2) | (uint32_t)c;
+                }
+                if (good && n > 0) {
+                    const int seen = atomicCAS(C.umi_len, 0, n);
+                    if (seen != 0 && seen != n) good = false;
+                }
+                if (!good || n == 0) atomicOr(flags, 256);
+                code = x + 1u;
+            }
+        }
+        O.umi[O.r0 + K] = code;
+    }
     krec[K] = rec_off[i];
     kprev[K] = prevpos[i];
     if (elig[i]) {
@@ -401,7 +502,7 @@ __global__ void k_gp_write(const uint8_t* __restrict__ ub, const uint32_t* __res
 // with it and deletes it; otherwise it becomes the entry if its mate lies ahead (mpos >= pos, or mpos == -1 of a
 // paired read). An entry is dead once its read has left the pileup buffer (end < position of the previous pushed read).
 __global__ void k_gp_pair(const unsigned long long* __restrict__ pkey, const uint32_t* __restrict__ pval, long long n,
-                          const uint8_t* __restrict__ ub, const uint32_t* __restrict__ krec, const int32_t* __restrict__ kprev,
+                          const uint8_t* __restrict__ ub, const recoff_t* __restrict__ krec, const int32_t* __restrict__ kprev,
                           raer_read_hdr* hdr, long long r0, int32_t* __restrict__ pair_b, unsigned long long* n_pairs, int* flags) {
     const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= n) return;
@@ -553,7 +654,7 @@ static void pin_release(uint8_t* p) {
 // everything one file contributes to the batch of a contig, still in its own buffers
 struct FileStage {
     DBufG comp, blk, ubuf, status, sp, cnt, base, rec_off, pass, pidx, r_pos, r_end, cpos, kept, kidx, ncig, coff, sqb, soff, elig, eidx,
-        prevpos, bsum, krec, kprev, pkey, pval, pkey2, pval2, hist, queue;
+        prevpos, bsum, krec, kprev, pkey, pval, pkey2, pval2, hist, queue, rec_cb;
     PinnedBuf hblk;
     long long n_rec = 0, n_pass = 0, n_kept = 0, n_cig = 0, n_sq = 0, n_elig = 0;
     unsigned long long u_total = 0;
@@ -578,7 +679,17 @@ struct raer_gi {
     std::vector<std::vector<BaiRef>> bai;
     std::vector<long long> fsize;
     std::vector<FileStage> stage;
-    DBufG small, site_bits, site_pre, hdr, maxend, cigar, seq, qual, pair_b, endtmp;
+    DBufG small, site_bits, site_pre, hdr, maxend, cigar, seq, qual, pair_b, endtmp, cb, umi, wl_key, wl_col, wl_off, wl_pool, umi_len;
+    uint32_t wl_mask = 0;
+    bool wl_built = false;
+    size_t pool_bytes() const {  // what the device pool holds for reuse (freed buffers of earlier contigs count as free memory)
+        cudaMemPool_t pool;
+        unsigned long long reserved = 0, used = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess) return 0;
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        return reserved > used ? (size_t)(reserved - used) : 0;
+    }
     unsigned long long* h_small = nullptr;  // pinned, 8 counters
     int64_t launches = 0, inflated = 0, compressed = 0, records = 0, walk_retries = 0;
     double t_read = 0, t_table = 0, t_alloc = 0, t_inflate = 0, t_pass = 0, t_kept = 0, t_write = 0;  // host wall seconds per stage
@@ -701,6 +812,11 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
         return RAER_ERR_IO;
     }
     const size_t nbytes = (size_t)(c_end - c_beg);
+    {   // compressed bytes + inflated records (about 4x) + per-record tables + this file's share of the batch: about 8x
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && nbytes * 8 > free_b + g->pool_bytes()) return RAER_GI_FALLBACK;
+        cudaGetLastError();
+    }
     // The range is read in chunks of 8 MB by a few threads. Each has one small pinned buffer and a stream of its own:
     // pread -> H2D copy -> (in chunk order) the BGZF block headers of its chunk, 18 bytes each, chained through BSIZE. A
     // chunk is read with 64 KiB of overlap so that every block that starts in it is complete. This thread collects the
@@ -878,7 +994,6 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     g->t_read += t_wait;
     g->t_table += raer::now_seconds() - t1 - t_wait;
     if (blocks.empty()) return RAER_OK;
-    if (u >= (1ull << 32) - 65536) return RAER_GI_FALLBACK;  // record offsets are 32 bit here
     if (too_small) {  // inflated size beyond the guess: the compressed bytes are on the device, inflate everything again
         GCK(cudaStreamSynchronize(st));
         if ((rc = S.ubuf.ensure((size_t)u + 64))) return rc;
@@ -967,20 +1082,21 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     if (S.n_rec == 0) return RAER_OK;
     const double t4 = raer::now_seconds();
     const size_t nr = (size_t)S.n_rec;
-    if ((rc = S.rec_off.ensure(nr * 4)) || (rc = S.pass.ensure(nr * 4)) || (rc = S.pidx.ensure(nr * 4)) || (rc = S.r_pos.ensure(nr * 4)) ||
+    if ((rc = S.rec_off.ensure(nr * 8)) || (rc = S.pass.ensure(nr * 4)) || (rc = S.pidx.ensure(nr * 4)) || (rc = S.r_pos.ensure(nr * 4)) ||
         (rc = S.r_end.ensure(nr * 4)) || (rc = S.cpos.ensure(nr * 4)) || (rc = S.kept.ensure(nr * 4)) || (rc = S.kidx.ensure(nr * 4)) ||
         (rc = S.ncig.ensure(nr * 4)) || (rc = S.coff.ensure(nr * 4)) || (rc = S.sqb.ensure(nr * 4)) || (rc = S.soff.ensure(nr * 4)) ||
-        (rc = S.elig.ensure(nr * 4)) || (rc = S.eidx.ensure(nr * 4)) || (rc = S.prevpos.ensure(nr * 4)))
+        (rc = S.elig.ensure(nr * 4)) || (rc = S.eidx.ensure(nr * 4)) || (rc = S.prevpos.ensure(nr * 4)) ||
+        (C0.sc && (rc = S.rec_cb.ensure(nr * 4))))
         return rc;
     g->t_alloc += raer::now_seconds() - t4;
     const double t5 = raer::now_seconds();
     k_gw_walk<true><<<(nsp + 127) / 128, 128, 0, st>>>((const uint8_t*)S.ubuf.p, u_last, (const unsigned long long*)S.sp.p, nsp, nullptr,
-                                                        (const uint32_t*)S.base.p, (uint32_t*)S.rec_off.p, d_flags);
+                                                        (const uint32_t*)S.base.p, (recoff_t*)S.rec_off.p, d_flags);
     GpConf C = C0;
     C.tid = ftid;
     const unsigned gr = (unsigned)((nr + 255) / 256);
-    k_gp_pass<<<gr, 256, 0, st>>>((const uint8_t*)S.ubuf.p, (const uint32_t*)S.rec_off.p, S.n_rec, C, (uint32_t*)S.pass.p,
-                                  (int32_t*)S.r_pos.p, (int32_t*)S.r_end.p, d_small + 2, d_flags);
+    k_gp_pass<<<gr, 256, 0, st>>>((const uint8_t*)S.ubuf.p, (const recoff_t*)S.rec_off.p, S.n_rec, C, (uint32_t*)S.pass.p,
+                                  (int32_t*)S.r_pos.p, (int32_t*)S.r_end.p, d_small + 2, d_flags, (int32_t*)S.rec_cb.p);
     g->launches += 2;
     if ((rc = g_scan<false>(g, S, (const uint32_t*)S.pass.p, (uint32_t*)S.pidx.p, S.n_rec, d_small + 5))) return rc;
     k_gp_cpos<<<gr, 256, 0, st>>>((const uint32_t*)S.pass.p, (const uint32_t*)S.pidx.p, (const int32_t*)S.r_pos.p, S.n_rec,
@@ -996,7 +1112,7 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     S.n_pass = (long long)g->h_small[5];
     g->t_pass += raer::now_seconds() - t5;
     const double t6 = raer::now_seconds();
-    k_gp_kept<<<gr, 256, 0, st>>>((const uint8_t*)S.ubuf.p, (const uint32_t*)S.rec_off.p, (const uint32_t*)S.pass.p,
+    k_gp_kept<<<gr, 256, 0, st>>>((const uint8_t*)S.ubuf.p, (const recoff_t*)S.rec_off.p, (const uint32_t*)S.pass.p,
                                   (const uint32_t*)S.pidx.p, (const int32_t*)S.r_pos.p, (const int32_t*)S.r_end.p,
                                   (const int32_t*)S.cpos.p, S.n_rec, S.n_pass, C, S.max_span, (uint32_t*)S.kept.p, (uint32_t*)S.ncig.p,
                                   (uint32_t*)S.sqb.p, (uint32_t*)S.elig.p, (int32_t*)S.prevpos.p, d_flags);
@@ -1042,6 +1158,56 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
     C.remove_overlaps = ic->remove_overlaps;
     C.min_overhang = ic->min_overhang;
     C.max_depth = ic->max_depth;
+    if (ic->sc) {
+        C.sc = 1;
+        C.has_cb_tag = ic->cb_index && ic->cb_tag.size() == 2;
+        C.has_umi_tag = ic->umi_tag.size() == 2;
+        C.fixed_cb = ic->fixed_cb;
+        if (C.has_cb_tag) { C.cb_tag[0] = (uint8_t)ic->cb_tag[0]; C.cb_tag[1] = (uint8_t)ic->cb_tag[1]; }
+        if (C.has_umi_tag) { C.umi_tag[0] = (uint8_t)ic->umi_tag[0]; C.umi_tag[1] = (uint8_t)ic->umi_tag[1]; }
+        if (C.has_cb_tag && !g->wl_built) {  // the whitelist as an open-addressing table, once per call
+            const size_t n = ic->cb_index->size();
+            size_t cap = 64;
+            while (cap < 2 * n + 2) cap <<= 1;
+            std::vector<unsigned long long> key(cap, 0);
+            std::vector<int32_t> col(cap, 0);
+            std::vector<uint32_t> off(cap, 0);
+            std::vector<uint8_t> pool;
+            for (const auto& kv : *ic->cb_index) {
+                unsigned long long h = 1469598103934665603ull;
+                for (unsigned char ch : kv.first) { if (!ch) break; h ^= ch; h *= 1099511628211ull; }
+                if (!h) h = 1;
+                size_t slot = (size_t)((uint32_t)h & (uint32_t)(cap - 1));
+                while (key[slot]) slot = (slot + 1) & (cap - 1);
+                key[slot] = h;
+                col[slot] = kv.second;
+                off[slot] = (uint32_t)pool.size();
+                pool.insert(pool.end(), kv.first.begin(), kv.first.end());
+                pool.push_back(0);
+            }
+            pool.push_back(0);
+            if ((rc = g->wl_key.ensure(cap * 8)) || (rc = g->wl_col.ensure(cap * 4)) || (rc = g->wl_off.ensure(cap * 4)) ||
+                (rc = g->wl_pool.ensure(pool.size())))
+                return rc;
+            GCK(cudaMemcpyAsync(g->wl_key.p, key.data(), cap * 8, cudaMemcpyHostToDevice, st));
+            GCK(cudaMemcpyAsync(g->wl_col.p, col.data(), cap * 4, cudaMemcpyHostToDevice, st));
+            GCK(cudaMemcpyAsync(g->wl_off.p, off.data(), cap * 4, cudaMemcpyHostToDevice, st));
+            GCK(cudaMemcpyAsync(g->wl_pool.p, pool.data(), pool.size(), cudaMemcpyHostToDevice, st));
+            GCK(cudaStreamSynchronize(st));
+            g->wl_mask = (uint32_t)(cap - 1);
+            g->wl_built = true;
+        }
+        C.wl_key = (const unsigned long long*)g->wl_key.p;
+        C.wl_col = (const int32_t*)g->wl_col.p;
+        C.wl_off = (const uint32_t*)g->wl_off.p;
+        C.wl_pool = (const uint8_t*)g->wl_pool.p;
+        C.wl_mask = g->wl_mask;
+        if (!g->umi_len.p) {
+            if ((rc = g->umi_len.ensure(16))) return rc;
+            GCK(cudaMemsetAsync(g->umi_len.p, 0, 16, st));
+        }
+        C.umi_len = (int*)g->umi_len.p;
+    }
     *site_mask_dev = nullptr;
     if (site) {
         const size_t words = ((size_t)contig_len + 31) / 32 + 1;
@@ -1087,7 +1253,8 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
     if ((rc = g->hdr.ensure((size_t)n_reads * sizeof(raer_read_hdr))) || (rc = g->maxend.ensure((size_t)n_reads * 4)) ||
         (rc = g->endtmp.ensure((size_t)n_reads * 4)) || (rc = g->cigar.ensure((size_t)n_cig * 4 + 16)) ||
         (rc = g->seq.ensure((size_t)n_sq + 16)) || (rc = g->qual.ensure((size_t)n_sq * 2 + 16)) ||
-        (rc = g->pair_b.ensure((size_t)n_reads * 4 + 16)))
+        (rc = g->pair_b.ensure((size_t)n_reads * 4 + 16)) ||
+        (ic->sc && ((rc = g->cb.ensure((size_t)n_reads * 4)) || (rc = g->umi.ensure((size_t)n_reads * 4)))))
         return rc;
     unsigned long long* d_small = (unsigned long long*)g->small.p;
     GCK(cudaMemsetAsync(d_small, 0, 256, st));
@@ -1099,7 +1266,7 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
         C.libtype = ic->libtype[(size_t)f];
         C.tid = ftid[f];
         const size_t nk = (size_t)S.n_kept, ne = (size_t)S.n_elig;
-        if ((rc = S.krec.ensure(nk * 4)) || (rc = S.kprev.ensure(nk * 4)) || (rc = S.pkey.ensure(ne * 8 + 16)) ||
+        if ((rc = S.krec.ensure(nk * 8)) || (rc = S.kprev.ensure(nk * 4)) || (rc = S.pkey.ensure(ne * 8 + 16)) ||
             (rc = S.pval.ensure(ne * 4 + 16)) || (rc = S.pkey2.ensure(ne * 8 + 16)) || (rc = S.pval2.ensure(ne * 4 + 16)))
             return rc;
         GpOut O;
@@ -1107,15 +1274,17 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
         O.cigar = (uint32_t*)g->cigar.p;
         O.seq = (uint8_t*)g->seq.p;
         O.qual = (uint8_t*)g->qual.p;
+        O.cb = (int32_t*)g->cb.p;
+        O.umi = (uint32_t*)g->umi.p;
         O.r0 = file_off[f];
         O.c0 = c0;
         O.s0 = s0;
         const unsigned gr = (unsigned)((S.n_rec + 255) / 256);
-        k_gp_write<<<gr, 256, 0, st>>>((const uint8_t*)S.ubuf.p, (const uint32_t*)S.rec_off.p, (const uint32_t*)S.kept.p,
+        k_gp_write<<<gr, 256, 0, st>>>((const uint8_t*)S.ubuf.p, (const recoff_t*)S.rec_off.p, (const uint32_t*)S.kept.p,
                                        (const uint32_t*)S.kidx.p, (const uint32_t*)S.coff.p, (const uint32_t*)S.soff.p,
                                        (const uint32_t*)S.elig.p, (const uint32_t*)S.eidx.p, (const int32_t*)S.r_end.p,
                                        (const int32_t*)S.prevpos.p, S.n_rec, C, O, (unsigned long long*)S.pkey.p, (uint32_t*)S.pval.p,
-                                       (uint32_t*)S.krec.p, (int32_t*)S.kprev.p);
+                                       (recoff_t*)S.krec.p, (int32_t*)S.kprev.p, (const int32_t*)S.rec_cb.p, (int*)(d_small + 1));
         ++g->launches;
         if (S.n_elig > 0) {
             const unsigned nblk = (unsigned)((S.n_elig + (long long)RS_BLOCK * RS_ITEMS - 1) / ((long long)RS_BLOCK * RS_ITEMS));
@@ -1126,7 +1295,7 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
             unsigned* v_out = (unsigned*)S.pval2.p;
             g->launches += rs_sort(k_in, v_in, k_out, v_out, S.n_elig, 64, (unsigned*)S.hist.p, st);
             k_gp_pair<<<(unsigned)((S.n_elig + 255) / 256), 256, 0, st>>>(k_in, v_in, S.n_elig, (const uint8_t*)S.ubuf.p,
-                                                                          (const uint32_t*)S.krec.p, (const int32_t*)S.kprev.p,
+                                                                          (const recoff_t*)S.krec.p, (const int32_t*)S.kprev.p,
                                                                           (raer_read_hdr*)g->hdr.p, file_off[f], (int32_t*)g->pair_b.p,
                                                                           d_small + 4, (int*)(d_small + 1));
             ++g->launches;
@@ -1138,6 +1307,7 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
     GCK(cudaStreamSynchronize(st));
     if (cudaGetLastError() != cudaSuccess) { set_error("device ingest kernels failed"); return RAER_ERR_CUDA; }
     if (g->h_small[1] & 16) return RAER_GI_FALLBACK;  // two read names with one 64-bit hash: the host's string table decides
+    if (g->h_small[1] & 256) return RAER_GI_FALLBACK;  // a UMI the 2-bit code does not cover: the host's dictionary takes it
     b->hdr = (const raer_read_hdr*)g->hdr.p;
     b->cigar = (const uint32_t*)g->cigar.p;
     b->seq = (const uint8_t*)g->seq.p;
@@ -1147,6 +1317,10 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
     b->pair_b = (const int32_t*)g->pair_b.p;
     b->n_pairs = (int64_t)g->h_small[4];
     b->n_aligned_bases = *aligned_bases;
+    if (ic->sc) {
+        b->cb = (const int32_t*)g->cb.p;
+        b->umi = (const uint32_t*)g->umi.p;
+    }
     rc = gi_maxend(g, b);
     g->t_write += raer::now_seconds() - t7;
     return rc;
@@ -1169,6 +1343,16 @@ static int gi_maxend(raer_gi* g, raer_read_batch* b) {
     GCK(cudaStreamSynchronize(g->st));
     b->maxend = (const int32_t*)g->maxend.p;
     return RAER_OK;
+}
+
+// single cell: number of ids the UMI code can take (4^length of the UMIs seen so far), 0 without UMIs
+extern "C" uint32_t raer_gi_umi_space(raer_gi* g) {
+    if (!g->umi_len.p) return 0;
+    int len = 0;
+    cudaSetDevice(g->device);
+    if (cudaMemcpy(&len, g->umi_len.p, 4, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (len <= 0) return 0;
+    return len >= 15 ? (1u << 30) : (1u << (2 * len));
 }
 
 extern "C" void raer_trim_device_cache(int32_t device) {

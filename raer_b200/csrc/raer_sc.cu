@@ -540,6 +540,42 @@ extern "C" int raer_sc_batch_host(raer_sc_ctx* c, const raer_sc_conf* conf, cons
     return RAER_OK;
 }
 
+// the same for a batch that already lives in device memory (device ingest): only the sites are uploaded
+extern "C" int raer_sc_batch_device_cells(raer_sc_ctx* c, const raer_sc_conf* conf, const raer_read_batch* db, raer_sc_cells* out) {
+    cudaSetDevice(c->device);
+    memset(out, 0, sizeof(*out));
+    raer_read_batch none;
+    memset(&none, 0, sizeof(none));
+    raer_read_batch dummy;
+    int rc = sc_upload(c, conf, &none, &dummy);  // sites only: the empty batch uploads nothing else
+    if (rc) return rc;
+    rc = sc_device(c, conf, db, (const int32_t*)c->spos.p, (const uint8_t*)c->sstr.p, (const uint8_t*)c->sref.p,
+                   (const uint8_t*)c->salt.p);
+    if (rc) return rc;
+    const size_t n = (size_t)c->n_cells, ns = (size_t)conf->n_sites;
+    out->n = (int64_t)n;
+    out->n_sites = (int64_t)ns;
+    out->cells = (int32_t*)malloc((n ? n : 1) * 16);
+    out->site_totals = (int32_t*)calloc(ns ? ns : 1, 8);
+    if (!out->cells || !out->site_totals) { raer_sc_cells_free(out); set_error("out of memory"); return RAER_ERR; }
+    if (n) SCK(cudaMemcpyAsync(out->cells, c->cells.p, n * 16, cudaMemcpyDeviceToHost, c->st));
+    if (ns && c->n_tuples > 0) SCK(cudaMemcpyAsync(out->site_totals, c->tot.p, ns * 8, cudaMemcpyDeviceToHost, c->st));
+    SCK(cudaStreamSynchronize(c->st));
+    return RAER_OK;
+}
+
+struct raer_gi;
+extern "C" raer_gi* raer_gi_create(int device, int nf, const char* const* paths, const char* const* indexes);
+extern "C" void raer_gi_destroy(raer_gi* g);
+extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_len, const raer::IngestConf* ic,
+                              const raer::RegionIndex::Chr* site, raer_read_batch* b, int64_t* file_off, const uint32_t** site_mask_dev,
+                              int64_t* aligned_bases);
+extern "C" uint32_t raer_gi_umi_space(raer_gi* g);
+
+static int64_t g_sc_last_device_contigs = 0;
+// contigs the last raer_scpileup() / raer_scpileup_triplets() call of this process took through the device ingest
+extern "C" int64_t raer_sc_last_device_contigs(void) { return g_sc_last_device_contigs; }
+
 // One engine behind both entry points: text files (the reference's contract), triplets in memory, or both.
 static int sc_run(const raer_scpileup_args* a, bool want_files, raer_sc_triplets* trip_out) {
     // check_sc_plp_args, src/sc-plp.c:874-940
@@ -615,6 +651,7 @@ static int sc_run(const raer_scpileup_args* a, bool want_files, raer_sc_triplets
     conf.n_barcodes = a->n_barcodes;
 
     int rc = RAER_OK;
+    int64_t n_device_contigs = 0;
     for (int bi = 0; bi < (is_ss2 ? a->nbam : 1) && rc == RAER_OK; ++bi) {
         raer::IngestConf ic;
         ic.n_files = 1;
@@ -639,6 +676,38 @@ static int sc_run(const raer_scpileup_args* a, bool want_files, raer_sc_triplets
         }
         const char* one_bam[1] = {a->bampaths[bi]};
         const char* one_idx[1] = {a->indexes ? a->indexes[bi] : nullptr};
+        // the sites of a contig as the arrays the kernels take
+        std::vector<int32_t> sp;
+        std::vector<uint8_t> ss, sr, sa;
+        auto contig_sites = [&](const std::string& name) -> const std::vector<int>* {
+            auto cit = by_chr.find(name);
+            const std::vector<int>* sites = cit == by_chr.end() ? nullptr : &cit->second;
+            const int ns = sites ? (int)sites->size() : 0;
+            sp.resize(ns); ss.resize(ns); sr.resize(ns); sa.resize(ns);
+            for (int k = 0; k < ns; ++k) {
+                const int s = (*sites)[k];
+                sp[k] = a->site_pos[s] - 1;
+                ss[k] = (uint8_t)a->site_strand[s];
+                sr[k] = (uint8_t)a->site_ref[s][0];
+                sa[k] = (uint8_t)a->site_alt[s][0];
+            }
+            conf.n_sites = ns;
+            conf.site_pos = sp.data(); conf.site_strand = ss.data(); conf.site_ref = sr.data(); conf.site_alt = sa.data();
+            return sites;
+        };
+        // site rule, src/sc-plp.c:586-596; the cells arrive sorted by (site, barcode)
+        auto emit_cells = [&](const std::vector<int>* sites, const raer_sc_cells& cells) {
+            for (int64_t i = 0; i < cells.n; ++i) {
+                const int32_t* t = cells.cells + 4 * i;
+                const int32_t* tt = cells.site_totals + 2 * t[0];
+                if (!(min_counts == 0 || (tt[0] + tt[1] >= min_counts && tt[1] >= min_var_reads))) continue;
+                if (fps.f[0]) fprintf(fps.f[0], "%d %d %d %d\n", a->site_idx[(*sites)[t[0]]], t[1], t[2], t[3]);
+                if (trip_out) {
+                    mem_site.push_back(a->site_idx[(*sites)[t[0]]]); mem_cb.push_back(t[1]);
+                    mem_ref.push_back(t[2]); mem_alt.push_back(t[3]);
+                }
+            }
+        };
         // One pass over an opened ingest: its contigs, their sites, their batches.
         auto drain = [&](raer::Ingest& ing) -> int {
             int rc2 = RAER_OK;
@@ -646,20 +715,8 @@ static int sc_run(const raer_scpileup_args* a, bool want_files, raer_sc_triplets
             raer::PackedBatch pb;
             int tid;
             while (rc2 == RAER_OK && (tid = ing.next_contig()) >= 0) {
-                auto cit = by_chr.find(names[tid]);
-                const std::vector<int>* sites = cit == by_chr.end() ? nullptr : &cit->second;
-                const int ns = sites ? (int)sites->size() : 0;
-                std::vector<int32_t> sp(ns);
-                std::vector<uint8_t> ss(ns), sr(ns), sa(ns);
-                for (int k = 0; k < ns; ++k) {
-                    const int s = (*sites)[k];
-                    sp[k] = a->site_pos[s] - 1;
-                    ss[k] = (uint8_t)a->site_strand[s];
-                    sr[k] = (uint8_t)a->site_ref[s][0];
-                    sa[k] = (uint8_t)a->site_alt[s][0];
-                }
-                conf.n_sites = ns;
-                conf.site_pos = sp.data(); conf.site_strand = ss.data(); conf.site_ref = sr.data(); conf.site_alt = sa.data();
+                const std::vector<int>* sites = contig_sites(names[tid]);
+                const int ns = conf.n_sites;
                 while (rc2 == RAER_OK && ing.next_batch(pb)) {
                     const raer_read_batch& b = pb.b;
                     if (a->poll && a->poll(a->poll_ctx)) {  // the calling thread polls between batches (src/sc-plp.c:707-712)
@@ -671,17 +728,7 @@ static int sc_run(const raer_scpileup_args* a, bool want_files, raer_sc_triplets
                     raer_sc_cells cells;
                     rc2 = raer_sc_batch_host(c, &conf, &b, &cells);
                     if (rc2) break;
-                    // site rule, src/sc-plp.c:586-596; the cells arrive sorted by (site, barcode)
-                    for (int64_t i = 0; i < cells.n; ++i) {
-                        const int32_t* t = cells.cells + 4 * i;
-                        const int32_t* tt = cells.site_totals + 2 * t[0];
-                        if (!(min_counts == 0 || (tt[0] + tt[1] >= min_counts && tt[1] >= min_var_reads))) continue;
-                        if (fps.f[0]) fprintf(fps.f[0], "%d %d %d %d\n", a->site_idx[(*sites)[t[0]]], t[1], t[2], t[3]);
-                        if (trip_out) {
-                            mem_site.push_back(a->site_idx[(*sites)[t[0]]]); mem_cb.push_back(t[1]);
-                            mem_ref.push_back(t[2]); mem_alt.push_back(t[3]);
-                        }
-                    }
+                    emit_cells(sites, cells);
                     raer_sc_cells_free(&cells);
                 }
             }
@@ -691,16 +738,75 @@ static int sc_run(const raer_scpileup_args* a, bool want_files, raer_sc_triplets
             }
             return rc2;
         };
-        if (!a->region && raer::indexes_usable(one_bam, one_idx, 1) && !getenv("RAER_SERIAL_INGEST")) {
+        // a region that is a plain contig name (the per-chromosome calls of R/sc-pileup.R:185-230) restricts the loop below;
+        // a coordinate range goes through the single stream
+        const bool whole_contig = a->region && !strchr(a->region, ':');
+        if ((!a->region || whole_contig) && raer::indexes_usable(one_bam, one_idx, 1) && !getenv("RAER_SERIAL_INGEST")) {
             // the sites are a list of positions: contig by contig through the BAI index, skipping what lies between them
             // (src/sc-plp.c:648-669 queries the index too)
             raer::BamStream hs;
             if (!hs.open(one_bam[0], 1, true)) { rc = RAER_ERR_IO; break; }
             const std::vector<std::string> names = hs.names();
+            const std::vector<int32_t> lens = hs.lengths();
+            // Device ingest (raer_gingest.cu): a contig whose sites are spread over most of it is inflated, parsed, filtered
+            // (cell-barcode whitelist included) and packed by kernels; the others, and whatever that path hands back,
+            // go through the host stream and the index.
+            bool use_gi = !(getenv("RAER_GPU_INGEST") && atoi(getenv("RAER_GPU_INGEST")) == 0) && !getenv("RAER_BATCH_READS");
+            if (use_gi) {
+                static const unsigned char eof_blk[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43,
+                                                          0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                unsigned char tail[28];
+                FILE* fp = fopen(one_bam[0], "rb");
+                use_gi = fp && fseek(fp, -28, SEEK_END) == 0 && fread(tail, 1, 28, fp) == 28 && memcmp(tail, eof_blk, 28) == 0;
+                if (fp) fclose(fp);
+            }
+            struct GiHolder {
+                raer_gi* g = nullptr;
+                ~GiHolder() { if (g) raer_gi_destroy(g); }
+            } gh;
+            if (use_gi) {
+                gh.g = raer_gi_create(a->device, 1, one_bam, one_idx);
+                if (!gh.g) { rc = RAER_ERR_IO; break; }
+            }
+            if (whole_contig && std::find(names.begin(), names.end(), std::string(a->region)) == names.end()) {
+                set_error("fail to parse region '%s'", a->region);
+                rc = RAER_ERR_IO;
+                break;
+            }
             for (size_t ci = 0; ci < names.size() && rc == RAER_OK; ++ci) {
+                if (whole_contig && names[ci] != a->region) continue;
                 const raer::RegionIndex::Chr* rchr = ridx.find(names[ci]);
                 if (!rchr) continue;
                 const std::vector<std::pair<int32_t, int32_t>> jl = raer::jump_intervals(rchr);
+                bool on_device = use_gi;
+                if (on_device) {
+                    int64_t covered = 0;
+                    for (const auto& iv : jl) covered += (int64_t)iv.second - iv.first;
+                    on_device = covered * 2 >= (int64_t)lens[ci];
+                }
+                if (on_device) {
+                    if (a->poll && a->poll(a->poll_ctx)) { set_error("interrupted"); rc = RAER_ERR_INTERRUPT; break; }
+                    raer_read_batch b;
+                    int64_t file_off[2] = {0, 0}, bases = 0;
+                    const uint32_t* d_sites = nullptr;
+                    const int ftid = (int)ci;
+                    const int r = raer_gi_contig(gh.g, (int)ci, &ftid, lens[ci], &ic, rchr, &b, file_off, &d_sites, &bases);
+                    if (r < 0) { rc = r; break; }
+                    if (r == 0) {
+                        const std::vector<int>* sites = contig_sites(names[ci]);
+                        if (conf.n_sites && b.n_reads > 0) {
+                            conf.n_umi = raer_gi_umi_space(gh.g);
+                            raer_sc_cells cells;
+                            rc = raer_sc_batch_device_cells(c, &conf, &b, &cells);
+                            if (rc) break;
+                            emit_cells(sites, cells);
+                            raer_sc_cells_free(&cells);
+                        }
+                        ++n_device_contigs;
+                        continue;
+                    }
+                    // r == 1: handed back (depth within reach of max_depth, UMIs the 2-bit code does not cover, ...)
+                }
                 raer::Ingest ing(ic);
                 if (!ing.open(one_bam, one_idx, a->host_threads, names[ci].c_str(), &jl)) { rc = RAER_ERR_IO; break; }
                 rc = drain(ing);
@@ -712,6 +818,8 @@ static int sc_run(const raer_scpileup_args* a, bool want_files, raer_sc_triplets
         }
     }
     if (rc != RAER_OK) return rc < 0 ? rc : RAER_ERR;
+    if (getenv("RAER_TIMING")) fprintf(stderr, "[raer_scpileup] %lld contig(s) through the device ingest\n", (long long)n_device_contigs);
+    g_sc_last_device_contigs = n_device_contigs;
     if (trip_out) {
         const size_t n = mem_site.size();
         trip_out->n = (int64_t)n;

@@ -275,3 +275,46 @@ def test_device_ingest_unsorted_input_fails(ext, tmp_path, monkeypatch):
     half = len(first) // 2
     bamtools.write_bam(p, hdr, refs, first[:half] + second + first[half:] + rest)
     _device_call_fails(p, ext.fasta, monkeypatch, "not sorted")
+
+
+# ---- single cell: screadaln on the device (cell-barcode whitelist, UMI codes)
+def _sc_triplets(sce):
+    o = np.lexsort((sce.col, sce.row))
+    return (sce.shape, list(sce.barcodes), sce.row[o].tolist(), sce.col[o].tolist(), sce.nRef[o].tolist(), sce.nAlt[o].tolist())
+
+
+@pytest.mark.parametrize("umi_tag", ["UB", None])
+def test_single_cell_device_ingest_matches_host_ingest(tmp_path, monkeypatch, umi_tag):
+    from raer_b200 import api
+
+    ds = synth.make_sc_dataset(str(tmp_path / "sc"))
+    gr = Sites(**ds["sites"])
+    fp = FilterParam(library_type="fr-second-strand", min_depth=0)
+    monkeypatch.setenv("RAER_GPU_INGEST", "1")
+    dev = api.pileup_cells_triplets(ds["bam"], gr, ds["barcodes"], umi_tag=umi_tag, param=fp)
+    assert _cabi.sc_last_device_contigs() >= 1
+    monkeypatch.setenv("RAER_GPU_INGEST", "0")
+    host = api.pileup_cells_triplets(ds["bam"], gr, ds["barcodes"], umi_tag=umi_tag, param=fp)
+    assert _cabi.sc_last_device_contigs() == 0
+    assert _sc_triplets(dev) == _sc_triplets(host)
+    assert sum(_sc_triplets(dev)[4]) > 1000
+
+
+def test_single_cell_device_ingest_on_the_bundled_10x_bam(ext, monkeypatch):
+    """the reference's own 10x example (known answers in test_sc_synth_parity / the golden suite): sparse sites there, so
+    the site list is widened until the contig qualifies for the device ingest"""
+    from raer_b200 import api
+
+    _, refs, recs = bamtools.read_bam(ext.scbam)
+    cbs = list(dict.fromkeys(r.tag_z("CB") for r in recs if r.tag_z("CB") is not None))
+    length = dict(refs)["2"]
+    pos = sorted(set([579, 589, 601, 625, 645] + list(range(1, length, 997))))
+    gr = Sites(["2"] * len(pos), pos, strand=["-"] * len(pos), ref=["A"] * len(pos), alt=["G"] * len(pos))
+    fp = FilterParam(library_type="fr-second-strand", min_depth=0)
+    monkeypatch.setenv("RAER_GPU_INGEST", "1")
+    dev = api.pileup_cells_triplets(ext.scbam, gr, cbs, param=fp)
+    assert _cabi.sc_last_device_contigs() == 1
+    monkeypatch.setenv("RAER_GPU_INGEST", "0")
+    host = api.pileup_cells_triplets(ext.scbam, gr, cbs, param=fp)
+    assert _sc_triplets(dev) == _sc_triplets(host)
+    assert sum(_sc_triplets(dev)[4]) > 100
