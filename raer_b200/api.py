@@ -292,11 +292,80 @@ def _sites_minus_snps(alu: Sites, snp_db: Optional[Sites], chroms) -> Sites:
     return Sites(names, starts, ends)
 
 
-def _calc_aei_fused(fused_call, bamfiles, fasta, alu_ranges, snp_db, param, indexes):
-    """Stranded libraries: one device call per BAM returns the 4 x 4 (REF of the row, counted base) sums of the rows
-    pileup_sites() would have produced inside alu_ranges minus the SNP positions (raer_pileup_args.aei_mode)."""
+def _merge_intervals(iv):
+    """sorted, disjoint union of closed integer intervals"""
+    out = []
+    for a, b in sorted(iv):
+        if out and a <= out[-1][1] + 1:
+            out[-1][1] = max(out[-1][1], b)
+        else:
+            out.append([a, b])
+    return out
+
+
+def _subtract_intervals(xs, ys):
+    """xs minus ys (both sorted, disjoint, closed)"""
+    out, j = [], 0
+    for a, b in xs:
+        cur = a
+        while j < len(ys) and ys[j][1] < cur:
+            j += 1
+        k = j
+        while k < len(ys) and ys[k][0] <= b:
+            if ys[k][0] > cur:
+                out.append([cur, ys[k][0] - 1])
+            cur = max(cur, ys[k][1] + 1)
+            k += 1
+        if cur <= b:
+            out.append([cur, b])
+    return out
+
+
+def _intersect_intervals(xs, ys):
+    out, i, j = [], 0, 0
+    while i < len(xs) and j < len(ys):
+        a, b = max(xs[i][0], ys[j][0]), min(xs[i][1], ys[j][1])
+        if a <= b:
+            out.append([a, b])
+        if xs[i][1] < ys[j][1]:
+            i += 1
+        else:
+            j += 1
+    return out
+
+
+def _sites_by_gene_strand(sites: Sites, genes: Sites):
+    """correct_strand() as interval arithmetic (R/calc_AEI.R:239-272): a site takes the strand of the genes that overlap
+    it when they agree; sites under genes of both strands or under none are dropped. Returns (plus, minus)."""
+    from collections import defaultdict
+
+    by = {"+": defaultdict(list), "-": defaultdict(list)}
+    for sn, a, b, st in zip(genes.seqnames, genes.start, genes.end, genes.strand):
+        if st in by:
+            by[st][sn].append((int(a), int(b)))
+    per_chr = defaultdict(list)
+    for sn, a, b in zip(sites.seqnames, sites.start, sites.end):
+        per_chr[sn].append((int(a), int(b)))
+    out = {"+": ([], [], []), "-": ([], [], [])}
+    for sn in dict.fromkeys(sites.seqnames):
+        mine = _merge_intervals(per_chr[sn])
+        up, um = _merge_intervals(by["+"][sn]), _merge_intervals(by["-"][sn])
+        for st, only in (("+", _subtract_intervals(up, um)), ("-", _subtract_intervals(um, up))):
+            for a, b in _intersect_intervals(mine, only):
+                out[st][0].append(sn); out[st][1].append(a); out[st][2].append(b)
+    return Sites(*out["+"]), Sites(*out["-"])
+
+
+def _calc_aei_fused(fused_call, bamfiles, fasta, alu_ranges, snp_db, param, indexes, txdb_genes=None):
+    """One device call per BAM returns the 4 x 4 (REF of the row, counted base) sums of the rows pileup_sites() would have
+    produced inside alu_ranges minus the SNP positions (raer_pileup_args.aei_mode). Unstranded libraries: every row is
+    on '+', and correct_strand() complements the rows that lie under minus-strand genes; here the site intervals are split
+    by gene strand up front, the reduction runs once per class, and the minus class is complemented as a matrix."""
+    import numpy as np
+
     aei, per = {}, {}
     idx = {"A": 0, "C": 1, "G": 2, "T": 3}
+    unstranded = param.library_type[0] == "unstranded"
     for bi, bam in enumerate(bamfiles):
         chroms, _, _ = glue.setup_valid_regions(bam, None, None, fasta)
         alu_chroms = set(alu_ranges.seqnames)
@@ -304,10 +373,20 @@ def _calc_aei_fused(fused_call, bamfiles, fasta, alu_ranges, snp_db, param, inde
         sites = _sites_minus_snps(alu_ranges, snp_db, chroms)
         name = os.path.basename(bam)
         tot = {p: (0, 0) for p in _AEI_PAIRS}
+        ix = None if indexes is None else [indexes[bi]]
+
+        def reduce(st_sites):
+            if len(st_sites) == 0:
+                return np.zeros((4, 4), dtype=np.int64)
+            pc = glue.prepare_pileup_call([bam], fasta, st_sites, None, None, param, None, ix)
+            return np.asarray(fused_call(pc)["aei"][0], dtype=np.int64)
+
         if len(sites) > 0:
-            ix = None if indexes is None else [indexes[bi]]
-            pc = glue.prepare_pileup_call([bam], fasta, sites, None, None, param, None, ix)
-            m = fused_call(pc)["aei"][0]
+            if unstranded:
+                plus, minus = _sites_by_gene_strand(sites, txdb_genes)
+                m = reduce(plus) + reduce(minus)[::-1, ::-1]  # A C G T reversed = T G C A: the complement of both axes
+            else:
+                m = reduce(sites)
             tot = {(r, a): (int(m[idx[r], idx[a]]), int(m[idx[r], idx[r]])) for r, a in _AEI_PAIRS}
         aei[name] = {f"{r}_{a}": (100.0 * alt / (alt + ref) if alt + ref > 0 else float("nan")) for (r, a), (alt, ref) in tot.items()}
         per[name] = {f"{r}_{a}": v for (r, a), v in tot.items()}
@@ -331,8 +410,8 @@ def _calc_aei_impl(call, bamfiles, fasta, alu_ranges: Optional[Sites] = None, tx
     unstranded = param.library_type[0] == "unstranded"
     if unstranded and txdb_genes is None:
         raise ValueError("txdb required for processing unstranded data")
-    if fused_call is not None and not unstranded:
-        return _calc_aei_fused(fused_call, bamfiles, fasta, alu_ranges, snp_db, param, indexes)
+    if fused_call is not None:
+        return _calc_aei_fused(fused_call, bamfiles, fasta, alu_ranges, snp_db, param, indexes, txdb_genes)
     snp_keys = None
     if snp_db is not None:
         snp_keys = set(zip(snp_db.seqnames, snp_db.start))
@@ -394,7 +473,7 @@ def calc_AEI(bamfiles, fasta, alu_ranges=None, txdb=None, snp_db=None, param=Non
     """Mirror of ``calc_AEI()`` (R/calc_AEI.R:68)."""
     from . import _cabi
 
-    # stranded libraries take the fused device reduction (SURVEY.md section 8f-2); unstranded ones need the gene
-    # annotation per site and go through the rows like the reference
+    # the fused device reduction (SURVEY.md section 8f-2); for unstranded libraries the site intervals are split by the
+    # strand of the overlapping genes first (correct_strand) and the minus class is complemented as a matrix
     return _calc_aei_impl(_cabi.pileup, bamfiles, fasta, alu_ranges, txdb, snp_db, param, indexes,
                           fused_call=lambda pc: _cabi.pileup(pc, aei=True))

@@ -112,3 +112,34 @@ def test_fused_device_reduction_equals_row_based_calc_aei(tmp_path, kw):
     want = oracle_backend.calc_AEI(ds["bams"], ds["fasta"], alu, snp_db=snps, param=fp)
     assert fused["AEI_per_chrom"] == rows["AEI_per_chrom"] == want["AEI_per_chrom"]
     assert sum(a + r for v in fused["AEI_per_chrom"].values() for a, r in v.values()) > 10_000
+
+
+@pytest.mark.gpu
+def test_fused_reduction_for_unstranded_libraries(tmp_path):
+    """correct_strand() as interval arithmetic in front of the device reduction: genes of both strands, overlapping
+    each other in places (those sites are dropped), sites outside every gene (dropped), a SNP list"""
+    import numpy as np
+
+    from raer_b200 import _cabi, api, synth
+
+    ds = synth.make_bulk_dataset(str(tmp_path), n_bams=1, n_contigs=2, contig_len=60_000, pairs_per_contig=8000, seed=37)
+    rng = np.random.default_rng(5)
+    names, starts, ends = [], [], []
+    for c in ds["names"]:
+        for s in sorted(rng.choice(59_000, size=50, replace=False)):
+            names.append(c); starts.append(int(s) + 1); ends.append(int(s) + int(rng.integers(100, 400)))
+    alu = Sites(names, starts, ends)
+    gn, gs, ge, gst = [], [], [], []
+    for c in ds["names"]:
+        for k in range(12):
+            a = int(rng.integers(1, 55_000))
+            gn.append(c); gs.append(a); ge.append(a + int(rng.integers(2_000, 9_000))); gst.append("+-"[k % 2])
+    genes = Sites(gn, gs, ge, strand=gst)
+    snp_pos = sorted(set(int(x) for x in rng.choice(60_000, size=2000, replace=False)))
+    snps = Sites([ds["names"][0]] * len(snp_pos), [p + 1 for p in snp_pos])
+    fp = FilterParam(library_type="unstranded")
+    fused = api.calc_AEI(ds["bams"], ds["fasta"], alu, genes, snp_db=snps, param=fp)
+    rows = api._calc_aei_impl(_cabi.pileup, ds["bams"], ds["fasta"], alu, genes, snps, fp)
+    want = oracle_backend.calc_AEI(ds["bams"], ds["fasta"], alu, genes, snp_db=snps, param=fp)
+    assert fused["AEI_per_chrom"] == rows["AEI_per_chrom"] == want["AEI_per_chrom"]
+    assert sum(a + r for v in fused["AEI_per_chrom"].values() for a, r in v.values()) > 5_000
