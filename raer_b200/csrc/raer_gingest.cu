@@ -673,6 +673,7 @@ struct raer_gi {
     int device = 0;
     cudaStream_t st = nullptr;
     int nf = 0;
+    int n_sm = 148;
     uint32_t check_crc = 1;  // RAER_SKIP_CRC=1 turns the CRC-32 check of the inflated blocks off, as in the host ingest
     std::vector<GiReader> readers;
     std::vector<FILE*> fp;
@@ -762,6 +763,16 @@ extern "C" raer_gi* raer_gi_create(int device, int nf, const char* const* paths,
         return nullptr;
     }
     if (getenv("RAER_SKIP_CRC")) g->check_crc = 0;
+    {   // per device: SM count, and the opt-in for the inflate kernel's shared memory
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) g->n_sm = v;
+        if (cudaFuncSetAttribute(k_gi_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM_BYTES) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("the device does not offer %d bytes of shared memory per block", (int)GI_SMEM_BYTES);
+            delete g;
+            return nullptr;
+        }
+    }
     int n_readers = 4;
     if (const char* e = getenv("RAER_GI_READERS")) n_readers = std::max(1, std::min(16, atoi(e)));
     g->readers.resize((size_t)n_readers);
@@ -924,12 +935,7 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
             for (auto& t : th) if (t.joinable()) t.join();
         }
     };
-    static int n_sm = 0;
-    if (!n_sm) {
-        cudaDeviceProp prop;
-        n_sm = cudaGetDeviceProperties(&prop, g->device) == cudaSuccess ? prop.multiProcessorCount : 148;
-        cudaFuncSetAttribute(k_gi_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM_BYTES);
-    }
+    const int n_sm = g->n_sm;
     // b_lo .. b_hi: entries already staged in S.hblk (or, beyond its capacity, passed in `extra`)
     int n_launch = 0;
     auto launch_inflate = [&](size_t b_lo, size_t b_hi, const GiBlock* extra) -> int {

@@ -1,5 +1,5 @@
 """Randomised CUDA-vs-oracle parity sweep (development aid): random synthetic datasets and random FilterParam
-combinations, both tile kernels. usage: python tools/fuzz_parity.py [n_rounds] [seed0]"""
+combinations, all three tile kernels, device and host ingest. usage: python tools/fuzz_parity.py [n_rounds] [seed0]"""
 import os
 import random
 import sys
@@ -46,6 +46,10 @@ def random_param(rng, n_bams):
         kw["remove_overlaps"] = False
     if rng.random() < 0.2:
         kw["min_variant_reads"] = 2
+    if rng.random() < 0.15:
+        kw["max_depth"] = rng.choice([8, 40, 200])  # within reach of the coverage: the device ingest hands the contig back
+    if rng.random() < 0.15:
+        kw["read_bqual"] = (rng.choice([0.1, 0.3]), float(rng.choice([15, 25])))
     return kw
 
 
@@ -64,11 +68,13 @@ def main():
                 kw = random_param(rng, n_bams)
                 fp = FilterParam(**kw)
                 want = oracle_backend.pileup_sites(ds["bams"], ds["fasta"], param=fp)
-                for kern in ("default", "generic"):
-                    if kern == "generic":
-                        os.environ["RAER_KERNEL"] = "generic"
-                    else:
-                        os.environ.pop("RAER_KERNEL", None)
+                for kern in ("default", "fast", "generic", "host-ingest"):
+                    os.environ.pop("RAER_KERNEL", None)
+                    os.environ.pop("RAER_GPU_INGEST", None)
+                    if kern in ("fast", "generic"):
+                        os.environ["RAER_KERNEL"] = kern
+                    if kern == "host-ingest":
+                        os.environ["RAER_GPU_INGEST"] = "0"
                     try:
                         got = api.pileup_sites(ds["bams"], ds["fasta"], param=fp)
                         _assert_same(got, want)
@@ -76,6 +82,7 @@ def main():
                         bad += 1
                         print(f"FAIL round {rnd} bams {n_bams} len {clen} pairs {pairs} kernel {kern} param {kw}: {str(e)[:300]}")
                 os.environ.pop("RAER_KERNEL", None)
+                os.environ.pop("RAER_GPU_INGEST", None)
                 print(f"round {rnd}.{k}: {len(want)} rows, {n_bams} BAMs, {kw}")
     print("failures:", bad)
     return 1 if bad else 0
