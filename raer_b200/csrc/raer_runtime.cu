@@ -77,18 +77,22 @@ extern "C" void raer_pinned_free(void* p, int pinned) {
 }
 
 // ------------------------------------------------------------------------------------- context
+// Device buffers of a context come from the device's stream-ordered memory pool, on the context's stream: growing one
+// does not synchronise the device, and what a call frees is still there for the next call of the process (cudaMalloc /
+// cudaFree cost between 5 and 270 ms per raer_pileup() call, depending on what else the process had allocated).
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    cudaStream_t st = nullptr;
     int ensure(size_t n) {
         if (n <= cap) return 0;
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, st);
         size_t want = n + n / 4 + 256;
-        if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; cap = 0; set_error("cudaMalloc(%zu) failed", want); return RAER_ERR_CUDA; }
+        if (cudaMallocAsync(&p, want, st) != cudaSuccess) { p = nullptr; cap = 0; cudaGetLastError(); set_error("cudaMallocAsync(%zu) failed", want); return RAER_ERR_CUDA; }
         cap = want;
         return 0;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) cudaFreeAsync(p, st); p = nullptr; cap = 0; }
 };
 
 struct raer_ctx {
@@ -126,16 +130,35 @@ struct raer_ctx {
     size_t pev_used = 0;
 };
 
+static std::vector<DevBuf*> ctx_bufs(raer_ctx* c) {
+    return {&c->hdr, &c->maxend, &c->cigar, &c->seq, &c->qual, &c->pair_b, &c->mask, &c->phase_clk, &c->aei, &c->umi_holes,
+            &c->ov_scratch, &c->tile_idx, &c->tile_list, &c->tile_first, &c->pmask_own, &c->pmask_cin, &c->tile_ranges,
+            &c->tile_rows, &c->small, &c->row_pos, &c->row_meta, &c->row_stats, &c->row_counts, &c->row_alt, &c->ref};
+}
+
 extern "C" raer_ctx* raer_ctx_create(int32_t device) {
     int n = raer_device_count();
     if (n <= 0 || device >= n) { set_error("no usable CUDA device (the product has no CPU path)"); return nullptr; }
     if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
     raer_ctx* c = new raer_ctx();
     c->device = device;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->n_sm = prop.multiProcessorCount;
+    {   // (cudaGetDeviceProperties takes tens of milliseconds: one attribute is all that is needed)
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->n_sm = v;
+    }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; set_error("stream"); return nullptr; }
     for (auto& e : c->ev) cudaEventCreate(&e);
+    for (DevBuf* b : ctx_bufs(c)) b->st = c->stream;
+    {   // keep up to 8 GB of freed buffers in the pool for the next call (raer_trim_device_cache() returns them)
+        cudaMemPool_t pool;
+        unsigned long long keep = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess && keep < (8ull << 30)) {
+            keep = 8ull << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     return c;
 }
 extern "C" void raer_ctx_destroy(raer_ctx* c) {
@@ -154,9 +177,8 @@ extern "C" void raer_ctx_destroy(raer_ctx* c) {
         }
     }
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->hdr, &c->maxend, &c->cigar, &c->seq, &c->qual, &c->pair_b, &c->mask, &c->tile_ranges, &c->tile_rows, &c->tile_idx, &c->tile_list, &c->tile_first, &c->pmask_own, &c->pmask_cin, &c->ov_scratch, &c->umi_holes, &c->aei,
-                      &c->small, &c->row_pos, &c->row_meta, &c->row_stats, &c->row_counts, &c->row_alt, &c->ref})
-        b->release();
+    for (DevBuf* b : ctx_bufs(c)) b->release();
+    cudaStreamSynchronize(c->stream);
     for (auto& e : c->ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
