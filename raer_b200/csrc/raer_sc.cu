@@ -259,18 +259,19 @@ extern "C" int raer_launch_overlap(const raer_read_hdr* hdr, const uint32_t* cig
                                    const int32_t* pair_b, long long n_pairs, int mode, cudaStream_t st, int* scratch);
 extern "C" int raer_device_count(void);
 
-struct DBuf {
+struct DBuf {  // stream-ordered pool allocation on the owning context's stream (see DevBuf in raer_runtime.cu)
     void* p = nullptr;
     size_t cap = 0;
+    cudaStream_t st = nullptr;
     int ensure(size_t n) {
         if (n <= cap && p) return 0;
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, st);
         size_t want = n + n / 4 + 256;
-        if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; cap = 0; set_error("cudaMalloc(%zu) failed", want); return RAER_ERR_CUDA; }
+        if (cudaMallocAsync(&p, want, st) != cudaSuccess) { p = nullptr; cap = 0; cudaGetLastError(); set_error("cudaMallocAsync(%zu) failed", want); return RAER_ERR_CUDA; }
         cap = want;
         return 0;
     }
-    ~DBuf() { if (p) cudaFree(p); }
+    void release() { if (p) cudaFreeAsync(p, st); p = nullptr; cap = 0; }
 };
 
 static int bits_for(unsigned long long maxval) {
@@ -296,10 +297,15 @@ struct raer_sc_ctx {
     std::vector<int> ev_class;
     size_t ev_used = 0;
     unsigned long long* h_small = nullptr;  // pinned: tuple counter | cell counter
+    std::vector<DBuf*> bufs() {
+        return {&hdr, &cigar, &seq, &qual, &pair, &cb, &umi, &spos, &sstr, &sref, &salt, &small, &keys, &vals, &keys2, &vals2, &hist,
+                &vote, &flag, &cnt, &bsum, &cells, &tot, &ov};
+    }
     ~raer_sc_ctx() {
+        for (DBuf* b : bufs()) b->release();
         for (auto e : ev) cudaEventDestroy(e);
         if (h_small) cudaFreeHost(h_small);
-        if (st) cudaStreamDestroy(st);
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     }
 };
 
@@ -315,6 +321,7 @@ extern "C" raer_sc_ctx* raer_sc_ctx_create(int32_t device) {
         set_error("stream / pinned memory");
         return nullptr;
     }
+    for (DBuf* b : c->bufs()) b->st = c->st;
     return c;
 }
 extern "C" void raer_sc_ctx_destroy(raer_sc_ctx* c) {
