@@ -390,82 +390,52 @@ __device__ __forceinline__ uint32_t wang_hash(uint32_t key) {
     return key;
 }
 
-struct GpOut {  // the batch arrays (device), this file's first read / CIGAR word / sequence byte
-    raer_read_hdr* hdr;
-    uint32_t* cigar;
-    uint8_t* seq;
-    uint8_t* qual;
-    int32_t* cb;     // single cell: whitelist column / UMI code of every read
-    uint32_t* umi;
-    long long r0, c0, s0;
+// Per kept read of a file (index K = arrival order among the kept reads): what the later stages need without going back
+// to the record table. A contig is handed to the pileup kernels in position windows (each window is one read batch with
+// 32-bit offsets); everything that depends on the order of the stream -- which reads are kept, who pairs with whom --
+// is decided here, once, over the whole contig.
+struct GpMeta {
+    recoff_t* krec;     // record offset in the inflated buffer
+    int32_t* kprev;     // position of the read pushed before it (overlap_push: when does an entry die)
+    int32_t* kpos;
+    int32_t* kend;
+    uint32_t* kcoff;    // exclusive sums of CIGAR words / packed sequence bytes (one extra element: the totals)
+    uint32_t* ksoff;
+    int32_t* kcb;       // single cell: whitelist column, UMI code
+    uint32_t* kumi;
+    int32_t* mateK;     // K of the earlier mate this read resolves an overlap with, or -1
+    int32_t* keepend;   // a read stays in the windows until this position: its own end or that of the mate paired with it
+    uint8_t* keepA;     // the earlier mate keeps its qualities (htslib >= 1.13 coin)
 };
 
-// one thread per kept record: header, CIGAR words, packed sequence, qualities; read-name hash of the reads that take
-// part in the mate-overlap pairing
-__global__ void k_gp_write(const uint8_t* __restrict__ ub, const recoff_t* __restrict__ rec_off, const uint32_t* __restrict__ kept,
-                           const uint32_t* __restrict__ kidx, const uint32_t* __restrict__ coff, const uint32_t* __restrict__ soff,
-                           const uint32_t* __restrict__ elig, const uint32_t* __restrict__ eidx, const int32_t* __restrict__ r_end,
-                           const int32_t* __restrict__ prevpos, long long n_rec, GpConf C, GpOut O,
-                           unsigned long long* __restrict__ pkey, uint32_t* __restrict__ pval, recoff_t* __restrict__ krec,
-                           int32_t* __restrict__ kprev, const int32_t* __restrict__ rec_cb, int* flags) {
+__global__ void k_gp_meta(const uint8_t* __restrict__ ub, const recoff_t* __restrict__ rec_off, const uint32_t* __restrict__ kept,
+                          const uint32_t* __restrict__ kidx, const uint32_t* __restrict__ coff, const uint32_t* __restrict__ soff,
+                          const uint32_t* __restrict__ elig, const uint32_t* __restrict__ eidx, const int32_t* __restrict__ r_pos,
+                          const int32_t* __restrict__ r_end, const int32_t* __restrict__ prevpos, long long n_rec, GpConf C, GpMeta M,
+                          unsigned long long* __restrict__ pkey, uint32_t* __restrict__ pval, const int32_t* __restrict__ rec_cb,
+                          int* flags) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n_rec || !kept[i]) return;
     const uint8_t* p = ub + rec_off[i] + 4;
-    const int pos = (int)ld32u(p + 4);
-    const int l_qname = p[8], mapq = p[9];
-    const int n_cigar = (int)ld16u(p + 12), flag = (int)ld16u(p + 14);
-    const int l_qseq = (int)ld32u(p + 16);
-    const uint8_t* cg = p + 32 + l_qname;
-    const uint8_t* sq = cg + 4 * n_cigar;
-    const uint8_t* ql = sq + ((l_qseq + 1) >> 1);
     const uint32_t K = kidx[i];
-    int bits = 0;
-    {  // invert_read_orientation (src/plp_utils.c:331-371)
-        const int lt = C.libtype, rev = (flag & 16) != 0;
-        int inv = 0;
-        if (lt == 1 || lt == 2) {
-            int r1 = -1;
-            if (!(flag & 1)) r1 = 1;
-            else if (flag & 64) r1 = 1;
-            else if (flag & 128) r1 = 0;
-            if (r1 >= 0) {
-                const int when_rev = (lt == 2);
-                inv = r1 ? (rev == when_rev) : (rev != when_rev);
-            }
-        }
-        if (inv) bits |= RAER_RB_INVERT;
-    }
-    if (C.min_overhang && l_qseq >= 2 && (sq[0] & 0xf) == 3) bits |= RAER_RB_OHANG_N;
-    raer_read_hdr h;
-    h.pos = pos;
-    h.end = r_end[i];
-    h.flag = (uint16_t)flag;
-    h.mapq = (uint8_t)mapq;
-    h.bits = (uint8_t)bits;
-    h.l_qseq = (uint16_t)l_qseq;
-    h.n_cigar = (uint16_t)n_cigar;
-    h.cigar_off = (uint32_t)(O.c0 + coff[i]);
-    h.sq_off = (uint32_t)(O.s0 + soff[i]);
-    h.mate = -1;
-    h.aux = (uint32_t)(O.r0 + K);  // its own batch index, like the host packer (bulk UMI mode never comes here)
-    O.hdr[O.r0 + K] = h;
-    uint32_t* co = O.cigar + O.c0 + coff[i];
-    for (int k = 0; k < n_cigar; ++k) co[k] = ld32u(cg + 4 * k);
-    const int nsb = (l_qseq + 1) >> 1, padded = (nsb + 3) & ~3;
-    uint8_t* so = O.seq + O.s0 + soff[i];
-    for (int k = 0; k < nsb; ++k) so[k] = sq[k];
-    for (int k = nsb; k < padded; ++k) so[k] = 0xff;
-    uint8_t* qo = O.qual + 2 * (O.s0 + soff[i]);
-    for (int k = 0; k < l_qseq; ++k) qo[k] = ql[k];
-    for (int k = l_qseq; k < 2 * padded; ++k) qo[k] = 0;
+    M.krec[K] = rec_off[i];
+    M.kprev[K] = prevpos[i];
+    M.kpos[K] = r_pos[i];
+    M.kend[K] = r_end[i];
+    M.kcoff[K] = coff[i];
+    M.ksoff[K] = soff[i];
+    M.mateK[K] = -1;
+    M.keepend[K] = r_end[i];
+    M.keepA[K] = 0;
     if (C.sc) {
-        O.cb[O.r0 + K] = rec_cb[i];
+        M.kcb[K] = rec_cb[i];
         uint32_t code = 0;
         if (C.has_umi_tag) {
             // The host keeps a dictionary string -> id; all the kernels need is that equal UMIs get equal ids. UMIs are
             // short runs of ACGT of one length: 2 bits per base + 1 is such an id without a dictionary. Anything else
             // (other letters, more than 15 bases, mixed lengths) sends the contig to the host.
-            const uint8_t* aux = ql + l_qseq;
+            const int l_qname = p[8], n_cigar = (int)ld16u(p + 12), l_qseq = (int)ld32u(p + 16);
+            const uint8_t* aux = p + 32 + l_qname + 4 * n_cigar + ((l_qseq + 1) >> 1) + l_qseq;
             const uint8_t* v = gp_aux_find(aux, p + ld32u(p - 4), C.umi_tag[0], C.umi_tag[1]);
             if (v && (*v == 'Z' || *v == 'H')) {
                 uint32_t x = 0;
@@ -484,10 +454,8 @@ __global__ void k_gp_write(const uint8_t* __restrict__ ub, const recoff_t* __res
                 code = x + 1u;
             }
         }
-        O.umi[O.r0 + K] = code;
+        M.kumi[K] = code;
     }
-    krec[K] = rec_off[i];
-    kprev[K] = prevpos[i];
     if (elig[i]) {
         // 64-bit FNV-1a of the read name: the sort key under which the records of one name meet
         unsigned long long hh = 1469598103934665603ull;
@@ -502,8 +470,7 @@ __global__ void k_gp_write(const uint8_t* __restrict__ ub, const recoff_t* __res
 // with it and deletes it; otherwise it becomes the entry if its mate lies ahead (mpos >= pos, or mpos == -1 of a
 // paired read). An entry is dead once its read has left the pileup buffer (end < position of the previous pushed read).
 __global__ void k_gp_pair(const unsigned long long* __restrict__ pkey, const uint32_t* __restrict__ pval, long long n,
-                          const uint8_t* __restrict__ ub, const recoff_t* __restrict__ krec, const int32_t* __restrict__ kprev,
-                          raer_read_hdr* hdr, long long r0, int32_t* __restrict__ pair_b, unsigned long long* n_pairs, int* flags) {
+                          const uint8_t* __restrict__ ub, GpMeta M, int* flags) {
     const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= n) return;
     const unsigned long long key = pkey[e];
@@ -511,9 +478,9 @@ __global__ void k_gp_pair(const unsigned long long* __restrict__ pkey, const uin
     long long entry = -1;                     // kept index of the record waiting for its mate
     for (long long j = e; j < n && pkey[j] == key; ++j) {
         const uint32_t K = pval[j];
-        const uint8_t* p = ub + krec[K] + 4;
+        const uint8_t* p = ub + M.krec[K] + 4;
         if (j > e) {  // same hash: must be the same name, else this is a collision the host has to sort out
-            const uint8_t* a = ub + krec[pval[e]] + 4 + 32;
+            const uint8_t* a = ub + M.krec[pval[e]] + 4 + 32;
             const uint8_t* b = p + 32;
             bool same = true;
             for (int k = 0;; ++k) {
@@ -522,18 +489,118 @@ __global__ void k_gp_pair(const unsigned long long* __restrict__ pkey, const uin
             }
             if (!same) { atomicOr(flags, 16); return; }
         }
-        if (entry >= 0 && hdr[r0 + entry].end < kprev[K]) entry = -1;  // its read left the buffer before this one came
+        if (entry >= 0 && M.kend[entry] < M.kprev[K]) entry = -1;  // its read left the buffer before this one came
         if (entry < 0) {
             const int pos = (int)ld32u(p + 4), flag = (int)ld16u(p + 14), mpos = (int)ld32u(p + 24);
             if (mpos >= pos || ((flag & 1) && mpos == -1)) entry = K;
         } else {
-            raer_read_hdr* h = hdr + r0 + K;
-            h->mate = (int32_t)(r0 + entry);
+            M.mateK[K] = (int32_t)entry;
             // htslib >= 1.13: the earlier mate keeps its qualities iff Wang(X31(name)) & 1
-            if (wang_hash(x31_hash(ub + krec[entry] + 4 + 32)) & 1u) h->bits |= RAER_RB_KEEP_A;
-            pair_b[atomicAdd(n_pairs, 1ull)] = (int32_t)(r0 + K);
+            M.keepA[K] = (uint8_t)(wang_hash(x31_hash(ub + M.krec[entry] + 4 + 32)) & 1u);
+            // htslib's overlap pass can rewrite qualities of the later mate far beyond the earlier mate's end (deletion
+            // catch-up across a ref-skip), so the earlier mate stays packed for as long as the later one is
+            atomicMax(&M.keepend[entry], M.kend[K]);
             entry = -1;
         }
+    }
+}
+
+// window planning helpers (one thread each): first K with kpos[K] >= w; kpos of the first K whose ksoff reaches `bytes`
+__global__ void k_gp_lower_pos(const int32_t* __restrict__ kpos, long long n, int w, unsigned long long* out) {
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (kpos[mid] < w) lo = mid + 1; else hi = mid;
+    }
+    *out = (unsigned long long)lo;
+}
+__global__ void k_gp_pos_at_bytes(const int32_t* __restrict__ kpos, const uint32_t* __restrict__ ksoff, long long n,
+                                  unsigned long long bytes, unsigned long long* out) {
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if ((unsigned long long)ksoff[mid] < bytes) lo = mid + 1; else hi = mid;
+    }
+    *out = lo < n ? (unsigned long long)(unsigned)max(kpos[lo], 0) : ~0ull;
+}
+// first K in [from, to) that has to be in a window starting at w (keepend > w); *out preset to `to`
+__global__ void k_gp_first_live(const int32_t* __restrict__ keepend, long long from, long long to, int w, unsigned long long* out) {
+    const long long K = from + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (K < to && keepend[K] > w) atomicMin(out, (unsigned long long)K);
+}
+
+struct GpOut {  // the batch arrays (device) of a window and where this file's share starts in them
+    raer_read_hdr* hdr;
+    uint32_t* cigar;
+    uint8_t* seq;
+    uint8_t* qual;
+    int32_t* cb;     // single cell: whitelist column / UMI code of every read
+    uint32_t* umi;
+    int32_t* pair_b;
+    unsigned long long* n_pairs;
+    long long r0, c0, s0;
+};
+
+// one thread per kept read K in [k_lo, k_hi): header, CIGAR words, packed sequence, qualities, mate link
+__global__ void k_gp_batch(const uint8_t* __restrict__ ub, GpMeta M, long long k_lo, long long k_hi, GpConf C, GpOut O) {
+    const long long K = k_lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (K >= k_hi) return;
+    const uint8_t* p = ub + M.krec[K] + 4;
+    const int l_qname = p[8], mapq = p[9];
+    const int n_cigar = (int)ld16u(p + 12), flag = (int)ld16u(p + 14);
+    const int l_qseq = (int)ld32u(p + 16);
+    const uint8_t* cg = p + 32 + l_qname;
+    const uint8_t* sq = cg + 4 * n_cigar;
+    const uint8_t* ql = sq + ((l_qseq + 1) >> 1);
+    const long long bi = O.r0 + (K - k_lo);
+    const long long co_ = O.c0 + (long long)(M.kcoff[K] - M.kcoff[k_lo]);
+    const long long so_ = O.s0 + (long long)(M.ksoff[K] - M.ksoff[k_lo]);
+    int bits = 0;
+    {  // invert_read_orientation (src/plp_utils.c:331-371)
+        const int lt = C.libtype, rev = (flag & 16) != 0;
+        int inv = 0;
+        if (lt == 1 || lt == 2) {
+            int r1 = -1;
+            if (!(flag & 1)) r1 = 1;
+            else if (flag & 64) r1 = 1;
+            else if (flag & 128) r1 = 0;
+            if (r1 >= 0) {
+                const int when_rev = (lt == 2);
+                inv = r1 ? (rev == when_rev) : (rev != when_rev);
+            }
+        }
+        if (inv) bits |= RAER_RB_INVERT;
+    }
+    if (C.min_overhang && l_qseq >= 2 && (sq[0] & 0xf) == 3) bits |= RAER_RB_OHANG_N;
+    const long long mk = M.mateK[K];
+    const bool paired = mk >= k_lo;  // an earlier mate in front of the window has nothing left in it
+    if (paired && M.keepA[K]) bits |= RAER_RB_KEEP_A;
+    raer_read_hdr h;
+    h.pos = M.kpos[K];
+    h.end = M.kend[K];
+    h.flag = (uint16_t)flag;
+    h.mapq = (uint8_t)mapq;
+    h.bits = (uint8_t)bits;
+    h.l_qseq = (uint16_t)l_qseq;
+    h.n_cigar = (uint16_t)n_cigar;
+    h.cigar_off = (uint32_t)co_;
+    h.sq_off = (uint32_t)so_;
+    h.mate = paired ? (int32_t)(O.r0 + (mk - k_lo)) : -1;
+    h.aux = (uint32_t)bi;  // its own batch index, like the host packer (bulk UMI mode never comes here)
+    O.hdr[bi] = h;
+    if (paired) O.pair_b[atomicAdd(O.n_pairs, 1ull)] = (int32_t)bi;
+    uint32_t* co = O.cigar + co_;
+    for (int k = 0; k < n_cigar; ++k) co[k] = ld32u(cg + 4 * k);
+    const int nsb = (l_qseq + 1) >> 1, padded = (nsb + 3) & ~3;
+    uint8_t* so = O.seq + so_;
+    for (int k = 0; k < nsb; ++k) so[k] = sq[k];
+    for (int k = nsb; k < padded; ++k) so[k] = 0xff;
+    uint8_t* qo = O.qual + 2 * so_;
+    for (int k = 0; k < l_qseq; ++k) qo[k] = ql[k];
+    for (int k = l_qseq; k < 2 * padded; ++k) qo[k] = 0;
+    if (C.sc) {
+        O.cb[bi] = M.kcb[K];
+        O.umi[bi] = M.kumi[K];
     }
 }
 
@@ -654,7 +721,9 @@ static void pin_release(uint8_t* p) {
 // everything one file contributes to the batch of a contig, still in its own buffers
 struct FileStage {
     DBufG comp, blk, ubuf, status, sp, cnt, base, rec_off, pass, pidx, r_pos, r_end, cpos, kept, kidx, ncig, coff, sqb, soff, elig, eidx,
-        prevpos, bsum, krec, kprev, pkey, pval, pkey2, pval2, hist, queue, rec_cb;
+        prevpos, bsum, krec, kprev, pkey, pval, pkey2, pval2, hist, queue, rec_cb, kpos, kend, kcoff, ksoff, kcb, kumi, mateK, keepend,
+        keepA;
+    long long k_lo_prev = 0;  // windows: where the previous window's live reads began
     PinnedBuf hblk;
     long long n_rec = 0, n_pass = 0, n_kept = 0, n_cig = 0, n_sq = 0, n_elig = 0;
     unsigned long long u_total = 0;
@@ -683,6 +752,12 @@ struct raer_gi {
     DBufG small, site_bits, site_pre, hdr, maxend, cigar, seq, qual, pair_b, endtmp, cb, umi, wl_key, wl_col, wl_off, wl_pool, umi_len;
     uint32_t wl_mask = 0;
     bool wl_built = false;
+    // the contig being served: position windows [win[j], win[j + 1]) and what a window's batch needs
+    std::vector<int> win;
+    std::vector<GpConf> fconf;  // per file (library type, contig number)
+    int cur_tid = -1, cur_len = 0;
+    bool cur_sc = false;
+    int64_t cur_bases = 0;
     size_t pool_bytes() const {  // what the device pool holds for reuse (freed buffers of earlier contigs count as free memory)
         cudaMemPool_t pool;
         unsigned long long reserved = 0, used = 0;
@@ -1142,17 +1217,29 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
 
 static int gi_maxend(raer_gi* g, raer_read_batch* b);
 
-// Builds the read batch of contig `tid` (numbering of file 0; `ftid[f]` = the same contig in file f's header) on the device.
-// site: the contig's intervals of the call's region list or nullptr. On RAER_OK *b describes device arrays owned by g
-// (valid until the next call); *site_mask_dev is the device bitmap of the listed positions (nullptr without a list).
+static GpMeta gi_meta(FileStage& S) {
+    GpMeta M;
+    M.krec = (recoff_t*)S.krec.p; M.kprev = (int32_t*)S.kprev.p; M.kpos = (int32_t*)S.kpos.p; M.kend = (int32_t*)S.kend.p;
+    M.kcoff = (uint32_t*)S.kcoff.p; M.ksoff = (uint32_t*)S.ksoff.p; M.kcb = (int32_t*)S.kcb.p; M.kumi = (uint32_t*)S.kumi.p;
+    M.mateK = (int32_t*)S.mateK.p; M.keepend = (int32_t*)S.keepend.p; M.keepA = (uint8_t*)S.keepA.p;
+    return M;
+}
+
+// Prepares contig `tid` (numbering of file 0; `ftid[f]` = the same contig in file f's header): every file's records are
+// inflated, parsed, filtered and paired on the device, and the contig is cut into position windows whose read batches fit
+// the 32-bit offsets of raer_read_hdr. site: the contig's intervals of the call's region list or nullptr;
+// *site_mask_dev is the device bitmap of the listed positions (nullptr without a list). *n_windows batches are then
+// fetched with raer_gi_window(), in order.
 extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_len, const raer::IngestConf* ic,
-                              const raer::RegionIndex::Chr* site, raer_read_batch* b, int64_t* file_off /* nf + 1 */,
-                              const uint32_t** site_mask_dev, int64_t* aligned_bases) {
+                              const raer::RegionIndex::Chr* site, int* n_windows, const uint32_t** site_mask_dev,
+                              int64_t* aligned_bases) {
     cudaSetDevice(g->device);
     cudaStream_t st = g->st;
     t_alloc_stream = st;
     const int nf = g->nf;
     int rc;
+    *n_windows = 0;
+    g->win.clear();
     GpConf C;
     memset(&C, 0, sizeof(C));
     C.keep0 = ic->keep_flag[0];
@@ -1232,65 +1319,58 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
         C.site_len = contig_len;
         *site_mask_dev = C.site_bits;
     }
-    long long n_reads = 0, n_cig = 0, n_sq = 0, n_elig_max = 0;
+    long long n_reads = 0;
+    unsigned long long sq_total = 0, sq_max = 0;
+    int f_max = 0;
     *aligned_bases = 0;
+    g->fconf.assign((size_t)nf, C);
     for (int f = 0; f < nf; ++f) {
         C.libtype = ic->libtype[(size_t)f];
         rc = gi_file_stage(g, f, ftid[f], C);
         if (rc) return rc;
-        const FileStage& S = g->stage[(size_t)f];
-        file_off[f] = n_reads;
+        FileStage& S = g->stage[(size_t)f];
+        S.k_lo_prev = 0;
+        g->fconf[(size_t)f] = C;
+        g->fconf[(size_t)f].tid = ftid[f];
         n_reads += S.n_kept;
-        n_cig += S.n_cig;
-        n_sq += S.n_sq;
-        n_elig_max = std::max(n_elig_max, S.n_elig);
+        sq_total += (unsigned long long)S.n_sq;
+        if ((unsigned long long)S.n_sq > sq_max) { sq_max = (unsigned long long)S.n_sq; f_max = f; }
         *aligned_bases += S.aligned_bases;
     }
-    file_off[nf] = n_reads;
-    memset(b, 0, sizeof(*b));
-    b->n_files = nf;
-    b->tid = tid;
-    b->beg = 0;
-    b->end = contig_len;
-    b->n_reads = n_reads;
-    b->file_off = file_off;
+    g->cur_tid = tid;
+    g->cur_len = contig_len;
+    g->cur_sc = ic->sc;
+    g->cur_bases = *aligned_bases;
     if (n_reads == 0) return RAER_OK;
-    if (n_reads >= INT_MAX || n_cig >= (1ll << 32) || n_sq >= (1ll << 31)) return RAER_GI_FALLBACK;  // 32-bit offsets in raer_read_hdr
-    if ((rc = g->hdr.ensure((size_t)n_reads * sizeof(raer_read_hdr))) || (rc = g->maxend.ensure((size_t)n_reads * 4)) ||
-        (rc = g->endtmp.ensure((size_t)n_reads * 4)) || (rc = g->cigar.ensure((size_t)n_cig * 4 + 16)) ||
-        (rc = g->seq.ensure((size_t)n_sq + 16)) || (rc = g->qual.ensure((size_t)n_sq * 2 + 16)) ||
-        (rc = g->pair_b.ensure((size_t)n_reads * 4 + 16)) ||
-        (ic->sc && ((rc = g->cb.ensure((size_t)n_reads * 4)) || (rc = g->umi.ensure((size_t)n_reads * 4)))))
-        return rc;
+    // a file whose own prefix sums overflow 32 bits cannot be described by the per-read tables either
+    for (int f = 0; f < nf; ++f)
+        if (g->stage[(size_t)f].n_kept >= INT_MAX || g->stage[(size_t)f].n_cig >= (1ll << 32) || g->stage[(size_t)f].n_sq >= (1ll << 32))
+            return RAER_GI_FALLBACK;
     unsigned long long* d_small = (unsigned long long*)g->small.p;
     GCK(cudaMemsetAsync(d_small, 0, 256, st));
     const double t7 = raer::now_seconds();
-    long long c0 = 0, s0 = 0;
     for (int f = 0; f < nf; ++f) {
         FileStage& S = g->stage[(size_t)f];
         if (S.n_kept == 0) continue;
-        C.libtype = ic->libtype[(size_t)f];
-        C.tid = ftid[f];
         const size_t nk = (size_t)S.n_kept, ne = (size_t)S.n_elig;
-        if ((rc = S.krec.ensure(nk * 8)) || (rc = S.kprev.ensure(nk * 4)) || (rc = S.pkey.ensure(ne * 8 + 16)) ||
+        if ((rc = S.krec.ensure(nk * 8)) || (rc = S.kprev.ensure(nk * 4)) || (rc = S.kpos.ensure(nk * 4)) || (rc = S.kend.ensure(nk * 4)) ||
+            (rc = S.kcoff.ensure((nk + 1) * 4)) || (rc = S.ksoff.ensure((nk + 1) * 4)) || (rc = S.mateK.ensure(nk * 4)) ||
+            (rc = S.keepend.ensure(nk * 4)) || (rc = S.keepA.ensure(nk)) ||
+            (ic->sc && ((rc = S.kcb.ensure(nk * 4)) || (rc = S.kumi.ensure(nk * 4)))) || (rc = S.pkey.ensure(ne * 8 + 16)) ||
             (rc = S.pval.ensure(ne * 4 + 16)) || (rc = S.pkey2.ensure(ne * 8 + 16)) || (rc = S.pval2.ensure(ne * 4 + 16)))
             return rc;
-        GpOut O;
-        O.hdr = (raer_read_hdr*)g->hdr.p;
-        O.cigar = (uint32_t*)g->cigar.p;
-        O.seq = (uint8_t*)g->seq.p;
-        O.qual = (uint8_t*)g->qual.p;
-        O.cb = (int32_t*)g->cb.p;
-        O.umi = (uint32_t*)g->umi.p;
-        O.r0 = file_off[f];
-        O.c0 = c0;
-        O.s0 = s0;
+        const GpMeta M = gi_meta(S);
+        const uint32_t tot[2] = {(uint32_t)S.n_cig, (uint32_t)S.n_sq};
+        GCK(cudaMemcpyAsync(M.kcoff + nk, &tot[0], 4, cudaMemcpyHostToDevice, st));
+        GCK(cudaMemcpyAsync(M.ksoff + nk, &tot[1], 4, cudaMemcpyHostToDevice, st));
+        GCK(cudaStreamSynchronize(st));  // tot lives on this frame
         const unsigned gr = (unsigned)((S.n_rec + 255) / 256);
-        k_gp_write<<<gr, 256, 0, st>>>((const uint8_t*)S.ubuf.p, (const recoff_t*)S.rec_off.p, (const uint32_t*)S.kept.p,
-                                       (const uint32_t*)S.kidx.p, (const uint32_t*)S.coff.p, (const uint32_t*)S.soff.p,
-                                       (const uint32_t*)S.elig.p, (const uint32_t*)S.eidx.p, (const int32_t*)S.r_end.p,
-                                       (const int32_t*)S.prevpos.p, S.n_rec, C, O, (unsigned long long*)S.pkey.p, (uint32_t*)S.pval.p,
-                                       (recoff_t*)S.krec.p, (int32_t*)S.kprev.p, (const int32_t*)S.rec_cb.p, (int*)(d_small + 1));
+        k_gp_meta<<<gr, 256, 0, st>>>((const uint8_t*)S.ubuf.p, (const recoff_t*)S.rec_off.p, (const uint32_t*)S.kept.p,
+                                      (const uint32_t*)S.kidx.p, (const uint32_t*)S.coff.p, (const uint32_t*)S.soff.p,
+                                      (const uint32_t*)S.elig.p, (const uint32_t*)S.eidx.p, (const int32_t*)S.r_pos.p,
+                                      (const int32_t*)S.r_end.p, (const int32_t*)S.prevpos.p, S.n_rec, g->fconf[(size_t)f], M,
+                                      (unsigned long long*)S.pkey.p, (uint32_t*)S.pval.p, (const int32_t*)S.rec_cb.p,
+                                      (int*)(d_small + 1));
         ++g->launches;
         if (S.n_elig > 0) {
             const unsigned nblk = (unsigned)((S.n_elig + (long long)RS_BLOCK * RS_ITEMS - 1) / ((long long)RS_BLOCK * RS_ITEMS));
@@ -1300,20 +1380,147 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
             unsigned long long* k_out = (unsigned long long*)S.pkey2.p;
             unsigned* v_out = (unsigned*)S.pval2.p;
             g->launches += rs_sort(k_in, v_in, k_out, v_out, S.n_elig, 64, (unsigned*)S.hist.p, st);
-            k_gp_pair<<<(unsigned)((S.n_elig + 255) / 256), 256, 0, st>>>(k_in, v_in, S.n_elig, (const uint8_t*)S.ubuf.p,
-                                                                          (const recoff_t*)S.krec.p, (const int32_t*)S.kprev.p,
-                                                                          (raer_read_hdr*)g->hdr.p, file_off[f], (int32_t*)g->pair_b.p,
-                                                                          d_small + 4, (int*)(d_small + 1));
+            k_gp_pair<<<(unsigned)((S.n_elig + 255) / 256), 256, 0, st>>>(k_in, v_in, S.n_elig, (const uint8_t*)S.ubuf.p, M,
+                                                                          (int*)(d_small + 1));
             ++g->launches;
         }
-        c0 += S.n_cig;
-        s0 += S.n_sq;
     }
     GCK(cudaMemcpyAsync(g->h_small, d_small, 64, cudaMemcpyDeviceToHost, st));
     GCK(cudaStreamSynchronize(st));
     if (cudaGetLastError() != cudaSuccess) { set_error("device ingest kernels failed"); return RAER_ERR_CUDA; }
     if (g->h_small[1] & 16) return RAER_GI_FALLBACK;  // two read names with one 64-bit hash: the host's string table decides
     if (g->h_small[1] & 256) return RAER_GI_FALLBACK;  // a UMI the 2-bit code does not cover: the host's dictionary takes it
+    // ---- position windows: boundaries at the positions where the largest file's packed sequence crosses equal shares
+    unsigned long long budget = 3ull << 29;  // packed sequence bytes per window, all files (the offsets are 31 bits)
+    if (const char* e = getenv("RAER_GI_WINDOW_BYTES")) budget = std::max<unsigned long long>(4096, strtoull(e, nullptr, 10));
+    const int n_cut = (int)std::min<unsigned long long>((sq_total + budget - 1) / budget, 1u << 20);
+    g->win.push_back(0);
+    if (n_cut > 1) {
+        FileStage& S = g->stage[(size_t)f_max];
+        const GpMeta M = gi_meta(S);
+        for (int j = 1; j < n_cut; ++j) {
+            const unsigned long long target = sq_max / (unsigned long long)n_cut * (unsigned long long)j;
+            k_gp_pos_at_bytes<<<1, 1, 0, st>>>(M.kpos, M.ksoff, S.n_kept, target, d_small + 8);
+            GCK(cudaMemcpyAsync(g->h_small, d_small + 8, 8, cudaMemcpyDeviceToHost, st));
+            GCK(cudaStreamSynchronize(st));
+            const unsigned long long w = g->h_small[0];
+            if (w != ~0ull && (int)w > g->win.back() && (int)w < contig_len) g->win.push_back((int)w);
+        }
+        g->launches += n_cut - 1;
+    }
+    g->win.push_back(std::max(contig_len, g->win.back() + 1));
+    *n_windows = (int)g->win.size() - 1;
+    g->t_write += raer::now_seconds() - t7;
+    return RAER_OK;
+}
+
+// The read batch of window j of the prepared contig: *b describes device arrays owned by g (valid until the next call).
+// Windows have to be fetched in ascending order. A window no read reaches comes back with n_reads == 0.
+extern "C" int raer_gi_window(raer_gi* g, int j, raer_read_batch* b, int64_t* file_off /* nf + 1 */) {
+    cudaSetDevice(g->device);
+    cudaStream_t st = g->st;
+    t_alloc_stream = st;
+    const int nf = g->nf;
+    int rc;
+    if (j < 0 || j + 1 >= (int)g->win.size()) { set_error("no such window"); return RAER_ERR_ARG; }
+    const int w0 = g->win[(size_t)j], w1 = g->win[(size_t)j + 1];
+    const bool last = j + 2 == (int)g->win.size();
+    const double t7 = raer::now_seconds();
+    unsigned long long* d_small = (unsigned long long*)g->small.p;
+    // per file: [k_lo, k_hi) = the reads that start before the window ends, from the first one that is still needed
+    std::vector<long long> k_lo((size_t)nf, 0), k_hi((size_t)nf, 0);
+    for (int f = 0; f < nf; ++f) {
+        FileStage& S = g->stage[(size_t)f];
+        if (S.n_kept == 0) continue;
+        const GpMeta M = gi_meta(S);
+        if (last) {
+            k_hi[(size_t)f] = S.n_kept;
+        } else {
+            k_gp_lower_pos<<<1, 1, 0, st>>>(M.kpos, S.n_kept, w1, d_small + 8);
+            GCK(cudaMemcpyAsync(g->h_small, d_small + 8, 8, cudaMemcpyDeviceToHost, st));
+            GCK(cudaStreamSynchronize(st));
+            k_hi[(size_t)f] = (long long)g->h_small[0];
+        }
+        const long long from = S.k_lo_prev, to = k_hi[(size_t)f];
+        k_lo[(size_t)f] = to;
+        if (to > from) {
+            const unsigned long long init = (unsigned long long)to;
+            GCK(cudaMemcpyAsync(d_small + 9, &init, 8, cudaMemcpyHostToDevice, st));
+            GCK(cudaStreamSynchronize(st));
+            k_gp_first_live<<<(unsigned)((to - from + 255) / 256), 256, 0, st>>>(M.keepend, from, to, w0, d_small + 9);
+            GCK(cudaMemcpyAsync(g->h_small, d_small + 9, 8, cudaMemcpyDeviceToHost, st));
+            GCK(cudaStreamSynchronize(st));
+            k_lo[(size_t)f] = (long long)g->h_small[0];
+        }
+        S.k_lo_prev = k_lo[(size_t)f];
+        g->launches += 2;
+    }
+    // sizes of the window: prefix sums at k_lo / k_hi
+    long long n_reads = 0, n_cig = 0, n_sq = 0;
+    std::vector<long long> c_of((size_t)nf, 0), s_of((size_t)nf, 0);
+    for (int f = 0; f < nf; ++f) {
+        FileStage& S = g->stage[(size_t)f];
+        file_off[f] = n_reads;
+        if (S.n_kept == 0 || k_hi[(size_t)f] <= k_lo[(size_t)f]) continue;
+        const GpMeta M = gi_meta(S);
+        uint32_t v[4];
+        GCK(cudaMemcpyAsync(&v[0], M.kcoff + k_lo[(size_t)f], 4, cudaMemcpyDeviceToHost, st));
+        GCK(cudaMemcpyAsync(&v[1], M.kcoff + k_hi[(size_t)f], 4, cudaMemcpyDeviceToHost, st));
+        GCK(cudaMemcpyAsync(&v[2], M.ksoff + k_lo[(size_t)f], 4, cudaMemcpyDeviceToHost, st));
+        GCK(cudaMemcpyAsync(&v[3], M.ksoff + k_hi[(size_t)f], 4, cudaMemcpyDeviceToHost, st));
+        GCK(cudaStreamSynchronize(st));
+        c_of[(size_t)f] = n_cig;
+        s_of[(size_t)f] = n_sq;
+        n_reads += k_hi[(size_t)f] - k_lo[(size_t)f];
+        n_cig += (long long)(v[1] - v[0]);
+        n_sq += (long long)(v[3] - v[2]);
+    }
+    file_off[nf] = n_reads;
+    memset(b, 0, sizeof(*b));
+    b->n_files = nf;
+    b->tid = g->cur_tid;
+    b->beg = w0;
+    b->end = last ? std::max(g->cur_len, w0 + 1) : w1;
+    b->n_reads = n_reads;
+    b->file_off = file_off;
+    if (n_reads == 0) return RAER_OK;
+    if (n_reads >= INT_MAX || n_cig >= (1ll << 32) || n_sq >= (1ll << 31)) {
+        // a window denser than the plan assumed (the boundaries follow the largest file only): not recoverable here, the
+        // rows of earlier windows are out already
+        set_error("device ingest: a window of %lld sequence bytes exceeds the 32-bit offsets of the read batch; set "
+                  "RAER_GI_WINDOW_BYTES lower", n_sq);
+        return RAER_ERR_LIMIT;
+    }
+    if ((rc = g->hdr.ensure((size_t)n_reads * sizeof(raer_read_hdr))) || (rc = g->maxend.ensure((size_t)n_reads * 4)) ||
+        (rc = g->endtmp.ensure((size_t)n_reads * 4)) || (rc = g->cigar.ensure((size_t)n_cig * 4 + 16)) ||
+        (rc = g->seq.ensure((size_t)n_sq + 16)) || (rc = g->qual.ensure((size_t)n_sq * 2 + 16)) ||
+        (rc = g->pair_b.ensure((size_t)n_reads * 4 + 16)) ||
+        (g->cur_sc && ((rc = g->cb.ensure((size_t)n_reads * 4)) || (rc = g->umi.ensure((size_t)n_reads * 4)))))
+        return rc;
+    GCK(cudaMemsetAsync(d_small + 4, 0, 8, st));
+    for (int f = 0; f < nf; ++f) {
+        FileStage& S = g->stage[(size_t)f];
+        const long long n = k_hi[(size_t)f] - k_lo[(size_t)f];
+        if (S.n_kept == 0 || n <= 0) continue;
+        GpOut O;
+        O.hdr = (raer_read_hdr*)g->hdr.p;
+        O.cigar = (uint32_t*)g->cigar.p;
+        O.seq = (uint8_t*)g->seq.p;
+        O.qual = (uint8_t*)g->qual.p;
+        O.cb = (int32_t*)g->cb.p;
+        O.umi = (uint32_t*)g->umi.p;
+        O.pair_b = (int32_t*)g->pair_b.p;
+        O.n_pairs = d_small + 4;
+        O.r0 = file_off[f];
+        O.c0 = c_of[(size_t)f];
+        O.s0 = s_of[(size_t)f];
+        k_gp_batch<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint8_t*)S.ubuf.p, gi_meta(S), k_lo[(size_t)f], k_hi[(size_t)f],
+                                                               g->fconf[(size_t)f], O);
+        ++g->launches;
+    }
+    GCK(cudaMemcpyAsync(g->h_small, d_small, 64, cudaMemcpyDeviceToHost, st));
+    GCK(cudaStreamSynchronize(st));
+    if (cudaGetLastError() != cudaSuccess) { set_error("device ingest kernels failed"); return RAER_ERR_CUDA; }
     b->hdr = (const raer_read_hdr*)g->hdr.p;
     b->cigar = (const uint32_t*)g->cigar.p;
     b->seq = (const uint8_t*)g->seq.p;
@@ -1322,8 +1529,8 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
     b->n_sq_bytes = n_sq;
     b->pair_b = (const int32_t*)g->pair_b.p;
     b->n_pairs = (int64_t)g->h_small[4];
-    b->n_aligned_bases = *aligned_bases;
-    if (ic->sc) {
+    b->n_aligned_bases = j == 0 ? g->cur_bases : 0;
+    if (g->cur_sc) {
         b->cb = (const int32_t*)g->cb.p;
         b->umi = (const uint32_t*)g->umi.p;
     }

@@ -40,8 +40,9 @@ struct raer_gi;
 extern "C" raer_gi* raer_gi_create(int device, int nf, const char* const* paths, const char* const* indexes);
 extern "C" void raer_gi_destroy(raer_gi* g);
 extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_len, const raer::IngestConf* ic,
-                              const raer::RegionIndex::Chr* site, raer_read_batch* b, int64_t* file_off, const uint32_t** site_mask_dev,
+                              const raer::RegionIndex::Chr* site, int* n_windows, const uint32_t** site_mask_dev,
                               int64_t* aligned_bases);
+extern "C" int raer_gi_window(raer_gi* g, int j, raer_read_batch* b, int64_t* file_off);
 extern "C" void raer_gi_stats(raer_gi* g, int64_t* launches, int64_t* inflated, int64_t* compressed, int64_t* records);
 
 #define CK(call)                                                                              \
@@ -1052,11 +1053,11 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
                 }
             }
             if (rc) break;
-            raer_read_batch b;
             const uint32_t* d_sites = nullptr;
             int64_t bases = 0;
+            int n_windows = 0;
             double t0b = raer::now_seconds();
-            int r = raer_gi_contig(gi, c, ftid.data(), lens[(size_t)c], &ic, rchr, &b, file_off.data(), &d_sites, &bases);
+            int r = raer_gi_contig(gi, c, ftid.data(), lens[(size_t)c], &ic, rchr, &n_windows, &d_sites, &bases);
             tm_batch += raer::now_seconds() - t0b;
             if (r == 1) {  // RAER_GI_FALLBACK
                 ++n_fallback;
@@ -1067,7 +1068,7 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             if (r) { rc = r; break; }
             out->n_aligned_bases += bases;
             ++out->n_device_contigs;
-            if (b.n_reads == 0) continue;
+            if (n_windows == 0) continue;
             std::string seq;
             double t0f = raer::now_seconds();
             if (!raer::fasta_fetch(a->fapath, names[c], seq)) seq.clear();
@@ -1079,21 +1080,31 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             bc.site_mask = d_sites;  // device pointer: the bitmap the prefilter used, over the whole contig
             bc.mask_beg = 0;
             bc.mask_bits = lens[(size_t)c];
-            raer_rows rows;
-            int64_t launches = 0;
-            double t0g = raer::now_seconds();
-            rc = raer_batch_pileup_device_rows(ctx, &bc, &b, &rows, &launches);
-            tm_gpu += raer::now_seconds() - t0g;
-            if (rc) break;
-            if (bc.aei_mode) {
-                std::vector<int64_t> sums((size_t)nf * 16);
-                if ((rc = raer_ctx_last_aei(ctx, sums.data(), nf))) { raer_rows_free(&rows); break; }
-                for (size_t i = 0; i < sums.size(); ++i) out->aei[i] += sums[i];
+            // the contig in position windows (one unless its reads exceed what a batch's 32-bit offsets describe)
+            for (int j = 0; j < n_windows && rc == RAER_OK; ++j) {
+                if (j > 0 && a->poll && a->poll(a->poll_ctx)) { set_error("interrupted"); rc = RAER_ERR_INTERRUPT; break; }
+                raer_read_batch b;
+                t0b = raer::now_seconds();
+                rc = raer_gi_window(gi, j, &b, file_off.data());
+                tm_batch += raer::now_seconds() - t0b;
+                if (rc) break;
+                if (b.n_reads == 0) continue;
+                raer_rows rows;
+                int64_t launches = 0;
+                double t0g = raer::now_seconds();
+                rc = raer_batch_pileup_device_rows(ctx, &bc, &b, &rows, &launches);
+                tm_gpu += raer::now_seconds() - t0g;
+                if (rc) break;
+                if (bc.aei_mode) {
+                    std::vector<int64_t> sums((size_t)nf * 16);
+                    if ((rc = raer_ctx_last_aei(ctx, sums.data(), nf))) { raer_rows_free(&rows); break; }
+                    for (size_t i = 0; i < sums.size(); ++i) out->aei[i] += sums[i];
+                }
+                out->gpu_launches += launches;
+                out->t_kernel += ctx->ms_kernel * 1e-3;
+                out->t_d2h += ctx->ms_d2h * 1e-3;
+                emit_rows(c, rows);
             }
-            out->gpu_launches += launches;
-            out->t_kernel += ctx->ms_kernel * 1e-3;
-            out->t_d2h += ctx->ms_d2h * 1e-3;
-            emit_rows(c, rows);
         }
         if (gi) {
             int64_t gl = 0, gin = 0, gco = 0, grec = 0;

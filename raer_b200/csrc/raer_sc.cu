@@ -575,8 +575,9 @@ struct raer_gi;
 extern "C" raer_gi* raer_gi_create(int device, int nf, const char* const* paths, const char* const* indexes);
 extern "C" void raer_gi_destroy(raer_gi* g);
 extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_len, const raer::IngestConf* ic,
-                              const raer::RegionIndex::Chr* site, raer_read_batch* b, int64_t* file_off, const uint32_t** site_mask_dev,
+                              const raer::RegionIndex::Chr* site, int* n_windows, const uint32_t** site_mask_dev,
                               int64_t* aligned_bases);
+extern "C" int raer_gi_window(raer_gi* g, int j, raer_read_batch* b, int64_t* file_off);
 extern "C" uint32_t raer_gi_umi_space(raer_gi* g);
 
 static int64_t g_sc_last_device_contigs = 0;
@@ -793,15 +794,18 @@ static int sc_run(const raer_scpileup_args* a, bool want_files, raer_sc_triplets
                 }
                 if (on_device) {
                     if (a->poll && a->poll(a->poll_ctx)) { set_error("interrupted"); rc = RAER_ERR_INTERRUPT; break; }
-                    raer_read_batch b;
                     int64_t file_off[2] = {0, 0}, bases = 0;
                     const uint32_t* d_sites = nullptr;
                     const int ftid = (int)ci;
-                    const int r = raer_gi_contig(gh.g, (int)ci, &ftid, lens[ci], &ic, rchr, &b, file_off, &d_sites, &bases);
+                    int n_windows = 0;
+                    const int r = raer_gi_contig(gh.g, (int)ci, &ftid, lens[ci], &ic, rchr, &n_windows, &d_sites, &bases);
                     if (r < 0) { rc = r; break; }
                     if (r == 0) {
                         const std::vector<int>* sites = contig_sites(names[ci]);
-                        if (conf.n_sites && b.n_reads > 0) {
+                        for (int j = 0; j < n_windows && rc == RAER_OK; ++j) {
+                            raer_read_batch b;
+                            if ((rc = raer_gi_window(gh.g, j, &b, file_off))) break;
+                            if (!conf.n_sites || b.n_reads == 0) continue;
                             conf.n_umi = raer_gi_umi_space(gh.g);
                             raer_sc_cells cells;
                             rc = raer_sc_batch_device_cells(c, &conf, &b, &cells);
@@ -809,6 +813,7 @@ static int sc_run(const raer_scpileup_args* a, bool want_files, raer_sc_triplets
                             emit_cells(sites, cells);
                             raer_sc_cells_free(&cells);
                         }
+                        if (rc) break;
                         ++n_device_contigs;
                         continue;
                     }

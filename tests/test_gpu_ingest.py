@@ -318,3 +318,42 @@ def test_single_cell_device_ingest_on_the_bundled_10x_bam(ext, monkeypatch):
     host = api.pileup_cells_triplets(ext.scbam, gr, cbs, param=fp)
     assert _sc_triplets(dev) == _sc_triplets(host)
     assert sum(_sc_triplets(dev)[4]) > 100
+
+
+# ---- position windows: a contig whose reads exceed what one batch's 32-bit offsets describe is served in several batches
+@pytest.mark.parametrize("window_bytes", ["4096", "20000", "150000"])
+def test_contig_served_in_position_windows(tmp_path, monkeypatch, window_bytes):
+    """RAER_GI_WINDOW_BYTES forces many small windows: halo reads, mates kept with their partners across a boundary,
+    pairs, per-window offsets; rows must not depend on where the boundaries fall"""
+    ds = synth.make_bulk_dataset(str(tmp_path), n_bams=2, n_contigs=2, contig_len=50_000, pairs_per_contig=12_000, seed=19)
+    pc = prepare_pileup_call(ds["bams"], ds["fasta"], param=FilterParam(min_depth=1, library_type="fr-first-strand"))
+    monkeypatch.setenv("RAER_GI_WINDOW_BYTES", window_bytes)
+    dev, host = _both(pc, monkeypatch)
+    assert dev["timing"]["n_device_contigs"] == 2 and dev["timing"]["n_host_contigs"] == 0
+    _columns_equal(dev, host)
+    monkeypatch.delenv("RAER_GI_WINDOW_BYTES")
+    monkeypatch.setenv("RAER_GPU_INGEST", "1")
+    one = _cabi.pileup(pc)
+    _columns_equal(dev, one)
+    assert dev["nrows"] > 10000
+
+
+def test_position_windows_on_the_golden_files_and_single_cell(ext, tmp_path, monkeypatch):
+    from raer_b200 import api
+
+    monkeypatch.setenv("RAER_GI_WINDOW_BYTES", "4096")
+    for kw in (dict(), dict(param=FilterParam(only_keep_variants=True, min_depth=2)),
+               dict(param=FilterParam(library_type="unstranded", trim_5p=4, splice_dist=3))):
+        pc = prepare_pileup_call([ext.bam1, ext.bam2], ext.fasta, **kw)
+        dev, host = _both(pc, monkeypatch)
+        assert dev["timing"]["n_device_contigs"] >= 1
+        _columns_equal(dev, host)
+    ds = synth.make_sc_dataset(str(tmp_path / "sc"))
+    gr = Sites(**ds["sites"])
+    fp = FilterParam(library_type="fr-second-strand", min_depth=0)
+    monkeypatch.setenv("RAER_GPU_INGEST", "1")
+    dev = api.pileup_cells_triplets(ds["bam"], gr, ds["barcodes"], param=fp)
+    assert _cabi.sc_last_device_contigs() >= 1
+    monkeypatch.setenv("RAER_GPU_INGEST", "0")
+    host = api.pileup_cells_triplets(ds["bam"], gr, ds["barcodes"], param=fp)
+    assert _sc_triplets(dev) == _sc_triplets(host)
