@@ -1409,6 +1409,44 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
         g->launches += n_cut - 1;
     }
     g->win.push_back(std::max(contig_len, g->win.back() + 1));
+    if (g->win.size() > 2) {
+        // the boundaries follow one file: make sure no window is too large over ALL files (a window that is gets cut in half,
+        // before any row of the contig is out)
+        auto bytes_before = [&](int w, unsigned long long* out) -> int {  // packed sequence of the reads that start before w
+            unsigned long long tot = 0;
+            for (int f = 0; f < nf; ++f) {
+                FileStage& S = g->stage[(size_t)f];
+                if (S.n_kept == 0) continue;
+                const GpMeta M = gi_meta(S);
+                k_gp_lower_pos<<<1, 1, 0, st>>>(M.kpos, S.n_kept, w, d_small + 8);
+                GCK(cudaMemcpyAsync(g->h_small, d_small + 8, 8, cudaMemcpyDeviceToHost, st));
+                GCK(cudaStreamSynchronize(st));
+                uint32_t v = 0;
+                GCK(cudaMemcpy(&v, M.ksoff + g->h_small[0], 4, cudaMemcpyDeviceToHost));
+                tot += v;
+                ++g->launches;
+            }
+            *out = tot;
+            return 0;
+        };
+        const unsigned long long hard = std::min<unsigned long long>(7ull << 28, std::max<unsigned long long>(budget + budget / 4, 8192));
+        std::vector<int> W = g->win;
+        std::vector<unsigned long long> B(W.size(), 0);
+        for (size_t k = 0; k < W.size(); ++k)
+            if ((rc = bytes_before(k + 1 == W.size() ? INT_MAX : W[k], &B[k]))) return rc;
+        for (size_t k = 0; k + 1 < W.size() && W.size() < (1u << 20);) {
+            if (B[k + 1] - B[k] > hard && W[k + 1] - W[k] > 1) {
+                const int mid = W[k] + (W[k + 1] - W[k]) / 2;
+                unsigned long long bm = 0;
+                if ((rc = bytes_before(mid, &bm))) return rc;
+                W.insert(W.begin() + (long)k + 1, mid);
+                B.insert(B.begin() + (long)k + 1, bm);
+                continue;
+            }
+            ++k;
+        }
+        g->win = W;
+    }
     *n_windows = (int)g->win.size() - 1;
     g->t_write += raer::now_seconds() - t7;
     return RAER_OK;
