@@ -339,18 +339,19 @@ def _sites_by_gene_strand(sites: Sites, genes: Sites):
     it when they agree; sites under genes of both strands or under none are dropped. Returns (plus, minus)."""
     from collections import defaultdict
 
-    by = {"+": defaultdict(list), "-": defaultdict(list)}
+    by = {"+": defaultdict(list), "-": defaultdict(list), "*": defaultdict(list)}
     for sn, a, b, st in zip(genes.seqnames, genes.start, genes.end, genes.strand):
-        if st in by:
-            by[st][sn].append((int(a), int(b)))
+        by[st if st in by else "*"][sn].append((int(a), int(b)))
     per_chr = defaultdict(list)
     for sn, a, b in zip(sites.seqnames, sites.start, sites.end):
         per_chr[sn].append((int(a), int(b)))
     out = {"+": ([], [], []), "-": ([], [], [])}
     for sn in dict.fromkeys(sites.seqnames):
         mine = _merge_intervals(per_chr[sn])
-        up, um = _merge_intervals(by["+"][sn]), _merge_intervals(by["-"][sn])
-        for st, only in (("+", _subtract_intervals(up, um)), ("-", _subtract_intervals(um, up))):
+        up, um, us = _merge_intervals(by["+"][sn]), _merge_intervals(by["-"][sn]), _merge_intervals(by["*"][sn])
+        # a gene without a strand makes the sites under it ambiguous (or, alone, unstranded): dropped either way
+        for st, only in (("+", _subtract_intervals(_subtract_intervals(up, um), us)),
+                         ("-", _subtract_intervals(_subtract_intervals(um, up), us))):
             for a, b in _intersect_intervals(mine, only):
                 out[st][0].append(sn); out[st][1].append(a); out[st][2].append(b)
     return Sites(*out["+"]), Sites(*out["-"])

@@ -143,3 +143,31 @@ def test_fused_reduction_for_unstranded_libraries(tmp_path):
     want = oracle_backend.calc_AEI(ds["bams"], ds["fasta"], alu, genes, snp_db=snps, param=fp)
     assert fused["AEI_per_chrom"] == rows["AEI_per_chrom"] == want["AEI_per_chrom"]
     assert sum(a + r for v in fused["AEI_per_chrom"].values() for a, r in v.values()) > 5_000
+
+
+def test_gene_strand_split_of_site_intervals():
+    """correct_strand() as interval arithmetic (api._sites_by_gene_strand) against the per-position definition: a site
+    takes the strand of the genes over it when they agree, and is dropped otherwise"""
+    import random
+
+    from raer_b200 import api
+
+    rng = random.Random(4)
+    for _ in range(60):
+        sites = Sites(["c"] * 4 + ["d"], [rng.randrange(1, 80) for _ in range(5)], None)
+        sites.end = [s + rng.randrange(0, 15) for s in sites.start]
+        gn, gs, ge, gst = [], [], [], []
+        for _ in range(rng.randrange(0, 7)):
+            a = rng.randrange(1, 90)
+            gn.append(rng.choice("cd")); gs.append(a); ge.append(a + rng.randrange(0, 30)); gst.append(rng.choice("+-*"))
+        genes = Sites(gn, gs, ge, strand=gst)
+        plus, minus = api._sites_by_gene_strand(sites, genes)
+        want = {"+": set(), "-": set()}
+        for sn, a, b in zip(sites.seqnames, sites.start, sites.end):
+            for p in range(a, b + 1):
+                st = {g for n, x, y, g in zip(gn, gs, ge, gst) if n == sn and x <= p <= y}
+                if len(st) == 1 and "*" not in st:
+                    want[st.pop()].add((sn, p))
+        for got, key in ((plus, "+"), (minus, "-")):
+            have = [(sn, p) for sn, a, b in zip(got.seqnames, got.start, got.end) for p in range(a, b + 1)]
+            assert len(have) == len(set(have)) and set(have) == want[key]
