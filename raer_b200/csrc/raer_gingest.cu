@@ -177,6 +177,7 @@ struct GpConf {
     // single cell (screadaln, src/sc-plp.c:449-511): the cell-barcode tag has to be on the whitelist (open-addressing table
     // of FNV-1a name hashes, strings compared on a hit), or every read of the file belongs to one column (Smart-seq2)
     int sc, has_cb_tag, has_umi_tag, fixed_cb;
+    int n_mm_type, n_mm;               // mismatch filter (max_mismatch_type): the MD verdict is one bit per read
     uint8_t cb_tag[2], umi_tag[2];
     const unsigned long long* wl_key;  // 0 = empty slot
     const int32_t* wl_col;             // 1-based whitelist column
@@ -405,8 +406,51 @@ struct GpMeta {
     uint32_t* kumi;
     int32_t* mateK;     // K of the earlier mate this read resolves an overlap with, or -1
     int32_t* keepend;   // a read stays in the windows until this position: its own end or that of the mate paired with it
-    uint8_t* keepA;     // the earlier mate keeps its qualities (htslib >= 1.13 coin)
+    uint8_t* keepA;     // bit 0: the earlier mate keeps its qualities (htslib >= 1.13 coin); bits 1, 2: MD verdict fail / inconsistent
 };
+
+// parse_mismatches (src/ext/htsbox/htsbox-ext.c:17-97) as one verdict per read, like the host's md_verdict: 0 pass,
+// > 0 fail, -1 MD tag inconsistent with the CIGAR
+__device__ int gp_md_verdict(const uint8_t* p, int n_types, int n_mis) {
+    const int l_qname = p[8], n_cigar = (int)ld16u(p + 12), l_qseq = (int)ld32u(p + 16);
+    const uint8_t* cg = p + 32 + l_qname;
+    const uint8_t* sq = cg + 4 * n_cigar;
+    const uint8_t* aux = sq + ((l_qseq + 1) >> 1) + l_qseq;
+    const uint8_t* md = gp_aux_find(aux, p + ld32u(p - 4), 'M', 'D');
+    if (!md || (*md != 'Z' && *md != 'H')) return 0;
+    int x = 0;
+    for (int k = 0; k < n_cigar; ++k) {
+        const uint32_t w = ld32u(cg + 4 * k);
+        const int op = (int)(w & 0xf);
+        if (op == 0 || op == 7 || op == 8) x += (int)(w >> 4);
+    }
+    const uint8_t* q = md + 1;
+    int y = 0, nm = 0, ntypes = 0;
+    unsigned seen = 0;
+    auto is_alpha = [](uint8_t c) { return (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z'); };
+    while (*q >= '0' && *q <= '9') {
+        long long v = 0;
+        while (*q >= '0' && *q <= '9') { v = v * 10 + (*q - '0'); if (v > INT_MAX) v = INT_MAX; ++q; }
+        y += (int)v;
+        if (*q == 0) break;
+        if (*q == '^') {
+            ++q;
+            while (is_alpha(*q)) ++q;
+        } else {
+            while (is_alpha(*q)) {
+                if (y >= x) { y = -1; break; }
+                const int code = y < l_qseq ? (sq[y >> 1] >> ((~y & 1) << 2)) & 0xf : 15;
+                ++nm;
+                if (!(seen & (1u << code))) { seen |= 1u << code; ++ntypes; }
+                ++y;
+                ++q;
+            }
+            if (y == -1) break;
+        }
+    }
+    if (x != y) return -1;
+    return (ntypes >= n_types && nm >= n_mis) ? (ntypes > 0 ? ntypes : 0) : 0;
+}
 
 __global__ void k_gp_meta(const uint8_t* __restrict__ ub, const recoff_t* __restrict__ rec_off, const uint32_t* __restrict__ kept,
                           const uint32_t* __restrict__ kidx, const uint32_t* __restrict__ coff, const uint32_t* __restrict__ soff,
@@ -426,7 +470,13 @@ __global__ void k_gp_meta(const uint8_t* __restrict__ ub, const recoff_t* __rest
     M.ksoff[K] = soff[i];
     M.mateK[K] = -1;
     M.keepend[K] = r_end[i];
-    M.keepA[K] = 0;
+    uint8_t rb = 0;  // bit 0: the earlier mate keeps its qualities (set by k_gp_pair); bits 1, 2: MD verdict
+    if (C.n_mm_type > 0 || C.n_mm > 0) {
+        const int m = gp_md_verdict(p, C.n_mm_type, C.n_mm);
+        if (m > 0) rb |= 2;
+        else if (m < 0) rb |= 4;
+    }
+    M.keepA[K] = rb;
     if (C.sc) {
         M.kcb[K] = rec_cb[i];
         uint32_t code = 0;
@@ -496,7 +546,7 @@ __global__ void k_gp_pair(const unsigned long long* __restrict__ pkey, const uin
         } else {
             M.mateK[K] = (int32_t)entry;
             // htslib >= 1.13: the earlier mate keeps its qualities iff Wang(X31(name)) & 1
-            M.keepA[K] = (uint8_t)(wang_hash(x31_hash(ub + M.krec[entry] + 4 + 32)) & 1u);
+            M.keepA[K] |= (uint8_t)(wang_hash(x31_hash(ub + M.krec[entry] + 4 + 32)) & 1u);
             // htslib's overlap pass can rewrite qualities of the later mate far beyond the earlier mate's end (deletion
             // catch-up across a ref-skip), so the earlier mate stays packed for as long as the later one is
             atomicMax(&M.keepend[entry], M.kend[K]);
@@ -574,7 +624,10 @@ __global__ void k_gp_batch(const uint8_t* __restrict__ ub, GpMeta M, long long k
     if (C.min_overhang && l_qseq >= 2 && (sq[0] & 0xf) == 3) bits |= RAER_RB_OHANG_N;
     const long long mk = M.mateK[K];
     const bool paired = mk >= k_lo;  // an earlier mate in front of the window has nothing left in it
-    if (paired && M.keepA[K]) bits |= RAER_RB_KEEP_A;
+    const int rb = M.keepA[K];
+    if (paired && (rb & 1)) bits |= RAER_RB_KEEP_A;
+    if (rb & 2) bits |= RAER_RB_MMFAIL;
+    if (rb & 4) bits |= RAER_RB_MMERR;
     raer_read_hdr h;
     h.pos = M.kpos[K];
     h.end = M.kend[K];
@@ -1245,6 +1298,8 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
     C.keep0 = ic->keep_flag[0];
     C.keep1 = ic->keep_flag[1];
     C.min_global_mq = ic->min_global_mq;
+    C.n_mm_type = ic->n_mm_type;
+    C.n_mm = ic->n_mm;
     C.has_rq = ic->rq_pct && ic->rq_minq;
     C.rq_minq = ic->rq_minq;
     C.rq_pct = (float)ic->rq_pct;

@@ -854,7 +854,7 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
     // path does not cover falls back, contig by contig, to the host stream
     // (a `region` is fine when it names a whole contig -- the per-chromosome calls of R/pileup.R:208-243 -- which is known
     // once the headers are read; a coordinate range goes through the host stream and the index)
-    bool use_gi = a->shard_count <= 1 && !a->umi_tag && ic.n_mm_type == 0 && ic.n_mm == 0 &&
+    bool use_gi = a->shard_count <= 1 && !a->umi_tag &&
                   !(a->region && strchr(a->region, ':')) && !getenv("RAER_SERIAL_INGEST") && !getenv("RAER_BATCH_READS");
     if (const char* e = getenv("RAER_GPU_INGEST")) use_gi = use_gi && atoi(e) != 0;
     if (use_gi) use_gi = raer::indexes_usable(a->bampaths, a->indexes, nf);

@@ -90,6 +90,9 @@ CASES = {
     "unstranded": dict(param=FilterParam(library_type="unstranded", min_depth=1)),
     "fr-second": dict(param=FilterParam(library_type="fr-second-strand", min_depth=1)),
     "no-overlap-removal": dict(param=FilterParam(remove_overlaps=False)),
+    # the MD verdict of parse_mismatches, one bit per read (the bundled BAMs carry MD tags)
+    "mismatch-filter": dict(param=FilterParam(max_mismatch_type=(1, 2), min_depth=1)),
+    "mismatch-filter-strict": dict(param=FilterParam(max_mismatch_type=(2, 2), only_keep_variants=True, library_type="unstranded")),
 }
 
 
