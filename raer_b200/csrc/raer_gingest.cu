@@ -29,6 +29,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <mutex>
+#include <queue>
 #include <string>
 #include <thread>
 #include <vector>
@@ -321,9 +322,9 @@ __global__ void k_gp_pass(const uint8_t* __restrict__ ub, const recoff_t* __rest
 
 // positions of the passing reads in their own (compact) numbering: the "previous pushed read" of read P is P - 1
 __global__ void k_gp_cpos(const uint32_t* __restrict__ pass, const uint32_t* __restrict__ pidx, const int32_t* __restrict__ r_pos,
-                          long long n_rec, int32_t* __restrict__ cpos) {
+                          const int32_t* __restrict__ r_end, long long n_rec, int32_t* __restrict__ cpos, int32_t* __restrict__ cend) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < n_rec && pass[i]) cpos[pidx[i]] = r_pos[i];
+    if (i < n_rec && pass[i]) { cpos[pidx[i]] = r_pos[i]; cend[pidx[i]] = r_end[i]; }
 }
 
 // bam_plp_push keeps a read only if it can still produce a column (end > position of the previous pushed read);
@@ -332,7 +333,8 @@ __global__ void k_gp_kept(const uint8_t* __restrict__ ub, const recoff_t* __rest
                           const uint32_t* __restrict__ pidx, const int32_t* __restrict__ r_pos, const int32_t* __restrict__ r_end,
                           const int32_t* __restrict__ cpos, long long n_rec, long long n_pass, GpConf C, int max_span,
                           uint32_t* __restrict__ kept, uint32_t* __restrict__ ncig, uint32_t* __restrict__ sqb,
-                          uint32_t* __restrict__ elig, int32_t* __restrict__ prevpos, int* flags) {
+                          uint32_t* __restrict__ elig, int32_t* __restrict__ prevpos, int* flags,
+                          const uint8_t* __restrict__ dropped) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n_rec) return;
     uint32_t k = 0, nc = 0, sb = 0, el = 0;
@@ -343,9 +345,10 @@ __global__ void k_gp_kept(const uint8_t* __restrict__ ub, const recoff_t* __rest
         pp = P > 0 ? cpos[P - 1] : INT_MIN;
         if (P > 0 && pos < pp) atomicOr(flags, 4);  // htslib: "the input is not sorted"
         k = (P == 0) || (end > pp);
+        if (dropped && dropped[P]) k = 0;  // max_depth: decided by the replay of the stream (gi_replay_max_depth)
         // max_depth (bam_plp_push drops a read that starts where the previous one did once the buffer holds more than
         // max_depth reads): reads still in the buffer all started within max_span positions in front of this one
-        if (P > 0 && pos == pp) {
+        if (!dropped && P > 0 && pos == pp) {
             long long lo = 0, hi = P;  // first passing read with position >= pos - max_span
             const int from = pos - max_span;
             while (lo < hi) {
@@ -774,7 +777,7 @@ static void pin_release(uint8_t* p) {
 // everything one file contributes to the batch of a contig, still in its own buffers
 struct FileStage {
     DBufG comp, blk, ubuf, status, sp, cnt, base, rec_off, pass, pidx, r_pos, r_end, cpos, kept, kidx, ncig, coff, sqb, soff, elig, eidx,
-        prevpos, bsum, krec, kprev, pkey, pval, pkey2, pval2, hist, queue, rec_cb, kpos, kend, kcoff, ksoff, kcb, kumi, mateK, keepend,
+        prevpos, bsum, cend, dropped, krec, kprev, pkey, pval, pkey2, pval2, hist, queue, rec_cb, kpos, kend, kcoff, ksoff, kcb, kumi, mateK, keepend,
         keepA;
     long long k_lo_prev = 0;  // windows: where the previous window's live reads began
     PinnedBuf hblk;
@@ -820,7 +823,7 @@ struct raer_gi {
         return reserved > used ? (size_t)(reserved - used) : 0;
     }
     unsigned long long* h_small = nullptr;  // pinned, 8 counters
-    int64_t launches = 0, inflated = 0, compressed = 0, records = 0, walk_retries = 0;
+    int64_t launches = 0, inflated = 0, compressed = 0, records = 0, walk_retries = 0, n_dropped = 0;
     double t_read = 0, t_table = 0, t_alloc = 0, t_inflate = 0, t_pass = 0, t_kept = 0, t_write = 0;  // host wall seconds per stage
     ~raer_gi() {
         for (FILE* f : fp) if (f) fclose(f);
@@ -927,6 +930,26 @@ static int g_scan(raer_gi* g, FileStage& S, const uint32_t* in, uint32_t* out, l
     k_sc_apply<MAX><<<nb, SC_BLOCK, 0, g->st>>>(in, n, (const uint32_t*)S.bsum.p, out);
     g->launches += 3;
     return 0;
+}
+
+// bam_plp_push's max_depth rule over the passing reads of one file and contig (pos / end in stream order): a read that
+// starts where the previous one did is dropped when the buffer already holds max_depth reads (reads that were pushed and
+// whose end has not fallen behind the iterator). Same decisions as Ingest::parse_one; a min-heap of ends instead of its
+// lazily compacted vector. Returns the number of dropped reads.
+static long long gi_replay_max_depth(const int32_t* pos, const int32_t* end, long long n, int max_depth, uint8_t* dropped) {
+    std::priority_queue<int32_t, std::vector<int32_t>, std::greater<int32_t>> live;
+    long long n_drop = 0;
+    int32_t prev = INT_MIN;
+    for (long long i = 0; i < n; ++i) {
+        if (i > 0 && pos[i] == prev && (long long)live.size() + 1 > max_depth) {
+            while (!live.empty() && live.top() < prev) live.pop();
+            if ((long long)live.size() + 1 > max_depth) { dropped[i] = 1; ++n_drop; continue; }
+        }
+        const bool kept = i == 0 || end[i] > prev;
+        prev = pos[i];
+        if (kept) live.push(end[i]);
+    }
+    return n_drop;
 }
 
 // Stage 1 for one file: compressed range -> inflated records -> record table -> prefilter -> kept reads and their sizes.
@@ -1219,7 +1242,7 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     if ((rc = S.rec_off.ensure(nr * 8)) || (rc = S.pass.ensure(nr * 4)) || (rc = S.pidx.ensure(nr * 4)) || (rc = S.r_pos.ensure(nr * 4)) ||
         (rc = S.r_end.ensure(nr * 4)) || (rc = S.cpos.ensure(nr * 4)) || (rc = S.kept.ensure(nr * 4)) || (rc = S.kidx.ensure(nr * 4)) ||
         (rc = S.ncig.ensure(nr * 4)) || (rc = S.coff.ensure(nr * 4)) || (rc = S.sqb.ensure(nr * 4)) || (rc = S.soff.ensure(nr * 4)) ||
-        (rc = S.elig.ensure(nr * 4)) || (rc = S.eidx.ensure(nr * 4)) || (rc = S.prevpos.ensure(nr * 4)) ||
+        (rc = S.elig.ensure(nr * 4)) || (rc = S.eidx.ensure(nr * 4)) || (rc = S.prevpos.ensure(nr * 4)) || (rc = S.cend.ensure(nr * 4)) ||
         (C0.sc && (rc = S.rec_cb.ensure(nr * 4))))
         return rc;
     g->t_alloc += raer::now_seconds() - t4;
@@ -1233,8 +1256,8 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
                                   (int32_t*)S.r_pos.p, (int32_t*)S.r_end.p, d_small + 2, d_flags, (int32_t*)S.rec_cb.p);
     g->launches += 2;
     if ((rc = g_scan<false>(g, S, (const uint32_t*)S.pass.p, (uint32_t*)S.pidx.p, S.n_rec, d_small + 5))) return rc;
-    k_gp_cpos<<<gr, 256, 0, st>>>((const uint32_t*)S.pass.p, (const uint32_t*)S.pidx.p, (const int32_t*)S.r_pos.p, S.n_rec,
-                                  (int32_t*)S.cpos.p);
+    k_gp_cpos<<<gr, 256, 0, st>>>((const uint32_t*)S.pass.p, (const uint32_t*)S.pidx.p, (const int32_t*)S.r_pos.p,
+                                  (const int32_t*)S.r_end.p, S.n_rec, (int32_t*)S.cpos.p, (int32_t*)S.cend.p);
     ++g->launches;
     GCK(cudaMemcpyAsync(g->h_small, d_small, 64, cudaMemcpyDeviceToHost, st));
     GCK(cudaStreamSynchronize(st));
@@ -1246,11 +1269,37 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     S.n_pass = (long long)g->h_small[5];
     g->t_pass += raer::now_seconds() - t5;
     const double t6 = raer::now_seconds();
-    k_gp_kept<<<gr, 256, 0, st>>>((const uint8_t*)S.ubuf.p, (const recoff_t*)S.rec_off.p, (const uint32_t*)S.pass.p,
-                                  (const uint32_t*)S.pidx.p, (const int32_t*)S.r_pos.p, (const int32_t*)S.r_end.p,
-                                  (const int32_t*)S.cpos.p, S.n_rec, S.n_pass, C, S.max_span, (uint32_t*)S.kept.p, (uint32_t*)S.ncig.p,
-                                  (uint32_t*)S.sqb.p, (uint32_t*)S.elig.p, (int32_t*)S.prevpos.p, d_flags);
-    ++g->launches;
+    auto launch_kept = [&](const uint8_t* dropped) {
+        k_gp_kept<<<gr, 256, 0, st>>>((const uint8_t*)S.ubuf.p, (const recoff_t*)S.rec_off.p, (const uint32_t*)S.pass.p,
+                                      (const uint32_t*)S.pidx.p, (const int32_t*)S.r_pos.p, (const int32_t*)S.r_end.p,
+                                      (const int32_t*)S.cpos.p, S.n_rec, S.n_pass, C, S.max_span, (uint32_t*)S.kept.p,
+                                      (uint32_t*)S.ncig.p, (uint32_t*)S.sqb.p, (uint32_t*)S.elig.p, (int32_t*)S.prevpos.p, d_flags,
+                                      dropped);
+        ++g->launches;
+    };
+    launch_kept(nullptr);
+    GCK(cudaMemcpyAsync(g->h_small, d_small, 64, cudaMemcpyDeviceToHost, st));
+    GCK(cudaStreamSynchronize(st));
+    if (g->h_small[1] & 4) { set_error("the input is not sorted (reads out of order)"); return RAER_ERR_IO; }
+    if (g->h_small[1] & 8) {
+        // The depth may reach max_depth somewhere on this contig. bam_plp_push then drops reads that start where the previous
+        // one did, which depends on what was dropped before: the stream is replayed -- over two integers per read, on the
+        // host -- and the verdicts go back to the device. (A dropped read also deletes the overlap entry of its name; with
+        // flags that let secondary or supplementary records through a name can have a third record that would notice: host.)
+        if (C.remove_overlaps && ((C.keep1 & 0x900u) != 0)) return RAER_GI_FALLBACK;
+        std::vector<int32_t> hp((size_t)S.n_pass), he((size_t)S.n_pass);
+        GCK(cudaMemcpyAsync(hp.data(), S.cpos.p, (size_t)S.n_pass * 4, cudaMemcpyDeviceToHost, st));
+        GCK(cudaMemcpyAsync(he.data(), S.cend.p, (size_t)S.n_pass * 4, cudaMemcpyDeviceToHost, st));
+        GCK(cudaStreamSynchronize(st));
+        std::vector<uint8_t> drop((size_t)S.n_pass, 0);
+        const long long n_drop = gi_replay_max_depth(hp.data(), he.data(), S.n_pass, C.max_depth, drop.data());
+        g->n_dropped += n_drop;
+        if ((rc = S.dropped.ensure((size_t)S.n_pass + 16))) return rc;
+        GCK(cudaMemcpyAsync(S.dropped.p, drop.data(), (size_t)S.n_pass, cudaMemcpyHostToDevice, st));
+        GCK(cudaMemsetAsync(d_flags, 0, 4, st));
+        launch_kept((const uint8_t*)S.dropped.p);
+        GCK(cudaStreamSynchronize(st));  // drop lives on this frame
+    }
     if ((rc = g_scan<false>(g, S, (const uint32_t*)S.kept.p, (uint32_t*)S.kidx.p, S.n_rec, d_small + 4)) ||
         (rc = g_scan<false>(g, S, (const uint32_t*)S.ncig.p, (uint32_t*)S.coff.p, S.n_rec, d_small + 5)) ||
         (rc = g_scan<false>(g, S, (const uint32_t*)S.sqb.p, (uint32_t*)S.soff.p, S.n_rec, d_small + 6)) ||
@@ -1258,8 +1307,6 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
         return rc;
     GCK(cudaMemcpyAsync(g->h_small, d_small, 64, cudaMemcpyDeviceToHost, st));
     GCK(cudaStreamSynchronize(st));
-    if (g->h_small[1] & 4) { set_error("the input is not sorted (reads out of order)"); return RAER_ERR_IO; }
-    if (g->h_small[1] & 8) return RAER_GI_FALLBACK;  // depth may reach max_depth: the stateful drop needs the stream replayed
     S.n_kept = (long long)g->h_small[4];
     S.n_cig = (long long)g->h_small[5];
     S.n_sq = (long long)g->h_small[6];

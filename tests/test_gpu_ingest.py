@@ -129,12 +129,23 @@ def test_device_ingest_synthetic_two_files(tmp_path, monkeypatch):
     assert dev["nrows"] > 10000
 
 
-def test_device_ingest_falls_back_where_it_must(ext, monkeypatch):
-    """max_depth within reach: the stateful drop of bam_plp_push needs the stream replayed on the host"""
+def test_max_depth_within_reach(ext, tmp_path, monkeypatch):
+    """bam_plp_push drops reads that start where the previous one did once the buffer holds max_depth reads, which depends
+    on what was dropped before: the device ingest replays that rule over (position, end) of the passing reads on the host
+    and keeps the contig on the device"""
     pc = prepare_pileup_call(ext.bam1, ext.fasta, param=FilterParam(max_depth=5))
     dev, host = _both(pc, monkeypatch)
-    assert dev["timing"]["n_host_contigs"] >= 1
+    assert dev["timing"]["n_device_contigs"] >= 1 and dev["timing"]["n_host_contigs"] == 0
     _columns_equal(dev, host)
+    full = _cabi.pileup(prepare_pileup_call(ext.bam1, ext.fasta))
+    assert dev["nrows"] > 0 and (dev["nrows"] != full["nrows"] or not np.array_equal(dev["files"][0]["nRef"], full["files"][0]["nRef"]))
+    # deep synthetic data, two files, several depth caps (coverage is about 190 per file)
+    ds = synth.make_bulk_dataset(str(tmp_path), n_bams=2, n_contigs=2, contig_len=20_000, pairs_per_contig=20_000, seed=23)
+    for md in (30, 150, 400):
+        pc = prepare_pileup_call(ds["bams"], ds["fasta"], param=FilterParam(max_depth=md, min_depth=1))
+        dev, host = _both(pc, monkeypatch)
+        assert dev["timing"]["n_device_contigs"] == 2 and dev["timing"]["n_host_contigs"] == 0
+        _columns_equal(dev, host)
 
 
 def test_records_straddling_bgzf_blocks(ext, tmp_path, monkeypatch):
