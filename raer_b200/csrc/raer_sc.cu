@@ -817,7 +817,7 @@ static int sc_run(const raer_scpileup_args* a, bool want_files, raer_sc_triplets
                         ++n_device_contigs;
                         continue;
                     }
-                    // r == 1: handed back (depth within reach of max_depth, UMIs the 2-bit code does not cover, ...)
+                    // r == 1: handed back (UMIs the 2-bit code does not cover, a name-hash collision, not enough device memory, ...)
                 }
                 raer::Ingest ing(ic);
                 if (!ing.open(one_bam, one_idx, a->host_threads, names[ci].c_str(), &jl)) { rc = RAER_ERR_IO; break; }
