@@ -36,7 +36,10 @@
 
 #include "raer_dev.h"
 #include "raer_host.h"
+#include <zlib.h>
+
 #include "raer_ginflate.cuh"
+#include "raer_inflate.h"
 #include "raer_radix.cuh"
 
 using raer::set_error;
@@ -758,6 +761,7 @@ static std::mutex g_pin_mu;
 static std::vector<uint8_t*> g_pin_pool;
 #define GI_CHUNK ((size_t)4 << 20)
 #define GI_OVERLAP ((size_t)65536 + 4096)
+#define GI_HOST_INFLATE_BYTES ((size_t)384 << 10)  // compressed ranges up to this size are inflated on the host
 static uint8_t* pin_acquire() {
     {
         std::lock_guard<std::mutex> lk(g_pin_mu);
@@ -799,6 +803,7 @@ struct raer_gi {
     cudaStream_t st = nullptr;
     int nf = 0;
     int n_sm = 148;
+    bool device_inflate_only = false;  // RAER_GI_DEVICE_INFLATE=1: tests send even tiny ranges through the inflate kernel
     uint32_t check_crc = 1;  // RAER_SKIP_CRC=1 turns the CRC-32 check of the inflated blocks off, as in the host ingest
     std::vector<GiReader> readers;
     std::vector<FILE*> fp;
@@ -894,6 +899,7 @@ extern "C" raer_gi* raer_gi_create(int device, int nf, const char* const* paths,
         return nullptr;
     }
     if (getenv("RAER_SKIP_CRC")) g->check_crc = 0;
+    if (const char* e = getenv("RAER_GI_DEVICE_INFLATE")) g->device_inflate_only = atoi(e) != 0;
     {   // per device: SM count, and the opt-in for the inflate kernel's shared memory
         int v = 0;
         if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) g->n_sm = v;
@@ -976,9 +982,84 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     const size_t nbytes = (size_t)(c_end - c_beg);
     {   // compressed bytes + inflated records (about 4x) + per-record tables + this file's share of the batch: about 8x
         size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && nbytes * 8 > free_b + g->pool_bytes()) return RAER_GI_FALLBACK;
+        if (nbytes > ((size_t)64 << 20) && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && nbytes * 8 > free_b + g->pool_bytes())
+            return RAER_GI_FALLBACK;
         cudaGetLastError();
     }
+    std::vector<GiBlock> blocks;
+    std::vector<long long> blk_c;  // file offset of every block
+    blocks.reserve(nbytes / 12000 + 64);
+    blk_c.reserve(nbytes / 12000 + 64);
+    unsigned long long u = 0;
+    size_t o = 0;  // next block header, relative to c_beg
+    // A range of a few blocks (a contig with few reads; assemblies have thousands of those) is inflated right here: one
+    // block takes the device decoder 4 ms however few there are, the host decoder a quarter of a millisecond.
+    const bool small = nbytes <= GI_HOST_INFLATE_BYTES && !g->device_inflate_only;
+    if (small) {
+        const double t0s = raer::now_seconds();
+        std::vector<uint8_t> cb(nbytes + 64, 0);
+        size_t got = 0;
+        while (got < nbytes) {
+            const ssize_t r = pread(fileno(g->fp[(size_t)f]), cb.data() + got, nbytes - got, (off_t)(c_beg + (long long)got));
+            if (r <= 0) break;
+            got += (size_t)r;
+        }
+        if (got != nbytes) { set_error("read error in BAM file"); return RAER_ERR_IO; }
+        std::vector<uint32_t> crcs;
+        while ((long long)o + c_beg <= c_last) {
+            if (o + 18 > nbytes) { set_error("truncated BGZF file (the index points beyond the end of the file)"); return RAER_ERR_IO; }
+            const uint8_t* h = cb.data() + o;
+            if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { set_error("corrupt BGZF block header"); return RAER_ERR_IO; }
+            const int xlen = h[10] | (h[11] << 8);
+            if (o + 12 + (size_t)xlen > nbytes) { set_error("truncated BGZF file (incomplete block at the end)"); return RAER_ERR_IO; }
+            int bsize = -1;
+            for (int e = 0; e + 4 <= xlen;) {
+                const int slen = h[12 + e + 2] | (h[12 + e + 3] << 8);
+                if (h[12 + e] == 'B' && h[13 + e] == 'C' && slen == 2) bsize = h[12 + e + 4] | (h[12 + e + 5] << 8);
+                e += 4 + slen;
+            }
+            if (bsize < 0 || bsize + 1 < 12 + xlen + 2 + 8) { set_error("corrupt BGZF block (BSIZE)"); return RAER_ERR_IO; }
+            if (o + (size_t)bsize + 1 > nbytes) { set_error("truncated BGZF file (incomplete block at the end)"); return RAER_ERR_IO; }
+            const uint32_t isize = h_le32(h + bsize + 1 - 4);
+            if (isize > 65536u) { set_error("corrupt BGZF block (ISIZE above 64 KiB)"); return RAER_ERR_IO; }
+            GiBlock b;
+            b.c_off = o + 12 + (size_t)xlen;
+            b.c_len = (uint32_t)(bsize + 1 - 12 - xlen - 8);
+            b.u_off = u;
+            b.u_len = isize;
+            b.crc = h_le32(h + bsize + 1 - 8);
+            b.check_crc = g->check_crc;
+            blocks.push_back(b);
+            blk_c.push_back(c_beg + (long long)o);
+            u += isize;
+            o += (size_t)bsize + 1;
+        }
+        if (blocks.empty()) return RAER_OK;
+        if (!S.hblk.ensure((size_t)u + 64)) { set_error("pinned allocation failed"); return RAER_ERR_CUDA; }
+        for (const GiBlock& b : blocks) {
+            if (!b.u_len) continue;
+            uint8_t* dst = S.hblk.p + b.u_off;
+            bool ok = raer::inflate_raw(cb.data() + b.c_off, b.c_len, dst, b.u_len) == 0;
+            if (!ok) {  // what the own decoder refuses goes to zlib, as in the host ingest
+                z_stream zs;
+                memset(&zs, 0, sizeof(zs));
+                if (inflateInit2(&zs, -15) == Z_OK) {
+                    zs.next_in = cb.data() + b.c_off;
+                    zs.avail_in = b.c_len;
+                    zs.next_out = dst;
+                    zs.avail_out = b.u_len;
+                    ok = inflate(&zs, Z_FINISH) == Z_STREAM_END && zs.avail_out == 0;
+                    inflateEnd(&zs);
+                }
+            }
+            if (!ok) { set_error("inflate failed (corrupt BGZF block)"); return RAER_ERR_IO; }
+            if (b.check_crc && (uint32_t)crc32(0L, dst, b.u_len) != b.crc) { set_error("inflate failed (BGZF block CRC32 mismatch)"); return RAER_ERR_IO; }
+        }
+        if ((rc = S.ubuf.ensure((size_t)u + 64)) || (rc = g->small.ensure(256))) return rc;
+        memset(S.hblk.p + u, 0, 64);
+        GCK(cudaMemcpyAsync(S.ubuf.p, S.hblk.p, (size_t)u + 64, cudaMemcpyHostToDevice, st));
+        g->t_read += raer::now_seconds() - t0s;
+    } else {
     // The range is read in chunks of 8 MB by a few threads. Each has one small pinned buffer and a stream of its own:
     // pread -> H2D copy -> (in chunk order) the BGZF block headers of its chunk, 18 bytes each, chained through BSIZE. A
     // chunk is read with 64 KiB of overlap so that every block that starts in it is complete. This thread collects the
@@ -999,12 +1080,6 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     GCK(cudaStreamSynchronize(st));  // the readers copy on their own streams
     g->t_alloc += raer::now_seconds() - t0;
     const double t1 = raer::now_seconds();
-    std::vector<GiBlock> blocks;
-    std::vector<long long> blk_c;  // file offset of every block
-    blocks.reserve(nbytes / 12000 + 64);
-    blk_c.reserve(nbytes / 12000 + 64);
-    unsigned long long u = 0;
-    size_t o = 0;            // next block header, relative to c_beg
     int turn = 0;            // chunk whose headers are scanned next
     bool scan_done = false;  // the block that holds the last record of the contig has been seen
     int fail = 0;
@@ -1159,6 +1234,7 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
         if ((rc = launch_inflate(0, blocks.size(), blocks.data()))) return rc;
         GCK(cudaStreamSynchronize(st));
     }
+    }  // device inflate
     S.u_total = u;
     g->compressed += (int64_t)o;
     g->inflated += (int64_t)u;
@@ -1207,8 +1283,8 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     unsigned long long* d_small = (unsigned long long*)g->small.p;  // [1] flags, [2] aligned bases, [3] max span, [4..] totals
     // ---- record table
     int* d_flags = (int*)(d_small + 1);
-    std::vector<int> status(blocks.size());
-    GCK(cudaMemcpyAsync(status.data(), S.status.p, blocks.size() * 4, cudaMemcpyDeviceToHost, st));
+    std::vector<int> status(small ? 0 : blocks.size());  // verdicts of the inflate kernel (a host-inflated range has been checked)
+    if (!small) GCK(cudaMemcpyAsync(status.data(), S.status.p, blocks.size() * 4, cudaMemcpyDeviceToHost, st));
     for (int attempt = try_blocks ? 0 : 1; attempt < 2; ++attempt) {
         std::vector<unsigned long long>& pts = attempt == 0 ? sp_blk : sp_lin;
         nsp = (int)pts.size() - 1;
