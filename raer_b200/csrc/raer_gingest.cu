@@ -597,9 +597,13 @@ struct GpOut {  // the batch arrays (device) of a window and where this file's s
     long long r0, c0, s0;
 };
 
-// one thread per kept read K in [k_lo, k_hi): header, CIGAR words, packed sequence, qualities, mate link
+// eight lanes per kept read K in [k_lo, k_hi): header, CIGAR words, packed sequence, qualities, mate link. The copies are
+// byte-wise (records lie at arbitrary offsets); spreading them over eight lanes cuts the chain of dependent accesses a
+// single thread per read would walk (measured with one thread per read: 1.17 ms per 10^6 reads at 3 % issue utilisation)
+#define GB_LANES 8
 __global__ void k_gp_batch(const uint8_t* __restrict__ ub, GpMeta M, long long k_lo, long long k_hi, GpConf C, GpOut O) {
-    const long long K = k_lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long K = k_lo + (blockIdx.x * (long long)blockDim.x + threadIdx.x) / GB_LANES;
+    const int sub = (int)(threadIdx.x & (GB_LANES - 1));
     if (K >= k_hi) return;
     const uint8_t* p = ub + M.krec[K] + 4;
     const int l_qname = p[8], mapq = p[9];
@@ -646,21 +650,21 @@ __global__ void k_gp_batch(const uint8_t* __restrict__ ub, GpMeta M, long long k
     h.sq_off = (uint32_t)so_;
     h.mate = paired ? (int32_t)(O.r0 + (mk - k_lo)) : -1;
     h.aux = (uint32_t)bi;  // its own batch index, like the host packer (bulk UMI mode never comes here)
-    O.hdr[bi] = h;
-    if (paired) O.pair_b[atomicAdd(O.n_pairs, 1ull)] = (int32_t)bi;
+    if (sub == 0) {
+        O.hdr[bi] = h;
+        if (paired) O.pair_b[atomicAdd(O.n_pairs, 1ull)] = (int32_t)bi;
+        if (C.sc) {
+            O.cb[bi] = M.kcb[K];
+            O.umi[bi] = M.kumi[K];
+        }
+    }
     uint32_t* co = O.cigar + co_;
-    for (int k = 0; k < n_cigar; ++k) co[k] = ld32u(cg + 4 * k);
+    for (int k = sub; k < n_cigar; k += GB_LANES) co[k] = ld32u(cg + 4 * k);
     const int nsb = (l_qseq + 1) >> 1, padded = (nsb + 3) & ~3;
     uint8_t* so = O.seq + so_;
-    for (int k = 0; k < nsb; ++k) so[k] = sq[k];
-    for (int k = nsb; k < padded; ++k) so[k] = 0xff;
+    for (int k = sub; k < padded; k += GB_LANES) so[k] = k < nsb ? sq[k] : (uint8_t)0xff;
     uint8_t* qo = O.qual + 2 * so_;
-    for (int k = 0; k < l_qseq; ++k) qo[k] = ql[k];
-    for (int k = l_qseq; k < 2 * padded; ++k) qo[k] = 0;
-    if (C.sc) {
-        O.cb[bi] = M.kcb[K];
-        O.umi[bi] = M.kumi[K];
-    }
+    for (int k = sub; k < 2 * padded; k += GB_LANES) qo[k] = k < l_qseq ? ql[k] : (uint8_t)0;
 }
 
 // ------------------------------------------------------------------------------------- host side
@@ -1730,7 +1734,7 @@ extern "C" int raer_gi_window(raer_gi* g, int j, raer_read_batch* b, int64_t* fi
         O.r0 = file_off[f];
         O.c0 = c_of[(size_t)f];
         O.s0 = s_of[(size_t)f];
-        k_gp_batch<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint8_t*)S.ubuf.p, gi_meta(S), k_lo[(size_t)f], k_hi[(size_t)f],
+        k_gp_batch<<<(unsigned)((n * GB_LANES + 255) / 256), 256, 0, st>>>((const uint8_t*)S.ubuf.p, gi_meta(S), k_lo[(size_t)f], k_hi[(size_t)f],
                                                                g->fconf[(size_t)f], O);
         ++g->launches;
     }
