@@ -268,14 +268,29 @@ def last_error() -> str:
 
 
 def _strs(xs):
-    arr = (C.c_char_p * max(len(xs), 1))()
+    """char** of the strings (None -> NULL). Site lists repeat a few contig names millions of times: every distinct string
+    is encoded once and the pointer array is gathered with numpy (a ctypes array built element by element costs about a
+    microsecond per entry)."""
+    table, keepalive, addr = {}, [], []
+    codes = np.empty(len(xs), dtype=np.int64)
+    get = table.get
     for i, x in enumerate(xs):
-        arr[i] = None if x is None else (x.encode() if isinstance(x, str) else x)
-    return arr
+        k = get(x)
+        if k is None:
+            b = x if (x is None or isinstance(x, bytes)) else x.encode()
+            k = table[x] = len(addr)
+            keepalive.append(b)
+            addr.append(0 if b is None else C.cast(C.c_char_p(b), C.c_void_p).value)
+        codes[i] = k
+    arr = np.asarray(addr, dtype=np.uint64)[codes] if len(xs) else np.zeros(1, dtype=np.uint64)
+    p = C.cast(arr.ctypes.data, C.POINTER(C.c_char_p))
+    p._keep = (arr, keepalive)  # the pointer array and the encoded strings live as long as the pointer object
+    return p
 
 
 def _ints(xs):
-    return (C.c_int32 * max(len(xs), 1))(*[int(x) for x in xs])
+    a = np.ascontiguousarray(xs, dtype=np.int32) if len(xs) else np.zeros(1, dtype=np.int32)
+    return (C.c_int32 * max(len(xs), 1)).from_buffer_copy(a.tobytes()) if len(xs) else (C.c_int32 * 1)()
 
 
 LAST_TIMING = {}

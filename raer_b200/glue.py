@@ -13,6 +13,7 @@ import os
 import struct
 import warnings
 import zlib
+import numpy as np
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -129,9 +130,12 @@ class Sites:
     alt: Optional[Sequence[str]] = None
 
     def __post_init__(self):
+        def ints(v):  # plain Python ints (numpy arrays and lists of numpy scalars included) without a Python-level loop
+            return np.asarray(v, dtype=np.int64).tolist() if len(v) else []
+
         self.seqnames = list(self.seqnames)
-        self.start = [int(x) for x in self.start]
-        self.end = list(self.start) if self.end is None else [int(x) for x in self.end]
+        self.start = ints(self.start)
+        self.end = list(self.start) if self.end is None else ints(self.end)
         n = len(self.seqnames)
         if self.strand is None:
             self.strand = ["*"] * n
@@ -143,8 +147,10 @@ class Sites:
         return len(self.seqnames)
 
     def subset(self, keep: Sequence[bool]) -> "Sites":
-        idx = [i for i, k in enumerate(keep) if k]
-        pick = lambda v: None if v is None else [v[i] for i in idx]  # noqa: E731
+        from itertools import compress
+
+        keep = [bool(k) for k in keep] if not isinstance(keep, list) else keep
+        pick = lambda v: None if v is None else list(compress(v, keep))  # noqa: E731
         return Sites(pick(self.seqnames), pick(self.start), pick(self.end), pick(self.strand), pick(self.ref),
                      pick(self.alt))
 
