@@ -373,6 +373,11 @@ int raer_gpu_inflate(const uint8_t* comp, int64_t comp_len, const int64_t* c_off
  * page-locked staging buffers, for the next call of the process. This hands both back to the driver (e.g. from the
  * unload hook of a binding). */
 void raer_trim_device_cache(int32_t device);
+/* bam_plp_push's max_depth rule over the passing reads of one file and contig in stream order (pos / end, 0-based, end
+ * exclusive): dropped[i] = 1 for the reads htslib drops (a read that starts where the previous one did while the buffer
+ * holds max_depth reads). Host only; what the device ingest runs when the depth can reach max_depth. Returns the number
+ * of dropped reads. */
+int64_t raer_replay_max_depth(const int32_t* pos, const int32_t* end, int64_t n, int32_t max_depth, uint8_t* dropped);
 /* same batch entry as raer_batch_pileup_device(), rows downloaded (what the device ingest calls per contig) */
 int raer_batch_pileup_device_rows(raer_ctx* ctx, const raer_bulk_conf* conf, const raer_read_batch* dev_batch, raer_rows* out,
                                   int64_t* launches);

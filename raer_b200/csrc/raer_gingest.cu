@@ -962,6 +962,12 @@ static long long gi_replay_max_depth(const int32_t* pos, const int32_t* end, lon
     return n_drop;
 }
 
+// the replay as a C-ABI entry (host only, no device needed): tests hold it to a literal restatement of the rule
+extern "C" int64_t raer_replay_max_depth(const int32_t* pos, const int32_t* end, int64_t n, int32_t max_depth, uint8_t* dropped) {
+    memset(dropped, 0, (size_t)n);
+    return gi_replay_max_depth(pos, end, n, max_depth, dropped);
+}
+
 // Stage 1 for one file: compressed range -> inflated records -> record table -> prefilter -> kept reads and their sizes.
 // Returns RAER_OK, RAER_GI_FALLBACK or an error.
 static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {

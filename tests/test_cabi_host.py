@@ -195,3 +195,33 @@ def test_documented_limit_is_refused_before_any_work(ext):
     pc = prepare_pileup_call(ext.bam1, ext.fasta, param=FilterParam(min_base_quality=200))
     with pytest.raises(_cabi.RaerError, match="needs min_base_quality <= 128"):
         _cabi.pileup(pc, aei=True)
+
+
+def test_max_depth_replay_matches_the_literal_rule():
+    """raer_replay_max_depth (what the device ingest runs when the depth can reach max_depth) against bam_plp_push's rule
+    written out with a plain list: a read that starts where the previous pushed read did is dropped while the buffer
+    (pushed reads whose end has not fallen behind the iterator) holds max_depth reads"""
+    L = _cabi.lib()
+    L.raer_replay_max_depth.restype = C.c_int64
+    L.raer_replay_max_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    rng = np.random.default_rng(9)
+    for trial in range(40):
+        n = int(rng.integers(1, 400))
+        pos = np.sort(rng.integers(0, max(2, n // int(rng.integers(1, 8))), n)).astype(np.int32)
+        end = (pos + rng.integers(0, 12, n)).astype(np.int32)  # zero-length reads included
+        md = int(rng.integers(1, 12))
+        want = np.zeros(n, dtype=np.uint8)
+        live, prev = [], None
+        for i in range(n):
+            if prev is not None and pos[i] == prev and len(live) + 1 > md:
+                live = [e for e in live if e >= prev]
+                if len(live) + 1 > md:
+                    want[i] = 1
+                    continue
+            kept = prev is None or end[i] > prev
+            prev = pos[i]
+            if kept:
+                live.append(end[i])
+        got = np.ones(n, dtype=np.uint8)
+        nd = L.raer_replay_max_depth(pos.ctypes.data, end.ctypes.data, n, md, got.ctypes.data)
+        assert np.array_equal(got, want) and nd == int(want.sum())
