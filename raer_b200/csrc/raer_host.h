@@ -241,7 +241,10 @@ struct FilePending {
     QnameTable olap;
     // ends of the reads pushed on the current contig; entries below the iterator position are dead and are
     // dropped lazily (the count is only needed when a read starts where the previous one did)
-    std::vector<int32_t> live_ends;
+    // ends of the pushed reads that can still be in htslib's pileup buffer, smallest on top: the max_depth rule asks how
+    // many have not fallen behind a position that never moves backwards, so stale ends are popped when it is asked
+    // (a vector that was compacted at every check cost max_depth steps per read at a locus deeper than max_depth)
+    std::priority_queue<int32_t, std::vector<int32_t>, std::greater<int32_t>> live_ends;
     size_t live_compact_at = 4096;
     int live_tid = -1;
     int64_t n_aligned_bases = 0;

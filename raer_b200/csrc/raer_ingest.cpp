@@ -886,15 +886,14 @@ bool Ingest::parse_one(int fi) {
 
         // ---- stream-order decisions of bam_plp_push
         if (F.live_tid != r.tid) {
-            F.live_ends.clear();
+            F.live_ends = decltype(F.live_ends)();
             F.live_tid = r.tid;
         }
         // the mempool count of bam_plp_push: reads still in the buffer (end >= position of the last pushed read) + 1.
         // It only matters for a read that starts where the previous one did, and only once that many were pushed.
         if (F.prev_tid == r.tid && F.prev_pos == r.pos && (int64_t)F.live_ends.size() + 1 > conf_.max_depth) {
             const int32_t lim = F.prev_pos;
-            F.live_ends.erase(std::remove_if(F.live_ends.begin(), F.live_ends.end(), [lim](int32_t e) { return e < lim; }),
-                              F.live_ends.end());
+            while (!F.live_ends.empty() && F.live_ends.top() < lim) F.live_ends.pop();
             if ((int64_t)F.live_ends.size() + 1 > conf_.max_depth) {
                 if (conf_.remove_overlaps) {
                     const size_t qn = strlen(r.qname);
@@ -1050,11 +1049,10 @@ bool Ingest::parse_one(int fi) {
         H.h.bits = bits;
         F.prev_tid = r.tid;
         F.prev_pos = r.pos;
-        F.live_ends.push_back(H.h.end);
+        F.live_ends.push(H.h.end);
         if (F.live_ends.size() > F.live_compact_at) {  // every later check asks for ends >= a position >= this one
             const int32_t lim = r.pos;
-            F.live_ends.erase(std::remove_if(F.live_ends.begin(), F.live_ends.end(), [lim](int32_t e) { return e < lim; }),
-                              F.live_ends.end());
+            while (!F.live_ends.empty() && F.live_ends.top() < lim) F.live_ends.pop();
             F.live_compact_at = std::max<size_t>(4096, 2 * F.live_ends.size());
         }
         if (conf_.sc) {

@@ -225,3 +225,32 @@ def test_max_depth_replay_matches_the_literal_rule():
         got = np.ones(n, dtype=np.uint8)
         nd = L.raer_replay_max_depth(pos.ctypes.data, end.ctypes.data, n, md, got.ctypes.data)
         assert np.array_equal(got, want) and nd == int(want.sum())
+
+
+def test_ingest_max_depth_drop(ext, monkeypatch):
+    """the host ingest's max_depth rule (min-heap of live ends) counted against the replay entry and bam_plp_push's
+    keep rule, per contig"""
+    L = _cabi.lib()
+    L.raer_replay_max_depth.restype = C.c_int64
+    L.raer_replay_max_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    monkeypatch.setenv("RAER_SERIAL_INGEST", "1")
+    for md in (3, 5, 12):
+        pc = prepare_pileup_call(ext.bam1, ext.fasta, param=FilterParam(max_depth=md))
+        s = _ingest(pc)
+        passing, _, _ = _expected_kept(ext.bam1, pc.int_args[12], pc.int_args[13])
+        expected = 0
+        for tid in sorted({r.tid for r in passing}):
+            rs = [r for r in passing if r.tid == tid]
+            pos = np.array([r.pos for r in rs], dtype=np.int32)
+            end = np.array([r.pos + r.ref_len() for r in rs], dtype=np.int32)
+            drop = np.zeros(len(rs), dtype=np.uint8)
+            L.raer_replay_max_depth(pos.ctypes.data, end.ctypes.data, len(rs), md, drop.ctypes.data)
+            prev = None
+            for i in range(len(rs)):
+                if drop[i]:
+                    continue
+                expected += prev is None or end[i] > prev
+                prev = pos[i]
+        assert s["distinct"] == expected
+        if md == 3:
+            assert expected < len(passing) - 20  # the rule bites at this depth
