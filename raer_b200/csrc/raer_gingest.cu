@@ -182,6 +182,7 @@ struct GpConf {
     // of FNV-1a name hashes, strings compared on a hit), or every read of the file belongs to one column (Smart-seq2)
     int sc, has_cb_tag, has_umi_tag, fixed_cb;
     int n_mm_type, n_mm;               // mismatch filter (max_mismatch_type): the MD verdict is one bit per read
+    int reg_on, reg_beg, reg_end;      // a coordinate range of the contig: only the reads that overlap [reg_beg, reg_end)
     uint8_t cb_tag[2], umi_tag[2];
     const unsigned long long* wl_key;  // 0 = empty slot
     const int32_t* wl_col;             // 1-based whitelist column
@@ -267,6 +268,10 @@ __global__ void k_gp_pass(const uint8_t* __restrict__ ub, const recoff_t* __rest
         const int op = (int)(w & 0xf);
         if ((0x3C1A7 >> (op << 1)) & 2) rlen += (int)(w >> 4);
         if (op == 0 || op == 7 || op == 8) nal += (w >> 4);
+    }
+    if (C.reg_on) {  // what the region iterator hands out (sam_itr_next): reads that start before the end and reach the begin
+        const int span = ((flag & 4) || n_cigar == 0 || rlen == 0) ? 1 : rlen;
+        if (!(pos < C.reg_end && pos + span > C.reg_beg)) ok = 0;
     }
     {   // unit of the bench metric: aligned bases of every mapped record, before filters; longest reference span
         const unsigned am = __activemask();
@@ -820,7 +825,7 @@ struct raer_gi {
     // the contig being served: position windows [win[j], win[j + 1]) and what a window's batch needs
     std::vector<int> win;
     std::vector<GpConf> fconf;  // per file (library type, contig number)
-    int cur_tid = -1, cur_len = 0;
+    int cur_tid = -1, cur_len = 0, cur_beg = 0;  // rows of [cur_beg, cur_len) are wanted
     bool cur_sc = false;
     int64_t cur_bases = 0;
     size_t pool_bytes() const {  // what the device pool holds for reuse (freed buffers of earlier contigs count as free memory)
@@ -970,7 +975,7 @@ extern "C" int64_t raer_replay_max_depth(const int32_t* pos, const int32_t* end,
 
 // Stage 1 for one file: compressed range -> inflated records -> record table -> prefilter -> kept reads and their sizes.
 // Returns RAER_OK, RAER_GI_FALLBACK or an error.
-static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
+static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0, bool to_contig_end = false) {
     FileStage& S = g->stage[(size_t)f];
     S.n_rec = S.n_pass = S.n_kept = S.n_cig = S.n_sq = S.n_elig = 0;
     S.aligned_bases = 0;
@@ -980,10 +985,30 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     if (R.vend <= R.vbeg) return RAER_OK;  // no records of this contig in this file
     cudaStream_t st = g->st;
     int rc;
-    // ---- compressed bytes of the contig: from the block of the first record to the block its last record ends in
-    const long long c_beg = (long long)(R.vbeg >> 16);
-    long long c_last = (long long)(R.vend >> 16);
-    if ((R.vend & 0xffff) == 0) c_last -= 1;  // the range ends exactly where a block starts: that block is not needed
+    // ---- the virtual-offset range to read: the whole contig, or -- for a coordinate range -- from the linear-index entry of
+    // the 16 kb window the range begins in (the first record that reaches that window, like sam_itr_querys) to the entry of
+    // a window behind its end. The records are sorted by position, so the range holds every read that starts before
+    // reg_end if the first record behind it starts at or after reg_end: that record is looked at once the blocks are
+    // inflated (peek), and if it does not, the stage is redone to the end of the contig.
+    uint64_t vb = R.vbeg, ve = R.vend;
+    bool peek = false;
+    if (C0.reg_on) {
+        const size_t n_intv = R.lin.size();
+        if (n_intv) {
+            size_t w = std::min<size_t>((size_t)(std::max(C0.reg_beg, 0) >> 14), n_intv - 1);
+            uint64_t v = R.lin[w];
+            while (v == 0 && w > 0) v = R.lin[--w];
+            if (v > vb && v < ve) vb = v;
+        }
+        if (!to_contig_end && C0.reg_end < INT_MAX - (1 << 16)) {
+            for (size_t k = (size_t)(C0.reg_end >> 14) + 2; k < n_intv; ++k)
+                if (R.lin[k] > vb && R.lin[k] < ve) { ve = R.lin[k]; peek = true; break; }
+        }
+    }
+    // ---- compressed bytes of the range: from the block of the first record to the block its last record ends in
+    const long long c_beg = (long long)(vb >> 16);
+    long long c_last = (long long)(ve >> 16);
+    if ((ve & 0xffff) == 0 && !peek) c_last -= 1;  // the range ends exactly where a block starts: that block is not needed
     long long c_end = std::min<long long>(c_last + 65536 + 32, g->fsize[(size_t)f]);
     if (c_end <= c_beg || c_last >= g->fsize[(size_t)f]) {  // the index describes records the file does not hold
         set_error("truncated BGZF file (the index points beyond the end of the file)");
@@ -1261,8 +1286,8 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
         return true;
     };
     unsigned long long u_first = 0, u_last = u;
-    if (!v2u(R.vbeg, &u_first)) return RAER_GI_FALLBACK;
-    if (!v2u(R.vend, &u_last)) u_last = u;
+    if (!v2u(vb, &u_first)) return RAER_GI_FALLBACK;
+    if (!v2u(ve, &u_last)) { if (peek) return gi_file_stage(g, f, ftid, C0, true); u_last = u; }
     // Start points of the record walk. htslib-style writers never let a record straddle two BGZF blocks (bgzf_flush_try
     // before every record), so every block start is a record start: try those first -- the walk verifies the guess,
     // every chain has to land exactly on the next start point -- and fall back to the linear index of the .bai, whose
@@ -1274,7 +1299,7 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     sp_lin.push_back(u_first);
     for (uint64_t v : R.lin) {
         unsigned long long x;
-        if (v > R.vbeg && v < R.vend && v2u(v, &x) && x > u_first && x < u_last) sp_lin.push_back(x);
+        if (v > vb && v < ve && v2u(v, &x) && x > u_first && x < u_last) sp_lin.push_back(x);
     }
     std::sort(sp_lin.begin(), sp_lin.end());
     sp_lin.erase(std::unique(sp_lin.begin(), sp_lin.end()), sp_lin.end());
@@ -1319,6 +1344,15 @@ static int gi_file_stage(raer_gi* g, int f, int ftid, const GpConf& C0) {
     if (!try_blocks)
         for (size_t k = 0; k < status.size(); ++k)
             if (status[k] != 0) { set_error("inflate failed (corrupt BGZF block, device code %d)", status[k]); return RAER_ERR_IO; }
+    if (peek) {  // the first record behind the range has to start at or after the end of the coordinate range
+        uint8_t hd[12];
+        bool ok = u_last + 12 <= u;
+        if (ok) {
+            GCK(cudaMemcpy(hd, (const uint8_t*)S.ubuf.p + u_last, 12, cudaMemcpyDeviceToHost));
+            ok = (int)h_le32(hd + 4) == ftid && (int)h_le32(hd + 8) >= C0.reg_end;
+        }
+        if (!ok) return gi_file_stage(g, f, ftid, C0, true);
+    }
     S.n_rec = (long long)g->h_small[4];
     g->records += S.n_rec;
     g->t_inflate += raer::now_seconds() - t3;
@@ -1417,8 +1451,8 @@ static GpMeta gi_meta(FileStage& S) {
 // *site_mask_dev is the device bitmap of the listed positions (nullptr without a list). *n_windows batches are then
 // fetched with raer_gi_window(), in order.
 extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_len, const raer::IngestConf* ic,
-                              const raer::RegionIndex::Chr* site, int* n_windows, const uint32_t** site_mask_dev,
-                              int64_t* aligned_bases) {
+                              const raer::RegionIndex::Chr* site, int reg_beg, int reg_end, int* n_windows,
+                              const uint32_t** site_mask_dev, int64_t* aligned_bases) {
     cudaSetDevice(g->device);
     cudaStream_t st = g->st;
     t_alloc_stream = st;
@@ -1433,6 +1467,9 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
     C.min_global_mq = ic->min_global_mq;
     C.n_mm_type = ic->n_mm_type;
     C.n_mm = ic->n_mm;
+    C.reg_on = reg_beg > 0 || reg_end < contig_len;  // [reg_beg, reg_end) = [0, INT_MAX) for a whole contig
+    C.reg_beg = reg_beg;
+    C.reg_end = reg_end;
     C.has_rq = ic->rq_pct && ic->rq_minq;
     C.rq_minq = ic->rq_minq;
     C.rq_pct = (float)ic->rq_pct;
@@ -1526,7 +1563,8 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
         *aligned_bases += S.aligned_bases;
     }
     g->cur_tid = tid;
-    g->cur_len = contig_len;
+    g->cur_len = std::min(contig_len, reg_end);
+    g->cur_beg = std::max(reg_beg, 0);
     g->cur_sc = ic->sc;
     g->cur_bases = *aligned_bases;
     if (n_reads == 0) return RAER_OK;
@@ -1582,7 +1620,7 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
     unsigned long long budget = 3ull << 29;  // packed sequence bytes per window, all files (the offsets are 31 bits)
     if (const char* e = getenv("RAER_GI_WINDOW_BYTES")) budget = std::max<unsigned long long>(4096, strtoull(e, nullptr, 10));
     const int n_cut = (int)std::min<unsigned long long>((sq_total + budget - 1) / budget, 1u << 20);
-    g->win.push_back(0);
+    g->win.push_back(g->cur_beg);
     if (n_cut > 1) {
         FileStage& S = g->stage[(size_t)f_max];
         const GpMeta M = gi_meta(S);
@@ -1592,11 +1630,11 @@ extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_l
             GCK(cudaMemcpyAsync(g->h_small, d_small + 8, 8, cudaMemcpyDeviceToHost, st));
             GCK(cudaStreamSynchronize(st));
             const unsigned long long w = g->h_small[0];
-            if (w != ~0ull && (int)w > g->win.back() && (int)w < contig_len) g->win.push_back((int)w);
+            if (w != ~0ull && (int)w > g->win.back() && (int)w < g->cur_len) g->win.push_back((int)w);
         }
         g->launches += n_cut - 1;
     }
-    g->win.push_back(std::max(contig_len, g->win.back() + 1));
+    g->win.push_back(std::max(g->cur_len, g->win.back() + 1));
     if (g->win.size() > 2) {
         // the boundaries follow one file: make sure no window is too large over ALL files (a window that is gets cut in half,
         // before any row of the contig is out)

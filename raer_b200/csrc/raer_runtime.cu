@@ -40,8 +40,8 @@ struct raer_gi;
 extern "C" raer_gi* raer_gi_create(int device, int nf, const char* const* paths, const char* const* indexes);
 extern "C" void raer_gi_destroy(raer_gi* g);
 extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_len, const raer::IngestConf* ic,
-                              const raer::RegionIndex::Chr* site, int* n_windows, const uint32_t** site_mask_dev,
-                              int64_t* aligned_bases);
+                              const raer::RegionIndex::Chr* site, int reg_beg, int reg_end, int* n_windows,
+                              const uint32_t** site_mask_dev, int64_t* aligned_bases);
 extern "C" int raer_gi_window(raer_gi* g, int j, raer_read_batch* b, int64_t* file_off);
 extern "C" void raer_gi_stats(raer_gi* g, int64_t* launches, int64_t* inflated, int64_t* compressed, int64_t* records);
 
@@ -854,8 +854,7 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
     // path does not cover falls back, contig by contig, to the host stream
     // (a `region` is fine when it names a whole contig -- the per-chromosome calls of R/pileup.R:208-243 -- which is known
     // once the headers are read; a coordinate range goes through the host stream and the index)
-    bool use_gi = a->shard_count <= 1 && !a->umi_tag &&
-                  !(a->region && strchr(a->region, ':')) && !getenv("RAER_SERIAL_INGEST") && !getenv("RAER_BATCH_READS");
+    bool use_gi = a->shard_count <= 1 && !a->umi_tag && !getenv("RAER_SERIAL_INGEST") && !getenv("RAER_BATCH_READS");
     if (const char* e = getenv("RAER_GPU_INGEST")) use_gi = use_gi && atoi(e) != 0;
     if (use_gi) use_gi = raer::indexes_usable(a->bampaths, a->indexes, nf);
     // The device ingest reads the byte ranges the index names and nothing else, so a file that lost its tail would go
@@ -872,14 +871,29 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
     }
 
     double tm_open = raer::now_seconds();
-    int gi_only_contig = -1;
+    int gi_only_contig = -1, gi_reg_beg = 0, gi_reg_end = INT_MAX;
     if (use_gi && a->region) {
         raer::Ingest probe(ic);
         if (!probe.open_headers(a->bampaths)) return RAER_ERR_IO;
         const std::vector<std::string>& hn = probe.names();
         for (size_t k = 0; k < hn.size() && gi_only_contig < 0; ++k)
             if (hn[k] == a->region) gi_only_contig = (int)k;
-        if (gi_only_contig < 0) use_gi = false;  // not a plain contig name: the host path parses (or refuses) it
+        if (gi_only_contig < 0) {
+            // "contig:beg-end" (hts_parse_reg: the name is what stands before the last colon). A wide range -- a tile of a
+            // contig cut for several GPUs, R/pileup.R:208-243 with ranges -- is worth the device path; a narrow one reads
+            // a handful of blocks through the index on the host.
+            int rb = 0, re = INT_MAX;
+            const int nl = raer::parse_region(a->region, &rb, &re);
+            long min_span = 1 << 18;
+            if (const char* e = getenv("RAER_GI_REGION_MIN")) min_span = atol(e);
+            if (nl > 0 && (long)re - rb >= min_span) {
+                const std::string nm(a->region, (size_t)nl);
+                for (size_t k = 0; k < hn.size() && gi_only_contig < 0; ++k)
+                    if (hn[k] == nm) gi_only_contig = (int)k;
+                if (gi_only_contig >= 0) { gi_reg_beg = rb; gi_reg_end = re; }
+            }
+        }
+        if (gi_only_contig < 0) use_gi = false;  // the host path parses (or refuses) it
     }
     raer::Ingest ing(ic);
     // the device ingest reads the files itself: only the headers are needed here
@@ -1007,7 +1021,9 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             raer::Ingest wi(ic);
             std::vector<std::pair<int32_t, int32_t>> jl;
             if (has_ridx) jl = raer::jump_intervals(ridx.find(names[c]));
-            if (!wi.open(a->bampaths, a->indexes, a->host_threads, names[c].c_str(), has_ridx ? &jl : nullptr)) return RAER_ERR_IO;
+            const bool ranged = gi_reg_beg > 0 || gi_reg_end < INT_MAX;  // a coordinate range: the call's own region string
+            if (!wi.open(a->bampaths, a->indexes, a->host_threads, ranged ? a->region : names[c].c_str(), has_ridx ? &jl : nullptr))
+                return RAER_ERR_IO;
             raer::PackedBatch pb;
             int r = RAER_OK;
             while (r == RAER_OK && wi.next_contig() >= 0) {
@@ -1018,7 +1034,8 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
                     if (a->poll && a->poll(a->poll_ctx)) { set_error("interrupted"); r = RAER_ERR_INTERRUPT; break; }
                     if (pb.b.n_reads == 0 || pb.b.end <= pb.b.beg) continue;
                     raer_rows rows;
-                    r = gpu_batch(has_ridx ? ridx.find(names[c]) : nullptr, 0, INT_MAX, pb, &rows);
+                    r = gpu_batch(has_ridx ? ridx.find(names[c]) : nullptr, wi.reg_tid() >= 0 ? wi.reg_beg() : 0,
+                                  wi.reg_tid() >= 0 ? wi.reg_end() : INT_MAX, pb, &rows);
                     if (r == RAER_OK) emit_rows(c, rows);
                 }
             }
@@ -1057,7 +1074,7 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             int64_t bases = 0;
             int n_windows = 0;
             double t0b = raer::now_seconds();
-            int r = raer_gi_contig(gi, c, ftid.data(), lens[(size_t)c], &ic, rchr, &n_windows, &d_sites, &bases);
+            int r = raer_gi_contig(gi, c, ftid.data(), lens[(size_t)c], &ic, rchr, gi_reg_beg, gi_reg_end, &n_windows, &d_sites, &bases);
             tm_batch += raer::now_seconds() - t0b;
             if (r == 1) {  // RAER_GI_FALLBACK
                 ++n_fallback;
@@ -1075,8 +1092,8 @@ extern "C" int raer_pileup(const raer_pileup_args* a, raer_pileup_result* out) {
             rc = raer_ctx_set_reference(ctx, c, seq.data(), (int64_t)seq.size());
             tm_fasta += raer::now_seconds() - t0f;
             if (rc) break;
-            bc.reg_beg = 0;
-            bc.reg_end = INT_MAX;
+            bc.reg_beg = gi_reg_beg;
+            bc.reg_end = gi_reg_end;
             bc.site_mask = d_sites;  // device pointer: the bitmap the prefilter used, over the whole contig
             bc.mask_beg = 0;
             bc.mask_bits = lens[(size_t)c];

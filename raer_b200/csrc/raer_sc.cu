@@ -575,8 +575,8 @@ struct raer_gi;
 extern "C" raer_gi* raer_gi_create(int device, int nf, const char* const* paths, const char* const* indexes);
 extern "C" void raer_gi_destroy(raer_gi* g);
 extern "C" int raer_gi_contig(raer_gi* g, int tid, const int* ftid, int contig_len, const raer::IngestConf* ic,
-                              const raer::RegionIndex::Chr* site, int* n_windows, const uint32_t** site_mask_dev,
-                              int64_t* aligned_bases);
+                              const raer::RegionIndex::Chr* site, int reg_beg, int reg_end, int* n_windows,
+                              const uint32_t** site_mask_dev, int64_t* aligned_bases);
 extern "C" int raer_gi_window(raer_gi* g, int j, raer_read_batch* b, int64_t* file_off);
 extern "C" uint32_t raer_gi_umi_space(raer_gi* g);
 
@@ -798,7 +798,7 @@ static int sc_run(const raer_scpileup_args* a, bool want_files, raer_sc_triplets
                     const uint32_t* d_sites = nullptr;
                     const int ftid = (int)ci;
                     int n_windows = 0;
-                    const int r = raer_gi_contig(gh.g, (int)ci, &ftid, lens[ci], &ic, rchr, &n_windows, &d_sites, &bases);
+                    const int r = raer_gi_contig(gh.g, (int)ci, &ftid, lens[ci], &ic, rchr, 0, INT_MAX, &n_windows, &d_sites, &bases);
                     if (r < 0) { rc = r; break; }
                     if (r == 0) {
                         const std::vector<int>* sites = contig_sites(names[ci]);

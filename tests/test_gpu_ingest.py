@@ -376,3 +376,30 @@ def test_position_windows_on_the_golden_files_and_single_cell(ext, tmp_path, mon
     monkeypatch.setenv("RAER_GPU_INGEST", "0")
     host = api.pileup_cells_triplets(ds["bam"], gr, ds["barcodes"], param=fp)
     assert _sc_triplets(dev) == _sc_triplets(host)
+
+
+# ---- coordinate ranges ("contig:beg-end": tiles of a contig cut for several GPUs, user regions)
+@pytest.mark.parametrize("region", ["chr1:1-60000", "chr1:20001-40000", "chr2:35000-60000", "chr1:1-17000", "chr2:52000-60000"])
+def test_coordinate_range_through_the_device_ingest(tmp_path, monkeypatch, region):
+    """the byte range of a coordinate range comes from the linear index (first record that reaches the window the range
+    begins in .. an entry behind its end, verified by looking at the first record behind it); rows equal the host
+    stream's for the same region string"""
+    ds = synth.make_bulk_dataset(str(tmp_path), n_bams=2, n_contigs=2, contig_len=60_000, pairs_per_contig=15_000, seed=29)
+    monkeypatch.setenv("RAER_GI_REGION_MIN", "0")
+    pc = prepare_pileup_call(ds["bams"], ds["fasta"], region=region, param=FilterParam(min_depth=1, library_type="fr-first-strand"))
+    dev, host = _both(pc, monkeypatch)
+    assert dev["timing"]["n_device_contigs"] == 1 and dev["timing"]["n_host_contigs"] == 0
+    assert host["timing"]["n_device_contigs"] == 0
+    _columns_equal(dev, host)
+    assert dev["nrows"] > 100
+    assert dev["timing"]["n_aligned_bases"] == host["timing"]["n_aligned_bases"]
+    monkeypatch.setenv("RAER_GI_WINDOW_BYTES", "20000")
+    monkeypatch.setenv("RAER_GPU_INGEST", "1")
+    _columns_equal(_cabi.pileup(pc), host)
+
+
+def test_narrow_coordinate_ranges_stay_with_the_host_stream(ext, monkeypatch):
+    pc = prepare_pileup_call(ext.bam1, ext.fasta, region="SSR3:203-205")
+    dev, host = _both(pc, monkeypatch)
+    assert dev["timing"]["n_device_contigs"] == 0
+    _columns_equal(dev, host)
